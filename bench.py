@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""Headline benchmark: Shopformer pose windows/sec on N B200s (BASELINE.json `metric`).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--config A|A1|B|C] [--windows 65536] [--precision fp32|bf16]
+
+A *step* is one pass of the scoring hot path (windows -> ST-GCN tokenizer -> transformer ->
+per-window reconstruction-error score) over one batch of synthetic windows per GPU.  At N=1 the
+workload is BASELINE.json configs[1]: 65,536 synthetic COCO-17 windows (T=24), config A
+(`shopformer/` train.py defaults), deterministic synthetic weights.  N>1 is weak scaling: every rank
+scores its own 65,536 windows and the scores are all-gathered over NCCL (the path's only collective).
+
+One JSON line is printed by rank 0:
+  value      windows/s, whole job, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e        the same metric through the C-ABI host-buffer call (`sf_runner_score`: H2D of the poses
+             from pinned memory, kernels, D2H of the scores inside the timed region)
+  roofline   dominant kernel (tokenizer) useful FLOP/s against the measured bf16 tensor peak
+  cpu_baseline  the CPU oracle port on the host cores on a bounded sample of the same workload
+`--impl reference` times the CPU restatement of the reference path (oracle/, torch CPU ops, all host
+threads) -- the reference itself is Python and cannot travel to the GPU box.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+import warnings
+from pathlib import Path
+
+REPO = Path(__file__).resolve().parent
+PKG = REPO / "computer-vision-shoplifting-detection_b200"
+for p in (str(REPO), str(PKG)):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "shopformer_pose_windows_per_sec"
+UNIT = "windows/s"
+
+
+def load_peaks():
+    path = REPO / "MEASURED_PEAKS.json"
+    if path.exists():
+        d = json.load(open(path))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_burst": d["bf16_tflops"], "bf16_sustained": d["bf16_tflops_sustained"],
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback"}
+
+
+def build_model(name: str):
+    """Drop-in facade of config `name` with deterministic synthetic weights (CPU, eval)."""
+    import importlib
+    from shopformer_b200 import configs as CFG
+    from shopformer_b200.synthetic import synth_state_dict
+    which = "shopformer" if CFG.variant_of(name) == 1 else "shopformer_2"
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k.split(".")[0] in ("models", "data", "utils")}
+    sys.path.insert(0, str(PKG / which))
+    try:
+        models = importlib.import_module("models")
+    finally:
+        sys.path.remove(str(PKG / which))
+        for k in list(sys.modules):
+            if k.split(".")[0] in ("models", "data", "utils"):
+                sys.modules.pop(k)
+        sys.modules.update(saved)
+    args = CFG.ctor_args(name)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model = models.Shopformer(**args) if CFG.variant_of(name) == 1 else models.Shopformer(args)
+    model.load_state_dict(synth_state_dict(model.state_dict(), seed=0), strict=True)
+    return model.eval()
+
+
+def oracle_runner(model, name: str):
+    """Closure scoring a float32 CPU tensor with the CPU oracle port (fp32, all host threads)."""
+    import oracle.scoring_oracle as O
+    from shopformer_b200 import configs as CFG
+    enc = model.gcae.encoder
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    kw = dict(variant=CFG.variant_of(name), strides=list(enc.strides), nhead=model.transformer.nhead,
+              pool_tokens=(enc.num_tokens if enc._needs_pooling else None))
+
+    def run(x: torch.Tensor) -> torch.Tensor:
+        with torch.no_grad():
+            return O.score_windows(sd, x, dtype=torch.float32, **kw)["score"]
+    return run
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        busy = [s for s in sm if s > 0]
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(a):
+    """CPU restatement of the reference path, timed on the host cores (rank 0 only)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from shopformer_b200 import configs as CFG
+    from shopformer_b200.synthetic import synth_windows
+    model = build_model(a.config)
+    run = oracle_runner(model, a.config)
+    C, T, V = CFG.input_shape(a.config)
+    sample = a.ref_windows
+    x = torch.from_numpy(synth_windows(sample, T, V, seed=1234)[0])
+    cores = torch.get_num_threads()
+    for _ in range(a.warmup):
+        run(x)
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        run(x)
+    dt = time.perf_counter() - t0
+    v = sample * a.steps / dt
+    line = {"metric": METRIC, "value": v, "unit": UNIT, "impl": "reference", "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"shopformer config {a.config}: {sample}-window sample of the {a.windows}-window batch, "
+                                   f"T={T}, V={V}, CPU oracle port (torch CPU ops), batch {sample}", "windows_per_step": sample},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{sample} windows x {a.steps} steps, fp32, torch {torch.__version__} CPU, {os.cpu_count()} logical cpus"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="A")
+    ap.add_argument("--windows", type=int, default=65536, help="windows per GPU per step")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--ref-windows", type=int, default=4096, help="--impl reference / cpu_baseline sample per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
+    if a.impl == "reference":
+        return run_reference(a)
+
+    from shopformer_b200 import configs as CFG
+    from shopformer_b200.sharding import ShardedScorer
+    from shopformer_b200.synthetic import synth_windows
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device visible; the scoring path has no CPU fallback "
+                         "(use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+
+    model = build_model(a.config)
+    cpu_run = oracle_runner(model, a.config) if rank == 0 else None
+    model = model.to(dev)
+    eng = model._sf_engine()
+    C, T, V = CFG.input_shape(a.config)
+    S, D = eng.token_shape(T)
+    n = a.windows
+    xs = synth_windows(n, T, V, seed=1234 + rank)[0]
+    x = torch.from_numpy(xs).to(dev)
+    sharded = ShardedScorer(eng, n)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step():
+        sharded.score(x, precision=a.precision)
+
+    # ---- parity guard on rank 0: a bench number from wrong scores is worthless
+    if rank == 0:
+        sub = np.random.RandomState(0).choice(n, 256, replace=False)
+        ref = cpu_run(torch.from_numpy(xs[sub])).numpy()
+        got = eng.score_windows(x[torch.from_numpy(sub).to(dev)], precision=a.precision).cpu().numpy()
+        err = float(np.max(np.abs(got - ref) / np.abs(ref)))
+        tol = 1e-3 if a.precision == "fp32" else 1e-2
+        if not err < tol:
+            raise SystemExit(f"bench.py: scores differ from the CPU oracle by {err:.3e} (> {tol}); refusing to report")
+    else:
+        err = None
+
+    # ---- device-resident throughput
+    for _ in range(a.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    # per-kernel timing of the two kernels of the path (same stream, same inputs), K launches each
+    tok = eng.tokenize(x)
+    k0, k1, k2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    torch.cuda.synchronize(dev)
+    k0.record()
+    for _ in range(a.steps):
+        eng.tokenize(x)
+    k1.record()
+    for _ in range(a.steps):
+        eng.reconstruct_tokens(tok)
+    k2.record()
+    torch.cuda.synchronize(dev)
+    tok_ms, xf_ms = k0.elapsed_time(k1) / a.steps, k1.elapsed_time(k2) / a.steps
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * n * a.steps / (ms * 1e-3)
+
+    # ---- end to end through the C-ABI host-buffer call (pinned staging inside the runner)
+    chunk = 8192
+    eng.score_host(xs[:chunk * 2], precision=a.precision, chunk=chunk)      # allocate runner, warm up
+    barrier()
+    e2e_steps = max(3, min(a.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        host_scores = eng.score_host(xs, precision=a.precision, chunk=chunk)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * e2e_steps / float(t.item())
+    h2d = int(xs.nbytes)
+    d2h = int(host_scores.nbytes)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (tokenizer): useful FLOPs per launch / its duration
+    tok_flops = {"A": 7_042_080, "A1": 26_988_384, "B": 7_729_344, "C": 17_057_120}.get(a.config)
+    dom = "tokenizer" if tok_ms >= xf_ms else "transformer"
+    path_flops = CFG.USEFUL_FLOPS.get(a.config)
+    if tok_flops is not None:
+        dom_flops = tok_flops if dom == "tokenizer" else path_flops - tok_flops
+        achieved = dom_flops * n / ((tok_ms if dom == "tokenizer" else xf_ms) * 1e-3) / 1e12
+        peak = peaks["bf16_sustained"]
+        roofline = {"bound": "tensor", "kernel": f"{dom}_{a.precision}", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": f"{peaks['source']} bf16 sustained (MEASURED_PEAKS.json)",
+                    "flops_per_window": dom_flops, "kernel_ms": {"tokenizer": tok_ms, "transformer": xf_ms},
+                    "path_frac": path_flops * n / ((tok_ms + xf_ms) * 1e-3) / 1e12 / peak,
+                    "note": "fp32 path runs on the FFMA pipe, not the tensor pipe; frac is vs the bf16 tensor peak"
+                            if a.precision == "fp32" else ""}
+    else:
+        roofline = None
+
+    # ---- CPU baseline: the oracle port on this box's host cores, bounded sample
+    cpu = None
+    if world == 1 and not a.no_cpu_baseline:
+        sample = min(a.ref_windows, n)
+        xc = torch.from_numpy(xs[:sample])
+        cpu_run(xc)
+        reps, t0 = 0, time.perf_counter()
+        while reps < 3 or (time.perf_counter() - t0 < 10.0 and reps < 200):
+            cpu_run(xc)
+            reps += 1
+        dt = time.perf_counter() - t0
+        cpu = {"value": sample * reps / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"{sample} windows x {reps} passes of the CPU oracle (torch {torch.__version__} CPU fp32), "
+                         f"{os.cpu_count()} logical cpus"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if a.precision == "fp32" else "bf16", "data": "synthetic",
+        "config": {"workload": f"shopformer config {a.config} (BASELINE configs[1]): {n} synthetic COCO-17 windows per GPU, "
+                               f"T={T}, V={V}, S={S}, d={D}, deterministic synthetic weights",
+                   "windows_per_gpu_per_step": n, "precision": a.precision,
+                   "l2": f"inputs larger than L2 ({xs.nbytes / 1e6:.0f} MB of windows per step vs 126 MB L2)",
+                   "collective": "NCCL all-gather of fp32 scores" if world > 1 else "none (1 GPU)"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "sf_runner_score (C ABI, host buffers, 8192-window chunks, 2 streams)", "steps": e2e_steps},
+        "gpu_launches": 2 * a.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "parity": {"max_rel_err_vs_cpu_oracle": err, "checked_windows": 256},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

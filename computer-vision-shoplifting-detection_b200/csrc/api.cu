@@ -1,0 +1,180 @@
+// C-ABI entry points of the scoring hot path + the host-buffer runner.
+#include <algorithm>
+#include <cstring>
+
+#include "sf_internal.h"
+
+using namespace sf;
+
+namespace {
+inline int64_t align256(int64_t x) { return (x + 255) & ~int64_t(255); }
+
+int check_T(const sf_model* m, int T) {
+  SF_REQUIRE(m, SF_E_INVALID, "null model");
+  SF_REQUIRE(T >= 1 && T <= 4096, SF_E_INVALID, "T=%d outside [1,4096]", T);
+  return SF_OK;
+}
+}  // namespace
+
+extern "C" int64_t sf_workspace_bytes(const sf_model* m, int64_t B, int32_t T) {
+  if (!m || B < 0 || T < 1) return SF_E_INVALID;
+  const int S = token_len(m, T);
+  // tokens staged between the two kernels when the caller does not ask for them
+  return align256(B * (int64_t)S * m->xf.d_tok * (int64_t)sizeof(float)) + align256(tokenizer_fp32_workspace(m, B, T));
+}
+
+extern "C" int sf_tokenize(const sf_model* m, const float* poses_dev, int64_t B, int32_t T, float* tokens_dev,
+                           void* workspace_dev, int64_t workspace_bytes, void* stream) {
+  int rc = check_T(m, T);
+  if (rc) return rc;
+  SF_REQUIRE(B >= 0 && (B == 0 || (poses_dev && tokens_dev)), SF_E_INVALID, "sf_tokenize: null buffer");
+  return launch_tokenizer_fp32(m, poses_dev, B, T, tokens_dev, workspace_dev, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int sf_reconstruct_tokens(const sf_model* m, const float* tokens_dev, int64_t B, int32_t S, float* recon_dev,
+                                     void* workspace_dev, int64_t workspace_bytes, void* stream) {
+  (void)workspace_dev;
+  (void)workspace_bytes;
+  SF_REQUIRE(m, SF_E_INVALID, "null model");
+  SF_REQUIRE(B >= 0 && (B == 0 || (tokens_dev && recon_dev)), SF_E_INVALID, "sf_reconstruct_tokens: null buffer");
+  return launch_transformer_fp32(m, tokens_dev, B, S, SF_REDUCE_MEAN, recon_dev, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int sf_normality_score(const sf_model* m, const float* tokens_dev, const float* recon_dev, int64_t B, int32_t S,
+                                  int32_t reduction, float* scores_dev, void* stream) {
+  SF_REQUIRE(m, SF_E_INVALID, "null model");
+  SF_REQUIRE(B >= 0 && (B == 0 || (tokens_dev && recon_dev && scores_dev)), SF_E_INVALID, "sf_normality_score: null buffer");
+  SF_REQUIRE(S >= 1 && S <= 100, SF_E_INVALID, "S=%d outside [1,100]", S);
+  return launch_score(m, tokens_dev, recon_dev, B, S, reduction, scores_dev, (cudaStream_t)stream);
+}
+
+extern "C" int sf_score_windows(const sf_model* m, const float* poses_dev, int64_t B, int32_t T, int32_t reduction,
+                                int32_t precision, float* scores_dev, float* tokens_dev, float* recon_dev,
+                                void* workspace_dev, int64_t workspace_bytes, void* stream) {
+  int rc = check_T(m, T);
+  if (rc) return rc;
+  SF_REQUIRE(B >= 0 && (B == 0 || (poses_dev && scores_dev)), SF_E_INVALID, "sf_score_windows: null buffer");
+  SF_REQUIRE(precision == SF_PREC_FP32 || precision == SF_PREC_BF16, SF_E_INVALID, "unknown precision %d", precision);
+  SF_REQUIRE(precision == SF_PREC_FP32, SF_E_UNSUPPORTED, "bf16 tensor-core path is not built into this library version");
+  if (B == 0) return SF_OK;
+  const int S = token_len(m, T);
+  const int64_t tok_bytes = align256(B * (int64_t)S * m->xf.d_tok * (int64_t)sizeof(float));
+  float* tok = tokens_dev;
+  char* ws = (char*)workspace_dev;
+  int64_t ws_left = workspace_bytes;
+  if (!tok) {
+    SF_REQUIRE(ws && ws_left >= tok_bytes, SF_E_INVALID, "sf_score_windows: workspace too small (%lld < %lld)",
+               (long long)workspace_bytes, (long long)sf_workspace_bytes(m, B, T));
+    tok = (float*)ws;
+    ws += tok_bytes;
+    ws_left -= tok_bytes;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = launch_tokenizer_fp32(m, poses_dev, B, T, tok, ws, ws_left, st);
+  if (rc) return rc;
+  return launch_transformer_fp32(m, tok, B, S, reduction, recon_dev, scores_dev, st);
+}
+
+// ------------------------------------------------------------------------------------ runner
+struct sf_runner {
+  const sf_model* m;
+  int T, S;
+  int64_t chunk;
+  size_t pose_elems;              // floats per window
+  cudaStream_t st[2];
+  cudaEvent_t done[2];
+  float* pin_in[2];
+  float* pin_out[2];
+  float* dev_in[2];
+  float* dev_out[2];
+  void* ws[2];
+  int64_t ws_bytes;
+};
+
+extern "C" int sf_runner_create(const sf_model* m, int32_t T, int64_t max_chunk, sf_runner** out) {
+  int rc = check_T(m, T);
+  if (rc) return rc;
+  SF_REQUIRE(out && max_chunk >= 1, SF_E_INVALID, "sf_runner_create: bad argument");
+  SF_CUDA_OK(cudaSetDevice(m->device));
+  sf_runner* r = new sf_runner();
+  memset(r, 0, sizeof(*r));
+  r->m = m;
+  r->T = T;
+  r->S = token_len(m, T);
+  r->chunk = max_chunk;
+  r->pose_elems = (size_t)m->cfg.in_channels * T * m->cfg.num_keypoints;
+  r->ws_bytes = sf_workspace_bytes(m, max_chunk, T);
+  cudaError_t e = cudaSuccess;
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+    e = cudaStreamCreateWithFlags(&r->st[i], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r->done[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&r->pin_in[i], r->pose_elems * max_chunk * sizeof(float));
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&r->pin_out[i], max_chunk * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&r->dev_in[i], r->pose_elems * max_chunk * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&r->dev_out[i], max_chunk * sizeof(float));
+    if (e == cudaSuccess && r->ws_bytes > 0) e = cudaMalloc(&r->ws[i], r->ws_bytes);
+  }
+  if (e != cudaSuccess) {
+    set_error("sf_runner_create: %s", cudaGetErrorString(e));
+    sf_runner_destroy(r);
+    return SF_E_CUDA;
+  }
+  *out = r;
+  return SF_OK;
+}
+
+extern "C" void sf_runner_destroy(sf_runner* r) {
+  if (!r) return;
+  cudaSetDevice(r->m->device);
+  for (int i = 0; i < 2; ++i) {
+    if (r->st[i]) cudaStreamSynchronize(r->st[i]);
+    if (r->pin_in[i]) cudaFreeHost(r->pin_in[i]);
+    if (r->pin_out[i]) cudaFreeHost(r->pin_out[i]);
+    if (r->dev_in[i]) cudaFree(r->dev_in[i]);
+    if (r->dev_out[i]) cudaFree(r->dev_out[i]);
+    if (r->ws[i]) cudaFree(r->ws[i]);
+    if (r->done[i]) cudaEventDestroy(r->done[i]);
+    if (r->st[i]) cudaStreamDestroy(r->st[i]);
+  }
+  delete r;
+}
+
+extern "C" float* sf_runner_pinned_poses(sf_runner* r, int32_t slot) {
+  if (!r || slot < 0 || slot > 1) return nullptr;
+  return r->pin_in[slot];
+}
+
+// Chunked, double-buffered: while chunk i computes on stream i%2, chunk i+1 is being
+// copied into pinned memory and uploaded on the other stream.
+extern "C" int sf_runner_score(sf_runner* r, const float* poses_host, int64_t B, int32_t precision, float* scores_host) {
+  SF_REQUIRE(r && (B == 0 || (poses_host && scores_host)), SF_E_INVALID, "sf_runner_score: null argument");
+  SF_CUDA_OK(cudaSetDevice(r->m->device));
+  const int64_t n_chunks = (B + r->chunk - 1) / r->chunk;
+  int64_t pending_off[2] = {-1, -1}, pending_n[2] = {0, 0};
+  for (int64_t c = 0; c < n_chunks; ++c) {
+    const int s = (int)(c & 1);
+    const int64_t off = c * r->chunk, n = std::min(r->chunk, B - off);
+    if (pending_off[s] >= 0) {                       // drain the slot before reusing its buffers
+      SF_CUDA_OK(cudaEventSynchronize(r->done[s]));
+      memcpy(scores_host + pending_off[s], r->pin_out[s], pending_n[s] * sizeof(float));
+      pending_off[s] = -1;
+    }
+    const float* src = poses_host + (size_t)off * r->pose_elems;
+    const bool direct = (src == r->pin_in[s]);       // producer wrote straight into our pinned slot
+    if (!direct) memcpy(r->pin_in[s], src, (size_t)n * r->pose_elems * sizeof(float));
+    SF_CUDA_OK(cudaMemcpyAsync(r->dev_in[s], r->pin_in[s], (size_t)n * r->pose_elems * sizeof(float), cudaMemcpyHostToDevice, r->st[s]));
+    int rc = sf_score_windows(r->m, r->dev_in[s], n, r->T, SF_REDUCE_MEAN, precision, r->dev_out[s], nullptr, nullptr,
+                              r->ws[s], r->ws_bytes, r->st[s]);
+    if (rc) return rc;
+    SF_CUDA_OK(cudaMemcpyAsync(r->pin_out[s], r->dev_out[s], (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, r->st[s]));
+    SF_CUDA_OK(cudaEventRecord(r->done[s], r->st[s]));
+    pending_off[s] = off;
+    pending_n[s] = n;
+  }
+  for (int s = 0; s < 2; ++s)
+    if (pending_off[s] >= 0) {
+      SF_CUDA_OK(cudaEventSynchronize(r->done[s]));
+      memcpy(scores_host + pending_off[s], r->pin_out[s], pending_n[s] * sizeof(float));
+    }
+  return SF_OK;
+}

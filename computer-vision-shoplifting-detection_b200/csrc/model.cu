@@ -1,0 +1,423 @@
+// sf_model_create: validate the state dict against the config, fold every eval-mode
+// BatchNorm into its neighbour, transpose the linears for coalesced reads and upload one
+// immutable arena.  Reference for the folded maths: SURVEY Appendix A.1-A.3
+// (shopformer/models/gcae.py:242-259,331-366; shopformer/models/transformer.py:60-196,304-329;
+//  shopformer_2/models/transformer.py:105-194).
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "sf_internal.h"
+
+namespace sf {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+namespace {
+
+constexpr double kBnEps = 1e-5;
+
+struct HostTensor {
+  const float* p;
+  int64_t n;
+};
+
+struct Packer {
+  std::map<std::string, HostTensor> sd;
+  std::vector<float> arena;      // staged host copy, 64-float (256 B) aligned sections
+  std::vector<int> iarena_dummy;
+  int err = SF_OK;
+
+  const float* get(const std::string& key, int64_t want) {
+    auto it = sd.find(key);
+    if (it == sd.end()) {
+      if (err == SF_OK) {
+        set_error("state dict is missing '%s'", key.c_str());
+        err = SF_E_MISSING;
+      }
+      return nullptr;
+    }
+    if (it->second.n != want) {
+      if (err == SF_OK) {
+        set_error("'%s' has %lld elements, config implies %lld", key.c_str(), (long long)it->second.n,
+                  (long long)want);
+        err = SF_E_SHAPE;
+      }
+      return nullptr;
+    }
+    return it->second.p;
+  }
+  bool has(const std::string& key) const { return sd.count(key) != 0; }
+
+  // reserve n floats, returns offset (in floats)
+  size_t alloc(size_t n) {
+    size_t off = (arena.size() + 63) & ~size_t(63);
+    arena.resize(off + n, 0.f);
+    return off;
+  }
+};
+
+// BatchNorm (eval) -> per-channel scale/shift in double
+static void bn_fold(Packer& pk, const std::string& p, int n, std::vector<double>& scale,
+                    std::vector<double>& shift) {
+  const float* w = pk.get(p + "weight", n);
+  const float* b = pk.get(p + "bias", n);
+  const float* rm = pk.get(p + "running_mean", n);
+  const float* rv = pk.get(p + "running_var", n);
+  scale.assign(n, 1.0);
+  shift.assign(n, 0.0);
+  if (!w || !b || !rm || !rv) return;
+  for (int i = 0; i < n; ++i) {
+    double s = (double)w[i] / std::sqrt((double)rv[i] + kBnEps);
+    scale[i] = s;
+    shift[i] = (double)b[i] - (double)rm[i] * s;
+  }
+}
+
+struct LinOff {
+  size_t wt, b;
+  int K, N;
+};
+
+// nn.Linear weight (N,K) row-major -> [K][N]
+static LinOff pack_linear(Packer& pk, const std::string& wkey, const std::string& bkey, int K, int N) {
+  LinOff o{0, 0, K, N};
+  const float* w = pk.get(wkey, (int64_t)K * N);
+  const float* b = pk.get(bkey, N);
+  o.wt = pk.alloc((size_t)K * N);
+  o.b = pk.alloc(N);
+  if (!w || !b) return o;
+  for (int n = 0; n < N; ++n)
+    for (int k = 0; k < K; ++k) pk.arena[o.wt + (size_t)k * N + n] = w[(size_t)n * K + k];
+  memcpy(&pk.arena[o.b], b, sizeof(float) * N);
+  return o;
+}
+
+struct NormOff {
+  size_t g, b;
+};
+static NormOff pack_norm(Packer& pk, const std::string& p, int d) {
+  NormOff o{pk.alloc(d), 0};
+  o.b = pk.alloc(d);
+  const float* g = pk.get(p + "weight", d);
+  const float* b = pk.get(p + "bias", d);
+  if (g && b) {
+    memcpy(&pk.arena[o.g], g, sizeof(float) * d);
+    memcpy(&pk.arena[o.b], b, sizeof(float) * d);
+  }
+  return o;
+}
+
+struct AttnOff {
+  LinOff qkv, out;
+};
+static AttnOff pack_attn(Packer& pk, const std::string& p, int d) {
+  AttnOff a;
+  a.qkv = pack_linear(pk, p + "in_proj_weight", p + "in_proj_bias", d, 3 * d);
+  a.out = pack_linear(pk, p + "out_proj.weight", p + "out_proj.bias", d, d);
+  return a;
+}
+
+}  // namespace
+}  // namespace sf
+
+using namespace sf;
+
+extern "C" int sf_abi_version(void) { return SF_ABI_VERSION; }
+extern "C" const char* sf_last_error(void) { return sf::last_error(); }
+
+extern "C" int sf_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    set_error("no CUDA device visible (%s); this library has no CPU fallback",
+              e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    return SF_E_NODEVICE;
+  }
+  int ok = 0;
+  for (int i = 0; i < n; ++i) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ++ok;
+  }
+  if (!ok) {
+    set_error("no sm_100 device among %d CUDA devices; kernels are built for sm_100a only", n);
+    return SF_E_NODEVICE;
+  }
+  return ok;
+}
+
+extern "C" int sf_model_create(const sf_config* cfg, int32_t n_tensors, const char* const* names,
+                               const float* const* data_host, const int64_t* numel, int32_t device,
+                               sf_model** out) {
+  SF_REQUIRE(cfg && names && data_host && numel && out, SF_E_INVALID, "sf_model_create: null argument");
+  *out = nullptr;
+  SF_REQUIRE(cfg->variant == SF_VARIANT_SHOPFORMER || cfg->variant == SF_VARIANT_SHOPFORMER_2, SF_E_INVALID,
+             "unknown variant %d", cfg->variant);
+  const int V = cfg->num_keypoints, nb = cfg->n_blocks, d = cfg->d_model, H = cfg->n_heads;
+  SF_REQUIRE(V >= 1 && V <= kMaxV, SF_E_UNSUPPORTED, "num_keypoints=%d outside [1,%d]", V, kMaxV);
+  SF_REQUIRE(nb >= 1 && nb <= kMaxBlocks, SF_E_UNSUPPORTED, "n_blocks=%d outside [1,%d]", nb, kMaxBlocks);
+  SF_REQUIRE(cfg->n_enc_layers >= 1 && cfg->n_enc_layers <= kMaxLayers && cfg->n_dec_layers >= 1 &&
+                 cfg->n_dec_layers <= kMaxLayers,
+             SF_E_UNSUPPORTED, "transformer depth %d+%d outside [1,%d]", cfg->n_enc_layers, cfg->n_dec_layers,
+             kMaxLayers);
+  SF_REQUIRE(cfg->channels[0] == cfg->in_channels && cfg->in_channels >= 1, SF_E_INVALID,
+             "channels[0] must equal in_channels");
+  for (int i = 0; i < nb; ++i) {
+    SF_REQUIRE(cfg->channels[i + 1] >= 1 && cfg->channels[i + 1] % 4 == 0, SF_E_UNSUPPORTED,
+               "block %d: out channels %d must be a positive multiple of 4", i, cfg->channels[i + 1]);
+    SF_REQUIRE(cfg->strides[i] >= 1 && cfg->strides[i] <= 8, SF_E_UNSUPPORTED, "block %d: stride %d outside [1,8]",
+               i, cfg->strides[i]);
+  }
+  const int d_tok = cfg->channels[nb] * V;
+  SF_REQUIRE(d >= 4 && d % 4 == 0 && H >= 1 && d % H == 0, SF_E_UNSUPPORTED,
+             "d_model=%d must be a multiple of 4 and of n_heads=%d", d, H);
+  SF_REQUIRE(cfg->d_ff >= 4 && cfg->d_ff % 4 == 0, SF_E_UNSUPPORTED, "d_ff=%d must be a multiple of 4", cfg->d_ff);
+  SF_REQUIRE(d_tok % 4 == 0, SF_E_UNSUPPORTED, "token width %d must be a multiple of 4", d_tok);
+  if (cfg->variant == SF_VARIANT_SHOPFORMER)
+    SF_REQUIRE(d == d_tok, SF_E_INVALID, "variant 1 needs d_model == latent*V (%d vs %d)", d, d_tok);
+
+  int rc = sf_device_count();
+  if (rc < 0) return rc;
+  SF_CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  SF_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  SF_REQUIRE(prop.major == 10, SF_E_NODEVICE, "device %d is sm_%d%d; this build targets sm_100a only", device,
+             prop.major, prop.minor);
+
+  Packer pk;
+  for (int i = 0; i < n_tensors; ++i) pk.sd[names[i]] = HostTensor{data_host[i], numel[i]};
+
+  // ------------------------------------------------------------- tokenizer
+  const std::string enc = "gcae.encoder.";
+  const int c0 = cfg->in_channels;
+  size_t off_in_scale = pk.alloc((size_t)c0 * V), off_in_shift = pk.alloc((size_t)c0 * V);
+  {
+    std::vector<double> s, t;
+    bn_fold(pk, enc + "bn_input.", c0 * V, s, t);
+    for (int i = 0; i < c0 * V; ++i) {
+      pk.arena[off_in_scale + i] = (float)s[i];
+      pk.arena[off_in_shift + i] = (float)t[i];
+    }
+  }
+  struct BlkOff {
+    size_t gw, gb, tw, rw, ob, ev, ec;
+    int ellw, identity;
+  } bo[kMaxBlocks];
+  std::vector<std::vector<int>> ell_cols(nb);
+  for (int i = 0; i < nb; ++i) {
+    const int ci = cfg->channels[i], co = cfg->channels[i + 1];
+    const std::string p = enc + "layers." + std::to_string(i) + ".";
+    BlkOff& b = bo[i];
+    // gcn
+    b.gw = pk.alloc((size_t)ci * co);
+    b.gb = pk.alloc(co);
+    if (const float* w = pk.get(p + "gcn.weight", (int64_t)ci * co)) memcpy(&pk.arena[b.gw], w, sizeof(float) * ci * co);
+    if (const float* w = pk.get(p + "gcn.bias", co)) memcpy(&pk.arena[b.gb], w, sizeof(float) * co);
+    // adjacency -> ELL (exactly the non-zeros of the checkpoint's buffer)
+    const float* adj = pk.get(p + "gcn.adj", (int64_t)V * V);
+    int width = 1;
+    if (adj)
+      for (int v = 0; v < V; ++v) {
+        int nnz = 0;
+        for (int u = 0; u < V; ++u) nnz += adj[v * V + u] != 0.f;
+        width = nnz > width ? nnz : width;
+      }
+    b.ellw = width;
+    b.ev = pk.alloc((size_t)V * width);
+    b.ec = pk.alloc((size_t)V * width);   // ints stored in the float arena (bit pattern)
+    if (adj)
+      for (int v = 0; v < V; ++v) {
+        int j = 0;
+        for (int u = 0; u < V; ++u)
+          if (adj[v * V + u] != 0.f) {
+            pk.arena[b.ev + (size_t)v * width + j] = adj[v * V + u];
+            int col = u;
+            memcpy(&pk.arena[b.ec + (size_t)v * width + j], &col, 4);
+            ++j;
+          }
+        for (; j < width; ++j) {
+          int col = v;
+          pk.arena[b.ev + (size_t)v * width + j] = 0.f;
+          memcpy(&pk.arena[b.ec + (size_t)v * width + j], &col, 4);
+        }
+      }
+    // temporal conv (co,co,9,1) + BN2d -> [c][k][o] * scale[o]
+    std::vector<double> ts, tt;
+    bn_fold(pk, p + "tcn.bn.", co, ts, tt);
+    b.tw = pk.alloc((size_t)co * kTaps * co);
+    b.ob = pk.alloc(co);
+    const float* tw = pk.get(p + "tcn.conv.weight", (int64_t)co * co * kTaps);
+    const float* tb = pk.get(p + "tcn.conv.bias", co);
+    if (tw && tb)
+      for (int o = 0; o < co; ++o) {
+        for (int c = 0; c < co; ++c)
+          for (int k = 0; k < kTaps; ++k)
+            pk.arena[b.tw + ((size_t)c * kTaps + k) * co + o] = (float)((double)tw[((size_t)o * co + c) * kTaps + k] * ts[o]);
+        pk.arena[b.ob + o] = (float)((double)tb[o] * ts[o] + tt[o]);
+      }
+    // residual: identity iff no conv in the state dict (gcae.py:234-240)
+    b.identity = !pk.has(p + "residual.0.weight");
+    b.rw = 0;
+    if (b.identity) {
+      SF_REQUIRE(ci == co && cfg->strides[i] == 1, SF_E_MISSING,
+                 "block %d has no residual conv in the state dict but cin!=cout or stride!=1", i);
+    } else {
+      std::vector<double> rs, rt;
+      bn_fold(pk, p + "residual.1.", co, rs, rt);
+      b.rw = pk.alloc((size_t)ci * co);
+      const float* rw = pk.get(p + "residual.0.weight", (int64_t)co * ci);
+      const float* rb = pk.get(p + "residual.0.bias", co);
+      if (rw && rb)
+        for (int o = 0; o < co; ++o) {
+          for (int c = 0; c < ci; ++c) pk.arena[b.rw + (size_t)c * co + o] = (float)((double)rw[(size_t)o * ci + c] * rs[o]);
+          pk.arena[b.ob + o] = (float)((double)pk.arena[b.ob + o] + (double)rb[o] * rs[o] + rt[o]);
+        }
+    }
+  }
+
+  // ------------------------------------------------------------- transformer
+  const std::string tp = "transformer.";
+  const bool v1 = cfg->variant == SF_VARIANT_SHOPFORMER;
+  const int pe_rows = 100;
+  size_t off_pe = pk.alloc((size_t)pe_rows * d), off_pe_score = 0;
+  if (const float* pe = pk.get(tp + "pos_encoder.pe", (int64_t)pe_rows * d)) memcpy(&pk.arena[off_pe], pe, sizeof(float) * pe_rows * d);
+  if (v1) {
+    off_pe_score = pk.alloc((size_t)pe_rows * d_tok);
+    if (const float* pe = pk.get("pos_encoder.pe", (int64_t)pe_rows * d_tok))
+      memcpy(&pk.arena[off_pe_score], pe, sizeof(float) * pe_rows * d_tok);
+  }
+  const bool io_proj = !v1 && pk.has(tp + "input_projection.weight");
+  if (!v1 && !io_proj)
+    SF_REQUIRE(d == d_tok, SF_E_MISSING, "variant 2 without input_projection needs d_model == latent*V (%d vs %d)", d, d_tok);
+  LinOff in_proj{}, out_proj{};
+  if (io_proj) {
+    in_proj = pack_linear(pk, tp + "input_projection.weight", tp + "input_projection.bias", d_tok, d);
+    out_proj = pack_linear(pk, tp + "output_projection.weight", tp + "output_projection.bias", d, d_tok);
+  } else if (v1) {
+    out_proj = pack_linear(pk, tp + "output_proj.weight", tp + "output_proj.bias", d, d);
+  }
+  struct EncOff { AttnOff sa; LinOff f1, f2; NormOff n1, n2; } eo[kMaxLayers];
+  struct DecOff { AttnOff sa, ca; LinOff f1, f2; NormOff n1, n2, n3; } dof[kMaxLayers];
+  const std::string encp = v1 ? tp + "encoder_layers." : tp + "encoder.layers.";
+  const std::string decp = v1 ? tp + "decoder_layers." : tp + "decoder.layers.";
+  for (int i = 0; i < cfg->n_enc_layers; ++i) {
+    const std::string p = encp + std::to_string(i) + ".";
+    eo[i].sa = pack_attn(pk, p + "self_attn.", d);
+    eo[i].f1 = pack_linear(pk, p + "linear1.weight", p + "linear1.bias", d, cfg->d_ff);
+    eo[i].f2 = pack_linear(pk, p + "linear2.weight", p + "linear2.bias", cfg->d_ff, d);
+    eo[i].n1 = pack_norm(pk, p + "norm1.", d);
+    eo[i].n2 = pack_norm(pk, p + "norm2.", d);
+  }
+  for (int i = 0; i < cfg->n_dec_layers; ++i) {
+    const std::string p = decp + std::to_string(i) + ".";
+    dof[i].sa = pack_attn(pk, p + "self_attn.", d);
+    dof[i].ca = pack_attn(pk, p + "multihead_attn.", d);
+    dof[i].f1 = pack_linear(pk, p + "linear1.weight", p + "linear1.bias", d, cfg->d_ff);
+    dof[i].f2 = pack_linear(pk, p + "linear2.weight", p + "linear2.bias", cfg->d_ff, d);
+    dof[i].n1 = pack_norm(pk, p + "norm1.", d);
+    dof[i].n2 = pack_norm(pk, p + "norm2.", d);
+    dof[i].n3 = pack_norm(pk, p + "norm3.", d);
+  }
+  NormOff enc_norm{}, dec_norm{};
+  if (!v1) {
+    enc_norm = pack_norm(pk, tp + "encoder.norm.", d);
+    dec_norm = pack_norm(pk, tp + "decoder.norm.", d);
+  }
+  if (pk.err != SF_OK) return pk.err;
+
+  // ------------------------------------------------------------- upload + pointer fix-up
+  sf_model* m = new sf_model();
+  m->cfg = *cfg;
+  m->device = device;
+  m->sm_count = prop.multiProcessorCount;
+  m->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  m->arena_bytes = pk.arena.size() * sizeof(float);
+  cudaError_t e = cudaMalloc((void**)&m->arena, m->arena_bytes);
+  if (e == cudaSuccess) e = cudaMemcpy(m->arena, pk.arena.data(), m->arena_bytes, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    set_error("uploading %zu bytes of packed weights failed: %s", m->arena_bytes, cudaGetErrorString(e));
+    if (m->arena) cudaFree(m->arena);
+    delete m;
+    return SF_E_CUDA;
+  }
+  const float* A = m->arena;
+  auto lin = [&](const LinOff& o) { return Linear{A + o.wt, A + o.b, o.K, o.N}; };
+  auto nrm = [&](const NormOff& o) { return Norm{A + o.g, A + o.b}; };
+  auto att = [&](const AttnOff& o) { return Attn{lin(o.qkv), lin(o.out)}; };
+
+  Tokenizer& T = m->tok;
+  T.n_blocks = nb;
+  T.V = V;
+  T.c_in = c0;
+  T.pool_tokens = cfg->pool_tokens;
+  T.in_scale = A + off_in_scale;
+  T.in_shift = A + off_in_shift;
+  for (int i = 0; i < nb; ++i) {
+    TokBlock& b = T.blk[i];
+    b.cin = cfg->channels[i];
+    b.cout = cfg->channels[i + 1];
+    b.stride = cfg->strides[i];
+    b.identity_res = bo[i].identity;
+    b.ell_width = bo[i].ellw;
+    b.gcn_w = A + bo[i].gw;
+    b.gcn_b = A + bo[i].gb;
+    b.tcn_w = A + bo[i].tw;
+    b.res_w = bo[i].identity ? nullptr : A + bo[i].rw;
+    b.out_b = A + bo[i].ob;
+    b.ell_val = A + bo[i].ev;
+    b.ell_col = reinterpret_cast<const int*>(A + bo[i].ec);
+  }
+  Transformer& X = m->xf;
+  X.variant = cfg->variant;
+  X.d_tok = d_tok;
+  X.d_model = d;
+  X.heads = H;
+  X.n_enc = cfg->n_enc_layers;
+  X.n_dec = cfg->n_dec_layers;
+  X.d_ff = cfg->d_ff;
+  X.has_io_proj = io_proj;
+  X.pe = A + off_pe;
+  X.pe_score = v1 ? A + off_pe_score : nullptr;
+  X.in_proj = io_proj ? lin(in_proj) : Linear{nullptr, nullptr, 0, 0};
+  X.out_proj = (io_proj || v1) ? lin(out_proj) : Linear{nullptr, nullptr, 0, 0};
+  X.enc_norm = v1 ? Norm{nullptr, nullptr} : nrm(enc_norm);
+  X.dec_norm = v1 ? Norm{nullptr, nullptr} : nrm(dec_norm);
+  for (int i = 0; i < X.n_enc; ++i) X.enc[i] = EncLayer{att(eo[i].sa), lin(eo[i].f1), lin(eo[i].f2), nrm(eo[i].n1), nrm(eo[i].n2)};
+  for (int i = 0; i < X.n_dec; ++i)
+    X.dec[i] = DecLayer{att(dof[i].sa), att(dof[i].ca), lin(dof[i].f1), lin(dof[i].f2), nrm(dof[i].n1), nrm(dof[i].n2), nrm(dof[i].n3)};
+  *out = m;
+  return SF_OK;
+}
+
+extern "C" void sf_model_destroy(sf_model* m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  if (m->arena) cudaFree(m->arena);
+  delete m;
+}
+
+int sf::token_len(const sf_model* m, int T) {
+  int t = T;
+  for (int i = 0; i < m->cfg.n_blocks; ++i) t = (t - 1) / m->cfg.strides[i] + 1;
+  if (m->cfg.pool_tokens > 0) t = m->cfg.pool_tokens;
+  return t;
+}
+
+extern "C" int sf_model_token_shape(const sf_model* m, int32_t T, int32_t* S, int32_t* D) {
+  SF_REQUIRE(m && T >= 1, SF_E_INVALID, "sf_model_token_shape: bad argument");
+  if (S) *S = sf::token_len(m, T);
+  if (D) *D = m->xf.d_tok;
+  return SF_OK;
+}

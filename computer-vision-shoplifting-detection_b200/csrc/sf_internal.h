@@ -1,0 +1,117 @@
+// Internal structures shared by the translation units of libshopformer_b200.so.
+// Nothing here is part of the C ABI (see include/shopformer_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "shopformer_b200.h"
+
+namespace sf {
+
+constexpr int kMaxBlocks = SF_MAX_BLOCKS;
+constexpr int kMaxLayers = 6;     // encoder / decoder depth supported by the by-value kernel params
+constexpr int kMaxV = 32;         // keypoints live on the lanes of one warp
+constexpr int kTaps = 9;          // temporal kernel size of the reference (gcae.py:223)
+constexpr int kHalo = 4;          // its padding
+
+// ---- error plumbing -----------------------------------------------------------------
+void set_error(const char* fmt, ...);
+#define SF_CUDA_OK(expr)                                                                    \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      ::sf::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return SF_E_CUDA;                                                                     \
+    }                                                                                       \
+  } while (0)
+#define SF_REQUIRE(cond, code, ...)  \
+  do {                               \
+    if (!(cond)) {                   \
+      ::sf::set_error(__VA_ARGS__);  \
+      return (code);                 \
+    }                                \
+  } while (0)
+
+// ---- tokenizer (device view; all pointers into one HBM arena) ------------------------
+struct TokBlock {
+  int cin, cout, stride, identity_res;
+  int ell_width;            // entries per row of the ELL adjacency
+  const float* gcn_w;       // [cin][cout]
+  const float* gcn_b;       // [cout]
+  const float* tcn_w;       // [cout(in)][9][cout(out)]   BatchNorm scale folded in
+  const float* res_w;       // [cin][cout] BN-folded 1x1 residual conv, nullptr if identity
+  const float* out_b;       // [cout] folded tcn bias (+ folded residual bias)
+  const float* ell_val;     // [V][ell_width]  normalised adjacency, row-compressed
+  const int* ell_col;       // [V][ell_width]
+};
+
+struct Tokenizer {
+  int n_blocks, V, c_in, pool_tokens;
+  const float* in_scale;    // [c_in*V]  BatchNorm1d folded to scale/shift, index c*V+v
+  const float* in_shift;
+  TokBlock blk[kMaxBlocks];
+};
+
+// ---- transformer ----------------------------------------------------------------------
+struct Linear {
+  const float* wt;          // [K][N]  (transposed nn.Linear weight: n contiguous)
+  const float* b;           // [N]
+  int K, N;
+};
+struct Norm {
+  const float* g;
+  const float* b;
+};
+struct Attn {
+  Linear qkv;               // packed in_proj: columns [0:d) q, [d:2d) k, [2d:3d) v
+  Linear out;
+};
+struct EncLayer {
+  Attn sa;
+  Linear ff1, ff2;
+  Norm n1, n2;
+};
+struct DecLayer {
+  Attn sa, ca;
+  Linear ff1, ff2;
+  Norm n1, n2, n3;
+};
+struct Transformer {
+  int variant, d_tok, d_model, heads, n_enc, n_dec, d_ff, has_io_proj;
+  const float* pe;          // [100][d_model]  transformer.pos_encoder.pe
+  const float* pe_score;    // [100][d_tok]    variant 1: the facade's pos_encoder.pe
+  Linear in_proj;           // variant 2, iff has_io_proj
+  Linear out_proj;          // variant 1 output_proj / variant 2 output_projection
+  Norm enc_norm, dec_norm;  // variant 2 final norms
+  EncLayer enc[kMaxLayers];
+  DecLayer dec[kMaxLayers];
+};
+static_assert(sizeof(Transformer) <= 3800, "Transformer must fit in kernel parameter space");
+static_assert(sizeof(Tokenizer) <= 3800, "Tokenizer must fit in kernel parameter space");
+
+}  // namespace sf
+
+struct sf_model {
+  sf_config cfg;
+  int device;
+  int sm_count;
+  int max_smem_optin;
+  float* arena;             // one cudaMalloc holding every packed fp32 tensor
+  size_t arena_bytes;
+  sf::Tokenizer tok;
+  sf::Transformer xf;
+};
+
+namespace sf {
+// launchers (fp32 CUDA-core path)
+int launch_tokenizer_fp32(const sf_model* m, const float* poses, int64_t B, int T, float* tokens,
+                          void* ws, int64_t ws_bytes, cudaStream_t st);
+int64_t tokenizer_fp32_workspace(const sf_model* m, int64_t B, int T);
+int launch_transformer_fp32(const sf_model* m, const float* tokens, int64_t B, int S, int reduction,
+                            float* recon, float* scores, cudaStream_t st);
+int launch_score(const sf_model* m, const float* tokens, const float* recon, int64_t B, int S,
+                 int reduction, float* scores, cudaStream_t st);
+int token_len(const sf_model* m, int T);
+}  // namespace sf

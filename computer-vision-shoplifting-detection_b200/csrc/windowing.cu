@@ -1,0 +1,424 @@
+// Pose-track windowing + centre/scale normalisation on the GPU (HBM-bound).
+//
+// Replaces the pure-Python hot loop of the reference's dataset construction:
+//   shopformer/data/poselift_dataset.py:297-329 (sliding windows, continuity, majority label),
+//   :331-365 (keypoint gather), :367-388 (normalise), :393-400 ((T,V,C)->(C,T,V));
+//   shopformer_2/data/poselift_dataset.py:57-91 (neck), :451-589 (same pipeline + frame_indices).
+//
+// Integer results (which windows exist, order, frame numbers, labels) are bit-exact.
+//
+// Pipeline (all on `stream`, no host sync unless the caller asks for the count):
+//   K_flag    one thread per candidate start position: continuity test over T-1 gaps,
+//             majority label, per-1024-candidate block sums
+//   K_scan    single CTA exclusive scan of the block sums
+//   K_compact per-block scan + scatter of (track, start, label) to the compacted order
+//   K_gather  one warp per window: the T*K*3 floats of a window are CONTIGUOUS in the packed
+//             track array, so they are staged into shared memory with 16-byte loads
+//             (scalar head/tail for the 204-byte frame pitch), reduced (centre = mean of valid
+//             keypoints in fp64, scale = max |coord - centre|) with warp shuffles and written
+//             back as two T x V planes with 16-byte stores.
+#include <algorithm>
+#include <vector>
+
+#include "sf_internal.h"
+
+namespace sf {
+namespace {
+
+constexpr int kScanBlock = 1024;
+
+struct WinCtx {
+  const float* kp;
+  const int32_t* frame_no;
+  const int64_t* track_off;     // device copies
+  const int64_t* cand_off;
+  const int32_t* track_video;
+  const int64_t* gt_off;
+  const uint8_t* gt;
+  int n_tracks, K, T, stride, max_gap, V, normalize;
+  int64_t n_cand;
+};
+
+__device__ __forceinline__ int find_track(const int64_t* __restrict__ cand_off, int n_tracks, int64_t c) {
+  int lo = 0, hi = n_tracks;             // cand_off[lo] <= c < cand_off[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(cand_off + mid) <= c) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(kScanBlock)
+k_flag(const WinCtx cx, uint8_t* __restrict__ flag, uint8_t* __restrict__ label, int32_t* __restrict__ block_sum) {
+  __shared__ int warp_sums[kScanBlock / 32];
+  const int64_t c = (int64_t)blockIdx.x * kScanBlock + threadIdx.x;
+  int ok = 0;
+  if (c < cx.n_cand) {
+    const int tr = find_track(cx.cand_off, cx.n_tracks, c);
+    const int64_t f0 = __ldg(cx.track_off + tr) + (c - __ldg(cx.cand_off + tr)) * cx.stride;
+    ok = 1;
+    int prev = __ldg(cx.frame_no + f0);
+    int votes = 0;
+    const bool has_gt = cx.gt != nullptr;
+    int64_t g0 = 0;
+    int glen = 0;
+    if (has_gt) {
+      const int vid = __ldg(cx.track_video + tr);
+      g0 = __ldg(cx.gt_off + vid);
+      glen = (int)(__ldg(cx.gt_off + vid + 1) - g0);
+    }
+    if (has_gt && glen > 0) votes += cx.gt[g0 + min(prev, glen - 1)];
+    for (int t = 1; t < cx.T; ++t) {
+      const int cur = __ldg(cx.frame_no + f0 + t);
+      if (cur - prev > cx.max_gap) ok = 0;
+      if (has_gt && glen > 0) votes += cx.gt[g0 + min(cur, glen - 1)];
+      prev = cur;
+    }
+    flag[c] = (uint8_t)ok;
+    label[c] = (uint8_t)(votes > cx.T / 2 ? 1 : 0);
+  }
+  // block sum of flags
+  int s = ok;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int v = warp_sums[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) block_sum[blockIdx.x] = v;
+  }
+}
+
+// exclusive scan of n block sums into int64 offsets; writes the grand total to *total
+__global__ void __launch_bounds__(1024) k_scan(const int32_t* __restrict__ block_sum, int64_t* __restrict__ block_off,
+                                               int n, int64_t* __restrict__ total) {
+  __shared__ int64_t warp_tot[32];
+  __shared__ int64_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int64_t v = i < n ? block_sum[i] : 0;
+    int64_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int64_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_tot[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      int64_t w = warp_tot[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int64_t y = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += y;
+      }
+      warp_tot[lane] = w;            // inclusive over warps
+    }
+    __syncthreads();
+    const int64_t before = carry + (warp ? warp_tot[warp - 1] : 0) + (x - v);
+    if (i < n) block_off[i] = before;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += warp_tot[31];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+
+__global__ void __launch_bounds__(kScanBlock)
+k_compact(const WinCtx cx, const uint8_t* __restrict__ flag, const uint8_t* __restrict__ label,
+          const int64_t* __restrict__ block_off, int32_t* __restrict__ labels_out, int32_t* __restrict__ win_track,
+          int32_t* __restrict__ win_start) {
+  __shared__ int warp_tot[kScanBlock / 32];
+  const int64_t c = (int64_t)blockIdx.x * kScanBlock + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int f = (c < cx.n_cand) ? flag[c] : 0;
+  int x = f;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) warp_tot[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    int w = warp_tot[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += y;
+    }
+    warp_tot[lane] = w;
+  }
+  __syncthreads();
+  if (f) {
+    const int64_t pos = block_off[blockIdx.x] + (warp ? warp_tot[warp - 1] : 0) + (x - 1);
+    const int tr = find_track(cx.cand_off, cx.n_tracks, c);
+    labels_out[pos] = label[c];
+    win_track[pos] = tr;
+    win_start[pos] = (int)((c - __ldg(cx.cand_off + tr)) * cx.stride);
+  }
+}
+
+constexpr int kGatherWarps = 8;
+
+// One warp per window.  smem per warp: T*K*3 raw floats (+ T*2 neck floats when V == 18).
+__global__ void __launch_bounds__(kGatherWarps * 32)
+k_gather(const WinCtx cx, const int64_t* __restrict__ n_windows, const int32_t* __restrict__ win_track,
+         const int32_t* __restrict__ win_start, float* __restrict__ poses, int32_t* __restrict__ frame_idx, int per_warp) {
+  extern __shared__ __align__(16) float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* slab = smem + (size_t)warp * per_warp;
+  const int T = cx.T, K = cx.K, V = cx.V;
+  const int n_raw = T * K * 3;
+  float* neck = slab + ((n_raw + 7) & ~3);         // [T][2], only used when V == 18
+  const bool add_neck = (V == 18);
+  const int Vsrc = add_neck ? 17 : min(V, K);      // keypoints taken from the detection itself
+  const int64_t nw = *n_windows;
+  const int64_t warps_total = (int64_t)gridDim.x * kGatherWarps;
+  for (int64_t w = (int64_t)blockIdx.x * kGatherWarps + warp; w < nw; w += warps_total) {
+    const int tr = __ldg(win_track + w);
+    const int64_t f0 = __ldg(cx.track_off + tr) + __ldg(win_start + w);
+    // ---- stage the contiguous chunk: scalar head, 16-byte body, scalar tail
+    const float* src = cx.kp + (size_t)f0 * K * 3;
+    const int mis = (int)((reinterpret_cast<uintptr_t>(src) >> 2) & 3);
+    float* raw = slab + mis;                        // same 16-byte phase in smem as in HBM
+    const int head = mis ? min(4 - mis, n_raw) : 0;
+    if (lane < head) raw[lane] = __ldg(src + lane);
+    const int body4 = (n_raw - head) >> 2;
+    const float4* s4 = reinterpret_cast<const float4*>(src + head);
+    float4* d4 = reinterpret_cast<float4*>(raw + head);
+    for (int i = lane; i < body4; i += 32) d4[i] = __ldg(s4 + i);
+    for (int i = head + 4 * body4 + lane; i < n_raw; i += 32) raw[i] = __ldg(src + i);
+    if (frame_idx)
+      for (int t = lane; t < T; t += 32) frame_idx[w * T + t] = __ldg(cx.frame_no + f0 + t);
+    __syncwarp();
+    if (add_neck) {
+      // add_neck_keypoint: midpoint of shoulders 5/6; np.allclose(.,0) == |x|,|y| <= 1e-8
+      for (int t = lane; t < T; t += 32) {
+        const float lx = raw[(t * K + 5) * 3], ly = raw[(t * K + 5) * 3 + 1];
+        const float rx = raw[(t * K + 6) * 3], ry = raw[(t * K + 6) * 3 + 1];
+        const bool l0 = fabsf(lx) <= 1e-8f && fabsf(ly) <= 1e-8f;
+        const bool r0 = fabsf(rx) <= 1e-8f && fabsf(ry) <= 1e-8f;
+        float nx = (lx + rx) * 0.5f, ny = (ly + ry) * 0.5f;
+        if (l0 && r0) { nx = 0.f; ny = 0.f; }
+        else if (l0) { nx = rx; ny = ry; }
+        else if (r0) { nx = lx; ny = ly; }
+        neck[2 * t] = nx;
+        neck[2 * t + 1] = ny;
+      }
+      __syncwarp();
+    }
+    auto coord = [&](int t, int v, int c) -> float {
+      if (v < Vsrc) return raw[(t * K + v) * 3 + c];
+      if (add_neck && v == 17) return neck[2 * t + c];
+      return 0.f;                                   // zero padding when the detection has fewer keypoints
+    };
+    const int n_el = T * V;
+    float cxm = 0.f, cym = 0.f, scale = 1.f;
+    if (cx.normalize) {
+      double sx = 0.0, sy = 0.0;
+      int cnt = 0;
+      for (int i = lane; i < n_el; i += 32) {
+        const int t = i / V, v = i % V;
+        const float x = coord(t, v, 0), y = coord(t, v, 1);
+        if (x != 0.f || y != 0.f) { sx += (double)x; sy += (double)y; ++cnt; }
+      }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        sx += __shfl_xor_sync(0xffffffffu, sx, o);
+        sy += __shfl_xor_sync(0xffffffffu, sy, o);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      }
+      if (cnt > 0) {
+        cxm = (float)(sx / (double)cnt);
+        cym = (float)(sy / (double)cnt);
+        float mx = 0.f;
+        for (int i = lane; i < n_el; i += 32) {
+          const int t = i / V, v = i % V;
+          const float x = coord(t, v, 0), y = coord(t, v, 1);
+          if (x != 0.f || y != 0.f) mx = fmaxf(mx, fmaxf(fabsf(x - cxm), fabsf(y - cym)));
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        scale = mx + 1e-6f;
+      }
+    }
+    // ---- write two T x V planes; 2*T*V floats per window
+    float* dst = poses + (size_t)w * 2 * n_el;
+    const bool vec_ok = ((2 * n_el) & 3) == 0;
+    if (vec_ok) {
+      for (int q = lane; q < (2 * n_el) >> 2; q += 32) {
+        float o4[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int i = 4 * q + e;
+          const int c = i / n_el, r = i % n_el;
+          float val = coord(r / V, r % V, c);
+          if (cx.normalize) {
+            val = (val - (c ? cym : cxm)) / scale;
+            if (!isfinite(val)) val = 0.f;          // nan_to_num(nan=0, posinf=0, neginf=0)
+          }
+          o4[e] = val;
+        }
+        __stcs(reinterpret_cast<float4*>(dst) + q, make_float4(o4[0], o4[1], o4[2], o4[3]));
+      }
+    } else {
+      for (int i = lane; i < 2 * n_el; i += 32) {
+        const int c = i / n_el, r = i % n_el;
+        float val = coord(r / V, r % V, c);
+        if (cx.normalize) {
+          val = (val - (c ? cym : cxm)) / scale;
+          if (!isfinite(val)) val = 0.f;
+        }
+        dst[i] = val;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+struct WsLayout {
+  size_t track_off, cand_off, track_video, gt_off, flag, label, block_sum, block_off, total;
+  int64_t n_cand;
+  int n_blocks;
+};
+
+int64_t candidates(const sf_tracks* tr, const sf_window_params* p, std::vector<int64_t>* cand_off) {
+  int64_t n = 0;
+  if (cand_off) cand_off->assign(tr->n_tracks + 1, 0);
+  for (int i = 0; i < tr->n_tracks; ++i) {
+    const int64_t len = tr->track_offsets_host[i + 1] - tr->track_offsets_host[i];
+    if (len >= p->seq_len) n += (len - p->seq_len) / p->stride + 1;
+    if (cand_off) (*cand_off)[i + 1] = n;
+  }
+  return n;
+}
+
+WsLayout layout(const sf_tracks* tr, const sf_window_params* p) {
+  WsLayout L{};
+  L.n_cand = candidates(tr, p, nullptr);
+  L.n_blocks = (int)((L.n_cand + kScanBlock - 1) / kScanBlock);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += (bytes + 255) & ~size_t(255);
+    return o;
+  };
+  L.track_off = take(sizeof(int64_t) * (tr->n_tracks + 1));
+  L.cand_off = take(sizeof(int64_t) * (tr->n_tracks + 1));
+  L.track_video = take(sizeof(int32_t) * std::max(tr->n_tracks, 1));
+  L.gt_off = take(sizeof(int64_t) * (tr->n_videos + 1));
+  L.flag = take((size_t)std::max<int64_t>(L.n_cand, 1));
+  L.label = take((size_t)std::max<int64_t>(L.n_cand, 1));
+  L.block_sum = take(sizeof(int32_t) * std::max(L.n_blocks, 1));
+  L.block_off = take(sizeof(int64_t) * std::max(L.n_blocks, 1));
+  L.total = off;
+  return L;
+}
+
+int check(const sf_tracks* tr, const sf_window_params* p) {
+  SF_REQUIRE(tr && p, SF_E_INVALID, "windowing: null argument");
+  SF_REQUIRE(p->seq_len >= 1 && p->stride >= 1 && p->max_gap >= 0, SF_E_INVALID, "windowing: bad seq_len/stride/max_gap");
+  SF_REQUIRE(tr->n_tracks >= 0 && tr->kp_per_frame >= 1, SF_E_INVALID, "windowing: bad track table");
+  SF_REQUIRE(p->num_keypoints >= 1 && p->num_keypoints <= kMaxV, SF_E_UNSUPPORTED, "windowing: V=%d outside [1,%d]",
+             p->num_keypoints, kMaxV);
+  SF_REQUIRE(p->num_keypoints != 18 || tr->kp_per_frame >= 17, SF_E_INVALID, "neck synthesis needs >= 17 source keypoints");
+  return SF_OK;
+}
+
+}  // namespace
+}  // namespace sf
+
+using namespace sf;
+
+extern "C" int64_t sf_window_capacity(const sf_tracks* tr, const sf_window_params* p) {
+  if (check(tr, p) != SF_OK) return SF_E_INVALID;
+  return candidates(tr, p, nullptr);
+}
+
+extern "C" int64_t sf_window_workspace_bytes(const sf_tracks* tr, const sf_window_params* p) {
+  if (check(tr, p) != SF_OK) return SF_E_INVALID;
+  return (int64_t)layout(tr, p).total;
+}
+
+extern "C" int sf_window_normalize(const sf_tracks* tr, const sf_window_params* p, float* poses_dev, int32_t* labels_dev,
+                                   int32_t* window_track_dev, int32_t* window_start_dev, int32_t* frame_idx_dev,
+                                   int64_t* n_windows_dev, int64_t* n_windows_host, void* workspace_dev,
+                                   int64_t workspace_bytes, void* stream) {
+  int rc = check(tr, p);
+  if (rc != SF_OK) return rc;
+  SF_REQUIRE(n_windows_dev, SF_E_INVALID, "windowing: n_windows_dev is required");
+  cudaStream_t st = (cudaStream_t)stream;
+  const WsLayout L = layout(tr, p);
+  SF_REQUIRE(workspace_dev && workspace_bytes >= (int64_t)L.total, SF_E_INVALID,
+             "windowing: workspace of %lld bytes needed, got %lld", (long long)L.total, (long long)workspace_bytes);
+  if (L.n_cand == 0) {
+    SF_CUDA_OK(cudaMemsetAsync(n_windows_dev, 0, sizeof(int64_t), st));
+    if (n_windows_host) {
+      SF_CUDA_OK(cudaStreamSynchronize(st));
+      *n_windows_host = 0;
+    }
+    return SF_OK;
+  }
+  SF_REQUIRE(poses_dev && labels_dev && window_track_dev && window_start_dev, SF_E_INVALID, "windowing: null output");
+  char* ws = (char*)workspace_dev;
+  std::vector<int64_t> cand_off;
+  candidates(tr, p, &cand_off);
+  SF_CUDA_OK(cudaMemcpyAsync(ws + L.track_off, tr->track_offsets_host, sizeof(int64_t) * (tr->n_tracks + 1), cudaMemcpyHostToDevice, st));
+  SF_CUDA_OK(cudaMemcpyAsync(ws + L.cand_off, cand_off.data(), sizeof(int64_t) * (tr->n_tracks + 1), cudaMemcpyHostToDevice, st));
+  const bool has_gt = tr->gt_dev && tr->gt_offsets_host && tr->track_video_host && tr->n_videos > 0;
+  if (has_gt) {
+    SF_CUDA_OK(cudaMemcpyAsync(ws + L.track_video, tr->track_video_host, sizeof(int32_t) * tr->n_tracks, cudaMemcpyHostToDevice, st));
+    SF_CUDA_OK(cudaMemcpyAsync(ws + L.gt_off, tr->gt_offsets_host, sizeof(int64_t) * (tr->n_videos + 1), cudaMemcpyHostToDevice, st));
+  }
+  // cand_off lives on this stack frame: the pageable copy above is staged before the call returns
+  WinCtx cx;
+  cx.kp = tr->kp_dev;
+  cx.frame_no = tr->frame_no_dev;
+  cx.track_off = (const int64_t*)(ws + L.track_off);
+  cx.cand_off = (const int64_t*)(ws + L.cand_off);
+  cx.track_video = (const int32_t*)(ws + L.track_video);
+  cx.gt_off = (const int64_t*)(ws + L.gt_off);
+  cx.gt = has_gt ? tr->gt_dev : nullptr;
+  cx.n_tracks = tr->n_tracks;
+  cx.K = tr->kp_per_frame;
+  cx.T = p->seq_len;
+  cx.stride = p->stride;
+  cx.max_gap = p->max_gap;
+  cx.V = p->num_keypoints;
+  cx.normalize = p->normalize;
+  cx.n_cand = L.n_cand;
+  uint8_t* flag = (uint8_t*)(ws + L.flag);
+  uint8_t* label = (uint8_t*)(ws + L.label);
+  int32_t* block_sum = (int32_t*)(ws + L.block_sum);
+  int64_t* block_off = (int64_t*)(ws + L.block_off);
+  k_flag<<<L.n_blocks, kScanBlock, 0, st>>>(cx, flag, label, block_sum);
+  k_scan<<<1, 1024, 0, st>>>(block_sum, block_off, L.n_blocks, n_windows_dev);
+  k_compact<<<L.n_blocks, kScanBlock, 0, st>>>(cx, flag, label, block_off, labels_dev, window_track_dev, window_start_dev);
+  const int n_raw = cx.T * cx.K * 3;
+  const int per_warp = ((n_raw + 7) & ~3) + ((2 * cx.T + 3) & ~3);
+  const size_t smem = (size_t)per_warp * kGatherWarps * sizeof(float);
+  int dev = 0, max_smem = 0, sms = 0;
+  SF_CUDA_OK(cudaGetDevice(&dev));
+  SF_CUDA_OK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  SF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  SF_REQUIRE(smem <= (size_t)max_smem, SF_E_UNSUPPORTED, "windowing: seq_len=%d needs %zu bytes of shared memory", cx.T, smem);
+  SF_CUDA_OK(cudaFuncSetAttribute(k_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 1;
+  SF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gather, kGatherWarps * 32, smem));
+  const int64_t want = (L.n_cand + kGatherWarps - 1) / kGatherWarps;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sms * std::max(occ, 1)));
+  k_gather<<<grid, kGatherWarps * 32, smem, st>>>(cx, n_windows_dev, window_track_dev, window_start_dev, poses_dev,
+                                                  frame_idx_dev, per_warp);
+  SF_CUDA_OK(cudaGetLastError());
+  if (n_windows_host) {
+    SF_CUDA_OK(cudaMemcpyAsync(n_windows_host, n_windows_dev, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    SF_CUDA_OK(cudaStreamSynchronize(st));
+  }
+  return SF_OK;
+}

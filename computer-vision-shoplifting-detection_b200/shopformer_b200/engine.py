@@ -1,0 +1,287 @@
+"""Host-side owner of a packed native model (``sf_model``) + the torch-facing calls.
+
+``ScoringEngine`` is what the drop-in facades hold: it turns a reference-format
+``state_dict`` + config into a ``sf_model`` (BatchNorm folding happens in native code),
+and exposes the C-ABI calls on torch CUDA tensors (torch supplies memory and the current
+stream, nothing else).  All compute is in ``libshopformer_b200.so``; a failure of the
+native library is an exception, never a fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import native as N
+
+
+@dataclass
+class EngineConfig:
+    """Everything sf_config needs (mirrors the reference constructors' arguments)."""
+    variant: int
+    in_channels: int
+    num_keypoints: int
+    channels: List[int]            # [in, hidden, ..., latent]
+    strides: List[int]
+    d_model: int
+    n_heads: int
+    n_enc_layers: int
+    n_dec_layers: int
+    d_ff: int
+    pool_tokens: int = 0
+
+    def to_native(self) -> N.SfConfig:
+        c = N.SfConfig()
+        c.variant, c.in_channels, c.num_keypoints = self.variant, self.in_channels, self.num_keypoints
+        c.n_blocks = len(self.strides)
+        if c.n_blocks > N.SF_MAX_BLOCKS or len(self.channels) != c.n_blocks + 1:
+            raise ValueError("bad tokenizer depth / channel list")
+        for i, v in enumerate(self.channels):
+            c.channels[i] = int(v)
+        for i, v in enumerate(self.strides):
+            c.strides[i] = int(v)
+        c.pool_tokens, c.d_model, c.n_heads = self.pool_tokens, self.d_model, self.n_heads
+        c.n_enc_layers, c.n_dec_layers, c.d_ff = self.n_enc_layers, self.n_dec_layers, self.d_ff
+        return c
+
+
+def _stream_ptr(device: torch.device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+class ScoringEngine:
+    """One immutable packed model on one GPU."""
+
+    def __init__(self, cfg: EngineConfig, state_dict: Dict[str, torch.Tensor], device: torch.device):
+        lib = N.load()
+        N.check(lib.sf_device_count(), "sf_device_count")
+        self.cfg = cfg
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("ScoringEngine needs a CUDA device; there is no CPU path")
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", idx)
+        names, arrays = [], []
+        for k, v in state_dict.items():
+            if not torch.is_tensor(v) or not v.is_floating_point():
+                continue
+            names.append(k.encode())
+            arrays.append(np.ascontiguousarray(v.detach().to("cpu", torch.float32).numpy()))
+        n = len(names)
+        c_names = (C.c_char_p * n)(*names)
+        c_ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in arrays])
+        c_numel = (C.c_int64 * n)(*[a.size for a in arrays])
+        handle = C.c_void_p()
+        ncfg = cfg.to_native()
+        N.check(lib.sf_model_create(C.byref(ncfg), n, c_names, c_ptrs, c_numel, idx, C.byref(handle)), "sf_model_create")
+        self._lib = lib
+        self._h = handle
+        self._runners: Dict[Tuple[int, int], C.c_void_p] = {}
+
+    # -- lifetime
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            for r in self._runners.values():
+                self._lib.sf_runner_destroy(r)
+            self._runners.clear()
+            self._lib.sf_model_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- shapes
+    def token_shape(self, T: int) -> Tuple[int, int]:
+        s, d = C.c_int32(), C.c_int32()
+        N.check(self._lib.sf_model_token_shape(self._h, T, C.byref(s), C.byref(d)), "sf_model_token_shape")
+        return s.value, d.value
+
+    def _workspace(self, B: int, T: int) -> Tuple[Optional[torch.Tensor], int]:
+        nbytes = self._lib.sf_workspace_bytes(self._h, B, T)
+        N.check(int(min(nbytes, 0)), "sf_workspace_bytes")
+        if nbytes == 0:
+            return None, 0
+        return torch.empty(nbytes, dtype=torch.uint8, device=self.device), int(nbytes)
+
+    def _poses(self, poses: torch.Tensor) -> torch.Tensor:
+        if poses.dim() != 4:
+            raise ValueError(f"poses must be (B,C,T,V), got {tuple(poses.shape)}")
+        if poses.shape[1] != self.cfg.in_channels or poses.shape[3] != self.cfg.num_keypoints:
+            raise ValueError(f"poses must be (B,{self.cfg.in_channels},T,{self.cfg.num_keypoints}), got {tuple(poses.shape)}")
+        if not poses.is_cuda:
+            raise RuntimeError("native scoring path takes CUDA tensors only (no CPU fallback)")
+        return poses.to(self.device, torch.float32).contiguous()
+
+    # -- the four reference-facing calls
+    def tokenize(self, poses: torch.Tensor) -> torch.Tensor:
+        x = self._poses(poses)
+        B, _, T, _ = x.shape
+        S, D = self.token_shape(T)
+        out = torch.empty(B, S, D, dtype=torch.float32, device=self.device)
+        ws, nb = self._workspace(B, T)
+        N.check(self._lib.sf_tokenize(self._h, _ptr(x), B, T, _ptr(out), _ptr(ws), nb, _stream_ptr(self.device)), "sf_tokenize")
+        return out
+
+    def reconstruct_tokens(self, tokens: torch.Tensor) -> torch.Tensor:
+        t = tokens.to(self.device, torch.float32).contiguous()
+        B, S, D = t.shape
+        out = torch.empty_like(t)
+        N.check(self._lib.sf_reconstruct_tokens(self._h, _ptr(t), B, S, _ptr(out), None, 0, _stream_ptr(self.device)),
+                "sf_reconstruct_tokens")
+        return out
+
+    def normality_score(self, tokens: torch.Tensor, recon: torch.Tensor, reduction: str = "mean") -> torch.Tensor:
+        t = tokens.to(self.device, torch.float32).contiguous()
+        r = recon.to(self.device, torch.float32).contiguous()
+        B, S, _ = t.shape
+        red = self._reduction(reduction)
+        out = torch.empty((B,) if red == N.SF_REDUCE_MEAN else (B, S), dtype=torch.float32, device=self.device)
+        N.check(self._lib.sf_normality_score(self._h, _ptr(t), _ptr(r), B, S, red, _ptr(out), _stream_ptr(self.device)),
+                "sf_normality_score")
+        return out
+
+    @staticmethod
+    def _reduction(reduction: str) -> int:
+        if reduction == "mean":
+            return N.SF_REDUCE_MEAN
+        if reduction == "none":
+            return N.SF_REDUCE_NONE
+        raise ValueError(f"Unknown reduction: {reduction}")
+
+    def score_windows(self, poses: torch.Tensor, reduction: str = "mean", precision: str = "fp32",
+                      return_tokens: bool = False, return_recon: bool = False, out: Optional[torch.Tensor] = None):
+        """poses -> scores (and optionally tokens / reconstruction) in one native call.  ``out`` lets the
+        caller have the scores written straight into a slice of a larger buffer (e.g. the all-gather buffer)."""
+        x = self._poses(poses)
+        B, _, T, _ = x.shape
+        S, D = self.token_shape(T)
+        red = self._reduction(reduction)
+        prec = {"fp32": N.SF_PREC_FP32, "bf16": N.SF_PREC_BF16}[precision]
+        shape = (B,) if red == N.SF_REDUCE_MEAN else (B, S)
+        if out is not None:
+            if out.shape != shape or out.dtype != torch.float32 or not out.is_contiguous() or out.device != self.device:
+                raise ValueError("`out` must be a contiguous fp32 tensor of the score shape on the engine's device")
+            scores = out
+        else:
+            scores = torch.empty(shape, dtype=torch.float32, device=self.device)
+        tok = torch.empty(B, S, D, dtype=torch.float32, device=self.device) if return_tokens else None
+        rec = torch.empty(B, S, D, dtype=torch.float32, device=self.device) if return_recon else None
+        ws, nb = self._workspace(B, T)
+        N.check(self._lib.sf_score_windows(self._h, _ptr(x), B, T, red, prec, _ptr(scores), _ptr(tok), _ptr(rec), _ptr(ws), nb,
+                                           _stream_ptr(self.device)), "sf_score_windows")
+        if return_tokens or return_recon:
+            return scores, tok, rec
+        return scores
+
+    # -- host-buffer path (what a reference-side loop calls per batch)
+    def score_host(self, poses: np.ndarray, precision: str = "fp32", chunk: int = 16384) -> np.ndarray:
+        """numpy (B,C,T,V) fp32 on the host -> numpy scores (B,); H2D, kernels and D2H are
+        pipelined in chunks inside the native runner (two streams, pinned staging)."""
+        a = np.ascontiguousarray(poses, dtype=np.float32)
+        if a.ndim != 4 or a.shape[1] != self.cfg.in_channels or a.shape[3] != self.cfg.num_keypoints:
+            raise ValueError(f"poses must be (B,{self.cfg.in_channels},T,{self.cfg.num_keypoints}), got {a.shape}")
+        B, _, T, _ = a.shape
+        key = (T, chunk)
+        if key not in self._runners:
+            h = C.c_void_p()
+            N.check(self._lib.sf_runner_create(self._h, T, chunk, C.byref(h)), "sf_runner_create")
+            self._runners[key] = h
+        out = np.empty(B, dtype=np.float32)
+        prec = {"fp32": N.SF_PREC_FP32, "bf16": N.SF_PREC_BF16}[precision]
+        N.check(self._lib.sf_runner_score(self._runners[key], C.c_void_p(a.ctypes.data), B, prec, C.c_void_p(out.ctypes.data)),
+                "sf_runner_score")
+        return out
+
+
+# --------------------------------------------------------------------------- windowing
+@dataclass
+class PackedTracks:
+    """Packed per-person tracks (see include/shopformer_b200.h, ``sf_tracks``)."""
+    kp: np.ndarray                 # (F, K, 3) fp32
+    frame_no: np.ndarray           # (F,) int32
+    track_offsets: np.ndarray      # (n_tracks+1,) int64
+    track_video: np.ndarray        # (n_tracks,) int32
+    gt: Optional[np.ndarray] = None        # concatenated uint8
+    gt_offsets: Optional[np.ndarray] = None  # (n_videos+1,) int64
+    video_names: List[str] = field(default_factory=list)
+
+    @property
+    def n_tracks(self) -> int:
+        return len(self.track_offsets) - 1
+
+
+class DeviceTracks:
+    """PackedTracks resident in HBM (upload once, window many times)."""
+
+    def __init__(self, tracks: PackedTracks, device: torch.device):
+        self.host = tracks
+        self.device = torch.device(device)
+        self.kp = torch.from_numpy(np.ascontiguousarray(tracks.kp, dtype=np.float32)).to(self.device)
+        self.frame_no = torch.from_numpy(np.ascontiguousarray(tracks.frame_no, dtype=np.int32)).to(self.device)
+        self.gt = None
+        if tracks.gt is not None and tracks.gt_offsets is not None and len(tracks.gt) > 0:
+            self.gt = torch.from_numpy(np.ascontiguousarray(tracks.gt, dtype=np.uint8)).to(self.device)
+        self._off = np.ascontiguousarray(tracks.track_offsets, dtype=np.int64)
+        self._vid = np.ascontiguousarray(tracks.track_video, dtype=np.int32)
+        self._gto = None if tracks.gt_offsets is None else np.ascontiguousarray(tracks.gt_offsets, dtype=np.int64)
+
+    def native(self) -> N.SfTracks:
+        t = N.SfTracks()
+        t.kp_dev = self.kp.data_ptr()
+        t.frame_no_dev = self.frame_no.data_ptr()
+        t.track_offsets_host = self._off.ctypes.data
+        t.track_video_host = self._vid.ctypes.data
+        t.gt_dev = 0 if self.gt is None else self.gt.data_ptr()
+        t.gt_offsets_host = 0 if self._gto is None else self._gto.ctypes.data
+        t.n_frames = int(self.kp.shape[0])
+        t.n_tracks = int(len(self._off) - 1)
+        t.n_videos = 0 if self._gto is None else int(len(self._gto) - 1)
+        t.kp_per_frame = int(self.kp.shape[1])
+        return t
+
+
+def window_normalize(tracks: DeviceTracks, seq_len: int, stride: int, num_keypoints: int = 17, max_gap: int = 5,
+                     normalize: bool = True, want_frame_indices: bool = False, sync: bool = True):
+    """Run the windowing kernels.  Returns a dict of CUDA tensors trimmed to the number of
+    valid windows when ``sync`` (one 8-byte D2H), else capacity-sized tensors + ``n_windows``
+    as a device scalar."""
+    lib = N.load()
+    dev = tracks.device
+    nt = tracks.native()
+    p = N.SfWindowParams()
+    p.seq_len, p.stride, p.max_gap, p.num_keypoints, p.normalize = seq_len, stride, max_gap, num_keypoints, int(normalize)
+    cap = lib.sf_window_capacity(C.byref(nt), C.byref(p))
+    N.check(int(min(cap, 0)), "sf_window_capacity")
+    wsb = lib.sf_window_workspace_bytes(C.byref(nt), C.byref(p))
+    N.check(int(min(wsb, 0)), "sf_window_workspace_bytes")
+    capn = max(int(cap), 1)
+    poses = torch.empty(capn, 2, seq_len, num_keypoints, dtype=torch.float32, device=dev)
+    labels = torch.empty(capn, dtype=torch.int32, device=dev)
+    wtrack = torch.empty(capn, dtype=torch.int32, device=dev)
+    wstart = torch.empty(capn, dtype=torch.int32, device=dev)
+    fidx = torch.empty(capn, seq_len, dtype=torch.int32, device=dev) if want_frame_indices else None
+    n_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+    ws = torch.empty(max(int(wsb), 1), dtype=torch.uint8, device=dev)
+    n_host = C.c_int64(0)
+    rc = lib.sf_window_normalize(C.byref(nt), C.byref(p), _ptr(poses), _ptr(labels), _ptr(wtrack), _ptr(wstart), _ptr(fidx),
+                                 _ptr(n_dev), C.byref(n_host) if sync else None, _ptr(ws), int(wsb), _stream_ptr(dev))
+    N.check(rc, "sf_window_normalize")
+    out = {"poses": poses, "labels": labels, "window_track": wtrack, "window_start": wstart, "frame_indices": fidx,
+           "n_windows": n_dev, "capacity": int(cap)}
+    if sync:
+        n = int(n_host.value)
+        for k in ("poses", "labels", "window_track", "window_start", "frame_indices"):
+            if out[k] is not None:
+                out[k] = out[k][:n]
+        out["n_windows"] = n
+    return out

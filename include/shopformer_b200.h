@@ -1,0 +1,199 @@
+/*
+ * shopformer_b200.h -- C ABI of the B200-native Shopformer scoring path.
+ *
+ * The reference (cthadeufaria/computer-vision-shoplifting-detection) has no FFI: its
+ * "plugin interface" for this path is a set of Python methods on nn.Module / Dataset
+ * objects.  Every entry point below names the reference method it replaces
+ * (file:line relative to the reference checkout).  INTEGRATION.md shows the ctypes
+ * stub a maintainer would add on the reference side.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary;
+ *   - `*_dev` pointers are device (HBM) pointers, `*_host` pointers are host pointers;
+ *   - outputs are caller-allocated; nothing is allocated per call except inside the
+ *     explicit `sf_runner_*` object; no entry point synchronises the device unless
+ *     its comment says so;
+ *   - `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default stream);
+ *   - every function returns SF_OK (0) or a negative SF_E* code and never throws;
+ *     `sf_last_error()` returns a thread-local message for the last failure;
+ *   - a `sf_model` is immutable after creation and may be used concurrently from
+ *     several host threads on distinct streams (each call brings its own workspace).
+ *
+ * Tensor layouts (all contiguous, fp32 unless stated)
+ *   poses   (B, C, T, V)      x-plane then y-plane, each T x V  (reference __getitem__ layout)
+ *   tokens  (B, S, D)         D = latent_channels * V, feature index c*V + v
+ *   recon   (B, S, D)
+ *   scores  (B)               or (B, S) for SF_REDUCE_NONE (variant 2 only)
+ */
+#ifndef SHOPFORMER_B200_H
+#define SHOPFORMER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SF_ABI_VERSION 1
+
+enum {
+  SF_OK = 0,
+  SF_E_INVALID = -1,      /* bad argument / shape / config                              */
+  SF_E_MISSING = -2,      /* a state-dict key the config requires was not supplied      */
+  SF_E_SHAPE = -3,        /* a supplied tensor has the wrong number of elements         */
+  SF_E_UNSUPPORTED = -4,  /* valid config that no kernel in this build covers           */
+  SF_E_CUDA = -5,         /* CUDA runtime error (message has the cudaError string)      */
+  SF_E_NODEVICE = -6      /* no sm_100 device visible: there is NO CPU fallback         */
+};
+
+enum { SF_VARIANT_SHOPFORMER = 1, SF_VARIANT_SHOPFORMER_2 = 2 };
+enum { SF_REDUCE_MEAN = 0, SF_REDUCE_NONE = 1 };
+/* arithmetic of the tokenizer/transformer contractions */
+enum { SF_PREC_FP32 = 0, SF_PREC_BF16 = 1 };
+
+#define SF_MAX_BLOCKS 8
+
+/* Everything that is not recoverable from tensor shapes.  Mirrors the constructor
+ * arguments of shopformer/models/shopformer.py:35-50 and the `model:` section of
+ * shopformer_2/configs/paper_config.yaml:5-26. */
+typedef struct sf_config {
+  int32_t variant;                 /* SF_VARIANT_*                                        */
+  int32_t in_channels;             /* 2                                                   */
+  int32_t num_keypoints;           /* V: 17 or 18 (<= 32)                                 */
+  int32_t n_blocks;                /* ST-GCN blocks in the tokenizer (4)                  */
+  int32_t channels[SF_MAX_BLOCKS + 1]; /* [in, hidden, hidden, hidden, latent]            */
+  int32_t strides[SF_MAX_BLOCKS];  /* temporal stride of each block                       */
+  int32_t pool_tokens;             /* variant 2 AdaptiveAvgPool target, 0 = no pooling    */
+  int32_t d_model;                 /* transformer width (136 / 144)                       */
+  int32_t n_heads;
+  int32_t n_enc_layers;
+  int32_t n_dec_layers;
+  int32_t d_ff;
+  int32_t reserved[8];
+} sf_config;
+
+typedef struct sf_model sf_model;    /* packed, BatchNorm-folded weights resident in HBM */
+typedef struct sf_runner sf_runner;  /* pinned staging + device buffers + 2 streams      */
+
+/* ------------------------------------------------------------------ library ------- */
+int sf_abi_version(void);
+const char* sf_last_error(void);
+/* Number of visible sm_100 devices; SF_E_NODEVICE if none. */
+int sf_device_count(void);
+
+/* ------------------------------------------------------------------ model --------- */
+/* Replaces: Shopformer.load_state_dict + .to(device) + .eval()
+ *   (shopformer/evaluate.py:75-78, shopformer/inference.py:59-62,
+ *    shopformer_2/train.py:512-521).
+ * `names[i]` are the reference's state-dict keys, `data_host[i]` fp32 host arrays of
+ * `numel[i]` elements.  BatchNorm running statistics are folded into the adjacent
+ * conv / affine here, once; the result is immutable.  Synchronises `device`. */
+int sf_model_create(const sf_config* cfg, int32_t n_tensors, const char* const* names,
+                    const float* const* data_host, const int64_t* numel, int32_t device,
+                    sf_model** out);
+void sf_model_destroy(sf_model* m);
+/* Token count S and token width D for windows of T frames (conv length (T-1)/s+1 per block). */
+int sf_model_token_shape(const sf_model* m, int32_t T, int32_t* S, int32_t* D);
+/* Bytes of device workspace the calls below need for a batch of B windows of T frames. */
+int64_t sf_workspace_bytes(const sf_model* m, int64_t B, int32_t T);
+
+/* ------------------------------------------------------------------ hot path ------ */
+/* Replaces: Shopformer.tokenize -> GCAEEncoder.forward
+ *   (shopformer/models/shopformer.py:125-136, shopformer/models/gcae.py:331-366;
+ *    shopformer_2/models/gcae.py:375-422). */
+int sf_tokenize(const sf_model* m, const float* poses_dev, int64_t B, int32_t T, float* tokens_dev,
+                void* workspace_dev, int64_t workspace_bytes, void* stream);
+
+/* Replaces: Shopformer.reconstruct_tokens -> ShopformerTransformer.forward
+ *   (shopformer/models/shopformer.py:138-148, shopformer/models/transformer.py:304-329;
+ *    shopformer_2/models/transformer.py:147-194). */
+int sf_reconstruct_tokens(const sf_model* m, const float* tokens_dev, int64_t B, int32_t S,
+                          float* recon_dev, void* workspace_dev, int64_t workspace_bytes, void* stream);
+
+/* Replaces: Shopformer.compute_normality_score (shopformer/models/shopformer.py:150-178)
+ *   and the MSE of compute_anomaly_score (shopformer_2/models/shopformer.py:178-186).
+ * Stand-alone HBM-bound kernel: reads tokens + recon, writes B (or B*S) floats. */
+int sf_normality_score(const sf_model* m, const float* tokens_dev, const float* recon_dev, int64_t B,
+                       int32_t S, int32_t reduction, float* scores_dev, void* stream);
+
+/* Replaces: Shopformer.forward()['normality_score'] (shopformer/models/shopformer.py:180-220)
+ *   and Shopformer.compute_anomaly_score (shopformer_2/models/shopformer.py:155-188).
+ * poses -> scores in one call; `tokens_dev` / `recon_dev` may be NULL (then neither ever
+ * reaches HBM as fp32 tensors).  `precision` is SF_PREC_*. */
+int sf_score_windows(const sf_model* m, const float* poses_dev, int64_t B, int32_t T, int32_t reduction,
+                     int32_t precision, float* scores_dev, float* tokens_dev, float* recon_dev,
+                     void* workspace_dev, int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ windowing ----- */
+/* Packed tracks (one entry per detection of one person, grouped per person in the
+ * reference's first-seen order, frames ascending inside a track):
+ *   kp_dev         (F, K, 3) fp32   x, y, conf as PoseLift stores them, K >= 17
+ *   frame_no_dev   (F) int32
+ *   track_offsets  (n_tracks + 1) int64, host
+ *   track_video    (n_tracks) int32, host        index into gt_offsets
+ *   gt_dev         concatenated per-video uint8 frame labels (may be NULL -> label 0)
+ *   gt_offsets     (n_videos + 1) int64, host
+ */
+typedef struct sf_tracks {
+  const float* kp_dev;
+  const int32_t* frame_no_dev;
+  const int64_t* track_offsets_host;
+  const int32_t* track_video_host;
+  const uint8_t* gt_dev;
+  const int64_t* gt_offsets_host;
+  int64_t n_frames;
+  int32_t n_tracks;
+  int32_t n_videos;
+  int32_t kp_per_frame;            /* K (17 for PoseLift)                                 */
+} sf_tracks;
+
+typedef struct sf_window_params {
+  int32_t seq_len;                 /* T                                                   */
+  int32_t stride;
+  int32_t max_gap;                 /* 5 in shopformer/, ctor arg in shopformer_2/         */
+  int32_t num_keypoints;           /* V: 17, or 18 = add neck (variant-2 semantics)       */
+  int32_t normalize;               /* centre / scale normalisation on/off                 */
+  int32_t reserved[3];
+} sf_window_params;
+
+/* Upper bound on the number of windows (every candidate start position), host-only. */
+int64_t sf_window_capacity(const sf_tracks* tr, const sf_window_params* p);
+int64_t sf_window_workspace_bytes(const sf_tracks* tr, const sf_window_params* p);
+
+/* Replaces: PoseLiftDataset._extract_sequences + _check_continuity +
+ *   _extract_pose_sequence + _normalize_sequence + __getitem__ transpose
+ *   (shopformer/data/poselift_dataset.py:256-400;
+ *    shopformer_2/data/poselift_dataset.py:57-91,410-589).
+ * Outputs sized by sf_window_capacity(); valid windows are compacted to the front in
+ * the reference's order.  `n_windows_dev` (int64, device) receives the count; if
+ * `n_windows_host` is non-NULL the call synchronises the stream and stores it there.
+ *   poses_dev        (cap, 2, T, V) fp32
+ *   labels_dev       (cap) int32           majority vote of GT[min(f, len-1)]
+ *   window_track_dev (cap) int32           which track each window came from
+ *   window_start_dev (cap) int32           start position inside the track
+ *   frame_idx_dev    (cap, T) int32 or NULL (shopformer_2 `frame_indices`)
+ */
+int sf_window_normalize(const sf_tracks* tr, const sf_window_params* p, float* poses_dev,
+                        int32_t* labels_dev, int32_t* window_track_dev, int32_t* window_start_dev,
+                        int32_t* frame_idx_dev, int64_t* n_windows_dev, int64_t* n_windows_host,
+                        void* workspace_dev, int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ host-buffer runner */
+/* The call a reference-side loop makes per batch: poses on the HOST, scores back on the
+ * HOST (shopformer/evaluate.py:90-99, shopformer/inference.py:67-94,
+ * shopformer/train.py:311-319, shopformer_2/evaluate.py:52-58).  The runner owns pinned
+ * staging, device buffers and two streams and pipelines H2D / kernels / D2H in chunks. */
+int sf_runner_create(const sf_model* m, int32_t T, int64_t max_chunk, sf_runner** out);
+void sf_runner_destroy(sf_runner* r);
+/* Blocking: returns after `scores_host[0..B)` is written.  `poses_host` need not be pinned. */
+int sf_runner_score(sf_runner* r, const float* poses_host, int64_t B, int32_t precision,
+                    float* scores_host);
+/* Pinned staging buffer of the runner (capacity `max_chunk` windows x 2 slots) so that
+ * producers can write windows straight into page-locked memory. */
+float* sf_runner_pinned_poses(sf_runner* r, int32_t slot);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHOPFORMER_B200_H */
