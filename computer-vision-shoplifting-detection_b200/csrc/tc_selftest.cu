@@ -1,0 +1,113 @@
+// sf_selftest_umma: one 128 x N x K tcgen05 product on a single CTA, used by the GPU tests to pin the
+// descriptor encodings (no-swizzle K-major A, K-major / MN-major B, arbitrary 16-byte row shifts of A),
+// the TMEM lane/column mapping of tcgen05.ld and the commit/mbarrier handshake against numpy.
+#include <vector>
+
+#include "sf_internal.h"
+#include "tc_common.cuh"
+
+namespace sf {
+namespace {
+
+using namespace tc;
+
+// A: (a_rows, K) fp32 row-major in global; the MMA uses rows [shift, shift+128).
+// B: mode 0 -> (N, K) row-major (K-major operand); mode 1 -> (K, N) row-major (MN-major operand).
+__global__ void __launch_bounds__(128, 1)
+umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D, int N, int K,
+                     int a_rows, int shift, int mode) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(smem_raw);               // [K/8][a_rows][8]
+  const int b_rows = mode == 0 ? N : K;                                          // rows of the B buffer
+  const int b_cols = mode == 0 ? K : N;
+  __nv_bfloat16* sB = sA + (size_t)(K / 8) * a_rows * 8;                         // [b_cols/8][b_rows][8]
+  const int warp = threadIdx.x >> 5;
+
+  if (warp == 0) tmem_alloc(&tmem_base, 64);
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  for (int i = threadIdx.x; i < a_rows * K; i += blockDim.x) {
+    const int r = i / K, c = i % K;
+    sA[pc_index(r, c, a_rows)] = __float2bfloat16(A[i]);
+  }
+  for (int i = threadIdx.x; i < b_rows * b_cols; i += blockDim.x) {
+    const int r = i / b_cols, c = i % b_cols;
+    sB[pc_index(r, c, b_rows)] = __float2bfloat16(B[i]);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tmem_base;
+
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = make_idesc(128, N, mode == 1);
+    const uint32_t a_plane = (uint32_t)a_rows * 16u, b_plane = (uint32_t)b_rows * 16u;
+    const uint64_t adesc0 = make_desc(smem_u32(sA) + (uint32_t)shift * 16u, /*lbo=*/a_plane, /*sbo=*/128u);
+    // K-major B: LBO = next K chunk (plane), SBO = next 8 N rows (128 B).
+    // MN-major B: LBO = next 8 K rows (128 B), SBO = next N chunk (plane).
+    const uint64_t bdesc0 = mode == 0 ? make_desc(smem_u32(sB), b_plane, 128u) : make_desc(smem_u32(sB), 128u, b_plane);
+    for (int k = 0; k < K / 16; ++k) {
+      const uint64_t ad = desc_advance(adesc0, (uint32_t)k * 2u * a_plane);                 // two K chunks per MMA
+      const uint64_t bd = mode == 0 ? desc_advance(bdesc0, (uint32_t)k * 2u * b_plane)      // two K chunks
+                                    : desc_advance(bdesc0, (uint32_t)k * 256u);             // 16 K rows
+      umma_bf16(tbase, ad, bd, idesc, k > 0);
+    }
+    umma_commit(&bar);
+  }
+  {
+    // bounded wait: a wrong descriptor must fail the test, not hang the GPU
+    bool done = false;
+    for (int spin = 0; spin < (1 << 22) && !done; ++spin) done = mbar_try_wait(&bar, 0);
+    if (!done) {
+      for (int c = 0; c < N; ++c) D[(warp * 32 + (threadIdx.x & 31)) * N + c] = __int_as_float(0x7fc00000);
+      return;
+    }
+  }
+  tc_fence_after();
+  const int row = warp * 32 + (threadIdx.x & 31);
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    float v[16];
+    tmem_ld16(tbase + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) D[row * N + c0 + j] = v[j];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tbase, 64);
+}
+
+}  // namespace
+}  // namespace sf
+
+extern "C" int sf_selftest_umma(int32_t mode, int32_t N, int32_t K, int32_t shift, const float* a_host,
+                                const float* b_host, float* d_host) {
+  using namespace sf;
+  SF_REQUIRE((mode == 0 || mode == 1) && N >= 16 && N <= 64 && N % 16 == 0 && K >= 16 && K % 16 == 0 && K <= 512 &&
+                 shift >= 0 && shift <= 64 && a_host && b_host && d_host,
+             SF_E_INVALID, "sf_selftest_umma: bad argument");
+  int rc = sf_device_count();
+  if (rc < 0) return rc;
+  const int a_rows = 128 + shift;
+  float *dA = nullptr, *dB = nullptr, *dD = nullptr;
+  SF_CUDA_OK(cudaMalloc(&dA, sizeof(float) * a_rows * K));
+  SF_CUDA_OK(cudaMalloc(&dB, sizeof(float) * N * K));
+  SF_CUDA_OK(cudaMalloc(&dD, sizeof(float) * 128 * N));
+  SF_CUDA_OK(cudaMemcpy(dA, a_host, sizeof(float) * a_rows * K, cudaMemcpyHostToDevice));
+  SF_CUDA_OK(cudaMemcpy(dB, b_host, sizeof(float) * N * K, cudaMemcpyHostToDevice));
+  const size_t smem = ((size_t)a_rows * K + (size_t)N * K) * 2 + 256;
+  SF_CUDA_OK(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_selftest_kernel<<<1, 128, smem>>>(dA, dB, dD, N, K, a_rows, shift, mode);
+  SF_CUDA_OK(cudaGetLastError());
+  SF_CUDA_OK(cudaDeviceSynchronize());
+  SF_CUDA_OK(cudaMemcpy(d_host, dD, sizeof(float) * 128 * N, cudaMemcpyDeviceToHost));
+  cudaFree(dA);
+  cudaFree(dB);
+  cudaFree(dD);
+  return SF_OK;
+}

@@ -193,6 +193,15 @@ int sf_runner_score(sf_runner* r, const float* poses_host, int64_t B, int32_t pr
  * producers can write windows straight into page-locked memory. */
 float* sf_runner_pinned_poses(sf_runner* r, int32_t slot);
 
+/* ------------------------------------------------------------------ diagnostics ---- */
+/* One 128 x N x K bf16 tcgen05 product (fp32 accumulate in TMEM) on a single CTA, host in / host out.
+ * Exists so that the tests can pin the shared-memory descriptor encodings the tensor-core kernels
+ * rely on.  mode 0: B is (N,K) row-major (K-major operand); mode 1: B is (K,N) row-major (MN-major
+ * operand).  A is (128+shift, K) row-major and the product uses rows [shift, shift+128).
+ * Synchronises the device.  No reference counterpart. */
+int sf_selftest_umma(int32_t mode, int32_t N, int32_t K, int32_t shift, const float* a_host,
+                     const float* b_host, float* d_host);
+
 #ifdef __cplusplus
 }
 #endif
