@@ -55,7 +55,6 @@ extern "C" int sf_score_windows(const sf_model* m, const float* poses_dev, int64
   if (rc) return rc;
   SF_REQUIRE(B >= 0 && (B == 0 || (poses_dev && scores_dev)), SF_E_INVALID, "sf_score_windows: null buffer");
   SF_REQUIRE(precision == SF_PREC_FP32 || precision == SF_PREC_BF16, SF_E_INVALID, "unknown precision %d", precision);
-  SF_REQUIRE(precision == SF_PREC_FP32, SF_E_UNSUPPORTED, "bf16 tensor-core path is not built into this library version");
   if (B == 0) return SF_OK;
   const int S = token_len(m, T);
   const int64_t tok_bytes = align256(B * (int64_t)S * m->xf.d_tok * (int64_t)sizeof(float));
@@ -70,7 +69,8 @@ extern "C" int sf_score_windows(const sf_model* m, const float* poses_dev, int64
     ws_left -= tok_bytes;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  rc = launch_tokenizer_fp32(m, poses_dev, B, T, tok, ws, ws_left, st);
+  rc = precision == SF_PREC_BF16 ? launch_tokenizer_bf16(m, poses_dev, B, T, tok, st)
+                                 : launch_tokenizer_fp32(m, poses_dev, B, T, tok, ws, ws_left, st);
   if (rc) return rc;
   return launch_transformer_fp32(m, tok, B, S, reduction, recon_dev, scores_dev, st);
 }

@@ -85,6 +85,15 @@ static void bn_fold(Packer& pk, const std::string& p, int n, std::vector<double>
   }
 }
 
+static inline uint16_t f2bf(float f) {       // round-to-nearest-even fp32 -> bf16
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+static inline int pad16(int x) { return (x + 15) & ~15; }
+
 struct LinOff {
   size_t wt, b;
   int K, N;
@@ -287,6 +296,54 @@ extern "C" int sf_model_create(const sf_config* cfg, int32_t n_tensors, const ch
     }
   }
 
+  // ------------------------------------------------------------- bf16 operand images (tcgen05 path)
+  std::vector<uint16_t> bf;                       // 16-byte aligned sections
+  struct BfOff { size_t tcn, gcn, res, gb, ob; int npad, kin; bool has_gcn, has_res; } bfo[kMaxBlocks];
+  auto bf_alloc = [&](size_t n) { size_t o = (bf.size() + 63) & ~size_t(63); bf.resize(o + n, 0); return o; };
+  if (pk.err == SF_OK)
+    for (int i = 0; i < nb; ++i) {
+      const int ci = cfg->channels[i], co = cfg->channels[i + 1];
+      const int npad = pad16(co), kin = i == 0 ? ci : pad16(ci);
+      BfOff& o = bfo[i];
+      o.npad = npad;
+      o.kin = kin;
+      o.has_gcn = i > 0;
+      o.has_res = i > 0 && !bo[i].identity;
+      // temporal conv: chunk (k, jc) -> [n][8], element = Kf[c = jc*8+e][k][n]
+      o.tcn = bf_alloc((size_t)kTaps * npad * npad);
+      for (int k = 0; k < kTaps; ++k)
+        for (int jc = 0; jc < npad / 8; ++jc)
+          for (int n = 0; n < npad; ++n)
+            for (int e = 0; e < 8; ++e) {
+              const int c = jc * 8 + e;
+              const float v = (c < co && n < co) ? pk.arena[bo[i].tw + ((size_t)c * kTaps + k) * co + n] : 0.f;
+              bf[o.tcn + (((size_t)k * (npad / 8) + jc) * npad + n) * 8 + e] = f2bf(v);
+            }
+      auto pack_kn = [&](size_t src, size_t dst) {   // fp32 [c][o] -> chunks [jc][n][8]
+        for (int jc = 0; jc < kin / 8; ++jc)
+          for (int n = 0; n < npad; ++n)
+            for (int e = 0; e < 8; ++e) {
+              const int c = jc * 8 + e;
+              bf[dst + ((size_t)jc * npad + n) * 8 + e] = f2bf((c < ci && n < co) ? pk.arena[src + (size_t)c * co + n] : 0.f);
+            }
+      };
+      o.gcn = o.res = 0;
+      if (o.has_gcn) {
+        o.gcn = bf_alloc((size_t)kin * npad);
+        pack_kn(bo[i].gw, o.gcn);
+      }
+      if (o.has_res) {
+        o.res = bf_alloc((size_t)kin * npad);
+        pack_kn(bo[i].rw, o.res);
+      }
+      o.gb = pk.alloc(npad);
+      o.ob = pk.alloc(npad);
+      for (int n = 0; n < co; ++n) {
+        pk.arena[o.gb + n] = pk.arena[bo[i].gb + n];
+        pk.arena[o.ob + n] = pk.arena[bo[i].ob + n];
+      }
+    }
+
   // ------------------------------------------------------------- transformer
   const std::string tp = "transformer.";
   const bool v1 = cfg->variant == SF_VARIANT_SHOPFORMER;
@@ -352,7 +409,28 @@ extern "C" int sf_model_create(const sf_config* cfg, int32_t n_tensors, const ch
     delete m;
     return SF_E_CUDA;
   }
+  m->arena_bf16 = nullptr;
+  m->arena_bf16_bytes = bf.size() * sizeof(uint16_t);
+  e = cudaMalloc((void**)&m->arena_bf16, m->arena_bf16_bytes + 256);
+  if (e == cudaSuccess) e = cudaMemcpy(m->arena_bf16, bf.data(), m->arena_bf16_bytes, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    set_error("uploading %zu bytes of bf16 operand images failed: %s", m->arena_bf16_bytes, cudaGetErrorString(e));
+    cudaFree(m->arena);
+    if (m->arena_bf16) cudaFree(m->arena_bf16);
+    delete m;
+    return SF_E_CUDA;
+  }
   const float* A = m->arena;
+  for (int i = 0; i < nb; ++i) {
+    BfBlockW& w = m->tokbf.blk[i];
+    w.tcn = m->arena_bf16 + bfo[i].tcn;
+    w.gcn = bfo[i].has_gcn ? m->arena_bf16 + bfo[i].gcn : nullptr;
+    w.res = bfo[i].has_res ? m->arena_bf16 + bfo[i].res : nullptr;
+    w.gcn_b = A + bfo[i].gb;
+    w.out_b = A + bfo[i].ob;
+    w.npad = bfo[i].npad;
+    w.kin_pad = bfo[i].kin;
+  }
   auto lin = [&](const LinOff& o) { return Linear{A + o.wt, A + o.b, o.K, o.N}; };
   auto nrm = [&](const NormOff& o) { return Norm{A + o.g, A + o.b}; };
   auto att = [&](const AttnOff& o) { return Attn{lin(o.qkv), lin(o.out)}; };
@@ -405,6 +483,7 @@ extern "C" void sf_model_destroy(sf_model* m) {
   if (!m) return;
   cudaSetDevice(m->device);
   if (m->arena) cudaFree(m->arena);
+  if (m->arena_bf16) cudaFree(m->arena_bf16);
   delete m;
 }
 

@@ -93,6 +93,23 @@ static_assert(sizeof(Tokenizer) <= 3800, "Tokenizer must fit in kernel parameter
 
 }  // namespace sf
 
+namespace sf {
+// bf16 operand images of the tokenizer for the tcgen05 path, pre-packed in the exact shared-memory
+// layout the MMA descriptors expect ([K chunk of 8][N row][8], see tc_common.cuh) so that staging is
+// a straight 16-byte copy.  Channel counts are padded up to multiples of 16 with zeros.
+struct BfBlockW {
+  const uint16_t* tcn;      // [9 taps x npad/8 chunks][npad][8]   BN-folded temporal conv
+  const uint16_t* gcn;      // [kin_pad/8][npad][8]                graph-conv weight (nullptr for block 0)
+  const uint16_t* res;      // [kin_pad/8][npad][8]                folded 1x1 residual (nullptr if identity / block 0)
+  const float* gcn_b;       // [npad] zero padded
+  const float* out_b;       // [npad] zero padded
+  int npad, kin_pad;
+};
+struct BfTokenizerW {
+  BfBlockW blk[kMaxBlocks];
+};
+}  // namespace sf
+
 struct sf_model {
   sf_config cfg;
   int device;
@@ -102,6 +119,9 @@ struct sf_model {
   size_t arena_bytes;
   sf::Tokenizer tok;
   sf::Transformer xf;
+  uint16_t* arena_bf16;     // bf16 operand images (tcgen05 path)
+  size_t arena_bf16_bytes;
+  sf::BfTokenizerW tokbf;
 };
 
 namespace sf {
@@ -114,4 +134,7 @@ int launch_transformer_fp32(const sf_model* m, const float* tokens, int64_t B, i
 int launch_score(const sf_model* m, const float* tokens, const float* recon, int64_t B, int S,
                  int reduction, float* scores, cudaStream_t st);
 int token_len(const sf_model* m, int T);
+// bf16 tcgen05 tokenizer (returns SF_E_UNSUPPORTED for shapes it does not cover)
+int launch_tokenizer_bf16(const sf_model* m, const float* poses, int64_t B, int T, float* tokens, cudaStream_t st);
+bool tokenizer_bf16_supported(const sf_model* m, int T);
 }  // namespace sf

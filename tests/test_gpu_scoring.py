@@ -188,3 +188,61 @@ def test_errors_are_loud(dropin1, dropin2):
     eng = model._sf_engine()
     with pytest.raises(NativeError):
         eng.tokenize(torch.zeros(1, 2, 5000, 17, device="cuda"))                   # T outside the supported range
+
+
+# ----------------------------------------------------------------------------------- bf16 tcgen05 path
+BF16_TOL = 1e-2          # north-star tolerance for the bf16 path (relative error of the score)
+
+
+@pytest.mark.parametrize("name", ["A", "A12", "B"])
+def test_bf16_tensor_core_path_matches_reference(name, golden_dir, dropin1, dropin2):
+    g = np.load(golden_dir / f"score_{name}.npz")
+    model = build_model(dropin1, dropin2, name).cuda()
+    x = torch.from_numpy(g["poses"]).cuda()
+    eng = model._sf_engine()
+    s, tok, rec = eng.score_windows(x, precision="bf16", return_tokens=True, return_recon=True)
+    n = g["tokens64"].shape[0]
+    tok_err = max_abs_rel(tok[:n].cpu().numpy(), g["tokens64"])
+    s_err = rel_err(s.cpu().numpy(), g["score64"])
+    print(f"[bf16 {name}] tokens max|d|/max|ref| = {tok_err:.3e}, score max rel = {s_err:.3e}")
+    assert tok_err < 2e-2
+    assert s_err < BF16_TOL
+    # fp32 path on the same inputs stays the precise one
+    assert rel_err(eng.score_windows(x, precision="fp32").cpu().numpy(), g["score64"]) < FP32_TOL
+
+
+def test_bf16_path_ragged_and_deterministic(dropin1, dropin2):
+    model = build_model(dropin1, dropin2, "A", seed=3)
+    xs, _ = synth_windows(1203, 24, 17, seed=77)
+    ref = O.score_windows(model.state_dict(), torch.from_numpy(xs), dtype=torch.float64, **oracle_kwargs(model, "A"))
+    model = model.cuda()
+    eng = model._sf_engine()
+    x = torch.from_numpy(xs).cuda()
+    s = eng.score_windows(x, precision="bf16")
+    assert rel_err(s.cpu().numpy(), ref["score"].numpy()) < BF16_TOL
+    assert torch.equal(s, eng.score_windows(x, precision="bf16"))
+    perm = torch.randperm(1203, device="cuda", generator=torch.Generator("cuda").manual_seed(1))
+    assert torch.equal(eng.score_windows(x[perm], precision="bf16"), s[perm])
+    assert torch.equal(eng.score_windows(x[:1], precision="bf16"), s[:1])
+
+
+def test_bf16_path_trained_checkpoint_ranking(golden_dir, dropin1):
+    from scipy.stats import spearmanr
+    g = np.load(golden_dir / "trained_A.npz")
+    model = dropin1["models"].Shopformer(**CFG.ctor_args("A"))
+    model.load_state_dict({k[4:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd::")}, strict=True)
+    model = model.cuda().eval()
+    s = model._sf_engine().score_windows(torch.from_numpy(g["poses"]).cuda(), precision="bf16").cpu().numpy()
+    gold = g["score64"]
+    err = rel_err(s, gold)
+    rho = spearmanr(s, gold).statistic
+    auc_gold = dropin1["metrics"].compute_metrics(g["labels"], gold)["auc_roc"]
+    auc_ours = dropin1["metrics"].compute_metrics(g["labels"], s)["auc_roc"]
+    print(f"[bf16 trained A] max rel {err:.3e}  spearman {rho:.6f}  auc {auc_ours:.6f} vs {auc_gold:.6f}")
+    assert err < BF16_TOL and rho > 0.999 and abs(auc_gold - auc_ours) < 1e-3
+
+
+def test_bf16_unsupported_shapes_are_loud(dropin1, dropin2):
+    model = build_model(dropin1, dropin2, "P").cuda()          # adaptive pooling: not on the tensor-core path
+    with pytest.raises(NativeError, match="SF_E_UNSUPPORTED"):
+        model._sf_engine().score_windows(torch.zeros(2, 2, 24, 17, device="cuda"), precision="bf16")
