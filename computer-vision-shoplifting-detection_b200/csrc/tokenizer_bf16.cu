@@ -7,13 +7,16 @@
 //     rows = (window, time, keypoint), columns = channels; accumulators live in TMEM (fp32);
 //   * the 9x1 temporal convolution is an implicit GEMM: the input of a stride-s block is stored split
 //     into s time phases, so tap k is a SHIFTED VIEW (row offset o_k * V) of phase (k-4) mod s -- nine
-//     smem descriptors into one buffer, no im2col, zero rows ("gaps") between windows give the padding;
+//     smem descriptors into one buffer, no im2col; zero rows ("gaps") between windows give the padding;
 //     taps that can only ever hit padding are skipped;
 //   * the BN-folded 1x1 strided residual conv is two more MMAs into the same accumulator (phase 0 of x);
-//   * graph conv = adjacency mix over keypoints on CUDA cores (bf16 rows in smem) followed by a
-//     [rows x Cin] x [Cin x Cout] tensor-core GEMM; block 0 (Cin = 2) is rebuilt on CUDA cores in fp32;
+//   * graph conv = adjacency mix over keypoints on CUDA cores (bf16 rows in smem, fp32 accumulate)
+//     followed by a [rows x Cin] x [Cin x Cout] tensor-core GEMM; block 0 (Cin = 2) is rebuilt on CUDA
+//     cores in fp32 with its weights held in registers;
 //   * epilogues read TMEM with tcgen05.ld, add the folded bias, ReLU, and write the next operand
-//     straight back to shared memory as bf16 -- nothing but the final tokens (fp32) goes to HBM.
+//     straight back to shared memory as bf16 -- nothing but the final tokens (fp32) goes to HBM;
+//   * every row -> (window, time, keypoint) decode is a shared-memory table built once per CTA, biases
+//     and the block-0 weights are staged once per CTA, MMA issue is spread over four warps.
 //
 // One CTA owns G windows at a time (persistent); phases are separated by mbarrier (MMA completion) and
 // __syncthreads; two CTAs per SM overlap one CTA's MMAs with the other's CUDA-core phases.
@@ -29,6 +32,9 @@ namespace {
 using namespace tc;
 
 constexpr int kThreads = 256;
+constexpr int kIssuers = 4;          // lane 0 of warps 0..3 issue the MMAs of tiles t = warp (mod 4)
+constexpr int kEllMax = 8;
+constexpr uint16_t kGap = 0xFFFF;
 
 struct BfBlk {
   int cin, kin, npad, cout;            // real / padded input channels, padded / real output channels
@@ -42,13 +48,16 @@ struct BfBlk {
   const uint16_t *w_tcn, *w_gcn, *w_res;
   const float *gcn_b, *out_b;          // [npad], zero padded
   const float *gcn_w32, *res_w32;      // block 0 only: fp32 [cin][cout]
+  uint32_t off_rowtab, off_mtab;       // smem tables (uint16)
 };
 
 struct BfPlan {
   int n_blocks, V, c_in, G, T0, S_out, c_last;
   const float *in_scale, *in_shift;
   BfBlk blk[kMaxBlocks];
-  uint32_t off_A, off_X0, off_X1, off_WT, off_WG, off_x0, off_m0, smem_bytes, tmem_cols;
+  uint32_t off_A, off_X0, off_X1, off_WT, off_WG, off_x0, off_m0;
+  uint32_t off_xrtab, off_xjtab, off_bias_g, off_bias_o, off_w0, off_r0, off_ellv, off_elld, off_scale, off_shift;
+  uint32_t smem_bytes, tmem_cols;
 };
 static_assert(sizeof(BfPlan) <= 3900, "BfPlan must fit in kernel parameter space");
 
@@ -62,23 +71,25 @@ __device__ __forceinline__ void stage(unsigned char* dst, const uint16_t* src, i
   const unsigned char* s = reinterpret_cast<const unsigned char*>(src);
   for (int i = threadIdx.x * 16; i < bytes; i += kThreads * 16) cp_async16(dst + i, s + i);
 }
-
-// decode a row of one phase buffer: returns false for gap rows
-__device__ __forceinline__ bool decode_row(const BfBlk& b, int V, int rloc, int& w, int& t, int& v) {
-  const int rr = rloc - b.gap * V;
-  if (rr < 0) return false;
-  const int slotV = b.slot * V;
-  w = rr / slotV;
-  const int q = rr - w * slotV;
-  if (q >= b.Tout * V) return false;
-  t = q / V;
-  v = q - t * V;
-  return true;
-}
-
 __device__ __forceinline__ void zero_fill(unsigned char* p, int bytes) {
   uint4* q = reinterpret_cast<uint4*>(p);
   for (int i = threadIdx.x; i < (bytes >> 4); i += kThreads) q[i] = make_uint4(0, 0, 0, 0);
+}
+// descriptor with separately tracked low word: advancing an operand is one 32-bit add
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr >> 4) & 0x3FFFu) | ((lbo_bytes >> 4) << 16);
+}
+__device__ __forceinline__ uint64_t desc_join(uint32_t lo) {      // SBO = 128 B, version 1
+  return ((uint64_t)((128u >> 4) | (1u << 14)) << 32) | lo;
+}
+__device__ __forceinline__ void unpack8(const uint4& q, float* f) {
+  f[0] = __uint_as_float(q.x << 16); f[1] = __uint_as_float(q.x & 0xFFFF0000u);
+  f[2] = __uint_as_float(q.y << 16); f[3] = __uint_as_float(q.y & 0xFFFF0000u);
+  f[4] = __uint_as_float(q.z << 16); f[5] = __uint_as_float(q.z & 0xFFFF0000u);
+  f[6] = __uint_as_float(q.w << 16); f[7] = __uint_as_float(q.w & 0xFFFF0000u);
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
 }
 
 __global__ void __launch_bounds__(kThreads, 2)
@@ -93,14 +104,93 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
   unsigned char* sWG = smem + pl.off_WG;
   float* x0 = reinterpret_cast<float*>(smem + pl.off_x0);      // [G][c_in][T0][V] fp32, BN folded
   float* m0 = reinterpret_cast<float*>(smem + pl.off_m0);      // adjacency-mixed copy
+  const uint16_t* xrtab = reinterpret_cast<const uint16_t*>(smem + pl.off_xrtab);   // block-0 residual source per M row
+  const uint8_t* xjtab = reinterpret_cast<const uint8_t*>(smem + pl.off_xjtab);     // c*V+v of every x0 element
+  const float* bias_g = reinterpret_cast<const float*>(smem + pl.off_bias_g);       // [blk][64]
+  const float* bias_o = reinterpret_cast<const float*>(smem + pl.off_bias_o);
+  const float* w0s = reinterpret_cast<const float*>(smem + pl.off_w0);              // [4][64]
+  const float* r0s = reinterpret_cast<const float*>(smem + pl.off_r0);              // [4][64]
+  const float* ellv = reinterpret_cast<const float*>(smem + pl.off_ellv);           // [blk][V][kEllMax]
+  const int* elld = reinterpret_cast<const int*>(smem + pl.off_elld);               // row delta (u - v)
+  const float* scale_s = reinterpret_cast<const float*>(smem + pl.off_scale);
+  const float* shift_s = reinterpret_cast<const float*>(smem + pl.off_shift);
   const int V = pl.V, G = pl.G;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int lane_grp = warp & 3, col_half = warp >> 2;
+  const int per_w = pl.c_in * pl.T0 * V;
 
+  // ------------------------------------------------------------------ one-time setup
   if (warp == 0) tmem_alloc(&tmem_base_s, pl.tmem_cols);
   if (threadIdx.x == 0) {
-    mbar_init(&bar, 1);
+    mbar_init(&bar, kIssuers);
     fence_mbar_init();
+  }
+  for (int bi = 0; bi < pl.n_blocks; ++bi) {
+    const BfBlk& b = pl.blk[bi];
+    uint16_t* rt = reinterpret_cast<uint16_t*>(smem + b.off_rowtab);
+    uint16_t* mt = reinterpret_cast<uint16_t*>(smem + b.off_mtab);
+    const int slotV = b.slot * V;
+    for (int r = threadIdx.x; r < b.rtot; r += kThreads) {          // row of the phase-split input buffer
+      const int ph = r / b.rows, rr = r - ph * b.rows - b.gap * V;
+      uint16_t e = kGap;
+      if (rr >= 0) {
+        const int w = rr / slotV, q = rr - w * slotV;
+        if (q < b.Tout * V) {
+          const int t2 = q / V, v = q - t2 * V;
+          e = (uint16_t)(v | ((b.stride * t2 + ph) << 5) | (w << 11));       // v, input time index, window
+        }
+      }
+      rt[r] = e;
+    }
+    const bool last = bi + 1 == pl.n_blocks;
+    for (int mrow = threadIdx.x; mrow < b.mrows; mrow += kThreads) {         // row of the conv output (M space)
+      const int w = mrow / slotV, q = mrow - w * slotV;
+      uint16_t e = kGap;
+      if (q < b.Tout * V) {
+        const int t = q / V, v = q - t * V;
+        int target;
+        if (!last) {
+          const BfBlk& nb = pl.blk[bi + 1];
+          target = (t % nb.stride) * nb.rows + nb.gap * V + w * nb.slot * V + (t / nb.stride) * V + v;
+        } else {
+          target = t * (pl.c_last * V) + v;                                   // offset inside the window's tokens
+        }
+        e = (uint16_t)(target | (w << 11));
+        if (bi == 0) reinterpret_cast<uint16_t*>(smem + pl.off_xrtab)[mrow] = (uint16_t)(w * per_w + (b.stride * t) * V + v);
+      }
+      mt[mrow] = e;
+    }
+    float* bg = reinterpret_cast<float*>(smem + pl.off_bias_g) + bi * 64;
+    float* bo = reinterpret_cast<float*>(smem + pl.off_bias_o) + bi * 64;
+    for (int i = threadIdx.x; i < 64; i += kThreads) {
+      bg[i] = i < b.npad ? __ldg(b.gcn_b + i) : 0.f;
+      bo[i] = i < b.npad ? __ldg(b.out_b + i) : 0.f;
+    }
+    float* ev = reinterpret_cast<float*>(smem + pl.off_ellv) + bi * V * kEllMax;
+    int* ed = reinterpret_cast<int*>(smem + pl.off_elld) + bi * V * kEllMax;
+    for (int i = threadIdx.x; i < V * kEllMax; i += kThreads) {
+      const int v = i / kEllMax, k = i % kEllMax;
+      const bool ok = k < b.ell_width;
+      ev[i] = ok ? __ldg(b.ell_val + v * b.ell_width + k) : 0.f;
+      ed[i] = ok ? __ldg(b.ell_col + v * b.ell_width + k) - v : 0;
+    }
+  }
+  {
+    const BfBlk& b0 = pl.blk[0];
+    for (int i = threadIdx.x; i < 4 * 64; i += kThreads) {
+      const int ci = i >> 6, c = i & 63;
+      const bool ok = ci < b0.cin && c < b0.cout;
+      reinterpret_cast<float*>(smem + pl.off_w0)[i] = ok ? __ldg(b0.gcn_w32 + ci * b0.cout + c) : 0.f;
+      reinterpret_cast<float*>(smem + pl.off_r0)[i] = ok ? __ldg(b0.res_w32 + ci * b0.cout + c) : 0.f;
+    }
+    for (int i = threadIdx.x; i < pl.c_in * V; i += kThreads) {
+      reinterpret_cast<float*>(smem + pl.off_scale)[i] = __ldg(pl.in_scale + i);
+      reinterpret_cast<float*>(smem + pl.off_shift)[i] = __ldg(pl.in_shift + i);
+    }
+    for (int i = threadIdx.x; i < G * per_w; i += kThreads) {
+      const int r = i % per_w;
+      reinterpret_cast<uint8_t*>(smem + pl.off_xjtab)[i] = (uint8_t)((r / (pl.T0 * V)) * V + r % V);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -108,67 +198,73 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
   const uint32_t tmem = tmem_base_s;
   uint32_t parity = 0;
 
+  // block-0 graph-conv weights of this thread's 8-channel chunk stay in registers for the whole kernel
+  const int chunks0 = pl.blk[0].npad >> 3;
+  const int tpc0 = kThreads / chunks0;                  // threads per chunk
+  const int j0 = threadIdx.x / tpc0, r0_first = threadIdx.x - j0 * tpc0;
+  float gw[4][8], gb[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    gb[e] = bias_g[j0 * 8 + e];
+#pragma unroll
+    for (int ci = 0; ci < 4; ++ci) gw[ci][e] = w0s[ci * 64 + j0 * 8 + e];
+  }
+
   const int64_t n_groups = (B + G - 1) / G;
   for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
     const int64_t w_first = grp * G;
     const int nw = (int)((B - w_first) < (int64_t)G ? (B - w_first) : (int64_t)G);
 
-    // =============================== block 0 ===============================
+    // =============================== block 0 prologue ===============================
     {
       const BfBlk& b = pl.blk[0];
       stage(sWT, b.w_tcn, kTaps * b.npad * b.npad * 2);
-      // x0 <- folded BN1d(poses); windows beyond the batch end are zero
-      const int per_w = pl.c_in * pl.T0 * V;
+      const float* src = poses + (size_t)w_first * per_w;
+      const int n_valid = nw * per_w;
       for (int i = threadIdx.x; i < G * per_w; i += kThreads) {
-        const int w = i / per_w, r = i - w * per_w;
-        const int v = r % V, c = r / (pl.T0 * V);
-        const int j = c * V + v;
-        x0[i] = w < nw ? fmaf(__ldg(poses + (size_t)(w_first + w) * per_w + r), __ldg(pl.in_scale + j), __ldg(pl.in_shift + j)) : 0.f;
+        const int j = xjtab[i];
+        x0[i] = i < n_valid ? fmaf(__ldg(src + i), scale_s[j], shift_s[j]) : 0.f;
       }
+      if (pl.n_blocks > 1) zero_fill(sX[0], pl.blk[1].rtot * pl.blk[1].kin * 2);
       __syncthreads();
       // m0 <- A_hat . x0 over the keypoint axis
       for (int i = threadIdx.x; i < G * per_w; i += kThreads) {
-        const int v = i % V;
-        const float* row = x0 + (i - v);
+        const int j = xjtab[i];
+        const int v = j % V;
         float a = 0.f;
-        for (int e = 0; e < b.ell_width; ++e) a = fmaf(__ldg(b.ell_val + v * b.ell_width + e), row[__ldg(b.ell_col + v * b.ell_width + e)], a);
+#pragma unroll
+        for (int k = 0; k < kEllMax; ++k) {
+          const float val = ellv[v * kEllMax + k];
+          if (k < b.ell_width) a = fmaf(val, x0[i + elld[v * kEllMax + k]], a);
+        }
         m0[i] = a;
       }
-      // next block's input buffer: gaps must be zero
-      if (pl.n_blocks > 1) zero_fill(sX[0], pl.blk[1].rtot * pl.blk[1].kin * 2);
       __syncthreads();
-      // g0 = relu(W0 . m0 + b0) -> bf16, phase-split rows, 8 channels (one 16-byte granule) per item
-      {
-        const int chunks = b.npad >> 3;
-        const int items = b.rtot * chunks;
-        for (int it = threadIdx.x; it < items; it += kThreads) {
-          const int r = it % b.rtot, j = it / b.rtot;
-          const int ph = r / b.rows, rloc = r - ph * b.rows;
-          int w, t2, v;
-          uint4 out = make_uint4(0, 0, 0, 0);
-          if (decode_row(b, V, rloc, w, t2, v) && w < nw) {
-            const int t = b.stride * t2 + ph;
-            float mv[4];
+      // g0 = relu(W0 . m0 + b0) -> bf16 rows of the phase-split operand buffer; one 16-byte granule per item
+      const uint16_t* rt = reinterpret_cast<const uint16_t*>(smem + b.off_rowtab);
+      const int tv = pl.T0 * V;
+      unsigned char* dstp = sA + (size_t)j0 * b.rtot * 16;
+      for (int r = r0_first; r < b.rtot; r += tpc0) {
+        const uint32_t e = rt[r];
+        uint4 out = make_uint4(0, 0, 0, 0);
+        if (e != kGap && (int)(e >> 11) < nw) {
+          const int v = e & 31, t = (e >> 5) & 63, w = e >> 11;
+          const float* mp = m0 + w * per_w + t * V + v;
+          float g[8];
 #pragma unroll
-            for (int ci = 0; ci < 4; ++ci) mv[ci] = ci < b.cin ? m0[((w * pl.c_in + ci) * pl.T0 + t) * V + v] : 0.f;
-            float g[8];
+          for (int q = 0; q < 8; ++q) g[q] = gb[q];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int c = j * 8 + e;
-              float a = 0.f;
-              if (c < b.cout) {
-                a = __ldg(b.gcn_b + c);
+          for (int ci = 0; ci < 4; ++ci)
+            if (ci < b.cin) {
+              const float mv = mp[ci * tv];
 #pragma unroll
-                for (int ci = 0; ci < 4; ++ci)
-                  if (ci < b.cin) a = fmaf(__ldg(b.gcn_w32 + ci * b.cout + c), mv[ci], a);
-                a = fmaxf(a, 0.f);
-              }
-              g[e] = a;
+              for (int q = 0; q < 8; ++q) g[q] = fmaf(gw[ci][q], mv, g[q]);
             }
-            out = make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]), pack_bf16x2(g[4], g[5]), pack_bf16x2(g[6], g[7]));
-          }
-          *reinterpret_cast<uint4*>(sA + ((size_t)j * b.rtot + r) * 16) = out;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) g[q] = fmaxf(g[q], 0.f);
+          out = pack8(g);
         }
+        *reinterpret_cast<uint4*>(dstp + (size_t)r * 16) = out;
       }
     }
 
@@ -178,6 +274,11 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
       unsigned char* sXout = sX[bi & 1];           // x_{b+1}
       const uint32_t planeA = (uint32_t)b.rtot * 16u;
       const int dcol = b.npad < 32 ? 32 : b.npad;   // TMEM column stride between accumulator tiles
+      const uint16_t* rt = reinterpret_cast<const uint16_t*>(smem + b.off_rowtab);
+      const uint16_t* mt = reinterpret_cast<const uint16_t*>(smem + b.off_mtab);
+      const int groups = b.npad >> 4;               // 16-column groups per accumulator tile
+      const int g_first = groups > 1 ? col_half : 0, g_step = groups > 1 ? 2 : 1;
+      const bool idle_half = groups == 1 && col_half == 1;
       if (bi > 0) {
         // ---- stage this block's weights, clear the output buffer, adjacency mix x_b -> A (bf16)
         stage(sWG, b.w_gcn, b.kin * b.npad * 2);
@@ -186,32 +287,35 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
         if (bi + 1 < pl.n_blocks) zero_fill(sXout, pl.blk[bi + 1].rtot * pl.blk[bi + 1].kin * 2);
         {
           const int chunks = b.kin >> 3;
-          const int items = b.rtot * chunks;
-          for (int it = threadIdx.x; it < items; it += kThreads) {
-            const int r = it % b.rtot, j = it / b.rtot;
-            const int ph = r / b.rows, rloc = r - ph * b.rows;
-            int w, t2, v;
+          const int tpc = kThreads / chunks;
+          const int j = threadIdx.x / tpc;
+          const unsigned char* plane = sXin + (size_t)j * planeA;
+          unsigned char* dstp = sA + (size_t)j * planeA;
+          const float* ev = ellv + bi * V * kEllMax;
+          const int* ed = elld + bi * V * kEllMax;
+          for (int r = threadIdx.x - j * tpc; r < b.rtot; r += tpc) {
+            const uint32_t e = rt[r];
             uint4 out = make_uint4(0, 0, 0, 0);
-            if (decode_row(b, V, rloc, w, t2, v)) {
+            if (e != kGap) {
+              const int v = e & 31;
               float a[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) a[e] = 0.f;
-              const unsigned char* plane = sXin + (size_t)j * planeA;
-              for (int e2 = 0; e2 < b.ell_width; ++e2) {
-                const float val = __ldg(b.ell_val + v * b.ell_width + e2);
-                const int u = __ldg(b.ell_col + v * b.ell_width + e2);
-                const uint4 q = *reinterpret_cast<const uint4*>(plane + (size_t)(r + u - v) * 16);
-                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+              for (int q = 0; q < 8; ++q) a[q] = 0.f;
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 f = __bfloat1622float2(h[e]);
-                  a[2 * e] = fmaf(val, f.x, a[2 * e]);
-                  a[2 * e + 1] = fmaf(val, f.y, a[2 * e + 1]);
+              for (int k = 0; k < kEllMax; ++k) {
+                if (k < b.ell_width) {
+                  const float val = ev[v * kEllMax + k];
+                  if (val != 0.f) {
+                    float f[8];
+                    unpack8(*reinterpret_cast<const uint4*>(plane + (size_t)(r + ed[v * kEllMax + k]) * 16), f);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) a[q] = fmaf(val, f[q], a[q]);
+                  }
                 }
               }
-              out = make_uint4(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]), pack_bf16x2(a[4], a[5]), pack_bf16x2(a[6], a[7]));
+              out = pack8(a);
             }
-            *reinterpret_cast<uint4*>(sA + ((size_t)j * b.rtot + r) * 16) = out;
+            *reinterpret_cast<uint4*>(dstp + (size_t)r * 16) = out;
           }
         }
         cp_async_wait_all();
@@ -220,15 +324,19 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
         __syncthreads();
         // ---- P = M . W  (all rows of all phases), accumulators in TMEM
         const int p_tiles = (b.rtot + 127) >> 7;
-        if (threadIdx.x == 0) {
+        if (lane == 0 && warp < kIssuers) {
           tc_fence_after();
           const uint32_t idesc = make_idesc(128, b.npad, false);
-          const uint64_t bdesc0 = make_desc(smem_u32(sWG), (uint32_t)b.npad * 16u, 128u);
-          for (int tile = 0; tile < p_tiles; ++tile) {
-            const uint64_t adesc0 = make_desc(smem_u32(sA) + (uint32_t)tile * 2048u, planeA, 128u);
-            for (int ks = 0; ks < (b.kin >> 4); ++ks)
-              umma_bf16(tmem + (uint32_t)(tile * dcol), desc_advance(adesc0, (uint32_t)ks * 2u * planeA),
-                        desc_advance(bdesc0, (uint32_t)ks * 2u * (uint32_t)b.npad * 16u), idesc, ks > 0);
+          const uint32_t w_plane = (uint32_t)b.npad * 16u;
+          const uint32_t blo0 = desc_lo(smem_u32(sWG), w_plane);
+          for (int tile = warp; tile < p_tiles; tile += kIssuers) {
+            uint32_t alo = desc_lo(smem_u32(sA) + (uint32_t)tile * 2048u, planeA);
+            uint32_t blo = blo0;
+            for (int ks = 0; ks < (b.kin >> 4); ++ks) {
+              umma_bf16(tmem + (uint32_t)(tile * dcol), desc_join(alo), desc_join(blo), idesc, ks > 0);
+              alo += (2u * planeA) >> 4;
+              blo += (2u * w_plane) >> 4;
+            }
           }
           umma_commit(&bar);
         }
@@ -236,27 +344,28 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
         parity ^= 1;
         tc_fence_after();
         // ---- g = relu(P + b) -> bf16 over M in place (gap rows -> 0)
+        const float* bgp = bias_g + bi * 64;
         for (int tile = 0; tile < p_tiles; ++tile) {
           const int r = tile * 128 + lane_grp * 32 + lane;
-          const int ph = r / b.rows, rloc = r - ph * b.rows;
-          int w, t2, v;
-          const bool data = r < b.rtot && decode_row(b, V, rloc, w, t2, v);
-          const int groups = b.npad >> 4;
-          for (int gq = (groups > 1 ? col_half : 0); gq < groups; gq += (groups > 1 ? 2 : 1)) {
-            if (groups == 1 && col_half) break;
+          const bool in = r < b.rtot;
+          const bool data = in && rt[r] != kGap;
+          if (idle_half) break;
+          for (int gq = g_first; gq < groups; gq += g_step) {
             float acc[16];
             tmem_ld16(tmem + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(tile * dcol + gq * 16), acc);
             tmem_ld_wait();
-            if (r < b.rtot) {
-              uint32_t pk[8];
+            if (in) {
+              float y[16];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const float lo = data ? fmaxf(acc[2 * e] + __ldg(b.gcn_b + gq * 16 + 2 * e), 0.f) : 0.f;
-                const float hi = data ? fmaxf(acc[2 * e + 1] + __ldg(b.gcn_b + gq * 16 + 2 * e + 1), 0.f) : 0.f;
-                pk[e] = pack_bf16x2(lo, hi);
+              for (int q4 = 0; q4 < 4; ++q4) {
+                const float4 bb = *reinterpret_cast<const float4*>(bgp + gq * 16 + q4 * 4);
+                y[q4 * 4 + 0] = data ? fmaxf(acc[q4 * 4 + 0] + bb.x, 0.f) : 0.f;
+                y[q4 * 4 + 1] = data ? fmaxf(acc[q4 * 4 + 1] + bb.y, 0.f) : 0.f;
+                y[q4 * 4 + 2] = data ? fmaxf(acc[q4 * 4 + 2] + bb.z, 0.f) : 0.f;
+                y[q4 * 4 + 3] = data ? fmaxf(acc[q4 * 4 + 3] + bb.w, 0.f) : 0.f;
               }
-              *reinterpret_cast<uint4*>(sA + ((size_t)(gq * 2) * b.rtot + r) * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-              *reinterpret_cast<uint4*>(sA + ((size_t)(gq * 2 + 1) * b.rtot + r) * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+              *reinterpret_cast<uint4*>(sA + ((size_t)(gq * 2) * b.rtot + r) * 16) = pack8(y);
+              *reinterpret_cast<uint4*>(sA + ((size_t)(gq * 2 + 1) * b.rtot + r) * 16) = pack8(y + 8);
             }
           }
         }
@@ -268,30 +377,35 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
       __syncthreads();
       // ---- temporal conv (+ residual conv) as shifted-view MMAs
       const int m_tiles = (b.mrows + 127) >> 7;
-      if (threadIdx.x == 0) {
+      if (lane == 0 && warp < kIssuers) {
         tc_fence_after();
         const uint32_t idesc = make_idesc(128, b.npad, false);
         const uint32_t w_plane = (uint32_t)b.npad * 16u;
         const int ksteps = b.npad >> 4;
-        for (int tile = 0; tile < m_tiles; ++tile) {
+        const uint32_t a_base = smem_u32(sA), w_base = smem_u32(sWT);
+        for (int tile = warp; tile < m_tiles; tile += kIssuers) {
           const uint32_t d = tmem + (uint32_t)(tile * dcol);
           uint32_t acc_flag = 0;
           for (int tp = 0; tp < b.n_taps; ++tp) {
             const int row0 = b.tap_phase[tp] * b.rows + b.gap * V + tile * 128 + b.tap_rowoff[tp];
-            const uint64_t adesc0 = make_desc(smem_u32(sA) + (uint32_t)row0 * 16u, planeA, 128u);
-            const uint64_t bdesc0 = make_desc(smem_u32(sWT) + (uint32_t)(b.tap_k[tp] * (b.npad >> 3)) * w_plane, w_plane, 128u);
+            uint32_t alo = desc_lo(a_base + (uint32_t)row0 * 16u, planeA);
+            uint32_t blo = desc_lo(w_base + (uint32_t)(b.tap_k[tp] * (b.npad >> 3)) * w_plane, w_plane);
             for (int ks = 0; ks < ksteps; ++ks) {
-              umma_bf16(d, desc_advance(adesc0, (uint32_t)ks * 2u * planeA), desc_advance(bdesc0, (uint32_t)ks * 2u * w_plane), idesc, acc_flag);
+              umma_bf16(d, desc_join(alo), desc_join(blo), idesc, acc_flag);
               acc_flag = 1;
+              alo += (2u * planeA) >> 4;
+              blo += (2u * w_plane) >> 4;
             }
           }
           if (bi > 0 && !b.identity_res) {
-            const uint32_t planeX = planeA;     // x_b shares the block's row geometry
             const int row0 = b.gap * V + tile * 128;                       // phase 0, offset 0: x[s*t']
-            const uint64_t adesc0 = make_desc(smem_u32(sXin) + (uint32_t)row0 * 16u, planeX, 128u);
-            const uint64_t bdesc0 = make_desc(smem_u32(sWT) + (uint32_t)(kTaps * b.npad * b.npad * 2), w_plane, 128u);
-            for (int ks = 0; ks < (b.kin >> 4); ++ks)
-              umma_bf16(d, desc_advance(adesc0, (uint32_t)ks * 2u * planeX), desc_advance(bdesc0, (uint32_t)ks * 2u * w_plane), idesc, 1u);
+            uint32_t alo = desc_lo(smem_u32(sXin) + (uint32_t)row0 * 16u, planeA);   // x_b shares the block's geometry
+            uint32_t blo = desc_lo(w_base + (uint32_t)(kTaps * b.npad * b.npad * 2), w_plane);
+            for (int ks = 0; ks < (b.kin >> 4); ++ks) {
+              umma_bf16(d, desc_join(alo), desc_join(blo), idesc, 1u);
+              alo += (2u * planeA) >> 4;
+              blo += (2u * w_plane) >> 4;
+            }
           }
         }
         umma_commit(&bar);
@@ -301,61 +415,59 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
       tc_fence_after();
       // ---- x_{b+1} = relu(acc + bias + residual): bf16 into the next block's phase layout, or fp32 tokens
       const bool last = bi + 1 == pl.n_blocks;
+      const float* bop = bias_o + bi * 64;
+      const int nxt_rtot = last ? 0 : pl.blk[bi + 1].rtot;
+      const int tv = pl.T0 * V;
       for (int tile = 0; tile < m_tiles; ++tile) {
+        if (idle_half) break;
         const int mrow = tile * 128 + lane_grp * 32 + lane;
-        const int slotV = b.slot * V;
-        const int w = mrow / slotV;
-        const int q = mrow - w * slotV;
-        const bool data = mrow < b.mrows && q < b.Tout * V && w < nw;
-        const int t = q / V, v = q - t * V;
-        const int groups = b.npad >> 4;
-        for (int gq = (groups > 1 ? col_half : 0); gq < groups; gq += (groups > 1 ? 2 : 1)) {
-          if (groups == 1 && col_half) break;
+        const uint32_t e = mrow < b.mrows ? mt[mrow] : kGap;
+        const int w = e >> 11, target = e & 0x7FF;
+        const bool data = e != kGap && w < nw;
+        for (int gq = g_first; gq < groups; gq += g_step) {
           float acc[16];
           tmem_ld16(tmem + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(tile * dcol + gq * 16), acc);
           tmem_ld_wait();
           if (!data) continue;
-          float res[16];
 #pragma unroll
-          for (int e = 0; e < 16; ++e) res[e] = __ldg(b.out_b + gq * 16 + e);
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const float4 bb = *reinterpret_cast<const float4*>(bop + gq * 16 + q4 * 4);
+            acc[q4 * 4 + 0] += bb.x; acc[q4 * 4 + 1] += bb.y; acc[q4 * 4 + 2] += bb.z; acc[q4 * 4 + 3] += bb.w;
+          }
           if (bi == 0) {
             // K = Cin (2) residual conv on CUDA cores in fp32 from the un-mixed input
-            for (int ci = 0; ci < b.cin; ++ci) {
-              const float xv = x0[((w * pl.c_in + ci) * pl.T0 + b.stride * t) * V + v];
+            const float* xp = x0 + xrtab[mrow];
 #pragma unroll
-              for (int e = 0; e < 16; ++e)
-                if (gq * 16 + e < b.cout) res[e] = fmaf(__ldg(b.res_w32 + ci * b.cout + gq * 16 + e), xv, res[e]);
-            }
+            for (int ci = 0; ci < 4; ++ci)
+              if (ci < b.cin) {
+                const float xv = xp[ci * tv];
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                  const float4 rr = *reinterpret_cast<const float4*>(r0s + ci * 64 + gq * 16 + q4 * 4);
+                  acc[q4 * 4 + 0] = fmaf(rr.x, xv, acc[q4 * 4 + 0]); acc[q4 * 4 + 1] = fmaf(rr.y, xv, acc[q4 * 4 + 1]);
+                  acc[q4 * 4 + 2] = fmaf(rr.z, xv, acc[q4 * 4 + 2]); acc[q4 * 4 + 3] = fmaf(rr.w, xv, acc[q4 * 4 + 3]);
+                }
+              }
           } else if (b.identity_res) {
             const int r = b.gap * V + mrow;                                  // phase 0 (stride 1)
+            float f[8];
+            unpack8(*reinterpret_cast<const uint4*>(sXin + ((size_t)(gq * 2) * b.rtot + r) * 16), f);
 #pragma unroll
-            for (int h2 = 0; h2 < 2; ++h2) {
-              const uint4 qx = *reinterpret_cast<const uint4*>(sXin + ((size_t)(gq * 2 + h2) * b.rtot + r) * 16);
-              const __nv_bfloat162* hx = reinterpret_cast<const __nv_bfloat162*>(&qx);
+            for (int q = 0; q < 8; ++q) acc[q] += f[q];
+            unpack8(*reinterpret_cast<const uint4*>(sXin + ((size_t)(gq * 2 + 1) * b.rtot + r) * 16), f);
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f = __bfloat1622float2(hx[e]);
-                res[h2 * 8 + 2 * e] += f.x;
-                res[h2 * 8 + 2 * e + 1] += f.y;
-              }
-            }
+            for (int q = 0; q < 8; ++q) acc[8 + q] += f[q];
           }
-          float y[16];
 #pragma unroll
-          for (int e = 0; e < 16; ++e) y[e] = fmaxf(acc[e] + res[e], 0.f);
+          for (int q = 0; q < 16; ++q) acc[q] = fmaxf(acc[q], 0.f);
           if (!last) {
-            const BfBlk& nb = pl.blk[bi + 1];
-            const int ph = t % nb.stride, t2 = t / nb.stride;
-            const int r = ph * nb.rows + nb.gap * V + w * nb.slot * V + t2 * V + v;
-            *reinterpret_cast<uint4*>(sXout + ((size_t)(gq * 2) * nb.rtot + r) * 16) =
-                make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
-            *reinterpret_cast<uint4*>(sXout + ((size_t)(gq * 2 + 1) * nb.rtot + r) * 16) =
-                make_uint4(pack_bf16x2(y[8], y[9]), pack_bf16x2(y[10], y[11]), pack_bf16x2(y[12], y[13]), pack_bf16x2(y[14], y[15]));
+            *reinterpret_cast<uint4*>(sXout + ((size_t)(gq * 2) * nxt_rtot + target) * 16) = pack8(acc);
+            *reinterpret_cast<uint4*>(sXout + ((size_t)(gq * 2 + 1) * nxt_rtot + target) * 16) = pack8(acc + 8);
           } else {
-            float* dst = tokens + ((size_t)(w_first + w) * pl.S_out + t) * (size_t)(pl.c_last * V) + v;
+            float* dst = tokens + (size_t)(w_first + w) * pl.S_out * (size_t)(pl.c_last * V) + target;
 #pragma unroll
-            for (int e = 0; e < 16; ++e)
-              if (gq * 16 + e < b.cout) dst[(gq * 16 + e) * V] = y[e];
+            for (int q = 0; q < 16; ++q)
+              if (gq * 16 + q < b.cout) dst[(gq * 16 + q) * V] = acc[q];
           }
         }
       }
@@ -368,16 +480,15 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
   if (warp == 0) tmem_dealloc(tmem, pl.tmem_cols);
 }
 
-inline int pad16(int x) { return (x + 15) & ~15; }
-
 // Build the per-launch plan; returns false if this (model, T) is outside what the kernel covers.
 bool build_plan(const sf_model* m, int T, int G, BfPlan* pl, const char** why) {
-  static const char* reason = "";
-  *why = reason;
+  *why = "";
   const Tokenizer& tk = m->tok;
   const int V = tk.V, nb = tk.n_blocks;
   if (tk.pool_tokens > 0) { *why = "adaptive pooling"; return false; }
   if (tk.c_in > 4) { *why = "more than 4 input channels"; return false; }
+  if (T > 63) { *why = "window longer than 63 frames"; return false; }
+  if (G > 4 || tk.c_in * V > 255) { *why = "group / keypoint count outside table range"; return false; }
   pl->n_blocks = nb;
   pl->V = V;
   pl->c_in = tk.c_in;
@@ -400,7 +511,9 @@ bool build_plan(const sf_model* m, int T, int G, BfPlan* pl, const char** why) {
     b.stride = tb.stride;
     b.Tin = Tin;
     b.Tout = Tin / tb.stride;
+    if (b.npad > 64 || (kThreads % (b.npad >> 3)) || (i > 0 && (kThreads % (b.kin >> 3)))) { *why = "channel count"; return false; }
     if (i > 0 && b.kin != pl->blk[i - 1].npad) { *why = "channel padding mismatch"; return false; }
+    if (tb.ell_width > kEllMax) { *why = "adjacency rows with more than 8 non-zeros"; return false; }
     // taps: input row t = s*t' + k - 4 -> phase p = (k-4) mod s, offset o = (k-4-p)/s; live iff |o| < Tout
     b.n_taps = 0;
     b.gap = 0;
@@ -419,6 +532,7 @@ bool build_plan(const sf_model* m, int T, int G, BfPlan* pl, const char** why) {
     b.mrows = G * b.slot * V;
     b.rows = b.gap * V + b.mrows;
     b.rtot = b.stride * b.rows;
+    if (b.rtot > 2047) { *why = "operand buffer longer than 2047 rows"; return false; }
     b.identity_res = tb.identity_res;
     b.ell_width = tb.ell_width;
     b.ell_val = tb.ell_val;
@@ -431,9 +545,8 @@ bool build_plan(const sf_model* m, int T, int G, BfPlan* pl, const char** why) {
     b.gcn_w32 = tb.gcn_w;
     b.res_w32 = tb.res_w;
     if (i == 0 && tb.identity_res) { *why = "identity residual in block 0"; return false; }
-    const size_t a_bytes = (size_t)b.rtot * std::max(b.npad, i > 0 ? b.kin : 0) * 2 + 4096;   // + MMA tile overrun slack
-    maxA = std::max(maxA, a_bytes);
-    if (i > 0) maxX[(i + 1) & 1] = std::max(maxX[(i + 1) & 1], (size_t)b.rtot * b.kin * 2 + 4096);
+    maxA = std::max(maxA, (size_t)b.rtot * std::max(b.npad, i > 0 ? b.kin : 0) * 2);
+    if (i > 0) maxX[(i + 1) & 1] = std::max(maxX[(i + 1) & 1], (size_t)b.rtot * b.kin * 2);
     maxWT = std::max(maxWT, (size_t)kTaps * b.npad * b.npad * 2 + (size_t)(w.res ? b.kin * b.npad * 2 : 0));
     if (i > 0) maxWG = std::max(maxWG, (size_t)b.kin * b.npad * 2);
     const int tiles = std::max((b.mrows + 127) / 128, i > 0 ? (b.rtot + 127) / 128 : 0);
@@ -442,23 +555,39 @@ bool build_plan(const sf_model* m, int T, int G, BfPlan* pl, const char** why) {
   }
   pl->S_out = Tin;
   pl->c_last = tk.blk[nb - 1].cout;
+  if (Tin * pl->c_last * V > 2047) { *why = "token block larger than the table range"; return false; }
   uint32_t cols = 32;
   while ((int)cols < max_cols) cols <<= 1;
   if (cols > 512) { *why = "accumulators exceed tensor memory"; return false; }
   pl->tmem_cols = cols;
   auto up = [](size_t x) { return (uint32_t)((x + 127) & ~size_t(127)); };
+  // Operand buffers first: an MMA tile that runs past the end of one buffer (rows that are discarded)
+  // only ever reads the bytes of the next region, never past the allocation.
   uint32_t off = 0;
   pl->off_A = off; off += up(maxA);
   pl->off_X0 = off; off += up(std::max(maxX[0], (size_t)16));
-  pl->off_X1 = off; off += up(std::max(maxX[1], (size_t)16));
+  pl->off_X1 = off; off += up(std::max(std::max(maxX[1], (size_t)16), (size_t)G * tk.c_in * T * V * sizeof(float)));
   pl->off_WT = off; off += up(maxWT);
   pl->off_WG = off; off += up(std::max(maxWG, (size_t)16));
   const size_t xbytes = (size_t)G * tk.c_in * T * V * sizeof(float);
   pl->off_x0 = off; off += up(xbytes);
-  pl->off_m0 = off; off += up(xbytes);
+  pl->off_m0 = pl->off_X1;                       // m0 is dead before x2 (X1) is first written
+  for (int i = 0; i < nb; ++i) {
+    pl->blk[i].off_rowtab = off; off += up((size_t)pl->blk[i].rtot * 2);
+    pl->blk[i].off_mtab = off; off += up((size_t)pl->blk[i].mrows * 2);
+  }
+  pl->off_xrtab = off; off += up((size_t)pl->blk[0].mrows * 2);
+  pl->off_xjtab = off; off += up((size_t)G * tk.c_in * T * V);
+  pl->off_bias_g = off; off += up((size_t)nb * 64 * 4);
+  pl->off_bias_o = off; off += up((size_t)nb * 64 * 4);
+  pl->off_w0 = off; off += up(4 * 64 * 4);
+  pl->off_r0 = off; off += up(4 * 64 * 4);
+  pl->off_ellv = off; off += up((size_t)nb * V * kEllMax * 4);
+  pl->off_elld = off; off += up((size_t)nb * V * kEllMax * 4);
+  pl->off_scale = off; off += up((size_t)tk.c_in * V * 4);
+  pl->off_shift = off; off += up((size_t)tk.c_in * V * 4);
   pl->smem_bytes = off;
   if (off > (uint32_t)m->max_smem_optin) { *why = "activations + weights exceed shared memory"; return false; }
-  // start-address field of the descriptor is 14 bits of 16-byte units = 256 KB: always fine on sm_100
   return true;
 }
 
