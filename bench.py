@@ -244,15 +244,15 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     # per-kernel timing of the two kernels of the path (same stream, same inputs), K launches each
-    tok = eng.tokenize(x)
+    tok = eng.tokenize(x, precision=a.precision)
     k0, k1, k2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     torch.cuda.synchronize(dev)
     k0.record()
     for _ in range(a.steps):
-        eng.tokenize(x)
+        eng.tokenize(x, precision=a.precision)
     k1.record()
     for _ in range(a.steps):
-        eng.reconstruct_tokens(tok)
+        eng.reconstruct_tokens(tok, precision=a.precision)
     k2.record()
     torch.cuda.synchronize(dev)
     tok_ms, xf_ms = k0.elapsed_time(k1) / a.steps, k1.elapsed_time(k2) / a.steps

@@ -23,20 +23,25 @@ extern "C" int64_t sf_workspace_bytes(const sf_model* m, int64_t B, int32_t T) {
   return align256(B * (int64_t)S * m->xf.d_tok * (int64_t)sizeof(float)) + align256(tokenizer_fp32_workspace(m, B, T));
 }
 
-extern "C" int sf_tokenize(const sf_model* m, const float* poses_dev, int64_t B, int32_t T, float* tokens_dev,
-                           void* workspace_dev, int64_t workspace_bytes, void* stream) {
+extern "C" int sf_tokenize(const sf_model* m, const float* poses_dev, int64_t B, int32_t T, int32_t precision,
+                           float* tokens_dev, void* workspace_dev, int64_t workspace_bytes, void* stream) {
   int rc = check_T(m, T);
   if (rc) return rc;
   SF_REQUIRE(B >= 0 && (B == 0 || (poses_dev && tokens_dev)), SF_E_INVALID, "sf_tokenize: null buffer");
+  SF_REQUIRE(precision == SF_PREC_FP32 || precision == SF_PREC_BF16, SF_E_INVALID, "unknown precision %d", precision);
+  if (precision == SF_PREC_BF16) return launch_tokenizer_bf16(m, poses_dev, B, T, tokens_dev, (cudaStream_t)stream);
   return launch_tokenizer_fp32(m, poses_dev, B, T, tokens_dev, workspace_dev, workspace_bytes, (cudaStream_t)stream);
 }
 
-extern "C" int sf_reconstruct_tokens(const sf_model* m, const float* tokens_dev, int64_t B, int32_t S, float* recon_dev,
-                                     void* workspace_dev, int64_t workspace_bytes, void* stream) {
+extern "C" int sf_reconstruct_tokens(const sf_model* m, const float* tokens_dev, int64_t B, int32_t S, int32_t precision,
+                                     float* recon_dev, void* workspace_dev, int64_t workspace_bytes, void* stream) {
   (void)workspace_dev;
   (void)workspace_bytes;
   SF_REQUIRE(m, SF_E_INVALID, "null model");
   SF_REQUIRE(B >= 0 && (B == 0 || (tokens_dev && recon_dev)), SF_E_INVALID, "sf_reconstruct_tokens: null buffer");
+  SF_REQUIRE(precision == SF_PREC_FP32 || precision == SF_PREC_BF16, SF_E_INVALID, "unknown precision %d", precision);
+  if (precision == SF_PREC_BF16)
+    return launch_transformer_bf16(m, tokens_dev, B, S, SF_REDUCE_MEAN, recon_dev, nullptr, (cudaStream_t)stream);
   return launch_transformer_fp32(m, tokens_dev, B, S, SF_REDUCE_MEAN, recon_dev, nullptr, (cudaStream_t)stream);
 }
 
@@ -72,6 +77,7 @@ extern "C" int sf_score_windows(const sf_model* m, const float* poses_dev, int64
   rc = precision == SF_PREC_BF16 ? launch_tokenizer_bf16(m, poses_dev, B, T, tok, st)
                                  : launch_tokenizer_fp32(m, poses_dev, B, T, tok, ws, ws_left, st);
   if (rc) return rc;
+  if (precision == SF_PREC_BF16) return launch_transformer_bf16(m, tok, B, S, reduction, recon_dev, scores_dev, st);
   return launch_transformer_fp32(m, tok, B, S, reduction, recon_dev, scores_dev, st);
 }
 

@@ -394,6 +394,115 @@ extern "C" int sf_model_create(const sf_config* cfg, int32_t n_tensors, const ch
   }
   if (pk.err != SF_OK) return pk.err;
 
+  // ------------------------------------------------------------- tensor-core transformer program
+  // Host-side op list with OFFSETS (bf16 image offset into `bf`, fp32 offsets into pk.arena); pointers are
+  // fixed up after the upload.  dp / dtp: widths padded to multiples of 16 (MMA K and N granularity).
+  struct HostOp { XfOp op; size_t w_off, b_off, g_off, lb_off; bool has_w, has_b, has_ln; };
+  std::vector<HostOp> prog;
+  const int dp = pad16(d), dtp = pad16(d_tok), dff = cfg->d_ff;
+  const int hd = d / H;
+  const int ffc = std::min(pad16(dff), 128);                  // FFN hidden processed in chunks of <= 128 columns
+  bool xf_ok = dp <= 160 && dtp <= 160 && hd % 4 == 0 && (H == 1 || H % 2 == 0) && d % 8 == 0 && d_tok % 8 == 0;
+  int max_w_bytes = 0;
+  auto image = [&](const LinOff& lin, int n0, int n_cnt, int k0, int k_cnt, int Npad, int Kpad) {
+    const size_t off = bf_alloc((size_t)Npad * Kpad);
+    for (int kc = 0; kc < Kpad / 8; ++kc)
+      for (int n = 0; n < Npad; ++n)
+        for (int e = 0; e < 8; ++e) {
+          const int k = kc * 8 + e;
+          const float v = (n < n_cnt && k < k_cnt) ? pk.arena[lin.wt + (size_t)(k0 + k) * lin.N + (n0 + n)] : 0.f;
+          bf[off + ((size_t)kc * Npad + n) * 8 + e] = f2bf(v);
+        }
+    max_w_bytes = std::max(max_w_bytes, Npad * Kpad * 2);
+    return off;
+  };
+  auto bias_pad = [&](const LinOff& lin, int n0, int n_cnt, int Npad) {
+    const size_t off = pk.alloc(Npad);
+    for (int n = 0; n < n_cnt; ++n) pk.arena[off + n] = pk.arena[lin.b + n0 + n];
+    return off;
+  };
+  auto op_gemm = [&](int a_src, const LinOff& lin, int n0, int n_cnt, int k0, int k_cnt, int Npad, int Kpad, int col,
+                     int accumulate, int epi, int act, bool with_bias) {
+    HostOp h{};
+    h.op.type = XF_GEMM; h.op.a_src = a_src; h.op.K = Kpad; h.op.N = Npad; h.op.tmem_col = col;
+    h.op.accumulate = accumulate; h.op.epi = epi; h.op.act = act; h.op.post = XP_NONE;
+    h.w_off = image(lin, n0, n_cnt, k0, k_cnt, Npad, Kpad); h.has_w = true;
+    h.has_b = with_bias;
+    if (with_bias) h.b_off = bias_pad(lin, n0, n_cnt, Npad);
+    prog.push_back(h);
+    return prog.size() - 1;
+  };
+  auto set_post = [&](size_t idx, int post, const NormOff* nm, int also_mem) {
+    prog[idx].op.post = post; prog[idx].op.also_mem = also_mem;
+    if (nm) { prog[idx].has_ln = true; prog[idx].g_off = nm->g; prog[idx].lb_off = nm->b; }
+  };
+  auto op_init = [&](int mode) {
+    HostOp h{};
+    h.op.type = XF_INIT; h.op.init_mode = mode;
+    prog.push_back(h);
+    return prog.size() - 1;
+  };
+  // attention block: q, k, v into TMEM columns [0,dp) [dp,2dp) [2dp,3dp), attention epilogue -> Hop, out_proj -> stream
+  auto attention = [&](const AttnOff& at, int kv_src) {
+    op_gemm(XS_AOP, at.qkv, 0, d, 0, d, dp, dp, 0, 0, XE_NONE, 0, true);
+    op_gemm(kv_src, at.qkv, d, d, 0, d, dp, dp, dp, 0, XE_NONE, 0, true);
+    op_gemm(kv_src, at.qkv, 2 * d, d, 0, d, dp, dp, 2 * dp, 0, XE_ATTN, 0, true);
+    return op_gemm(XS_HOP, at.out, 0, d, 0, d, dp, dp, 0, 0, XE_STREAM_ADD, 0, true);
+  };
+  // FFN: hidden in chunks of ffc columns; ff2 accumulates in TMEM columns [0,dp), ff1 chunk lands at column 256
+  auto ffn = [&](const LinOff& f1, const LinOff& f2, int act) {
+    size_t last = 0;
+    const int n_chunks = (dff + ffc - 1) / ffc;
+    for (int c = 0; c < n_chunks; ++c) {
+      const int cnt = std::min(ffc, dff - c * ffc), cpad = pad16(cnt);
+      op_gemm(XS_AOP, f1, c * ffc, cnt, 0, d, cpad, dp, 256, 0, XE_ACT_H, act, true);
+      last = op_gemm(XS_HOP, f2, 0, d, c * ffc, cnt, dp, cpad, 0, c > 0, c + 1 == n_chunks ? XE_STREAM_ADD : XE_NONE, 0,
+                     c + 1 == n_chunks);
+    }
+    return last;
+  };
+  if (xf_ok) {
+    if (v1) {
+      set_post(op_init(XI_TOK_PE), XP_COPY_TO_AOP, nullptr, 0);
+      for (int i = 0; i < cfg->n_enc_layers; ++i) {
+        set_post(attention(eo[i].sa, XS_AOP), XP_LN_INPLACE_TO_AOP, &eo[i].n1, 0);
+        set_post(ffn(eo[i].f1, eo[i].f2, 1), XP_LN_INPLACE_TO_AOP, &eo[i].n2, i + 1 == cfg->n_enc_layers);
+      }
+      set_post(op_init(XI_SHIFT_TOK_PE), XP_COPY_TO_AOP, nullptr, 0);
+      for (int i = 0; i < cfg->n_dec_layers; ++i) {
+        set_post(attention(dof[i].sa, XS_AOP), XP_LN_INPLACE_TO_AOP, &dof[i].n1, 0);
+        set_post(attention(dof[i].ca, XS_MEM), XP_LN_INPLACE_TO_AOP, &dof[i].n2, 0);
+        set_post(ffn(dof[i].f1, dof[i].f2, 1), XP_LN_INPLACE_TO_AOP, &dof[i].n3, 0);
+      }
+      op_gemm(XS_AOP, out_proj, 0, d, 0, d, dp, dp, 0, 0, XE_SCORE, 0, true);
+    } else {
+      auto embed = [&](const NormOff* first_norm) {
+        if (io_proj) {
+          op_init(XI_TOK_TO_AOP);
+          set_post(op_gemm(XS_AOP, in_proj, 0, d, 0, d_tok, dp, dtp, 0, 0, XE_STREAM_SET_PE, 0, true), XP_LN_TO_AOP, first_norm, 0);
+        } else {
+          set_post(op_init(XI_TOK_PE), XP_LN_TO_AOP, first_norm, 0);
+        }
+      };
+      embed(&eo[0].n1);
+      for (int i = 0; i < cfg->n_enc_layers; ++i) {
+        const bool lastl = i + 1 == cfg->n_enc_layers;
+        set_post(attention(eo[i].sa, XS_AOP), XP_LN_TO_AOP, &eo[i].n2, 0);
+        set_post(ffn(eo[i].f1, eo[i].f2, 2), lastl ? XP_LN_TO_MEM : XP_LN_TO_AOP, lastl ? &enc_norm : &eo[i + 1].n1, 0);
+      }
+      embed(&dof[0].n1);
+      for (int i = 0; i < cfg->n_dec_layers; ++i) {
+        const bool lastl = i + 1 == cfg->n_dec_layers;
+        set_post(attention(dof[i].sa, XS_AOP), XP_LN_TO_AOP, &dof[i].n2, 0);
+        set_post(attention(dof[i].ca, XS_MEM), XP_LN_TO_AOP, &dof[i].n3, 0);
+        const size_t f = ffn(dof[i].f1, dof[i].f2, 2);
+        if (!lastl) set_post(f, XP_LN_TO_AOP, &dof[i + 1].n1, 0);
+        else set_post(f, io_proj ? XP_LN_TO_AOP : XP_LN_SCORE, &dec_norm, 0);
+      }
+      if (io_proj) op_gemm(XS_AOP, out_proj, 0, d_tok, 0, d, dtp, dp, 0, 0, XE_SCORE, 0, true);
+    }
+  }
+
   // ------------------------------------------------------------- upload + pointer fix-up
   sf_model* m = new sf_model();
   m->cfg = *cfg;
@@ -430,6 +539,30 @@ extern "C" int sf_model_create(const sf_config* cfg, int32_t n_tensors, const ch
     w.out_b = A + bfo[i].ob;
     w.npad = bfo[i].npad;
     w.kin_pad = bfo[i].kin;
+  }
+  {
+    std::vector<XfOp> ops(prog.size());
+    for (size_t i = 0; i < prog.size(); ++i) {
+      ops[i] = prog[i].op;
+      ops[i].w = prog[i].has_w ? m->arena_bf16 + prog[i].w_off : nullptr;
+      ops[i].bias = prog[i].has_b ? A + prog[i].b_off : nullptr;
+      ops[i].ln_g = prog[i].has_ln ? A + prog[i].g_off : nullptr;
+      ops[i].ln_b = prog[i].has_ln ? A + prog[i].lb_off : nullptr;
+    }
+    m->xfops_dev = nullptr;
+    m->xfprog = XfProgram{nullptr, (int)ops.size(), dp, dtp, xf_ok && !ops.empty() ? 1 : 0, max_w_bytes};
+    if (!ops.empty()) {
+      e = cudaMalloc((void**)&m->xfops_dev, ops.size() * sizeof(XfOp));
+      if (e == cudaSuccess) e = cudaMemcpy(m->xfops_dev, ops.data(), ops.size() * sizeof(XfOp), cudaMemcpyHostToDevice);
+      if (e != cudaSuccess) {
+        set_error("uploading the transformer program failed: %s", cudaGetErrorString(e));
+        cudaFree(m->arena);
+        cudaFree(m->arena_bf16);
+        delete m;
+        return SF_E_CUDA;
+      }
+      m->xfprog.ops = m->xfops_dev;
+    }
   }
   auto lin = [&](const LinOff& o) { return Linear{A + o.wt, A + o.b, o.K, o.N}; };
   auto nrm = [&](const NormOff& o) { return Norm{A + o.g, A + o.b}; };
@@ -484,6 +617,7 @@ extern "C" void sf_model_destroy(sf_model* m) {
   cudaSetDevice(m->device);
   if (m->arena) cudaFree(m->arena);
   if (m->arena_bf16) cudaFree(m->arena_bf16);
+  if (m->xfops_dev) cudaFree(m->xfops_dev);
   delete m;
 }
 

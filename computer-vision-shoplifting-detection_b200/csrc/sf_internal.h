@@ -110,6 +110,28 @@ struct BfTokenizerW {
 };
 }  // namespace sf
 
+namespace sf {
+// "Program" of the tensor-core transformer: the host flattens either variant (post-LN/ReLU/shifted target
+// or pre-LN/GELU/final norms/projections) into a list of ops that one kernel interprets per row tile.
+enum XfOpType { XF_INIT = 0, XF_GEMM = 1, XF_POST = 2 };
+enum XfInit { XI_TOK_PE = 0, XI_SHIFT_TOK_PE = 1, XI_TOK_TO_AOP = 2 };
+enum XfEpi { XE_NONE = 0, XE_ATTN = 1, XE_ACT_H = 2, XE_STREAM_ADD = 3, XE_STREAM_SET_PE = 4, XE_SCORE = 5 };
+enum XfPost { XP_NONE = 0, XP_COPY_TO_AOP = 1, XP_LN_INPLACE_TO_AOP = 2, XP_LN_TO_AOP = 3, XP_LN_TO_MEM = 4, XP_LN_SCORE = 5 };
+enum XfSrc { XS_AOP = 0, XS_HOP = 1, XS_MEM = 2 };
+struct XfOp {
+  int32_t type, init_mode, a_src, K, N, tmem_col, accumulate, epi, act, post, also_mem, h_col;
+  const uint16_t* w;        // [K/8][N][8] bf16 operand image (K-major B)
+  const float* bias;        // [N] zero padded
+  const float* ln_g;
+  const float* ln_b;
+};
+struct XfProgram {
+  const XfOp* ops;          // device
+  int n_ops, dp, dtp, supported;
+  int max_w_bytes;          // largest weight image (ring slot size)
+};
+}  // namespace sf
+
 struct sf_model {
   sf_config cfg;
   int device;
@@ -122,6 +144,8 @@ struct sf_model {
   uint16_t* arena_bf16;     // bf16 operand images (tcgen05 path)
   size_t arena_bf16_bytes;
   sf::BfTokenizerW tokbf;
+  sf::XfProgram xfprog;
+  sf::XfOp* xfops_dev;
 };
 
 namespace sf {
@@ -137,4 +161,8 @@ int token_len(const sf_model* m, int T);
 // bf16 tcgen05 tokenizer (returns SF_E_UNSUPPORTED for shapes it does not cover)
 int launch_tokenizer_bf16(const sf_model* m, const float* poses, int64_t B, int T, float* tokens, cudaStream_t st);
 bool tokenizer_bf16_supported(const sf_model* m, int T);
+// bf16 tcgen05 transformer + fused score
+int launch_transformer_bf16(const sf_model* m, const float* tokens, int64_t B, int S, int reduction, float* recon,
+                            float* scores, cudaStream_t st);
+bool transformer_bf16_supported(const sf_model* m, int S);
 }  // namespace sf

@@ -1,0 +1,487 @@
+// bf16 tcgen05 encoder/decoder transformer + fused reconstruction-error score.
+//
+// Same maths as transformer_fp32.cu (reference shopformer/models/transformer.py:60-196,
+// 304-329, shopformer/models/shopformer.py:150-178; shopformer_2/models/transformer.py:105-194,
+// shopformer_2/models/shopformer.py:178-186).  The host flattens either variant into an op list
+// (model.cu: "tensor-core transformer program"); this kernel interprets it for one tile of rows at a time:
+//
+//   * one CTA = 128 TMEM lanes = 4 lane groups x 32 rows; a lane group holds floor(32/S) whole windows
+//     (S = 2..4 tokens each), so the S x S attention of a window never leaves a warp: QK^T and PV are
+//     computed straight out of TMEM with warp shuffles over the token axis;
+//   * every nn.Linear is a chain of tcgen05.mma (M=128, N = padded width, K = 16 per instruction) with the
+//     bf16 activation operand in shared memory (planar-chunk layout, tc_common.cuh) and the weight image
+//     streamed L2 -> smem through a 2-slot cp.async ring, prefetched one GEMM ahead;
+//   * the fp32 residual stream of a row lives in REGISTERS (two warps share a row: even / odd 16-column
+//     groups); bias, residual add, LayerNorm (two-pass, partial sums exchanged through smem), ReLU / exact
+//     GELU and the bf16 down-conversion of the next operand all happen in the TMEM epilogue;
+//   * q, k, v accumulate side by side in TMEM columns [0,dp) [dp,2dp) [2dp,3dp); the FFN hidden layer is
+//     processed in chunks of <= 128 columns with the second GEMM accumulating in TMEM across chunks;
+//   * the squared error against the score target is reduced in the last epilogue: only B floats are written.
+#include <algorithm>
+
+#include "sf_internal.h"
+#include "tc_common.cuh"
+
+namespace sf {
+namespace {
+
+using namespace tc;
+
+constexpr int kThreads = 256;
+constexpr int kSlots = 5;              // 16-column groups per thread: widths up to 160
+constexpr int kSMax = 4;
+constexpr float kLnEps = 1e-5f;
+
+struct XfGeo {
+  int S, wpw, rows_per_warp, win_per_tile;
+  uint32_t off_aop, off_hop, off_mem, off_w, off_red, smem_bytes;
+  int slot_bytes, plane;               // plane = 128 rows * 16 B
+};
+
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void stage(unsigned char* dst, const uint16_t* src, int bytes) {
+  const unsigned char* s = reinterpret_cast<const unsigned char*>(src);
+  for (int i = threadIdx.x * 16; i < bytes; i += kThreads * 16) cp_async16(dst + i, s + i);
+}
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr >> 4) & 0x3FFFu) | ((lbo_bytes >> 4) << 16);
+}
+__device__ __forceinline__ uint64_t desc_join(uint32_t lo) { return ((uint64_t)((128u >> 4) | (1u << 14)) << 32) | lo; }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+
+// write one 16-column group of a row into a planar-chunk operand buffer
+__device__ __forceinline__ void store_group(unsigned char* buf, int plane, int row, int g, const float* y) {
+  *reinterpret_cast<uint4*>(buf + (size_t)(2 * g) * plane + row * 16) = pack8(y);
+  *reinterpret_cast<uint4*>(buf + (size_t)(2 * g + 1) * plane + row * 16) = pack8(y + 8);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo, const __grid_constant__ Transformer xf,
+                        const float* __restrict__ tokens, int64_t B, int reduction, float* __restrict__ recon_out,
+                        float* __restrict__ scores) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  unsigned char* sAop = smem + geo.off_aop;
+  unsigned char* sHop = smem + geo.off_hop;
+  unsigned char* sMem = smem + geo.off_mem;
+  unsigned char* sW = smem + geo.off_w;                       // 2 ring slots
+  float* red = reinterpret_cast<float*>(smem + geo.off_red);  // [2 halves][128 rows]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lane_grp = warp & 3, half = warp >> 2;
+  const int row = lane_grp * 32 + lane;
+  const int S = geo.S, d = xf.d_model, dt = xf.d_tok, dp = prog.dp, plane = geo.plane;
+  const int tok_s = lane % S, win_l = lane / S, wb = win_l * S;       // token index, window in warp, first lane of window
+  const bool lane_ok = lane < geo.rows_per_warp;
+  const uint32_t lane_addr = (uint32_t)(lane_grp * 32) << 16;
+
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  // zero the operand buffers once: padded columns / idle rows must stay finite (NaN * 0 = NaN in the MMA)
+  for (int i = threadIdx.x; i < (int)((geo.off_w - geo.off_aop) >> 4); i += kThreads)
+    reinterpret_cast<uint4*>(smem + geo.off_aop)[i] = make_uint4(0, 0, 0, 0);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  uint32_t parity = 0;
+
+  // index of the first / next GEMM op (for the weight ring)
+  const int n_ops = prog.n_ops;
+  const XfOp* __restrict__ ops = prog.ops;
+
+  const int64_t n_tiles = (B + geo.win_per_tile - 1) / geo.win_per_tile;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t window = tile * geo.win_per_tile + lane_grp * geo.wpw + win_l;
+    const bool valid = lane_ok && window < B;
+    const float* tok_row = tokens + ((size_t)(valid ? window : 0) * S + tok_s) * dt;
+    float st[kSlots][16];
+#pragma unroll
+    for (int i = 0; i < kSlots; ++i)
+#pragma unroll
+      for (int q = 0; q < 16; ++q) st[i][q] = 0.f;
+
+    int slot = 0;
+    {   // prefetch the first GEMM's weights
+      int nx = 0;
+      while (nx < n_ops && ops[nx].type != XF_GEMM) ++nx;
+      if (nx < n_ops) stage(sW, ops[nx].w, ops[nx].K * ops[nx].N * 2);
+    }
+
+    for (int oi = 0; oi < n_ops; ++oi) {
+      const XfOp op = ops[oi];
+      int post = op.post;
+      // ------------------------------------------------------------------ stream initialisation
+      if (op.type == XF_INIT) {
+        if (op.init_mode == XI_TOK_TO_AOP) {
+          const int ng = prog.dtp >> 4;
+#pragma unroll
+          for (int i = 0; i < kSlots; ++i) {
+            const int g = 2 * i + half;
+            if (g < ng) {
+              float y[16];
+#pragma unroll
+              for (int q = 0; q < 16; ++q) {
+                const int c = g * 16 + q;
+                y[q] = (valid && c < dt) ? __ldg(tok_row + c) : 0.f;
+              }
+              store_group(sAop, plane, row, g, y);
+            }
+          }
+        } else {
+          const bool shift = op.init_mode == XI_SHIFT_TOK_PE;
+          const int ng = dp >> 4;
+#pragma unroll
+          for (int i = 0; i < kSlots; ++i) {
+            const int g = 2 * i + half;
+            if (g < ng) {
+#pragma unroll
+              for (int q = 0; q < 16; ++q) {
+                const int c = g * 16 + q;
+                float v = 0.f;
+                if (valid && c < d) {
+                  v = __ldg(xf.pe + tok_s * d + c);
+                  if (!shift) v += __ldg(tok_row + c);
+                  else if (tok_s > 0) v += __ldg(tok_row - dt + c);      // zero start token + tokens shifted by one
+                }
+                st[i][q] = v;
+              }
+            }
+          }
+        }
+      }
+      // ------------------------------------------------------------------ GEMM + epilogue
+      if (op.type == XF_GEMM) {
+        cp_async_wait_all();
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          tc_fence_after();
+          const unsigned char* a = op.a_src == XS_AOP ? sAop : (op.a_src == XS_HOP ? sHop : sMem);
+          const uint32_t idesc = make_idesc(128, op.N, false);
+          const uint32_t w_plane = (uint32_t)op.N * 16u;
+          uint32_t alo = desc_lo(smem_u32(a), (uint32_t)plane);
+          uint32_t blo = desc_lo(smem_u32(sW + slot * geo.slot_bytes), w_plane);
+          for (int ks = 0; ks < (op.K >> 4); ++ks) {
+            umma_bf16(tmem + (uint32_t)op.tmem_col, desc_join(alo), desc_join(blo), idesc, (op.accumulate || ks > 0) ? 1u : 0u);
+            alo += (2u * (uint32_t)plane) >> 4;
+            blo += (2u * w_plane) >> 4;
+          }
+          umma_commit(&bar);
+        }
+        {   // prefetch the next GEMM's weights into the other ring slot (its previous user has completed)
+          int nx = oi + 1;
+          while (nx < n_ops && ops[nx].type != XF_GEMM) ++nx;
+          if (nx < n_ops) stage(sW + (slot ^ 1) * geo.slot_bytes, ops[nx].w, ops[nx].K * ops[nx].N * 2);
+        }
+        slot ^= 1;
+        mbar_wait(&bar, parity);
+        parity ^= 1;
+        tc_fence_after();
+
+        if (op.epi == XE_ATTN) {
+          // ---- softmax(q k^T / sqrt(hd)) v per (row, head); heads split between the two warps of a lane group
+          const int H = xf.heads, hd = d / H;
+          const int h_lo = H == 1 ? 0 : half * (H >> 1), h_hi = H == 1 ? (half == 0 ? 1 : 0) : (half + 1) * (H >> 1);
+          const float scale = rsqrtf((float)hd);
+          const float* bq = ops[oi - 2].bias;
+          const float* bk = ops[oi - 1].bias;
+          const float* bv = op.bias;
+          for (int h = h_lo; h < h_hi; ++h) {
+            const int c0 = h * hd;
+            float sc[kSMax];
+#pragma unroll
+            for (int j = 0; j < kSMax; ++j) sc[j] = 0.f;
+            for (int c4 = 0; c4 < hd; c4 += 4) {
+              float q4[4], k4[4];
+              tmem_ld4(tmem + lane_addr + (uint32_t)(c0 + c4), q4);
+              tmem_ld4(tmem + lane_addr + (uint32_t)(dp + c0 + c4), k4);
+              tmem_ld_wait();
+              const float4 bq4 = __ldg(reinterpret_cast<const float4*>(bq + c0 + c4));
+              const float4 bk4 = __ldg(reinterpret_cast<const float4*>(bk + c0 + c4));
+              q4[0] += bq4.x; q4[1] += bq4.y; q4[2] += bq4.z; q4[3] += bq4.w;
+              k4[0] += bk4.x; k4[1] += bk4.y; k4[2] += bk4.z; k4[3] += bk4.w;
+#pragma unroll
+              for (int j = 0; j < kSMax; ++j)
+                if (j < S) {
+                  const int src = (wb + j) & 31;
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) sc[j] = fmaf(q4[e], __shfl_sync(0xffffffffu, k4[e], src), sc[j]);
+                }
+            }
+            float mx = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < kSMax; ++j)
+              if (j < S) {
+                sc[j] *= scale;
+                mx = fmaxf(mx, sc[j]);
+              }
+            float den = 0.f;
+#pragma unroll
+            for (int j = 0; j < kSMax; ++j)
+              if (j < S) {
+                sc[j] = expf(sc[j] - mx);
+                den += sc[j];
+              }
+            const float inv = 1.f / den;
+            for (int c4 = 0; c4 < hd; c4 += 4) {
+              float v4[4];
+              tmem_ld4(tmem + lane_addr + (uint32_t)(2 * dp + c0 + c4), v4);
+              tmem_ld_wait();
+              const float4 bv4 = __ldg(reinterpret_cast<const float4*>(bv + c0 + c4));
+              v4[0] += bv4.x; v4[1] += bv4.y; v4[2] += bv4.z; v4[3] += bv4.w;
+              float o4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+              for (int j = 0; j < kSMax; ++j)
+                if (j < S) {
+                  const int src = (wb + j) & 31;
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) o4[e] = fmaf(sc[j], __shfl_sync(0xffffffffu, v4[e], src), o4[e]);
+                }
+              const int c = c0 + c4;
+              uint2 pk = make_uint2(pack_bf16x2(o4[0] * inv, o4[1] * inv), pack_bf16x2(o4[2] * inv, o4[3] * inv));
+              *reinterpret_cast<uint2*>(sHop + (size_t)(c >> 3) * plane + row * 16 + (c & 7) * 2) = pk;
+            }
+          }
+        } else if (op.epi == XE_ACT_H) {
+          const int ng = op.N >> 4;
+#pragma unroll
+          for (int i = 0; i < kSlots; ++i) {
+            const int g = 2 * i + half;
+            if (g < ng) {
+              float acc[16];
+              tmem_ld16(tmem + lane_addr + (uint32_t)(op.tmem_col + g * 16), acc);
+              tmem_ld_wait();
+#pragma unroll
+              for (int q = 0; q < 16; ++q) {
+                const float v = acc[q] + __ldg(op.bias + g * 16 + q);
+                acc[q] = op.act == 2 ? gelu_erf(v) : fmaxf(v, 0.f);
+              }
+              store_group(sHop, plane, row, g, acc);
+            }
+          }
+        } else if (op.epi == XE_STREAM_ADD || op.epi == XE_STREAM_SET_PE) {
+          const int ng = op.N >> 4;
+          const bool set_pe = op.epi == XE_STREAM_SET_PE;
+#pragma unroll
+          for (int i = 0; i < kSlots; ++i) {
+            const int g = 2 * i + half;
+            if (g < ng) {
+              float acc[16];
+              tmem_ld16(tmem + lane_addr + (uint32_t)(op.tmem_col + g * 16), acc);
+              tmem_ld_wait();
+#pragma unroll
+              for (int q = 0; q < 16; ++q) {
+                const int c = g * 16 + q;
+                const float v = acc[q] + __ldg(op.bias + c);
+                if (set_pe) st[i][q] = (valid && c < d) ? v + __ldg(xf.pe + tok_s * d + c) : 0.f;
+                else st[i][q] += v;
+              }
+            }
+          }
+        } else if (op.epi == XE_SCORE) {
+          // recon = D + bias (width dt); squared error against the score target
+          const int ng = op.N >> 4;
+          float part = 0.f;
+#pragma unroll
+          for (int i = 0; i < kSlots; ++i) {
+            const int g = 2 * i + half;
+            if (g < ng) {
+              float acc[16];
+              tmem_ld16(tmem + lane_addr + (uint32_t)(op.tmem_col + g * 16), acc);
+              tmem_ld_wait();
+#pragma unroll
+              for (int q = 0; q < 16; ++q) {
+                const int c = g * 16 + q;
+                if (valid && c < dt) {
+                  const float r = acc[q] + __ldg(op.bias + c);
+                  float target = __ldg(tok_row + c);
+                  if (xf.variant == SF_VARIANT_SHOPFORMER) target += __ldg(xf.pe_score + tok_s * dt + c);
+                  const float df = r - target;
+                  part = fmaf(df, df, part);
+                  if (recon_out) recon_out[((size_t)window * S + tok_s) * dt + c] = r;
+                }
+              }
+            }
+          }
+          red[half * 128 + row] = part;
+          __syncthreads();
+          if (half == 0) {
+            const float tot = red[row] + red[128 + row];
+            if (reduction == SF_REDUCE_NONE) {
+              if (valid && scores) scores[(size_t)window * S + tok_s] = tot / (float)dt;
+            } else {
+              float wsum = 0.f;
+#pragma unroll
+              for (int j = 0; j < kSMax; ++j)
+                if (j < S) wsum += __shfl_sync(0xffffffffu, tot, (wb + j) & 31);
+              if (valid && tok_s == 0 && scores) scores[window] = wsum / (float)(S * dt);
+            }
+          }
+          __syncthreads();
+          post = XP_NONE;
+        }
+      }
+      // ------------------------------------------------------------------ post step on the register stream
+      if (post == XP_COPY_TO_AOP) {
+        const int ng = dp >> 4;
+#pragma unroll
+        for (int i = 0; i < kSlots; ++i) {
+          const int g = 2 * i + half;
+          if (g < ng) store_group(sAop, plane, row, g, st[i]);
+        }
+      } else if (post >= XP_LN_INPLACE_TO_AOP) {
+        const int ng = dp >> 4;
+        float s1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < kSlots; ++i) {
+          const int g = 2 * i + half;
+          if (g < ng) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q)
+              if (g * 16 + q < d) s1 += st[i][q];
+          }
+        }
+        red[half * 128 + row] = s1;
+        __syncthreads();
+        const float mean = (red[row] + red[128 + row]) / (float)d;
+        __syncthreads();
+        float s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < kSlots; ++i) {
+          const int g = 2 * i + half;
+          if (g < ng) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q)
+              if (g * 16 + q < d) {
+                const float c0 = st[i][q] - mean;
+                s2 = fmaf(c0, c0, s2);
+              }
+          }
+        }
+        red[half * 128 + row] = s2;
+        __syncthreads();
+        const float rstd = rsqrtf((red[row] + red[128 + row]) / (float)d + kLnEps);
+        __syncthreads();
+        float part = 0.f;
+#pragma unroll
+        for (int i = 0; i < kSlots; ++i) {
+          const int g = 2 * i + half;
+          if (g < ng) {
+            float y[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              const int c = g * 16 + q;
+              y[q] = c < d ? (st[i][q] - mean) * rstd * __ldg(op.ln_g + c) + __ldg(op.ln_b + c) : 0.f;
+            }
+            if (post == XP_LN_INPLACE_TO_AOP) {
+#pragma unroll
+              for (int q = 0; q < 16; ++q) st[i][q] = y[q];
+            }
+            if (post == XP_LN_INPLACE_TO_AOP || post == XP_LN_TO_AOP) store_group(sAop, plane, row, g, y);
+            if (post == XP_LN_TO_MEM || op.also_mem) store_group(sMem, plane, row, g, y);
+            if (post == XP_LN_SCORE) {
+#pragma unroll
+              for (int q = 0; q < 16; ++q) {
+                const int c = g * 16 + q;
+                if (valid && c < dt) {
+                  const float df = __ldg(tok_row + c) - y[q];
+                  part = fmaf(df, df, part);
+                  if (recon_out) recon_out[((size_t)window * S + tok_s) * dt + c] = y[q];
+                }
+              }
+            }
+          }
+        }
+        if (post == XP_LN_SCORE) {
+          red[half * 128 + row] = part;
+          __syncthreads();
+          if (half == 0) {
+            const float tot = red[row] + red[128 + row];
+            if (reduction == SF_REDUCE_NONE) {
+              if (valid && scores) scores[(size_t)window * S + tok_s] = tot / (float)dt;
+            } else {
+              float wsum = 0.f;
+#pragma unroll
+              for (int j = 0; j < kSMax; ++j)
+                if (j < S) wsum += __shfl_sync(0xffffffffu, tot, (wb + j) & 31);
+              if (valid && tok_s == 0 && scores) scores[window] = wsum / (float)(S * dt);
+            }
+          }
+          __syncthreads();
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+bool make_geo(const sf_model* m, int S, XfGeo* g) {
+  const XfProgram& p = m->xfprog;
+  if (!p.supported || S < 1 || S > kSMax) return false;
+  if (m->xf.variant == SF_VARIANT_SHOPFORMER && S < 1) return false;
+  g->S = S;
+  g->wpw = 32 / S;
+  g->rows_per_warp = g->wpw * S;
+  g->win_per_tile = 4 * g->wpw;
+  g->plane = 128 * 16;
+  const int width = std::max(std::max(p.dp, p.dtp), 128);       // operand buffers hold activations, ctx and FFN chunks
+  const uint32_t op_bytes = (uint32_t)(width / 8) * g->plane;
+  g->slot_bytes = (p.max_w_bytes + 127) & ~127;
+  uint32_t off = 0;
+  g->off_aop = off; off += op_bytes;
+  g->off_hop = off; off += op_bytes;
+  g->off_mem = off; off += op_bytes;
+  g->off_w = off; off += 2u * (uint32_t)g->slot_bytes;
+  g->off_red = off; off += 2 * 128 * sizeof(float);
+  g->smem_bytes = off;
+  return off <= (uint32_t)m->max_smem_optin;
+}
+
+}  // namespace
+
+bool transformer_bf16_supported(const sf_model* m, int S) {
+  XfGeo g;
+  return make_geo(m, S, &g);
+}
+
+int launch_transformer_bf16(const sf_model* m, const float* tokens, int64_t B, int S, int reduction, float* recon,
+                            float* scores, cudaStream_t st) {
+  if (B == 0) return SF_OK;
+  XfGeo g;
+  SF_REQUIRE(make_geo(m, S, &g), SF_E_UNSUPPORTED,
+             "bf16 tensor-core transformer does not cover this shape (d_model=%d, heads=%d, S=%d)", m->xf.d_model, m->xf.heads, S);
+  SF_REQUIRE(reduction == SF_REDUCE_MEAN || (reduction == SF_REDUCE_NONE && m->xf.variant == SF_VARIANT_SHOPFORMER_2),
+             SF_E_INVALID, "reduction %d not available for variant %d", reduction, m->xf.variant);
+  SF_CUDA_OK(cudaFuncSetAttribute(transformer_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+  const int64_t n_tiles = (B + g.win_per_tile - 1) / g.win_per_tile;
+  const int grid = (int)std::min<int64_t>(n_tiles, m->sm_count);
+  transformer_bf16_kernel<<<grid, kThreads, g.smem_bytes, st>>>(m->xfprog, g, m->xf, tokens, B, reduction, recon, scores);
+  SF_CUDA_OK(cudaGetLastError());
+  return SF_OK;
+}
+
+}  // namespace sf

@@ -123,20 +123,24 @@ class ScoringEngine:
         return poses.to(self.device, torch.float32).contiguous()
 
     # -- the four reference-facing calls
-    def tokenize(self, poses: torch.Tensor) -> torch.Tensor:
+    _PREC = {"fp32": N.SF_PREC_FP32, "bf16": N.SF_PREC_BF16}
+
+    def tokenize(self, poses: torch.Tensor, precision: str = "fp32") -> torch.Tensor:
         x = self._poses(poses)
         B, _, T, _ = x.shape
         S, D = self.token_shape(T)
         out = torch.empty(B, S, D, dtype=torch.float32, device=self.device)
         ws, nb = self._workspace(B, T)
-        N.check(self._lib.sf_tokenize(self._h, _ptr(x), B, T, _ptr(out), _ptr(ws), nb, _stream_ptr(self.device)), "sf_tokenize")
+        N.check(self._lib.sf_tokenize(self._h, _ptr(x), B, T, self._PREC[precision], _ptr(out), _ptr(ws), nb,
+                                      _stream_ptr(self.device)), "sf_tokenize")
         return out
 
-    def reconstruct_tokens(self, tokens: torch.Tensor) -> torch.Tensor:
+    def reconstruct_tokens(self, tokens: torch.Tensor, precision: str = "fp32") -> torch.Tensor:
         t = tokens.to(self.device, torch.float32).contiguous()
         B, S, D = t.shape
         out = torch.empty_like(t)
-        N.check(self._lib.sf_reconstruct_tokens(self._h, _ptr(t), B, S, _ptr(out), None, 0, _stream_ptr(self.device)),
+        N.check(self._lib.sf_reconstruct_tokens(self._h, _ptr(t), B, S, self._PREC[precision], _ptr(out), None, 0,
+                                                _stream_ptr(self.device)),
                 "sf_reconstruct_tokens")
         return out
 

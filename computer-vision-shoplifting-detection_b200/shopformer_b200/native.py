@@ -93,8 +93,8 @@ def load() -> C.CDLL:
         "sf_model_destroy": (None, [vp]),
         "sf_model_token_shape": (C.c_int, [vp, i32, P(i32), P(i32)]),
         "sf_workspace_bytes": (i64, [vp, i64, i32]),
-        "sf_tokenize": (C.c_int, [vp, vp, i64, i32, vp, vp, i64, vp]),
-        "sf_reconstruct_tokens": (C.c_int, [vp, vp, i64, i32, vp, vp, i64, vp]),
+        "sf_tokenize": (C.c_int, [vp, vp, i64, i32, i32, vp, vp, i64, vp]),
+        "sf_reconstruct_tokens": (C.c_int, [vp, vp, i64, i32, i32, vp, vp, i64, vp]),
         "sf_normality_score": (C.c_int, [vp, vp, vp, i64, i32, i32, vp, vp]),
         "sf_score_windows": (C.c_int, [vp, vp, i64, i32, i32, i32, vp, vp, vp, vp, i64, vp]),
         "sf_window_capacity": (i64, [P(SfTracks), P(SfWindowParams)]),

@@ -102,13 +102,13 @@ int64_t sf_workspace_bytes(const sf_model* m, int64_t B, int32_t T);
 /* Replaces: Shopformer.tokenize -> GCAEEncoder.forward
  *   (shopformer/models/shopformer.py:125-136, shopformer/models/gcae.py:331-366;
  *    shopformer_2/models/gcae.py:375-422). */
-int sf_tokenize(const sf_model* m, const float* poses_dev, int64_t B, int32_t T, float* tokens_dev,
-                void* workspace_dev, int64_t workspace_bytes, void* stream);
+int sf_tokenize(const sf_model* m, const float* poses_dev, int64_t B, int32_t T, int32_t precision,
+                float* tokens_dev, void* workspace_dev, int64_t workspace_bytes, void* stream);
 
 /* Replaces: Shopformer.reconstruct_tokens -> ShopformerTransformer.forward
  *   (shopformer/models/shopformer.py:138-148, shopformer/models/transformer.py:304-329;
  *    shopformer_2/models/transformer.py:147-194). */
-int sf_reconstruct_tokens(const sf_model* m, const float* tokens_dev, int64_t B, int32_t S,
+int sf_reconstruct_tokens(const sf_model* m, const float* tokens_dev, int64_t B, int32_t S, int32_t precision,
                           float* recon_dev, void* workspace_dev, int64_t workspace_bytes, void* stream);
 
 /* Replaces: Shopformer.compute_normality_score (shopformer/models/shopformer.py:150-178)

@@ -246,3 +246,22 @@ def test_bf16_unsupported_shapes_are_loud(dropin1, dropin2):
     model = build_model(dropin1, dropin2, "P").cuda()          # adaptive pooling: not on the tensor-core path
     with pytest.raises(NativeError, match="SF_E_UNSUPPORTED"):
         model._sf_engine().score_windows(torch.zeros(2, 2, 24, 17, device="cuda"), precision="bf16")
+
+
+@pytest.mark.parametrize("name", ["A", "A1", "A12", "B", "C"])
+def test_bf16_transformer_alone_matches_oracle(name, golden_dir, dropin1, dropin2):
+    """Tensor-core transformer fed with the ORACLE's tokens (isolates it from the tokenizer), incl. config C
+    (12 heads, 4+4 layers, FFN 512 in four chunks, 136<->144 projections)."""
+    g = np.load(golden_dir / f"score_{name}.npz")
+    model = build_model(dropin1, dropin2, name)
+    kw = oracle_kwargs(model, name)
+    ref = O.score_windows(model.state_dict(), torch.from_numpy(g["poses"]), dtype=torch.float64, **kw)
+    model = model.cuda()
+    eng = model._sf_engine()
+    tok = ref["tokens"].float().cuda()
+    rec = eng.reconstruct_tokens(tok, precision="bf16")
+    err = max_abs_rel(rec.cpu().numpy(), ref["recon"].numpy())
+    s = eng.normality_score(tok, rec)
+    s_err = rel_err(s.cpu().numpy(), ref["score"].numpy())
+    print(f"[bf16 xf {name}] recon max|d|/max|ref| = {err:.3e}, score max rel = {s_err:.3e}")
+    assert err < 2e-2 and s_err < BF16_TOL
