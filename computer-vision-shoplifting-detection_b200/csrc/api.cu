@@ -157,6 +157,12 @@ extern "C" int sf_runner_score(sf_runner* r, const float* poses_host, int64_t B,
   SF_CUDA_OK(cudaSetDevice(r->m->device));
   const int64_t n_chunks = (B + r->chunk - 1) / r->chunk;
   int64_t pending_off[2] = {-1, -1}, pending_n[2] = {0, 0};
+  bool src_pinned = false;
+  if (B > 0) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, poses_host) == cudaSuccess) src_pinned = attr.type == cudaMemoryTypeHost;
+    else cudaGetLastError();
+  }
   for (int64_t c = 0; c < n_chunks; ++c) {
     const int s = (int)(c & 1);
     const int64_t off = c * r->chunk, n = std::min(r->chunk, B - off);
@@ -166,9 +172,14 @@ extern "C" int sf_runner_score(sf_runner* r, const float* poses_host, int64_t B,
       pending_off[s] = -1;
     }
     const float* src = poses_host + (size_t)off * r->pose_elems;
-    const bool direct = (src == r->pin_in[s]);       // producer wrote straight into our pinned slot
-    if (!direct) memcpy(r->pin_in[s], src, (size_t)n * r->pose_elems * sizeof(float));
-    SF_CUDA_OK(cudaMemcpyAsync(r->dev_in[s], r->pin_in[s], (size_t)n * r->pose_elems * sizeof(float), cudaMemcpyHostToDevice, r->st[s]));
+    // page-locked sources (the runner's own slots, cudaHostAlloc / cudaHostRegister / torch pinned memory) are
+    // DMA-ed directly; pageable sources are staged through the runner's pinned slot first.
+    const float* dma_src = src;
+    if (!src_pinned) {
+      memcpy(r->pin_in[s], src, (size_t)n * r->pose_elems * sizeof(float));
+      dma_src = r->pin_in[s];
+    }
+    SF_CUDA_OK(cudaMemcpyAsync(r->dev_in[s], dma_src, (size_t)n * r->pose_elems * sizeof(float), cudaMemcpyHostToDevice, r->st[s]));
     int rc = sf_score_windows(r->m, r->dev_in[s], n, r->T, SF_REDUCE_MEAN, precision, r->dev_out[s], nullptr, nullptr,
                               r->ws[s], r->ws_bytes, r->st[s]);
     if (rc) return rc;

@@ -605,9 +605,14 @@ int launch_tokenizer_bf16(const sf_model* m, const float* poses, int64_t B, int 
   const char* why = "";
   SF_REQUIRE(build_plan(m, T, 1, &pl, &why), SF_E_UNSUPPORTED, "bf16 tensor-core tokenizer does not cover this shape: %s", why);
   SF_CUDA_OK(cudaFuncSetAttribute(tokenizer_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
-  int occ = 1;
-  SF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tokenizer_bf16_kernel, kThreads, pl.smem_bytes));
-  occ = std::max(1, std::min(occ, (int)(512 / pl.tmem_cols)));      // co-resident CTAs must all get their TMEM columns
+  SF_CUDA_OK(cudaFuncSetAttribute(tokenizer_bf16_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  (int)cudaSharedmemCarveoutMaxShared));
+  // CTAs per SM: shared memory (1 KB driver reservation per CTA), registers (128 x 256 threads) and TMEM columns --
+  // co-resident CTAs must all get their tensor-memory allocation or they would serialise on tcgen05.alloc.
+  int smem_per_sm = 0;
+  SF_CUDA_OK(cudaDeviceGetAttribute(&smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, m->device));
+  int occ = smem_per_sm / (int)(pl.smem_bytes + 1024 + 256);
+  occ = std::max(1, std::min(std::min(occ, 2), (int)(512 / pl.tmem_cols)));
   const int64_t n_groups = (B + pl.G - 1) / pl.G;
   const int grid = (int)std::min<int64_t>(n_groups, (int64_t)m->sm_count * occ);
   tokenizer_bf16_kernel<<<grid, kThreads, pl.smem_bytes, st>>>(pl, poses, tokens, B);

@@ -168,7 +168,7 @@ constexpr int kGatherWarps = 8;
 
 // One warp per window.  smem per warp: T*K*3 raw floats (+ T*2 neck floats when V == 18).
 __global__ void __launch_bounds__(kGatherWarps * 32)
-k_gather(const WinCtx cx, const int64_t* __restrict__ n_windows, const int32_t* __restrict__ win_track,
+k_gather(const WinCtx cx, const int64_t* __restrict__ n_windows, int64_t n_fixed, const int32_t* __restrict__ win_track,
          const int32_t* __restrict__ win_start, float* __restrict__ poses, int32_t* __restrict__ frame_idx, int per_warp) {
   extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -178,11 +178,11 @@ k_gather(const WinCtx cx, const int64_t* __restrict__ n_windows, const int32_t* 
   float* neck = slab + ((n_raw + 7) & ~3);         // [T][2], only used when V == 18
   const bool add_neck = (V == 18);
   const int Vsrc = add_neck ? 17 : min(V, K);      // keypoints taken from the detection itself
-  const int64_t nw = *n_windows;
+  const int64_t nw = n_windows ? *n_windows : n_fixed;      // pre-cut windows: the count is known on the host
   const int64_t warps_total = (int64_t)gridDim.x * kGatherWarps;
   for (int64_t w = (int64_t)blockIdx.x * kGatherWarps + warp; w < nw; w += warps_total) {
-    const int tr = __ldg(win_track + w);
-    const int64_t f0 = __ldg(cx.track_off + tr) + __ldg(win_start + w);
+    // pre-cut mode (win_track == nullptr): window w is frames [w*T, (w+1)*T)
+    const int64_t f0 = win_track ? __ldg(cx.track_off + __ldg(win_track + w)) + __ldg(win_start + w) : w * (int64_t)cx.T;
     // ---- stage the contiguous chunk: scalar head, 16-byte body, scalar tail
     const float* src = cx.kp + (size_t)f0 * K * 3;
     const int mis = (int)((reinterpret_cast<uintptr_t>(src) >> 2) & 3);
@@ -194,7 +194,7 @@ k_gather(const WinCtx cx, const int64_t* __restrict__ n_windows, const int32_t* 
     float4* d4 = reinterpret_cast<float4*>(raw + head);
     for (int i = lane; i < body4; i += 32) d4[i] = __ldg(s4 + i);
     for (int i = head + 4 * body4 + lane; i < n_raw; i += 32) raw[i] = __ldg(src + i);
-    if (frame_idx)
+    if (frame_idx && cx.frame_no)
       for (int t = lane; t < T; t += 32) frame_idx[w * T + t] = __ldg(cx.frame_no + f0 + t);
     __syncwarp();
     if (add_neck) {
@@ -413,12 +413,50 @@ extern "C" int sf_window_normalize(const sf_tracks* tr, const sf_window_params* 
   SF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gather, kGatherWarps * 32, smem));
   const int64_t want = (L.n_cand + kGatherWarps - 1) / kGatherWarps;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sms * std::max(occ, 1)));
-  k_gather<<<grid, kGatherWarps * 32, smem, st>>>(cx, n_windows_dev, window_track_dev, window_start_dev, poses_dev,
+  k_gather<<<grid, kGatherWarps * 32, smem, st>>>(cx, n_windows_dev, 0, window_track_dev, window_start_dev, poses_dev,
                                                   frame_idx_dev, per_warp);
   SF_CUDA_OK(cudaGetLastError());
   if (n_windows_host) {
     SF_CUDA_OK(cudaMemcpyAsync(n_windows_host, n_windows_dev, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     SF_CUDA_OK(cudaStreamSynchronize(st));
   }
+  return SF_OK;
+}
+
+// Normalisation of PRE-CUT windows (streaming mode / callers that window on the host): raw_dev is
+// (B, T, K, 3) AoS keypoints, the output is the model's (B, 2, T, V) layout.  No host work, no sync:
+// capturable in a CUDA graph.
+extern "C" int sf_normalize_windows(const float* raw_dev, int64_t B, int32_t T, int32_t K, int32_t V, int32_t normalize,
+                                    float* poses_dev, void* stream) {
+  SF_REQUIRE(B >= 0 && T >= 1 && K >= 1 && V >= 1 && V <= kMaxV && (B == 0 || (raw_dev && poses_dev)), SF_E_INVALID,
+             "sf_normalize_windows: bad argument");
+  SF_REQUIRE(V != 18 || K >= 17, SF_E_INVALID, "neck synthesis needs >= 17 source keypoints");
+  if (B == 0) return SF_OK;
+  WinCtx cx{};
+  cx.kp = raw_dev;
+  cx.K = K;
+  cx.T = T;
+  cx.V = V;
+  cx.normalize = normalize;
+  const int n_raw = T * K * 3;
+  const int per_warp = ((n_raw + 7) & ~3) + ((2 * T + 3) & ~3);
+  const size_t smem = (size_t)per_warp * kGatherWarps * sizeof(float);
+  static thread_local int sms = 0, max_smem = 0, occ = 0, cfg_smem = -1;
+  if (!sms) {
+    int dev = 0;
+    SF_CUDA_OK(cudaGetDevice(&dev));
+    SF_CUDA_OK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    SF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  SF_REQUIRE(smem <= (size_t)max_smem, SF_E_UNSUPPORTED, "sf_normalize_windows: T=%d needs %zu bytes of shared memory", T, smem);
+  if (cfg_smem != (int)smem) {
+    SF_CUDA_OK(cudaFuncSetAttribute(k_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gather, kGatherWarps * 32, smem));
+    cfg_smem = (int)smem;
+  }
+  const int64_t want = (B + kGatherWarps - 1) / kGatherWarps;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sms * std::max(occ, 1)));
+  k_gather<<<grid, kGatherWarps * 32, smem, (cudaStream_t)stream>>>(cx, nullptr, B, nullptr, nullptr, poses_dev, nullptr, per_warp);
+  SF_CUDA_OK(cudaGetLastError());
   return SF_OK;
 }

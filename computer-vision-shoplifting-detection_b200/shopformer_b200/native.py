@@ -32,7 +32,7 @@ ABI_SYMBOLS = (
     "sf_model_token_shape", "sf_workspace_bytes", "sf_tokenize", "sf_reconstruct_tokens",
     "sf_normality_score", "sf_score_windows", "sf_window_capacity", "sf_window_workspace_bytes",
     "sf_window_normalize", "sf_runner_create", "sf_runner_destroy", "sf_runner_score",
-    "sf_runner_pinned_poses", "sf_selftest_umma",
+    "sf_runner_pinned_poses", "sf_selftest_umma", "sf_normalize_windows",
 )
 
 
@@ -105,6 +105,7 @@ def load() -> C.CDLL:
         "sf_runner_score": (C.c_int, [vp, vp, i64, i32, vp]),
         "sf_runner_pinned_poses": (vp, [vp, i32]),
         "sf_selftest_umma": (C.c_int, [i32, i32, i32, i32, vp, vp, vp]),
+        "sf_normalize_windows": (C.c_int, [vp, i64, i32, i32, i32, i32, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -179,6 +179,13 @@ int sf_window_normalize(const sf_tracks* tr, const sf_window_params* p, float* p
                         int32_t* frame_idx_dev, int64_t* n_windows_dev, int64_t* n_windows_host,
                         void* workspace_dev, int64_t workspace_bytes, void* stream);
 
+/* Replaces: _extract_pose_sequence + _normalize_sequence + the (T,V,C)->(C,T,V) transpose for windows that
+ *   are ALREADY cut (shopformer/data/poselift_dataset.py:331-400): raw_dev is (B, T, K, 3) AoS keypoints,
+ *   poses_dev the model's (B, 2, T, V) layout (V = 18 adds the synthetic neck).  No host work and no
+ *   synchronisation, so a streaming tick can be captured in a CUDA graph. */
+int sf_normalize_windows(const float* raw_dev, int64_t B, int32_t T, int32_t K, int32_t V, int32_t normalize,
+                         float* poses_dev, void* stream);
+
 /* ------------------------------------------------------------------ host-buffer runner */
 /* The call a reference-side loop makes per batch: poses on the HOST, scores back on the
  * HOST (shopformer/evaluate.py:90-99, shopformer/inference.py:67-94,
