@@ -49,13 +49,14 @@ struct BfBlk {
   const float *gcn_b, *out_b;          // [npad], zero padded
   const float *gcn_w32, *res_w32;      // block 0 only: fp32 [cin][cout]
   uint32_t off_rowtab, off_mtab;       // smem tables (uint16)
+  uint32_t off_dtab;                   // uint32 descriptor low words: [4 P tiles][4 conv tiles x 9 taps][9 weight taps][residual x 4 tiles][1]
 };
 
 struct BfPlan {
   int n_blocks, V, c_in, G, T0, S_out, c_last;
   const float *in_scale, *in_shift;
   BfBlk blk[kMaxBlocks];
-  uint32_t off_A, off_X0, off_X1, off_WT, off_WG, off_x0, off_m0;
+  uint32_t off_A, off_X0, off_X1, off_WT, off_WG, off_x0, off_x0b, off_m0;
   uint32_t off_xrtab, off_xjtab, off_bias_g, off_bias_o, off_w0, off_r0, off_ellv, off_elld, off_scale, off_shift;
   uint32_t smem_bytes, tmem_cols;
 };
@@ -102,8 +103,8 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
   unsigned char* sX[2] = {smem + pl.off_X0, smem + pl.off_X1};
   unsigned char* sWT = smem + pl.off_WT;
   unsigned char* sWG = smem + pl.off_WG;
-  float* x0 = reinterpret_cast<float*>(smem + pl.off_x0);      // [G][c_in][T0][V] fp32, BN folded
-  float* m0 = reinterpret_cast<float*>(smem + pl.off_m0);      // adjacency-mixed copy
+  float* xbuf[2] = {reinterpret_cast<float*>(smem + pl.off_x0), reinterpret_cast<float*>(smem + pl.off_x0b)};
+  float* m0 = reinterpret_cast<float*>(smem + pl.off_m0);      // adjacency-mixed copy (aliases x1's buffer)
   const uint16_t* xrtab = reinterpret_cast<const uint16_t*>(smem + pl.off_xrtab);   // block-0 residual source per M row
   const uint8_t* xjtab = reinterpret_cast<const uint8_t*>(smem + pl.off_xjtab);     // c*V+v of every x0 element
   const float* bias_g = reinterpret_cast<const float*>(smem + pl.off_bias_g);       // [blk][64]
@@ -160,6 +161,30 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
       }
       mt[mrow] = e;
     }
+    {
+      // every MMA operand address is fixed for the lifetime of the CTA: precompute the descriptor low words
+      uint32_t* dt = reinterpret_cast<uint32_t*>(smem + b.off_dtab);
+      const uint32_t planeA_ = (uint32_t)b.rtot * 16u, w_plane_ = (uint32_t)b.npad * 16u;
+      unsigned char* xin = sX[(bi + 1) & 1];
+      for (int i = threadIdx.x; i < 4 + 36 + 9 + 4 + 1; i += kThreads) {
+        uint32_t v = 0;
+        if (i < 4) {                                   // P GEMM: A tile i
+          v = desc_lo(smem_u32(sA) + (uint32_t)i * 2048u, planeA_);
+        } else if (i < 40) {                           // conv: A view of (tile, tap)
+          const int tile = (i - 4) / 9, tp = (i - 4) % 9;
+          if (tp < b.n_taps)
+            v = desc_lo(smem_u32(sA) + (uint32_t)(b.tap_phase[tp] * b.rows + b.gap * V + tile * 128 + b.tap_rowoff[tp]) * 16u, planeA_);
+        } else if (i < 49) {                           // conv: weight slab of tap
+          const int tp = i - 40;
+          if (tp < b.n_taps) v = desc_lo(smem_u32(sWT) + (uint32_t)(b.tap_k[tp] * (b.npad >> 3)) * w_plane_, w_plane_);
+        } else if (i < 53) {                           // residual: A = phase 0 of x_b at the tile's rows
+          v = desc_lo(smem_u32(xin) + (uint32_t)(b.gap * V + (i - 49) * 128) * 16u, planeA_);
+        } else {                                       // residual weights follow the conv weights
+          v = desc_lo(smem_u32(sWT) + (uint32_t)(kTaps * b.npad * b.npad * 2), w_plane_);
+        }
+        dt[i] = v;
+      }
+    }
     float* bg = reinterpret_cast<float*>(smem + pl.off_bias_g) + bi * 64;
     float* bo = reinterpret_cast<float*>(smem + pl.off_bias_o) + bi * 64;
     for (int i = threadIdx.x; i < 64; i += kThreads) {
@@ -211,21 +236,33 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
   }
 
   const int64_t n_groups = (B + G - 1) / G;
+  // raw poses of a window group are prefetched with cp.async one iteration ahead (16-byte granules)
+  auto prefetch = [&](int64_t g_idx, float* dst) {
+    if (g_idx >= n_groups) return;
+    const int64_t wf = g_idx * G;
+    const int cnt = (int)((B - wf) < (int64_t)G ? (B - wf) : (int64_t)G) * per_w;
+    const float* src = poses + (size_t)wf * per_w;
+    for (int i = threadIdx.x * 4; i < cnt; i += kThreads * 4) cp_async16(dst + i, src + i);
+  };
+  int xcur = 0;
+  prefetch(blockIdx.x, xbuf[0]);
   for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
     const int64_t w_first = grp * G;
     const int nw = (int)((B - w_first) < (int64_t)G ? (B - w_first) : (int64_t)G);
+    float* x0 = xbuf[xcur];
 
     // =============================== block 0 prologue ===============================
     {
       const BfBlk& b = pl.blk[0];
+      cp_async_wait_all();                               // this group's poses (prefetched during the previous group)
+      __syncthreads();
       stage(sWT, b.w_tcn, kTaps * b.npad * b.npad * 2);
-      const float* src = poses + (size_t)w_first * per_w;
+      prefetch(grp + gridDim.x, xbuf[xcur ^ 1]);
       const int n_valid = nw * per_w;
       for (int i = threadIdx.x; i < G * per_w; i += kThreads) {
         const int j = xjtab[i];
-        x0[i] = i < n_valid ? fmaf(__ldg(src + i), scale_s[j], shift_s[j]) : 0.f;
+        x0[i] = i < n_valid ? fmaf(x0[i], scale_s[j], shift_s[j]) : 0.f;      // folded BatchNorm1d, in place
       }
-      if (pl.n_blocks > 1) zero_fill(sX[0], pl.blk[1].rtot * pl.blk[1].kin * 2);
       __syncthreads();
       // m0 <- A_hat . x0 over the keypoint axis
       for (int i = threadIdx.x; i < G * per_w; i += kThreads) {
@@ -266,6 +303,9 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
         }
         *reinterpret_cast<uint4*>(dstp + (size_t)r * 16) = out;
       }
+      __syncthreads();                                    // m0 (aliases x1's buffer) is dead from here
+      if (pl.n_blocks > 1) zero_fill(sX[0], pl.blk[1].rtot * pl.blk[1].kin * 2);
+      xcur ^= 1;
     }
 
     for (int bi = 0; bi < pl.n_blocks; ++bi) {
@@ -329,8 +369,9 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
           const uint32_t idesc = make_idesc(128, b.npad, false);
           const uint32_t w_plane = (uint32_t)b.npad * 16u;
           const uint32_t blo0 = desc_lo(smem_u32(sWG), w_plane);
+          const uint32_t* dt = reinterpret_cast<const uint32_t*>(smem + b.off_dtab);
           for (int tile = warp; tile < p_tiles; tile += kIssuers) {
-            uint32_t alo = desc_lo(smem_u32(sA) + (uint32_t)tile * 2048u, planeA);
+            uint32_t alo = dt[tile];
             uint32_t blo = blo0;
             for (int ks = 0; ks < (b.kin >> 4); ++ks) {
               umma_bf16(tmem + (uint32_t)(tile * dcol), desc_join(alo), desc_join(blo), idesc, ks > 0);
@@ -340,7 +381,8 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
           }
           umma_commit(&bar);
         }
-        mbar_wait(&bar, parity);
+        if (warp == 0) mbar_wait(&bar, parity);     // one polling warp; the others block in the hardware barrier
+        __syncthreads();
         parity ^= 1;
         tc_fence_after();
         // ---- g = relu(P + b) -> bf16 over M in place (gap rows -> 0)
@@ -382,14 +424,14 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
         const uint32_t idesc = make_idesc(128, b.npad, false);
         const uint32_t w_plane = (uint32_t)b.npad * 16u;
         const int ksteps = b.npad >> 4;
-        const uint32_t a_base = smem_u32(sA), w_base = smem_u32(sWT);
+        const uint32_t* dt = reinterpret_cast<const uint32_t*>(smem + b.off_dtab);
+        const int n_taps = b.n_taps;
         for (int tile = warp; tile < m_tiles; tile += kIssuers) {
           const uint32_t d = tmem + (uint32_t)(tile * dcol);
           uint32_t acc_flag = 0;
-          for (int tp = 0; tp < b.n_taps; ++tp) {
-            const int row0 = b.tap_phase[tp] * b.rows + b.gap * V + tile * 128 + b.tap_rowoff[tp];
-            uint32_t alo = desc_lo(a_base + (uint32_t)row0 * 16u, planeA);
-            uint32_t blo = desc_lo(w_base + (uint32_t)(b.tap_k[tp] * (b.npad >> 3)) * w_plane, w_plane);
+          for (int tp = 0; tp < n_taps; ++tp) {
+            uint32_t alo = dt[4 + tile * 9 + tp];
+            uint32_t blo = dt[40 + tp];
             for (int ks = 0; ks < ksteps; ++ks) {
               umma_bf16(d, desc_join(alo), desc_join(blo), idesc, acc_flag);
               acc_flag = 1;
@@ -398,9 +440,8 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
             }
           }
           if (bi > 0 && !b.identity_res) {
-            const int row0 = b.gap * V + tile * 128;                       // phase 0, offset 0: x[s*t']
-            uint32_t alo = desc_lo(smem_u32(sXin) + (uint32_t)row0 * 16u, planeA);   // x_b shares the block's geometry
-            uint32_t blo = desc_lo(w_base + (uint32_t)(kTaps * b.npad * b.npad * 2), w_plane);
+            uint32_t alo = dt[49 + tile];                                  // phase 0, offset 0: x[s*t'] (x_b shares the geometry)
+            uint32_t blo = dt[53];
             for (int ks = 0; ks < (b.kin >> 4); ++ks) {
               umma_bf16(d, desc_join(alo), desc_join(blo), idesc, 1u);
               alo += (2u * planeA) >> 4;
@@ -410,7 +451,8 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
         }
         umma_commit(&bar);
       }
-      mbar_wait(&bar, parity);
+      if (warp == 0) mbar_wait(&bar, parity);
+      __syncthreads();
       parity ^= 1;
       tc_fence_after();
       // ---- x_{b+1} = relu(acc + bias + residual): bf16 into the next block's phase layout, or fp32 tokens
@@ -563,18 +605,27 @@ bool build_plan(const sf_model* m, int T, int G, BfPlan* pl, const char** why) {
   auto up = [](size_t x) { return (uint32_t)((x + 127) & ~size_t(127)); };
   // Operand buffers first: an MMA tile that runs past the end of one buffer (rows that are discarded)
   // only ever reads the bytes of the next region, never past the allocation.
+  // x2 (X1) is first written by block 1's epilogue, when the A buffer only holds M_b / g_b of blocks >= 1:
+  // it lives in the tail of the A region that only g0 needs.
+  size_t maxA_late = 0;
+  for (int i = 1; i < nb; ++i) maxA_late = std::max(maxA_late, (size_t)pl->blk[i].rtot * std::max(pl->blk[i].npad, pl->blk[i].kin) * 2);
+  const size_t xbytes = (size_t)G * tk.c_in * T * V * sizeof(float);
+  if (xbytes % 16) { *why = "window size not a multiple of 16 bytes"; return false; }
   uint32_t off = 0;
-  pl->off_A = off; off += up(maxA);
-  pl->off_X0 = off; off += up(std::max(maxX[0], (size_t)16));
-  pl->off_X1 = off; off += up(std::max(std::max(maxX[1], (size_t)16), (size_t)G * tk.c_in * T * V * sizeof(float)));
+  pl->off_A = off;
+  pl->off_X1 = off + up(maxA_late);
+  off += std::max(up(maxA), up(maxA_late) + up(std::max(maxX[1], (size_t)16)));
+  pl->off_X0 = off; off += up(std::max(std::max(maxX[0], (size_t)16), xbytes));
   pl->off_WT = off; off += up(maxWT);
   pl->off_WG = off; off += up(std::max(maxWG, (size_t)16));
-  const size_t xbytes = (size_t)G * tk.c_in * T * V * sizeof(float);
   pl->off_x0 = off; off += up(xbytes);
-  pl->off_m0 = pl->off_X1;                       // m0 is dead before x2 (X1) is first written
+  pl->off_x0b = off; off += up(xbytes);
+  pl->off_m0 = pl->off_X0;                       // m0 is dead before x1 (X0) is cleared and written
   for (int i = 0; i < nb; ++i) {
     pl->blk[i].off_rowtab = off; off += up((size_t)pl->blk[i].rtot * 2);
     pl->blk[i].off_mtab = off; off += up((size_t)pl->blk[i].mrows * 2);
+    pl->blk[i].off_dtab = off; off += up(54 * 4);
+    if ((pl->blk[i].mrows + 127) / 128 > 4 || (i > 0 && (pl->blk[i].rtot + 127) / 128 > 4)) { *why = "more than 4 accumulator tiles per phase"; return false; }
   }
   pl->off_xrtab = off; off += up((size_t)pl->blk[0].mrows * 2);
   pl->off_xjtab = off; off += up((size_t)G * tk.c_in * T * V);
