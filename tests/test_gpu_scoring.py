@@ -194,7 +194,7 @@ def test_errors_are_loud(dropin1, dropin2):
 BF16_TOL = 1e-2          # north-star tolerance for the bf16 path (relative error of the score)
 
 
-@pytest.mark.parametrize("name", ["A", "A12", "B"])
+@pytest.mark.parametrize("name", ["A", "A1", "A12", "B", "C"])
 def test_bf16_tensor_core_path_matches_reference(name, golden_dir, dropin1, dropin2):
     g = np.load(golden_dir / f"score_{name}.npz")
     model = build_model(dropin1, dropin2, name).cuda()
