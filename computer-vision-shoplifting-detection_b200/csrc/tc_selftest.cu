@@ -111,3 +111,57 @@ extern "C" int sf_selftest_umma(int32_t mode, int32_t N, int32_t K, int32_t shif
   cudaFree(dD);
   return SF_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// debugging aid (not part of the C ABI): cycles for `n_mma` back-to-back 128 x N x 16 MMAs issued by one thread
+// on no-swizzle operands (garbage data), measured from first issue to mbarrier completion.
+namespace sf {
+namespace {
+__global__ void __launch_bounds__(128, 1) umma_timing_kernel(int N, int n_mma, int a_rows_shift, long long* out) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  using namespace tc;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) tmem_alloc(&tmem_base, 256);
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  for (int i = threadIdx.x; i < 48 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem_raw)[i] = 0x3c003c00u;
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = make_idesc(128, N, false);
+    const uint32_t a_plane = 1024u * 16u, b_plane = (uint32_t)N * 16u;
+    const uint64_t ad = make_desc(smem_u32(smem_raw) + (uint32_t)a_rows_shift * 16u, a_plane, 128u);
+    const uint64_t bd = make_desc(smem_u32(smem_raw) + 40960u, b_plane, 128u);
+    const long long t0 = clock64();
+    for (int k = 0; k < n_mma; ++k) umma_bf16(tmem_base, ad, bd, idesc, k > 0);
+    const long long t1 = clock64();
+    umma_commit(&bar);
+    while (!mbar_try_wait(&bar, 0)) {
+    }
+    const long long t2 = clock64();
+    out[0] = t1 - t0;
+    out[1] = t2 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+}  // namespace
+}  // namespace sf
+
+extern "C" int sfdbg_umma_timing(int N, int n_mma, int shift, long long* out_host) {
+  long long* d = nullptr;
+  if (cudaMalloc(&d, 16) != cudaSuccess) return -1;
+  cudaFuncSetAttribute(sf::umma_timing_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  sf::umma_timing_kernel<<<1, 128, 64 * 1024>>>(N, n_mma, shift, d);
+  if (cudaDeviceSynchronize() != cudaSuccess) return -2;
+  cudaMemcpy(out_host, d, 16, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return 0;
+}

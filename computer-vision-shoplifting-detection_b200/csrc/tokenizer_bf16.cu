@@ -27,6 +27,8 @@
 #include "tc_common.cuh"
 
 namespace sf {
+__device__ long long g_tok_timing[512];
+__device__ int g_tok_timing_on = 0;
 namespace {
 
 using namespace tc;
@@ -93,6 +95,64 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
 }
 
+
+// ---- branch-free, loads-first inner loops (the CUDA-core phases are latency bound: keep independent loads in flight)
+// packed ELL entry: .x = adjacency value, .y = row delta (u - v) as int bits; unused entries are (0, 0)
+template <int W>
+__device__ __forceinline__ void mix_x0(const float* __restrict__ x0, float* __restrict__ m0, const uint8_t* __restrict__ xvtab,
+                                       const float2* __restrict__ ell, int n) {
+  for (int i = threadIdx.x; i < n; i += kThreads) {
+    const int v = xvtab[i];
+    float2 e[W];
+#pragma unroll
+    for (int k = 0; k < W; ++k) e[k] = ell[v * kEllMax + k];
+    float xv[W];
+#pragma unroll
+    for (int k = 0; k < W; ++k) xv[k] = x0[i + __float_as_int(e[k].y)];
+    float a = 0.f;
+#pragma unroll
+    for (int k = 0; k < W; ++k) a = fmaf(e[k].x, xv[k], a);
+    m0[i] = a;
+  }
+}
+
+// adjacency mix of one 8-channel granule column of the bf16 activation buffer: dst[r] = sum_k val_k * src[r + delta_k]
+template <int W>
+__device__ __forceinline__ void mix_rows(const unsigned char* __restrict__ plane, unsigned char* __restrict__ dstp,
+                                         const uint16_t* __restrict__ rt, const float2* __restrict__ ell, int r_first,
+                                         int r_step, int rtot) {
+  for (int r = r_first; r < rtot; r += r_step) {
+    const uint32_t en = rt[r];
+    const bool ok = en != kGap;
+    const int v = ok ? (int)(en & 31) : 0;
+    float2 e[W];
+#pragma unroll
+    for (int k = 0; k < W; ++k) e[k] = ell[v * kEllMax + k];
+    uint4 q[W];
+#pragma unroll
+    for (int k = 0; k < W; ++k) q[k] = *reinterpret_cast<const uint4*>(plane + (size_t)(r + (ok ? __float_as_int(e[k].y) : 0)) * 16);
+    float a[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) a[c] = 0.f;
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+      float f[8];
+      unpack8(q[k], f);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) a[c] = fmaf(e[k].x, f[c], a[c]);
+    }
+    *reinterpret_cast<uint4*>(dstp + (size_t)r * 16) = ok ? pack8(a) : make_uint4(0, 0, 0, 0);
+  }
+}
+
+#define TOK_STAMP(id)                                                                   \
+  do {                                                                                  \
+    if (timing && threadIdx.x == 0 && stamp_i < 510) {                                  \
+      g_tok_timing[stamp_i++] = (long long)(id);                                        \
+      g_tok_timing[stamp_i++] = clock64();                                              \
+    }                                                                                   \
+  } while (0)
+
 __global__ void __launch_bounds__(kThreads, 2)
 tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict__ poses, float* __restrict__ tokens,
                       int64_t B) {
@@ -111,8 +171,8 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
   const float* bias_o = reinterpret_cast<const float*>(smem + pl.off_bias_o);
   const float* w0s = reinterpret_cast<const float*>(smem + pl.off_w0);              // [4][64]
   const float* r0s = reinterpret_cast<const float*>(smem + pl.off_r0);              // [4][64]
-  const float* ellv = reinterpret_cast<const float*>(smem + pl.off_ellv);           // [blk][V][kEllMax]
-  const int* elld = reinterpret_cast<const int*>(smem + pl.off_elld);               // row delta (u - v)
+  const float2* ell2 = reinterpret_cast<const float2*>(smem + pl.off_ellv);         // [blk][V][kEllMax] (value, row delta)
+  const uint8_t* xvtab = reinterpret_cast<const uint8_t*>(smem + pl.off_elld);      // keypoint index of every x0 element
   const float* scale_s = reinterpret_cast<const float*>(smem + pl.off_scale);
   const float* shift_s = reinterpret_cast<const float*>(smem + pl.off_shift);
   const int V = pl.V, G = pl.G;
@@ -191,13 +251,13 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
       bg[i] = i < b.npad ? __ldg(b.gcn_b + i) : 0.f;
       bo[i] = i < b.npad ? __ldg(b.out_b + i) : 0.f;
     }
-    float* ev = reinterpret_cast<float*>(smem + pl.off_ellv) + bi * V * kEllMax;
-    int* ed = reinterpret_cast<int*>(smem + pl.off_elld) + bi * V * kEllMax;
+    float2* e2 = reinterpret_cast<float2*>(smem + pl.off_ellv) + bi * V * kEllMax;
     for (int i = threadIdx.x; i < V * kEllMax; i += kThreads) {
       const int v = i / kEllMax, k = i % kEllMax;
       const bool ok = k < b.ell_width;
-      ev[i] = ok ? __ldg(b.ell_val + v * b.ell_width + k) : 0.f;
-      ed[i] = ok ? __ldg(b.ell_col + v * b.ell_width + k) - v : 0;
+      const float val = ok ? __ldg(b.ell_val + v * b.ell_width + k) : 0.f;
+      const int dl = (ok && val != 0.f) ? __ldg(b.ell_col + v * b.ell_width + k) - v : 0;
+      e2[i] = make_float2(val, __int_as_float(dl));
     }
   }
   {
@@ -215,6 +275,7 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
     for (int i = threadIdx.x; i < G * per_w; i += kThreads) {
       const int r = i % per_w;
       reinterpret_cast<uint8_t*>(smem + pl.off_xjtab)[i] = (uint8_t)((r / (pl.T0 * V)) * V + r % V);
+      reinterpret_cast<uint8_t*>(smem + pl.off_elld)[i] = (uint8_t)(r % V);
     }
   }
   tc_fence_before();
@@ -222,18 +283,14 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
   uint32_t parity = 0;
+  const bool timing = g_tok_timing_on && blockIdx.x == 0;
+  int stamp_i = 0;
 
-  // block-0 graph-conv weights of this thread's 8-channel chunk stay in registers for the whole kernel
+  // block-0 graph-conv: this thread's 8-channel chunk (weights are re-read from smem per window group so that
+  // they do not occupy 40 registers during the other phases)
   const int chunks0 = pl.blk[0].npad >> 3;
   const int tpc0 = kThreads / chunks0;                  // threads per chunk
   const int j0 = threadIdx.x / tpc0, r0_first = threadIdx.x - j0 * tpc0;
-  float gw[4][8], gb[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    gb[e] = bias_g[j0 * 8 + e];
-#pragma unroll
-    for (int ci = 0; ci < 4; ++ci) gw[ci][e] = w0s[ci * 64 + j0 * 8 + e];
-  }
 
   const int64_t n_groups = (B + G - 1) / G;
   // raw poses of a window group are prefetched with cp.async one iteration ahead (16-byte granules)
@@ -250,6 +307,7 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
     const int64_t w_first = grp * G;
     const int nw = (int)((B - w_first) < (int64_t)G ? (B - w_first) : (int64_t)G);
     float* x0 = xbuf[xcur];
+    TOK_STAMP(100);
 
     // =============================== block 0 prologue ===============================
     {
@@ -264,44 +322,41 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
         x0[i] = i < n_valid ? fmaf(x0[i], scale_s[j], shift_s[j]) : 0.f;      // folded BatchNorm1d, in place
       }
       __syncthreads();
+      TOK_STAMP(101);
       // m0 <- A_hat . x0 over the keypoint axis
-      for (int i = threadIdx.x; i < G * per_w; i += kThreads) {
-        const int j = xjtab[i];
-        const int v = j % V;
-        float a = 0.f;
-#pragma unroll
-        for (int k = 0; k < kEllMax; ++k) {
-          const float val = ellv[v * kEllMax + k];
-          if (k < b.ell_width) a = fmaf(val, x0[i + elld[v * kEllMax + k]], a);
-        }
-        m0[i] = a;
-      }
+      if (b.ell_width <= 5) mix_x0<5>(x0, m0, xvtab, ell2, G * per_w);
+      else mix_x0<kEllMax>(x0, m0, xvtab, ell2, G * per_w);
       __syncthreads();
+      TOK_STAMP(102);
       // g0 = relu(W0 . m0 + b0) -> bf16 rows of the phase-split operand buffer; one 16-byte granule per item
       const uint16_t* rt = reinterpret_cast<const uint16_t*>(smem + b.off_rowtab);
       const int tv = pl.T0 * V;
       unsigned char* dstp = sA + (size_t)j0 * b.rtot * 16;
+      const int cin0 = b.cin;
+      float gw[4][8], gb[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        gb[e] = bias_g[j0 * 8 + e];
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) gw[ci][e] = w0s[ci * 64 + j0 * 8 + e];
+      }
       for (int r = r0_first; r < b.rtot; r += tpc0) {
-        const uint32_t e = rt[r];
-        uint4 out = make_uint4(0, 0, 0, 0);
-        if (e != kGap && (int)(e >> 11) < nw) {
-          const int v = e & 31, t = (e >> 5) & 63, w = e >> 11;
-          const float* mp = m0 + w * per_w + t * V + v;
-          float g[8];
+        const uint32_t e1 = rt[r];
+        const bool ok1 = e1 != kGap && (int)(e1 >> 11) < nw;
+        const int o1 = ok1 ? (int)(e1 >> 11) * per_w + (int)((e1 >> 5) & 63) * V + (int)(e1 & 31) : 0;
+        float mv1[4];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) g[q] = gb[q];
+        for (int ci = 0; ci < 4; ++ci) mv1[ci] = ci < cin0 ? m0[o1 + ci * tv] : 0.f;
+        float g1[8];
 #pragma unroll
-          for (int ci = 0; ci < 4; ++ci)
-            if (ci < b.cin) {
-              const float mv = mp[ci * tv];
+        for (int q = 0; q < 8; ++q) g1[q] = gb[q];
 #pragma unroll
-              for (int q = 0; q < 8; ++q) g[q] = fmaf(gw[ci][q], mv, g[q]);
-            }
+        for (int ci = 0; ci < 4; ++ci)
 #pragma unroll
-          for (int q = 0; q < 8; ++q) g[q] = fmaxf(g[q], 0.f);
-          out = pack8(g);
-        }
-        *reinterpret_cast<uint4*>(dstp + (size_t)r * 16) = out;
+          for (int q = 0; q < 8; ++q) g1[q] = fmaf(gw[ci][q], mv1[ci], g1[q]);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) g1[q] = fmaxf(g1[q], 0.f);
+        *reinterpret_cast<uint4*>(dstp + (size_t)r * 16) = ok1 ? pack8(g1) : make_uint4(0, 0, 0, 0);
       }
       __syncthreads();                                    // m0 (aliases x1's buffer) is dead from here
       if (pl.n_blocks > 1) zero_fill(sX[0], pl.blk[1].rtot * pl.blk[1].kin * 2);
@@ -319,6 +374,7 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
       const int groups = b.npad >> 4;               // 16-column groups per accumulator tile
       const int g_first = groups > 1 ? col_half : 0, g_step = groups > 1 ? 2 : 1;
       const bool idle_half = groups == 1 && col_half == 1;
+      TOK_STAMP(110 + bi * 10);
       if (bi > 0) {
         // ---- stage this block's weights, clear the output buffer, adjacency mix x_b -> A (bf16)
         stage(sWG, b.w_gcn, b.kin * b.npad * 2);
@@ -331,37 +387,16 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
           const int j = threadIdx.x / tpc;
           const unsigned char* plane = sXin + (size_t)j * planeA;
           unsigned char* dstp = sA + (size_t)j * planeA;
-          const float* ev = ellv + bi * V * kEllMax;
-          const int* ed = elld + bi * V * kEllMax;
-          for (int r = threadIdx.x - j * tpc; r < b.rtot; r += tpc) {
-            const uint32_t e = rt[r];
-            uint4 out = make_uint4(0, 0, 0, 0);
-            if (e != kGap) {
-              const int v = e & 31;
-              float a[8];
-#pragma unroll
-              for (int q = 0; q < 8; ++q) a[q] = 0.f;
-#pragma unroll
-              for (int k = 0; k < kEllMax; ++k) {
-                if (k < b.ell_width) {
-                  const float val = ev[v * kEllMax + k];
-                  if (val != 0.f) {
-                    float f[8];
-                    unpack8(*reinterpret_cast<const uint4*>(plane + (size_t)(r + ed[v * kEllMax + k]) * 16), f);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) a[q] = fmaf(val, f[q], a[q]);
-                  }
-                }
-              }
-              out = pack8(a);
-            }
-            *reinterpret_cast<uint4*>(dstp + (size_t)r * 16) = out;
-          }
+          const float2* el = ell2 + bi * V * kEllMax;
+          if (b.ell_width <= 5) mix_rows<5>(plane, dstp, rt, el, threadIdx.x - j * tpc, tpc, b.rtot);
+          else mix_rows<kEllMax>(plane, dstp, rt, el, threadIdx.x - j * tpc, tpc, b.rtot);
         }
+        TOK_STAMP(111 + bi * 10);
         cp_async_wait_all();
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
+        TOK_STAMP(112 + bi * 10);
         // ---- P = M . W  (all rows of all phases), accumulators in TMEM
         const int p_tiles = (b.rtot + 127) >> 7;
         if (lane == 0 && warp < kIssuers) {
@@ -385,38 +420,50 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
         __syncthreads();
         parity ^= 1;
         tc_fence_after();
+        TOK_STAMP(113 + bi * 10);
         // ---- g = relu(P + b) -> bf16 over M in place (gap rows -> 0)
         const float* bgp = bias_g + bi * 64;
-        for (int tile = 0; tile < p_tiles; ++tile) {
-          const int r = tile * 128 + lane_grp * 32 + lane;
-          const bool in = r < b.rtot;
-          const bool data = in && rt[r] != kGap;
-          if (idle_half) break;
+        if (!idle_half) {
           for (int gq = g_first; gq < groups; gq += g_step) {
-            float acc[16];
-            tmem_ld16(tmem + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(tile * dcol + gq * 16), acc);
-            tmem_ld_wait();
-            if (in) {
-              float y[16];
+            // all TMEM loads of this column group first (one wait), then the arithmetic
+            float4 bb[4];
 #pragma unroll
-              for (int q4 = 0; q4 < 4; ++q4) {
-                const float4 bb = *reinterpret_cast<const float4*>(bgp + gq * 16 + q4 * 4);
-                y[q4 * 4 + 0] = data ? fmaxf(acc[q4 * 4 + 0] + bb.x, 0.f) : 0.f;
-                y[q4 * 4 + 1] = data ? fmaxf(acc[q4 * 4 + 1] + bb.y, 0.f) : 0.f;
-                y[q4 * 4 + 2] = data ? fmaxf(acc[q4 * 4 + 2] + bb.z, 0.f) : 0.f;
-                y[q4 * 4 + 3] = data ? fmaxf(acc[q4 * 4 + 3] + bb.w, 0.f) : 0.f;
+            for (int q4 = 0; q4 < 4; ++q4) bb[q4] = *reinterpret_cast<const float4*>(bgp + gq * 16 + q4 * 4);
+            for (int t0 = 0; t0 < p_tiles; t0 += 1) {
+            float acc[1][16];
+#pragma unroll
+            for (int tl = 0; tl < 1; ++tl)
+              if (t0 + tl < p_tiles) tmem_ld16(tmem + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)((t0 + tl) * dcol + gq * 16), acc[tl]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int tl = 0; tl < 1; ++tl) {
+              const int tile = tl;
+              const int r = (t0 + tl) * 128 + lane_grp * 32 + lane;
+              if (t0 + tl < p_tiles && r < b.rtot) {
+                const bool data = rt[r] != kGap;
+                float y[16];
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                  y[q4 * 4 + 0] = data ? fmaxf(acc[tile][q4 * 4 + 0] + bb[q4].x, 0.f) : 0.f;
+                  y[q4 * 4 + 1] = data ? fmaxf(acc[tile][q4 * 4 + 1] + bb[q4].y, 0.f) : 0.f;
+                  y[q4 * 4 + 2] = data ? fmaxf(acc[tile][q4 * 4 + 2] + bb[q4].z, 0.f) : 0.f;
+                  y[q4 * 4 + 3] = data ? fmaxf(acc[tile][q4 * 4 + 3] + bb[q4].w, 0.f) : 0.f;
+                }
+                *reinterpret_cast<uint4*>(sA + ((size_t)(gq * 2) * b.rtot + r) * 16) = pack8(y);
+                *reinterpret_cast<uint4*>(sA + ((size_t)(gq * 2 + 1) * b.rtot + r) * 16) = pack8(y + 8);
               }
-              *reinterpret_cast<uint4*>(sA + ((size_t)(gq * 2) * b.rtot + r) * 16) = pack8(y);
-              *reinterpret_cast<uint4*>(sA + ((size_t)(gq * 2 + 1) * b.rtot + r) * 16) = pack8(y + 8);
+            }
             }
           }
         }
       } else {
         cp_async_wait_all();
       }
+      TOK_STAMP(114 + bi * 10);
       fence_proxy_async();
       tc_fence_before();
       __syncthreads();
+      TOK_STAMP(115 + bi * 10);
       // ---- temporal conv (+ residual conv) as shifted-view MMAs
       const int m_tiles = (b.mrows + 127) >> 7;
       if (lane == 0 && warp < kIssuers) {
@@ -455,66 +502,79 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
       __syncthreads();
       parity ^= 1;
       tc_fence_after();
+      TOK_STAMP(116 + bi * 10);
       // ---- x_{b+1} = relu(acc + bias + residual): bf16 into the next block's phase layout, or fp32 tokens
       const bool last = bi + 1 == pl.n_blocks;
       const float* bop = bias_o + bi * 64;
       const int nxt_rtot = last ? 0 : pl.blk[bi + 1].rtot;
       const int tv = pl.T0 * V;
-      for (int tile = 0; tile < m_tiles; ++tile) {
-        if (idle_half) break;
-        const int mrow = tile * 128 + lane_grp * 32 + lane;
-        const uint32_t e = mrow < b.mrows ? mt[mrow] : kGap;
-        const int w = e >> 11, target = e & 0x7FF;
-        const bool data = e != kGap && w < nw;
+      if (!idle_half) {
         for (int gq = g_first; gq < groups; gq += g_step) {
-          float acc[16];
-          tmem_ld16(tmem + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(tile * dcol + gq * 16), acc);
+          // all TMEM loads of this column group first (one wait), then the arithmetic of each tile
+          float4 bb[4];
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) bb[q4] = *reinterpret_cast<const float4*>(bop + gq * 16 + q4 * 4);
+          for (int t0 = 0; t0 < m_tiles; t0 += 1) {
+          float accs[1][16];
+#pragma unroll
+          for (int tl = 0; tl < 1; ++tl)
+            if (t0 + tl < m_tiles) tmem_ld16(tmem + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)((t0 + tl) * dcol + gq * 16), accs[tl]);
           tmem_ld_wait();
-          if (!data) continue;
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            const float4 bb = *reinterpret_cast<const float4*>(bop + gq * 16 + q4 * 4);
-            acc[q4 * 4 + 0] += bb.x; acc[q4 * 4 + 1] += bb.y; acc[q4 * 4 + 2] += bb.z; acc[q4 * 4 + 3] += bb.w;
-          }
-          if (bi == 0) {
-            // K = Cin (2) residual conv on CUDA cores in fp32 from the un-mixed input
-            const float* xp = x0 + xrtab[mrow];
+          for (int tl = 0; tl < 1; ++tl) {
+            const int tile = tl;
+            if (t0 + tl >= m_tiles) continue;
+            const int mrow = (t0 + tl) * 128 + lane_grp * 32 + lane;
+            const uint32_t e = mrow < b.mrows ? mt[mrow] : kGap;
+            const int w = e >> 11, target = e & 0x7FF;
+            if (e == kGap || w >= nw) continue;
+            float* acc = accs[tile];
 #pragma unroll
-            for (int ci = 0; ci < 4; ++ci)
-              if (ci < b.cin) {
-                const float xv = xp[ci * tv];
+            for (int q4 = 0; q4 < 4; ++q4) {
+              acc[q4 * 4 + 0] += bb[q4].x; acc[q4 * 4 + 1] += bb[q4].y; acc[q4 * 4 + 2] += bb[q4].z; acc[q4 * 4 + 3] += bb[q4].w;
+            }
+            if (bi == 0) {
+              // K = Cin (2) residual conv on CUDA cores in fp32 from the un-mixed input
+              const float* xp = x0 + xrtab[mrow];
 #pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) {
-                  const float4 rr = *reinterpret_cast<const float4*>(r0s + ci * 64 + gq * 16 + q4 * 4);
-                  acc[q4 * 4 + 0] = fmaf(rr.x, xv, acc[q4 * 4 + 0]); acc[q4 * 4 + 1] = fmaf(rr.y, xv, acc[q4 * 4 + 1]);
-                  acc[q4 * 4 + 2] = fmaf(rr.z, xv, acc[q4 * 4 + 2]); acc[q4 * 4 + 3] = fmaf(rr.w, xv, acc[q4 * 4 + 3]);
+              for (int ci = 0; ci < 4; ++ci)
+                if (ci < b.cin) {
+                  const float xv = xp[ci * tv];
+#pragma unroll
+                  for (int q4 = 0; q4 < 4; ++q4) {
+                    const float4 rr = *reinterpret_cast<const float4*>(r0s + ci * 64 + gq * 16 + q4 * 4);
+                    acc[q4 * 4 + 0] = fmaf(rr.x, xv, acc[q4 * 4 + 0]); acc[q4 * 4 + 1] = fmaf(rr.y, xv, acc[q4 * 4 + 1]);
+                    acc[q4 * 4 + 2] = fmaf(rr.z, xv, acc[q4 * 4 + 2]); acc[q4 * 4 + 3] = fmaf(rr.w, xv, acc[q4 * 4 + 3]);
+                  }
                 }
-              }
-          } else if (b.identity_res) {
-            const int r = b.gap * V + mrow;                                  // phase 0 (stride 1)
-            float f[8];
-            unpack8(*reinterpret_cast<const uint4*>(sXin + ((size_t)(gq * 2) * b.rtot + r) * 16), f);
+            } else if (b.identity_res) {
+              const int r = b.gap * V + mrow;                                  // phase 0 (stride 1)
+              float f[8];
+              unpack8(*reinterpret_cast<const uint4*>(sXin + ((size_t)(gq * 2) * b.rtot + r) * 16), f);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) acc[q] += f[q];
-            unpack8(*reinterpret_cast<const uint4*>(sXin + ((size_t)(gq * 2 + 1) * b.rtot + r) * 16), f);
+              for (int q = 0; q < 8; ++q) acc[q] += f[q];
+              unpack8(*reinterpret_cast<const uint4*>(sXin + ((size_t)(gq * 2 + 1) * b.rtot + r) * 16), f);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) acc[8 + q] += f[q];
+              for (int q = 0; q < 8; ++q) acc[8 + q] += f[q];
+            }
+#pragma unroll
+            for (int q = 0; q < 16; ++q) acc[q] = fmaxf(acc[q], 0.f);
+            if (!last) {
+              *reinterpret_cast<uint4*>(sXout + ((size_t)(gq * 2) * nxt_rtot + target) * 16) = pack8(acc);
+              *reinterpret_cast<uint4*>(sXout + ((size_t)(gq * 2 + 1) * nxt_rtot + target) * 16) = pack8(acc + 8);
+            } else {
+              float* dst = tokens + (size_t)(w_first + w) * pl.S_out * (size_t)(pl.c_last * V) + target;
+#pragma unroll
+              for (int q = 0; q < 16; ++q)
+                if (gq * 16 + q < b.cout) dst[(gq * 16 + q) * V] = acc[q];
+            }
           }
-#pragma unroll
-          for (int q = 0; q < 16; ++q) acc[q] = fmaxf(acc[q], 0.f);
-          if (!last) {
-            *reinterpret_cast<uint4*>(sXout + ((size_t)(gq * 2) * nxt_rtot + target) * 16) = pack8(acc);
-            *reinterpret_cast<uint4*>(sXout + ((size_t)(gq * 2 + 1) * nxt_rtot + target) * 16) = pack8(acc + 8);
-          } else {
-            float* dst = tokens + (size_t)(w_first + w) * pl.S_out * (size_t)(pl.c_last * V) + target;
-#pragma unroll
-            for (int q = 0; q < 16; ++q)
-              if (gq * 16 + q < b.cout) dst[(gq * 16 + q) * V] = acc[q];
           }
         }
       }
       tc_fence_before();
       __syncthreads();
+      TOK_STAMP(117 + bi * 10);
     }
   }
   tc_fence_before();
@@ -633,8 +693,8 @@ bool build_plan(const sf_model* m, int T, int G, BfPlan* pl, const char** why) {
   pl->off_bias_o = off; off += up((size_t)nb * 64 * 4);
   pl->off_w0 = off; off += up(4 * 64 * 4);
   pl->off_r0 = off; off += up(4 * 64 * 4);
-  pl->off_ellv = off; off += up((size_t)nb * V * kEllMax * 4);
-  pl->off_elld = off; off += up((size_t)nb * V * kEllMax * 4);
+  pl->off_ellv = off; off += up((size_t)nb * V * kEllMax * 8);
+  pl->off_elld = off; off += up((size_t)G * tk.c_in * T * V);
   pl->off_scale = off; off += up((size_t)tk.c_in * V * 4);
   pl->off_shift = off; off += up((size_t)tk.c_in * V * 4);
   pl->smem_bytes = off;
@@ -672,3 +732,14 @@ int launch_tokenizer_bf16(const sf_model* m, const float* poses, int64_t B, int 
 }
 
 }  // namespace sf
+
+// debugging aid (not part of the C ABI): phase timestamps of CTA 0, pairs of (phase id, clock64)
+extern "C" int sfdbg_tokenizer_timing(int enable, long long* out_host, int n) {
+  int on = enable;
+  if (cudaMemcpyToSymbol(sf::g_tok_timing_on, &on, sizeof(int)) != cudaSuccess) return -1;
+  if (out_host && n > 0) {
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    if (cudaMemcpyFromSymbol(out_host, sf::g_tok_timing, sizeof(long long) * (n < 512 ? n : 512)) != cudaSuccess) return -1;
+  }
+  return 0;
+}

@@ -1,0 +1,31 @@
+"""Phase timeline of CTA 0 of the bf16 tokenizer (debug aid): python profiles/tok_timing.py"""
+import ctypes as C, sys
+sys.path.insert(0, "."); sys.path.insert(0, "computer-vision-shoplifting-detection_b200")
+import numpy as np, torch
+import bench
+from shopformer_b200 import native as N
+from shopformer_b200.synthetic import synth_windows
+lib = N.load()
+model = bench.build_model("A").cuda()
+eng = model._sf_engine()
+x = torch.from_numpy(synth_windows(65536, 24, 17, seed=1)[0]).cuda()
+eng.tokenize(x, precision="bf16"); torch.cuda.synchronize()
+lib.sfdbg_tokenizer_timing(1, None, 0)
+eng.tokenize(x, precision="bf16"); torch.cuda.synchronize()
+buf = (C.c_longlong * 512)()
+lib.sfdbg_tokenizer_timing(0, buf, 512)
+a = np.array(buf[:]).reshape(-1, 2)
+a = a[a[:, 0] >= 100]
+names = {100: "group start", 101: "x0 affine done", 102: "m0 mix done"}
+for b in range(4):
+    names.update({110 + 10 * b: f"b{b} start (g0 done)" if b == 0 else f"b{b} start", 111 + 10 * b: f"b{b} mix done", 112 + 10 * b: f"b{b} weights+sync",
+                  113 + 10 * b: f"b{b} P mma done", 114 + 10 * b: f"b{b} g-epi done", 115 + 10 * b: f"b{b} sync", 116 + 10 * b: f"b{b} conv mma done",
+                  117 + 10 * b: f"b{b} x-epi done"})
+# print the 3rd window of the CTA (steady state)
+starts = np.where(a[:, 0] == 100)[0]
+lo, hi = starts[2], starts[3]
+t0 = a[lo, 1]
+prev = t0
+for i in range(lo, hi + 1):
+    print(f"{names.get(int(a[i,0]), a[i,0]):24s} +{a[i,1]-prev:7d}  @{a[i,1]-t0:7d}")
+    prev = a[i, 1]
