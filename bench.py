@@ -280,17 +280,18 @@ def main():
     ms = e0.elapsed_time(e1)
     # per-kernel timing of the two kernels of the path (same stream, same inputs), K launches each
     tok = eng.tokenize(x, precision=a.precision)
-    k0, k1, k2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    rec = eng.reconstruct_tokens(tok, precision=a.precision)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(a.steps)]
     torch.cuda.synchronize(dev)
-    k0.record()
-    for _ in range(a.steps):
-        eng.tokenize(x, precision=a.precision)
-    k1.record()
-    for _ in range(a.steps):
-        eng.reconstruct_tokens(tok, precision=a.precision)
-    k2.record()
+    for k in range(a.steps):                       # same interleaving as a step: tokenizer then transformer
+        evs[k][0].record()
+        eng.tokenize(x, precision=a.precision, out=tok)
+        evs[k][1].record()
+        eng.reconstruct_tokens(tok, precision=a.precision, out=rec)
+        evs[k][2].record()
     torch.cuda.synchronize(dev)
-    tok_ms, xf_ms = k0.elapsed_time(k1) / a.steps, k1.elapsed_time(k2) / a.steps
+    tok_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / a.steps
+    xf_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / a.steps
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:

@@ -117,7 +117,7 @@ extern "C" int sf_selftest_umma(int32_t mode, int32_t N, int32_t K, int32_t shif
 // on no-swizzle operands (garbage data), measured from first issue to mbarrier completion.
 namespace sf {
 namespace {
-__global__ void __launch_bounds__(128, 1) umma_timing_kernel(int N, int n_mma, int a_rows_shift, long long* out) {
+__global__ void __launch_bounds__(128, 1) umma_timing_kernel(int N, int n_mma, int a_rows_shift, int mode, long long* out) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base;
@@ -136,10 +136,64 @@ __global__ void __launch_bounds__(128, 1) umma_timing_kernel(int N, int n_mma, i
   if (threadIdx.x == 0) {
     const uint32_t idesc = make_idesc(128, N, false);
     const uint32_t a_plane = 1024u * 16u, b_plane = (uint32_t)N * 16u;
-    const uint64_t ad = make_desc(smem_u32(smem_raw) + (uint32_t)a_rows_shift * 16u, a_plane, 128u);
-    const uint64_t bd = make_desc(smem_u32(smem_raw) + 40960u, b_plane, 128u);
+    uint64_t ad = make_desc(smem_u32(smem_raw) + (uint32_t)a_rows_shift * 16u, a_plane, 128u);
+    uint64_t bd = make_desc(smem_u32(smem_raw) + 40960u, b_plane, 128u);
+    if (mode >= 2) {
+      // SWIZZLE_128B K-major: rows of 128 B (64 bf16 of K), 8-row atoms of 1024 B: SBO = 1024, LBO unused (1), layout type 2
+      ad = make_desc(smem_u32(smem_raw), 16u, 1024u) | ((uint64_t)2 << 61);
+      bd = make_desc(smem_u32(smem_raw) + 32768u, 16u, 1024u) | ((uint64_t)2 << 61);
+    }
+    if (mode == 4 || mode == 5) {
+      // conv-like: LBO = 544 rows * 16 B, A start = (34 + 17 * tap_offset) rows (+ second K chunk pair), weight slab per tap
+      const uint32_t pa = 544u * 16u;
+      ad = make_desc(smem_u32(smem_raw), pa, 128u);
+      bd = make_desc(smem_u32(smem_raw) + 40960u, b_plane, 128u);
+    }
+    if (mode >= 10) {
+      // straight-line: 16 descriptor pairs prepared BEFORE the timed region, then 16 back-to-back MMAs (x repeats)
+      uint64_t av[16], bv[16];
+      const uint32_t pa = 544u * 16u;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const int tap = (k >> 1) % 9, ks = k & 1;
+        if (mode == 10) { av[k] = ad; bv[k] = bd; }
+        else if (mode == 11) {   // conv-like, unaligned row offsets
+          av[k] = desc_advance(make_desc(smem_u32(smem_raw), pa, 128u), (uint32_t)(34 + 17 * (tap / 2)) * 16u + (uint32_t)ks * 2u * pa);
+          bv[k] = desc_advance(bd, (uint32_t)(tap * 4 + ks * 2) * 512u);
+        } else {                 // conv-like, 128-byte aligned row offsets
+          av[k] = desc_advance(make_desc(smem_u32(smem_raw), pa, 128u), (uint32_t)(32 + 16 * (tap / 2)) * 16u + (uint32_t)ks * 2u * pa);
+          bv[k] = desc_advance(bd, (uint32_t)(tap * 4 + ks * 2) * 512u);
+        }
+      }
+      const long long t0 = clock64();
+      for (int rep = 0; rep < n_mma / 16; ++rep) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) umma_bf16(tmem_base, av[k], bv[k], idesc, 1u);
+      }
+      const long long t1 = clock64();
+      umma_commit(&bar);
+      while (!mbar_try_wait(&bar, 0)) {
+      }
+      const long long t2 = clock64();
+      out[0] = t1 - t0;
+      out[1] = t2 - t0;
+    } else {
     const long long t0 = clock64();
-    for (int k = 0; k < n_mma; ++k) umma_bf16(tmem_base, ad, bd, idesc, k > 0);
+    for (int k = 0; k < n_mma; ++k) {
+      uint64_t a_k = ad, b_k = bd;
+      if (mode == 1 || mode == 3) a_k = desc_advance(ad, (uint32_t)(k & 7) * 2048u);   // a different A tile every MMA
+      if (mode == 4) {
+        const int tap = (k >> 1) % 9, ks = k & 1;
+        a_k = desc_advance(ad, (uint32_t)(34 + 17 * (tap / 2)) * 16u + (uint32_t)ks * 2u * 544u * 16u);
+        b_k = desc_advance(bd, (uint32_t)(tap * 4 + ks * 2) * 512u);
+      }
+      if (mode == 5) {     // same as 4 but 128-byte aligned row offsets (multiples of 8 rows)
+        const int tap = (k >> 1) % 9, ks = k & 1;
+        a_k = desc_advance(ad, (uint32_t)(32 + 16 * (tap / 2)) * 16u + (uint32_t)ks * 2u * 544u * 16u);
+        b_k = desc_advance(bd, (uint32_t)(tap * 4 + ks * 2) * 512u);
+      }
+      umma_bf16(tmem_base, a_k, b_k, idesc, k > 0);
+    }
     const long long t1 = clock64();
     umma_commit(&bar);
     while (!mbar_try_wait(&bar, 0)) {
@@ -147,6 +201,7 @@ __global__ void __launch_bounds__(128, 1) umma_timing_kernel(int N, int n_mma, i
     const long long t2 = clock64();
     out[0] = t1 - t0;
     out[1] = t2 - t0;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -155,11 +210,11 @@ __global__ void __launch_bounds__(128, 1) umma_timing_kernel(int N, int n_mma, i
 }  // namespace
 }  // namespace sf
 
-extern "C" int sfdbg_umma_timing(int N, int n_mma, int shift, long long* out_host) {
+extern "C" int sfdbg_umma_timing(int N, int n_mma, int shift, int mode, long long* out_host) {
   long long* d = nullptr;
   if (cudaMalloc(&d, 16) != cudaSuccess) return -1;
   cudaFuncSetAttribute(sf::umma_timing_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-  sf::umma_timing_kernel<<<1, 128, 64 * 1024>>>(N, n_mma, shift, d);
+  sf::umma_timing_kernel<<<1, 128, 64 * 1024>>>(N, n_mma, shift, mode, d);
   if (cudaDeviceSynchronize() != cudaSuccess) return -2;
   cudaMemcpy(out_host, d, 16, cudaMemcpyDeviceToHost);
   cudaFree(d);

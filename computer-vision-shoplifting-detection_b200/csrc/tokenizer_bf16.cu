@@ -44,6 +44,7 @@ struct BfBlk {
   int rows, mrows, rtot;               // rows per phase, M-space rows (G*slot*V), total rows (stride*rows)
   int n_taps;
   int tap_k[kTaps], tap_phase[kTaps], tap_rowoff[kTaps];
+  int tap_arel[kTaps], tap_wrel[kTaps];   // per tap: A-view row offset and weight-slab offset, both in 16-byte units
   int identity_res, ell_width;
   const float* ell_val;
   const int* ell_col;
@@ -100,12 +101,12 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 // packed ELL entry: .x = adjacency value, .y = row delta (u - v) as int bits; unused entries are (0, 0)
 template <int W>
 __device__ __forceinline__ void mix_x0(const float* __restrict__ x0, float* __restrict__ m0, const uint8_t* __restrict__ xvtab,
-                                       const float2* __restrict__ ell, int n) {
+                                       const float2* __restrict__ ell, int ellV, int n) {
   for (int i = threadIdx.x; i < n; i += kThreads) {
     const int v = xvtab[i];
     float2 e[W];
 #pragma unroll
-    for (int k = 0; k < W; ++k) e[k] = ell[v * kEllMax + k];
+    for (int k = 0; k < W; ++k) e[k] = ell[k * ellV + v];
     float xv[W];
 #pragma unroll
     for (int k = 0; k < W; ++k) xv[k] = x0[i + __float_as_int(e[k].y)];
@@ -119,15 +120,15 @@ __device__ __forceinline__ void mix_x0(const float* __restrict__ x0, float* __re
 // adjacency mix of one 8-channel granule column of the bf16 activation buffer: dst[r] = sum_k val_k * src[r + delta_k]
 template <int W>
 __device__ __forceinline__ void mix_rows(const unsigned char* __restrict__ plane, unsigned char* __restrict__ dstp,
-                                         const uint16_t* __restrict__ rt, const float2* __restrict__ ell, int r_first,
-                                         int r_step, int rtot) {
+                                         const uint16_t* __restrict__ rt, const float2* __restrict__ ell, int ellV,
+                                         int r_first, int r_step, int rtot) {
   for (int r = r_first; r < rtot; r += r_step) {
     const uint32_t en = rt[r];
     const bool ok = en != kGap;
     const int v = ok ? (int)(en & 31) : 0;
     float2 e[W];
 #pragma unroll
-    for (int k = 0; k < W; ++k) e[k] = ell[v * kEllMax + k];
+    for (int k = 0; k < W; ++k) e[k] = ell[k * ellV + v];
     uint4 q[W];
 #pragma unroll
     for (int k = 0; k < W; ++k) q[k] = *reinterpret_cast<const uint4*>(plane + (size_t)(r + (ok ? __float_as_int(e[k].y) : 0)) * 16);
@@ -143,6 +144,28 @@ __device__ __forceinline__ void mix_rows(const unsigned char* __restrict__ plane
     }
     *reinterpret_cast<uint4*>(dstp + (size_t)r * 16) = ok ? pack8(a) : make_uint4(0, 0, 0, 0);
   }
+}
+
+// Straight-line MMA issue for one accumulator tile, executed by ONE thread: all descriptor words are computed
+// first (independent adds), then the tcgen05.mma instructions go out back to back.  Measured on B200: ~50 cycles
+// per 128x32x16 MMA this way versus ~180 when descriptor arithmetic / branches sit between the MMAs.
+template <int NT, int KS, int RS>
+__device__ __forceinline__ void conv_issue(uint32_t d, uint32_t a_lo0, uint32_t b_lo0, const int* __restrict__ arel,
+                                           const int* __restrict__ wrel, uint32_t astep, uint32_t bstep, uint32_t idesc,
+                                           uint32_t r_alo, uint32_t r_blo) {
+  uint32_t al[NT], bl[NT];
+#pragma unroll
+  for (int tp = 0; tp < NT; ++tp) {
+    al[tp] = a_lo0 + (uint32_t)arel[tp];
+    bl[tp] = b_lo0 + (uint32_t)wrel[tp];
+  }
+#pragma unroll
+  for (int tp = 0; tp < NT; ++tp)
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+      umma_bf16(d, desc_join(al[tp] + ks * astep), desc_join(bl[tp] + ks * bstep), idesc, (tp | ks) ? 1u : 0u);
+#pragma unroll
+  for (int ks = 0; ks < RS; ++ks) umma_bf16(d, desc_join(r_alo + ks * astep), desc_join(r_blo + ks * bstep), idesc, 1u);
 }
 
 #define TOK_STAMP(id)                                                                   \
@@ -171,12 +194,13 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
   const float* bias_o = reinterpret_cast<const float*>(smem + pl.off_bias_o);
   const float* w0s = reinterpret_cast<const float*>(smem + pl.off_w0);              // [4][64]
   const float* r0s = reinterpret_cast<const float*>(smem + pl.off_r0);              // [4][64]
-  const float2* ell2 = reinterpret_cast<const float2*>(smem + pl.off_ellv);         // [blk][V][kEllMax] (value, row delta)
+  const float2* ell2 = reinterpret_cast<const float2*>(smem + pl.off_ellv);         // [blk][kEllMax][V] (value, row delta)
   const uint8_t* xvtab = reinterpret_cast<const uint8_t*>(smem + pl.off_elld);      // keypoint index of every x0 element
   const float* scale_s = reinterpret_cast<const float*>(smem + pl.off_scale);
   const float* shift_s = reinterpret_cast<const float*>(smem + pl.off_shift);
   const int V = pl.V, G = pl.G;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform on purpose (uniform datapath)
+  const int lane = threadIdx.x & 31;
   const int lane_grp = warp & 3, col_half = warp >> 2;
   const int per_w = pl.c_in * pl.T0 * V;
 
@@ -253,7 +277,7 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
     }
     float2* e2 = reinterpret_cast<float2*>(smem + pl.off_ellv) + bi * V * kEllMax;
     for (int i = threadIdx.x; i < V * kEllMax; i += kThreads) {
-      const int v = i / kEllMax, k = i % kEllMax;
+      const int k = i / V, v = i % V;                    // [k][v]: a warp's lanes read consecutive entries
       const bool ok = k < b.ell_width;
       const float val = ok ? __ldg(b.ell_val + v * b.ell_width + k) : 0.f;
       const int dl = (ok && val != 0.f) ? __ldg(b.ell_col + v * b.ell_width + k) - v : 0;
@@ -324,8 +348,8 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
       __syncthreads();
       TOK_STAMP(101);
       // m0 <- A_hat . x0 over the keypoint axis
-      if (b.ell_width <= 5) mix_x0<5>(x0, m0, xvtab, ell2, G * per_w);
-      else mix_x0<kEllMax>(x0, m0, xvtab, ell2, G * per_w);
+      if (b.ell_width <= 5) mix_x0<5>(x0, m0, xvtab, ell2, V, G * per_w);
+      else mix_x0<kEllMax>(x0, m0, xvtab, ell2, V, G * per_w);
       __syncthreads();
       TOK_STAMP(102);
       // g0 = relu(W0 . m0 + b0) -> bf16 rows of the phase-split operand buffer; one 16-byte granule per item
@@ -388,8 +412,8 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
           const unsigned char* plane = sXin + (size_t)j * planeA;
           unsigned char* dstp = sA + (size_t)j * planeA;
           const float2* el = ell2 + bi * V * kEllMax;
-          if (b.ell_width <= 5) mix_rows<5>(plane, dstp, rt, el, threadIdx.x - j * tpc, tpc, b.rtot);
-          else mix_rows<kEllMax>(plane, dstp, rt, el, threadIdx.x - j * tpc, tpc, b.rtot);
+          if (b.ell_width <= 5) mix_rows<5>(plane, dstp, rt, el, V, threadIdx.x - j * tpc, tpc, b.rtot);
+          else mix_rows<kEllMax>(plane, dstp, rt, el, V, threadIdx.x - j * tpc, tpc, b.rtot);
         }
         TOK_STAMP(111 + bi * 10);
         cp_async_wait_all();
@@ -399,22 +423,25 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
         TOK_STAMP(112 + bi * 10);
         // ---- P = M . W  (all rows of all phases), accumulators in TMEM
         const int p_tiles = (b.rtot + 127) >> 7;
-        if (lane == 0 && warp < kIssuers) {
+        if (warp < kIssuers) {
+          // warp-uniform control flow and descriptor arithmetic (uniform registers); only the MMA itself is
+          // predicated on one lane
           tc_fence_after();
           const uint32_t idesc = make_idesc(128, b.npad, false);
           const uint32_t w_plane = (uint32_t)b.npad * 16u;
           const uint32_t blo0 = desc_lo(smem_u32(sWG), w_plane);
-          const uint32_t* dt = reinterpret_cast<const uint32_t*>(smem + b.off_dtab);
+          const uint32_t a0 = smem_u32(sA);
+          const int ksp = b.kin >> 4;
           for (int tile = warp; tile < p_tiles; tile += kIssuers) {
-            uint32_t alo = dt[tile];
+            uint32_t alo = desc_lo(a0 + (uint32_t)tile * 2048u, planeA);
             uint32_t blo = blo0;
-            for (int ks = 0; ks < (b.kin >> 4); ++ks) {
-              umma_bf16(tmem + (uint32_t)(tile * dcol), desc_join(alo), desc_join(blo), idesc, ks > 0);
+            for (int ks = 0; ks < ksp; ++ks) {
+              if (lane == 0) umma_bf16(tmem + (uint32_t)(tile * dcol), desc_join(alo), desc_join(blo), idesc, ks > 0);
               alo += (2u * planeA) >> 4;
               blo += (2u * w_plane) >> 4;
             }
           }
-          umma_commit(&bar);
+          if (lane == 0) umma_commit(&bar);
         }
         if (warp == 0) mbar_wait(&bar, parity);     // one polling warp; the others block in the hardware barrier
         __syncthreads();
@@ -466,39 +493,49 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
       TOK_STAMP(115 + bi * 10);
       // ---- temporal conv (+ residual conv) as shifted-view MMAs
       const int m_tiles = (b.mrows + 127) >> 7;
-      if (lane == 0 && warp < kIssuers) {
+      if (warp < kIssuers) {
         tc_fence_after();
         const uint32_t idesc = make_idesc(128, b.npad, false);
         const uint32_t w_plane = (uint32_t)b.npad * 16u;
         const int ksteps = b.npad >> 4;
-        const uint32_t* dt = reinterpret_cast<const uint32_t*>(smem + b.off_dtab);
         const int n_taps = b.n_taps;
+        const uint32_t a0 = smem_u32(sA), w0a = smem_u32(sWT);
+        const uint32_t astep = (2u * planeA) >> 4, bstep = (2u * w_plane) >> 4;
+        const int rsteps = (bi > 0 && !b.identity_res) ? (b.kin >> 4) : 0;
         for (int tile = warp; tile < m_tiles; tile += kIssuers) {
           const uint32_t d = tmem + (uint32_t)(tile * dcol);
-          uint32_t acc_flag = 0;
-          for (int tp = 0; tp < n_taps; ++tp) {
-            uint32_t alo = dt[4 + tile * 9 + tp];
-            uint32_t blo = dt[40 + tp];
-            for (int ks = 0; ks < ksteps; ++ks) {
-              umma_bf16(d, desc_join(alo), desc_join(blo), idesc, acc_flag);
-              acc_flag = 1;
-              alo += (2u * planeA) >> 4;
-              blo += (2u * w_plane) >> 4;
+          const uint32_t a_lo0 = desc_lo(a0, planeA) + (uint32_t)(tile * 128), b_lo0 = desc_lo(w0a, w_plane);
+          const uint32_t r_alo = desc_lo(smem_u32(sXin) + (uint32_t)(b.gap * V + tile * 128) * 16u, planeA);   // phase 0 of x_b
+          const uint32_t r_blo = desc_lo(w0a + (uint32_t)(kTaps * b.npad * b.npad * 2), w_plane);
+          if (lane == 0) {
+            const int* arel = b.tap_arel;
+            const int* wrel = b.tap_wrel;
+#define SF_ISSUE(NT, KS, RS) \
+  if (n_taps == NT && ksteps == KS && rsteps == RS) conv_issue<NT, KS, RS>(d, a_lo0, b_lo0, arel, wrel, astep, bstep, idesc, r_alo, r_blo); else
+            SF_ISSUE(9, 2, 0) SF_ISSUE(9, 2, 2) SF_ISSUE(7, 2, 2) SF_ISSUE(5, 2, 2) SF_ISSUE(5, 1, 2) SF_ISSUE(3, 1, 2)
+            SF_ISSUE(9, 4, 0) SF_ISSUE(9, 4, 4) SF_ISSUE(7, 4, 4) SF_ISSUE(5, 4, 4) SF_ISSUE(3, 4, 4) SF_ISSUE(5, 1, 4) SF_ISSUE(3, 1, 4)
+            SF_ISSUE(3, 2, 2) SF_ISSUE(5, 4, 0) SF_ISSUE(3, 4, 0)
+            {   // generic fallback (any tap count / K split)
+              uint32_t acc_flag = 0;
+              for (int tp = 0; tp < n_taps; ++tp) {
+                uint32_t alo = a_lo0 + (uint32_t)arel[tp], blo = b_lo0 + (uint32_t)wrel[tp];
+                for (int ks = 0; ks < ksteps; ++ks) {
+                  umma_bf16(d, desc_join(alo), desc_join(blo), idesc, acc_flag);
+                  acc_flag = 1;
+                  alo += astep;
+                  blo += bstep;
+                }
+              }
+              for (int ks = 0; ks < rsteps; ++ks) umma_bf16(d, desc_join(r_alo + ks * astep), desc_join(r_blo + ks * bstep), idesc, 1u);
             }
-          }
-          if (bi > 0 && !b.identity_res) {
-            uint32_t alo = dt[49 + tile];                                  // phase 0, offset 0: x[s*t'] (x_b shares the geometry)
-            uint32_t blo = dt[53];
-            for (int ks = 0; ks < (b.kin >> 4); ++ks) {
-              umma_bf16(d, desc_join(alo), desc_join(blo), idesc, 1u);
-              alo += (2u * planeA) >> 4;
-              blo += (2u * w_plane) >> 4;
-            }
+#undef SF_ISSUE
           }
         }
-        umma_commit(&bar);
+        if (lane == 0) umma_commit(&bar);
+        TOK_STAMP(118 + bi * 10);
       }
       if (warp == 0) mbar_wait(&bar, parity);
+      TOK_STAMP(119 + bi * 10);
       __syncthreads();
       parity ^= 1;
       tc_fence_after();
@@ -627,6 +664,7 @@ bool build_plan(const sf_model* m, int T, int G, BfPlan* pl, const char** why) {
       b.tap_k[b.n_taps] = k;
       b.tap_phase[b.n_taps] = p;
       b.tap_rowoff[b.n_taps] = o * V;
+      b.tap_wrel[b.n_taps] = k * (w.npad >> 3) * w.npad;
       b.gap = std::max(b.gap, std::abs(o));
       ++b.n_taps;
     }
@@ -634,6 +672,7 @@ bool build_plan(const sf_model* m, int T, int G, BfPlan* pl, const char** why) {
     b.mrows = G * b.slot * V;
     b.rows = b.gap * V + b.mrows;
     b.rtot = b.stride * b.rows;
+    for (int tp = 0; tp < b.n_taps; ++tp) b.tap_arel[tp] = b.tap_phase[tp] * b.rows + b.gap * V + b.tap_rowoff[tp];
     if (b.rtot > 2047) { *why = "operand buffer longer than 2047 rows"; return false; }
     b.identity_res = tb.identity_res;
     b.ell_width = tb.ell_width;
@@ -724,6 +763,7 @@ int launch_tokenizer_bf16(const sf_model* m, const float* poses, int64_t B, int 
   SF_CUDA_OK(cudaDeviceGetAttribute(&smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, m->device));
   int occ = smem_per_sm / (int)(pl.smem_bytes + 1024 + 256);
   occ = std::max(1, std::min(std::min(occ, 2), (int)(512 / pl.tmem_cols)));
+  if (const char* dbg = getenv("SF_TOK_OCC")) occ = std::max(1, std::min(occ, atoi(dbg)));     // debugging aid
   const int64_t n_groups = (B + pl.G - 1) / pl.G;
   const int grid = (int)std::min<int64_t>(n_groups, (int64_t)m->sm_count * occ);
   tokenizer_bf16_kernel<<<grid, kThreads, pl.smem_bytes, st>>>(pl, poses, tokens, B);

@@ -125,20 +125,24 @@ class ScoringEngine:
     # -- the four reference-facing calls
     _PREC = {"fp32": N.SF_PREC_FP32, "bf16": N.SF_PREC_BF16}
 
-    def tokenize(self, poses: torch.Tensor, precision: str = "fp32") -> torch.Tensor:
+    def tokenize(self, poses: torch.Tensor, precision: str = "fp32", out: Optional[torch.Tensor] = None) -> torch.Tensor:
         x = self._poses(poses)
         B, _, T, _ = x.shape
         S, D = self.token_shape(T)
-        out = torch.empty(B, S, D, dtype=torch.float32, device=self.device)
+        if out is None:
+            out = torch.empty(B, S, D, dtype=torch.float32, device=self.device)
+        elif out.shape != (B, S, D) or out.dtype != torch.float32 or not out.is_contiguous():
+            raise ValueError("`out` must be a contiguous fp32 (B,S,D) tensor")
         ws, nb = self._workspace(B, T)
         N.check(self._lib.sf_tokenize(self._h, _ptr(x), B, T, self._PREC[precision], _ptr(out), _ptr(ws), nb,
                                       _stream_ptr(self.device)), "sf_tokenize")
         return out
 
-    def reconstruct_tokens(self, tokens: torch.Tensor, precision: str = "fp32") -> torch.Tensor:
+    def reconstruct_tokens(self, tokens: torch.Tensor, precision: str = "fp32", out: Optional[torch.Tensor] = None) -> torch.Tensor:
         t = tokens.to(self.device, torch.float32).contiguous()
         B, S, D = t.shape
-        out = torch.empty_like(t)
+        if out is None:
+            out = torch.empty_like(t)
         N.check(self._lib.sf_reconstruct_tokens(self._h, _ptr(t), B, S, self._PREC[precision], _ptr(out), None, 0,
                                                 _stream_ptr(self.device)),
                 "sf_reconstruct_tokens")
