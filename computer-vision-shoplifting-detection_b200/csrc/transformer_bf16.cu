@@ -23,19 +23,32 @@
 #include "tc_common.cuh"
 
 namespace sf {
+__device__ long long g_xf_timing[1024];
+__device__ int g_xf_timing_on = 0;
 namespace {
 
 using namespace tc;
+
+#define XF_STAMP(id)                                                             \
+  do {                                                                           \
+    if (timing && threadIdx.x == 0 && stamp_i < 1022) {                          \
+      g_xf_timing[stamp_i++] = (long long)(id);                                  \
+      g_xf_timing[stamp_i++] = clock64();                                        \
+    }                                                                            \
+  } while (0)
 
 constexpr int kThreads = 256;
 constexpr int kSlots = 5;              // 16-column groups per thread: widths up to 160
 constexpr int kSMax = 4;
 constexpr float kLnEps = 1e-5f;
+// per-slot parameter block (floats): [bias | bias_q | bias_k | ln_gamma | ln_beta], 160 each
+constexpr int kPW = 160, kParamFloats = 5 * kPW;
 
 struct XfGeo {
   int S, wpw, rows_per_warp, win_per_tile;
   uint32_t off_aop, off_hop, off_mem, off_w, off_red, smem_bytes;
   int slot_bytes, plane;               // plane = 128 rows * 16 B
+  int param_off;                       // byte offset of the fp32 parameter block inside a ring slot
 };
 
 __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
@@ -63,6 +76,35 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+
+template <int KS>
+__device__ __forceinline__ void gemm_issue(uint32_t d, uint32_t alo0, uint32_t blo0, uint32_t astep, uint32_t bstep,
+                                           uint32_t idesc, uint32_t accumulate) {
+  uint32_t al[KS], bl[KS];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+    al[ks] = alo0 + ks * astep;
+    bl[ks] = blo0 + ks * bstep;
+  }
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) umma_bf16(d, desc_join(al[ks]), desc_join(bl[ks]), idesc, (accumulate || ks > 0) ? 1u : 0u);
+}
+__device__ __forceinline__ void stagef(float* dst, const float* src, int n_floats) {
+  for (int i = threadIdx.x * 4; i < n_floats; i += kThreads * 4) cp_async16(dst + i, src + i);
+}
+
+// 16 consecutive floats of a 16-byte aligned global row; columns >= lim (lim % 4 == 0) or !ok read as zero
+__device__ __forceinline__ void ldg16(const float* __restrict__ p, int c0, int lim, bool ok, float* out) {
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ok && c0 + 4 * e < lim) v = __ldg(reinterpret_cast<const float4*>(p + c0 + 4 * e));
+    out[4 * e + 0] = v.x;
+    out[4 * e + 1] = v.y;
+    out[4 * e + 2] = v.z;
+    out[4 * e + 3] = v.w;
+  }
+}
 
 // write one 16-column group of a row into a planar-chunk operand buffer
 __device__ __forceinline__ void store_group(unsigned char* buf, int plane, int row, int g, const float* y) {
@@ -103,6 +145,8 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
   uint32_t parity = 0;
+  const bool timing = g_xf_timing_on && blockIdx.x == 0;
+  int stamp_i = 0;
 
   // index of the first / next GEMM op (for the weight ring)
   const int n_ops = prog.n_ops;
@@ -120,15 +164,33 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
       for (int q = 0; q < 16; ++q) st[i][q] = 0.f;
 
     int slot = 0;
-    {   // prefetch the first GEMM's weights
+    // weights + the op's fp32 parameters (biases, LayerNorm affine) go into ring slot `sl`
+    auto stage_op = [&](int idx, int sl) {
+      const XfOp o = ops[idx];
+      unsigned char* base = sW + sl * geo.slot_bytes;
+      stage(base, o.w, o.K * o.N * 2);
+      float* pp = reinterpret_cast<float*>(base + geo.param_off);
+      if (o.bias) stagef(pp, o.bias, o.N);
+      if (o.epi == XE_ATTN) {
+        stagef(pp + kPW, ops[idx - 2].bias, o.N);          // q bias
+        stagef(pp + 2 * kPW, ops[idx - 1].bias, o.N);      // k bias
+      }
+      if (o.ln_g) {
+        stagef(pp + 3 * kPW, o.ln_g, (d + 3) & ~3);
+        stagef(pp + 4 * kPW, o.ln_b, (d + 3) & ~3);
+      }
+    };
+    {   // prefetch the first GEMM
       int nx = 0;
       while (nx < n_ops && ops[nx].type != XF_GEMM) ++nx;
-      if (nx < n_ops) stage(sW, ops[nx].w, ops[nx].K * ops[nx].N * 2);
+      if (nx < n_ops) stage_op(nx, 0);
     }
 
     for (int oi = 0; oi < n_ops; ++oi) {
       const XfOp op = ops[oi];
       int post = op.post;
+      XF_STAMP(oi * 8 + 0);
+      const float* pbase = nullptr;              // staged parameters of this op (GEMM ops only)
       // ------------------------------------------------------------------ stream initialisation
       if (op.type == XF_INIT) {
         if (op.init_mode == XI_TOK_TO_AOP) {
@@ -138,11 +200,7 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
             const int g = 2 * i + half;
             if (g < ng) {
               float y[16];
-#pragma unroll
-              for (int q = 0; q < 16; ++q) {
-                const int c = g * 16 + q;
-                y[q] = (valid && c < dt) ? __ldg(tok_row + c) : 0.f;
-              }
+              ldg16(tok_row, g * 16, dt, valid, y);
               store_group(sAop, plane, row, g, y);
             }
           }
@@ -153,17 +211,11 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
           for (int i = 0; i < kSlots; ++i) {
             const int g = 2 * i + half;
             if (g < ng) {
+              float pe16[16], tk[16];
+              ldg16(xf.pe + tok_s * d, g * 16, d, valid, pe16);
+              ldg16(shift ? tok_row - dt : tok_row, g * 16, d, valid && (!shift || tok_s > 0), tk);   // zero start token + shift by one
 #pragma unroll
-              for (int q = 0; q < 16; ++q) {
-                const int c = g * 16 + q;
-                float v = 0.f;
-                if (valid && c < d) {
-                  v = __ldg(xf.pe + tok_s * d + c);
-                  if (!shift) v += __ldg(tok_row + c);
-                  else if (tok_s > 0) v += __ldg(tok_row - dt + c);      // zero start token + tokens shifted by one
-                }
-                st[i][q] = v;
-              }
+              for (int q = 0; q < 16; ++q) st[i][q] = pe16[q] + tk[q];
             }
           }
         }
@@ -174,6 +226,7 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
+        XF_STAMP(oi * 8 + 1);
         if (threadIdx.x == 0) {
           tc_fence_after();
           const unsigned char* a = op.a_src == XS_AOP ? sAop : (op.a_src == XS_HOP ? sHop : sMem);
@@ -181,51 +234,71 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
           const uint32_t w_plane = (uint32_t)op.N * 16u;
           uint32_t alo = desc_lo(smem_u32(a), (uint32_t)plane);
           uint32_t blo = desc_lo(smem_u32(sW + slot * geo.slot_bytes), w_plane);
-          for (int ks = 0; ks < (op.K >> 4); ++ks) {
-            umma_bf16(tmem + (uint32_t)op.tmem_col, desc_join(alo), desc_join(blo), idesc, (op.accumulate || ks > 0) ? 1u : 0u);
-            alo += (2u * (uint32_t)plane) >> 4;
-            blo += (2u * w_plane) >> 4;
+          const uint32_t dd = tmem + (uint32_t)op.tmem_col, astep = (2u * (uint32_t)plane) >> 4, bstep = (2u * w_plane) >> 4;
+          const uint32_t accf = op.accumulate ? 1u : 0u;
+          switch (op.K >> 4) {
+            case 9: gemm_issue<9>(dd, alo, blo, astep, bstep, idesc, accf); break;
+            case 4: gemm_issue<4>(dd, alo, blo, astep, bstep, idesc, accf); break;
+            case 8: gemm_issue<8>(dd, alo, blo, astep, bstep, idesc, accf); break;
+            case 10: gemm_issue<10>(dd, alo, blo, astep, bstep, idesc, accf); break;
+            case 2: gemm_issue<2>(dd, alo, blo, astep, bstep, idesc, accf); break;
+            default:
+              for (int ks = 0; ks < (op.K >> 4); ++ks) {
+                umma_bf16(dd, desc_join(alo), desc_join(blo), idesc, (accf || ks > 0) ? 1u : 0u);
+                alo += astep;
+                blo += bstep;
+              }
           }
           umma_commit(&bar);
+          XF_STAMP(oi * 8 + 2);
         }
         {   // prefetch the next GEMM's weights into the other ring slot (its previous user has completed)
           int nx = oi + 1;
           while (nx < n_ops && ops[nx].type != XF_GEMM) ++nx;
-          if (nx < n_ops) stage(sW + (slot ^ 1) * geo.slot_bytes, ops[nx].w, ops[nx].K * ops[nx].N * 2);
+          if (nx < n_ops) stage_op(nx, slot ^ 1);
         }
+        pbase = reinterpret_cast<const float*>(sW + slot * geo.slot_bytes + geo.param_off);
         slot ^= 1;
         mbar_wait(&bar, parity);
         parity ^= 1;
         tc_fence_after();
+        XF_STAMP(oi * 8 + 3);
 
         if (op.epi == XE_ATTN) {
           // ---- softmax(q k^T / sqrt(hd)) v per (row, head); heads split between the two warps of a lane group
           const int H = xf.heads, hd = d / H;
           const int h_lo = H == 1 ? 0 : half * (H >> 1), h_hi = H == 1 ? (half == 0 ? 1 : 0) : (half + 1) * (H >> 1);
           const float scale = rsqrtf((float)hd);
-          const float* bq = ops[oi - 2].bias;
-          const float* bk = ops[oi - 1].bias;
-          const float* bv = op.bias;
+          const float* bq = pbase + kPW;
+          const float* bk = pbase + 2 * kPW;
+          const float* bv = pbase;
           for (int h = h_lo; h < h_hi; ++h) {
             const int c0 = h * hd;
             float sc[kSMax];
 #pragma unroll
             for (int j = 0; j < kSMax; ++j) sc[j] = 0.f;
-            for (int c4 = 0; c4 < hd; c4 += 4) {
-              float q4[4], k4[4];
-              tmem_ld4(tmem + lane_addr + (uint32_t)(c0 + c4), q4);
-              tmem_ld4(tmem + lane_addr + (uint32_t)(dp + c0 + c4), k4);
+            // 16 accumulator columns per TMEM round trip (columns past the head are loaded but not used)
+            for (int c16 = 0; c16 < hd; c16 += 16) {
+              float q16[16], k16[16];
+              tmem_ld16(tmem + lane_addr + (uint32_t)(c0 + c16), q16);
+              tmem_ld16(tmem + lane_addr + (uint32_t)(dp + c0 + c16), k16);
               tmem_ld_wait();
-              const float4 bq4 = __ldg(reinterpret_cast<const float4*>(bq + c0 + c4));
-              const float4 bk4 = __ldg(reinterpret_cast<const float4*>(bk + c0 + c4));
-              q4[0] += bq4.x; q4[1] += bq4.y; q4[2] += bq4.z; q4[3] += bq4.w;
-              k4[0] += bk4.x; k4[1] += bk4.y; k4[2] += bk4.z; k4[3] += bk4.w;
 #pragma unroll
-              for (int j = 0; j < kSMax; ++j)
-                if (j < S) {
-                  const int src = (wb + j) & 31;
+              for (int e4 = 0; e4 < 4; ++e4)
+                if (c16 + 4 * e4 < hd) {
+                  const float4 bq4 = *reinterpret_cast<const float4*>(bq + c0 + c16 + 4 * e4);
+                  const float4 bk4 = *reinterpret_cast<const float4*>(bk + c0 + c16 + 4 * e4);
+                  float* q4 = q16 + 4 * e4;
+                  float* k4 = k16 + 4 * e4;
+                  q4[0] += bq4.x; q4[1] += bq4.y; q4[2] += bq4.z; q4[3] += bq4.w;
+                  k4[0] += bk4.x; k4[1] += bk4.y; k4[2] += bk4.z; k4[3] += bk4.w;
 #pragma unroll
-                  for (int e = 0; e < 4; ++e) sc[j] = fmaf(q4[e], __shfl_sync(0xffffffffu, k4[e], src), sc[j]);
+                  for (int j = 0; j < kSMax; ++j)
+                    if (j < S) {
+                      const int src = (wb + j) & 31;
+#pragma unroll
+                      for (int e = 0; e < 4; ++e) sc[j] = fmaf(q4[e], __shfl_sync(0xffffffffu, k4[e], src), sc[j]);
+                    }
                 }
             }
             float mx = -INFINITY;
@@ -243,23 +316,28 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
                 den += sc[j];
               }
             const float inv = 1.f / den;
-            for (int c4 = 0; c4 < hd; c4 += 4) {
-              float v4[4];
-              tmem_ld4(tmem + lane_addr + (uint32_t)(2 * dp + c0 + c4), v4);
+            for (int c16 = 0; c16 < hd; c16 += 16) {
+              float v16[16];
+              tmem_ld16(tmem + lane_addr + (uint32_t)(2 * dp + c0 + c16), v16);
               tmem_ld_wait();
-              const float4 bv4 = __ldg(reinterpret_cast<const float4*>(bv + c0 + c4));
-              v4[0] += bv4.x; v4[1] += bv4.y; v4[2] += bv4.z; v4[3] += bv4.w;
-              float o4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-              for (int j = 0; j < kSMax; ++j)
-                if (j < S) {
-                  const int src = (wb + j) & 31;
+              for (int e4 = 0; e4 < 4; ++e4)
+                if (c16 + 4 * e4 < hd) {
+                  const float4 bv4 = *reinterpret_cast<const float4*>(bv + c0 + c16 + 4 * e4);
+                  float* v4 = v16 + 4 * e4;
+                  v4[0] += bv4.x; v4[1] += bv4.y; v4[2] += bv4.z; v4[3] += bv4.w;
+                  float o4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                  for (int e = 0; e < 4; ++e) o4[e] = fmaf(sc[j], __shfl_sync(0xffffffffu, v4[e], src), o4[e]);
+                  for (int j = 0; j < kSMax; ++j)
+                    if (j < S) {
+                      const int src = (wb + j) & 31;
+#pragma unroll
+                      for (int e = 0; e < 4; ++e) o4[e] = fmaf(sc[j], __shfl_sync(0xffffffffu, v4[e], src), o4[e]);
+                    }
+                  const int c = c0 + c16 + 4 * e4;
+                  uint2 pk = make_uint2(pack_bf16x2(o4[0] * inv, o4[1] * inv), pack_bf16x2(o4[2] * inv, o4[3] * inv));
+                  *reinterpret_cast<uint2*>(sHop + (size_t)(c >> 3) * plane + row * 16 + (c & 7) * 2) = pk;
                 }
-              const int c = c0 + c4;
-              uint2 pk = make_uint2(pack_bf16x2(o4[0] * inv, o4[1] * inv), pack_bf16x2(o4[2] * inv, o4[3] * inv));
-              *reinterpret_cast<uint2*>(sHop + (size_t)(c >> 3) * plane + row * 16 + (c & 7) * 2) = pk;
             }
           }
         } else if (op.epi == XE_ACT_H) {
@@ -273,7 +351,7 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
               tmem_ld_wait();
 #pragma unroll
               for (int q = 0; q < 16; ++q) {
-                const float v = acc[q] + __ldg(op.bias + g * 16 + q);
+                const float v = acc[q] + pbase[g * 16 + q];
                 acc[q] = op.act == 2 ? gelu_erf(v) : fmaxf(v, 0.f);
               }
               store_group(sHop, plane, row, g, acc);
@@ -288,13 +366,16 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
             if (g < ng) {
               float acc[16];
               tmem_ld16(tmem + lane_addr + (uint32_t)(op.tmem_col + g * 16), acc);
-              tmem_ld_wait();
+              if (set_pe) {
+                float pe16[16];
+                ldg16(xf.pe + tok_s * d, g * 16, d, valid, pe16);
+                tmem_ld_wait();
 #pragma unroll
-              for (int q = 0; q < 16; ++q) {
-                const int c = g * 16 + q;
-                const float v = acc[q] + __ldg(op.bias + c);
-                if (set_pe) st[i][q] = (valid && c < d) ? v + __ldg(xf.pe + tok_s * d + c) : 0.f;
-                else st[i][q] += v;
+                for (int q = 0; q < 16; ++q) st[i][q] = (valid && g * 16 + q < d) ? acc[q] + pbase[g * 16 + q] + pe16[q] : 0.f;
+              } else {
+                tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < 16; ++q) st[i][q] += acc[q] + pbase[g * 16 + q];
               }
             }
           }
@@ -306,20 +387,30 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
           for (int i = 0; i < kSlots; ++i) {
             const int g = 2 * i + half;
             if (g < ng) {
-              float acc[16];
+              float acc[16], target[16];
               tmem_ld16(tmem + lane_addr + (uint32_t)(op.tmem_col + g * 16), acc);
+              ldg16(tok_row, g * 16, dt, valid, target);
+              if (xf.variant == SF_VARIANT_SHOPFORMER) {
+                float pe16[16];
+                ldg16(xf.pe_score + tok_s * dt, g * 16, dt, valid, pe16);
+#pragma unroll
+                for (int q = 0; q < 16; ++q) target[q] += pe16[q];
+              }
               tmem_ld_wait();
 #pragma unroll
               for (int q = 0; q < 16; ++q) {
                 const int c = g * 16 + q;
-                if (valid && c < dt) {
-                  const float r = acc[q] + __ldg(op.bias + c);
-                  float target = __ldg(tok_row + c);
-                  if (xf.variant == SF_VARIANT_SHOPFORMER) target += __ldg(xf.pe_score + tok_s * dt + c);
-                  const float df = r - target;
-                  part = fmaf(df, df, part);
-                  if (recon_out) recon_out[((size_t)window * S + tok_s) * dt + c] = r;
-                }
+                const float r = acc[q] + pbase[c];
+                const float df = (valid && c < dt) ? r - target[q] : 0.f;
+                part = fmaf(df, df, part);
+                acc[q] = r;
+              }
+              if (recon_out && valid) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  if (g * 16 + 4 * e < dt)
+                    *reinterpret_cast<float4*>(recon_out + ((size_t)window * S + tok_s) * dt + g * 16 + 4 * e) =
+                        make_float4(acc[4 * e], acc[4 * e + 1], acc[4 * e + 2], acc[4 * e + 3]);
               }
             }
           }
@@ -341,6 +432,7 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
           post = XP_NONE;
         }
       }
+      XF_STAMP(oi * 8 + 4);
       // ------------------------------------------------------------------ post step on the register stream
       if (post == XP_COPY_TO_AOP) {
         const int ng = dp >> 4;
@@ -365,6 +457,7 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
         __syncthreads();
         const float mean = (red[row] + red[128 + row]) / (float)d;
         __syncthreads();
+        XF_STAMP(oi * 8 + 5);
         float s2 = 0.f;
 #pragma unroll
         for (int i = 0; i < kSlots; ++i) {
@@ -382,6 +475,9 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
         __syncthreads();
         const float rstd = rsqrtf((red[row] + red[128 + row]) / (float)d + kLnEps);
         __syncthreads();
+        XF_STAMP(oi * 8 + 6);
+        const float* ln_g = pbase ? pbase + 3 * kPW : op.ln_g;
+        const float* ln_b = pbase ? pbase + 4 * kPW : op.ln_b;
         float part = 0.f;
 #pragma unroll
         for (int i = 0; i < kSlots; ++i) {
@@ -389,9 +485,16 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
           if (g < ng) {
             float y[16];
 #pragma unroll
-            for (int q = 0; q < 16; ++q) {
-              const int c = g * 16 + q;
-              y[q] = c < d ? (st[i][q] - mean) * rstd * __ldg(op.ln_g + c) + __ldg(op.ln_b + c) : 0.f;
+            for (int e = 0; e < 4; ++e) {
+              // generic loads: staged copy in the ring slot (GEMM ops) or the arena itself (stand-alone norms)
+              const bool in = g * 16 + 4 * e < d;          // d % 4 == 0 (make_geo)
+              const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              const float4 gm = in ? *reinterpret_cast<const float4*>(ln_g + g * 16 + 4 * e) : zero4;
+              const float4 bt = in ? *reinterpret_cast<const float4*>(ln_b + g * 16 + 4 * e) : zero4;
+              y[4 * e + 0] = in ? fmaf((st[i][4 * e + 0] - mean) * rstd, gm.x, bt.x) : 0.f;
+              y[4 * e + 1] = in ? fmaf((st[i][4 * e + 1] - mean) * rstd, gm.y, bt.y) : 0.f;
+              y[4 * e + 2] = in ? fmaf((st[i][4 * e + 2] - mean) * rstd, gm.z, bt.z) : 0.f;
+              y[4 * e + 3] = in ? fmaf((st[i][4 * e + 3] - mean) * rstd, gm.w, bt.w) : 0.f;
             }
             if (post == XP_LN_INPLACE_TO_AOP) {
 #pragma unroll
@@ -400,14 +503,19 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
             if (post == XP_LN_INPLACE_TO_AOP || post == XP_LN_TO_AOP) store_group(sAop, plane, row, g, y);
             if (post == XP_LN_TO_MEM || op.also_mem) store_group(sMem, plane, row, g, y);
             if (post == XP_LN_SCORE) {
+              float target[16];
+              ldg16(tok_row, g * 16, dt, valid, target);
 #pragma unroll
               for (int q = 0; q < 16; ++q) {
-                const int c = g * 16 + q;
-                if (valid && c < dt) {
-                  const float df = __ldg(tok_row + c) - y[q];
-                  part = fmaf(df, df, part);
-                  if (recon_out) recon_out[((size_t)window * S + tok_s) * dt + c] = y[q];
-                }
+                const float df = (valid && g * 16 + q < dt) ? target[q] - y[q] : 0.f;
+                part = fmaf(df, df, part);
+              }
+              if (recon_out && valid) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  if (g * 16 + 4 * e < dt)
+                    *reinterpret_cast<float4*>(recon_out + ((size_t)window * S + tok_s) * dt + g * 16 + 4 * e) =
+                        make_float4(y[4 * e], y[4 * e + 1], y[4 * e + 2], y[4 * e + 3]);
               }
             }
           }
@@ -431,6 +539,7 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
         }
       }
     }
+    XF_STAMP(9999);
     tc_fence_before();
     __syncthreads();
   }
@@ -442,7 +551,7 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
 bool make_geo(const sf_model* m, int S, XfGeo* g) {
   const XfProgram& p = m->xfprog;
   if (!p.supported || S < 1 || S > kSMax) return false;
-  if (m->xf.variant == SF_VARIANT_SHOPFORMER && S < 1) return false;
+  if ((m->xf.d_model & 3) || (m->xf.d_tok & 3)) return false;    // float4 row accesses
   g->S = S;
   g->wpw = 32 / S;
   g->rows_per_warp = g->wpw * S;
@@ -450,7 +559,8 @@ bool make_geo(const sf_model* m, int S, XfGeo* g) {
   g->plane = 128 * 16;
   const int width = std::max(std::max(p.dp, p.dtp), 128);       // operand buffers hold activations, ctx and FFN chunks
   const uint32_t op_bytes = (uint32_t)(width / 8) * g->plane;
-  g->slot_bytes = (p.max_w_bytes + 127) & ~127;
+  g->param_off = (p.max_w_bytes + 127) & ~127;
+  g->slot_bytes = g->param_off + kParamFloats * (int)sizeof(float);
   uint32_t off = 0;
   g->off_aop = off; off += op_bytes;
   g->off_hop = off; off += op_bytes;
@@ -476,6 +586,8 @@ int launch_transformer_bf16(const sf_model* m, const float* tokens, int64_t B, i
              "bf16 tensor-core transformer does not cover this shape (d_model=%d, heads=%d, S=%d)", m->xf.d_model, m->xf.heads, S);
   SF_REQUIRE(reduction == SF_REDUCE_MEAN || (reduction == SF_REDUCE_NONE && m->xf.variant == SF_VARIANT_SHOPFORMER_2),
              SF_E_INVALID, "reduction %d not available for variant %d", reduction, m->xf.variant);
+  SF_REQUIRE(((uintptr_t)tokens & 15) == 0 && ((uintptr_t)recon & 15) == 0, SF_E_INVALID,
+             "token / reconstruction buffers must be 16-byte aligned");
   SF_CUDA_OK(cudaFuncSetAttribute(transformer_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
   const int64_t n_tiles = (B + g.win_per_tile - 1) / g.win_per_tile;
   const int grid = (int)std::min<int64_t>(n_tiles, m->sm_count);
@@ -485,3 +597,14 @@ int launch_transformer_bf16(const sf_model* m, const float* tokens, int64_t B, i
 }
 
 }  // namespace sf
+
+// debugging aid (not part of the C ABI): per-op timestamps of CTA 0, pairs of (op*8 + phase, clock64)
+extern "C" int sfdbg_transformer_timing(int enable, long long* out_host, int n) {
+  int on = enable;
+  if (cudaMemcpyToSymbol(sf::g_xf_timing_on, &on, sizeof(int)) != cudaSuccess) return -1;
+  if (out_host && n > 0) {
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    if (cudaMemcpyFromSymbol(out_host, sf::g_xf_timing, sizeof(long long) * (n < 1024 ? n : 1024)) != cudaSuccess) return -1;
+  }
+  return 0;
+}
