@@ -300,8 +300,8 @@ def main():
     value = world * n * a.steps / (ms * 1e-3)
 
     # ---- end to end through the C-ABI host-buffer call: inputs in page-locked host memory, H2D + kernels + D2H
-    # of every chunk pipelined on two streams inside sf_runner_score
-    chunk = 8192
+    # of every chunk pipelined on a copy + a compute stream inside sf_runner_score
+    chunk = 16384
     xs_pinned = torch.from_numpy(xs).pin_memory()
     xs = xs_pinned.numpy()
     eng.score_host(xs[:chunk * 2], precision=a.precision, chunk=chunk)      # allocate runner, warm up
@@ -382,7 +382,7 @@ def main():
                    "l2": f"inputs larger than L2 ({xs.nbytes / 1e6:.0f} MB of windows per step vs 126 MB L2)",
                    "collective": "NCCL all-gather of fp32 scores" if world > 1 else "none (1 GPU)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "api": "sf_runner_score (C ABI, host buffers, 8192-window chunks, 2 streams)", "steps": e2e_steps},
+                "api": "sf_runner_score (C ABI, host buffers, <=16384-window whole-wave chunks, copy + compute stream, 4-slot ring)", "steps": e2e_steps},
         "gpu_launches": 2 * a.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         "parity": {"max_rel_err_vs_cpu_oracle": err, "checked_windows": 256, "tolerance": 1e-3 if a.precision == "fp32" else 1e-2},
         "other_precision": other_line,

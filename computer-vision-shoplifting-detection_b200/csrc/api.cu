@@ -82,18 +82,22 @@ extern "C" int sf_score_windows(const sf_model* m, const float* poses_dev, int64
 }
 
 // ------------------------------------------------------------------------------------ runner
+// Host-buffer scoring pipeline: a copy stream uploads chunk c+1.. while the compute stream scores chunk c.  kRing
+// device/pinned slots let the DMA engine run ahead of the kernels; the kernels of consecutive chunks queue back
+// to back on ONE stream (they fill the GPU on their own, so running two chunks side by side only adds tail waves).
+constexpr int kRing = 4;
 struct sf_runner {
   const sf_model* m;
   int T, S;
   int64_t chunk;
   size_t pose_elems;              // floats per window
-  cudaStream_t st[2];
-  cudaEvent_t done[2];
-  float* pin_in[2];
-  float* pin_out[2];
-  float* dev_in[2];
-  float* dev_out[2];
-  void* ws[2];
+  cudaStream_t copy_st, comp_st;
+  cudaEvent_t copied[kRing], computed[kRing];
+  float* pin_in[kRing];
+  float* pin_out[kRing];
+  float* dev_in[kRing];
+  float* dev_out[kRing];
+  void* ws;
   int64_t ws_bytes;
 };
 
@@ -107,18 +111,22 @@ extern "C" int sf_runner_create(const sf_model* m, int32_t T, int64_t max_chunk,
   r->m = m;
   r->T = T;
   r->S = token_len(m, T);
-  r->chunk = max_chunk;
+  // whole waves: the tensor-core transformer walks tiles of 4 * floor(32 / S) windows with one CTA per SM, so a
+  // chunk that is a multiple of sm_count * tile leaves no partial wave (and is a whole number of tokenizer waves)
+  const int64_t wave = (int64_t)m->sm_count * 4 * (32 / std::max(1, std::min(r->S, 32)));
+  r->chunk = max_chunk >= wave ? max_chunk / wave * wave : max_chunk;
   r->pose_elems = (size_t)m->cfg.in_channels * T * m->cfg.num_keypoints;
-  r->ws_bytes = sf_workspace_bytes(m, max_chunk, T);
-  cudaError_t e = cudaSuccess;
-  for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
-    e = cudaStreamCreateWithFlags(&r->st[i], cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r->done[i], cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaMallocHost((void**)&r->pin_in[i], r->pose_elems * max_chunk * sizeof(float));
-    if (e == cudaSuccess) e = cudaMallocHost((void**)&r->pin_out[i], max_chunk * sizeof(float));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&r->dev_in[i], r->pose_elems * max_chunk * sizeof(float));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&r->dev_out[i], max_chunk * sizeof(float));
-    if (e == cudaSuccess && r->ws_bytes > 0) e = cudaMalloc(&r->ws[i], r->ws_bytes);
+  r->ws_bytes = sf_workspace_bytes(m, r->chunk, T);
+  cudaError_t e = cudaStreamCreateWithFlags(&r->copy_st, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&r->comp_st, cudaStreamNonBlocking);
+  if (e == cudaSuccess && r->ws_bytes > 0) e = cudaMalloc(&r->ws, r->ws_bytes);
+  for (int i = 0; i < kRing && e == cudaSuccess; ++i) {
+    e = cudaEventCreateWithFlags(&r->copied[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r->computed[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&r->pin_in[i], r->pose_elems * r->chunk * sizeof(float));
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&r->pin_out[i], r->chunk * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&r->dev_in[i], r->pose_elems * r->chunk * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&r->dev_out[i], r->chunk * sizeof(float));
   }
   if (e != cudaSuccess) {
     set_error("sf_runner_create: %s", cudaGetErrorString(e));
@@ -132,31 +140,33 @@ extern "C" int sf_runner_create(const sf_model* m, int32_t T, int64_t max_chunk,
 extern "C" void sf_runner_destroy(sf_runner* r) {
   if (!r) return;
   cudaSetDevice(r->m->device);
-  for (int i = 0; i < 2; ++i) {
-    if (r->st[i]) cudaStreamSynchronize(r->st[i]);
+  if (r->copy_st) cudaStreamSynchronize(r->copy_st);
+  if (r->comp_st) cudaStreamSynchronize(r->comp_st);
+  for (int i = 0; i < kRing; ++i) {
     if (r->pin_in[i]) cudaFreeHost(r->pin_in[i]);
     if (r->pin_out[i]) cudaFreeHost(r->pin_out[i]);
     if (r->dev_in[i]) cudaFree(r->dev_in[i]);
     if (r->dev_out[i]) cudaFree(r->dev_out[i]);
-    if (r->ws[i]) cudaFree(r->ws[i]);
-    if (r->done[i]) cudaEventDestroy(r->done[i]);
-    if (r->st[i]) cudaStreamDestroy(r->st[i]);
+    if (r->copied[i]) cudaEventDestroy(r->copied[i]);
+    if (r->computed[i]) cudaEventDestroy(r->computed[i]);
   }
+  if (r->ws) cudaFree(r->ws);
+  if (r->copy_st) cudaStreamDestroy(r->copy_st);
+  if (r->comp_st) cudaStreamDestroy(r->comp_st);
   delete r;
 }
 
 extern "C" float* sf_runner_pinned_poses(sf_runner* r, int32_t slot) {
-  if (!r || slot < 0 || slot > 1) return nullptr;
+  if (!r || slot < 0 || slot >= kRing) return nullptr;
   return r->pin_in[slot];
 }
 
-// Chunked, double-buffered: while chunk i computes on stream i%2, chunk i+1 is being
-// copied into pinned memory and uploaded on the other stream.
 extern "C" int sf_runner_score(sf_runner* r, const float* poses_host, int64_t B, int32_t precision, float* scores_host) {
   SF_REQUIRE(r && (B == 0 || (poses_host && scores_host)), SF_E_INVALID, "sf_runner_score: null argument");
   SF_CUDA_OK(cudaSetDevice(r->m->device));
   const int64_t n_chunks = (B + r->chunk - 1) / r->chunk;
-  int64_t pending_off[2] = {-1, -1}, pending_n[2] = {0, 0};
+  int64_t pending_off[kRing], pending_n[kRing];
+  for (int i = 0; i < kRing; ++i) pending_off[i] = -1, pending_n[i] = 0;
   bool src_pinned = false;
   if (B > 0) {
     cudaPointerAttributes attr;
@@ -164,10 +174,10 @@ extern "C" int sf_runner_score(sf_runner* r, const float* poses_host, int64_t B,
     else cudaGetLastError();
   }
   for (int64_t c = 0; c < n_chunks; ++c) {
-    const int s = (int)(c & 1);
+    const int s = (int)(c % kRing);
     const int64_t off = c * r->chunk, n = std::min(r->chunk, B - off);
     if (pending_off[s] >= 0) {                       // drain the slot before reusing its buffers
-      SF_CUDA_OK(cudaEventSynchronize(r->done[s]));
+      SF_CUDA_OK(cudaEventSynchronize(r->computed[s]));
       memcpy(scores_host + pending_off[s], r->pin_out[s], pending_n[s] * sizeof(float));
       pending_off[s] = -1;
     }
@@ -179,19 +189,23 @@ extern "C" int sf_runner_score(sf_runner* r, const float* poses_host, int64_t B,
       memcpy(r->pin_in[s], src, (size_t)n * r->pose_elems * sizeof(float));
       dma_src = r->pin_in[s];
     }
-    SF_CUDA_OK(cudaMemcpyAsync(r->dev_in[s], dma_src, (size_t)n * r->pose_elems * sizeof(float), cudaMemcpyHostToDevice, r->st[s]));
+    SF_CUDA_OK(cudaMemcpyAsync(r->dev_in[s], dma_src, (size_t)n * r->pose_elems * sizeof(float), cudaMemcpyHostToDevice, r->copy_st));
+    SF_CUDA_OK(cudaEventRecord(r->copied[s], r->copy_st));
+    SF_CUDA_OK(cudaStreamWaitEvent(r->comp_st, r->copied[s], 0));
     int rc = sf_score_windows(r->m, r->dev_in[s], n, r->T, SF_REDUCE_MEAN, precision, r->dev_out[s], nullptr, nullptr,
-                              r->ws[s], r->ws_bytes, r->st[s]);
+                              r->ws, r->ws_bytes, r->comp_st);
     if (rc) return rc;
-    SF_CUDA_OK(cudaMemcpyAsync(r->pin_out[s], r->dev_out[s], (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, r->st[s]));
-    SF_CUDA_OK(cudaEventRecord(r->done[s], r->st[s]));
+    SF_CUDA_OK(cudaMemcpyAsync(r->pin_out[s], r->dev_out[s], (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, r->comp_st));
+    SF_CUDA_OK(cudaEventRecord(r->computed[s], r->comp_st));
     pending_off[s] = off;
     pending_n[s] = n;
   }
-  for (int s = 0; s < 2; ++s)
+  for (int64_t c = std::max<int64_t>(0, n_chunks - kRing); c < n_chunks; ++c) {     // oldest first
+    const int s = (int)(c % kRing);
     if (pending_off[s] >= 0) {
-      SF_CUDA_OK(cudaEventSynchronize(r->done[s]));
+      SF_CUDA_OK(cudaEventSynchronize(r->computed[s]));
       memcpy(scores_host + pending_off[s], r->pin_out[s], pending_n[s] * sizeof(float));
     }
+  }
   return SF_OK;
 }

@@ -402,7 +402,7 @@ extern "C" int sf_model_create(const sf_config* cfg, int32_t n_tensors, const ch
   const int dp = pad16(d), dtp = pad16(d_tok), dff = cfg->d_ff;
   const int hd = d / H;
   const int ffc = std::min(pad16(dff), 128);                  // FFN hidden processed in chunks of <= 128 columns
-  bool xf_ok = dp <= 160 && dtp <= 160 && hd % 4 == 0 && (H == 1 || H % 2 == 0) && d % 8 == 0 && d_tok % 8 == 0;
+  bool xf_ok = dp <= 160 && dtp <= 160 && hd % 4 == 0 && (H == 1 || H == 2 || H % 4 == 0) && d % 8 == 0 && d_tok % 8 == 0;
   int max_w_bytes = 0;
   auto image = [&](const LinOff& lin, int n0, int n_cnt, int k0, int k_cnt, int Npad, int Kpad) {
     const size_t off = bf_alloc((size_t)Npad * Kpad);

@@ -11,8 +11,8 @@
 //   * every nn.Linear is a chain of tcgen05.mma (M=128, N = padded width, K = 16 per instruction) with the
 //     bf16 activation operand in shared memory (planar-chunk layout, tc_common.cuh) and the weight image
 //     streamed L2 -> smem through a 2-slot cp.async ring, prefetched one GEMM ahead;
-//   * the fp32 residual stream of a row lives in REGISTERS (two warps share a row: even / odd 16-column
-//     groups); bias, residual add, LayerNorm (two-pass, partial sums exchanged through smem), ReLU / exact
+//   * the fp32 residual stream of a row lives in REGISTERS (four warps share a row: every 4th 16-column
+//     group each); bias, residual add, LayerNorm (two-pass, partial sums exchanged through smem), ReLU / exact
 //     GELU and the bf16 down-conversion of the next operand all happen in the TMEM epilogue;
 //   * q, k, v accumulate side by side in TMEM columns [0,dp) [dp,2dp) [2dp,3dp); the FFN hidden layer is
 //     processed in chunks of <= 128 columns with the second GEMM accumulating in TMEM across chunks;
@@ -37,8 +37,9 @@ using namespace tc;
     }                                                                            \
   } while (0)
 
-constexpr int kThreads = 256;
-constexpr int kSlots = 5;              // 16-column groups per thread: widths up to 160
+constexpr int kThreads = 512;
+constexpr int kParts = kThreads / 128;  // warps sharing one 32-row lane group: each owns every kParts-th 16-column group
+constexpr int kSlots = 3;              // 16-column groups per thread: widths up to 192
 constexpr int kSMax = 4;
 constexpr float kLnEps = 1e-5f;
 // per-slot parameter block (floats): [bias | bias_q | bias_k | ln_gamma | ln_beta], 160 each
@@ -65,13 +66,6 @@ __device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, uint32_t lbo_byt
   return ((smem_addr >> 4) & 0x3FFFu) | ((lbo_bytes >> 4) << 16);
 }
 __device__ __forceinline__ uint64_t desc_join(uint32_t lo) { return ((uint64_t)((128u >> 4) | (1u << 14)) << 32) | lo; }
-__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
-  uint32_t* u = reinterpret_cast<uint32_t*>(v);
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3])
-               : "r"(taddr)
-               : "memory");
-}
 __device__ __forceinline__ uint4 pack8(const float* f) {
   return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
 }
@@ -106,6 +100,13 @@ __device__ __forceinline__ void ldg16(const float* __restrict__ p, int c0, int l
   }
 }
 
+__device__ __forceinline__ float red_sum(const float* red, int row) {
+  float t = 0.f;
+#pragma unroll
+  for (int p = 0; p < kParts; ++p) t += red[p * 128 + row];
+  return t;
+}
+
 // write one 16-column group of a row into a planar-chunk operand buffer
 __device__ __forceinline__ void store_group(unsigned char* buf, int plane, int row, int g, const float* y) {
   *reinterpret_cast<uint4*>(buf + (size_t)(2 * g) * plane + row * 16) = pack8(y);
@@ -123,9 +124,10 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
   unsigned char* sHop = smem + geo.off_hop;
   unsigned char* sMem = smem + geo.off_mem;
   unsigned char* sW = smem + geo.off_w;                       // 2 ring slots
-  float* red = reinterpret_cast<float*>(smem + geo.off_red);  // [2 halves][128 rows]
+  float* red = reinterpret_cast<float*>(smem + geo.off_red);  // [kParts][128 rows]
+  float* xsc = red + kParts * 128;                            // [kParts][kSMax][128 rows] partial attention logits
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int lane_grp = warp & 3, half = warp >> 2;
+  const int lane_grp = warp & 3, part = warp >> 2;
   const int row = lane_grp * 32 + lane;
   const int S = geo.S, d = xf.d_model, dt = xf.d_tok, dp = prog.dp, plane = geo.plane;
   const int tok_s = lane % S, win_l = lane / S, wb = win_l * S;       // token index, window in warp, first lane of window
@@ -197,7 +199,7 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
           const int ng = prog.dtp >> 4;
 #pragma unroll
           for (int i = 0; i < kSlots; ++i) {
-            const int g = 2 * i + half;
+            const int g = kParts * i + part;
             if (g < ng) {
               float y[16];
               ldg16(tok_row, g * 16, dt, valid, y);
@@ -209,7 +211,7 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
           const int ng = dp >> 4;
 #pragma unroll
           for (int i = 0; i < kSlots; ++i) {
-            const int g = 2 * i + half;
+            const int g = kParts * i + part;
             if (g < ng) {
               float pe16[16], tk[16];
               ldg16(xf.pe + tok_s * d, g * 16, d, valid, pe16);
@@ -259,33 +261,40 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
         }
         pbase = reinterpret_cast<const float*>(sW + slot * geo.slot_bytes + geo.param_off);
         slot ^= 1;
-        mbar_wait(&bar, parity);
+        if (warp == 0) mbar_wait(&bar, parity);      // one polling warp; the others block in the hardware barrier
+        __syncthreads();
         parity ^= 1;
         tc_fence_after();
         XF_STAMP(oi * 8 + 3);
 
         if (op.epi == XE_ATTN) {
-          // ---- softmax(q k^T / sqrt(hd)) v per (row, head); heads split between the two warps of a lane group
+          // ---- softmax(q k^T / sqrt(hd)) v per (row, head).  The kParts warps of a lane group split the heads
+          // (H >= kParts) or the columns of a head (H < kParts; partial logits are summed through smem).
           const int H = xf.heads, hd = d / H;
-          const int h_lo = H == 1 ? 0 : half * (H >> 1), h_hi = H == 1 ? (half == 0 ? 1 : 0) : (half + 1) * (H >> 1);
+          const int P = H >= kParts ? 1 : kParts / H;          // column parts per head
+          const int hpw = H >= kParts ? H / kParts : 1;        // heads per warp
+          const int n4 = hd >> 2;
           const float scale = rsqrtf((float)hd);
           const float* bq = pbase + kPW;
           const float* bk = pbase + 2 * kPW;
           const float* bv = pbase;
-          for (int h = h_lo; h < h_hi; ++h) {
-            const int c0 = h * hd;
+          for (int hh = 0; hh < hpw; ++hh) {
+            const int h = P == 1 ? part * hpw + hh : part / P;
+            const int cp = P == 1 ? 0 : part % P;
+            const int f_lo = (cp * n4) / P, f_hi = ((cp + 1) * n4) / P;
+            const int c0 = h * hd + 4 * f_lo, ncol = 4 * (f_hi - f_lo);
             float sc[kSMax];
 #pragma unroll
             for (int j = 0; j < kSMax; ++j) sc[j] = 0.f;
-            // 16 accumulator columns per TMEM round trip (columns past the head are loaded but not used)
-            for (int c16 = 0; c16 < hd; c16 += 16) {
+            // 16 accumulator columns per TMEM round trip (columns past the range are loaded but not used)
+            for (int c16 = 0; c16 < ncol; c16 += 16) {
               float q16[16], k16[16];
               tmem_ld16(tmem + lane_addr + (uint32_t)(c0 + c16), q16);
               tmem_ld16(tmem + lane_addr + (uint32_t)(dp + c0 + c16), k16);
               tmem_ld_wait();
 #pragma unroll
               for (int e4 = 0; e4 < 4; ++e4)
-                if (c16 + 4 * e4 < hd) {
+                if (c16 + 4 * e4 < ncol) {
                   const float4 bq4 = *reinterpret_cast<const float4*>(bq + c0 + c16 + 4 * e4);
                   const float4 bk4 = *reinterpret_cast<const float4*>(bk + c0 + c16 + 4 * e4);
                   float* q4 = q16 + 4 * e4;
@@ -299,6 +308,19 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
 #pragma unroll
                       for (int e = 0; e < 4; ++e) sc[j] = fmaf(q4[e], __shfl_sync(0xffffffffu, k4[e], src), sc[j]);
                     }
+                }
+            }
+            if (P > 1) {   // uniform over the CTA (hpw == 1 here): one exchange per attention op
+#pragma unroll
+              for (int j = 0; j < kSMax; ++j)
+                if (j < S) xsc[(part * kSMax + j) * 128 + row] = sc[j];
+              __syncthreads();
+#pragma unroll
+              for (int j = 0; j < kSMax; ++j)
+                if (j < S) {
+                  float t = 0.f;
+                  for (int pp = 0; pp < P; ++pp) t += xsc[((h * P + pp) * kSMax + j) * 128 + row];
+                  sc[j] = t;
                 }
             }
             float mx = -INFINITY;
@@ -316,13 +338,13 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
                 den += sc[j];
               }
             const float inv = 1.f / den;
-            for (int c16 = 0; c16 < hd; c16 += 16) {
+            for (int c16 = 0; c16 < ncol; c16 += 16) {
               float v16[16];
               tmem_ld16(tmem + lane_addr + (uint32_t)(2 * dp + c0 + c16), v16);
               tmem_ld_wait();
 #pragma unroll
               for (int e4 = 0; e4 < 4; ++e4)
-                if (c16 + 4 * e4 < hd) {
+                if (c16 + 4 * e4 < ncol) {
                   const float4 bv4 = *reinterpret_cast<const float4*>(bv + c0 + c16 + 4 * e4);
                   float* v4 = v16 + 4 * e4;
                   v4[0] += bv4.x; v4[1] += bv4.y; v4[2] += bv4.z; v4[3] += bv4.w;
@@ -344,7 +366,7 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
           const int ng = op.N >> 4;
 #pragma unroll
           for (int i = 0; i < kSlots; ++i) {
-            const int g = 2 * i + half;
+            const int g = kParts * i + part;
             if (g < ng) {
               float acc[16];
               tmem_ld16(tmem + lane_addr + (uint32_t)(op.tmem_col + g * 16), acc);
@@ -362,7 +384,7 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
           const bool set_pe = op.epi == XE_STREAM_SET_PE;
 #pragma unroll
           for (int i = 0; i < kSlots; ++i) {
-            const int g = 2 * i + half;
+            const int g = kParts * i + part;
             if (g < ng) {
               float acc[16];
               tmem_ld16(tmem + lane_addr + (uint32_t)(op.tmem_col + g * 16), acc);
@@ -382,10 +404,10 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
         } else if (op.epi == XE_SCORE) {
           // recon = D + bias (width dt); squared error against the score target
           const int ng = op.N >> 4;
-          float part = 0.f;
+          float sq = 0.f;
 #pragma unroll
           for (int i = 0; i < kSlots; ++i) {
-            const int g = 2 * i + half;
+            const int g = kParts * i + part;
             if (g < ng) {
               float acc[16], target[16];
               tmem_ld16(tmem + lane_addr + (uint32_t)(op.tmem_col + g * 16), acc);
@@ -402,7 +424,7 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
                 const int c = g * 16 + q;
                 const float r = acc[q] + pbase[c];
                 const float df = (valid && c < dt) ? r - target[q] : 0.f;
-                part = fmaf(df, df, part);
+                sq = fmaf(df, df, sq);
                 acc[q] = r;
               }
               if (recon_out && valid) {
@@ -414,10 +436,10 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
               }
             }
           }
-          red[half * 128 + row] = part;
+          red[part * 128 + row] = sq;
           __syncthreads();
-          if (half == 0) {
-            const float tot = red[row] + red[128 + row];
+          if (part == 0) {
+            const float tot = red_sum(red, row);
             if (reduction == SF_REDUCE_NONE) {
               if (valid && scores) scores[(size_t)window * S + tok_s] = tot / (float)dt;
             } else {
@@ -438,7 +460,7 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
         const int ng = dp >> 4;
 #pragma unroll
         for (int i = 0; i < kSlots; ++i) {
-          const int g = 2 * i + half;
+          const int g = kParts * i + part;
           if (g < ng) store_group(sAop, plane, row, g, st[i]);
         }
       } else if (post >= XP_LN_INPLACE_TO_AOP) {
@@ -446,22 +468,22 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
         float s1 = 0.f;
 #pragma unroll
         for (int i = 0; i < kSlots; ++i) {
-          const int g = 2 * i + half;
+          const int g = kParts * i + part;
           if (g < ng) {
 #pragma unroll
             for (int q = 0; q < 16; ++q)
               if (g * 16 + q < d) s1 += st[i][q];
           }
         }
-        red[half * 128 + row] = s1;
+        red[part * 128 + row] = s1;
         __syncthreads();
-        const float mean = (red[row] + red[128 + row]) / (float)d;
+        const float mean = red_sum(red, row) / (float)d;
         __syncthreads();
         XF_STAMP(oi * 8 + 5);
         float s2 = 0.f;
 #pragma unroll
         for (int i = 0; i < kSlots; ++i) {
-          const int g = 2 * i + half;
+          const int g = kParts * i + part;
           if (g < ng) {
 #pragma unroll
             for (int q = 0; q < 16; ++q)
@@ -471,17 +493,17 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
               }
           }
         }
-        red[half * 128 + row] = s2;
+        red[part * 128 + row] = s2;
         __syncthreads();
-        const float rstd = rsqrtf((red[row] + red[128 + row]) / (float)d + kLnEps);
+        const float rstd = rsqrtf(red_sum(red, row) / (float)d + kLnEps);
         __syncthreads();
         XF_STAMP(oi * 8 + 6);
         const float* ln_g = pbase ? pbase + 3 * kPW : op.ln_g;
         const float* ln_b = pbase ? pbase + 4 * kPW : op.ln_b;
-        float part = 0.f;
+        float sq = 0.f;
 #pragma unroll
         for (int i = 0; i < kSlots; ++i) {
-          const int g = 2 * i + half;
+          const int g = kParts * i + part;
           if (g < ng) {
             float y[16];
 #pragma unroll
@@ -508,7 +530,7 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
 #pragma unroll
               for (int q = 0; q < 16; ++q) {
                 const float df = (valid && g * 16 + q < dt) ? target[q] - y[q] : 0.f;
-                part = fmaf(df, df, part);
+                sq = fmaf(df, df, sq);
               }
               if (recon_out && valid) {
 #pragma unroll
@@ -521,10 +543,10 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
           }
         }
         if (post == XP_LN_SCORE) {
-          red[half * 128 + row] = part;
+          red[part * 128 + row] = sq;
           __syncthreads();
-          if (half == 0) {
-            const float tot = red[row] + red[128 + row];
+          if (part == 0) {
+            const float tot = red_sum(red, row);
             if (reduction == SF_REDUCE_NONE) {
               if (valid && scores) scores[(size_t)window * S + tok_s] = tot / (float)dt;
             } else {
@@ -566,7 +588,7 @@ bool make_geo(const sf_model* m, int S, XfGeo* g) {
   g->off_hop = off; off += op_bytes;
   g->off_mem = off; off += op_bytes;
   g->off_w = off; off += 2u * (uint32_t)g->slot_bytes;
-  g->off_red = off; off += 2 * 128 * sizeof(float);
+  g->off_red = off; off += (kParts + kParts * kSMax) * 128 * sizeof(float);
   g->smem_bytes = off;
   return off <= (uint32_t)m->max_smem_optin;
 }

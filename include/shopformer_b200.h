@@ -74,7 +74,7 @@ typedef struct sf_config {
 } sf_config;
 
 typedef struct sf_model sf_model;    /* packed, BatchNorm-folded weights resident in HBM */
-typedef struct sf_runner sf_runner;  /* pinned staging + device buffers + 2 streams      */
+typedef struct sf_runner sf_runner;  /* pinned staging + device buffer ring + 2 streams    */
 
 /* ------------------------------------------------------------------ library ------- */
 int sf_abi_version(void);
@@ -190,13 +190,15 @@ int sf_normalize_windows(const float* raw_dev, int64_t B, int32_t T, int32_t K, 
 /* The call a reference-side loop makes per batch: poses on the HOST, scores back on the
  * HOST (shopformer/evaluate.py:90-99, shopformer/inference.py:67-94,
  * shopformer/train.py:311-319, shopformer_2/evaluate.py:52-58).  The runner owns pinned
- * staging, device buffers and two streams and pipelines H2D / kernels / D2H in chunks. */
+ * staging, a ring of 4 device buffers, a copy stream and a compute stream, and pipelines
+ * H2D / kernels / D2H in chunks of at most `max_chunk` windows (rounded down to whole
+ * waves of the transformer grid when `max_chunk` allows). */
 int sf_runner_create(const sf_model* m, int32_t T, int64_t max_chunk, sf_runner** out);
 void sf_runner_destroy(sf_runner* r);
 /* Blocking: returns after `scores_host[0..B)` is written.  `poses_host` need not be pinned. */
 int sf_runner_score(sf_runner* r, const float* poses_host, int64_t B, int32_t precision,
                     float* scores_host);
-/* Pinned staging buffer of the runner (capacity `max_chunk` windows x 2 slots) so that
+/* Pinned staging buffer of the runner (capacity one chunk of windows, slots 0..3) so that
  * producers can write windows straight into page-locked memory. */
 float* sf_runner_pinned_poses(sf_runner* r, int32_t slot);
 
