@@ -45,6 +45,19 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool b_mn_major)
          ((uint32_t)(M >> 4) << 24);
 }
 
+// one lane of a converged warp (ptxas keeps code predicated on elect.sync in the uniform datapath)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.b32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -100,6 +100,10 @@ __device__ __forceinline__ void ldg16(const float* __restrict__ p, int c0, int l
   }
 }
 
+// barrier over the kParts warps that share lane group `lane_grp` (ids 1..4; id 0 is __syncthreads)
+__device__ __forceinline__ void group_barrier(int lane_grp) {
+  asm volatile("bar.sync %0, %1;" ::"r"(1 + lane_grp), "r"(kParts * 32) : "memory");
+}
 __device__ __forceinline__ float red_sum(const float* red, int row) {
   float t = 0.f;
 #pragma unroll
@@ -124,9 +128,10 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
   unsigned char* sHop = smem + geo.off_hop;
   unsigned char* sMem = smem + geo.off_mem;
   unsigned char* sW = smem + geo.off_w;                       // 2 ring slots
-  float* red = reinterpret_cast<float*>(smem + geo.off_red);  // [kParts][128 rows]
-  float* xsc = red + kParts * 128;                            // [kParts][kSMax][128 rows] partial attention logits
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* red = reinterpret_cast<float*>(smem + geo.off_red);  // LayerNorm partial sums: [2 buffers][sum, sumsq][kParts][128 rows]
+  float* xsc = red + 4 * kParts * 128;                            // [kParts][kSMax][128 rows] partial attention logits
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform on purpose (uniform datapath)
+  const int lane = threadIdx.x & 31;
   const int lane_grp = warp & 3, part = warp >> 2;
   const int row = lane_grp * 32 + lane;
   const int S = geo.S, d = xf.d_model, dt = xf.d_tok, dp = prog.dp, plane = geo.plane;
@@ -165,7 +170,7 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
 #pragma unroll
       for (int q = 0; q < 16; ++q) st[i][q] = 0.f;
 
-    int slot = 0;
+    int slot = 0, ln_buf = 0;
     // weights + the op's fp32 parameters (biases, LayerNorm affine) go into ring slot `sl`
     auto stage_op = [&](int idx, int sl) {
       const XfOp o = ops[idx];
@@ -229,7 +234,7 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
         tc_fence_before();
         __syncthreads();
         XF_STAMP(oi * 8 + 1);
-        if (threadIdx.x == 0) {
+        if (warp == 0 && elect_one()) {            // uniform-datapath issue: descriptors live in uniform registers
           tc_fence_after();
           const unsigned char* a = op.a_src == XS_AOP ? sAop : (op.a_src == XS_HOP ? sHop : sMem);
           const uint32_t idesc = make_idesc(128, op.N, false);
@@ -436,10 +441,10 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
               }
             }
           }
-          red[part * 128 + row] = sq;
+          xsc[part * 128 + row] = sq;
           __syncthreads();
           if (part == 0) {
-            const float tot = red_sum(red, row);
+            const float tot = red_sum(xsc, row);
             if (reduction == SF_REDUCE_NONE) {
               if (valid && scores) scores[(size_t)window * S + tok_s] = tot / (float)dt;
             } else {
@@ -465,38 +470,29 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
         }
       } else if (post >= XP_LN_INPLACE_TO_AOP) {
         const int ng = dp >> 4;
-        float s1 = 0.f;
+        // one-pass statistics (padded columns of the stream are exactly 0, so they need no masking); the four
+        // warps of a lane group exchange partial sums through smem under their own named barrier, and two
+        // alternating buffers make a single barrier per LayerNorm enough
+        float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int i = 0; i < kSlots; ++i) {
           const int g = kParts * i + part;
           if (g < ng) {
 #pragma unroll
-            for (int q = 0; q < 16; ++q)
-              if (g * 16 + q < d) s1 += st[i][q];
+            for (int q = 0; q < 16; ++q) {
+              s1 += st[i][q];
+              s2 = fmaf(st[i][q], st[i][q], s2);
+            }
           }
         }
-        red[part * 128 + row] = s1;
-        __syncthreads();
-        const float mean = red_sum(red, row) / (float)d;
-        __syncthreads();
-        XF_STAMP(oi * 8 + 5);
-        float s2 = 0.f;
-#pragma unroll
-        for (int i = 0; i < kSlots; ++i) {
-          const int g = kParts * i + part;
-          if (g < ng) {
-#pragma unroll
-            for (int q = 0; q < 16; ++q)
-              if (g * 16 + q < d) {
-                const float c0 = st[i][q] - mean;
-                s2 = fmaf(c0, c0, s2);
-              }
-          }
-        }
-        red[part * 128 + row] = s2;
-        __syncthreads();
-        const float rstd = rsqrtf(red_sum(red, row) / (float)d + kLnEps);
-        __syncthreads();
+        float* rb = red + ln_buf * (2 * kParts * 128);
+        ln_buf ^= 1;
+        rb[part * 128 + row] = s1;
+        rb[(kParts + part) * 128 + row] = s2;
+        group_barrier(lane_grp);
+        const float mean = red_sum(rb, row) / (float)d;
+        const float var = fmaxf(red_sum(rb + kParts * 128, row) / (float)d - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + kLnEps);
         XF_STAMP(oi * 8 + 6);
         const float* ln_g = pbase ? pbase + 3 * kPW : op.ln_g;
         const float* ln_b = pbase ? pbase + 4 * kPW : op.ln_b;
@@ -543,10 +539,10 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
           }
         }
         if (post == XP_LN_SCORE) {
-          red[part * 128 + row] = sq;
+          xsc[part * 128 + row] = sq;
           __syncthreads();
           if (part == 0) {
-            const float tot = red_sum(red, row);
+            const float tot = red_sum(xsc, row);
             if (reduction == SF_REDUCE_NONE) {
               if (valid && scores) scores[(size_t)window * S + tok_s] = tot / (float)dt;
             } else {
@@ -588,7 +584,7 @@ bool make_geo(const sf_model* m, int S, XfGeo* g) {
   g->off_hop = off; off += op_bytes;
   g->off_mem = off; off += op_bytes;
   g->off_w = off; off += 2u * (uint32_t)g->slot_bytes;
-  g->off_red = off; off += (kParts + kParts * kSMax) * 128 * sizeof(float);
+  g->off_red = off; off += (4 * kParts + kParts * kSMax) * 128 * sizeof(float);
   g->smem_bytes = off;
   return off <= (uint32_t)m->max_smem_optin;
 }

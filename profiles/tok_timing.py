@@ -18,7 +18,7 @@ a = np.array(buf[:]).reshape(-1, 2)
 a = a[a[:, 0] >= 100]
 names = {100: "group start", 101: "x0 affine done", 102: "m0 mix done"}
 for b in range(4):
-    names.update({110 + 10 * b: f"b{b} start (g0 done)" if b == 0 else f"b{b} start", 111 + 10 * b: f"b{b} mix done", 112 + 10 * b: f"b{b} weights+sync",
+    names.update({110 + 10 * b: f"b{b} start", 111 + 10 * b: f"b{b} Q-epi done", 112 + 10 * b: f"b{b} zero A_big + sync", 200 + 10 * b: f"b{b} GEMM2 done",
                   113 + 10 * b: f"b{b} P mma done", 114 + 10 * b: f"b{b} g-epi done", 115 + 10 * b: f"b{b} sync", 116 + 10 * b: f"b{b} conv mma done",
                   117 + 10 * b: f"b{b} x-epi done", 118 + 10 * b: f"b{b} conv issued", 119 + 10 * b: f"b{b} conv mbar"})
 # print the 3rd window of the CTA (steady state)
