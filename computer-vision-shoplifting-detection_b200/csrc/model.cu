@@ -117,8 +117,10 @@ struct NormOff {
   size_t g, b;
 };
 static NormOff pack_norm(Packer& pk, const std::string& p, int d) {
-  NormOff o{pk.alloc(d), 0};
-  o.b = pk.alloc(d);
+  // padded to the widest stream (160 columns) with zeros: the tensor-core path applies gamma / beta to padded
+  // columns without masking (0 * x + 0)
+  NormOff o{pk.alloc(std::max(d, 160)), 0};
+  o.b = pk.alloc(std::max(d, 160));
   const float* g = pk.get(p + "weight", d);
   const float* b = pk.get(p + "bias", d);
   if (g && b) {

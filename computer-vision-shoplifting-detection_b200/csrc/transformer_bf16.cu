@@ -145,7 +145,8 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
     fence_mbar_init();
   }
   // zero the operand buffers once: padded columns / idle rows must stay finite (NaN * 0 = NaN in the MMA)
-  for (int i = threadIdx.x; i < (int)((geo.off_w - geo.off_aop) >> 4); i += kThreads)
+  // (also the parameter blocks of the ring slots: LayerNorm gamma / beta beyond d_model stay 0)
+  for (int i = threadIdx.x; i < (int)((geo.off_red - geo.off_aop) >> 4); i += kThreads)
     reinterpret_cast<uint4*>(smem + geo.off_aop)[i] = make_uint4(0, 0, 0, 0);
   tc_fence_before();
   __syncthreads();
@@ -180,7 +181,6 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
       if (o.bias) stagef(pp, o.bias, o.N);
       if (o.epi == XE_ATTN) {
         stagef(pp + kPW, ops[idx - 2].bias, o.N);          // q bias
-        stagef(pp + 2 * kPW, ops[idx - 1].bias, o.N);      // k bias
       }
       if (o.ln_g) {
         stagef(pp + 3 * kPW, o.ln_g, (d + 3) & ~3);
@@ -280,8 +280,10 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
           const int hpw = H >= kParts ? H / kParts : 1;        // heads per warp
           const int n4 = hd >> 2;
           const float scale = rsqrtf((float)hd);
+          int rot[kSMax];                                      // lane of the j-th next token of this window
+#pragma unroll
+          for (int j = 0; j < kSMax; ++j) rot[j] = (wb + (tok_s + j) % S) & 31;
           const float* bq = pbase + kPW;
-          const float* bk = pbase + 2 * kPW;
           const float* bv = pbase;
           for (int hh = 0; hh < hpw; ++hh) {
             const int h = P == 1 ? part * hpw + hh : part / P;
@@ -291,7 +293,9 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
             float sc[kSMax];
 #pragma unroll
             for (int j = 0; j < kSMax; ++j) sc[j] = 0.f;
-            // 16 accumulator columns per TMEM round trip (columns past the range are loaded but not used)
+            // 16 accumulator columns per TMEM round trip (columns past the range are loaded but not used).
+            // The key bias adds the same q.b_k to every logit of a row -- softmax cancels it, so it is skipped.
+            // Own token first, then the other S-1 tokens of the window in rotating order (S-1 shuffles per value).
             for (int c16 = 0; c16 < ncol; c16 += 16) {
               float q16[16], k16[16];
               tmem_ld16(tmem + lane_addr + (uint32_t)(c0 + c16), q16);
@@ -301,17 +305,16 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
               for (int e4 = 0; e4 < 4; ++e4)
                 if (c16 + 4 * e4 < ncol) {
                   const float4 bq4 = *reinterpret_cast<const float4*>(bq + c0 + c16 + 4 * e4);
-                  const float4 bk4 = *reinterpret_cast<const float4*>(bk + c0 + c16 + 4 * e4);
                   float* q4 = q16 + 4 * e4;
                   float* k4 = k16 + 4 * e4;
                   q4[0] += bq4.x; q4[1] += bq4.y; q4[2] += bq4.z; q4[3] += bq4.w;
-                  k4[0] += bk4.x; k4[1] += bk4.y; k4[2] += bk4.z; k4[3] += bk4.w;
 #pragma unroll
-                  for (int j = 0; j < kSMax; ++j)
+                  for (int e = 0; e < 4; ++e) sc[0] = fmaf(q4[e], k4[e], sc[0]);
+#pragma unroll
+                  for (int j = 1; j < kSMax; ++j)
                     if (j < S) {
-                      const int src = (wb + j) & 31;
 #pragma unroll
-                      for (int e = 0; e < 4; ++e) sc[j] = fmaf(q4[e], __shfl_sync(0xffffffffu, k4[e], src), sc[j]);
+                      for (int e = 0; e < 4; ++e) sc[j] = fmaf(q4[e], __shfl_sync(0xffffffffu, k4[e], rot[j]), sc[j]);
                     }
                 }
             }
@@ -319,7 +322,7 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
 #pragma unroll
               for (int j = 0; j < kSMax; ++j)
                 if (j < S) xsc[(part * kSMax + j) * 128 + row] = sc[j];
-              __syncthreads();
+              group_barrier(lane_grp);
 #pragma unroll
               for (int j = 0; j < kSMax; ++j)
                 if (j < S) {
@@ -353,13 +356,14 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
                   const float4 bv4 = *reinterpret_cast<const float4*>(bv + c0 + c16 + 4 * e4);
                   float* v4 = v16 + 4 * e4;
                   v4[0] += bv4.x; v4[1] += bv4.y; v4[2] += bv4.z; v4[3] += bv4.w;
-                  float o4[4] = {0.f, 0.f, 0.f, 0.f};
+                  float o4[4];
 #pragma unroll
-                  for (int j = 0; j < kSMax; ++j)
+                  for (int e = 0; e < 4; ++e) o4[e] = sc[0] * v4[e];
+#pragma unroll
+                  for (int j = 1; j < kSMax; ++j)
                     if (j < S) {
-                      const int src = (wb + j) & 31;
 #pragma unroll
-                      for (int e = 0; e < 4; ++e) o4[e] = fmaf(sc[j], __shfl_sync(0xffffffffu, v4[e], src), o4[e]);
+                      for (int e = 0; e < 4; ++e) o4[e] = fmaf(sc[j], __shfl_sync(0xffffffffu, v4[e], rot[j]), o4[e]);
                     }
                   const int c = c0 + c16 + 4 * e4;
                   uint2 pk = make_uint2(pack_bf16x2(o4[0] * inv, o4[1] * inv), pack_bf16x2(o4[2] * inv, o4[3] * inv));
@@ -505,14 +509,13 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               // generic loads: staged copy in the ring slot (GEMM ops) or the arena itself (stand-alone norms)
-              const bool in = g * 16 + 4 * e < d;          // d % 4 == 0 (make_geo)
-              const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-              const float4 gm = in ? *reinterpret_cast<const float4*>(ln_g + g * 16 + 4 * e) : zero4;
-              const float4 bt = in ? *reinterpret_cast<const float4*>(ln_b + g * 16 + 4 * e) : zero4;
-              y[4 * e + 0] = in ? fmaf((st[i][4 * e + 0] - mean) * rstd, gm.x, bt.x) : 0.f;
-              y[4 * e + 1] = in ? fmaf((st[i][4 * e + 1] - mean) * rstd, gm.y, bt.y) : 0.f;
-              y[4 * e + 2] = in ? fmaf((st[i][4 * e + 2] - mean) * rstd, gm.z, bt.z) : 0.f;
-              y[4 * e + 3] = in ? fmaf((st[i][4 * e + 3] - mean) * rstd, gm.w, bt.w) : 0.f;
+              // gamma / beta are zero beyond d_model (padded arena / zeroed staging block): padded columns give 0
+              const float4 gm = *reinterpret_cast<const float4*>(ln_g + g * 16 + 4 * e);
+              const float4 bt = *reinterpret_cast<const float4*>(ln_b + g * 16 + 4 * e);
+              y[4 * e + 0] = fmaf((st[i][4 * e + 0] - mean) * rstd, gm.x, bt.x);
+              y[4 * e + 1] = fmaf((st[i][4 * e + 1] - mean) * rstd, gm.y, bt.y);
+              y[4 * e + 2] = fmaf((st[i][4 * e + 2] - mean) * rstd, gm.z, bt.z);
+              y[4 * e + 3] = fmaf((st[i][4 * e + 3] - mean) * rstd, gm.w, bt.w);
             }
             if (post == XP_LN_INPLACE_TO_AOP) {
 #pragma unroll
