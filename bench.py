@@ -54,6 +54,10 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback"}
 
 
+# DRAM bytes per launch of the dominant kernel, from the committed ncu capture (profiles/r1_bf16_summary.md)
+NCU_DRAM_BYTES = {("A", "bf16", "tokenizer"): 294_720_512}
+
+
 def build_model(name: str):
     """Drop-in facade of config `name` with deterministic synthetic weights (CPU, eval)."""
     import importlib
@@ -278,20 +282,25 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    # per-kernel timing of the two kernels of the path (same stream, same inputs), K launches each
+    # per-kernel timing of the two kernels of the path (same stream, same inputs): K back-to-back launches each,
+    # CUDA events on the launching stream.  (The step itself is ONE native call that launches both kernels, so no
+    # event can be placed between them there; tok_ms + xf_ms is checked against the step time below.)
     tok = eng.tokenize(x, precision=a.precision)
     rec = eng.reconstruct_tokens(tok, precision=a.precision)
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(a.steps)]
-    torch.cuda.synchronize(dev)
-    for k in range(a.steps):                       # same interleaving as a step: tokenizer then transformer
-        evs[k][0].record()
-        eng.tokenize(x, precision=a.precision, out=tok)
-        evs[k][1].record()
-        eng.reconstruct_tokens(tok, precision=a.precision, out=rec)
-        evs[k][2].record()
-    torch.cuda.synchronize(dev)
-    tok_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / a.steps
-    xf_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / a.steps
+
+    def _loop_ms(fn):
+        fn()
+        torch.cuda.synchronize(dev)
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        for _ in range(a.steps):
+            fn()
+        k1.record()
+        torch.cuda.synchronize(dev)
+        return k0.elapsed_time(k1) / a.steps
+
+    tok_ms = _loop_ms(lambda: eng.tokenize(x, precision=a.precision, out=tok))
+    xf_ms = _loop_ms(lambda: eng.reconstruct_tokens(tok, precision=a.precision, out=rec))
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -349,8 +358,11 @@ def main():
         achieved = dom_flops * n / ((tok_ms if dom == "tokenizer" else xf_ms) * 1e-3) / 1e12
         peak = peaks["bf16_sustained"]
         roofline = {"bound": "tensor", "kernel": f"{dom}_{a.precision}", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": f"{peaks['source']} bf16 sustained (MEASURED_PEAKS.json)",
-                    "flops_per_window": dom_flops, "kernel_ms": {"tokenizer": tok_ms, "transformer": xf_ms},
+                    "frac": achieved / peak, "traffic": NCU_DRAM_BYTES.get((a.config, a.precision, dom)) if n == 65536 else None,
+                    "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel per 65,536-window launch, bytes, from the ncu --set full "
+                                    "capture summarised in profiles/r1_bf16_summary.md (algorithmic: 213.9 MB poses in + 106.9 MB tokens out)",
+                    "peak_source": f"{peaks['source']} bf16 sustained (MEASURED_PEAKS.json)",
+                    "flops_per_window": dom_flops, "kernel_ms": {"tokenizer": tok_ms, "transformer": xf_ms, "sum_vs_step": (tok_ms + xf_ms) / (ms / a.steps)},
                     "path_frac": path_flops * n / ((tok_ms + xf_ms) * 1e-3) / 1e12 / peak,
                     "note": "fp32 path runs on the FFMA pipe, not the tensor pipe; frac is vs the bf16 tensor peak"
                             if a.precision == "fp32" else ""}
@@ -376,10 +388,11 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if a.precision == "fp32" else "bf16", "data": "synthetic",
-        "config": {"workload": f"shopformer config {a.config} (BASELINE configs[1]): {n} synthetic COCO-17 windows per GPU, "
+        "config": {"workload": f"shopformer config {a.config}{' (BASELINE configs[1])' if a.config == 'A' else ''}: {n} synthetic windows per GPU, "
                                f"T={T}, V={V}, S={S}, d={D}, deterministic synthetic weights",
                    "windows_per_gpu_per_step": n, "precision": a.precision,
-                   "l2": f"inputs larger than L2 ({xs.nbytes / 1e6:.0f} MB of windows per step vs 126 MB L2)",
+                   "l2": (f"inputs larger than L2 ({xs.nbytes / 1e6:.0f} MB of windows per step vs 126 MB L2)" if xs.nbytes > 126e6 else
+                          f"inputs ({xs.nbytes / 1e6:.0f} MB) + tokens smaller than the 126 MB L2: not a headline configuration"),
                    "collective": "NCCL all-gather of fp32 scores" if world > 1 else "none (1 GPU)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "sf_runner_score (C ABI, host buffers, <=16384-window whole-wave chunks, copy + compute stream, 4-slot ring)", "steps": e2e_steps},

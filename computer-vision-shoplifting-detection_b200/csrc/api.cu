@@ -89,7 +89,7 @@ constexpr int kRing = 4;
 struct sf_runner {
   const sf_model* m;
   int T, S;
-  int64_t chunk;
+  int64_t chunk, first_chunk;     // windows per upload; a shorter first upload (one wave) when chunk spans several
   size_t pose_elems;              // floats per window
   cudaStream_t copy_st, comp_st;
   cudaEvent_t copied[kRing], computed[kRing];
@@ -115,6 +115,7 @@ extern "C" int sf_runner_create(const sf_model* m, int32_t T, int64_t max_chunk,
   // chunk that is a multiple of sm_count * tile leaves no partial wave (and is a whole number of tokenizer waves)
   const int64_t wave = (int64_t)m->sm_count * 4 * (32 / std::max(1, std::min(r->S, 32)));
   r->chunk = max_chunk >= wave ? max_chunk / wave * wave : max_chunk;
+  r->first_chunk = r->chunk > wave ? wave : 0;
   r->pose_elems = (size_t)m->cfg.in_channels * T * m->cfg.num_keypoints;
   r->ws_bytes = sf_workspace_bytes(m, r->chunk, T);
   cudaError_t e = cudaStreamCreateWithFlags(&r->copy_st, cudaStreamNonBlocking);
@@ -164,7 +165,6 @@ extern "C" float* sf_runner_pinned_poses(sf_runner* r, int32_t slot) {
 extern "C" int sf_runner_score(sf_runner* r, const float* poses_host, int64_t B, int32_t precision, float* scores_host) {
   SF_REQUIRE(r && (B == 0 || (poses_host && scores_host)), SF_E_INVALID, "sf_runner_score: null argument");
   SF_CUDA_OK(cudaSetDevice(r->m->device));
-  const int64_t n_chunks = (B + r->chunk - 1) / r->chunk;
   int64_t pending_off[kRing], pending_n[kRing];
   for (int i = 0; i < kRing; ++i) pending_off[i] = -1, pending_n[i] = 0;
   bool src_pinned = false;
@@ -173,9 +173,12 @@ extern "C" int sf_runner_score(sf_runner* r, const float* poses_host, int64_t B,
     if (cudaPointerGetAttributes(&attr, poses_host) == cudaSuccess) src_pinned = attr.type == cudaMemoryTypeHost;
     else cudaGetLastError();
   }
-  for (int64_t c = 0; c < n_chunks; ++c) {
+  int64_t off = 0;
+  for (int64_t c = 0; off < B; ++c) {
     const int s = (int)(c % kRing);
-    const int64_t off = c * r->chunk, n = std::min(r->chunk, B - off);
+    // the first upload is not hidden behind any kernel: start with a single wave, then full chunks
+    const int64_t want = (c == 0 && r->first_chunk > 0) ? r->first_chunk : r->chunk;
+    const int64_t n = std::min(want, B - off);
     if (pending_off[s] >= 0) {                       // drain the slot before reusing its buffers
       SF_CUDA_OK(cudaEventSynchronize(r->computed[s]));
       memcpy(scores_host + pending_off[s], r->pin_out[s], pending_n[s] * sizeof(float));
@@ -199,13 +202,12 @@ extern "C" int sf_runner_score(sf_runner* r, const float* poses_host, int64_t B,
     SF_CUDA_OK(cudaEventRecord(r->computed[s], r->comp_st));
     pending_off[s] = off;
     pending_n[s] = n;
+    off += n;
   }
-  for (int64_t c = std::max<int64_t>(0, n_chunks - kRing); c < n_chunks; ++c) {     // oldest first
-    const int s = (int)(c % kRing);
+  for (int s = 0; s < kRing; ++s)                   // drain (one compute stream: any order)
     if (pending_off[s] >= 0) {
       SF_CUDA_OK(cudaEventSynchronize(r->computed[s]));
       memcpy(scores_host + pending_off[s], r->pin_out[s], pending_n[s] * sizeof(float));
     }
-  }
   return SF_OK;
 }
