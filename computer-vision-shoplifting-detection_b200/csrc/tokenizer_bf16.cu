@@ -33,7 +33,7 @@ namespace {
 
 using namespace tc;
 
-constexpr int kThreads = 256;
+constexpr int kThreadsMin = 256;      // 2 CTAs/SM shapes; shapes that only fit one CTA per SM run 512 threads
 constexpr int kIssuers = 4;          // lane 0 of warps 0..3 issue the MMAs of tiles t = warp (mod 4)
 constexpr int kEllMax = 8;
 constexpr uint16_t kGap = 0xFFFF;
@@ -72,11 +72,11 @@ __device__ __forceinline__ void cp_async_wait_all() {
 }
 __device__ __forceinline__ void stage(unsigned char* dst, const uint16_t* src, int bytes) {
   const unsigned char* s = reinterpret_cast<const unsigned char*>(src);
-  for (int i = threadIdx.x * 16; i < bytes; i += kThreads * 16) cp_async16(dst + i, s + i);
+  for (int i = threadIdx.x * 16; i < bytes; i += (int)blockDim.x * 16) cp_async16(dst + i, s + i);
 }
 __device__ __forceinline__ void zero_fill(unsigned char* p, int bytes) {
   uint4* q = reinterpret_cast<uint4*>(p);
-  for (int i = threadIdx.x; i < (bytes >> 4); i += kThreads) q[i] = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < (bytes >> 4); i += (int)blockDim.x) q[i] = make_uint4(0, 0, 0, 0);
 }
 // descriptor with separately tracked low word: advancing an operand is one 32-bit add
 __device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
@@ -106,7 +106,7 @@ template <int W>
 __device__ __forceinline__ void mix_a0(const float* __restrict__ x0, unsigned char* __restrict__ a0, uint32_t plane_bytes,
                                        const uint16_t* __restrict__ rt, const float2* __restrict__ ell, int V, int cin, int tv,
                                        int per_w, int nw, int rtot) {
-  for (int r = threadIdx.x; r < rtot; r += kThreads) {
+  for (int r = threadIdx.x; r < rtot; r += (int)blockDim.x) {
     const uint32_t en = rt[r];
     const bool ok = en != kGap && (int)(en >> 11) < nw;
     const int v = ok ? (int)(en & 31) : 0;
@@ -198,7 +198,8 @@ __device__ __forceinline__ void conv_issue(uint32_t d, uint32_t a_lo0, uint32_t 
     }                                                                                   \
   } while (0)
 
-__global__ void __launch_bounds__(kThreads, 2)
+template <int kThreads>
+__global__ void __launch_bounds__(kThreads, kThreads == 256 ? 2 : 1)
 tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict__ poses, float* __restrict__ tokens,
                       int64_t B) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -221,7 +222,8 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
   const int V = pl.V, G = pl.G;
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform on purpose (uniform datapath)
   const int lane = threadIdx.x & 31;
-  const int lane_grp = warp & 3, col_half = warp >> 2;
+  const int lane_grp = warp & 3, col_part = warp >> 2;
+  constexpr int kParts = kThreads / 128;                 // warps sharing a 32-row lane group split (column group, tile) units
   const int per_w = pl.c_in * pl.T0 * V;
 
   // ------------------------------------------------------------------ one-time setup
@@ -367,8 +369,10 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
       const uint16_t* rt = reinterpret_cast<const uint16_t*>(smem + b.off_rowtab);
       const uint16_t* mt = reinterpret_cast<const uint16_t*>(smem + b.off_mtab);
       const int groups = b.npad >> 4;               // 16-column groups per accumulator tile
-      const int g_first = groups > 1 ? col_half : 0, g_step = groups > 1 ? 2 : 1;
-      const bool idle_half = groups == 1 && col_half == 1;
+      // epilogue work split over the kParts warps of a lane group: by column group when there are enough of them,
+      // otherwise also by accumulator tile
+      const int g_first = groups >= kParts ? col_part : col_part % groups, g_step = groups >= kParts ? kParts : groups;
+      const int t_first = groups >= kParts ? 0 : col_part / groups, t_step = groups >= kParts ? 1 : kParts / groups;
       TOK_STAMP(110 + bi * 10);
       if (bi > 0) {
         // ---- stage this block's weights, clear the output buffer, adjacency mix x_b -> A (bf16)
@@ -426,37 +430,28 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
         if (bi == 0 && pl.n_blocks > 1) zero_fill(sX[0], pl.blk[1].rtot * pl.blk[1].kin * 2);    // A0 is dead: clear x1
         // ---- g = relu(P + b) -> bf16 over M in place (gap rows -> 0)
         const float* bgp = bias_g + bi * 64;
-        if (!idle_half) {
-          for (int gq = g_first; gq < groups; gq += g_step) {
-            // all TMEM loads of this column group first (one wait), then the arithmetic
-            float4 bb[4];
+        for (int gq = g_first; gq < groups; gq += g_step) {
+          float4 bb[4];
 #pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) bb[q4] = *reinterpret_cast<const float4*>(bgp + gq * 16 + q4 * 4);
-            for (int t0 = 0; t0 < p_tiles; t0 += 1) {
-            float acc[1][16];
+          for (int q4 = 0; q4 < 4; ++q4) bb[q4] = *reinterpret_cast<const float4*>(bgp + gq * 16 + q4 * 4);
+          for (int t0 = t_first; t0 < p_tiles; t0 += t_step) {
+          float acc[16];
+          tmem_ld16(tmem + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(t0 * dcol + gq * 16), acc);
+          tmem_ld_wait();
+          const int r = t0 * 128 + lane_grp * 32 + lane;
+          if (r < b.rtot) {
+            const bool data = rt[r] != kGap;
+            float y[16];
 #pragma unroll
-            for (int tl = 0; tl < 1; ++tl)
-              if (t0 + tl < p_tiles) tmem_ld16(tmem + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)((t0 + tl) * dcol + gq * 16), acc[tl]);
-            tmem_ld_wait();
-#pragma unroll
-            for (int tl = 0; tl < 1; ++tl) {
-              const int tile = tl;
-              const int r = (t0 + tl) * 128 + lane_grp * 32 + lane;
-              if (t0 + tl < p_tiles && r < b.rtot) {
-                const bool data = rt[r] != kGap;
-                float y[16];
-#pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) {
-                  y[q4 * 4 + 0] = data ? fmaxf(acc[tile][q4 * 4 + 0] + bb[q4].x, 0.f) : 0.f;
-                  y[q4 * 4 + 1] = data ? fmaxf(acc[tile][q4 * 4 + 1] + bb[q4].y, 0.f) : 0.f;
-                  y[q4 * 4 + 2] = data ? fmaxf(acc[tile][q4 * 4 + 2] + bb[q4].z, 0.f) : 0.f;
-                  y[q4 * 4 + 3] = data ? fmaxf(acc[tile][q4 * 4 + 3] + bb[q4].w, 0.f) : 0.f;
-                }
-                *reinterpret_cast<uint4*>(sA + ((size_t)(gq * 2) * b.rtot + r) * 16) = pack8(y);
-                *reinterpret_cast<uint4*>(sA + ((size_t)(gq * 2 + 1) * b.rtot + r) * 16) = pack8(y + 8);
-              }
+            for (int q4 = 0; q4 < 4; ++q4) {
+              y[q4 * 4 + 0] = data ? fmaxf(acc[q4 * 4 + 0] + bb[q4].x, 0.f) : 0.f;
+              y[q4 * 4 + 1] = data ? fmaxf(acc[q4 * 4 + 1] + bb[q4].y, 0.f) : 0.f;
+              y[q4 * 4 + 2] = data ? fmaxf(acc[q4 * 4 + 2] + bb[q4].z, 0.f) : 0.f;
+              y[q4 * 4 + 3] = data ? fmaxf(acc[q4 * 4 + 3] + bb[q4].w, 0.f) : 0.f;
             }
-            }
+            *reinterpret_cast<uint4*>(sA + ((size_t)(gq * 2) * b.rtot + r) * 16) = pack8(y);
+            *reinterpret_cast<uint4*>(sA + ((size_t)(gq * 2 + 1) * b.rtot + r) * 16) = pack8(y + 8);
+          }
           }
         }
       }
@@ -523,27 +518,20 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
       const float* bop = bias_o + bi * 64;
       const int nxt_rtot = last ? 0 : pl.blk[bi + 1].rtot;
       const int tv = pl.T0 * V;
-      if (!idle_half) {
-        for (int gq = g_first; gq < groups; gq += g_step) {
-          // all TMEM loads of this column group first (one wait), then the arithmetic of each tile
+      for (int gq = g_first; gq < groups; gq += g_step) {
+        {
           float4 bb[4];
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) bb[q4] = *reinterpret_cast<const float4*>(bop + gq * 16 + q4 * 4);
-          for (int t0 = 0; t0 < m_tiles; t0 += 1) {
-          float accs[1][16];
-#pragma unroll
-          for (int tl = 0; tl < 1; ++tl)
-            if (t0 + tl < m_tiles) tmem_ld16(tmem + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)((t0 + tl) * dcol + gq * 16), accs[tl]);
+          for (int t0 = t_first; t0 < m_tiles; t0 += t_step) {
+          float acc[16];
+          tmem_ld16(tmem + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(t0 * dcol + gq * 16), acc);
           tmem_ld_wait();
-#pragma unroll
-          for (int tl = 0; tl < 1; ++tl) {
-            const int tile = tl;
-            if (t0 + tl >= m_tiles) continue;
-            const int mrow = (t0 + tl) * 128 + lane_grp * 32 + lane;
+          {
+            const int mrow = t0 * 128 + lane_grp * 32 + lane;
             const uint32_t e = mrow < b.mrows ? mt[mrow] : kGap;
             const int w = e >> 11, target = e & 0x7FF;
             if (e == kGap || w >= nw) continue;
-            float* acc = accs[tile];
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4) {
               acc[q4 * 4 + 0] += bb[q4].x; acc[q4 * 4 + 1] += bb[q4].y; acc[q4 * 4 + 2] += bb[q4].z; acc[q4 * 4 + 3] += bb[q4].w;
@@ -628,7 +616,7 @@ bool build_plan(const sf_model* m, int T, int G, BfPlan* pl, const char** why) {
     b.stride = tb.stride;
     b.Tin = Tin;
     b.Tout = Tin / tb.stride;
-    if (b.npad > 64 || (kThreads % (b.npad >> 3)) || (i > 0 && (kThreads % (b.kin >> 3)))) { *why = "channel count"; return false; }
+    if (b.npad > 64 || (kThreadsMin % (b.npad >> 3)) || (i > 0 && (kThreadsMin % (b.kin >> 3)))) { *why = "channel count"; return false; }
     if (i > 0 && b.kin != pl->blk[i - 1].npad) { *why = "channel padding mismatch"; return false; }
     if (tb.ell_width > kEllMax) { *why = "adjacency rows with more than 8 non-zeros"; return false; }
     // taps: input row t = s*t' + k - 4 -> phase p = (k-4) mod s, offset o = (k-4-p)/s; live iff |o| < Tout
@@ -729,9 +717,6 @@ int launch_tokenizer_bf16(const sf_model* m, const float* poses, int64_t B, int 
   BfPlan pl;
   const char* why = "";
   SF_REQUIRE(build_plan(m, T, 1, &pl, &why), SF_E_UNSUPPORTED, "bf16 tensor-core tokenizer does not cover this shape: %s", why);
-  SF_CUDA_OK(cudaFuncSetAttribute(tokenizer_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
-  SF_CUDA_OK(cudaFuncSetAttribute(tokenizer_bf16_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                  (int)cudaSharedmemCarveoutMaxShared));
   // CTAs per SM: shared memory (1 KB driver reservation per CTA), registers (128 x 256 threads) and TMEM columns --
   // co-resident CTAs must all get their tensor-memory allocation or they would serialise on tcgen05.alloc.
   int smem_per_sm = 0;
@@ -741,7 +726,17 @@ int launch_tokenizer_bf16(const sf_model* m, const float* poses, int64_t B, int 
   if (const char* dbg = getenv("SF_TOK_OCC")) occ = std::max(1, std::min(occ, atoi(dbg)));     // debugging aid
   const int64_t n_groups = (B + pl.G - 1) / pl.G;
   const int grid = (int)std::min<int64_t>(n_groups, (int64_t)m->sm_count * occ);
-  tokenizer_bf16_kernel<<<grid, kThreads, pl.smem_bytes, st>>>(pl, poses, tokens, B);
+  // two CTAs per SM run 256 threads each; a shape that only fits one CTA per SM gets 512 threads so that the
+  // CUDA-core phases still have 16 warps per SM to hide latency with
+  auto launch = [&](auto kernel, int threads) -> int {
+    SF_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
+    SF_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    kernel<<<grid, threads, pl.smem_bytes, st>>>(pl, poses, tokens, B);
+    return SF_OK;
+  };
+  const bool wide = occ == 1 && !getenv("SF_TOK_NARROW");
+  int rc = wide ? launch(tokenizer_bf16_kernel<512>, 512) : launch(tokenizer_bf16_kernel<256>, 256);
+  if (rc) return rc;
   SF_CUDA_OK(cudaGetLastError());
   return SF_OK;
 }
