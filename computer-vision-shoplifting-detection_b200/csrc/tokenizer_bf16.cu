@@ -16,7 +16,8 @@
 //   * epilogues read TMEM with tcgen05.ld, add the folded bias, ReLU, and write the next operand
 //     straight back to shared memory as bf16 -- nothing but the final tokens (fp32) goes to HBM;
 //   * every row -> (window, time, keypoint) decode is a shared-memory table built once per CTA, biases
-//     and the block-0 weights are staged once per CTA, MMA issue is spread over four warps.
+//     and the block-0 weights are staged once per CTA, MMA issue is spread over four warps;
+//   * per-block weight images and the next window's poses arrive by TMA (cp.async.bulk, mbarrier complete_tx).
 //
 // One CTA owns G windows at a time (persistent); phases are separated by mbarrier (MMA completion) and
 // __syncthreads; two CTAs per SM overlap one CTA's MMAs with the other's CUDA-core phases.
@@ -64,16 +65,6 @@ struct BfPlan {
 };
 static_assert(sizeof(BfPlan) <= 3900, "BfPlan must fit in kernel parameter space");
 
-__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-}
-__device__ __forceinline__ void stage(unsigned char* dst, const uint16_t* src, int bytes) {
-  const unsigned char* s = reinterpret_cast<const unsigned char*>(src);
-  for (int i = threadIdx.x * 16; i < bytes; i += (int)blockDim.x * 16) cp_async16(dst + i, s + i);
-}
 __device__ __forceinline__ void zero_fill(unsigned char* p, int bytes) {
   uint4* q = reinterpret_cast<uint4*>(p);
   for (int i = threadIdx.x; i < (bytes >> 4); i += (int)blockDim.x) q[i] = make_uint4(0, 0, 0, 0);
@@ -203,7 +194,7 @@ __global__ void __launch_bounds__(kThreads, kThreads == 256 ? 2 : 1)
 tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict__ poses, float* __restrict__ tokens,
                       int64_t B) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar, wbar, pbar[2];     // MMA completion; TMA: weights of a block, poses of a window group (2 buffers)
   __shared__ uint32_t tmem_base_s;
   unsigned char* sA = smem + pl.off_A;
   unsigned char* sX[2] = {smem + pl.off_X0, smem + pl.off_X1};
@@ -230,6 +221,9 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
   if (warp == 0) tmem_alloc(&tmem_base_s, pl.tmem_cols);
   if (threadIdx.x == 0) {
     mbar_init(&bar, kIssuers);
+    mbar_init(&wbar, 1);
+    mbar_init(&pbar[0], 1);
+    mbar_init(&pbar[1], 1);
     fence_mbar_init();
   }
   for (int bi = 0; bi < pl.n_blocks; ++bi) {
@@ -322,16 +316,17 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
   int stamp_i = 0;
 
   const int64_t n_groups = (B + G - 1) / G;
-  // raw poses of a window group are prefetched with cp.async one iteration ahead (16-byte granules)
-  auto prefetch = [&](int64_t g_idx, float* dst) {
-    if (g_idx >= n_groups) return;
+  // raw poses of a window group are fetched by TMA one iteration ahead (one bulk copy, issued by thread 0)
+  auto prefetch = [&](int64_t g_idx, int buf) {
+    if (g_idx >= n_groups || threadIdx.x != 0) return;
     const int64_t wf = g_idx * G;
-    const int cnt = (int)((B - wf) < (int64_t)G ? (B - wf) : (int64_t)G) * per_w;
-    const float* src = poses + (size_t)wf * per_w;
-    for (int i = threadIdx.x * 4; i < cnt; i += kThreads * 4) cp_async16(dst + i, src + i);
+    const uint32_t bytes = (uint32_t)((B - wf) < (int64_t)G ? (B - wf) : (int64_t)G) * (uint32_t)per_w * 4u;
+    mbar_expect_tx(&pbar[buf], bytes);
+    tma_load_1d(xbuf[buf], poses + (size_t)wf * per_w, bytes, &pbar[buf]);
   };
   int xcur = 0;
-  prefetch(blockIdx.x, xbuf[0]);
+  uint32_t wpar = 0, ppar = 0;                          // phase parities: weights barrier, pose barriers (bit per buffer)
+  prefetch(blockIdx.x, 0);
   for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
     const int64_t w_first = grp * G;
     const int nw = (int)((B - w_first) < (int64_t)G ? (B - w_first) : (int64_t)G);
@@ -341,10 +336,15 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
     // =============================== block 0 prologue ===============================
     {
       const BfBlk& b = pl.blk[0];
-      cp_async_wait_all();                               // this group's poses (prefetched during the previous group)
+      if (warp == 0) mbar_wait(&pbar[xcur], (ppar >> xcur) & 1u);      // this group's poses (fetched during the previous group)
+      ppar ^= 1u << xcur;
       __syncthreads();
-      stage(sWT, b.w_tcn, kTaps * b.npad * b.npad * 2);
-      prefetch(grp + gridDim.x, xbuf[xcur ^ 1]);
+      if (threadIdx.x == 0) {                            // temporal-conv weights of block 0: one bulk copy
+        const uint32_t bytes = (uint32_t)(kTaps * b.npad * b.npad * 2);
+        mbar_expect_tx(&wbar, bytes);
+        tma_load_1d(sWT, b.w_tcn, bytes, &wbar);
+      }
+      prefetch(grp + gridDim.x, xcur ^ 1);
       const int n_valid = nw * per_w;
       for (int i = threadIdx.x; i < G * per_w; i += kThreads) {
         const int j = xjtab[i];
@@ -376,9 +376,14 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
       TOK_STAMP(110 + bi * 10);
       if (bi > 0) {
         // ---- stage this block's weights, clear the output buffer, adjacency mix x_b -> A (bf16)
-        stage(sWG, b.w_gcn, b.kin * b.npad * 2);
-        stage(sWT, b.w_tcn, kTaps * b.npad * b.npad * 2);
-        if (b.w_res) stage(sWT + kTaps * b.npad * b.npad * 2, b.w_res, b.kin * b.npad * 2);
+        if (threadIdx.x == 0) {                          // TMA: graph-conv, temporal-conv and residual weight images
+          const uint32_t bg = (uint32_t)(b.kin * b.npad * 2), bt = (uint32_t)(kTaps * b.npad * b.npad * 2);
+          const uint32_t br = b.w_res ? bg : 0u;
+          mbar_expect_tx(&wbar, bg + bt + br);
+          tma_load_1d(sWG, b.w_gcn, bg, &wbar);
+          tma_load_1d(sWT, b.w_tcn, bt, &wbar);
+          if (br) tma_load_1d(sWT + bt, b.w_res, br, &wbar);
+        }
         if (bi + 1 < pl.n_blocks) zero_fill(sXout, pl.blk[bi + 1].rtot * pl.blk[bi + 1].kin * 2);
         {
           const int chunks = b.kin >> 3;
@@ -391,7 +396,8 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
           else mix_rows<kEllMax>(plane, dstp, rt, el, V, threadIdx.x - j * tpc, tpc, b.rtot);
         }
         TOK_STAMP(111 + bi * 10);
-        cp_async_wait_all();
+        if (warp == 0) mbar_wait(&wbar, wpar);
+        wpar ^= 1u;
       }
       {
         fence_proxy_async();
@@ -455,7 +461,10 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
           }
         }
       }
-      if (bi == 0) cp_async_wait_all();               // temporal-conv weights (staged in the prologue)
+      if (bi == 0) {                                  // temporal-conv weights (requested in the prologue)
+        if (warp == 0) mbar_wait(&wbar, wpar);
+        wpar ^= 1u;
+      }
       TOK_STAMP(114 + bi * 10);
       fence_proxy_async();
       tc_fence_before();
@@ -717,6 +726,7 @@ int launch_tokenizer_bf16(const sf_model* m, const float* poses, int64_t B, int 
   BfPlan pl;
   const char* why = "";
   SF_REQUIRE(build_plan(m, T, 1, &pl, &why), SF_E_UNSUPPORTED, "bf16 tensor-core tokenizer does not cover this shape: %s", why);
+  SF_REQUIRE(((uintptr_t)poses & 15) == 0, SF_E_INVALID, "pose buffer must be 16-byte aligned (TMA bulk copies)");
   // CTAs per SM: shared memory (1 KB driver reservation per CTA), registers (128 x 256 threads) and TMEM columns --
   // co-resident CTAs must all get their tensor-memory allocation or they would serialise on tcgen05.alloc.
   int smem_per_sm = 0;

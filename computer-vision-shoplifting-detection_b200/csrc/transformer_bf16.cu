@@ -10,7 +10,7 @@
 //     computed straight out of TMEM with warp shuffles over the token axis;
 //   * every nn.Linear is a chain of tcgen05.mma (M=128, N = padded width, K = 16 per instruction) with the
 //     bf16 activation operand in shared memory (planar-chunk layout, tc_common.cuh) and the weight image
-//     streamed L2 -> smem through a 2-slot cp.async ring, prefetched one GEMM ahead;
+//     streamed L2 -> smem by TMA (cp.async.bulk + mbarrier complete_tx) through a 2-slot ring, one GEMM ahead;
 //   * the fp32 residual stream of a row lives in REGISTERS (four warps share a row: every 4th 16-column
 //     group each); bias, residual add, LayerNorm (two-pass, partial sums exchanged through smem), ReLU / exact
 //     GELU and the bf16 down-conversion of the next operand all happen in the TMEM epilogue;
@@ -52,16 +52,6 @@ struct XfGeo {
   int param_off;                       // byte offset of the fp32 parameter block inside a ring slot
 };
 
-__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-}
-__device__ __forceinline__ void stage(unsigned char* dst, const uint16_t* src, int bytes) {
-  const unsigned char* s = reinterpret_cast<const unsigned char*>(src);
-  for (int i = threadIdx.x * 16; i < bytes; i += kThreads * 16) cp_async16(dst + i, s + i);
-}
 __device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
   return ((smem_addr >> 4) & 0x3FFFu) | ((lbo_bytes >> 4) << 16);
 }
@@ -82,9 +72,6 @@ __device__ __forceinline__ void gemm_issue(uint32_t d, uint32_t alo0, uint32_t b
   }
 #pragma unroll
   for (int ks = 0; ks < KS; ++ks) umma_bf16(d, desc_join(al[ks]), desc_join(bl[ks]), idesc, (accumulate || ks > 0) ? 1u : 0u);
-}
-__device__ __forceinline__ void stagef(float* dst, const float* src, int n_floats) {
-  for (int i = threadIdx.x * 4; i < n_floats; i += kThreads * 4) cp_async16(dst + i, src + i);
 }
 
 // 16 consecutive floats of a 16-byte aligned global row; columns >= lim (lim % 4 == 0) or !ok read as zero
@@ -122,7 +109,7 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
                         const float* __restrict__ tokens, int64_t B, int reduction, float* __restrict__ recon_out,
                         float* __restrict__ scores) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar, wbar[2];            // MMA completion; TMA completion per weight-ring slot
   __shared__ uint32_t tmem_base_s;
   unsigned char* sAop = smem + geo.off_aop;
   unsigned char* sHop = smem + geo.off_hop;
@@ -142,6 +129,8 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
   if (warp == 0) tmem_alloc(&tmem_base_s, 512);
   if (threadIdx.x == 0) {
     mbar_init(&bar, 1);
+    mbar_init(&wbar[0], 1);
+    mbar_init(&wbar[1], 1);
     fence_mbar_init();
   }
   // zero the operand buffers once: padded columns / idle rows must stay finite (NaN * 0 = NaN in the MMA)
@@ -152,7 +141,7 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
-  uint32_t parity = 0;
+  uint32_t parity = 0, wpar = 0;
   const bool timing = g_xf_timing_on && blockIdx.x == 0;
   int stamp_i = 0;
 
@@ -173,18 +162,22 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
 
     int slot = 0, ln_buf = 0;
     // weights + the op's fp32 parameters (biases, LayerNorm affine) go into ring slot `sl`
+    // TMA (bulk async copies issued by thread 0, completion on the slot's mbarrier): the weight image and the op's
+    // fp32 parameters (bias, q-bias for attention, LayerNorm gamma / beta padded to 160 columns)
     auto stage_op = [&](int idx, int sl) {
+      if (threadIdx.x != 0) return;
       const XfOp o = ops[idx];
       unsigned char* base = sW + sl * geo.slot_bytes;
-      stage(base, o.w, o.K * o.N * 2);
       float* pp = reinterpret_cast<float*>(base + geo.param_off);
-      if (o.bias) stagef(pp, o.bias, o.N);
-      if (o.epi == XE_ATTN) {
-        stagef(pp + kPW, ops[idx - 2].bias, o.N);          // q bias
-      }
+      const uint32_t wbytes = (uint32_t)(o.K * o.N * 2), bbytes = (uint32_t)o.N * 4u, lbytes = kPW * 4u;
+      const float* qb = o.epi == XE_ATTN ? ops[idx - 2].bias : nullptr;
+      mbar_expect_tx(&wbar[sl], wbytes + (o.bias ? bbytes : 0u) + (qb ? bbytes : 0u) + (o.ln_g ? 2u * lbytes : 0u));
+      tma_load_1d(base, o.w, wbytes, &wbar[sl]);
+      if (o.bias) tma_load_1d(pp, o.bias, bbytes, &wbar[sl]);
+      if (qb) tma_load_1d(pp + kPW, qb, bbytes, &wbar[sl]);
       if (o.ln_g) {
-        stagef(pp + 3 * kPW, o.ln_g, (d + 3) & ~3);
-        stagef(pp + 4 * kPW, o.ln_b, (d + 3) & ~3);
+        tma_load_1d(pp + 3 * kPW, o.ln_g, lbytes, &wbar[sl]);
+        tma_load_1d(pp + 4 * kPW, o.ln_b, lbytes, &wbar[sl]);
       }
     };
     {   // prefetch the first GEMM
@@ -229,7 +222,8 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
       }
       // ------------------------------------------------------------------ GEMM + epilogue
       if (op.type == XF_GEMM) {
-        cp_async_wait_all();
+        if (warp == 0) mbar_wait(&wbar[slot], (wpar >> slot) & 1u);      // this op's weights + parameters have landed
+        wpar ^= 1u << slot;
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
