@@ -359,8 +359,9 @@ def main():
         peak = peaks["bf16_sustained"]
         roofline = {"bound": "tensor", "kernel": f"{dom}_{a.precision}", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                     "frac": achieved / peak, "traffic": NCU_DRAM_BYTES.get((a.config, a.precision, dom)) if n == 65536 else None,
-                    "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel per 65,536-window launch, bytes, from the ncu --set full "
-                                    "capture summarised in profiles/r1_bf16_summary.md (algorithmic: 213.9 MB poses in + 106.9 MB tokens out)",
+                    "traffic_note": ("dram__bytes_read.sum + dram__bytes_write.sum of this kernel per 65,536-window launch, bytes, from the ncu "
+                                     "--set full capture summarised in profiles/r1_bf16_summary.md (algorithmic: 213.9 MB poses in + 106.9 MB "
+                                     "tokens out)") if (a.config, a.precision, dom) in NCU_DRAM_BYTES and n == 65536 else None,
                     "peak_source": f"{peaks['source']} bf16 sustained (MEASURED_PEAKS.json)",
                     "flops_per_window": dom_flops, "kernel_ms": {"tokenizer": tok_ms, "transformer": xf_ms, "sum_vs_step": (tok_ms + xf_ms) / (ms / a.steps)},
                     "path_frac": path_flops * n / ((tok_ms + xf_ms) * 1e-3) / 1e12 / peak,
