@@ -149,6 +149,11 @@ def run_reference(a):
     C, T, V = CFG.input_shape(a.config)
     sample = a.ref_windows
     x = torch.from_numpy(synth_windows(sample, T, V, seed=1234)[0])
+    # all the host threads the box has: torchrun exports OMP_NUM_THREADS=1 to its workers, which would throttle this arm
+    try:
+        torch.set_num_threads(len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        torch.set_num_threads(os.cpu_count() or 1)
     cores = torch.get_num_threads()
     for _ in range(a.warmup):
         run(x)
@@ -374,6 +379,10 @@ def main():
     cpu = None
     if world == 1 and not a.no_cpu_baseline:
         sample = min(a.ref_windows, n)
+        try:
+            torch.set_num_threads(len(os.sched_getaffinity(0)))
+        except (AttributeError, OSError):
+            torch.set_num_threads(os.cpu_count() or 1)
         xc = torch.from_numpy(xs[:sample])
         cpu_run(xc)
         reps, t0 = 0, time.perf_counter()
