@@ -16,8 +16,15 @@ int check_T(const sf_model* m, int T) {
 }
 }  // namespace
 
+// Windows per internal pass of sf_score_windows when the caller does not ask for the tokens: bounds the workspace of a
+// 10 M-window sweep to what 131,072 windows need, and a pass's tokens (<= 214 MB) largely stay in the 126 MB L2 between
+// the two kernels.  A multiple of the transformer wave (sm_count x tile) would be marginally better; it only matters
+// for B > 131,072.
+constexpr int64_t kScoreChunk = 131072;
+
 extern "C" int64_t sf_workspace_bytes(const sf_model* m, int64_t B, int32_t T) {
   if (!m || B < 0 || T < 1) return SF_E_INVALID;
+  B = std::min(B, kScoreChunk);
   const int S = token_len(m, T);
   // tokens staged between the two kernels when the caller does not ask for them
   return align256(B * (int64_t)S * m->xf.d_tok * (int64_t)sizeof(float)) + align256(tokenizer_fp32_workspace(m, B, T));
@@ -62,23 +69,35 @@ extern "C" int sf_score_windows(const sf_model* m, const float* poses_dev, int64
   SF_REQUIRE(precision == SF_PREC_FP32 || precision == SF_PREC_BF16, SF_E_INVALID, "unknown precision %d", precision);
   if (B == 0) return SF_OK;
   const int S = token_len(m, T);
-  const int64_t tok_bytes = align256(B * (int64_t)S * m->xf.d_tok * (int64_t)sizeof(float));
-  float* tok = tokens_dev;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t pose_elems = (int64_t)m->cfg.in_channels * T * m->cfg.num_keypoints, tok_elems = (int64_t)S * m->xf.d_tok;
+  // with caller-provided token storage the whole batch goes in one pass; otherwise in passes of kScoreChunk windows
+  const int64_t pass = tokens_dev ? B : std::min(B, kScoreChunk);
+  const int64_t tok_bytes = align256(pass * tok_elems * (int64_t)sizeof(float));
   char* ws = (char*)workspace_dev;
   int64_t ws_left = workspace_bytes;
-  if (!tok) {
+  float* tok_ws = nullptr;
+  if (!tokens_dev) {
     SF_REQUIRE(ws && ws_left >= tok_bytes, SF_E_INVALID, "sf_score_windows: workspace too small (%lld < %lld)",
                (long long)workspace_bytes, (long long)sf_workspace_bytes(m, B, T));
-    tok = (float*)ws;
+    tok_ws = (float*)ws;
     ws += tok_bytes;
     ws_left -= tok_bytes;
   }
-  cudaStream_t st = (cudaStream_t)stream;
-  rc = precision == SF_PREC_BF16 ? launch_tokenizer_bf16(m, poses_dev, B, T, tok, st)
-                                 : launch_tokenizer_fp32(m, poses_dev, B, T, tok, ws, ws_left, st);
-  if (rc) return rc;
-  if (precision == SF_PREC_BF16) return launch_transformer_bf16(m, tok, B, S, reduction, recon_dev, scores_dev, st);
-  return launch_transformer_fp32(m, tok, B, S, reduction, recon_dev, scores_dev, st);
+  const int64_t score_stride = reduction == SF_REDUCE_NONE ? S : 1;
+  for (int64_t off = 0; off < B; off += pass) {
+    const int64_t n = std::min(pass, B - off);
+    float* tok = tokens_dev ? tokens_dev + off * tok_elems : tok_ws;
+    const float* x = poses_dev + off * pose_elems;
+    rc = precision == SF_PREC_BF16 ? launch_tokenizer_bf16(m, x, n, T, tok, st) : launch_tokenizer_fp32(m, x, n, T, tok, ws, ws_left, st);
+    if (rc) return rc;
+    float* rec = recon_dev ? recon_dev + off * tok_elems : nullptr;
+    float* sc = scores_dev + off * score_stride;
+    rc = precision == SF_PREC_BF16 ? launch_transformer_bf16(m, tok, n, S, reduction, rec, sc, st)
+                                   : launch_transformer_fp32(m, tok, n, S, reduction, rec, sc, st);
+    if (rc) return rc;
+  }
+  return SF_OK;
 }
 
 // ------------------------------------------------------------------------------------ runner

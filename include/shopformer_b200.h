@@ -95,7 +95,8 @@ int sf_model_create(const sf_config* cfg, int32_t n_tensors, const char* const* 
 void sf_model_destroy(sf_model* m);
 /* Token count S and token width D for windows of T frames (conv length (T-1)/s+1 per block). */
 int sf_model_token_shape(const sf_model* m, int32_t T, int32_t* S, int32_t* D);
-/* Bytes of device workspace the calls below need for a batch of B windows of T frames. */
+/* Bytes of device workspace the calls below need for a batch of B windows of T frames.
+ * Bounded: batches beyond 131,072 windows are processed in internal passes of that size. */
 int64_t sf_workspace_bytes(const sf_model* m, int64_t B, int32_t T);
 
 /* ------------------------------------------------------------------ hot path ------ */

@@ -12,6 +12,7 @@ import torch
 import oracle.scoring_oracle as O
 from helpers import build_model, max_abs_rel, oracle_kwargs, rel_err
 from shopformer_b200 import configs as CFG
+from shopformer_b200 import native as N
 from shopformer_b200.native import NativeError
 from shopformer_b200.synthetic import synth_state_dict, synth_windows
 
@@ -176,6 +177,23 @@ def test_full_size_properties(dropin1, dropin2):
     ref = O.score_windows({k: v.cpu() for k, v in model.state_dict().items()}, torch.from_numpy(xs[sub]),
                           dtype=torch.float64, **oracle_kwargs(model, "A"))
     assert rel_err(s.cpu().numpy()[sub], ref["score"].numpy()) < FP32_TOL
+
+
+def test_score_windows_multi_pass(dropin1, dropin2):
+    """Batches beyond 131,072 windows are scored in internal passes with a bounded workspace: same scores per window."""
+    model = build_model(dropin1, dropin2, "A").cuda()
+    eng = model._sf_engine()
+    xs, _ = synth_windows(4096, 24, 17, seed=7)
+    base = torch.from_numpy(xs).cuda()
+    n = 131072 + 777
+    idx = torch.arange(n, device="cuda") % 4096
+    x = base[idx].contiguous()
+    for prec in ("bf16", "fp32"):
+        ref = eng.score_windows(base, precision=prec)
+        got = eng.score_windows(x, precision=prec)
+        assert got.shape == (n,)
+        assert torch.equal(got, ref[idx]), prec
+    assert N.load().sf_workspace_bytes(eng._h, n, 24) == N.load().sf_workspace_bytes(eng._h, 131072, 24)
 
 
 def test_errors_are_loud(dropin1, dropin2):
