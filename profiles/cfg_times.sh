@@ -1,2 +1,1 @@
 for c in A A1 B C; do echo -n "$c: "; python profiles/kernel_times.py $c | tail -1; done
-
