@@ -42,7 +42,7 @@ constexpr uint16_t kGap = 0xFFFF;
 struct BfBlk {
   int cin, kin, npad, cout;            // real / padded input channels, padded / real output channels
   int stride, Tin, Tout, gap, slot;    // slot = Tout + gap time rows per window in a phase buffer
-  int rows, mrows, rtot;               // rows per phase, M-space rows (G*slot*V), total rows (stride*rows)
+  int rows, mrows, rtot;               // rows between phase starts, M-space rows (G*slot*V), total rows of the buffer
   int n_taps;
   int tap_k[kTaps], tap_phase[kTaps], tap_rowoff[kTaps];
   int tap_arel[kTaps], tap_wrel[kTaps];   // per tap: A-view row offset and weight-slab offset, both in 16-byte units
@@ -645,8 +645,10 @@ bool build_plan(const sf_model* m, int T, int G, BfPlan* pl, const char** why) {
     }
     b.slot = b.Tout + b.gap;
     b.mrows = G * b.slot * V;
-    b.rows = b.gap * V + b.mrows;
-    b.rtot = b.stride * b.rows;
+    // phase p = [gap frames][G window slots]; with one window per group the trailing gap of a phase is the leading gap
+    // of the next one (shared), and one more gap closes the buffer
+    b.rows = G == 1 ? (b.gap + b.Tout) * V : b.gap * V + b.mrows;
+    b.rtot = G == 1 ? b.stride * b.rows + b.gap * V : b.stride * b.rows;
     for (int tp = 0; tp < b.n_taps; ++tp) b.tap_arel[tp] = b.tap_phase[tp] * b.rows + b.gap * V + b.tap_rowoff[tp];
     if (b.rtot > 2047) { *why = "operand buffer longer than 2047 rows"; return false; }
     b.identity_res = tb.identity_res;
