@@ -22,6 +22,7 @@
 // One CTA owns G windows at a time (persistent); phases are separated by mbarrier (MMA completion) and
 // __syncthreads; two CTAs per SM overlap one CTA's MMAs with the other's CUDA-core phases.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 #include "sf_internal.h"
@@ -34,6 +35,7 @@ namespace {
 
 using namespace tc;
 
+constexpr int kMaxOcc = 3;            // CTAs per SM the register budget allows (3 x 256 threads x 80 registers)
 constexpr int kThreadsMin = 256;      // 2 CTAs/SM shapes; shapes that only fit one CTA per SM run 512 threads
 constexpr int kIssuers = 4;          // lane 0 of warps 0..3 issue the MMAs of tiles t = warp (mod 4)
 constexpr int kEllMax = 8;
@@ -57,10 +59,11 @@ struct BfBlk {
 
 struct BfPlan {
   int n_blocks, V, c_in, G, T0, S_out, c_last;
+  int bstride, ell_stride;             // floats per block in the bias tables (widest npad), ELL entries per keypoint row kept
   const float *in_scale, *in_shift;
   BfBlk blk[kMaxBlocks];
-  uint32_t off_A, off_X0, off_X1, off_WT, off_WG, off_x0, off_x0b, off_w0img;
-  uint32_t off_xrtab, off_xjtab, off_bias_g, off_bias_o, off_r0, off_ellv, off_scale, off_shift;
+  uint32_t off_A, off_X0, off_X1, off_WG, off_x0, off_w0img;
+  uint32_t off_xjtab, off_bias_g, off_bias_o, off_r0, off_ellv, off_scale, off_shift;
   uint32_t smem_bytes, tmem_cols;
 };
 static_assert(sizeof(BfPlan) <= 3900, "BfPlan must fit in kernel parameter space");
@@ -190,18 +193,16 @@ __device__ __forceinline__ void conv_issue(uint32_t d, uint32_t a_lo0, uint32_t 
   } while (0)
 
 template <int kThreads>
-__global__ void __launch_bounds__(kThreads, kThreads == 256 ? 2 : 1)
+__global__ void __launch_bounds__(kThreads, kThreads == 256 ? kMaxOcc : 1)
 tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict__ poses, float* __restrict__ tokens,
                       int64_t B) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ uint64_t bar, wbar, pbar[2];     // MMA completion; TMA: weights of a block, poses of a window group (2 buffers)
+  __shared__ uint64_t bar, wbar, pbar;        // MMA completion; TMA: weights of a block, poses of a window group
   __shared__ uint32_t tmem_base_s;
   unsigned char* sA = smem + pl.off_A;
   unsigned char* sX[2] = {smem + pl.off_X0, smem + pl.off_X1};
-  unsigned char* sWT = smem + pl.off_WT;
   unsigned char* sWG = smem + pl.off_WG;
-  float* xbuf[2] = {reinterpret_cast<float*>(smem + pl.off_x0), reinterpret_cast<float*>(smem + pl.off_x0b)};
-  const uint16_t* xrtab = reinterpret_cast<const uint16_t*>(smem + pl.off_xrtab);   // block-0 residual source per M row
+  float* x0 = reinterpret_cast<float*>(smem + pl.off_x0);      // raw poses of the current window group (fp32)
   const uint8_t* xjtab = reinterpret_cast<const uint8_t*>(smem + pl.off_xjtab);     // c*V+v of every x0 element
   const float* bias_g = reinterpret_cast<const float*>(smem + pl.off_bias_g);       // [blk][64]
   const float* bias_o = reinterpret_cast<const float*>(smem + pl.off_bias_o);
@@ -222,8 +223,7 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
   if (threadIdx.x == 0) {
     mbar_init(&bar, kIssuers);
     mbar_init(&wbar, 1);
-    mbar_init(&pbar[0], 1);
-    mbar_init(&pbar[1], 1);
+    mbar_init(&pbar, 1);
     fence_mbar_init();
   }
   for (int bi = 0; bi < pl.n_blocks; ++bi) {
@@ -257,18 +257,17 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
           target = t * (pl.c_last * V) + v;                                   // offset inside the window's tokens
         }
         e = (uint16_t)(target | (w << 11));
-        if (bi == 0) reinterpret_cast<uint16_t*>(smem + pl.off_xrtab)[mrow] = (uint16_t)(w * per_w + (b.stride * t) * V + v);
       }
       mt[mrow] = e;
     }
-    float* bg = reinterpret_cast<float*>(smem + pl.off_bias_g) + bi * 64;
-    float* bo = reinterpret_cast<float*>(smem + pl.off_bias_o) + bi * 64;
-    for (int i = threadIdx.x; i < 64; i += kThreads) {
+    float* bg = reinterpret_cast<float*>(smem + pl.off_bias_g) + bi * pl.bstride;
+    float* bo = reinterpret_cast<float*>(smem + pl.off_bias_o) + bi * pl.bstride;
+    for (int i = threadIdx.x; i < pl.bstride; i += kThreads) {
       bg[i] = i < b.npad ? __ldg(b.gcn_b + i) : 0.f;
       bo[i] = i < b.npad ? __ldg(b.out_b + i) : 0.f;
     }
-    float2* e2 = reinterpret_cast<float2*>(smem + pl.off_ellv) + bi * V * kEllMax;
-    for (int i = threadIdx.x; i < V * kEllMax; i += kThreads) {
+    float2* e2 = reinterpret_cast<float2*>(smem + pl.off_ellv) + bi * V * pl.ell_stride;
+    for (int i = threadIdx.x; i < V * pl.ell_stride; i += kThreads) {
       const int k = i / V, v = i % V;                    // [k][v]: a warp's lanes read consecutive entries
       const bool ok = k < b.ell_width;
       const float val = ok ? __ldg(b.ell_val + v * b.ell_width + k) : 0.f;
@@ -278,7 +277,7 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
   }
   {
     const BfBlk& b0 = pl.blk[0];
-    for (int i = threadIdx.x; i < 4 * 64; i += kThreads) {
+    for (int i = threadIdx.x; i < pl.c_in * 64; i += kThreads) {
       const int ci = i >> 6, c = i & 63;
       const bool ok = ci < b0.cin && c < b0.cout;
       reinterpret_cast<float*>(smem + pl.off_r0)[i] = ok ? __ldg(b0.res_w32 + ci * b0.cout + c) : 0.f;
@@ -317,34 +316,31 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
 
   const int64_t n_groups = (B + G - 1) / G;
   // raw poses of a window group are fetched by TMA one iteration ahead (one bulk copy, issued by thread 0)
-  auto prefetch = [&](int64_t g_idx, int buf) {
+  auto prefetch = [&](int64_t g_idx) {
     if (g_idx >= n_groups || threadIdx.x != 0) return;
     const int64_t wf = g_idx * G;
     const uint32_t bytes = (uint32_t)((B - wf) < (int64_t)G ? (B - wf) : (int64_t)G) * (uint32_t)per_w * 4u;
-    mbar_expect_tx(&pbar[buf], bytes);
-    tma_load_1d(xbuf[buf], poses + (size_t)wf * per_w, bytes, &pbar[buf]);
+    mbar_expect_tx(&pbar, bytes);
+    tma_load_1d(x0, poses + (size_t)wf * per_w, bytes, &pbar);
   };
-  int xcur = 0;
-  uint32_t wpar = 0, ppar = 0;                          // phase parities: weights barrier, pose barriers (bit per buffer)
-  prefetch(blockIdx.x, 0);
+  uint32_t wpar = 0, ppar = 0;                          // phase parities: weights barrier, pose barrier
+  prefetch(blockIdx.x);
   for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
     const int64_t w_first = grp * G;
     const int nw = (int)((B - w_first) < (int64_t)G ? (B - w_first) : (int64_t)G);
-    float* x0 = xbuf[xcur];
     TOK_STAMP(100);
 
     // =============================== block 0 prologue ===============================
     {
       const BfBlk& b = pl.blk[0];
-      if (warp == 0) mbar_wait(&pbar[xcur], (ppar >> xcur) & 1u);      // this group's poses (fetched during the previous group)
-      ppar ^= 1u << xcur;
+      if (warp == 0) mbar_wait(&pbar, ppar);             // this group's poses (requested after the previous group's block 0)
+      ppar ^= 1u;
       __syncthreads();
-      if (threadIdx.x == 0) {                            // temporal-conv weights of block 0: one bulk copy
+      if (threadIdx.x == 0) {                            // temporal-conv weights of block 0 into x1's (still unused) buffer
         const uint32_t bytes = (uint32_t)(kTaps * b.npad * b.npad * 2);
         mbar_expect_tx(&wbar, bytes);
-        tma_load_1d(sWT, b.w_tcn, bytes, &wbar);
+        tma_load_1d(sX[0], b.w_tcn, bytes, &wbar);
       }
-      prefetch(grp + gridDim.x, xcur ^ 1);
       const int n_valid = nw * per_w;
       for (int i = threadIdx.x; i < G * per_w; i += kThreads) {
         const int j = xjtab[i];
@@ -352,18 +348,18 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
       }
       __syncthreads();
       TOK_STAMP(101);
-      // A0 <- split(A_hat . x0): K = 16 operand rows of the phase-split layout (x1's buffer, free until the conv epilogue)
+      // A0 <- split(A_hat . x0): K = 16 operand rows of the phase-split layout, in the A buffer (g0 later overwrites it)
       const uint16_t* rt0 = reinterpret_cast<const uint16_t*>(smem + b.off_rowtab);
-      if (b.ell_width <= 5) mix_a0<5>(x0, sX[0], (uint32_t)b.rtot * 16u, rt0, ell2, V, b.cin, pl.T0 * V, per_w, nw, b.rtot);
-      else mix_a0<kEllMax>(x0, sX[0], (uint32_t)b.rtot * 16u, rt0, ell2, V, b.cin, pl.T0 * V, per_w, nw, b.rtot);
+      if (b.ell_width <= 5) mix_a0<5>(x0, sA, (uint32_t)b.rtot * 16u, rt0, ell2, V, b.cin, pl.T0 * V, per_w, nw, b.rtot);
+      else mix_a0<kEllMax>(x0, sA, (uint32_t)b.rtot * 16u, rt0, ell2, V, b.cin, pl.T0 * V, per_w, nw, b.rtot);
       TOK_STAMP(102);
-      xcur ^= 1;
     }
 
     for (int bi = 0; bi < pl.n_blocks; ++bi) {
       const BfBlk& b = pl.blk[bi];
       unsigned char* sXin = sX[(bi + 1) & 1];      // x_b   (b >= 1)
       unsigned char* sXout = sX[bi & 1];           // x_{b+1}
+      unsigned char* sWT = sXout;                  // ... which holds this block's conv weights until the conv epilogue
       const uint32_t planeA = (uint32_t)b.rtot * 16u;
       const int dcol = b.npad < 32 ? 32 : b.npad;   // TMEM column stride between accumulator tiles
       const uint16_t* rt = reinterpret_cast<const uint16_t*>(smem + b.off_rowtab);
@@ -381,17 +377,16 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
           const uint32_t br = b.w_res ? bg : 0u;
           mbar_expect_tx(&wbar, bg + bt + br);
           tma_load_1d(sWG, b.w_gcn, bg, &wbar);
-          tma_load_1d(sWT, b.w_tcn, bt, &wbar);
+          tma_load_1d(sWT, b.w_tcn, bt, &wbar);           // (sWT = x_{b+1}'s buffer)
           if (br) tma_load_1d(sWT + bt, b.w_res, br, &wbar);
         }
-        if (bi + 1 < pl.n_blocks) zero_fill(sXout, pl.blk[bi + 1].rtot * pl.blk[bi + 1].kin * 2);
         {
           const int chunks = b.kin >> 3;
           const int tpc = kThreads / chunks;
           const int j = threadIdx.x / tpc;
           const unsigned char* plane = sXin + (size_t)j * planeA;
           unsigned char* dstp = sA + (size_t)j * planeA;
-          const float2* el = ell2 + bi * V * kEllMax;
+          const float2* el = ell2 + bi * V * pl.ell_stride;
           if (b.ell_width <= 5) mix_rows<5>(plane, dstp, rt, el, V, threadIdx.x - j * tpc, tpc, b.rtot);
           else mix_rows<kEllMax>(plane, dstp, rt, el, V, threadIdx.x - j * tpc, tpc, b.rtot);
         }
@@ -413,7 +408,7 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
           const uint32_t idesc = make_idesc(128, b.npad, false);
           const uint32_t w_plane = (uint32_t)b.npad * 16u;
           const uint32_t blo0 = desc_lo(smem_u32(bi == 0 ? w0img : sWG), w_plane);
-          const uint32_t a0 = smem_u32(bi == 0 ? sX[0] : sA);
+          const uint32_t a0 = smem_u32(sA);
           const int ksp = bi == 0 ? 1 : b.kin >> 4;
           if (elect_one()) {
             for (int tile = warp; tile < p_tiles; tile += kIssuers) {
@@ -433,9 +428,8 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
         parity ^= 1;
         tc_fence_after();
         TOK_STAMP(113 + bi * 10);
-        if (bi == 0 && pl.n_blocks > 1) zero_fill(sX[0], pl.blk[1].rtot * pl.blk[1].kin * 2);    // A0 is dead: clear x1
         // ---- g = relu(P + b) -> bf16 over M in place (gap rows -> 0)
-        const float* bgp = bias_g + bi * 64;
+        const float* bgp = bias_g + bi * pl.bstride;
         for (int gq = g_first; gq < groups; gq += g_step) {
           float4 bb[4];
 #pragma unroll
@@ -524,7 +518,17 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
       TOK_STAMP(116 + bi * 10);
       // ---- x_{b+1} = relu(acc + bias + residual): bf16 into the next block's phase layout, or fp32 tokens
       const bool last = bi + 1 == pl.n_blocks;
-      const float* bop = bias_o + bi * 64;
+      if (!last) {
+        // the conv weights that lived in x_{b+1}'s buffer are dead: zero its gap rows (the data rows are all written below)
+        const BfBlk& nx = pl.blk[bi + 1];
+        const uint16_t* rtn = reinterpret_cast<const uint16_t*>(smem + nx.off_rowtab);
+        const int planes_n = nx.kin >> 3;
+        for (int r = threadIdx.x; r < nx.rtot; r += kThreads)
+          if (rtn[r] == kGap)
+            for (int j = 0; j < planes_n; ++j)
+              *reinterpret_cast<uint4*>(sXout + ((size_t)j * nx.rtot + r) * 16) = make_uint4(0, 0, 0, 0);
+      }
+      const float* bop = bias_o + bi * pl.bstride;
       const int nxt_rtot = last ? 0 : pl.blk[bi + 1].rtot;
       const int tv = pl.T0 * V;
       for (int gq = g_first; gq < groups; gq += g_step) {
@@ -547,7 +551,9 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
             }
             if (bi == 0) {
               // K = Cin (2) residual conv on CUDA cores in fp32 from the un-mixed input
-              const float* xp = x0 + xrtab[mrow];
+              // raw-pose element of this output row: window w, frame stride * t', keypoint v  (mrow = w*slot*V + t'*V + v)
+              const int q0 = mrow - w * b.slot * V, t0r = q0 / V;
+              const float* xp = x0 + w * per_w + (b.stride * t0r) * V + (q0 - t0r * V);
 #pragma unroll
               for (int ci = 0; ci < 4; ++ci)
                 if (ci < b.cin) {
@@ -584,9 +590,11 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
           }
         }
       }
+      fence_proxy_async();                            // x_{b+1} (generic stores) before later TMA / MMA accesses of these buffers
       tc_fence_before();
       __syncthreads();
       TOK_STAMP(117 + bi * 10);
+      if (bi == 0) prefetch(grp + gridDim.x);         // the raw poses are dead: fetch the next group's
     }
   }
   tc_fence_before();
@@ -611,7 +619,7 @@ bool build_plan(const sf_model* m, int T, int G, BfPlan* pl, const char** why) {
   pl->in_scale = tk.in_scale;
   pl->in_shift = tk.in_shift;
   int Tin = T;
-  size_t maxA = 0, maxX[2] = {0, 0}, maxWT = 0, maxWG = 0;
+  size_t maxWG = 0;
   int max_cols = 0;
   for (int i = 0; i < nb; ++i) {
     const TokBlock& tb = tk.blk[i];
@@ -663,10 +671,6 @@ bool build_plan(const sf_model* m, int T, int G, BfPlan* pl, const char** why) {
     b.gcn_w32 = tb.gcn_w;
     b.res_w32 = tb.res_w;
     if (i == 0 && tb.identity_res) { *why = "identity residual in block 0"; return false; }
-    maxA = std::max(maxA, (size_t)b.rtot * std::max(b.npad, i > 0 ? b.kin : 0) * 2);
-    if (i > 0) maxX[(i + 1) & 1] = std::max(maxX[(i + 1) & 1], (size_t)b.rtot * b.kin * 2);
-    else maxX[0] = std::max(maxX[0], (size_t)b.rtot * 16 * 2);      // block 0: split K = 16 operand A0
-    maxWT = std::max(maxWT, (size_t)kTaps * b.npad * b.npad * 2 + (size_t)(w.res ? b.kin * b.npad * 2 : 0));
     if (i > 0) maxWG = std::max(maxWG, (size_t)b.kin * b.npad * 2);
     const int tiles = std::max((b.mrows + 127) / 128, (b.rtot + 127) / 128);
     max_cols = std::max(max_cols, tiles * std::max(b.npad, 32));
@@ -684,30 +688,50 @@ bool build_plan(const sf_model* m, int T, int G, BfPlan* pl, const char** why) {
   // only ever reads the bytes of the next region, never past the allocation.
   // x2 (X1) is first written by block 1's epilogue, when the A buffer only holds M_b / g_b of blocks >= 1:
   // it lives in the tail of the A region that only g0 needs.
-  size_t maxA_late = 0;
-  for (int i = 1; i < nb; ++i) maxA_late = std::max(maxA_late, (size_t)pl->blk[i].rtot * std::max(pl->blk[i].npad, pl->blk[i].kin) * 2);
+  // Shared-memory plan (three CTAs per SM for the default shapes):
+  //   A   : block 0's split operand A0, then g0 in place; blocks >= 1: M_b / g_b in its first `A_late` bytes and the
+  //         odd x buffer X1 in the tail that only g0 needs;
+  //   X0/X1: x_{b+1} of even / odd blocks.  x_{b+1}'s buffer is dead until block b's conv epilogue writes it, so it
+  //         first holds block b's temporal-conv (+ residual) weight images: W_b lands there by TMA, the conv MMAs read
+  //         it, then the epilogue zeroes the gap rows and writes the data rows over it.
+  size_t maxA_late = 0, need_x[2] = {16, 16};
+  for (int i = 0; i < nb; ++i) {
+    const BfBlk& bb = pl->blk[i];
+    if (i > 0) {
+      maxA_late = std::max(maxA_late, (size_t)bb.rtot * std::max(bb.npad, bb.kin) * 2);
+      need_x[(i + 1) & 1] = std::max(need_x[(i + 1) & 1], (size_t)bb.rtot * bb.kin * 2);          // x_i = input of block i
+    }
+    const size_t wb = (size_t)kTaps * bb.npad * bb.npad * 2 + (size_t)(bb.w_res ? bb.kin * bb.npad * 2 : 0);
+    need_x[i & 1] = std::max(need_x[i & 1], wb);                                                    // W_i in x_{i+1}'s buffer
+  }
+  const size_t a0_bytes = (size_t)pl->blk[0].rtot * 16 * 2, g0_bytes = (size_t)pl->blk[0].rtot * pl->blk[0].npad * 2;
   const size_t xbytes = (size_t)G * tk.c_in * T * V * sizeof(float);
   if (xbytes % 16) { *why = "window size not a multiple of 16 bytes"; return false; }
   uint32_t off = 0;
   pl->off_A = off;
   pl->off_X1 = off + up(maxA_late);
-  off += std::max(up(maxA), up(maxA_late) + up(std::max(maxX[1], (size_t)16)));
-  pl->off_X0 = off; off += up(std::max(std::max(maxX[0], (size_t)16), xbytes));
-  pl->off_WT = off; off += up(maxWT);
+  off += std::max(up(std::max(a0_bytes, g0_bytes)), up(maxA_late) + up(need_x[1]));
+  pl->off_X0 = off; off += up(need_x[0]);
   pl->off_WG = off; off += up(std::max(maxWG, (size_t)16));
   pl->off_x0 = off; off += up(xbytes);
-  pl->off_x0b = off; off += up(xbytes);
   for (int i = 0; i < nb; ++i) {
     pl->blk[i].off_rowtab = off; off += up((size_t)pl->blk[i].rtot * 2);
     pl->blk[i].off_mtab = off; off += up((size_t)pl->blk[i].mrows * 2);
   }
-  pl->off_xrtab = off; off += up((size_t)pl->blk[0].mrows * 2);
   pl->off_xjtab = off; off += up((size_t)G * tk.c_in * T * V);
-  pl->off_bias_g = off; off += up((size_t)nb * 64 * 4);
-  pl->off_bias_o = off; off += up((size_t)nb * 64 * 4);
+  pl->bstride = 16;
+  pl->ell_stride = 1;
+  for (int i = 0; i < nb; ++i) {
+    pl->bstride = std::max(pl->bstride, pl->blk[i].npad);
+    pl->ell_stride = std::max(pl->ell_stride, pl->blk[i].ell_width);
+  }
+  if (pl->ell_stride > 5) pl->ell_stride = kEllMax;      // the mix templates read 5 or 8 entries per row
+  else pl->ell_stride = 5;
+  pl->off_bias_g = off; off += up((size_t)nb * pl->bstride * 4);
+  pl->off_bias_o = off; off += up((size_t)nb * pl->bstride * 4);
   pl->off_w0img = off; off += up((size_t)2 * pl->blk[0].npad * 16);
-  pl->off_r0 = off; off += up(4 * 64 * 4);
-  pl->off_ellv = off; off += up((size_t)nb * V * kEllMax * 8);
+  pl->off_r0 = off; off += up((size_t)tk.c_in * 64 * 4);
+  pl->off_ellv = off; off += up((size_t)nb * V * pl->ell_stride * 8);
   pl->off_scale = off; off += up((size_t)tk.c_in * V * 4);
   pl->off_shift = off; off += up((size_t)tk.c_in * V * 4);
   pl->smem_bytes = off;
@@ -734,10 +758,11 @@ int launch_tokenizer_bf16(const sf_model* m, const float* poses, int64_t B, int 
   int smem_per_sm = 0;
   SF_CUDA_OK(cudaDeviceGetAttribute(&smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, m->device));
   int occ = smem_per_sm / (int)(pl.smem_bytes + 1024 + 256);
-  occ = std::max(1, std::min(std::min(occ, 2), (int)(512 / pl.tmem_cols)));
+  occ = std::max(1, std::min(std::min(occ, kMaxOcc), (int)(512 / pl.tmem_cols)));
   if (const char* dbg = getenv("SF_TOK_OCC")) occ = std::max(1, std::min(occ, atoi(dbg)));     // debugging aid
   const int64_t n_groups = (B + pl.G - 1) / pl.G;
   const int grid = (int)std::min<int64_t>(n_groups, (int64_t)m->sm_count * occ);
+  if (getenv("SF_TOK_DEBUG")) fprintf(stderr, "tokenizer_bf16: smem %u B, tmem %u cols, %d CTAs/SM, grid %d\n", pl.smem_bytes, pl.tmem_cols, occ, grid);
   // two CTAs per SM run 256 threads each; a shape that only fits one CTA per SM gets 512 threads so that the
   // CUDA-core phases still have 16 warps per SM to hide latency with
   auto launch = [&](auto kernel, int threads) -> int {
