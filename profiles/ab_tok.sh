@@ -4,7 +4,7 @@ L=computer-vision-shoplifting-detection_b200/shopformer_b200/libshopformer_b200.
 cp $L ab/libCand.so
 for v in A Cand; do
   cp ab/lib$v.so $L
-  for occ in 1 2; do
+  for occ in 2 3; do
     echo -n "build $v occ $occ: "; SF_TOK_OCC=$occ python profiles/kernel_times.py | tail -1
   done
 done
