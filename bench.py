@@ -318,7 +318,8 @@ def main():
     chunk = 16384
     xs_pinned = torch.from_numpy(xs).pin_memory()
     xs = xs_pinned.numpy()
-    eng.score_host(xs[:chunk * 2], precision=a.precision, chunk=chunk)      # allocate runner, warm up
+    eng.score_host(xs, precision=a.precision, chunk=chunk)      # allocate the runner and touch every page once (the first device
+    eng.score_host(xs, precision=a.precision, chunk=chunk)      # read of a freshly pinned buffer pays a one-time mapping cost)
     barrier()
     e2e_steps = max(3, min(a.steps, 10))
     t0 = time.perf_counter()
@@ -405,7 +406,7 @@ def main():
                           f"inputs ({xs.nbytes / 1e6:.0f} MB) + tokens smaller than the 126 MB L2: not a headline configuration"),
                    "collective": "NCCL all-gather of fp32 scores" if world > 1 else "none (1 GPU)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "api": "sf_runner_score (C ABI, host buffers, <=16384-window whole-wave chunks, copy + compute stream, 4-slot ring)", "steps": e2e_steps},
+                "api": "sf_runner_score (C ABI, host buffers): the page-locked pose buffer is read in place by the tokenizer's TMA over PCIe (h2d bytes moved by the kernel), scores copied back; pageable sources go through a 4-slot pinned ring", "steps": e2e_steps},
         "gpu_launches": 2 * a.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         "parity": {"max_rel_err_vs_cpu_oracle": err, "checked_windows": 256, "tolerance": 1e-3 if a.precision == "fp32" else 1e-2},
         "other_precision": other_line,

@@ -118,6 +118,11 @@ struct sf_runner {
   float* dev_out[kRing];
   void* ws;
   int64_t ws_bytes;
+  // page-locked sources are scored in place (see sf_runner_score): full-batch score buffer + workspace, grown on demand
+  float* big_out;
+  int64_t big_out_cap;
+  void* big_ws;
+  int64_t big_ws_bytes;
 };
 
 extern "C" int sf_runner_create(const sf_model* m, int32_t T, int64_t max_chunk, sf_runner** out) {
@@ -171,6 +176,8 @@ extern "C" void sf_runner_destroy(sf_runner* r) {
     if (r->computed[i]) cudaEventDestroy(r->computed[i]);
   }
   if (r->ws) cudaFree(r->ws);
+  if (r->big_out) cudaFree(r->big_out);
+  if (r->big_ws) cudaFree(r->big_ws);
   if (r->copy_st) cudaStreamDestroy(r->copy_st);
   if (r->comp_st) cudaStreamDestroy(r->comp_st);
   delete r;
@@ -191,6 +198,36 @@ extern "C" int sf_runner_score(sf_runner* r, const float* poses_host, int64_t B,
     cudaPointerAttributes attr;
     if (cudaPointerGetAttributes(&attr, poses_host) == cudaSuccess) src_pinned = attr.type == cudaMemoryTypeHost;
     else cudaGetLastError();
+  }
+  if (src_pinned) {
+    // Page-locked source: no staging copy at all.  The tokenizer's TMA (the precise path: its global loads) reads each
+    // window straight out of host memory over PCIe one window ahead of use, so the whole batch is ONE pass of the two
+    // kernels; only the scores come back.  (h2d bytes per call are the same B * window bytes, moved by the kernel.)
+    const float* dptr = nullptr;
+    if (cudaHostGetDevicePointer((void**)&dptr, (void*)poses_host, 0) == cudaSuccess && dptr) {
+      const int64_t need_ws = sf_workspace_bytes(r->m, B, r->T);
+      if (need_ws > r->big_ws_bytes) {
+        if (r->big_ws) cudaFree(r->big_ws);
+        r->big_ws = nullptr;
+        r->big_ws_bytes = 0;
+        SF_CUDA_OK(cudaMalloc(&r->big_ws, (size_t)need_ws));
+        r->big_ws_bytes = need_ws;
+      }
+      if (B > r->big_out_cap) {
+        if (r->big_out) cudaFree(r->big_out);
+        r->big_out = nullptr;
+        r->big_out_cap = 0;
+        SF_CUDA_OK(cudaMalloc((void**)&r->big_out, (size_t)B * sizeof(float)));
+        r->big_out_cap = B;
+      }
+      int rc = sf_score_windows(r->m, dptr, B, r->T, SF_REDUCE_MEAN, precision, r->big_out, nullptr, nullptr, r->big_ws,
+                                r->big_ws_bytes, r->comp_st);
+      if (rc) return rc;
+      SF_CUDA_OK(cudaMemcpyAsync(scores_host, r->big_out, (size_t)B * sizeof(float), cudaMemcpyDeviceToHost, r->comp_st));
+      SF_CUDA_OK(cudaStreamSynchronize(r->comp_st));
+      return SF_OK;
+    }
+    cudaGetLastError();        // not mappable: fall through to the staged pipeline
   }
   int64_t off = 0;
   for (int64_t c = 0; off < B; ++c) {

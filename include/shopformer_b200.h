@@ -196,7 +196,9 @@ int sf_normalize_windows(const float* raw_dev, int64_t B, int32_t T, int32_t K, 
  * waves of the transformer grid when `max_chunk` allows). */
 int sf_runner_create(const sf_model* m, int32_t T, int64_t max_chunk, sf_runner** out);
 void sf_runner_destroy(sf_runner* r);
-/* Blocking: returns after `scores_host[0..B)` is written.  `poses_host` need not be pinned. */
+/* Blocking: returns after `scores_host[0..B)` is written.  `poses_host` need not be pinned: a pageable
+ * buffer is staged through the runner's pinned ring; a page-locked one (cudaHostAlloc / cudaHostRegister /
+ * torch pinned memory) is read in place by the kernels over PCIe, with no staging copy. */
 int sf_runner_score(sf_runner* r, const float* poses_host, int64_t B, int32_t precision,
                     float* scores_host);
 /* Pinned staging buffer of the runner (capacity one chunk of windows, slots 0..3) so that

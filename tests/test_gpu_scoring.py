@@ -196,6 +196,20 @@ def test_score_windows_multi_pass(dropin1, dropin2):
     assert N.load().sf_workspace_bytes(eng._h, n, 24) == N.load().sf_workspace_bytes(eng._h, 131072, 24)
 
 
+def test_runner_reads_pinned_sources_in_place(dropin1, dropin2):
+    """Page-locked host buffers are scored without a staging copy (the kernels read them over PCIe); pageable ones go
+    through the pinned ring.  Same scores either way, equal to the device-resident call."""
+    model = build_model(dropin1, dropin2, "A").cuda()
+    eng = model._sf_engine()
+    n = 20011
+    xs, _ = synth_windows(n, 24, 17, seed=99)
+    pinned = torch.from_numpy(xs).pin_memory()
+    for prec in ("bf16", "fp32"):
+        ref = eng.score_windows(torch.from_numpy(xs).cuda(), precision=prec).cpu().numpy()
+        assert np.array_equal(eng.score_host(pinned.numpy(), precision=prec), ref), prec      # in place
+        assert np.array_equal(eng.score_host(xs, precision=prec, chunk=4096), ref), prec         # staged ring
+
+
 def test_errors_are_loud(dropin1, dropin2):
     model = build_model(dropin1, dropin2, "A").cuda()
     with torch.no_grad():
