@@ -11,16 +11,20 @@
 //     taps that can only ever hit padding are skipped;
 //   * the BN-folded 1x1 strided residual conv is two more MMAs into the same accumulator (phase 0 of x);
 //   * graph conv = adjacency mix over keypoints on CUDA cores (bf16 rows in smem, fp32 accumulate)
-//     followed by a [rows x Cin] x [Cin x Cout] tensor-core GEMM; block 0 (Cin = 2) is rebuilt on CUDA
-//     cores in fp32 with its weights held in registers;
+//     followed by a [rows x Cin] x [Cin x Cout] tensor-core GEMM; block 0 (Cin = 2 raw coordinates) feeds the
+//     same GEMM with a K = 16 operand that carries the mixed poses split into bf16 hi + lo against split
+//     weights, so its inputs are not rounded to bf16;
 //   * epilogues read TMEM with tcgen05.ld, add the folded bias, ReLU, and write the next operand
 //     straight back to shared memory as bf16 -- nothing but the final tokens (fp32) goes to HBM;
-//   * every row -> (window, time, keypoint) decode is a shared-memory table built once per CTA, biases
-//     and the block-0 weights are staged once per CTA, MMA issue is spread over four warps;
-//   * per-block weight images and the next window's poses arrive by TMA (cp.async.bulk, mbarrier complete_tx).
+//   * every row -> (window, time, keypoint) decode is a shared-memory table built once per CTA, MMA issue is
+//     spread over four warps;
+//   * per-block weight images and the next window's poses arrive by TMA (cp.async.bulk, mbarrier complete_tx);
+//     block b's temporal-conv weights land in x_{b+1}'s buffer, which is dead until block b's epilogue.
 //
-// One CTA owns G windows at a time (persistent); phases are separated by mbarrier (MMA completion) and
-// __syncthreads; two CTAs per SM overlap one CTA's MMAs with the other's CUDA-core phases.
+// One CTA owns one window at a time (persistent).  A window is a chain of 13 dependent phases separated by
+// mbarrier waits (MMA completion) and __syncthreads, so SM throughput is the number of chains running side by
+// side: the shared-memory plan (build_plan) fits THREE CTAs per SM for hidden 32 (76.5 KB, 128 TMEM columns,
+// 80 registers x 256 threads each); shapes that only fit one CTA per SM run a 512-thread instantiation.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -435,11 +439,11 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) bb[q4] = *reinterpret_cast<const float4*>(bgp + gq * 16 + q4 * 4);
           for (int t0 = t_first; t0 < p_tiles; t0 += t_step) {
-          float acc[16];
-          tmem_ld16(tmem + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(t0 * dcol + gq * 16), acc);
-          tmem_ld_wait();
-          const int r = t0 * 128 + lane_grp * 32 + lane;
-          if (r < b.rtot) {
+            float acc[16];
+            tmem_ld16(tmem + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(t0 * dcol + gq * 16), acc);
+            tmem_ld_wait();
+            const int r = t0 * 128 + lane_grp * 32 + lane;
+            if (r >= b.rtot) continue;
             const bool data = rt[r] != kGap;
             float y[16];
 #pragma unroll
@@ -451,7 +455,6 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
             }
             *reinterpret_cast<uint4*>(sA + ((size_t)(gq * 2) * b.rtot + r) * 16) = pack8(y);
             *reinterpret_cast<uint4*>(sA + ((size_t)(gq * 2 + 1) * b.rtot + r) * 16) = pack8(y + 8);
-          }
           }
         }
       }
@@ -532,61 +535,57 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
       const int nxt_rtot = last ? 0 : pl.blk[bi + 1].rtot;
       const int tv = pl.T0 * V;
       for (int gq = g_first; gq < groups; gq += g_step) {
-        {
-          float4 bb[4];
+        float4 bb[4];
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) bb[q4] = *reinterpret_cast<const float4*>(bop + gq * 16 + q4 * 4);
-          for (int t0 = t_first; t0 < m_tiles; t0 += t_step) {
+        for (int q4 = 0; q4 < 4; ++q4) bb[q4] = *reinterpret_cast<const float4*>(bop + gq * 16 + q4 * 4);
+        for (int t0 = t_first; t0 < m_tiles; t0 += t_step) {
           float acc[16];
           tmem_ld16(tmem + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(t0 * dcol + gq * 16), acc);
           tmem_ld_wait();
-          {
-            const int mrow = t0 * 128 + lane_grp * 32 + lane;
-            const uint32_t e = mrow < b.mrows ? mt[mrow] : kGap;
-            const int w = e >> 11, target = e & 0x7FF;
-            if (e == kGap || w >= nw) continue;
+          const int mrow = t0 * 128 + lane_grp * 32 + lane;
+          const uint32_t e = mrow < b.mrows ? mt[mrow] : kGap;
+          const int w = e >> 11, target = e & 0x7FF;
+          if (e == kGap || w >= nw) continue;
 #pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-              acc[q4 * 4 + 0] += bb[q4].x; acc[q4 * 4 + 1] += bb[q4].y; acc[q4 * 4 + 2] += bb[q4].z; acc[q4 * 4 + 3] += bb[q4].w;
-            }
-            if (bi == 0) {
-              // K = Cin (2) residual conv on CUDA cores in fp32 from the un-mixed input
-              // raw-pose element of this output row: window w, frame stride * t', keypoint v  (mrow = w*slot*V + t'*V + v)
-              const int q0 = mrow - w * b.slot * V, t0r = q0 / V;
-              const float* xp = x0 + w * per_w + (b.stride * t0r) * V + (q0 - t0r * V);
-#pragma unroll
-              for (int ci = 0; ci < 4; ++ci)
-                if (ci < b.cin) {
-                  const float xv = xp[ci * tv];
-#pragma unroll
-                  for (int q4 = 0; q4 < 4; ++q4) {
-                    const float4 rr = *reinterpret_cast<const float4*>(r0s + ci * 64 + gq * 16 + q4 * 4);
-                    acc[q4 * 4 + 0] = fmaf(rr.x, xv, acc[q4 * 4 + 0]); acc[q4 * 4 + 1] = fmaf(rr.y, xv, acc[q4 * 4 + 1]);
-                    acc[q4 * 4 + 2] = fmaf(rr.z, xv, acc[q4 * 4 + 2]); acc[q4 * 4 + 3] = fmaf(rr.w, xv, acc[q4 * 4 + 3]);
-                  }
-                }
-            } else if (b.identity_res) {
-              const int r = b.gap * V + mrow;                                  // phase 0 (stride 1)
-              float f[8];
-              unpack8(*reinterpret_cast<const uint4*>(sXin + ((size_t)(gq * 2) * b.rtot + r) * 16), f);
-#pragma unroll
-              for (int q = 0; q < 8; ++q) acc[q] += f[q];
-              unpack8(*reinterpret_cast<const uint4*>(sXin + ((size_t)(gq * 2 + 1) * b.rtot + r) * 16), f);
-#pragma unroll
-              for (int q = 0; q < 8; ++q) acc[8 + q] += f[q];
-            }
-#pragma unroll
-            for (int q = 0; q < 16; ++q) acc[q] = fmaxf(acc[q], 0.f);
-            if (!last) {
-              *reinterpret_cast<uint4*>(sXout + ((size_t)(gq * 2) * nxt_rtot + target) * 16) = pack8(acc);
-              *reinterpret_cast<uint4*>(sXout + ((size_t)(gq * 2 + 1) * nxt_rtot + target) * 16) = pack8(acc + 8);
-            } else {
-              float* dst = tokens + (size_t)(w_first + w) * pl.S_out * (size_t)(pl.c_last * V) + target;
-#pragma unroll
-              for (int q = 0; q < 16; ++q)
-                if (gq * 16 + q < b.cout) dst[(gq * 16 + q) * V] = acc[q];
-            }
+          for (int q4 = 0; q4 < 4; ++q4) {
+            acc[q4 * 4 + 0] += bb[q4].x; acc[q4 * 4 + 1] += bb[q4].y; acc[q4 * 4 + 2] += bb[q4].z; acc[q4 * 4 + 3] += bb[q4].w;
           }
+          if (bi == 0) {
+            // K = Cin (2) residual conv on CUDA cores in fp32 from the un-mixed input: raw-pose element of this output
+            // row = window w, frame stride * t', keypoint v  (mrow = w*slot*V + t'*V + v)
+            const int q0 = mrow - w * b.slot * V, t0r = q0 / V;
+            const float* xp = x0 + w * per_w + (b.stride * t0r) * V + (q0 - t0r * V);
+#pragma unroll
+            for (int ci = 0; ci < 4; ++ci)
+              if (ci < b.cin) {
+                const float xv = xp[ci * tv];
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                  const float4 rr = *reinterpret_cast<const float4*>(r0s + ci * 64 + gq * 16 + q4 * 4);
+                  acc[q4 * 4 + 0] = fmaf(rr.x, xv, acc[q4 * 4 + 0]); acc[q4 * 4 + 1] = fmaf(rr.y, xv, acc[q4 * 4 + 1]);
+                  acc[q4 * 4 + 2] = fmaf(rr.z, xv, acc[q4 * 4 + 2]); acc[q4 * 4 + 3] = fmaf(rr.w, xv, acc[q4 * 4 + 3]);
+                }
+              }
+          } else if (b.identity_res) {
+            const int r = b.gap * V + mrow;                                  // phase 0 (stride 1)
+            float f[8];
+            unpack8(*reinterpret_cast<const uint4*>(sXin + ((size_t)(gq * 2) * b.rtot + r) * 16), f);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[q] += f[q];
+            unpack8(*reinterpret_cast<const uint4*>(sXin + ((size_t)(gq * 2 + 1) * b.rtot + r) * 16), f);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[8 + q] += f[q];
+          }
+#pragma unroll
+          for (int q = 0; q < 16; ++q) acc[q] = fmaxf(acc[q], 0.f);
+          if (!last) {
+            *reinterpret_cast<uint4*>(sXout + ((size_t)(gq * 2) * nxt_rtot + target) * 16) = pack8(acc);
+            *reinterpret_cast<uint4*>(sXout + ((size_t)(gq * 2 + 1) * nxt_rtot + target) * 16) = pack8(acc + 8);
+          } else {
+            float* dst = tokens + (size_t)(w_first + w) * pl.S_out * (size_t)(pl.c_last * V) + target;
+#pragma unroll
+            for (int q = 0; q < 16; ++q)
+              if (gq * 16 + q < b.cout) dst[(gq * 16 + q) * V] = acc[q];
           }
         }
       }
