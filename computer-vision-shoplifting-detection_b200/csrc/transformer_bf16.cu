@@ -47,7 +47,8 @@ constexpr int kPW = 160, kParamFloats = 5 * kPW;
 
 struct XfGeo {
   int S, wpw, rows_per_warp, win_per_tile;
-  uint32_t off_aop, off_hop, off_mem, off_w, off_red, smem_bytes;
+  uint32_t off_aop, off_hop, off_mem, off_w, off_red, off_ops, smem_bytes;
+  int ops_in_smem;                     // the op program is copied into shared memory when it fits (else read from global)
   int slot_bytes, plane;               // plane = 128 rows * 16 B
   int param_off;                       // byte offset of the fp32 parameter block inside a ring slot
 };
@@ -148,6 +149,14 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
   // index of the first / next GEMM op (for the weight ring)
   const int n_ops = prog.n_ops;
   const XfOp* __restrict__ ops = prog.ops;
+  if (geo.ops_in_smem) {      // every op costs several dependent global loads otherwise (the interpreter walks the list per tile)
+    static_assert(sizeof(XfOp) % 16 == 0, "XfOp is copied in 16-byte pieces");
+    const uint4* src = reinterpret_cast<const uint4*>(prog.ops);
+    uint4* dst = reinterpret_cast<uint4*>(smem + geo.off_ops);
+    for (int i = threadIdx.x; i < n_ops * (int)(sizeof(XfOp) / 16); i += kThreads) dst[i] = __ldg(src + i);
+    __syncthreads();
+    ops = reinterpret_cast<const XfOp*>(smem + geo.off_ops);
+  }
 
   const int64_t n_tiles = (B + geo.win_per_tile - 1) / geo.win_per_tile;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -582,6 +591,10 @@ bool make_geo(const sf_model* m, int S, XfGeo* g) {
   g->off_mem = off; off += op_bytes;
   g->off_w = off; off += 2u * (uint32_t)g->slot_bytes;
   g->off_red = off; off += (4 * kParts + kParts * kSMax) * 128 * sizeof(float);
+  g->off_ops = off;
+  const uint32_t ops_bytes = ((uint32_t)p.n_ops * (uint32_t)sizeof(XfOp) + 127u) & ~127u;
+  g->ops_in_smem = off + ops_bytes <= (uint32_t)m->max_smem_optin ? 1 : 0;
+  if (g->ops_in_smem) off += ops_bytes;
   g->smem_bytes = off;
   return off <= (uint32_t)m->max_smem_optin;
 }
