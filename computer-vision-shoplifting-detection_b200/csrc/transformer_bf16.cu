@@ -99,6 +99,15 @@ __device__ __forceinline__ float red_sum(const float* red, int row) {
   return t;
 }
 
+// 16 consecutive floats of a 16-byte aligned shared-memory array (bias blocks): four 128-bit loads
+__device__ __forceinline__ void lds16(const float* p, float* out) {
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float4 v = *reinterpret_cast<const float4*>(p + 4 * e);
+    out[4 * e + 0] = v.x; out[4 * e + 1] = v.y; out[4 * e + 2] = v.z; out[4 * e + 3] = v.w;
+  }
+}
+
 // write one 16-column group of a row into a planar-chunk operand buffer
 __device__ __forceinline__ void store_group(unsigned char* buf, int plane, int row, int g, const float* y) {
   *reinterpret_cast<uint4*>(buf + (size_t)(2 * g) * plane + row * 16) = pack8(y);
@@ -380,12 +389,13 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
           for (int i = 0; i < kSlots; ++i) {
             const int g = kParts * i + part;
             if (g < ng) {
-              float acc[16];
+              float acc[16], bs[16];
               tmem_ld16(tmem + lane_addr + (uint32_t)(op.tmem_col + g * 16), acc);
+              lds16(pbase + g * 16, bs);
               tmem_ld_wait();
 #pragma unroll
               for (int q = 0; q < 16; ++q) {
-                const float v = acc[q] + pbase[g * 16 + q];
+                const float v = acc[q] + bs[q];
                 acc[q] = op.act == 2 ? gelu_erf(v) : fmaxf(v, 0.f);
               }
               store_group(sHop, plane, row, g, acc);
@@ -398,18 +408,19 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
           for (int i = 0; i < kSlots; ++i) {
             const int g = kParts * i + part;
             if (g < ng) {
-              float acc[16];
+              float acc[16], bs[16];
               tmem_ld16(tmem + lane_addr + (uint32_t)(op.tmem_col + g * 16), acc);
+              lds16(pbase + g * 16, bs);
               if (set_pe) {
                 float pe16[16];
                 ldg16(xf.pe + tok_s * d, g * 16, d, valid, pe16);
                 tmem_ld_wait();
 #pragma unroll
-                for (int q = 0; q < 16; ++q) st[i][q] = (valid && g * 16 + q < d) ? acc[q] + pbase[g * 16 + q] + pe16[q] : 0.f;
+                for (int q = 0; q < 16; ++q) st[i][q] = (valid && g * 16 + q < d) ? acc[q] + bs[q] + pe16[q] : 0.f;
               } else {
                 tmem_ld_wait();
 #pragma unroll
-                for (int q = 0; q < 16; ++q) st[i][q] += acc[q] + pbase[g * 16 + q];
+                for (int q = 0; q < 16; ++q) st[i][q] += acc[q] + bs[q];
               }
             }
           }
@@ -421,9 +432,10 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
           for (int i = 0; i < kSlots; ++i) {
             const int g = kParts * i + part;
             if (g < ng) {
-              float acc[16], target[16];
+              float acc[16], target[16], bs[16];
               tmem_ld16(tmem + lane_addr + (uint32_t)(op.tmem_col + g * 16), acc);
               ldg16(tok_row, g * 16, dt, valid, target);
+              lds16(pbase + g * 16, bs);
               if (xf.variant == SF_VARIANT_SHOPFORMER) {
                 float pe16[16];
                 ldg16(xf.pe_score + tok_s * dt, g * 16, dt, valid, pe16);
@@ -434,7 +446,7 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
 #pragma unroll
               for (int q = 0; q < 16; ++q) {
                 const int c = g * 16 + q;
-                const float r = acc[q] + pbase[c];
+                const float r = acc[q] + bs[q];
                 const float df = (valid && c < dt) ? r - target[q] : 0.f;
                 sq = fmaf(df, df, sq);
                 acc[q] = r;
