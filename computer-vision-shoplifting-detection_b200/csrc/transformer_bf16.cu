@@ -330,6 +330,7 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
                     }
                 }
             }
+            XF_STAMP(oi * 8 + 5);
             if (P > 1) {   // uniform over the CTA (hpw == 1 here): one exchange per attention op
 #pragma unroll
               for (int j = 0; j < kSMax; ++j)
@@ -358,6 +359,7 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
                 den += sc[j];
               }
             const float inv = 1.f / den;
+            XF_STAMP(oi * 8 + 7);
             for (int c16 = 0; c16 < ncol; c16 += 16) {
               float v16[16];
               tmem_ld16(tmem + lane_addr + (uint32_t)(2 * dp + c0 + c16), v16);

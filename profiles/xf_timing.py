@@ -16,7 +16,7 @@ lib.sfdbg_transformer_timing(0, buf, 1024)
 a = np.array(buf[:]).reshape(-1, 2)
 end = np.where(a[:, 0] == 9999)[0]
 lo, hi = end[0] + 1, end[1]           # second tile of the CTA
-names = {0: "op start", 1: "w ready+sync", 2: "issued", 3: "mma done", 4: "epi done", 5: "ln mean", 6: "ln rstd"}
+names = {0: "op start", 1: "w ready+sync", 2: "issued", 3: "mma done", 4: "epi done", 5: "attn QK done", 6: "ln rstd", 7: "attn softmax done"}
 t0 = a[lo, 1]; prev = t0
 agg = {}
 for i in range(lo, hi + 1):
