@@ -59,6 +59,8 @@ struct BfBlk {
   const float *gcn_b, *out_b;          // [npad], zero padded
   const float *gcn_w32, *res_w32;      // block 0 only: fp32 [cin][cout]
   uint32_t off_rowtab, off_mtab;       // smem tables (uint16)
+  uint32_t off_drtab;                  // blocks >= 1: the data rows of the input buffer, row | keypoint << 11
+  int n_data;
 };
 
 struct BfPlan {
@@ -67,7 +69,7 @@ struct BfPlan {
   const float *in_scale, *in_shift;
   BfBlk blk[kMaxBlocks];
   uint32_t off_A, off_X0, off_X1, off_WG, off_x0, off_w0img;
-  uint32_t off_xjtab, off_bias_g, off_bias_o, off_r0, off_ellv, off_scale, off_shift;
+  uint32_t off_bias_g, off_bias_o, off_r0, off_ellv, off_scale, off_shift;
   uint32_t smem_bytes, tmem_cols;
 };
 static_assert(sizeof(BfPlan) <= 3900, "BfPlan must fit in kernel parameter space");
@@ -100,24 +102,25 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 // tensor-core GEMM.  Each mixed value m is split m = hi + lo (two bf16) and each weight w = w_hi + w_lo, and the
 // K axis carries the three significant products per input channel: columns [3c, 3c+1, 3c+2] = [hi, hi, lo] against
 // weight rows [w_hi, w_lo, w_hi] -- the graph conv of block 0 stays at fp32 input accuracy on the tensor cores.
-template <int W>
+template <int W, int CIN>
 __device__ __forceinline__ void mix_a0(const float* __restrict__ x0, unsigned char* __restrict__ a0, uint32_t plane_bytes,
-                                       const uint16_t* __restrict__ rt, const float2* __restrict__ ell, int V, int cin, int tv,
+                                       const uint16_t* __restrict__ rt, const float2* __restrict__ ell, int V, int tv,
                                        int per_w, int nw, int rtot) {
   for (int r = threadIdx.x; r < rtot; r += (int)blockDim.x) {
     const uint32_t en = rt[r];
-    const bool ok = en != kGap && (int)(en >> 11) < nw;
-    const int v = ok ? (int)(en & 31) : 0;
-    const int base = ok ? (int)(en >> 11) * per_w + (int)((en >> 5) & 63) * V + v : 0;
+    if (en == kGap) continue;             // gap rows of A0 only feed GEMM rows that the g0 epilogue replaces by zeros
+    const bool ok = (int)(en >> 11) < nw;
+    const int v = (int)(en & 31);
+    const int base = ok ? (int)(en >> 11) * per_w + (int)((en >> 5) & 63) * V + v : v;
     float2 e[W];
 #pragma unroll
     for (int k = 0; k < W; ++k) e[k] = ell[k * V + v];
-    float m[4];
+    float m[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int ci = 0; ci < 4; ++ci) {
+    for (int ci = 0; ci < CIN; ++ci) {
       float xv[W];
 #pragma unroll
-      for (int k = 0; k < W; ++k) xv[k] = ci < cin ? x0[base + ci * tv + (ok ? __float_as_int(e[k].y) : 0)] : 0.f;
+      for (int k = 0; k < W; ++k) xv[k] = x0[base + ci * tv + __float_as_int(e[k].y)];
       float acc = 0.f;
 #pragma unroll
       for (int k = 0; k < W; ++k) acc = fmaf(e[k].x, xv[k], acc);
@@ -137,21 +140,22 @@ __device__ __forceinline__ void mix_a0(const float* __restrict__ x0, unsigned ch
   }
 }
 
-// adjacency mix of one 8-channel granule column of the bf16 activation buffer: dst[r] = sum_k val_k * src[r + delta_k]
+// adjacency mix of one 8-channel granule column of the bf16 activation buffer: dst[r] = sum_k val_k * src[r + delta_k],
+// over the DATA rows only (dr[i] = row | keypoint << 11).  Gap rows of the destination are left as they are: they only
+// feed GEMM rows whose outputs the next epilogue replaces by zeros.
 template <int W>
 __device__ __forceinline__ void mix_rows(const unsigned char* __restrict__ plane, unsigned char* __restrict__ dstp,
-                                         const uint16_t* __restrict__ rt, const float2* __restrict__ ell, int ellV,
-                                         int r_first, int r_step, int rtot) {
-  for (int r = r_first; r < rtot; r += r_step) {
-    const uint32_t en = rt[r];
-    const bool ok = en != kGap;
-    const int v = ok ? (int)(en & 31) : 0;
+                                         const uint16_t* __restrict__ dr, const float2* __restrict__ ell, int ellV,
+                                         int i_first, int i_step, int n_data) {
+  for (int i = i_first; i < n_data; i += i_step) {
+    const uint32_t en = dr[i];
+    const int r = (int)(en & 0x7FF), v = (int)(en >> 11);
     float2 e[W];
 #pragma unroll
     for (int k = 0; k < W; ++k) e[k] = ell[k * ellV + v];
     uint4 q[W];
 #pragma unroll
-    for (int k = 0; k < W; ++k) q[k] = *reinterpret_cast<const uint4*>(plane + (size_t)(r + (ok ? __float_as_int(e[k].y) : 0)) * 16);
+    for (int k = 0; k < W; ++k) q[k] = *reinterpret_cast<const uint4*>(plane + (size_t)(r + __float_as_int(e[k].y)) * 16);
     float a[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) a[c] = 0.f;
@@ -162,7 +166,7 @@ __device__ __forceinline__ void mix_rows(const unsigned char* __restrict__ plane
 #pragma unroll
       for (int c = 0; c < 8; ++c) a[c] = fmaf(e[k].x, f[c], a[c]);
     }
-    *reinterpret_cast<uint4*>(dstp + (size_t)r * 16) = ok ? pack8(a) : make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(dstp + (size_t)r * 16) = pack8(a);
   }
 }
 
@@ -207,7 +211,6 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
   unsigned char* sX[2] = {smem + pl.off_X0, smem + pl.off_X1};
   unsigned char* sWG = smem + pl.off_WG;
   float* x0 = reinterpret_cast<float*>(smem + pl.off_x0);      // raw poses of the current window group (fp32)
-  const uint8_t* xjtab = reinterpret_cast<const uint8_t*>(smem + pl.off_xjtab);     // c*V+v of every x0 element
   const float* bias_g = reinterpret_cast<const float*>(smem + pl.off_bias_g);       // [blk][64]
   const float* bias_o = reinterpret_cast<const float*>(smem + pl.off_bias_o);
   const unsigned char* w0img = smem + pl.off_w0img;                                 // block-0 graph-conv weights, [2][npad][8] bf16
@@ -246,6 +249,16 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
         }
       }
       rt[r] = e;
+    }
+    if (bi > 0) {
+      uint16_t* dr = reinterpret_cast<uint16_t*>(smem + b.off_drtab);
+      const int per_phase = G * b.Tout * V;                             // data rows of one phase, in row order
+      for (int i = threadIdx.x; i < b.n_data; i += kThreads) {
+        const int ph = i / per_phase, q = i - ph * per_phase;
+        const int w = q / (b.Tout * V), qq = q - w * b.Tout * V;
+        const int r = ph * b.rows + b.gap * V + w * slotV + qq;
+        dr[i] = (uint16_t)(r | ((qq % V) << 11));
+      }
     }
     const bool last = bi + 1 == pl.n_blocks;
     for (int mrow = threadIdx.x; mrow < b.mrows; mrow += kThreads) {         // row of the conv output (M space)
@@ -302,10 +315,6 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
       reinterpret_cast<float*>(smem + pl.off_scale)[i] = __ldg(pl.in_scale + i);
       reinterpret_cast<float*>(smem + pl.off_shift)[i] = __ldg(pl.in_shift + i);
     }
-    for (int i = threadIdx.x; i < G * per_w; i += kThreads) {
-      const int r = i % per_w;
-      reinterpret_cast<uint8_t*>(smem + pl.off_xjtab)[i] = (uint8_t)((r / (pl.T0 * V)) * V + r % V);
-    }
   }
   // operand buffers start out finite: an MMA may read stale bytes against zero weights, and NaN * 0 = NaN
   zero_fill(smem + pl.off_A, (int)(pl.off_x0 - pl.off_A));
@@ -347,15 +356,24 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
       }
       const int n_valid = nw * per_w;
       for (int i = threadIdx.x; i < G * per_w; i += kThreads) {
-        const int j = xjtab[i];
+        const int ii = i % per_w, j = (ii / (pl.T0 * V)) * V + ii % V;          // c*V + v of this pose element
         x0[i] = i < n_valid ? fmaf(x0[i], scale_s[j], shift_s[j]) : 0.f;      // folded BatchNorm1d, in place
       }
       __syncthreads();
       TOK_STAMP(101);
       // A0 <- split(A_hat . x0): K = 16 operand rows of the phase-split layout, in the A buffer (g0 later overwrites it)
       const uint16_t* rt0 = reinterpret_cast<const uint16_t*>(smem + b.off_rowtab);
-      if (b.ell_width <= 5) mix_a0<5>(x0, sA, (uint32_t)b.rtot * 16u, rt0, ell2, V, b.cin, pl.T0 * V, per_w, nw, b.rtot);
-      else mix_a0<kEllMax>(x0, sA, (uint32_t)b.rtot * 16u, rt0, ell2, V, b.cin, pl.T0 * V, per_w, nw, b.rtot);
+      const uint32_t pa0 = (uint32_t)b.rtot * 16u;
+      const int tv0 = pl.T0 * V;
+#define SF_MIX_A0(W_) \
+  switch (b.cin) { \
+    case 1: mix_a0<W_, 1>(x0, sA, pa0, rt0, ell2, V, tv0, per_w, nw, b.rtot); break; \
+    case 2: mix_a0<W_, 2>(x0, sA, pa0, rt0, ell2, V, tv0, per_w, nw, b.rtot); break; \
+    case 3: mix_a0<W_, 3>(x0, sA, pa0, rt0, ell2, V, tv0, per_w, nw, b.rtot); break; \
+    default: mix_a0<W_, 4>(x0, sA, pa0, rt0, ell2, V, tv0, per_w, nw, b.rtot); break; \
+  }
+      if (b.ell_width <= 5) { SF_MIX_A0(5) } else { SF_MIX_A0(kEllMax) }
+#undef SF_MIX_A0
       TOK_STAMP(102);
     }
 
@@ -391,8 +409,9 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
           const unsigned char* plane = sXin + (size_t)j * planeA;
           unsigned char* dstp = sA + (size_t)j * planeA;
           const float2* el = ell2 + bi * V * pl.ell_stride;
-          if (b.ell_width <= 5) mix_rows<5>(plane, dstp, rt, el, V, threadIdx.x - j * tpc, tpc, b.rtot);
-          else mix_rows<kEllMax>(plane, dstp, rt, el, V, threadIdx.x - j * tpc, tpc, b.rtot);
+          const uint16_t* dr = reinterpret_cast<const uint16_t*>(smem + b.off_drtab);
+          if (b.ell_width <= 5) mix_rows<5>(plane, dstp, dr, el, V, threadIdx.x - j * tpc, tpc, b.n_data);
+          else mix_rows<kEllMax>(plane, dstp, dr, el, V, threadIdx.x - j * tpc, tpc, b.n_data);
         }
         TOK_STAMP(111 + bi * 10);
         if (warp == 0) mbar_wait(&wbar, wpar);
@@ -716,8 +735,10 @@ bool build_plan(const sf_model* m, int T, int G, BfPlan* pl, const char** why) {
   for (int i = 0; i < nb; ++i) {
     pl->blk[i].off_rowtab = off; off += up((size_t)pl->blk[i].rtot * 2);
     pl->blk[i].off_mtab = off; off += up((size_t)pl->blk[i].mrows * 2);
+    pl->blk[i].n_data = i > 0 ? pl->blk[i].stride * G * pl->blk[i].Tout * V : 0;
+    pl->blk[i].off_drtab = off;
+    if (i > 0) off += up((size_t)pl->blk[i].n_data * 2);
   }
-  pl->off_xjtab = off; off += up((size_t)G * tk.c_in * T * V);
   pl->bstride = 16;
   pl->ell_stride = 1;
   for (int i = 0; i < nb; ++i) {
