@@ -9,10 +9,22 @@ using namespace sf;
 namespace {
 inline int64_t align256(int64_t x) { return (x + 255) & ~int64_t(255); }
 
-int check_T(const sf_model* m, int T) {
+int check_model(const sf_model* m) {
   SF_REQUIRE(m, SF_E_INVALID, "null model");
+  SF_REQUIRE(m->device >= 0, SF_E_INVALID, "host-only model (emulator fixture): no entry point computes with it");
+  return SF_OK;
+}
+int check_T(const sf_model* m, int T) {
+  int rc = check_model(m);
+  if (rc) return rc;
   SF_REQUIRE(T >= 1 && T <= 4096, SF_E_INVALID, "T=%d outside [1,4096]", T);
   return SF_OK;
+}
+// tensor-core tokenizer: the multi-window tile kernel (tokenizer2_bf16.cu) when it covers the shape, otherwise the
+// one-window-per-pass kernel (tokenizer_bf16.cu)
+int launch_tokenizer_tc(const sf_model* m, const float* poses, int64_t B, int T, float* tokens, cudaStream_t st) {
+  if (tokenizer2_supported(m, T)) return launch_tokenizer2(m, poses, B, T, tokens, st);
+  return launch_tokenizer_bf16(m, poses, B, T, tokens, st);
 }
 }  // namespace
 
@@ -23,7 +35,7 @@ int check_T(const sf_model* m, int T) {
 constexpr int64_t kScoreChunk = 131072;
 
 extern "C" int64_t sf_workspace_bytes(const sf_model* m, int64_t B, int32_t T) {
-  if (!m || B < 0 || T < 1) return SF_E_INVALID;
+  if (!m || m->device < 0 || B < 0 || T < 1) return SF_E_INVALID;
   B = std::min(B, kScoreChunk);
   const int S = token_len(m, T);
   // tokens staged between the two kernels when the caller does not ask for them
@@ -36,7 +48,9 @@ extern "C" int sf_tokenize(const sf_model* m, const float* poses_dev, int64_t B,
   if (rc) return rc;
   SF_REQUIRE(B >= 0 && (B == 0 || (poses_dev && tokens_dev)), SF_E_INVALID, "sf_tokenize: null buffer");
   SF_REQUIRE(precision == SF_PREC_FP32 || precision == SF_PREC_BF16, SF_E_INVALID, "unknown precision %d", precision);
-  if (precision == SF_PREC_BF16) return launch_tokenizer_bf16(m, poses_dev, B, T, tokens_dev, (cudaStream_t)stream);
+  DeviceGuard guard;
+  SF_CUDA_OK(guard.enter(m->device));
+  if (precision == SF_PREC_BF16) return launch_tokenizer_tc(m, poses_dev, B, T, tokens_dev, (cudaStream_t)stream);
   return launch_tokenizer_fp32(m, poses_dev, B, T, tokens_dev, workspace_dev, workspace_bytes, (cudaStream_t)stream);
 }
 
@@ -44,9 +58,13 @@ extern "C" int sf_reconstruct_tokens(const sf_model* m, const float* tokens_dev,
                                      float* recon_dev, void* workspace_dev, int64_t workspace_bytes, void* stream) {
   (void)workspace_dev;
   (void)workspace_bytes;
-  SF_REQUIRE(m, SF_E_INVALID, "null model");
+  int rc = check_model(m);
+  if (rc) return rc;
   SF_REQUIRE(B >= 0 && (B == 0 || (tokens_dev && recon_dev)), SF_E_INVALID, "sf_reconstruct_tokens: null buffer");
+  SF_REQUIRE(S >= 1 && S <= 100, SF_E_INVALID, "S=%d outside [1,100]", S);
   SF_REQUIRE(precision == SF_PREC_FP32 || precision == SF_PREC_BF16, SF_E_INVALID, "unknown precision %d", precision);
+  DeviceGuard guard;
+  SF_CUDA_OK(guard.enter(m->device));
   if (precision == SF_PREC_BF16)
     return launch_transformer_bf16(m, tokens_dev, B, S, SF_REDUCE_MEAN, recon_dev, nullptr, (cudaStream_t)stream);
   return launch_transformer_fp32(m, tokens_dev, B, S, SF_REDUCE_MEAN, recon_dev, nullptr, (cudaStream_t)stream);
@@ -54,9 +72,12 @@ extern "C" int sf_reconstruct_tokens(const sf_model* m, const float* tokens_dev,
 
 extern "C" int sf_normality_score(const sf_model* m, const float* tokens_dev, const float* recon_dev, int64_t B, int32_t S,
                                   int32_t reduction, float* scores_dev, void* stream) {
-  SF_REQUIRE(m, SF_E_INVALID, "null model");
+  int rc = check_model(m);
+  if (rc) return rc;
   SF_REQUIRE(B >= 0 && (B == 0 || (tokens_dev && recon_dev && scores_dev)), SF_E_INVALID, "sf_normality_score: null buffer");
   SF_REQUIRE(S >= 1 && S <= 100, SF_E_INVALID, "S=%d outside [1,100]", S);
+  DeviceGuard guard;
+  SF_CUDA_OK(guard.enter(m->device));
   return launch_score(m, tokens_dev, recon_dev, B, S, reduction, scores_dev, (cudaStream_t)stream);
 }
 
@@ -68,6 +89,8 @@ extern "C" int sf_score_windows(const sf_model* m, const float* poses_dev, int64
   SF_REQUIRE(B >= 0 && (B == 0 || (poses_dev && scores_dev)), SF_E_INVALID, "sf_score_windows: null buffer");
   SF_REQUIRE(precision == SF_PREC_FP32 || precision == SF_PREC_BF16, SF_E_INVALID, "unknown precision %d", precision);
   if (B == 0) return SF_OK;
+  DeviceGuard guard;
+  SF_CUDA_OK(guard.enter(m->device));
   const int S = token_len(m, T);
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t pose_elems = (int64_t)m->cfg.in_channels * T * m->cfg.num_keypoints, tok_elems = (int64_t)S * m->xf.d_tok;
@@ -89,7 +112,7 @@ extern "C" int sf_score_windows(const sf_model* m, const float* poses_dev, int64
     const int64_t n = std::min(pass, B - off);
     float* tok = tokens_dev ? tokens_dev + off * tok_elems : tok_ws;
     const float* x = poses_dev + off * pose_elems;
-    rc = precision == SF_PREC_BF16 ? launch_tokenizer_bf16(m, x, n, T, tok, st) : launch_tokenizer_fp32(m, x, n, T, tok, ws, ws_left, st);
+    rc = precision == SF_PREC_BF16 ? launch_tokenizer_tc(m, x, n, T, tok, st) : launch_tokenizer_fp32(m, x, n, T, tok, ws, ws_left, st);
     if (rc) return rc;
     float* rec = recon_dev ? recon_dev + off * tok_elems : nullptr;
     float* sc = scores_dev + off * score_stride;
@@ -129,7 +152,8 @@ extern "C" int sf_runner_create(const sf_model* m, int32_t T, int64_t max_chunk,
   int rc = check_T(m, T);
   if (rc) return rc;
   SF_REQUIRE(out && max_chunk >= 1, SF_E_INVALID, "sf_runner_create: bad argument");
-  SF_CUDA_OK(cudaSetDevice(m->device));
+  DeviceGuard guard;
+  SF_CUDA_OK(guard.enter(m->device));
   sf_runner* r = new sf_runner();
   memset(r, 0, sizeof(*r));
   r->m = m;
@@ -164,7 +188,8 @@ extern "C" int sf_runner_create(const sf_model* m, int32_t T, int64_t max_chunk,
 
 extern "C" void sf_runner_destroy(sf_runner* r) {
   if (!r) return;
-  cudaSetDevice(r->m->device);
+  DeviceGuard guard;
+  guard.enter(r->m->device);
   if (r->copy_st) cudaStreamSynchronize(r->copy_st);
   if (r->comp_st) cudaStreamSynchronize(r->comp_st);
   for (int i = 0; i < kRing; ++i) {
@@ -190,7 +215,8 @@ extern "C" float* sf_runner_pinned_poses(sf_runner* r, int32_t slot) {
 
 extern "C" int sf_runner_score(sf_runner* r, const float* poses_host, int64_t B, int32_t precision, float* scores_host) {
   SF_REQUIRE(r && (B == 0 || (poses_host && scores_host)), SF_E_INVALID, "sf_runner_score: null argument");
-  SF_CUDA_OK(cudaSetDevice(r->m->device));
+  DeviceGuard guard;
+  SF_CUDA_OK(guard.enter(r->m->device));
   int64_t pending_off[kRing], pending_n[kRing];
   for (int i = 0; i < kRing; ++i) pending_off[i] = -1, pending_n[i] = 0;
   bool src_pinned = false;
@@ -265,5 +291,31 @@ extern "C" int sf_runner_score(sf_runner* r, const float* poses_host, int64_t B,
       SF_CUDA_OK(cudaEventSynchronize(r->computed[s]));
       memcpy(scores_host + pending_off[s], r->pin_out[s], pending_n[s] * sizeof(float));
     }
+  return SF_OK;
+}
+
+// ------------------------------------------------------------------------------------ test infrastructure
+// Runs the tokenizer-v2 tile program of `m` (which may be a HOST-ONLY model, device < 0) on the host emulator
+// (tok2_emulate.cu).  Returns SF_E_UNSUPPORTED when the shape is outside tokenizer v2, SF_E_INVALID on an emulator
+// failure (deadlock / hazard; message in sf_last_error).  Not part of the C ABI; no product path calls it.
+#include "tok2_build.h"
+namespace sf { const t2::Static* tok2_static(const Tok2State* s); }
+extern "C" int sfdbg_tok2_emulate(const sf_model* m, const float* poses_host, int64_t B, int32_t T, float* tokens_host,
+                                  uint32_t schedule_seed, int32_t* info_out) {
+  SF_REQUIRE(m && m->tok2 && (B == 0 || (poses_host && tokens_host)), SF_E_INVALID, "sfdbg_tok2_emulate: bad argument");
+  const t2::Static* st = tok2_static(m->tok2);
+  t2::Program pr;
+  t2::build_program(*st, T, m->max_smem_optin, &pr);
+  SF_REQUIRE(pr.ok, SF_E_UNSUPPORTED, "tokenizer v2 does not cover this shape: %s", pr.why.c_str());
+  if (info_out) {
+    info_out[0] = pr.plan.n_groups;
+    info_out[1] = pr.plan.n_stages;
+    info_out[2] = pr.plan.n_loads;
+    info_out[3] = pr.plan.n_mma;
+    info_out[4] = (int32_t)pr.plan.smem_bytes;
+    info_out[5] = pr.plan.WT;
+  }
+  std::string err;
+  SF_REQUIRE(t2::emulate(*st, pr, poses_host, B, tokens_host, schedule_seed, &err), SF_E_INVALID, "%s", err.c_str());
   return SF_OK;
 }

@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -199,13 +200,23 @@ extern "C" int sf_model_create(const sf_config* cfg, int32_t n_tensors, const ch
   if (cfg->variant == SF_VARIANT_SHOPFORMER)
     SF_REQUIRE(d == d_tok, SF_E_INVALID, "variant 1 needs d_model == latent*V (%d vs %d)", d, d_tok);
 
-  int rc = sf_device_count();
-  if (rc < 0) return rc;
-  SF_CUDA_OK(cudaSetDevice(device));
+  // device < 0: HOST-ONLY model for the tile-program emulator (sfdbg_tok2_emulate, test infrastructure).  Every compute
+  // entry point rejects such a model; nothing below touches CUDA for it.
+  const bool host_only = device < 0;
   cudaDeviceProp prop;
-  SF_CUDA_OK(cudaGetDeviceProperties(&prop, device));
-  SF_REQUIRE(prop.major == 10, SF_E_NODEVICE, "device %d is sm_%d%d; this build targets sm_100a only", device,
-             prop.major, prop.minor);
+  memset(&prop, 0, sizeof(prop));
+  DeviceGuard guard;
+  if (!host_only) {
+    int rc = sf_device_count();
+    if (rc < 0) return rc;
+    SF_CUDA_OK(guard.enter(device));
+    SF_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    SF_REQUIRE(prop.major == 10, SF_E_NODEVICE, "device %d is sm_%d%d; this build targets sm_100a only", device,
+               prop.major, prop.minor);
+  } else {
+    prop.multiProcessorCount = 148;
+    prop.sharedMemPerBlockOptin = 232448;
+  }
 
   Packer pk;
   for (int i = 0; i < n_tensors; ++i) pk.sd[names[i]] = HostTensor{data_host[i], numel[i]};
@@ -512,11 +523,55 @@ extern "C" int sf_model_create(const sf_config* cfg, int32_t n_tensors, const ch
   m->sm_count = prop.multiProcessorCount;
   m->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   m->arena_bytes = pk.arena.size() * sizeof(float);
+  m->tok2 = nullptr;
+  m->host_arena = nullptr;
+  m->arena_bf16 = nullptr;
+  m->xfops_dev = nullptr;
+  auto fill_tok = [&](const float* A, Tokenizer& T) {
+    T.n_blocks = nb;
+    T.V = V;
+    T.c_in = c0;
+    T.pool_tokens = cfg->pool_tokens;
+    T.in_scale = A + off_in_scale;
+    T.in_shift = A + off_in_shift;
+    for (int i = 0; i < nb; ++i) {
+      TokBlock& b = T.blk[i];
+      b.cin = cfg->channels[i];
+      b.cout = cfg->channels[i + 1];
+      b.stride = cfg->strides[i];
+      b.identity_res = bo[i].identity;
+      b.ell_width = bo[i].ellw;
+      b.gcn_w = A + bo[i].gw;
+      b.gcn_b = A + bo[i].gb;
+      b.tcn_w = A + bo[i].tw;
+      b.res_w = bo[i].identity ? nullptr : A + bo[i].rw;
+      b.out_b = A + bo[i].ob;
+      b.ell_val = A + bo[i].ev;
+      b.ell_col = reinterpret_cast<const int*>(A + bo[i].ec);
+    }
+  };
+  {
+    Tokenizer host_tok;
+    fill_tok(pk.arena.data(), host_tok);
+    m->tok2 = tok2_create(host_tok, cfg->pool_tokens, !host_only);
+  }
+  if (host_only) {
+    m->host_arena = (float*)malloc(m->arena_bytes);
+    memcpy(m->host_arena, pk.arena.data(), m->arena_bytes);
+    m->arena = nullptr;
+    fill_tok(m->host_arena, m->tok);
+    memset(&m->xf, 0, sizeof(m->xf));
+    m->xf.d_tok = d_tok;
+    m->xfprog = XfProgram{nullptr, 0, 0, 0, 0, 0};
+    *out = m;
+    return SF_OK;
+  }
   cudaError_t e = cudaMalloc((void**)&m->arena, m->arena_bytes);
   if (e == cudaSuccess) e = cudaMemcpy(m->arena, pk.arena.data(), m->arena_bytes, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
     set_error("uploading %zu bytes of packed weights failed: %s", m->arena_bytes, cudaGetErrorString(e));
     if (m->arena) cudaFree(m->arena);
+    tok2_destroy(m->tok2);
     delete m;
     return SF_E_CUDA;
   }
@@ -528,6 +583,7 @@ extern "C" int sf_model_create(const sf_config* cfg, int32_t n_tensors, const ch
     set_error("uploading %zu bytes of bf16 operand images failed: %s", m->arena_bf16_bytes, cudaGetErrorString(e));
     cudaFree(m->arena);
     if (m->arena_bf16) cudaFree(m->arena_bf16);
+    tok2_destroy(m->tok2);
     delete m;
     return SF_E_CUDA;
   }
@@ -560,6 +616,7 @@ extern "C" int sf_model_create(const sf_config* cfg, int32_t n_tensors, const ch
         set_error("uploading the transformer program failed: %s", cudaGetErrorString(e));
         cudaFree(m->arena);
         cudaFree(m->arena_bf16);
+        tok2_destroy(m->tok2);
         delete m;
         return SF_E_CUDA;
       }
@@ -570,28 +627,7 @@ extern "C" int sf_model_create(const sf_config* cfg, int32_t n_tensors, const ch
   auto nrm = [&](const NormOff& o) { return Norm{A + o.g, A + o.b}; };
   auto att = [&](const AttnOff& o) { return Attn{lin(o.qkv), lin(o.out)}; };
 
-  Tokenizer& T = m->tok;
-  T.n_blocks = nb;
-  T.V = V;
-  T.c_in = c0;
-  T.pool_tokens = cfg->pool_tokens;
-  T.in_scale = A + off_in_scale;
-  T.in_shift = A + off_in_shift;
-  for (int i = 0; i < nb; ++i) {
-    TokBlock& b = T.blk[i];
-    b.cin = cfg->channels[i];
-    b.cout = cfg->channels[i + 1];
-    b.stride = cfg->strides[i];
-    b.identity_res = bo[i].identity;
-    b.ell_width = bo[i].ellw;
-    b.gcn_w = A + bo[i].gw;
-    b.gcn_b = A + bo[i].gb;
-    b.tcn_w = A + bo[i].tw;
-    b.res_w = bo[i].identity ? nullptr : A + bo[i].rw;
-    b.out_b = A + bo[i].ob;
-    b.ell_val = A + bo[i].ev;
-    b.ell_col = reinterpret_cast<const int*>(A + bo[i].ec);
-  }
+  fill_tok(A, m->tok);
   Transformer& X = m->xf;
   X.variant = cfg->variant;
   X.d_tok = d_tok;
@@ -616,7 +652,15 @@ extern "C" int sf_model_create(const sf_config* cfg, int32_t n_tensors, const ch
 
 extern "C" void sf_model_destroy(sf_model* m) {
   if (!m) return;
-  cudaSetDevice(m->device);
+  if (m->device < 0) {
+    tok2_destroy(m->tok2);
+    free(m->host_arena);
+    delete m;
+    return;
+  }
+  DeviceGuard guard;
+  guard.enter(m->device);
+  tok2_destroy(m->tok2);
   if (m->arena) cudaFree(m->arena);
   if (m->arena_bf16) cudaFree(m->arena_bf16);
   if (m->xfops_dev) cudaFree(m->xfops_dev);

@@ -34,6 +34,26 @@ void set_error(const char* fmt, ...);
     }                                \
   } while (0)
 
+// Every entry point that takes a model / tracks runs on THAT object's device and leaves the caller's current device
+// untouched (a torch process has its own notion of the current device).
+struct DeviceGuard {
+  int prev = -1;
+  bool active = false;
+  cudaError_t enter(int device) {
+    cudaError_t e = cudaGetDevice(&prev);
+    if (e != cudaSuccess) return e;
+    if (prev != device) {
+      e = cudaSetDevice(device);
+      if (e != cudaSuccess) return e;
+      active = true;
+    }
+    return cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (active) cudaSetDevice(prev);
+  }
+};
+
 // ---- tokenizer (device view; all pointers into one HBM arena) ------------------------
 struct TokBlock {
   int cin, cout, stride, identity_res;
@@ -132,6 +152,8 @@ struct XfProgram {
 };
 }  // namespace sf
 
+namespace sf { struct Tok2State; }
+
 struct sf_model {
   sf_config cfg;
   int device;
@@ -146,6 +168,8 @@ struct sf_model {
   sf::BfTokenizerW tokbf;
   sf::XfProgram xfprog;
   sf::XfOp* xfops_dev;
+  sf::Tok2State* tok2;      // tokenizer v2: operand images + per-T tile programs (tokenizer2_bf16.cu)
+  float* host_arena;        // device < 0 only: a HOST model for the program emulator (tests); no entry point computes with it
 };
 
 namespace sf {
@@ -161,6 +185,12 @@ int token_len(const sf_model* m, int T);
 // bf16 tcgen05 tokenizer (returns SF_E_UNSUPPORTED for shapes it does not cover)
 int launch_tokenizer_bf16(const sf_model* m, const float* poses, int64_t B, int T, float* tokens, cudaStream_t st);
 bool tokenizer_bf16_supported(const sf_model* m, int T);
+// tokenizer v2 (multi-window tiles, see tok2.h); `tokenizer_bf16` dispatches to it when the shape is covered
+Tok2State* tok2_create(const Tokenizer& host_tok, int pool_tokens, bool upload);
+void tok2_destroy(Tok2State* s);
+bool tokenizer2_supported(const sf_model* m, int T);
+const char* tokenizer2_why(const sf_model* m, int T);
+int launch_tokenizer2(const sf_model* m, const float* poses, int64_t B, int T, float* tokens, cudaStream_t st);
 // bf16 tcgen05 transformer + fused score
 int launch_transformer_bf16(const sf_model* m, const float* tokens, int64_t B, int S, int reduction, float* recon,
                             float* scores, cudaStream_t st);

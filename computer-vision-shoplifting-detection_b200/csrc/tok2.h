@@ -1,0 +1,91 @@
+// Tokenizer v2 ("tok2"): the tile program shared by the host builder (tok2_build.cu), the sm_100a kernel
+// (tokenizer2_bf16.cu) and the host emulator of the program (tok2_emulate.cu, test infrastructure).
+//
+// Layout idea (reference maths: shopformer/models/gcae.py:124-154,185-195,242-259,331-366):
+//   * one tile = WT = floor(128 / V) whole windows; MMA row r = w * V + v  (window, keypoint),
+//     MMA column = (time, channel).  Every activation buffer is the planar-chunk layout of tc_common.cuh with
+//     128 rows: byte = (col / 8) * 2048 + row * 16 + (col % 8) * 2.
+//   * adjacency mix  = one 128x128 block-diagonal A operand (I_WT (x) A_hat) times the activation buffer used as an
+//     MN-major B operand (K = rows);
+//   * graph-conv weights = per-time-step [128 x Cin] x [Cin x Cout] MMAs;
+//   * temporal conv = Toeplitz product done WITHOUT a Toeplitz matrix: for input time t the taps that are valid for
+//     consecutive output times t' are consecutive blocks of a tap image stored in descending-tap order per stride phase,
+//     so ONE MMA with N = (#valid t') * Cout adds time t's contribution to all its outputs; no padding taps are computed;
+//   * strided 1x1 residual conv = per-output-time MMAs into the same accumulator (they also initialise it).
+// The host flattens a (model, T) pair into three in-order item sequences -- G (MMA groups, one issuing thread),
+// E (epilogue / prep stages, 8 warps) and L (TMA loads, one thread) -- and derives every cross-sequence wait from the
+// items' read / write sets (shared-memory byte ranges and TMEM column ranges).  Each item owns one mbarrier that
+// completes exactly once per tile.
+#pragma once
+#include <stdint.h>
+
+namespace sf {
+namespace t2 {
+
+constexpr int kRows = 128;               // MMA M
+constexpr uint32_t kPlane = 2048;        // bytes of one 8-column chunk of a 128-row activation buffer
+constexpr int kEpiWarps = 8;             // warps 4..11
+constexpr int kThreads = 384;            // warp 0: MMA issue, warp 1: TMA, warps 2-3: idle, warps 4-11: epilogue
+constexpr int kMaxGroups = 96, kMaxStages = 96, kMaxLoads = 12, kMaxMma = 512;
+
+struct Mma {                 // one tcgen05.mma (M = 128, K = 16)
+  uint32_t a_lo;             // descriptor low word relative to the dynamic smem base: (offset >> 4) | (LBO >> 4) << 16
+  uint32_t b_lo;
+  uint32_t d;                // [0,9) TMEM column | bit 16 accumulate | bit 17 B is MN-major (SBO = plane instead of 128 B)
+  uint32_t idesc;
+};
+
+struct Group {               // G item: a run of MMAs followed by one commit
+  uint16_t first, count;
+  int16_t wait_e, wait_l;    // E stage / L load that must have completed this tile (-1: none)
+  int16_t wait_e_prev;       // E stage of the PREVIOUS tile (-1: none)
+  int16_t pad[3];
+};
+
+enum StageType { ST_PREP = 0, ST_CVT = 1, ST_TOKENS = 2 };
+enum StageFlags { SF_RELU = 1, SF_BIAS = 2, SF_DRAIN_STORE = 4 };
+
+struct Stage {               // E item
+  uint8_t type, flags;
+  int16_t wait_g;            // G group of this tile (-1: none)
+  int16_t wait_l;            // L load (PREP: the poses)
+  int16_t wait_g_prev;       // G group of the previous tile (-1: none)
+  uint16_t tmem_col, n_cg;   // CVT / TOKENS: first accumulator column, number of 16-column groups
+  uint32_t dst_off;          // CVT: smem byte offset of destination column 0
+  uint32_t bias_off;         // byte offset of the fp32 bias vector (period `bias_period` columns)
+  uint16_t bias_period;
+  uint16_t p0, p1, p2;       // PREP: [p0, p1) time steps of A0; p2 = 1: also build A0x (all output times)
+  uint32_t pad;
+};
+
+enum LoadKind { LD_WEIGHTS = 0, LD_POSES = 1 };
+struct Load {                // L item
+  uint8_t kind, pad0;
+  int16_t wait_g, wait_e;    // this tile
+  int16_t wait_g_prev;       // previous tile
+  uint32_t dst_off, bytes;
+  uint64_t src;              // LD_WEIGHTS: global address of the image
+};
+
+struct Plan {                // kernel parameter (by value)
+  int V, WT, rows, c_in, T0, S_out, c_last, cp_last, d_tok;
+  int per_w;                 // floats per pose window
+  int n_groups, n_stages, n_loads, n_mma;
+  const Mma* mma;            // device tables
+  const Group* groups;
+  const Stage* stages;
+  const Load* loads;
+  const unsigned char* const_src;   // resident images + fp32 tables, copied to smem once per CTA
+  uint32_t const_bytes;
+  // shared-memory map (byte offsets from the dynamic smem base)
+  uint32_t off_const, off_P, off_Q, off_W, off_mma, off_groups, off_stages, off_loads, off_bars, off_flags;
+  uint32_t off_xin, off_a0, off_a0x, off_stage_tok;
+  uint32_t off_ell, off_scale, off_shift;       // inside the const blob: ELL (value, delta) [5|8][V], BN1d scale/shift
+  int ell_width;
+  int a0_chunks, a0x_chunks, stride0;
+  int bar_g0, bar_e0, bar_l0, n_bars;           // barrier index bases
+  uint32_t smem_bytes;
+};
+
+}  // namespace t2
+}  // namespace sf

@@ -1,0 +1,638 @@
+// Tokenizer v2, host side: operand images (once per model) and the tile program (once per window length T).
+// See tok2.h for the layout.  Reference maths: shopformer/models/gcae.py:124-154 (graph conv), :185-195 (temporal
+// conv + BN), :242-259 (block), :331-366 (encoder); shopformer_2/models/gcae.py:375-422.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "tok2_build.h"
+
+namespace sf {
+namespace t2 {
+namespace {
+
+inline uint16_t f2bf(float f) {       // round-to-nearest-even fp32 -> bf16
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+inline float bf2f(uint16_t h) {
+  uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+inline int pad16(int x) { return (x + 15) & ~15; }
+inline uint32_t up128(size_t x) { return (uint32_t)((x + 127) & ~size_t(127)); }
+
+struct Blob {
+  std::vector<unsigned char>& b;
+  uint32_t alloc(size_t bytes) {
+    const uint32_t off = up128(b.size());
+    b.resize(off + bytes, 0);
+    return off;
+  }
+  uint16_t* bf(uint32_t off) { return reinterpret_cast<uint16_t*>(b.data() + off); }
+  float* f32(uint32_t off) { return reinterpret_cast<float*>(b.data() + off); }
+};
+
+// K-major image [K/8][nrows][8] of val(n, k)
+template <class F>
+void fill_kmajor(uint16_t* dst, int nrows, int K, F val) {
+  for (int kc = 0; kc < K / 8; ++kc)
+    for (int n = 0; n < nrows; ++n)
+      for (int e = 0; e < 8; ++e) dst[((size_t)kc * nrows + n) * 8 + e] = f2bf(val(n, kc * 8 + e));
+}
+
+}  // namespace
+
+void build_static(const Tokenizer& tok, int pool_tokens, Static* out) {
+  Static& s = *out;
+  s = Static();
+  const int V = tok.V, nb = tok.n_blocks;
+  auto fail = [&](const char* w) { s.ok = false; s.why = w; };
+  if (pool_tokens > 0) return fail("adaptive pooling");
+  if (tok.c_in > 2) return fail("more than 2 input channels");
+  if (nb < 2) return fail("fewer than 2 blocks");
+  if (V > 64 || V < 2) return fail("keypoint count outside [2,64]");
+  s.V = V;
+  s.WT = kRows / V;
+  s.rows = s.WT * V;
+  s.c_in = tok.c_in;
+  s.n_blocks = nb;
+  Blob bl{s.blob};
+
+  // dense adjacency per block from the ELL rows; blocks >= 1 must share one adjacency (one block-diagonal mix operand)
+  std::vector<std::vector<float>> adj(nb, std::vector<float>((size_t)V * V, 0.f));
+  for (int b = 0; b < nb; ++b) {
+    const TokBlock& tb = tok.blk[b];
+    for (int v = 0; v < V; ++v)
+      for (int k = 0; k < tb.ell_width; ++k) adj[b][(size_t)v * V + tb.ell_col[v * tb.ell_width + k]] += tb.ell_val[v * tb.ell_width + k];
+  }
+  for (int b = 2; b < nb; ++b)
+    if (adj[b] != adj[1]) return fail("blocks use different adjacency matrices");
+  if (tok.blk[0].ell_width > 8) return fail("adjacency rows with more than 8 non-zeros");
+  if (tok.blk[0].identity_res) return fail("identity residual in block 0");
+
+  // ---- const part ------------------------------------------------------------------------------------------
+  // block-diagonal mix operand (A, K-major): (m, k) = A_hat[v_m][u_k] iff same window
+  s.off_ablk = bl.alloc((size_t)kRows * kRows * 2);
+  fill_kmajor(bl.bf(s.off_ablk), kRows, kRows, [&](int m, int k) -> float {
+    if (m >= s.rows || k >= s.rows || m / V != k / V) return 0.f;
+    return adj[1][(size_t)(m % V) * V + (k % V)];
+  });
+  for (int b = 0; b < nb; ++b) {
+    const TokBlock& tb = tok.blk[b];
+    BlockStatic& o = s.blk[b];
+    o.cin = tb.cin;
+    o.cout = tb.cout;
+    o.cin_p = b == 0 ? tb.cin : pad16(tb.cin);
+    o.cp = pad16(tb.cout);
+    o.stride = tb.stride;
+    o.identity = tb.identity_res;
+    if (o.cp > 128) return fail("more than 128 channels");
+    if (b > 0 && o.cin_p != s.blk[b - 1].cp) return fail("channel padding mismatch");
+  }
+  {
+    // block 0: K = 16 split images.  A columns per time step: [hx, hx, lx, hy, hy, ly, 1, 1]; B rows [w_hi, w_lo, w_hi | b_hi, b_lo]
+    const TokBlock& t0 = tok.blk[0];
+    const int cp = s.blk[0].cp, co = t0.cout;
+    auto split_image = [&](uint32_t off, const float* w, const float* bias) {
+      fill_kmajor(bl.bf(off), 2 * cp, 16, [&](int n, int k) -> float {
+        const int half = n / cp, o = n % cp, kk = k % 8, kh = k / 8;
+        if (kh != half || o >= co) return 0.f;
+        float src;
+        bool lo;
+        if (kk < 6) {
+          const int ci = kk / 3, j = kk % 3;
+          if (ci >= t0.cin) return 0.f;
+          src = w[ci * co + o];
+          lo = j == 1;
+        } else {
+          src = bias[o];
+          lo = kk == 7;
+        }
+        const float hi = bf2f(f2bf(src));
+        return lo ? src - hi : hi;
+      });
+    };
+    s.off_w0 = bl.alloc((size_t)2 * cp * 16 * 2);
+    split_image(s.off_w0, t0.gcn_w, t0.gcn_b);
+    s.off_r0 = bl.alloc((size_t)2 * cp * 16 * 2);
+    split_image(s.off_r0, t0.res_w, t0.out_b);
+  }
+  for (int b = 1; b < nb; ++b) {
+    const TokBlock& tb = tok.blk[b];
+    BlockStatic& o = s.blk[b];
+    o.off_gcn = bl.alloc((size_t)o.cin_p * o.cp * 2);
+    fill_kmajor(bl.bf(o.off_gcn), o.cp, o.cin_p, [&](int n, int k) -> float { return (n < tb.cout && k < tb.cin) ? tb.gcn_w[k * tb.cout + n] : 0.f; });
+    o.off_res = bl.alloc((size_t)o.cin_p * o.cp * 2);
+    fill_kmajor(bl.bf(o.off_res), o.cp, o.cin_p, [&](int n, int k) -> float {
+      if (n >= tb.cout || k >= tb.cin) return 0.f;
+      return tb.identity_res ? (n == k ? 1.f : 0.f) : tb.res_w[k * tb.cout + n];
+    });
+    o.off_bias_g = bl.alloc((size_t)o.cp * 4);
+    o.off_bias_o = bl.alloc((size_t)o.cp * 4);
+    for (int n = 0; n < tb.cout; ++n) {
+      bl.f32(o.off_bias_g)[n] = tb.gcn_b[n];
+      bl.f32(o.off_bias_o)[n] = tb.out_b[n];
+    }
+  }
+  {
+    // prep tables: block-0 adjacency as ELL [k][V] (value, row delta), folded BatchNorm1d
+    const TokBlock& t0 = tok.blk[0];
+    s.ell_width = t0.ell_width <= 5 ? 5 : 8;
+    s.off_ell = bl.alloc((size_t)s.ell_width * V * 8);
+    for (int k = 0; k < s.ell_width; ++k)
+      for (int v = 0; v < V; ++v) {
+        float val = 0.f;
+        int dl = 0;
+        if (k < t0.ell_width) {
+          val = t0.ell_val[v * t0.ell_width + k];
+          dl = val != 0.f ? t0.ell_col[v * t0.ell_width + k] - v : 0;
+        }
+        bl.f32(s.off_ell)[(size_t)(k * V + v) * 2] = val;
+        memcpy(&bl.f32(s.off_ell)[(size_t)(k * V + v) * 2 + 1], &dl, 4);
+      }
+    s.off_scale = bl.alloc((size_t)tok.c_in * V * 4);
+    s.off_shift = bl.alloc((size_t)tok.c_in * V * 4);
+    memcpy(bl.f32(s.off_scale), tok.in_scale, sizeof(float) * tok.c_in * V);
+    memcpy(bl.f32(s.off_shift), tok.in_shift, sizeof(float) * tok.c_in * V);
+  }
+  s.const_bytes = up128(s.blob.size());
+  s.blob.resize(s.const_bytes, 0);
+
+  // ---- temporal-conv images: per stride phase p the taps k = p (mod s) in DESCENDING order, so that for one input
+  // time the taps of consecutive output times are consecutive N blocks
+  for (int b = 0; b < nb; ++b) {
+    const TokBlock& tb = tok.blk[b];
+    BlockStatic& o = s.blk[b];
+    int pos = 0;
+    for (int p = 0; p < tb.stride && p < kTaps; ++p) {
+      int kmax = p;
+      while (kmax + tb.stride < kTaps) kmax += tb.stride;
+      for (int k = kmax; k >= 0; k -= tb.stride) o.tap_pos[k] = pos++;
+    }
+    std::vector<int> tap_at(kTaps);
+    for (int k = 0; k < kTaps; ++k) tap_at[o.tap_pos[k]] = k;
+    o.tcn_bytes = (uint32_t)(kTaps * o.cp * o.cp * 2);
+    o.off_tcn = bl.alloc(o.tcn_bytes);
+    const int co = tb.cout;
+    fill_kmajor(bl.bf(o.off_tcn), kTaps * o.cp, o.cp, [&](int n, int c) -> float {
+      const int k = tap_at[n / o.cp], oc = n % o.cp;
+      return (c < co && oc < co) ? tb.tcn_w[((size_t)c * kTaps + k) * co + oc] : 0.f;
+    });
+  }
+  s.blob.resize(up128(s.blob.size()), 0);
+  s.ok = true;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct Rng {
+  int space;        // 0 = shared-memory bytes, 1 = TMEM columns
+  uint32_t lo, hi;
+};
+struct Item {
+  int side, idx;    // 0 = G, 1 = E, 2 = L
+  std::vector<Rng> rd, wr;
+};
+bool overlap(const std::vector<Rng>& a, const std::vector<Rng>& b) {
+  for (const Rng& x : a)
+    for (const Rng& y : b)
+      if (x.space == y.space && x.lo < y.hi && y.lo < x.hi) return true;
+  return false;
+}
+
+}  // namespace
+
+void build_program(const Static& st, int T, int max_smem, Program* out) {
+  Program& pr = *out;
+  pr = Program();
+  auto fail = [&](const std::string& w) { pr.ok = false; pr.why = w; };
+  if (!st.ok) return fail(st.why);
+  const int nb = st.n_blocks, V = st.V;
+  if (T < 1 || T > 256) return fail("window length outside [1,256]");
+  int Tin[kMaxBlocks], Tout[kMaxBlocks];
+  {
+    int t = T;
+    for (int b = 0; b < nb; ++b) {
+      Tin[b] = t;
+      Tout[b] = (t - 1) / st.blk[b].stride + 1;
+      t = Tout[b];
+    }
+  }
+  const int per_w = st.c_in * T * V;
+  if ((per_w * 4) % 16) return fail("window size not a multiple of 16 bytes");
+  const uint32_t xin_bytes = (uint32_t)st.WT * per_w * 4, xin_alloc = up128(xin_bytes);
+  const int cp0 = st.blk[0].cp;
+  const int n_sl = (T + 1) / 2;
+  const int a0_chunks = 2 * n_sl, a0x_chunks = 2 * ((Tout[0] + 1) / 2);
+  if (Tout[0] * cp0 + 4 * cp0 > 512) return fail("block-0 accumulators exceed tensor memory");
+  if (2 * cp0 > 256) return fail("block-0 width");
+
+  // ---- chunking of blocks >= 1 (time steps per mix / graph-conv chunk) and region sizes
+  int ct[kMaxBlocks] = {0}, nch[kMaxBlocks] = {0};
+  uint32_t slot_bytes[kMaxBlocks] = {0};
+  uint32_t x_bytes[kMaxBlocks + 1] = {0};          // x_b = input of block b (b >= 1), planar-chunk bf16
+  for (int b = 1; b <= nb; ++b) x_bytes[b] = b < nb ? (uint32_t)(Tin[b] * st.blk[b].cin_p / 8) * kPlane : 0u;
+  const uint32_t ring0_slot = (uint32_t)(2 * cp0 / 8) * kPlane;
+  const int ring0_slots = std::min(3, n_sl);
+  uint32_t P_need = (uint32_t)(a0_chunks + a0x_chunks) * kPlane + xin_alloc, Q_need = ring0_slot * ring0_slots;
+  const uint32_t ring_cap_q = 49152;
+  for (int b = 1; b < nb; ++b) {
+    const BlockStatic& k = st.blk[b];
+    const bool x_in_P = (b & 1) != 0;                 // x1 in P, x2 in Q, ...
+    (x_in_P ? P_need : Q_need) = std::max(x_in_P ? P_need : Q_need, x_bytes[b]);
+    const int accw = Tout[b] * k.cp;
+    int best = 0;
+    for (int c = Tin[b]; c >= 1; --c) {
+      const int chunks = (Tin[b] + c - 1) / c;
+      const uint32_t sb = (uint32_t)(c * std::max(k.cin_p, k.cp) / 8) * kPlane;
+      const uint32_t ring = sb * (uint32_t)std::min(2, chunks);
+      if (c * k.cin_p > 256 || c * k.cp > 256) continue;
+      if (accw + c * k.cin_p + c * k.cp > 512) continue;
+      const uint32_t cap = x_in_P ? ring_cap_q : std::max(P_need, (uint32_t)98304);
+      if (ring > cap) continue;
+      best = c;
+      break;
+    }
+    if (!best) return fail("no chunking fits tensor memory / shared memory");
+    ct[b] = best;
+    nch[b] = (Tin[b] + best - 1) / best;
+    slot_bytes[b] = (uint32_t)(best * std::max(k.cin_p, k.cp) / 8) * kPlane;
+    const uint32_t ring = slot_bytes[b] * (uint32_t)std::min(2, nch[b]);
+    (x_in_P ? Q_need : P_need) = std::max(x_in_P ? Q_need : P_need, ring);
+  }
+  // token staging (fp32, the tile's tokens contiguous as in HBM) lives at the end of Q, clear of the last block's
+  // ring slot / input
+  const int S_out = Tout[nb - 1], c_last = st.blk[nb - 1].cout, d_tok = c_last * V;
+  const uint32_t stage_bytes = up128((size_t)st.WT * S_out * d_tok * 4);
+  {
+    const bool last_x_in_P = ((nb - 1) & 1) != 0;
+    const uint32_t q_used_last = last_x_in_P ? slot_bytes[nb - 1] * (uint32_t)std::min(2, nch[nb - 1]) : x_bytes[nb - 1];
+    Q_need = std::max(Q_need, up128(q_used_last) + stage_bytes);
+  }
+  const uint32_t P_size = up128(P_need), Q_size = up128(Q_need);
+  uint32_t W_size = 0;
+  for (int b = 0; b < nb; ++b) W_size = std::max(W_size, st.blk[b].tcn_bytes);
+
+  Plan& pl = pr.plan;
+  memset(&pl, 0, sizeof(pl));
+  pl.V = V;
+  pl.WT = st.WT;
+  pl.rows = st.rows;
+  pl.c_in = st.c_in;
+  pl.T0 = T;
+  pl.S_out = S_out;
+  pl.c_last = c_last;
+  pl.cp_last = st.blk[nb - 1].cp;
+  pl.d_tok = d_tok;
+  pl.per_w = per_w;
+  pl.const_bytes = st.const_bytes;
+  pl.ell_width = st.ell_width;
+  pl.a0_chunks = a0_chunks;
+  pl.a0x_chunks = a0x_chunks;
+  pl.stride0 = st.blk[0].stride;
+  uint32_t off = 0;
+  pl.off_const = off; off += st.const_bytes;
+  pl.off_P = off; off += P_size;
+  pl.off_Q = off; off += Q_size;
+  pl.off_W = off; off += up128(W_size);
+  pl.off_ell = pl.off_const + st.off_ell;
+  pl.off_scale = pl.off_const + st.off_scale;
+  pl.off_shift = pl.off_const + st.off_shift;
+  pl.off_a0 = pl.off_P;
+  pl.off_a0x = pl.off_P + (uint32_t)a0_chunks * kPlane;
+  pl.off_xin = pl.off_P + P_size - xin_alloc;
+  pl.off_stage_tok = pl.off_Q + Q_size - stage_bytes;
+
+  // ---- emit the items ----------------------------------------------------------------------------------------
+  std::vector<Item> order;          // one valid sequential schedule of a tile
+  std::vector<Item*> dummy;
+  auto smem_r = [](uint32_t lo, uint32_t bytes) { return Rng{0, lo, lo + bytes}; };
+  auto tmem_r = [](int col, int n) { return Rng{1, (uint32_t)col, (uint32_t)(col + n)}; };
+  const uint32_t c_lo = pl.off_const, c_hi = pl.off_const + st.const_bytes;
+  auto is_const = [&](uint32_t o) { return o >= c_lo && o < c_hi; };
+
+  auto new_group = [&]() -> int {
+    Group g;
+    memset(&g, 0, sizeof(g));
+    g.first = (uint16_t)pr.mma.size();
+    g.wait_e = g.wait_l = g.wait_e_prev = -1;
+    pr.groups.push_back(g);
+    order.push_back(Item{0, (int)pr.groups.size() - 1, {}, {}});
+    return (int)pr.groups.size() - 1;
+  };
+  // one MMA: A K-major at a_off (LBO = a_lbo), B at b_off: K-major (LBO = b_lbo, rows = N) or MN-major (activation
+  // buffer used with K = rows: K step kk at +256 B, N chunks one plane apart)
+  auto add_mma = [&](uint32_t a_off, uint32_t a_lbo, uint32_t b_off, uint32_t b_lbo, bool b_mn, int N, int dcol, bool acc) {
+    Mma m;
+    m.a_lo = ((a_off >> 4) & 0x3FFFu) | ((a_lbo >> 4) << 16);
+    m.b_lo = ((b_off >> 4) & 0x3FFFu) | (((b_mn ? 128u : b_lbo) >> 4) << 16);
+    m.d = (uint32_t)dcol | (acc ? 1u << 16 : 0u) | (b_mn ? 1u << 17 : 0u);
+    m.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
+    pr.mma.push_back(m);
+    pr.groups.back().count++;
+    Item& it = order.back();
+    if (!is_const(a_off)) {
+      it.rd.push_back(smem_r(a_off, kPlane));
+      it.rd.push_back(smem_r(a_off + a_lbo, kPlane));
+    }
+    if (!is_const(b_off)) {
+      if (b_mn) it.rd.push_back(smem_r(b_off & ~(kPlane - 1), (uint32_t)(N / 8) * kPlane));
+      else {
+        it.rd.push_back(smem_r(b_off, (uint32_t)N * 16));
+        it.rd.push_back(smem_r(b_off + b_lbo, (uint32_t)N * 16));
+      }
+    }
+    it.wr.push_back(tmem_r(dcol, N));
+  };
+  auto new_stage = [&](int type, int flags) -> Stage& {
+    Stage s;
+    memset(&s, 0, sizeof(s));
+    s.type = (uint8_t)type;
+    s.flags = (uint8_t)flags;
+    s.wait_g = s.wait_l = s.wait_g_prev = -1;
+    pr.stages.push_back(s);
+    order.push_back(Item{1, (int)pr.stages.size() - 1, {}, {}});
+    return pr.stages.back();
+  };
+  auto cvt_stage = [&](int tmem_col, int ncols, uint32_t dst_off, int flags, uint32_t bias_off, int period) {
+    Stage& s = new_stage(ST_CVT, flags);
+    s.tmem_col = (uint16_t)tmem_col;
+    s.n_cg = (uint16_t)(ncols / 16);
+    s.dst_off = dst_off;
+    s.bias_off = bias_off;
+    s.bias_period = (uint16_t)period;
+    order.back().rd.push_back(tmem_r(tmem_col, ncols));
+    order.back().wr.push_back(smem_r(dst_off, (uint32_t)(ncols / 8) * kPlane));
+  };
+  auto new_load = [&](int kind, uint32_t dst_off, uint32_t bytes, uint64_t src) {
+    Load l;
+    memset(&l, 0, sizeof(l));
+    l.kind = (uint8_t)kind;
+    l.wait_g = l.wait_e = l.wait_g_prev = -1;
+    l.dst_off = dst_off;
+    l.bytes = bytes;
+    l.src = src;
+    pr.loads.push_back(l);
+    order.push_back(Item{2, (int)pr.loads.size() - 1, {}, {smem_r(dst_off, bytes)}});
+  };
+
+  // ======================= block 0
+  {
+    const BlockStatic& k = st.blk[0];
+    const int cp = k.cp, s0 = k.stride;
+    const int acc = 0, stg[2] = {Tout[0] * cp, Tout[0] * cp + 2 * cp};
+    const uint32_t w_img = pl.off_W, w_plane = (uint32_t)kTaps * cp * 16;
+    new_load(LD_WEIGHTS, pl.off_W, k.tcn_bytes, k.off_tcn);
+    auto prep = [&](int t0, int t1, bool with_x) {
+      Stage& s = new_stage(ST_PREP, 0);
+      s.p0 = (uint16_t)t0;
+      s.p1 = (uint16_t)t1;
+      s.p2 = with_x ? 1 : 0;
+      Item& it = order.back();
+      it.rd.push_back(smem_r(pl.off_xin, xin_bytes));
+      const int c1 = (t1 >= T) ? a0_chunks : t1;       // the last prep stage also clears the pad chunk
+      it.wr.push_back(smem_r(pl.off_a0 + (uint32_t)t0 * kPlane, (uint32_t)(c1 - t0) * kPlane));
+      if (with_x) it.wr.push_back(smem_r(pl.off_a0x, (uint32_t)a0x_chunks * kPlane));
+    };
+    const int sl_a = std::min(2, n_sl), sl_b = std::min(6, n_sl);
+    prep(0, std::min(T, 2 * sl_a), true);
+    {
+      // residual conv of block 0 from the split raw poses: initialises every accumulator column (and adds the bias)
+      new_group();
+      for (int j = 0; j < a0x_chunks / 2; ++j)
+        add_mma(pl.off_a0x + (uint32_t)(2 * j) * kPlane, kPlane, pl.off_const + st.off_r0, (uint32_t)(2 * cp) * 16, false,
+                (2 * j + 1 < Tout[0]) ? 2 * cp : cp, acc + 2 * j * cp, false);
+    }
+    auto gcn0 = [&](int i) {
+      new_group();
+      add_mma(pl.off_a0 + (uint32_t)(2 * i) * kPlane, kPlane, pl.off_const + st.off_w0, (uint32_t)(2 * cp) * 16, false, 2 * cp,
+              stg[i & 1], false);
+    };
+    auto epi0 = [&](int i) {
+      cvt_stage(stg[i & 1], 2 * cp, pl.off_Q + (uint32_t)(i % ring0_slots) * ring0_slot, SF_RELU, 0, 0);
+    };
+    auto tcn0 = [&](int i) {
+      new_group();
+      const uint32_t slot = pl.off_Q + (uint32_t)(i % ring0_slots) * ring0_slot;
+      for (int tl = 0; tl < 2; ++tl) {
+        const int t = 2 * i + tl;
+        if (t >= T) break;
+        int lo = (t - kHalo + s0 - 1) / s0;
+        if (t - kHalo < 0) lo = 0;
+        const int hi = std::min(Tout[0] - 1, (t + kHalo) / s0);
+        if (lo > hi) continue;
+        const int k_lo = t - s0 * lo + kHalo;
+        for (int n0 = lo; n0 <= hi;) {
+          const int cnt = std::min(hi - n0 + 1, 256 / cp);
+          const int ktap = k_lo - s0 * (n0 - lo);
+          for (int ks = 0; ks < cp / 16; ++ks)
+            add_mma(slot + (uint32_t)(tl * cp / 8 + 2 * ks) * kPlane, kPlane,
+                    w_img + (uint32_t)(k.tap_pos[ktap] * cp) * 16 + (uint32_t)(2 * ks) * w_plane, w_plane, false, cnt * cp,
+                    acc + n0 * cp, true);
+          n0 += cnt;
+        }
+      }
+    };
+    gcn0(0);
+    if (n_sl > 1) gcn0(1);
+    if (2 * sl_a < T) prep(2 * sl_a, std::min(T, 2 * sl_b), false);
+    bool prep2_done = 2 * sl_b >= T;
+    for (int i = 0; i < n_sl; ++i) {
+      epi0(i);
+      if (!prep2_done && i >= 1) {
+        prep(2 * sl_b, T, false);
+        prep2_done = true;
+      }
+      tcn0(i);
+      if (pr.groups.back().count == 0) {          // (cannot happen for 9 taps / halo 4, kept for safety)
+        pr.groups.pop_back();
+        order.pop_back();
+      }
+      if (i + 2 < n_sl) gcn0(i + 2);
+    }
+    if (!prep2_done) prep(2 * sl_b, T, false);
+    if (nb > 1) new_load(LD_WEIGHTS, pl.off_W, st.blk[1].tcn_bytes, st.blk[1].off_tcn);
+    // x1 = relu(acc) -> P (bias already inside the residual product); chunked like block 1's mix
+    const int cw = ct[1] * cp;
+    for (int c0 = 0; c0 < Tout[0] * cp; c0 += cw)
+      cvt_stage(acc + c0, std::min(cw, Tout[0] * cp - c0), pl.off_P + (uint32_t)(c0 / 8) * kPlane, SF_RELU, 0, 0);
+  }
+
+  // ======================= blocks >= 1
+  for (int b = 1; b < nb; ++b) {
+    const BlockStatic& k = st.blk[b];
+    const bool x_in_P = (b & 1) != 0;
+    const uint32_t xb = x_in_P ? pl.off_P : pl.off_Q, ring = x_in_P ? pl.off_Q : pl.off_P;
+    const int cin = k.cin_p, cp = k.cp, s = k.stride;
+    const int accw = Tout[b] * cp, smw = ct[b] * cin;
+    const int acc = x_in_P ? 512 - accw : 0;
+    const int SM = x_in_P ? 0 : accw, SG = SM + smw;
+    const uint32_t w_img = pl.off_W, w_plane = (uint32_t)kTaps * cp * 16;
+    const uint32_t g_img = pl.off_const + k.off_gcn, r_img = pl.off_const + k.off_res, gr_plane = (uint32_t)cp * 16;
+    const bool last = b + 1 == nb;
+    const int n_slots = std::min(2, nch[b]);
+    auto slot_of = [&](int c) { return ring + (uint32_t)(c % n_slots) * slot_bytes[b]; };
+    auto nt_of = [&](int c) { return std::min(ct[b], Tin[b] - c * ct[b]); };
+    auto mix = [&](int c) {
+      new_group();
+      const int nt = nt_of(c);
+      for (int kk = 0; kk < kRows / 16; ++kk)
+        add_mma(pl.off_const + st.off_ablk + (uint32_t)(2 * kk) * kPlane, kPlane, xb + (uint32_t)(c * ct[b] * cin / 8) * kPlane + (uint32_t)kk * 256u, 0,
+                true, nt * cin, SM, kk > 0);
+    };
+    auto mepi = [&](int c) { cvt_stage(SM, nt_of(c) * cin, slot_of(c), 0, 0, 0); };
+    auto gcn = [&](int c) {
+      new_group();
+      for (int tl = 0; tl < nt_of(c); ++tl)
+        for (int ks = 0; ks < cin / 16; ++ks)
+          add_mma(slot_of(c) + (uint32_t)(tl * cin / 8 + 2 * ks) * kPlane, kPlane, g_img + (uint32_t)(2 * ks) * gr_plane, gr_plane, false, cp,
+                  SG + tl * cp, ks > 0);
+    };
+    auto gepi = [&](int c) { cvt_stage(SG, nt_of(c) * cp, slot_of(c), SF_RELU | SF_BIAS, pl.off_const + k.off_bias_g, cp); };
+    auto res = [&]() {
+      new_group();
+      for (int tp = 0; tp < Tout[b]; ++tp)
+        for (int ks = 0; ks < cin / 16; ++ks)
+          add_mma(xb + (uint32_t)((s * tp) * cin / 8 + 2 * ks) * kPlane, kPlane, r_img + (uint32_t)(2 * ks) * gr_plane, gr_plane, false, cp,
+                  acc + tp * cp, ks > 0);
+    };
+    auto tcn = [&](int c) {
+      new_group();
+      for (int tl = 0; tl < nt_of(c); ++tl) {
+        const int t = c * ct[b] + tl;
+        int lo = (t - kHalo + s - 1) / s;
+        if (t - kHalo < 0) lo = 0;
+        const int hi = std::min(Tout[b] - 1, (t + kHalo) / s);
+        if (lo > hi) continue;
+        const int k_lo = t - s * lo + kHalo;
+        for (int n0 = lo; n0 <= hi;) {
+          const int cnt = std::min(hi - n0 + 1, 256 / cp);
+          const int ktap = k_lo - s * (n0 - lo);
+          for (int ks = 0; ks < cp / 16; ++ks)
+            add_mma(slot_of(c) + (uint32_t)(tl * cp / 8 + 2 * ks) * kPlane, kPlane,
+                    w_img + (uint32_t)(k.tap_pos[ktap] * cp) * 16 + (uint32_t)(2 * ks) * w_plane, w_plane, false, cnt * cp,
+                    acc + n0 * cp, true);
+          n0 += cnt;
+        }
+      }
+    };
+    mix(0);
+    mepi(0);
+    for (int c = 0; c < nch[b]; ++c) {
+      gcn(c);
+      if (c + 1 < nch[b]) mix(c + 1);
+      if (c == 0) res();
+      gepi(c);
+      if (c + 1 < nch[b]) mepi(c + 1);
+      tcn(c);
+      if (pr.groups.back().count == 0) {
+        pr.groups.pop_back();
+        order.pop_back();
+      }
+    }
+    if (!last) {
+      new_load(LD_WEIGHTS, pl.off_W, st.blk[b + 1].tcn_bytes, st.blk[b + 1].off_tcn);
+      const uint32_t xn = x_in_P ? pl.off_Q : pl.off_P;
+      const int cw = ct[b + 1] * cp;
+      for (int c0 = 0; c0 < accw; c0 += cw)
+        cvt_stage(acc + c0, std::min(cw, accw - c0), xn + (uint32_t)(c0 / 8) * kPlane, SF_RELU | SF_BIAS, pl.off_const + k.off_bias_o, cp);
+    } else {
+      Stage& s2 = new_stage(ST_TOKENS, SF_RELU | SF_BIAS);
+      s2.tmem_col = (uint16_t)acc;
+      s2.n_cg = (uint16_t)(accw / 16);
+      s2.bias_off = pl.off_const + k.off_bias_o;
+      s2.bias_period = (uint16_t)cp;
+      order.back().rd.push_back(tmem_r(acc, accw));
+      order.back().wr.push_back(smem_r(pl.off_stage_tok, stage_bytes));
+    }
+  }
+
+  // ---- the next tile's poses: after the last item of this tile that touches the pose slot
+  {
+    const std::vector<Rng> slot{smem_r(pl.off_xin, xin_alloc)};
+    size_t last_touch = 0;
+    for (size_t i = 0; i < order.size(); ++i)
+      if (overlap(order[i].rd, slot) || overlap(order[i].wr, slot)) last_touch = i;
+    Load l;
+    memset(&l, 0, sizeof(l));
+    l.kind = LD_POSES;
+    l.wait_g = l.wait_e = l.wait_g_prev = -1;
+    l.dst_off = pl.off_xin;
+    l.bytes = xin_bytes;
+    // L items must stay in emission order on their side: the pose load goes LAST in the L sequence, so it has to be
+    // placed after every weight load as well
+    size_t at = last_touch + 1;
+    for (size_t i = 0; i < order.size(); ++i)
+      if (order[i].side == 2) at = std::max(at, i + 1);
+    pr.loads.push_back(l);
+    order.insert(order.begin() + at, Item{2, (int)pr.loads.size() - 1, {}, slot});
+  }
+
+  // ---- cross-sequence waits from the read / write sets
+  for (size_t i = 0; i < order.size(); ++i) {
+    Item& x = order[i];
+    int w[3] = {-1, -1, -1};
+    for (size_t j = 0; j < i; ++j) {
+      const Item& y = order[j];
+      if (y.side == x.side) continue;
+      if (overlap(y.wr, x.rd) || overlap(y.rd, x.wr) || overlap(y.wr, x.wr)) w[y.side] = std::max(w[y.side], y.idx);
+    }
+    if (x.side == 0) {
+      pr.groups[x.idx].wait_e = (int16_t)w[1];
+      pr.groups[x.idx].wait_l = (int16_t)w[2];
+    } else if (x.side == 1) {
+      pr.stages[x.idx].wait_g = (int16_t)w[0];
+      pr.stages[x.idx].wait_l = (int16_t)w[2];
+    } else {
+      pr.loads[x.idx].wait_g = (int16_t)w[0];
+      pr.loads[x.idx].wait_e = (int16_t)w[1];
+    }
+  }
+  // tile boundary: the first prep stage overwrites the operand regions the previous tile's last MMAs read, the first
+  // weight load overwrites the weights they read; the prep stage reads the poses the previous tile's last load fetched
+  const int last_g = (int)pr.groups.size() - 1;
+  pr.stages[0].wait_g_prev = (int16_t)last_g;
+  pr.stages[0].wait_l = (int16_t)((int)pr.loads.size() - 1);
+  pr.loads[0].wait_g_prev = (int16_t)last_g;
+  // the block-0 prep stages read the pose slot: all of them wait for the same load (same completion as stage 0)
+  for (Stage& s : pr.stages)
+    if (s.type == ST_PREP) s.wait_l = (int16_t)((int)pr.loads.size() - 1);
+  // stages that write over the token staging area first drain the previous tile's bulk store
+  {
+    const std::vector<Rng> stg{smem_r(pl.off_stage_tok, stage_bytes)};
+    for (const Item& it : order)
+      if (it.side == 1 && overlap(it.wr, stg)) pr.stages[it.idx].flags |= SF_DRAIN_STORE;
+  }
+
+  // ---- tables + barriers
+  pl.n_groups = (int)pr.groups.size();
+  pl.n_stages = (int)pr.stages.size();
+  pl.n_loads = (int)pr.loads.size();
+  pl.n_mma = (int)pr.mma.size();
+  if (pl.n_groups > kMaxGroups || pl.n_stages > kMaxStages || pl.n_loads > kMaxLoads || pl.n_mma > kMaxMma)
+    return fail("tile program too long");
+  pl.off_mma = off; off += up128(pr.mma.size() * sizeof(Mma));
+  pl.off_groups = off; off += up128(pr.groups.size() * sizeof(Group));
+  pl.off_stages = off; off += up128(pr.stages.size() * sizeof(Stage));
+  pl.off_loads = off; off += up128(pr.loads.size() * sizeof(Load));
+  pl.bar_g0 = 0;
+  pl.bar_e0 = pl.n_groups;
+  pl.bar_l0 = pl.n_groups + pl.n_stages;
+  pl.n_bars = pl.n_groups + pl.n_stages + pl.n_loads;
+  pl.off_bars = off; off += up128((size_t)pl.n_bars * 8);
+  pl.off_flags = off; off += 512;
+  pl.smem_bytes = off;
+  if ((int)off > max_smem) return fail("tile does not fit shared memory (" + std::to_string(off) + " bytes)");
+  if (off >= (1u << 18)) return fail("operand offsets exceed the descriptor range");
+  pr.ok = true;
+}
+
+}  // namespace t2
+}  // namespace sf

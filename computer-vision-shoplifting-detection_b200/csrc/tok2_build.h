@@ -1,0 +1,52 @@
+// Host side of tokenizer v2: operand images built once per model + the per-(model, T) tile program.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "sf_internal.h"
+#include "tok2.h"
+
+namespace sf {
+namespace t2 {
+
+struct BlockStatic {
+  int cin, cout, cin_p, cp, stride, identity;
+  uint32_t off_gcn, off_res;        // const blob: [cin_p/8][cp][8] K-major B images (block 0: unused)
+  uint32_t off_bias_g, off_bias_o;  // const blob: fp32 [cp]
+  uint32_t off_tcn, tcn_bytes;      // blob (after the const part): [cp/8][9 taps * cp][8], taps in descending order per stride phase
+  int tap_pos[kTaps];               // block index of tap k inside the image
+};
+
+struct Static {
+  bool ok = false;
+  std::string why;
+  int V = 0, WT = 0, rows = 0, c_in = 0, n_blocks = 0;
+  BlockStatic blk[kMaxBlocks];
+  uint32_t off_ablk = 0, off_w0 = 0, off_r0 = 0, off_ell = 0, off_scale = 0, off_shift = 0;
+  int ell_width = 5;
+  uint32_t const_bytes = 0;
+  std::vector<unsigned char> blob;  // const part [0, const_bytes) then the temporal-conv images
+};
+
+// `tok` must point at HOST copies of the folded fp32 weights.
+void build_static(const Tokenizer& tok, int pool_tokens, Static* out);
+
+struct Program {
+  bool ok = false;
+  std::string why;
+  Plan plan;                        // table / blob pointers are filled in by whoever uploads (or emulates)
+  std::vector<Mma> mma;
+  std::vector<Group> groups;
+  std::vector<Stage> stages;
+  std::vector<Load> loads;          // Load::src holds a BLOB OFFSET until fix-up
+};
+
+void build_program(const Static& st, int T, int max_smem, Program* out);
+
+// test infrastructure: executes the program on the host (bf16 operands, fp32 accumulate) for B windows.
+// schedule_seed picks the interleaving of the three item sequences; returns false on deadlock / hazard.
+bool emulate(const Static& st, const Program& pr, const float* poses, int64_t B, float* tokens, uint32_t schedule_seed,
+             std::string* err);
+
+}  // namespace t2
+}  // namespace sf

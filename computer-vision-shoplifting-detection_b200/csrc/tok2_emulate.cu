@@ -1,0 +1,402 @@
+// Host emulator of the tokenizer-v2 tile program -- TEST INFRASTRUCTURE, never on a product path.
+//
+// It executes exactly what tokenizer2_kernel executes: the same descriptor table (decoded the way the tensor core
+// decodes no-swizzle K-major / MN-major operands), the same epilogue / prep stages, the same mbarrier waits with the
+// hardware's PARITY semantics (a barrier that runs a phase ahead of a waiter is reported, as it would hang the GPU).
+// The three item sequences and the eight epilogue warps advance in a pseudo-random interleaving chosen by
+// `schedule_seed`; asynchronous items (MMA groups, TMA loads) take effect either at issue or at a later, randomly
+// chosen completion point.  A dependency the builder missed shows up as a result that changes with the seed, a
+// dependency cycle as a reported deadlock.  Used by tests/test_tok2_program.py on GPU-less hosts.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <deque>
+
+#include "tok2_build.h"
+
+namespace sf {
+namespace t2 {
+namespace {
+
+inline uint16_t f2bf(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+inline float bf2f(uint16_t h) {
+  uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+struct Emu {
+  const Static& st;
+  const Program& pr;
+  const Plan& pl;
+  std::vector<unsigned char> smem;
+  std::vector<float> tmem;             // [128][512]
+  std::vector<long> done;              // completions per barrier
+  std::vector<int> arrivals;           // pending arrivals of the E barriers
+  uint64_t rng;
+  Emu(const Static& s, const Program& p, uint32_t seed)
+      : st(s), pr(p), pl(p.plan), smem(p.plan.smem_bytes, 0), tmem(128 * 512, 0.f), done(p.plan.n_bars, 0), arrivals(p.plan.n_bars, 0),
+        rng(seed * 0x9E3779B97F4A7C15ull + 12345) {}
+  uint32_t rnd() {
+    rng ^= rng << 13;
+    rng ^= rng >> 7;
+    rng ^= rng << 17;
+    return (uint32_t)(rng >> 11);
+  }
+  // hardware parity wait: passes iff the barrier's current phase parity differs from `par`
+  // returns 1 pass, 0 not yet, -1 the barrier is a phase AHEAD of this waiter (would hang)
+  int wait(int bar, long need_completions) {
+    if (done[bar] == need_completions) return 1;
+    if (done[bar] < need_completions) return 0;
+    return -1;
+  }
+  float bf_at(uint32_t byte) const {
+    uint16_t h;
+    memcpy(&h, &smem[byte], 2);
+    return bf2f(h);
+  }
+  void mma(const Mma& m) {
+    const uint32_t a_off = (m.a_lo & 0x3FFFu) << 4, a_lbo = ((m.a_lo >> 16) & 0x3FFFu) << 4;
+    const uint32_t b_off = (m.b_lo & 0x3FFFu) << 4, b_lbo = ((m.b_lo >> 16) & 0x3FFFu) << 4;
+    const bool mn = (m.idesc >> 16) & 1u;
+    const int N = (int)((m.idesc >> 17) & 0x3Fu) << 3;
+    const int dcol = (int)(m.d & 0x1FFu);
+    const bool acc = (m.d >> 16) & 1u;
+    std::vector<float> A(128 * 16), Bm((size_t)16 * N);
+    for (int r = 0; r < 128; ++r)
+      for (int k = 0; k < 16; ++k) A[r * 16 + k] = bf_at(a_off + (uint32_t)(k / 8) * a_lbo + (uint32_t)r * 16 + (uint32_t)(k % 8) * 2);
+    for (int k = 0; k < 16; ++k)
+      for (int n = 0; n < N; ++n)
+        Bm[(size_t)k * N + n] = mn ? bf_at(b_off + (uint32_t)(n / 8) * kPlane + (uint32_t)(k / 8) * b_lbo + (uint32_t)(k % 8) * 16 + (uint32_t)(n % 8) * 2)
+                                   : bf_at(b_off + (uint32_t)(k / 8) * b_lbo + (uint32_t)n * 16 + (uint32_t)(k % 8) * 2);
+    for (int r = 0; r < 128; ++r)
+      for (int n = 0; n < N; ++n) {
+        float s = 0.f;
+        for (int k = 0; k < 16; ++k) s += A[r * 16 + k] * Bm[(size_t)k * N + n];
+        float& d = tmem[(size_t)r * 512 + dcol + n];
+        d = acc ? d + s : s;
+      }
+  }
+  void group_effect(int g) {
+    const Group& gr = pr.groups[g];
+    for (int i = gr.first; i < gr.first + gr.count; ++i) mma(pr.mma[i]);
+  }
+  void load_effect(const Load& ld, const float* poses, int64_t B, int64_t tile) {
+    if (ld.kind == LD_WEIGHTS) {
+      memcpy(&smem[ld.dst_off], st.blob.data() + ld.src, ld.bytes);
+    } else {
+      const int64_t w0 = tile * pl.WT;
+      const int64_t nw = std::min<int64_t>(pl.WT, B - w0);
+      memcpy(&smem[pl.off_xin], poses + (size_t)w0 * pl.per_w, (size_t)nw * pl.per_w * 4);
+    }
+  }
+};
+
+uint16_t pack_one(float x, bool relu) {
+  if (relu && !(x > 0.f)) x = 0.f;
+  return f2bf(x);
+}
+
+}  // namespace
+
+bool emulate(const Static& st, const Program& pr, const float* poses, int64_t B, float* tokens, uint32_t seed, std::string* err) {
+  auto fail = [&](const std::string& m) {
+    if (err) *err = m;
+    return false;
+  };
+  if (!st.ok || !pr.ok) return fail("program not built: " + (st.ok ? pr.why : st.why));
+  Emu E(st, pr, seed);
+  const Plan& pl = pr.plan;
+  memcpy(&E.smem[pl.off_const], st.blob.data(), st.const_bytes);
+  // garbage (finite) in the operand regions: stale data must never reach a result
+  for (uint32_t i = pl.off_P; i + 1 < pl.off_mma; i += 2) {
+    const uint16_t h = f2bf((float)((int)(E.rnd() % 2001) - 1000) * 1e-3f);
+    memcpy(&E.smem[i], &h, 2);
+  }
+  for (size_t i = 0; i < E.tmem.size(); ++i) E.tmem[i] = (float)((int)(E.rnd() % 2001) - 1000);
+  const int64_t n_tiles = (B + pl.WT - 1) / pl.WT;
+  if (n_tiles == 0) return true;
+  const int V = pl.V, rows = pl.rows, T0 = pl.T0, tv = T0 * V;
+  const int Tout0 = (T0 - 1) / pl.stride0 + 1;
+  const float* ellf = reinterpret_cast<const float*>(&E.smem[pl.off_ell]);
+  const float* scale = reinterpret_cast<const float*>(&E.smem[pl.off_scale]);
+  const float* shift = reinterpret_cast<const float*>(&E.smem[pl.off_shift]);
+  std::vector<int> poison(128, 0);
+
+  // sequence state
+  struct Pending { int idx; int64_t tile; bool effect_done; };
+  int g_next = 0;
+  int64_t g_it = 0;
+  std::deque<Pending> g_pending;
+  int l_next = 0;
+  int64_t l_it = 0;
+  std::deque<Pending> l_pending;
+  struct WarpState { int e = 0; int64_t it = 0; int sub = 0; };
+  WarpState ws[kEpiWarps];
+  int named_arrived[2] = {0, 0};      // named barrier generations (0: drain, 1: tokens)
+  long named_gen[2] = {0, 0};
+  long warp_gen[kEpiWarps][2] = {{0}};
+  bool store_pending = false;          // bulk store issued, smem not yet read
+  std::vector<float> store_data;
+  int64_t store_tile = 0;
+  int store_nw = 0;
+
+  // prologue: poses of tile 0
+  {
+    Load l0 = pr.loads.back();
+    E.load_effect(l0, poses, B, 0);
+    E.done[pl.bar_l0 + pl.n_loads - 1] = 1;
+  }
+  auto bar_ok = [&](int bar, long need, bool* ahead) {
+    const int w = E.wait(bar, need);
+    if (w < 0) *ahead = true;
+    return w == 1;
+  };
+  const bool eager = seed == 0;
+  long steps = 0;
+  std::string ahead_msg;
+  for (;;) {
+    const bool g_done = g_it >= n_tiles && g_pending.empty();
+    const bool l_done = l_it >= n_tiles && l_pending.empty();
+    bool e_done = true;
+    for (auto& w : ws) e_done &= w.it >= n_tiles;
+    if (g_done && l_done && e_done && !store_pending) break;
+    if (++steps > 50000000) return fail("emulator: step limit");
+    // enumerate runnable actions
+    enum { A_G_ISSUE, A_G_DONE, A_L_ISSUE, A_L_DONE, A_E0, A_STORE = 100 };
+    std::vector<int> acts;
+    bool ahead = false;
+    if (g_it < n_tiles && (int)g_pending.size() < 6) {
+      const Group& gr = pr.groups[g_next];
+      bool ok = true;
+      if (gr.wait_e >= 0) ok &= bar_ok(pl.bar_e0 + gr.wait_e, g_it + 1, &ahead);
+      if (gr.wait_l >= 0) ok &= bar_ok(pl.bar_l0 + gr.wait_l, g_it + 1, &ahead);
+      if (gr.wait_e_prev >= 0 && g_it > 0) ok &= bar_ok(pl.bar_e0 + gr.wait_e_prev, g_it, &ahead);
+      if (ahead) ahead_msg = "G group " + std::to_string(g_next);
+      if (ok) acts.push_back(A_G_ISSUE);
+    }
+    if (!g_pending.empty()) acts.push_back(A_G_DONE);
+    if (l_it < n_tiles && (int)l_pending.size() < 4) {
+      const Load& ld = pr.loads[l_next];
+      bool ok = true, ah = false;
+      if (ld.wait_g >= 0) ok &= bar_ok(pl.bar_g0 + ld.wait_g, l_it + 1, &ah);
+      if (ld.wait_e >= 0) ok &= bar_ok(pl.bar_e0 + ld.wait_e, l_it + 1, &ah);
+      if (ld.wait_g_prev >= 0 && l_it > 0) ok &= bar_ok(pl.bar_g0 + ld.wait_g_prev, l_it, &ah);
+      if (ah) { ahead = true; ahead_msg = "L load " + std::to_string(l_next); }
+      if (ok) acts.push_back(A_L_ISSUE);
+    }
+    if (!l_pending.empty()) acts.push_back(A_L_DONE);
+    for (int w = 0; w < kEpiWarps; ++w) {
+      WarpState& W = ws[w];
+      if (W.it >= n_tiles) continue;
+      const Stage& s = pr.stages[W.e];
+      bool ok = true, ah = false;
+      if (W.sub == 0) {
+        if (s.wait_g >= 0) ok &= bar_ok(pl.bar_g0 + s.wait_g, W.it + 1, &ah);
+        // the pose barrier is one completion ahead of the tile counter (prologue load)
+        if (s.wait_l >= 0) ok &= bar_ok(pl.bar_l0 + s.wait_l, W.it + 1, &ah);
+        if (s.wait_g_prev >= 0 && W.it > 0) ok &= bar_ok(pl.bar_g0 + s.wait_g_prev, W.it, &ah);
+      } else if (W.sub == 1) {
+        ok = named_gen[0] > warp_gen[w][0];       // waiting at the drain barrier
+      } else if (W.sub == 3) {
+        ok = named_gen[1] > warp_gen[w][1];       // waiting at the tokens barrier
+      }
+      if (ah) { ahead = true; ahead_msg = "E stage " + std::to_string(W.e) + " warp " + std::to_string(w); }
+      if (ok) acts.push_back(A_E0 + w);
+    }
+    if (store_pending) acts.push_back(A_STORE);
+    if (ahead) return fail("emulator: a barrier ran a phase ahead of a waiter (" + ahead_msg + "): the GPU would hang");
+    if (acts.empty()) {
+      std::string m = "emulator: deadlock at G " + std::to_string(g_next) + "/it " + std::to_string(g_it) + ", L " + std::to_string(l_next) + ", E";
+      for (auto& w : ws) m += " " + std::to_string(w.e) + "." + std::to_string(w.sub);
+      return fail(m);
+    }
+    const int act = eager ? acts[0] : acts[E.rnd() % acts.size()];
+    if (act == A_G_ISSUE) {
+      // MMAs execute in issue order: a group can only take effect at issue if nothing older is still in flight
+      bool older_in_flight = false;
+      for (const Pending& p : g_pending) older_in_flight |= !p.effect_done;
+      const bool now = eager || (!older_in_flight && (E.rnd() & 1));
+      if (now) E.group_effect(g_next);
+      g_pending.push_back(Pending{g_next, g_it, now});
+      if (++g_next == pl.n_groups) { g_next = 0; ++g_it; }
+    } else if (act == A_G_DONE) {
+      Pending p = g_pending.front();
+      g_pending.pop_front();
+      if (!p.effect_done) E.group_effect(p.idx);
+      E.done[pl.bar_g0 + p.idx]++;
+    } else if (act == A_L_ISSUE) {
+      const Load& ld = pr.loads[l_next];
+      const bool skip = ld.kind == LD_POSES && l_it + 1 >= n_tiles;
+      if (!skip) {
+        const bool now = eager || (E.rnd() & 1);
+        if (now) E.load_effect(ld, poses, B, l_it + 1);
+        l_pending.push_back(Pending{l_next, l_it + 1, now});
+      }
+      if (++l_next == pl.n_loads) { l_next = 0; ++l_it; }
+    } else if (act == A_L_DONE) {
+      Pending p = l_pending.front();
+      l_pending.pop_front();
+      if (!p.effect_done) E.load_effect(pr.loads[p.idx], poses, B, p.tile);
+      E.done[pl.bar_l0 + p.idx]++;
+    } else if (act == A_STORE) {
+      // the bulk store reads the staging area now
+      const float* stg = reinterpret_cast<const float*>(&E.smem[pl.off_stage_tok]);
+      memcpy(tokens + (size_t)store_tile * pl.WT * pl.S_out * pl.d_tok, stg, (size_t)store_nw * pl.S_out * pl.d_tok * 4);
+      store_pending = false;
+    } else {
+      const int w = act - A_E0;
+      WarpState& W = ws[w];
+      const Stage& s = pr.stages[W.e];
+      const int q = w & 3, half = w >> 2;
+      const int64_t tile = W.it;
+      const int nw = (int)std::min<int64_t>(pl.WT, B - tile * pl.WT);
+      const int par = (int)(W.it & 1);
+      auto arrive_named = [&](int which) {
+        warp_gen[w][which] = named_gen[which];
+        if (++named_arrived[which] == kEpiWarps) {
+          named_arrived[which] = 0;
+          named_gen[which]++;
+        }
+      };
+      bool finish = false;
+      if (W.sub == 0 && (s.flags & SF_DRAIN_STORE)) {
+        // thread 0 (warp 0) must see the previous store's reads complete before it arrives
+        if (w == 0 && store_pending) {
+          const float* stg = reinterpret_cast<const float*>(&E.smem[pl.off_stage_tok]);
+          memcpy(tokens + (size_t)store_tile * pl.WT * pl.S_out * pl.d_tok, stg, (size_t)store_nw * pl.S_out * pl.d_tok * 4);
+          store_pending = false;
+        }
+        arrive_named(0);
+        W.sub = 1;
+        continue;
+      }
+      if (W.sub == 0 || W.sub == 1) {
+        // ---- the stage body of this warp
+        if (s.type == ST_CVT) {
+          for (int cg = half; cg < s.n_cg; cg += 2)
+            for (int ln = 0; ln < 32; ++ln) {
+              const int row = q * 32 + ln;
+              for (int j = 0; j < 16; ++j) {
+                float a = E.tmem[(size_t)row * 512 + s.tmem_col + cg * 16 + j];
+                if (s.flags & SF_BIAS) a += reinterpret_cast<const float*>(&E.smem[s.bias_off])[(cg * 16) % s.bias_period + j];
+                const uint16_t h = pack_one(a, s.flags & SF_RELU);
+                const int col = cg * 16 + j;
+                memcpy(&E.smem[s.dst_off + (uint32_t)(col / 8) * kPlane + (uint32_t)row * 16 + (uint32_t)(col % 8) * 2], &h, 2);
+              }
+            }
+        } else if (s.type == ST_PREP) {
+          auto put = [&](uint32_t base, int chunk, int r, const float* m, bool valid) {
+            uint16_t o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            if (valid) {
+              const float hx = bf2f(f2bf(m[0])), hy = bf2f(f2bf(m[1]));
+              o[0] = o[1] = f2bf(hx);
+              o[2] = f2bf(m[0] - hx);
+              o[3] = o[4] = f2bf(hy);
+              o[5] = f2bf(m[1] - hy);
+              o[6] = o[7] = 0x3F80;
+            }
+            memcpy(&E.smem[base + (uint32_t)chunk * kPlane + (uint32_t)r * 16], o, 16);
+          };
+          const float* xin = reinterpret_cast<const float*>(&E.smem[pl.off_xin]);
+          const int nt = s.p1 - s.p0;
+          for (int i = w * 32; i < rows * nt; i += kEpiWarps * 32)
+            for (int ln = 0; ln < 32 && i + ln < rows * nt; ++ln) {
+              const int ii = i + ln, tl = ii / rows, r = ii - tl * rows, t = s.p0 + tl, ww = r / V, v = r - ww * V;
+              float m[2] = {0.f, 0.f};
+              bool bad = false;
+              if (ww < nw) {
+                const float* xp = xin + ww * pl.per_w + t * V + v;
+                for (int k = 0; k < pl.ell_width; ++k) {
+                  const float val = ellf[(size_t)(k * V + v) * 2];
+                  int dl;
+                  memcpy(&dl, &ellf[(size_t)(k * V + v) * 2 + 1], 4);
+                  for (int c = 0; c < pl.c_in; ++c) {
+                    const float xv = xp[c * tv + dl];
+                    bad |= !(std::fabs(xv) <= 3.0e38f);
+                    m[c] = std::fmaf(val, std::fmaf(xv, scale[c * V + v + dl], shift[c * V + v + dl]), m[c]);
+                  }
+                }
+                if (bad) poison[par * 64 + ww] = 1;
+              }
+              put(pl.off_a0, t, r, m, ww < nw && !bad);
+            }
+          if (s.p1 >= T0 && pl.a0_chunks > T0)
+            for (int r = w * 32; r < kRows; r += kEpiWarps * 32)
+              for (int ln = 0; ln < 32 && r + ln < kRows; ++ln) memset(&E.smem[pl.off_a0 + (uint32_t)T0 * kPlane + (uint32_t)(r + ln) * 16], 0, 16);
+          if (s.p2) {
+            for (int i = w * 32; i < rows * Tout0; i += kEpiWarps * 32)
+              for (int ln = 0; ln < 32 && i + ln < rows * Tout0; ++ln) {
+                const int ii = i + ln, tp = ii / rows, r = ii - tp * rows, t = pl.stride0 * tp, ww = r / V, v = r - ww * V;
+                float m[2] = {0.f, 0.f};
+                bool bad = false;
+                if (ww < nw) {
+                  const float* xp = xin + ww * pl.per_w + t * V + v;
+                  for (int c = 0; c < pl.c_in; ++c) {
+                    const float xv = xp[c * tv];
+                    bad |= !(std::fabs(xv) <= 3.0e38f);
+                    m[c] = std::fmaf(xv, scale[c * V + v], shift[c * V + v]);
+                  }
+                  if (bad) poison[par * 64 + ww] = 1;
+                }
+                put(pl.off_a0x, tp, r, m, ww < nw && !bad);
+              }
+            if (pl.a0x_chunks > Tout0)
+              for (int r = w * 32; r < kRows; r += kEpiWarps * 32)
+                for (int ln = 0; ln < 32 && r + ln < kRows; ++ln) memset(&E.smem[pl.off_a0x + (uint32_t)Tout0 * kPlane + (uint32_t)(r + ln) * 16], 0, 16);
+          }
+        } else {   // ST_TOKENS, part 1: staging writes, then the named barrier
+          float* stg = reinterpret_cast<float*>(&E.smem[pl.off_stage_tok]);
+          const float* bp = reinterpret_cast<const float*>(&E.smem[s.bias_off]);
+          for (int cg = half; cg < s.n_cg; cg += 2)
+            for (int ln = 0; ln < 32; ++ln) {
+              const int row = q * 32 + ln, mw = row / V, mv = row - mw * V;
+              if (!(row < rows && mw < nw)) continue;
+              for (int j = 0; j < 16; ++j) {
+                const int col = cg * 16 + j, t = col / pl.cp_last, c = col - t * pl.cp_last;
+                if (c >= pl.c_last) continue;
+                float y = E.tmem[(size_t)row * 512 + s.tmem_col + col] + bp[c];
+                y = y > 0.f ? y : 0.f;
+                if (poison[par * 64 + mw]) y = NAN;
+                stg[(mw * pl.S_out + t) * pl.d_tok + c * V + mv] = y;
+              }
+            }
+          if (w < 2)
+            for (int i = w * 32; i < w * 32 + 32; ++i) poison[(par ^ 1) * 64 + i] = 0;
+          arrive_named(1);
+          W.sub = 3;
+          continue;
+        }
+        finish = true;
+      } else if (W.sub == 3) {
+        if (w == 0) {
+          if (store_pending) return fail("emulator: token staging overwritten while a bulk store is pending");
+          store_pending = true;
+          store_tile = tile;
+          store_nw = nw;
+        }
+        finish = true;
+      }
+      if (finish) {
+        const int bar = pl.bar_e0 + W.e;
+        if (++E.arrivals[bar] == kEpiWarps) {
+          E.arrivals[bar] = 0;
+          E.done[bar]++;
+        }
+        W.sub = 0;
+        if (++W.e == pl.n_stages) { W.e = 0; ++W.it; }
+      }
+    }
+  }
+  return true;
+}
+
+}  // namespace t2
+}  // namespace sf

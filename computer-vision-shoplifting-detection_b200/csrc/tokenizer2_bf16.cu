@@ -1,0 +1,455 @@
+// Tokenizer v2 (bf16 tcgen05 / TMEM): (window, keypoint) rows x (time, channel) columns, see tok2.h.
+//
+// One persistent CTA per SM interprets the tile program built by tok2_build.cu with three specialised roles:
+//   warp 0      MMA issue: walks the G sequence, waits on the mbarriers of the E / L items a group depends on, issues the
+//               group's tcgen05.mma from the descriptor table in shared memory and commits to the group's mbarrier;
+//   warp 1      TMA: per-block temporal-conv weight images (L2 -> smem) and the NEXT tile's poses (HBM -> smem);
+//   warps 4-11  epilogue / prep: block-0 operand preparation from the raw poses (BatchNorm1d fold, adjacency mix, bf16
+//               hi/lo split), TMEM -> (bias, ReLU, bf16) -> shared-memory operand of the next MMA group, and the final
+//               tokens (fp32) staged in shared memory and written by ONE bulk store per tile.
+// Nothing but poses in and tokens out touches HBM; MMA groups of one chunk run under the epilogue of the previous one.
+// Reference maths: shopformer/models/gcae.py:124-154,185-195,242-259,331-366; shopformer_2/models/gcae.py:375-422.
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <mutex>
+
+#include "sf_internal.h"
+#include "tc_common.cuh"
+#include "tok2_build.h"
+
+namespace sf {
+__device__ long long g_tok2_timing[1024];
+__device__ int g_tok2_timing_on = 0;
+namespace {
+
+using namespace tc;
+using namespace t2;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// two fp32 -> packed bf16x2 (lo in the low half), optionally through ReLU
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ uint32_t pack2_relu(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ float bf_hi(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+// A MMA with a 64-bit B descriptor whose high word depends on the operand kind
+__device__ __forceinline__ void issue_mma(uint32_t tmem, const Mma& m, uint32_t base16) {
+  constexpr uint32_t kHiK = (128u >> 4) | (1u << 14);        // SBO = 128 B (next 8 rows), descriptor version 1
+  constexpr uint32_t kHiMN = (kPlane >> 4) | (1u << 14);     // MN-major B: SBO = next 8-column chunk (one plane)
+  const uint64_t ad = ((uint64_t)kHiK << 32) | (uint64_t)(m.a_lo + base16);
+  const uint64_t bd = ((uint64_t)((m.d & (1u << 17)) ? kHiMN : kHiK) << 32) | (uint64_t)(m.b_lo + base16);
+  umma_bf16(tmem + (m.d & 0x1FFu), ad, bd, m.idesc, (m.d >> 16) & 1u);
+}
+
+#define T2_STAMP(id)                                                      \
+  do {                                                                    \
+    if (timing && lane == 0 && stamp_i < stamp_end) {                     \
+      g_tok2_timing[stamp_i++] = (long long)(id);                         \
+      g_tok2_timing[stamp_i++] = clock64();                               \
+    }                                                                     \
+  } while (0)
+
+__global__ void __launch_bounds__(kThreads, 1)
+tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ poses, float* __restrict__ tokens, int64_t B) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint32_t tmem_base_s;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + pl.off_bars);
+  int* poison = reinterpret_cast<int*>(smem + pl.off_flags);                 // [2][64]
+  const int64_t n_tiles = (B + pl.WT - 1) / pl.WT;
+
+  // ------------------------------------------------------------------ one-time setup
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(pl.const_src);
+    uint4* dst = reinterpret_cast<uint4*>(smem + pl.off_const);
+    for (uint32_t i = threadIdx.x; i < pl.const_bytes / 16; i += kThreads) dst[i] = __ldg(src + i);
+    uint4* z = reinterpret_cast<uint4*>(smem + pl.off_P);                   // operand regions start out finite (0 * NaN = NaN)
+    for (uint32_t i = threadIdx.x; i < (pl.off_mma - pl.off_P) / 16; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
+    auto copy_tab = [&](uint32_t off, const void* g, uint32_t bytes) {
+      const uint4* s4 = reinterpret_cast<const uint4*>(g);
+      uint4* d4 = reinterpret_cast<uint4*>(smem + off);
+      for (uint32_t i = threadIdx.x; i < bytes / 16; i += kThreads) d4[i] = __ldg(s4 + i);
+    };
+    copy_tab(pl.off_mma, pl.mma, (uint32_t)pl.n_mma * sizeof(Mma));
+    copy_tab(pl.off_groups, pl.groups, (uint32_t)pl.n_groups * sizeof(Group));
+    copy_tab(pl.off_stages, pl.stages, (uint32_t)pl.n_stages * sizeof(Stage));
+    copy_tab(pl.off_loads, pl.loads, (uint32_t)pl.n_loads * sizeof(Load));
+    if (threadIdx.x < 128) poison[threadIdx.x] = 0;
+  }
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < pl.n_groups; ++i) mbar_init(&bars[pl.bar_g0 + i], 1);
+    for (int i = 0; i < pl.n_stages; ++i) mbar_init(&bars[pl.bar_e0 + i], kEpiWarps);
+    for (int i = 0; i < pl.n_loads; ++i) mbar_init(&bars[pl.bar_l0 + i], 1);
+    fence_mbar_init();
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const bool timing = g_tok2_timing_on && blockIdx.x == 0;
+  int stamp_i = warp == 0 ? 0 : 512;                       // MMA warp: first half of the buffer, epilogue warp 4: second half
+  const int stamp_end = stamp_i + 510;
+  const uint32_t stamp_it = (int64_t)blockIdx.x + gridDim.x < n_tiles ? 1u : 0u;     // steady-state tile when there is one
+
+  if (warp == 0) {
+    // =================================================================== MMA issue
+    const Mma* mtab = reinterpret_cast<const Mma*>(smem + pl.off_mma);
+    const Group* gtab = reinterpret_cast<const Group*>(smem + pl.off_groups);
+    const uint32_t base16 = smem_u32(smem) >> 4;
+    uint32_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t par = it & 1u;
+      for (int g = 0; g < pl.n_groups; ++g) {
+        const Group gr = gtab[g];
+        if (gr.wait_e >= 0) mbar_wait(&bars[pl.bar_e0 + gr.wait_e], par);
+        if (gr.wait_l >= 0) mbar_wait(&bars[pl.bar_l0 + gr.wait_l], par);
+        if (gr.wait_e_prev >= 0 && it > 0) mbar_wait(&bars[pl.bar_e0 + gr.wait_e_prev], par ^ 1u);
+        tc_fence_after();
+        if (timing && it == stamp_it) T2_STAMP(1000 + g);
+        if (elect_one()) {
+          const int end = gr.first + gr.count;
+#pragma unroll 4
+          for (int i = gr.first; i < end; ++i) issue_mma(tmem, mtab[i], base16);
+          umma_commit(&bars[pl.bar_g0 + g]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // =================================================================== TMA
+    if (lane == 0) {
+      const Load* ltab = reinterpret_cast<const Load*>(smem + pl.off_loads);
+      auto pose_load = [&](int64_t tile) {
+        if (tile >= n_tiles) return;
+        const int64_t w0 = tile * pl.WT;
+        const uint32_t nw = (uint32_t)((B - w0) < (int64_t)pl.WT ? (B - w0) : (int64_t)pl.WT);
+        const uint32_t bytes = nw * (uint32_t)pl.per_w * 4u;
+        uint64_t* bar = &bars[pl.bar_l0 + pl.n_loads - 1];
+        mbar_expect_tx(bar, bytes);
+        tma_load_1d(smem + pl.off_xin, poses + (size_t)w0 * pl.per_w, bytes, bar);
+      };
+      pose_load(blockIdx.x);
+      uint32_t it = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const uint32_t par = it & 1u;
+        for (int l = 0; l < pl.n_loads; ++l) {
+          const Load ld = ltab[l];
+          // the pose barrier is one completion ahead (the prologue load): the load of tile n+1 is completion n+1
+          if (ld.wait_g >= 0) mbar_wait(&bars[pl.bar_g0 + ld.wait_g], par);
+          if (ld.wait_e >= 0) mbar_wait(&bars[pl.bar_e0 + ld.wait_e], par);
+          if (ld.wait_g_prev >= 0 && it > 0) mbar_wait(&bars[pl.bar_g0 + ld.wait_g_prev], par ^ 1u);
+          if (ld.kind == LD_WEIGHTS) {
+            uint64_t* bar = &bars[pl.bar_l0 + l];
+            mbar_expect_tx(bar, ld.bytes);
+            tma_load_1d(smem + ld.dst_off, reinterpret_cast<const void*>(ld.src), ld.bytes, bar);
+          } else {
+            pose_load(tile + gridDim.x);
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // =================================================================== epilogue / prep (8 warps)
+    const Stage* stab = reinterpret_cast<const Stage*>(smem + pl.off_stages);
+    const int et = (int)threadIdx.x - 128;                  // 0..255
+    const int q = warp & 3, half = (warp - 4) >> 2;
+    const int row = q * 32 + lane;
+    const int V = pl.V, rows = pl.rows, T0 = pl.T0;
+    const int my_w = row / V, my_v = row - my_w * V;
+    const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+    const float2* ell = reinterpret_cast<const float2*>(smem + pl.off_ell);
+    const float* scale = reinterpret_cast<const float*>(smem + pl.off_scale);
+    const float* shift = reinterpret_cast<const float*>(smem + pl.off_shift);
+    const float* xin = reinterpret_cast<const float*>(smem + pl.off_xin);
+    const int tv = T0 * V;
+    const int Tout0 = (T0 - 1) / pl.stride0 + 1;
+    uint32_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t par = it & 1u;
+      const int64_t w_first = tile * pl.WT;
+      const int nw = (int)((B - w_first) < (int64_t)pl.WT ? (B - w_first) : (int64_t)pl.WT);
+      int* pz = poison + par * 64;
+      for (int e = 0; e < pl.n_stages; ++e) {
+        const Stage s = stab[e];
+        if (s.wait_g >= 0) mbar_wait(&bars[pl.bar_g0 + s.wait_g], par);
+        if (s.wait_l >= 0) mbar_wait(&bars[pl.bar_l0 + s.wait_l], par);
+        if (s.wait_g_prev >= 0 && it > 0) mbar_wait(&bars[pl.bar_g0 + s.wait_g_prev], par ^ 1u);
+        tc_fence_after();
+        if (timing && it == stamp_it && warp == 4) T2_STAMP(2000 + e);
+        if (s.flags & SF_DRAIN_STORE) {
+          if (et == 0) bulk_wait_read();
+          named_bar_sync(1, kEpiWarps * 32);
+        }
+        if (s.type == ST_CVT) {
+          const bool relu = s.flags & SF_RELU, bias = s.flags & SF_BIAS;
+          const float* bp = reinterpret_cast<const float*>(smem + s.bias_off);
+          unsigned char* dst = smem + s.dst_off + (size_t)row * 16;
+          for (int cg = half; cg < (int)s.n_cg; cg += 2) {
+            float a[16];
+            tmem_ld16(lane_base + (uint32_t)(s.tmem_col + cg * 16), a);
+            tmem_ld_wait();
+            if (bias) {
+              const float* b16 = bp + (cg * 16) % s.bias_period;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float4 bb = *reinterpret_cast<const float4*>(b16 + 4 * j);
+                a[4 * j + 0] += bb.x; a[4 * j + 1] += bb.y; a[4 * j + 2] += bb.z; a[4 * j + 3] += bb.w;
+              }
+            }
+            uint4 o0, o1;
+            if (relu) {
+              o0 = make_uint4(pack2_relu(a[0], a[1]), pack2_relu(a[2], a[3]), pack2_relu(a[4], a[5]), pack2_relu(a[6], a[7]));
+              o1 = make_uint4(pack2_relu(a[8], a[9]), pack2_relu(a[10], a[11]), pack2_relu(a[12], a[13]), pack2_relu(a[14], a[15]));
+            } else {
+              o0 = make_uint4(pack2(a[0], a[1]), pack2(a[2], a[3]), pack2(a[4], a[5]), pack2(a[6], a[7]));
+              o1 = make_uint4(pack2(a[8], a[9]), pack2(a[10], a[11]), pack2(a[12], a[13]), pack2(a[14], a[15]));
+            }
+            *reinterpret_cast<uint4*>(dst + (size_t)(2 * cg) * kPlane) = o0;
+            *reinterpret_cast<uint4*>(dst + (size_t)(2 * cg + 1) * kPlane) = o1;
+          }
+        } else if (s.type == ST_PREP) {
+          // A0 chunk t, row (w, v): [hi(mx), hi(mx), lo(mx), hi(my), hi(my), lo(my), 1, 1] of the adjacency-mixed, BatchNorm-folded
+          // pose; A0x chunk t' the same of the un-mixed pose at time stride * t' (operand of the residual conv)
+          const int nt = (int)s.p1 - (int)s.p0;
+          for (int i = et; i < rows * nt; i += kEpiWarps * 32) {
+            const int tl = i / rows, r = i - tl * rows, t = (int)s.p0 + tl;
+            const int w = r / V, v = r - w * V;
+            uint4 o = make_uint4(0, 0, 0, 0);
+            if (w < nw) {
+              const float* xp = xin + w * pl.per_w + t * V + v;
+              float m[2] = {0.f, 0.f};
+              bool bad = false;
+              for (int k = 0; k < pl.ell_width; ++k) {
+                const float2 e2 = ell[k * V + v];
+                const int dl = __float_as_int(e2.y);
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+                  if (c < pl.c_in) {
+                    const float xv = xp[c * tv + dl];
+                    bad |= !(fabsf(xv) <= 3.0e38f);
+                    m[c] = fmaf(e2.x, fmaf(xv, scale[c * V + v + dl], shift[c * V + v + dl]), m[c]);
+                  }
+              }
+              if (bad) {
+                atomicOr(&pz[w], 1);
+              } else {
+                const float hx = bf_hi(m[0]), hy = bf_hi(m[1]);
+                o = make_uint4(pack2(hx, hx), pack2(m[0] - hx, hy), pack2(hy, m[1] - hy), 0x3F803F80u);
+              }
+            }
+            *reinterpret_cast<uint4*>(smem + pl.off_a0 + (size_t)t * kPlane + (size_t)r * 16) = o;
+          }
+          if ((int)s.p1 >= T0 && pl.a0_chunks > T0)
+            for (int r = et; r < kRows; r += kEpiWarps * 32)
+              *reinterpret_cast<uint4*>(smem + pl.off_a0 + (size_t)T0 * kPlane + (size_t)r * 16) = make_uint4(0, 0, 0, 0);
+          if (s.p2) {
+            for (int i = et; i < rows * Tout0; i += kEpiWarps * 32) {
+              const int tp = i / rows, r = i - tp * rows, t = pl.stride0 * tp;
+              const int w = r / V, v = r - w * V;
+              uint4 o = make_uint4(0, 0, 0, 0);
+              if (w < nw) {
+                const float* xp = xin + w * pl.per_w + t * V + v;
+                float m[2] = {0.f, 0.f};
+                bool bad = false;
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+                  if (c < pl.c_in) {
+                    const float xv = xp[c * tv];
+                    bad |= !(fabsf(xv) <= 3.0e38f);
+                    m[c] = fmaf(xv, scale[c * V + v], shift[c * V + v]);
+                  }
+                if (bad) {
+                  atomicOr(&pz[w], 1);
+                } else {
+                  const float hx = bf_hi(m[0]), hy = bf_hi(m[1]);
+                  o = make_uint4(pack2(hx, hx), pack2(m[0] - hx, hy), pack2(hy, m[1] - hy), 0x3F803F80u);
+                }
+              }
+              *reinterpret_cast<uint4*>(smem + pl.off_a0x + (size_t)tp * kPlane + (size_t)r * 16) = o;
+            }
+            if (pl.a0x_chunks > Tout0)
+              for (int r = et; r < kRows; r += kEpiWarps * 32)
+                *reinterpret_cast<uint4*>(smem + pl.off_a0x + (size_t)Tout0 * kPlane + (size_t)r * 16) = make_uint4(0, 0, 0, 0);
+          }
+        } else {   // ST_TOKENS
+          const float* bp = reinterpret_cast<const float*>(smem + s.bias_off);
+          float* stg = reinterpret_cast<float*>(smem + pl.off_stage_tok);
+          const bool live = row < rows && my_w < nw;
+          const bool poisoned = live && pz[my_w] != 0;
+          for (int cg = half; cg < (int)s.n_cg; cg += 2) {
+            float a[16];
+            tmem_ld16(lane_base + (uint32_t)(s.tmem_col + cg * 16), a);
+            tmem_ld_wait();
+            if (live) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const int col = cg * 16 + j, t = col / pl.cp_last, c = col - t * pl.cp_last;
+                if (c < pl.c_last) {
+                  float y = fmaxf(a[j] + bp[c], 0.f);
+                  if (poisoned) y = __int_as_float(0x7fc00000);
+                  stg[(my_w * pl.S_out + t) * pl.d_tok + c * V + my_v] = y;
+                }
+              }
+            }
+          }
+          if (et < 64) poison[(par ^ 1u) * 64 + et] = 0;           // the next tile's flags
+          fence_proxy_async();
+          named_bar_sync(1, kEpiWarps * 32);
+          if (et == 0)
+            bulk_store(tokens + (size_t)w_first * pl.S_out * pl.d_tok, stg, (uint32_t)nw * (uint32_t)(pl.S_out * pl.d_tok) * 4u);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[pl.bar_e0 + e]);
+      }
+    }
+    if (et == 0) bulk_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// ---- per-model cache of uploaded programs (one per window length)
+struct Uploaded {
+  Program prog;
+  void* dev = nullptr;
+};
+struct Cache {
+  std::mutex mu;
+  std::map<int, Uploaded*> by_T;
+};
+
+}  // namespace
+
+struct Tok2State {
+  t2::Static st;
+  unsigned char* blob_dev = nullptr;
+  Cache cache;
+};
+
+Tok2State* tok2_create(const Tokenizer& host_tok, int pool_tokens, bool upload) {
+  Tok2State* s = new Tok2State();
+  t2::build_static(host_tok, pool_tokens, &s->st);
+  if (s->st.ok && upload) {
+    if (cudaMalloc((void**)&s->blob_dev, s->st.blob.size()) != cudaSuccess ||
+        cudaMemcpy(s->blob_dev, s->st.blob.data(), s->st.blob.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+      cudaGetLastError();
+      s->st.ok = false;
+      s->st.why = "uploading the operand images failed";
+    }
+  }
+  return s;
+}
+
+void tok2_destroy(Tok2State* s) {
+  if (!s) return;
+  for (auto& kv : s->cache.by_T) {
+    if (kv.second->dev) cudaFree(kv.second->dev);
+    delete kv.second;
+  }
+  if (s->blob_dev) cudaFree(s->blob_dev);
+  delete s;
+}
+
+const t2::Static* tok2_static(const Tok2State* s) { return s ? &s->st : nullptr; }
+
+static Uploaded* tok2_program(const sf_model* m, int T) {
+  Tok2State* s = m->tok2;
+  if (!s || !s->st.ok || !s->blob_dev) return nullptr;
+  std::lock_guard<std::mutex> lk(s->cache.mu);
+  auto it = s->cache.by_T.find(T);
+  if (it != s->cache.by_T.end()) return it->second;
+  Uploaded* u = new Uploaded();
+  t2::build_program(s->st, T, m->max_smem_optin - 2304, &u->prog);   // minus the kernel's static shared memory
+  if (u->prog.ok) {
+    Program& p = u->prog;
+    for (Load& l : p.loads)
+      if (l.kind == LD_WEIGHTS) l.src = (uint64_t)(uintptr_t)(s->blob_dev + l.src);
+    const size_t b0 = p.mma.size() * sizeof(Mma), b1 = p.groups.size() * sizeof(Group), b2 = p.stages.size() * sizeof(Stage),
+                 b3 = p.loads.size() * sizeof(Load);
+    auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
+    const size_t o1 = up(b0), o2 = o1 + up(b1), o3 = o2 + up(b2), total = o3 + up(b3);
+    std::vector<unsigned char> host(total, 0);
+    memcpy(host.data(), p.mma.data(), b0);
+    memcpy(host.data() + o1, p.groups.data(), b1);
+    memcpy(host.data() + o2, p.stages.data(), b2);
+    memcpy(host.data() + o3, p.loads.data(), b3);
+    if (cudaMalloc(&u->dev, total) != cudaSuccess || cudaMemcpy(u->dev, host.data(), total, cudaMemcpyHostToDevice) != cudaSuccess) {
+      cudaGetLastError();
+      p.ok = false;
+      p.why = "uploading the tile program failed";
+    } else {
+      unsigned char* d = (unsigned char*)u->dev;
+      p.plan.mma = (const Mma*)d;
+      p.plan.groups = (const Group*)(d + o1);
+      p.plan.stages = (const Stage*)(d + o2);
+      p.plan.loads = (const Load*)(d + o3);
+      p.plan.const_src = s->blob_dev;
+    }
+  }
+  s->cache.by_T[T] = u;
+  return u;
+}
+
+bool tokenizer2_supported(const sf_model* m, int T) {
+  if (getenv("SF_TOK2_OFF")) return false;
+  Uploaded* u = tok2_program(m, T);
+  return u && u->prog.ok;
+}
+
+const char* tokenizer2_why(const sf_model* m, int T) {
+  if (!m->tok2) return "no tokenizer-v2 state";
+  if (!m->tok2->st.ok) return m->tok2->st.why.c_str();
+  Uploaded* u = tok2_program(m, T);
+  return u ? u->prog.why.c_str() : "";
+}
+
+int launch_tokenizer2(const sf_model* m, const float* poses, int64_t B, int T, float* tokens, cudaStream_t st) {
+  if (B == 0) return SF_OK;
+  Uploaded* u = tok2_program(m, T);
+  SF_REQUIRE(u && u->prog.ok, SF_E_UNSUPPORTED, "tokenizer v2 does not cover this shape: %s", tokenizer2_why(m, T));
+  SF_REQUIRE(((uintptr_t)poses & 15) == 0 && ((uintptr_t)tokens & 15) == 0, SF_E_INVALID,
+             "pose / token buffers must be 16-byte aligned (TMA bulk copies)");
+  const Plan& pl = u->prog.plan;
+  const int64_t n_tiles = (B + pl.WT - 1) / pl.WT;
+  const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)m->sm_count);
+  SF_CUDA_OK(cudaFuncSetAttribute(tokenizer2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
+  tokenizer2_kernel<<<grid, kThreads, pl.smem_bytes, st>>>(pl, poses, tokens, B);
+  SF_CUDA_OK(cudaGetLastError());
+  return SF_OK;
+}
+
+}  // namespace sf
+
+// debugging aid (not part of the C ABI): stage / group start stamps of CTA 0's second tile, pairs of (id, clock64)
+extern "C" int sfdbg_tokenizer2_timing(int enable, long long* out_host, int n) {
+  int on = enable;
+  if (cudaMemcpyToSymbol(sf::g_tok2_timing_on, &on, sizeof(int)) != cudaSuccess) return -1;
+  if (out_host && n > 0) {
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    if (cudaMemcpyFromSymbol(out_host, sf::g_tok2_timing, sizeof(long long) * (n < 1024 ? n : 1024)) != cudaSuccess) return -1;
+  }
+  return 0;
+}

@@ -1,0 +1,35 @@
+"""Group / stage start stamps of CTA 0's second tile of tokenizer v2 (debug aid): python profiles/tok2_timing.py
+MMA warp: one stamp per G group just before its MMAs are issued (id 1000 + g); epilogue warp 4: one stamp per E stage
+after its waits (id 2000 + e).  Prints both timelines relative to the first stamp, cycles @ SM clock."""
+import ctypes as C, sys
+sys.path.insert(0, "."); sys.path.insert(0, "computer-vision-shoplifting-detection_b200")
+import numpy as np, torch
+import bench
+from shopformer_b200 import native as N
+from shopformer_b200.synthetic import synth_windows
+lib = N.load()
+model = bench.build_model("A").cuda()
+eng = model._sf_engine()
+x = torch.from_numpy(synth_windows(65536, 24, 17, seed=1)[0]).cuda()
+eng.tokenize(x, precision="bf16"); torch.cuda.synchronize()
+lib.sfdbg_tokenizer2_timing(1, None, 0)
+eng.tokenize(x, precision="bf16"); torch.cuda.synchronize()
+buf = (C.c_longlong * 1024)()
+lib.sfdbg_tokenizer2_timing(0, buf, 1024)
+a = np.array(buf[:]).reshape(-1, 2)
+g = a[:256][(a[:256, 0] >= 1000) & (a[:256, 0] < 2000)]
+e = a[256:][(a[256:, 0] >= 2000) & (a[256:, 0] < 3000)]
+if len(g) == 0:
+    raise SystemExit("no stamps (tokenizer v2 not used for this shape?)")
+t0 = min(g[0, 1], e[0, 1])
+print("MMA groups (id, start, delta to previous):")
+prev = g[0, 1]
+for i, t in g:
+    print(f"  G{i-1000:3d}  @{t-t0:7d}  +{t-prev:6d}")
+    prev = t
+print("epilogue stages (warp 4):")
+prev = e[0, 1]
+for i, t in e:
+    print(f"  E{i-2000:3d}  @{t-t0:7d}  +{t-prev:6d}")
+    prev = t
+print("tile span (G first -> last stamp):", g[-1, 1] - g[0, 1], " E:", e[-1, 1] - e[0, 1])
