@@ -80,7 +80,8 @@ struct Plan {                // kernel parameter (by value)
   // shared-memory map (byte offsets from the dynamic smem base)
   uint32_t off_const, off_P, off_Q, off_W, off_mma, off_groups, off_stages, off_loads, off_bars, off_flags;
   uint32_t off_xin, off_a0, off_a0x, off_stage_tok;
-  uint32_t off_ell, off_scale, off_shift;       // inside the const blob: ELL (value, delta) [5|8][V], BN1d scale/shift
+  uint32_t off_ell, off_hc, off_scale, off_shift;   // const blob: mix coefficients float4 (A_hat*scale_x, A_hat*scale_y, row delta, 0) [5|8][V],
+                                                   // float2 [V] mixed BN shifts, BN1d scale / shift [c_in][V]
   int ell_width;
   int a0_chunks, a0x_chunks, stride0;
   int bar_g0, bar_e0, bar_l0, n_bars;           // barrier index bases

@@ -141,21 +141,33 @@ void build_static(const Tokenizer& tok, int pool_tokens, Static* out) {
     }
   }
   {
-    // prep tables: block-0 adjacency as ELL [k][V] (value, row delta), folded BatchNorm1d
+    // prep tables: block-0 adjacency row of keypoint v with the BatchNorm1d scale folded in -- float4 [k][V] =
+    // (A_hat[v][u] * scale_x[u], A_hat[v][u] * scale_y[u], row delta u - v, 0) -- the mixed shifts float2 [V] =
+    // sum_u A_hat[v][u] * shift_c[u], and the plain scale / shift for the un-mixed residual operand
     const TokBlock& t0 = tok.blk[0];
     s.ell_width = t0.ell_width <= 5 ? 5 : 8;
-    s.off_ell = bl.alloc((size_t)s.ell_width * V * 8);
-    for (int k = 0; k < s.ell_width; ++k)
-      for (int v = 0; v < V; ++v) {
+    s.off_ell = bl.alloc((size_t)s.ell_width * V * 16);
+    s.off_hc = bl.alloc((size_t)V * 8);
+    for (int v = 0; v < V; ++v) {
+      float h[2] = {0.f, 0.f};
+      for (int k = 0; k < s.ell_width; ++k) {
         float val = 0.f;
         int dl = 0;
         if (k < t0.ell_width) {
           val = t0.ell_val[v * t0.ell_width + k];
           dl = val != 0.f ? t0.ell_col[v * t0.ell_width + k] - v : 0;
         }
-        bl.f32(s.off_ell)[(size_t)(k * V + v) * 2] = val;
-        memcpy(&bl.f32(s.off_ell)[(size_t)(k * V + v) * 2 + 1], &dl, 4);
+        float* e = bl.f32(s.off_ell) + (size_t)(k * V + v) * 4;
+        for (int c = 0; c < 2; ++c) {
+          e[c] = c < tok.c_in ? val * tok.in_scale[c * V + v + dl] : 0.f;
+          if (c < tok.c_in) h[c] = std::fmaf(val, tok.in_shift[c * V + v + dl], h[c]);
+        }
+        memcpy(&e[2], &dl, 4);
+        e[3] = 0.f;
       }
+      bl.f32(s.off_hc)[v * 2] = h[0];
+      bl.f32(s.off_hc)[v * 2 + 1] = h[1];
+    }
     s.off_scale = bl.alloc((size_t)tok.c_in * V * 4);
     s.off_shift = bl.alloc((size_t)tok.c_in * V * 4);
     memcpy(bl.f32(s.off_scale), tok.in_scale, sizeof(float) * tok.c_in * V);
@@ -303,6 +315,7 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
   pl.off_Q = off; off += Q_size;
   pl.off_W = off; off += up128(W_size);
   pl.off_ell = pl.off_const + st.off_ell;
+  pl.off_hc = pl.off_const + st.off_hc;
   pl.off_scale = pl.off_const + st.off_scale;
   pl.off_shift = pl.off_const + st.off_shift;
   pl.off_a0 = pl.off_P;
@@ -593,6 +606,25 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
     } else {
       pr.loads[x.idx].wait_g = (int16_t)w[0];
       pr.loads[x.idx].wait_e = (int16_t)w[1];
+    }
+  }
+  // a wait that an earlier item of the same sequence already performed (or implied: E stages and G commits complete in
+  // order) is dropped -- most groups then issue without touching a barrier
+  {
+    int seen_e = -1;
+    std::vector<char> seen_l(pr.loads.size(), 0);
+    for (Group& g : pr.groups) {
+      if (g.wait_e >= 0 && g.wait_e <= seen_e) g.wait_e = -1;
+      seen_e = std::max(seen_e, (int)g.wait_e);
+      if (g.wait_l >= 0) {
+        if (seen_l[g.wait_l]) g.wait_l = -1;
+        else seen_l[g.wait_l] = 1;
+      }
+    }
+    int seen_g = -1;
+    for (Stage& s : pr.stages) {
+      if (s.wait_g >= 0 && s.wait_g <= seen_g) s.wait_g = -1;
+      seen_g = std::max(seen_g, (int)s.wait_g);
     }
   }
   // tile boundary: the first prep stage overwrites the operand regions the previous tile's last MMAs read, the first

@@ -125,7 +125,6 @@ bool emulate(const Static& st, const Program& pr, const float* poses, int64_t B,
   if (n_tiles == 0) return true;
   const int V = pl.V, rows = pl.rows, T0 = pl.T0, tv = T0 * V;
   const int Tout0 = (T0 - 1) / pl.stride0 + 1;
-  const float* ellf = reinterpret_cast<const float*>(&E.smem[pl.off_ell]);
   const float* scale = reinterpret_cast<const float*>(&E.smem[pl.off_scale]);
   const float* shift = reinterpret_cast<const float*>(&E.smem[pl.off_shift]);
   std::vector<int> poison(128, 0);
@@ -306,51 +305,47 @@ bool emulate(const Static& st, const Program& pr, const float* poses, int64_t B,
             memcpy(&E.smem[base + (uint32_t)chunk * kPlane + (uint32_t)r * 16], o, 16);
           };
           const float* xin = reinterpret_cast<const float*>(&E.smem[pl.off_xin]);
-          const int nt = s.p1 - s.p0;
-          for (int i = w * 32; i < rows * nt; i += kEpiWarps * 32)
-            for (int ln = 0; ln < 32 && i + ln < rows * nt; ++ln) {
-              const int ii = i + ln, tl = ii / rows, r = ii - tl * rows, t = s.p0 + tl, ww = r / V, v = r - ww * V;
+          const float* coef = reinterpret_cast<const float*>(&E.smem[pl.off_ell]);
+          const float* hcs = reinterpret_cast<const float*>(&E.smem[pl.off_hc]);
+          // thread = (row, time parity `half`), as in the kernel
+          for (int ln = 0; ln < 32; ++ln) {
+            const int row = q * 32 + ln, ww = row / V, v = row - ww * V;
+            const bool valid = row < rows && ww < nw;
+            bool bad = false;
+            const float* xw = xin + ww * pl.per_w + v;
+            for (int t = s.p0 + half; t < s.p1; t += 2) {
               float m[2] = {0.f, 0.f};
-              bool bad = false;
-              if (ww < nw) {
-                const float* xp = xin + ww * pl.per_w + t * V + v;
+              if (valid) {
+                m[0] = hcs[v * 2];
+                m[1] = hcs[v * 2 + 1];
                 for (int k = 0; k < pl.ell_width; ++k) {
-                  const float val = ellf[(size_t)(k * V + v) * 2];
+                  const float* e = coef + (size_t)(k * V + v) * 4;
                   int dl;
-                  memcpy(&dl, &ellf[(size_t)(k * V + v) * 2 + 1], 4);
+                  memcpy(&dl, &e[2], 4);
                   for (int c = 0; c < pl.c_in; ++c) {
-                    const float xv = xp[c * tv + dl];
+                    const float xv = xw[t * V + c * tv + dl];
                     bad |= !(std::fabs(xv) <= 3.0e38f);
-                    m[c] = std::fmaf(val, std::fmaf(xv, scale[c * V + v + dl], shift[c * V + v + dl]), m[c]);
+                    m[c] = std::fmaf(e[c], xv, m[c]);
                   }
                 }
-                if (bad) poison[par * 64 + ww] = 1;
               }
-              put(pl.off_a0, t, r, m, ww < nw && !bad);
+              put(pl.off_a0, t, row, m, valid);
             }
-          if (s.p1 >= T0 && pl.a0_chunks > T0)
-            for (int r = w * 32; r < kRows; r += kEpiWarps * 32)
-              for (int ln = 0; ln < 32 && r + ln < kRows; ++ln) memset(&E.smem[pl.off_a0 + (uint32_t)T0 * kPlane + (uint32_t)(r + ln) * 16], 0, 16);
-          if (s.p2) {
-            for (int i = w * 32; i < rows * Tout0; i += kEpiWarps * 32)
-              for (int ln = 0; ln < 32 && i + ln < rows * Tout0; ++ln) {
-                const int ii = i + ln, tp = ii / rows, r = ii - tp * rows, t = pl.stride0 * tp, ww = r / V, v = r - ww * V;
+            if (s.p1 > s.p0 && s.p1 >= T0 && pl.a0_chunks > T0 && half == 0) memset(&E.smem[pl.off_a0 + (uint32_t)T0 * kPlane + (uint32_t)row * 16], 0, 16);
+            if (s.p2) {
+              for (int tp = half; tp < Tout0; tp += 2) {
                 float m[2] = {0.f, 0.f};
-                bool bad = false;
-                if (ww < nw) {
-                  const float* xp = xin + ww * pl.per_w + t * V + v;
+                if (valid)
                   for (int c = 0; c < pl.c_in; ++c) {
-                    const float xv = xp[c * tv];
+                    const float xv = xw[pl.stride0 * tp * V + c * tv];
                     bad |= !(std::fabs(xv) <= 3.0e38f);
                     m[c] = std::fmaf(xv, scale[c * V + v], shift[c * V + v]);
                   }
-                  if (bad) poison[par * 64 + ww] = 1;
-                }
-                put(pl.off_a0x, tp, r, m, ww < nw && !bad);
+                put(pl.off_a0x, tp, row, m, valid);
               }
-            if (pl.a0x_chunks > Tout0)
-              for (int r = w * 32; r < kRows; r += kEpiWarps * 32)
-                for (int ln = 0; ln < 32 && r + ln < kRows; ++ln) memset(&E.smem[pl.off_a0x + (uint32_t)Tout0 * kPlane + (uint32_t)(r + ln) * 16], 0, 16);
+              if (pl.a0x_chunks > Tout0 && half == 0) memset(&E.smem[pl.off_a0x + (uint32_t)Tout0 * kPlane + (uint32_t)row * 16], 0, 16);
+            }
+            if (bad) poison[par * 64 + ww] = 1;
           }
         } else {   // ST_TOKENS, part 1: staging writes, then the named barrier
           float* stg = reinterpret_cast<float*>(&E.smem[pl.off_stage_tok]);

@@ -58,6 +58,82 @@ __device__ __forceinline__ void issue_mma(uint32_t tmem, const Mma& m, uint32_t 
   umma_bf16(tmem + (m.d & 0x1FFu), ad, bd, m.idesc, (m.d >> 16) & 1u);
 }
 
+// Block-0 operand preparation of one prep stage for one thread (see the ST_PREP case).
+template <int KW>
+__device__ __forceinline__ void prep_stage(const Plan& pl, const Stage& s, unsigned char* smem, int row, int half, int my_w, int my_v,
+                                           int nw, int* pz) {
+  const int V = pl.V, T0 = pl.T0, tv = T0 * V;
+  const bool valid = row < pl.rows && my_w < nw;
+  const float* xw = reinterpret_cast<const float*>(smem + pl.off_xin) + my_w * pl.per_w + my_v;
+  const bool two = pl.c_in > 1;
+  bool bad = false;
+  if ((int)s.p1 > (int)s.p0) {
+    float4 cf[KW];
+    float2 hc = make_float2(0.f, 0.f);
+    if (valid) {
+      const float4* coef = reinterpret_cast<const float4*>(smem + pl.off_ell);
+#pragma unroll
+      for (int k = 0; k < KW; ++k) cf[k] = coef[k * V + my_v];
+      hc = reinterpret_cast<const float2*>(smem + pl.off_hc)[my_v];
+    }
+    for (int t = (int)s.p0 + half; t < (int)s.p1; t += 2) {
+      uint4 o = make_uint4(0, 0, 0, 0);
+      if (valid) {
+        const float* xp = xw + t * V;
+        float x0[KW], x1[KW];
+#pragma unroll
+        for (int k = 0; k < KW; ++k) {
+          const int dl = __float_as_int(cf[k].z);
+          x0[k] = xp[dl];
+          x1[k] = two ? xp[tv + dl] : 0.f;
+        }
+        float m0 = hc.x, m1 = hc.y;
+#pragma unroll
+        for (int k = 0; k < KW; ++k) {
+          bad |= !(fabsf(x0[k]) <= 3.0e38f) | !(fabsf(x1[k]) <= 3.0e38f);
+          m0 = fmaf(cf[k].x, x0[k], m0);
+          m1 = fmaf(cf[k].y, x1[k], m1);
+        }
+        const float hx = bf_hi(m0), hy = bf_hi(m1);
+        o = make_uint4(pack2(hx, hx), pack2(m0 - hx, hy), pack2(hy, m1 - hy), 0x3F803F80u);
+      }
+      *reinterpret_cast<uint4*>(smem + pl.off_a0 + (size_t)t * kPlane + (size_t)row * 16) = o;
+    }
+    if ((int)s.p1 >= T0 && pl.a0_chunks > T0 && half == 0)
+      *reinterpret_cast<uint4*>(smem + pl.off_a0 + (size_t)T0 * kPlane + (size_t)row * 16) = make_uint4(0, 0, 0, 0);
+  }
+  if (s.p2) {
+    const int Tout0 = (T0 - 1) / pl.stride0 + 1;
+    float sc0 = 0.f, sh0 = 0.f, sc1 = 0.f, sh1 = 0.f;
+    if (valid) {
+      const float* scale = reinterpret_cast<const float*>(smem + pl.off_scale);
+      const float* shift = reinterpret_cast<const float*>(smem + pl.off_shift);
+      sc0 = scale[my_v];
+      sh0 = shift[my_v];
+      if (two) {
+        sc1 = scale[V + my_v];
+        sh1 = shift[V + my_v];
+      }
+    }
+    for (int tp = half; tp < Tout0; tp += 2) {
+      uint4 o = make_uint4(0, 0, 0, 0);
+      if (valid) {
+        const float* xp = xw + pl.stride0 * tp * V;
+        const float xa = xp[0], xb = two ? xp[tv] : 0.f;
+        bad |= !(fabsf(xa) <= 3.0e38f) | !(fabsf(xb) <= 3.0e38f);
+        const float m0 = fmaf(xa, sc0, sh0), m1 = fmaf(xb, sc1, sh1);
+        const float hx = bf_hi(m0), hy = bf_hi(m1);
+        o = make_uint4(pack2(hx, hx), pack2(m0 - hx, hy), pack2(hy, m1 - hy), 0x3F803F80u);
+      }
+      *reinterpret_cast<uint4*>(smem + pl.off_a0x + (size_t)tp * kPlane + (size_t)row * 16) = o;
+    }
+    if (pl.a0x_chunks > Tout0 && half == 0)
+      *reinterpret_cast<uint4*>(smem + pl.off_a0x + (size_t)Tout0 * kPlane + (size_t)row * 16) = make_uint4(0, 0, 0, 0);
+  }
+  // a window with a non-finite pose is reported as NaN tokens (the mix MMA would otherwise spread it over the tile)
+  if (bad) atomicOr(&pz[my_w], 1);
+}
+
 #define T2_STAMP(id)                                                      \
   do {                                                                    \
     if (timing && lane == 0 && stamp_i < stamp_end) {                     \
@@ -127,9 +203,16 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
         tc_fence_after();
         if (timing && it == stamp_it) T2_STAMP(1000 + g);
         if (elect_one()) {
+          // table entries are loaded four at a time BEFORE the (volatile, memory-clobbering) MMA instructions, so the
+          // shared-memory latency is paid once per four MMAs instead of once per MMA
           const int end = gr.first + gr.count;
-#pragma unroll 4
-          for (int i = gr.first; i < end; ++i) issue_mma(tmem, mtab[i], base16);
+          for (int i = gr.first; i < end; i += 4) {
+            const Mma e0 = mtab[i], e1 = mtab[min(i + 1, end - 1)], e2 = mtab[min(i + 2, end - 1)], e3 = mtab[min(i + 3, end - 1)];
+            issue_mma(tmem, e0, base16);
+            if (i + 1 < end) issue_mma(tmem, e1, base16);
+            if (i + 2 < end) issue_mma(tmem, e2, base16);
+            if (i + 3 < end) issue_mma(tmem, e3, base16);
+          }
           umma_commit(&bars[pl.bar_g0 + g]);
         }
         __syncwarp();
@@ -174,15 +257,9 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
     const int et = (int)threadIdx.x - 128;                  // 0..255
     const int q = warp & 3, half = (warp - 4) >> 2;
     const int row = q * 32 + lane;
-    const int V = pl.V, rows = pl.rows, T0 = pl.T0;
+    const int V = pl.V, rows = pl.rows;
     const int my_w = row / V, my_v = row - my_w * V;
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
-    const float2* ell = reinterpret_cast<const float2*>(smem + pl.off_ell);
-    const float* scale = reinterpret_cast<const float*>(smem + pl.off_scale);
-    const float* shift = reinterpret_cast<const float*>(smem + pl.off_shift);
-    const float* xin = reinterpret_cast<const float*>(smem + pl.off_xin);
-    const int tv = T0 * V;
-    const int Tout0 = (T0 - 1) / pl.stride0 + 1;
     uint32_t it = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const uint32_t par = it & 1u;
@@ -204,93 +281,44 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
           const bool relu = s.flags & SF_RELU, bias = s.flags & SF_BIAS;
           const float* bp = reinterpret_cast<const float*>(smem + s.bias_off);
           unsigned char* dst = smem + s.dst_off + (size_t)row * 16;
-          for (int cg = half; cg < (int)s.n_cg; cg += 2) {
-            float a[16];
-            tmem_ld16(lane_base + (uint32_t)(s.tmem_col + cg * 16), a);
-            tmem_ld_wait();
-            if (bias) {
-              const float* b16 = bp + (cg * 16) % s.bias_period;
+          // this warp's column groups: cg = half, half + 2, ...; up to four TMEM loads in flight before one wait
+          for (int cg0 = half; cg0 < (int)s.n_cg; cg0 += 8) {
+            float a[4][16];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float4 bb = *reinterpret_cast<const float4*>(b16 + 4 * j);
-                a[4 * j + 0] += bb.x; a[4 * j + 1] += bb.y; a[4 * j + 2] += bb.z; a[4 * j + 3] += bb.w;
+            for (int b = 0; b < 4; ++b)
+              if (cg0 + 2 * b < (int)s.n_cg) tmem_ld16(lane_base + (uint32_t)(s.tmem_col + (cg0 + 2 * b) * 16), a[b]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              const int cg = cg0 + 2 * b;
+              if (cg < (int)s.n_cg) {
+                if (bias) {
+                  const float* b16 = bp + (cg * 16) % s.bias_period;
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float4 bb = *reinterpret_cast<const float4*>(b16 + 4 * j);
+                    a[b][4 * j + 0] += bb.x; a[b][4 * j + 1] += bb.y; a[b][4 * j + 2] += bb.z; a[b][4 * j + 3] += bb.w;
+                  }
+                }
+                uint4 o0, o1;
+                if (relu) {
+                  o0 = make_uint4(pack2_relu(a[b][0], a[b][1]), pack2_relu(a[b][2], a[b][3]), pack2_relu(a[b][4], a[b][5]), pack2_relu(a[b][6], a[b][7]));
+                  o1 = make_uint4(pack2_relu(a[b][8], a[b][9]), pack2_relu(a[b][10], a[b][11]), pack2_relu(a[b][12], a[b][13]), pack2_relu(a[b][14], a[b][15]));
+                } else {
+                  o0 = make_uint4(pack2(a[b][0], a[b][1]), pack2(a[b][2], a[b][3]), pack2(a[b][4], a[b][5]), pack2(a[b][6], a[b][7]));
+                  o1 = make_uint4(pack2(a[b][8], a[b][9]), pack2(a[b][10], a[b][11]), pack2(a[b][12], a[b][13]), pack2(a[b][14], a[b][15]));
+                }
+                *reinterpret_cast<uint4*>(dst + (size_t)(2 * cg) * kPlane) = o0;
+                *reinterpret_cast<uint4*>(dst + (size_t)(2 * cg + 1) * kPlane) = o1;
               }
             }
-            uint4 o0, o1;
-            if (relu) {
-              o0 = make_uint4(pack2_relu(a[0], a[1]), pack2_relu(a[2], a[3]), pack2_relu(a[4], a[5]), pack2_relu(a[6], a[7]));
-              o1 = make_uint4(pack2_relu(a[8], a[9]), pack2_relu(a[10], a[11]), pack2_relu(a[12], a[13]), pack2_relu(a[14], a[15]));
-            } else {
-              o0 = make_uint4(pack2(a[0], a[1]), pack2(a[2], a[3]), pack2(a[4], a[5]), pack2(a[6], a[7]));
-              o1 = make_uint4(pack2(a[8], a[9]), pack2(a[10], a[11]), pack2(a[12], a[13]), pack2(a[14], a[15]));
-            }
-            *reinterpret_cast<uint4*>(dst + (size_t)(2 * cg) * kPlane) = o0;
-            *reinterpret_cast<uint4*>(dst + (size_t)(2 * cg + 1) * kPlane) = o1;
           }
         } else if (s.type == ST_PREP) {
           // A0 chunk t, row (w, v): [hi(mx), hi(mx), lo(mx), hi(my), hi(my), lo(my), 1, 1] of the adjacency-mixed, BatchNorm-folded
-          // pose; A0x chunk t' the same of the un-mixed pose at time stride * t' (operand of the residual conv)
-          const int nt = (int)s.p1 - (int)s.p0;
-          for (int i = et; i < rows * nt; i += kEpiWarps * 32) {
-            const int tl = i / rows, r = i - tl * rows, t = (int)s.p0 + tl;
-            const int w = r / V, v = r - w * V;
-            uint4 o = make_uint4(0, 0, 0, 0);
-            if (w < nw) {
-              const float* xp = xin + w * pl.per_w + t * V + v;
-              float m[2] = {0.f, 0.f};
-              bool bad = false;
-              for (int k = 0; k < pl.ell_width; ++k) {
-                const float2 e2 = ell[k * V + v];
-                const int dl = __float_as_int(e2.y);
-#pragma unroll
-                for (int c = 0; c < 2; ++c)
-                  if (c < pl.c_in) {
-                    const float xv = xp[c * tv + dl];
-                    bad |= !(fabsf(xv) <= 3.0e38f);
-                    m[c] = fmaf(e2.x, fmaf(xv, scale[c * V + v + dl], shift[c * V + v + dl]), m[c]);
-                  }
-              }
-              if (bad) {
-                atomicOr(&pz[w], 1);
-              } else {
-                const float hx = bf_hi(m[0]), hy = bf_hi(m[1]);
-                o = make_uint4(pack2(hx, hx), pack2(m[0] - hx, hy), pack2(hy, m[1] - hy), 0x3F803F80u);
-              }
-            }
-            *reinterpret_cast<uint4*>(smem + pl.off_a0 + (size_t)t * kPlane + (size_t)r * 16) = o;
-          }
-          if ((int)s.p1 >= T0 && pl.a0_chunks > T0)
-            for (int r = et; r < kRows; r += kEpiWarps * 32)
-              *reinterpret_cast<uint4*>(smem + pl.off_a0 + (size_t)T0 * kPlane + (size_t)r * 16) = make_uint4(0, 0, 0, 0);
-          if (s.p2) {
-            for (int i = et; i < rows * Tout0; i += kEpiWarps * 32) {
-              const int tp = i / rows, r = i - tp * rows, t = pl.stride0 * tp;
-              const int w = r / V, v = r - w * V;
-              uint4 o = make_uint4(0, 0, 0, 0);
-              if (w < nw) {
-                const float* xp = xin + w * pl.per_w + t * V + v;
-                float m[2] = {0.f, 0.f};
-                bool bad = false;
-#pragma unroll
-                for (int c = 0; c < 2; ++c)
-                  if (c < pl.c_in) {
-                    const float xv = xp[c * tv];
-                    bad |= !(fabsf(xv) <= 3.0e38f);
-                    m[c] = fmaf(xv, scale[c * V + v], shift[c * V + v]);
-                  }
-                if (bad) {
-                  atomicOr(&pz[w], 1);
-                } else {
-                  const float hx = bf_hi(m[0]), hy = bf_hi(m[1]);
-                  o = make_uint4(pack2(hx, hx), pack2(m[0] - hx, hy), pack2(hy, m[1] - hy), 0x3F803F80u);
-                }
-              }
-              *reinterpret_cast<uint4*>(smem + pl.off_a0x + (size_t)tp * kPlane + (size_t)r * 16) = o;
-            }
-            if (pl.a0x_chunks > Tout0)
-              for (int r = et; r < kRows; r += kEpiWarps * 32)
-                *reinterpret_cast<uint4*>(smem + pl.off_a0x + (size_t)Tout0 * kPlane + (size_t)r * 16) = make_uint4(0, 0, 0, 0);
-          }
+          // pose; A0x chunk t' the same of the un-mixed pose at time stride * t' (operand of the residual conv).
+          // Thread = (row, time parity): its keypoint's coefficient row (A_hat[v][u] * bn_scale[c][u], row delta) is loaded once.
+          if (pl.ell_width <= 5) prep_stage<5>(pl, s, smem, row, half, my_w, my_v, nw, pz);
+          else prep_stage<8>(pl, s, smem, row, half, my_w, my_v, nw, pz);
         } else {   // ST_TOKENS
           const float* bp = reinterpret_cast<const float*>(smem + s.bias_off);
           float* stg = reinterpret_cast<float*>(smem + pl.off_stage_tok);

@@ -18,12 +18,20 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(scope="module")
 def model_a(dropin1, dropin2):
-    return build_model(dropin1, dropin2, "A")
+    return build_model(dropin1, dropin2, "A")           # stays on the CPU (oracle / emulator side)
 
 
-def test_tok2_is_the_kernel_that_runs(model_a):
+@pytest.fixture(scope="module")
+def eng_a(dropin1, dropin2):
+    m = build_model(dropin1, dropin2, "A").cuda()
+    eng = m._sf_engine()
+    eng._keepalive = m
+    return eng
+
+
+def test_tok2_is_the_kernel_that_runs(eng_a):
     lib = N.load()
-    eng = model_a.cuda()._sf_engine()
+    eng = eng_a
     lib.sfdbg_tokenizer2_timing(1, None, 0)
     x = torch.from_numpy(synth_windows(64, 24, 17, seed=1)[0]).cuda()
     eng.tokenize(x, precision="bf16")
@@ -35,7 +43,7 @@ def test_tok2_is_the_kernel_that_runs(model_a):
 
 
 @pytest.mark.parametrize("T,B", [(24, 23), (24, 1), (24, 7), (24, 8), (12, 50), (18, 9), (22, 15)])
-def test_tok2_matches_oracle_and_emulator(model_a, T, B):
+def test_tok2_matches_oracle_and_emulator(model_a, eng_a, T, B):
     kw = oracle_kwargs(model_a, "A")
     xs = np.ascontiguousarray(synth_windows(B, T, 17, seed=11)[0])
     ref = O.tokenize(model_a.state_dict(), torch.from_numpy(xs).double(), kw["strides"]).numpy()
@@ -45,17 +53,18 @@ def test_tok2_matches_oracle_and_emulator(model_a, T, B):
         N.check(rc, "emulate")
     finally:
         lib.sf_model_destroy(h)
-    eng = model_a.cuda()._sf_engine()
+    eng = eng_a
     got = eng.tokenize(torch.from_numpy(xs).cuda(), precision="bf16").cpu().numpy()
     assert max_abs_rel(got, ref) < 1e-2
-    # same bf16 roundings, fp32 accumulation in a different order: far inside one bf16 ulp of the largest token
-    assert max_abs_rel(got, emu) < 2e-4, "hardware disagrees with the emulated tile program"
+    # same program, fp32 accumulation in a different order: an intermediate may round to the neighbouring bf16 (one ulp =
+    # 0.4 % of that element), which is all that may differ
+    assert max_abs_rel(got, emu) < 4e-3, "hardware disagrees with the emulated tile program"
 
 
-def test_tok2_large_ragged_deterministic_and_position_independent(model_a):
+def test_tok2_large_ragged_deterministic_and_position_independent(model_a, eng_a):
     kw = oracle_kwargs(model_a, "A")
     xs = synth_windows(1203, 24, 17, seed=77)[0]
-    eng = model_a.cuda()._sf_engine()
+    eng = eng_a
     x = torch.from_numpy(xs).cuda()
     t = eng.tokenize(x, precision="bf16")
     ref = O.tokenize(model_a.state_dict(), torch.from_numpy(xs).double(), kw["strides"]).numpy()
@@ -66,10 +75,10 @@ def test_tok2_large_ragged_deterministic_and_position_independent(model_a):
     assert torch.equal(eng.tokenize(x[5:6].contiguous(), precision="bf16"), t[5:6])
 
 
-def test_tok2_many_tiles_per_cta(model_a):
+def test_tok2_many_tiles_per_cta(eng_a):
     """More tiles than SMs x 2: every CTA runs several tiles (barrier phases, pose prefetch, bulk-store drain)."""
     xs = synth_windows(7 * 148 * 3 + 5, 24, 17, seed=5)[0]
-    eng = model_a.cuda()._sf_engine()
+    eng = eng_a
     x = torch.from_numpy(xs).cuda()
     t = eng.tokenize(x, precision="bf16")
     # the same windows in one-tile launches
@@ -78,9 +87,9 @@ def test_tok2_many_tiles_per_cta(model_a):
         assert torch.equal(eng.tokenize(x[i:i + 1].contiguous(), precision="bf16"), t[i:i + 1])
 
 
-def test_tok2_non_finite_pose_stays_in_its_window(model_a):
+def test_tok2_non_finite_pose_stays_in_its_window(eng_a):
     xs = synth_windows(20, 24, 17, seed=3)[0]
-    eng = model_a.cuda()._sf_engine()
+    eng = eng_a
     clean = eng.tokenize(torch.from_numpy(xs).cuda(), precision="bf16").cpu().numpy()
     xs[4, 1, 7, 3] = np.inf
     xs[12, 0, 0, 0] = np.nan
@@ -90,12 +99,12 @@ def test_tok2_non_finite_pose_stays_in_its_window(model_a):
     assert np.array_equal(got[keep], clean[keep])
 
 
-def test_one_window_kernel_still_serves_the_same_shape(model_a):
+def test_one_window_kernel_still_serves_the_same_shape(model_a, eng_a):
     """SF_TOK2_OFF routes config A to tokenizer_bf16_kernel (what hidden-64 shapes use): both meet the tolerance."""
     kw = oracle_kwargs(model_a, "A")
     xs = synth_windows(300, 24, 17, seed=9)[0]
     ref = O.tokenize(model_a.state_dict(), torch.from_numpy(xs).double(), kw["strides"]).numpy()
-    eng = model_a.cuda()._sf_engine()
+    eng = eng_a
     x = torch.from_numpy(xs).cuda()
     new = eng.tokenize(x, precision="bf16").cpu().numpy()
     os.environ["SF_TOK2_OFF"] = "1"
