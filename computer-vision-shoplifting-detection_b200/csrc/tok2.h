@@ -26,7 +26,7 @@ constexpr int kRows = 128;               // MMA M
 constexpr uint32_t kPlane = 2048;        // bytes of one 8-column chunk of a 128-row activation buffer
 constexpr int kEpiWarps = 8;             // warps 4..11
 constexpr int kThreads = 384;            // warp 0: MMA issue, warp 1: TMA, warps 2-3: idle, warps 4-11: epilogue
-constexpr int kMaxGroups = 96, kMaxStages = 96, kMaxLoads = 12, kMaxMma = 512;
+constexpr int kMaxGroups = 80, kMaxStages = 64, kMaxLoads = 10, kMaxMma = 384;
 
 struct Mma {                 // one tcgen05.mma (M = 128, K = 16)
   uint32_t a_lo;             // descriptor low word relative to the dynamic smem base: (offset >> 4) | (LBO >> 4) << 16
@@ -64,21 +64,17 @@ struct Load {                // L item
   int16_t wait_g, wait_e;    // this tile
   int16_t wait_g_prev;       // previous tile
   uint32_t dst_off, bytes;
-  uint64_t src;              // LD_WEIGHTS: global address of the image
+  uint32_t src_off, pad1;    // LD_WEIGHTS: byte offset of the image inside the model's blob (Plan::const_src)
 };
 
 struct Plan {                // kernel parameter (by value)
   int V, WT, rows, c_in, T0, S_out, c_last, cp_last, d_tok;
   int per_w;                 // floats per pose window
   int n_groups, n_stages, n_loads, n_mma;
-  const Mma* mma;            // device tables
-  const Group* groups;
-  const Stage* stages;
-  const Load* loads;
   const unsigned char* const_src;   // resident images + fp32 tables, copied to smem once per CTA
   uint32_t const_bytes;
   // shared-memory map (byte offsets from the dynamic smem base)
-  uint32_t off_const, off_P, off_Q, off_W, off_mma, off_groups, off_stages, off_loads, off_bars, off_flags;
+  uint32_t off_const, off_P, off_Q, off_W, off_bars, off_flags;
   uint32_t off_xin, off_a0, off_a0x, off_stage_tok;
   uint32_t off_ell, off_hc, off_scale, off_shift;   // const blob: mix coefficients float4 (A_hat*scale_x, A_hat*scale_y, row delta, 0) [5|8][V],
                                                    // float2 [V] mixed BN shifts, BN1d scale / shift [c_in][V]
@@ -86,7 +82,14 @@ struct Plan {                // kernel parameter (by value)
   int a0_chunks, a0x_chunks, stride0;
   int bar_g0, bar_e0, bar_l0, n_bars;           // barrier index bases
   uint32_t smem_bytes;
+  // The tile program itself travels in the kernel's parameter space (constant bank): the MMA-issuing thread reads
+  // descriptors with uniform-datapath constant loads, no shared-memory round trip and no register -> uniform moves.
+  Group groups[kMaxGroups];
+  Stage stages[kMaxStages];
+  Load loads[kMaxLoads];
+  Mma mma[kMaxMma];
 };
+static_assert(sizeof(Plan) < 16000, "Plan travels as a kernel parameter");
 
 }  // namespace t2
 }  // namespace sf

@@ -384,14 +384,14 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
     order.back().rd.push_back(tmem_r(tmem_col, ncols));
     order.back().wr.push_back(smem_r(dst_off, (uint32_t)(ncols / 8) * kPlane));
   };
-  auto new_load = [&](int kind, uint32_t dst_off, uint32_t bytes, uint64_t src) {
+  auto new_load = [&](int kind, uint32_t dst_off, uint32_t bytes, uint32_t src) {
     Load l;
     memset(&l, 0, sizeof(l));
     l.kind = (uint8_t)kind;
     l.wait_g = l.wait_e = l.wait_g_prev = -1;
     l.dst_off = dst_off;
     l.bytes = bytes;
-    l.src = src;
+    l.src_off = src;
     pr.loads.push_back(l);
     order.push_back(Item{2, (int)pr.loads.size() - 1, {}, {smem_r(dst_off, bytes)}});
   };
@@ -650,10 +650,6 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
   pl.n_mma = (int)pr.mma.size();
   if (pl.n_groups > kMaxGroups || pl.n_stages > kMaxStages || pl.n_loads > kMaxLoads || pl.n_mma > kMaxMma)
     return fail("tile program too long");
-  pl.off_mma = off; off += up128(pr.mma.size() * sizeof(Mma));
-  pl.off_groups = off; off += up128(pr.groups.size() * sizeof(Group));
-  pl.off_stages = off; off += up128(pr.stages.size() * sizeof(Stage));
-  pl.off_loads = off; off += up128(pr.loads.size() * sizeof(Load));
   pl.bar_g0 = 0;
   pl.bar_e0 = pl.n_groups;
   pl.bar_l0 = pl.n_groups + pl.n_stages;
@@ -663,6 +659,10 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
   pl.smem_bytes = off;
   if ((int)off > max_smem) return fail("tile does not fit shared memory (" + std::to_string(off) + " bytes)");
   if (off >= (1u << 18)) return fail("operand offsets exceed the descriptor range");
+  memcpy(pl.groups, pr.groups.data(), pr.groups.size() * sizeof(Group));
+  memcpy(pl.stages, pr.stages.data(), pr.stages.size() * sizeof(Stage));
+  memcpy(pl.loads, pr.loads.data(), pr.loads.size() * sizeof(Load));
+  memcpy(pl.mma, pr.mma.data(), pr.mma.size() * sizeof(Mma));
   pr.ok = true;
 }
 

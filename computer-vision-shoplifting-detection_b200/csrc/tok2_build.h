@@ -34,11 +34,11 @@ void build_static(const Tokenizer& tok, int pool_tokens, Static* out);
 struct Program {
   bool ok = false;
   std::string why;
-  Plan plan;                        // table / blob pointers are filled in by whoever uploads (or emulates)
+  Plan plan;                        // const_src is filled in by the launcher
   std::vector<Mma> mma;
   std::vector<Group> groups;
   std::vector<Stage> stages;
-  std::vector<Load> loads;          // Load::src holds a BLOB OFFSET until fix-up
+  std::vector<Load> loads;
 };
 
 void build_program(const Static& st, int T, int max_smem, Program* out);

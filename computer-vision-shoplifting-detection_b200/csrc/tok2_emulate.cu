@@ -90,7 +90,7 @@ struct Emu {
   }
   void load_effect(const Load& ld, const float* poses, int64_t B, int64_t tile) {
     if (ld.kind == LD_WEIGHTS) {
-      memcpy(&smem[ld.dst_off], st.blob.data() + ld.src, ld.bytes);
+      memcpy(&smem[ld.dst_off], st.blob.data() + ld.src_off, ld.bytes);
     } else {
       const int64_t w0 = tile * pl.WT;
       const int64_t nw = std::min<int64_t>(pl.WT, B - w0);
@@ -116,7 +116,7 @@ bool emulate(const Static& st, const Program& pr, const float* poses, int64_t B,
   const Plan& pl = pr.plan;
   memcpy(&E.smem[pl.off_const], st.blob.data(), st.const_bytes);
   // garbage (finite) in the operand regions: stale data must never reach a result
-  for (uint32_t i = pl.off_P; i + 1 < pl.off_mma; i += 2) {
+  for (uint32_t i = pl.off_P; i + 1 < pl.off_bars; i += 2) {
     const uint16_t h = f2bf((float)((int)(E.rnd() % 2001) - 1000) * 1e-3f);
     memcpy(&E.smem[i], &h, 2);
   }

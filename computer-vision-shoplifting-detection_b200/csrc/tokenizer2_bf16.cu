@@ -19,7 +19,7 @@
 #include "tok2_build.h"
 
 namespace sf {
-__device__ long long g_tok2_timing[1024];
+__device__ long long g_tok2_timing[4096];
 __device__ int g_tok2_timing_on = 0;
 namespace {
 
@@ -158,16 +158,7 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
     uint4* dst = reinterpret_cast<uint4*>(smem + pl.off_const);
     for (uint32_t i = threadIdx.x; i < pl.const_bytes / 16; i += kThreads) dst[i] = __ldg(src + i);
     uint4* z = reinterpret_cast<uint4*>(smem + pl.off_P);                   // operand regions start out finite (0 * NaN = NaN)
-    for (uint32_t i = threadIdx.x; i < (pl.off_mma - pl.off_P) / 16; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
-    auto copy_tab = [&](uint32_t off, const void* g, uint32_t bytes) {
-      const uint4* s4 = reinterpret_cast<const uint4*>(g);
-      uint4* d4 = reinterpret_cast<uint4*>(smem + off);
-      for (uint32_t i = threadIdx.x; i < bytes / 16; i += kThreads) d4[i] = __ldg(s4 + i);
-    };
-    copy_tab(pl.off_mma, pl.mma, (uint32_t)pl.n_mma * sizeof(Mma));
-    copy_tab(pl.off_groups, pl.groups, (uint32_t)pl.n_groups * sizeof(Group));
-    copy_tab(pl.off_stages, pl.stages, (uint32_t)pl.n_stages * sizeof(Stage));
-    copy_tab(pl.off_loads, pl.loads, (uint32_t)pl.n_loads * sizeof(Load));
+    for (uint32_t i = threadIdx.x; i < (pl.off_bars - pl.off_P) / 16; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
     if (threadIdx.x < 128) poison[threadIdx.x] = 0;
   }
   if (warp == 0) tmem_alloc(&tmem_base_s, 512);
@@ -183,36 +174,27 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
   const bool timing = g_tok2_timing_on && blockIdx.x == 0;
-  int stamp_i = warp == 0 ? 0 : 512;                       // MMA warp: first half of the buffer, epilogue warp 4: second half
-  const int stamp_end = stamp_i + 510;
+  int stamp_i = warp == 0 ? 0 : 1024;                      // MMA warp: first quarter of the buffer, epilogue warp 4: the rest
+  const int stamp_end = warp == 0 ? 1022 : 4094;
   const uint32_t stamp_it = (int64_t)blockIdx.x + gridDim.x < n_tiles ? 1u : 0u;     // steady-state tile when there is one
 
   if (warp == 0) {
     // =================================================================== MMA issue
-    const Mma* mtab = reinterpret_cast<const Mma*>(smem + pl.off_mma);
-    const Group* gtab = reinterpret_cast<const Group*>(smem + pl.off_groups);
     const uint32_t base16 = smem_u32(smem) >> 4;
     uint32_t it = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const uint32_t par = it & 1u;
       for (int g = 0; g < pl.n_groups; ++g) {
-        const Group gr = gtab[g];
+        const Group gr = pl.groups[g];
         if (gr.wait_e >= 0) mbar_wait(&bars[pl.bar_e0 + gr.wait_e], par);
         if (gr.wait_l >= 0) mbar_wait(&bars[pl.bar_l0 + gr.wait_l], par);
         if (gr.wait_e_prev >= 0 && it > 0) mbar_wait(&bars[pl.bar_e0 + gr.wait_e_prev], par ^ 1u);
         tc_fence_after();
         if (timing && it == stamp_it) T2_STAMP(1000 + g);
         if (elect_one()) {
-          // table entries are loaded four at a time BEFORE the (volatile, memory-clobbering) MMA instructions, so the
-          // shared-memory latency is paid once per four MMAs instead of once per MMA
+          // descriptors come straight from the parameter (constant) bank with a warp-uniform index
           const int end = gr.first + gr.count;
-          for (int i = gr.first; i < end; i += 4) {
-            const Mma e0 = mtab[i], e1 = mtab[min(i + 1, end - 1)], e2 = mtab[min(i + 2, end - 1)], e3 = mtab[min(i + 3, end - 1)];
-            issue_mma(tmem, e0, base16);
-            if (i + 1 < end) issue_mma(tmem, e1, base16);
-            if (i + 2 < end) issue_mma(tmem, e2, base16);
-            if (i + 3 < end) issue_mma(tmem, e3, base16);
-          }
+          for (int i = gr.first; i < end; ++i) issue_mma(tmem, pl.mma[i], base16);
           umma_commit(&bars[pl.bar_g0 + g]);
         }
         __syncwarp();
@@ -221,7 +203,6 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
   } else if (warp == 1) {
     // =================================================================== TMA
     if (lane == 0) {
-      const Load* ltab = reinterpret_cast<const Load*>(smem + pl.off_loads);
       auto pose_load = [&](int64_t tile) {
         if (tile >= n_tiles) return;
         const int64_t w0 = tile * pl.WT;
@@ -236,7 +217,7 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const uint32_t par = it & 1u;
         for (int l = 0; l < pl.n_loads; ++l) {
-          const Load ld = ltab[l];
+          const Load ld = pl.loads[l];
           // the pose barrier is one completion ahead (the prologue load): the load of tile n+1 is completion n+1
           if (ld.wait_g >= 0) mbar_wait(&bars[pl.bar_g0 + ld.wait_g], par);
           if (ld.wait_e >= 0) mbar_wait(&bars[pl.bar_e0 + ld.wait_e], par);
@@ -244,7 +225,7 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
           if (ld.kind == LD_WEIGHTS) {
             uint64_t* bar = &bars[pl.bar_l0 + l];
             mbar_expect_tx(bar, ld.bytes);
-            tma_load_1d(smem + ld.dst_off, reinterpret_cast<const void*>(ld.src), ld.bytes, bar);
+            tma_load_1d(smem + ld.dst_off, pl.const_src + ld.src_off, ld.bytes, bar);
           } else {
             pose_load(tile + gridDim.x);
           }
@@ -253,7 +234,6 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
     }
   } else if (warp >= 4) {
     // =================================================================== epilogue / prep (8 warps)
-    const Stage* stab = reinterpret_cast<const Stage*>(smem + pl.off_stages);
     const int et = (int)threadIdx.x - 128;                  // 0..255
     const int q = warp & 3, half = (warp - 4) >> 2;
     const int row = q * 32 + lane;
@@ -267,7 +247,8 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
       const int nw = (int)((B - w_first) < (int64_t)pl.WT ? (B - w_first) : (int64_t)pl.WT);
       int* pz = poison + par * 64;
       for (int e = 0; e < pl.n_stages; ++e) {
-        const Stage s = stab[e];
+        const Stage s = pl.stages[e];
+        if (timing && it == stamp_it && warp == 4) T2_STAMP(1500 + e);      // stage descriptor loaded, before the waits
         if (s.wait_g >= 0) mbar_wait(&bars[pl.bar_g0 + s.wait_g], par);
         if (s.wait_l >= 0) mbar_wait(&bars[pl.bar_l0 + s.wait_l], par);
         if (s.wait_g_prev >= 0 && it > 0) mbar_wait(&bars[pl.bar_g0 + s.wait_g_prev], par ^ 1u);
@@ -288,6 +269,7 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
             for (int b = 0; b < 4; ++b)
               if (cg0 + 2 * b < (int)s.n_cg) tmem_ld16(lane_base + (uint32_t)(s.tmem_col + (cg0 + 2 * b) * 16), a[b]);
             tmem_ld_wait();
+            if (timing && it == stamp_it && warp == 4) T2_STAMP(3000 + e);  // accumulators in registers
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
               const int cg = cg0 + 2 * b;
@@ -346,7 +328,9 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
           if (et == 0)
             bulk_store(tokens + (size_t)w_first * pl.S_out * pl.d_tok, stg, (uint32_t)nw * (uint32_t)(pl.S_out * pl.d_tok) * 4u);
         }
+        if (timing && it == stamp_it && warp == 4) T2_STAMP(4000 + e);      // body done
         fence_proxy_async();
+        if (timing && it == stamp_it && warp == 4) T2_STAMP(5000 + e);      // proxy fence done
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[pl.bar_e0 + e]);
@@ -362,7 +346,6 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
 // ---- per-model cache of uploaded programs (one per window length)
 struct Uploaded {
   Program prog;
-  void* dev = nullptr;
 };
 struct Cache {
   std::mutex mu;
@@ -393,10 +376,7 @@ Tok2State* tok2_create(const Tokenizer& host_tok, int pool_tokens, bool upload) 
 
 void tok2_destroy(Tok2State* s) {
   if (!s) return;
-  for (auto& kv : s->cache.by_T) {
-    if (kv.second->dev) cudaFree(kv.second->dev);
-    delete kv.second;
-  }
+  for (auto& kv : s->cache.by_T) delete kv.second;
   if (s->blob_dev) cudaFree(s->blob_dev);
   delete s;
 }
@@ -411,32 +391,7 @@ static Uploaded* tok2_program(const sf_model* m, int T) {
   if (it != s->cache.by_T.end()) return it->second;
   Uploaded* u = new Uploaded();
   t2::build_program(s->st, T, m->max_smem_optin - 2304, &u->prog);   // minus the kernel's static shared memory
-  if (u->prog.ok) {
-    Program& p = u->prog;
-    for (Load& l : p.loads)
-      if (l.kind == LD_WEIGHTS) l.src = (uint64_t)(uintptr_t)(s->blob_dev + l.src);
-    const size_t b0 = p.mma.size() * sizeof(Mma), b1 = p.groups.size() * sizeof(Group), b2 = p.stages.size() * sizeof(Stage),
-                 b3 = p.loads.size() * sizeof(Load);
-    auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
-    const size_t o1 = up(b0), o2 = o1 + up(b1), o3 = o2 + up(b2), total = o3 + up(b3);
-    std::vector<unsigned char> host(total, 0);
-    memcpy(host.data(), p.mma.data(), b0);
-    memcpy(host.data() + o1, p.groups.data(), b1);
-    memcpy(host.data() + o2, p.stages.data(), b2);
-    memcpy(host.data() + o3, p.loads.data(), b3);
-    if (cudaMalloc(&u->dev, total) != cudaSuccess || cudaMemcpy(u->dev, host.data(), total, cudaMemcpyHostToDevice) != cudaSuccess) {
-      cudaGetLastError();
-      p.ok = false;
-      p.why = "uploading the tile program failed";
-    } else {
-      unsigned char* d = (unsigned char*)u->dev;
-      p.plan.mma = (const Mma*)d;
-      p.plan.groups = (const Group*)(d + o1);
-      p.plan.stages = (const Stage*)(d + o2);
-      p.plan.loads = (const Load*)(d + o3);
-      p.plan.const_src = s->blob_dev;
-    }
-  }
+  if (u->prog.ok) u->prog.plan.const_src = s->blob_dev;
   s->cache.by_T[T] = u;
   return u;
 }
@@ -477,7 +432,7 @@ extern "C" int sfdbg_tokenizer2_timing(int enable, long long* out_host, int n) {
   if (cudaMemcpyToSymbol(sf::g_tok2_timing_on, &on, sizeof(int)) != cudaSuccess) return -1;
   if (out_host && n > 0) {
     if (cudaDeviceSynchronize() != cudaSuccess) return -1;
-    if (cudaMemcpyFromSymbol(out_host, sf::g_tok2_timing, sizeof(long long) * (n < 1024 ? n : 1024)) != cudaSuccess) return -1;
+    if (cudaMemcpyFromSymbol(out_host, sf::g_tok2_timing, sizeof(long long) * (n < 4096 ? n : 4096)) != cudaSuccess) return -1;
   }
   return 0;
 }
