@@ -309,7 +309,7 @@ extern "C" int sfdbg_tok2_emulate(const sf_model* m, const float* poses_host, in
   SF_REQUIRE(pr.ok, SF_E_UNSUPPORTED, "tokenizer v2 does not cover this shape: %s", pr.why.c_str());
   if (info_out) {
     info_out[0] = pr.plan.n_groups;
-    info_out[1] = pr.plan.n_stages;
+    info_out[1] = pr.plan.n_stages[0] + pr.plan.n_stages[1];
     info_out[2] = pr.plan.n_loads;
     info_out[3] = pr.plan.n_mma;
     info_out[4] = (int32_t)pr.plan.smem_bytes;

@@ -5,17 +5,20 @@
 //   * one tile = WT = floor(128 / V) whole windows; MMA row r = w * V + v  (window, keypoint),
 //     MMA column = (time, channel).  Every activation buffer is the planar-chunk layout of tc_common.cuh with
 //     128 rows: byte = (col / 8) * 2048 + row * 16 + (col % 8) * 2.
-//   * adjacency mix  = one 128x128 block-diagonal A operand (I_WT (x) A_hat) times the activation buffer used as an
-//     MN-major B operand (K = rows);
+//   * block 0's graph conv (2 raw coordinates -> C channels) runs on the CUDA cores in fp32 straight from the poses
+//     (BatchNorm1d folded into the adjacency coefficients), one time-slice at a time into a ring of bf16 operand slots;
+//   * adjacency mix of the later blocks = one 128x128 block-diagonal A operand (I_WT (x) A_hat) times the activation
+//     buffer used as an MN-major B operand (K = rows);
 //   * graph-conv weights = per-time-step [128 x Cin] x [Cin x Cout] MMAs;
 //   * temporal conv = Toeplitz product done WITHOUT a Toeplitz matrix: for input time t the taps that are valid for
 //     consecutive output times t' are consecutive blocks of a tap image stored in descending-tap order per stride phase,
 //     so ONE MMA with N = (#valid t') * Cout adds time t's contribution to all its outputs; no padding taps are computed;
-//   * strided 1x1 residual conv = per-output-time MMAs into the same accumulator (they also initialise it).
-// The host flattens a (model, T) pair into three in-order item sequences -- G (MMA groups, one issuing thread),
-// E (epilogue / prep stages, 8 warps) and L (TMA loads, one thread) -- and derives every cross-sequence wait from the
-// items' read / write sets (shared-memory byte ranges and TMEM column ranges).  Each item owns one mbarrier that
-// completes exactly once per tile.
+//   * strided 1x1 residual conv = per-output-time MMAs into the same accumulator (they also initialise it); block 0's
+//     (2 input channels) is added in fp32 by the epilogue that drains the accumulator.
+// The host flattens a (model, T) pair into four in-order item sequences -- G (MMA groups, one issuing thread),
+// E0 / E1 (epilogue stages of two 4-warp teams) and L (TMA loads, one thread) -- and derives every cross-sequence wait
+// from the items' read / write sets (shared-memory byte ranges and TMEM column ranges).  Each item owns one mbarrier
+// that completes exactly once per tile.
 #pragma once
 #include <stdint.h>
 
@@ -24,9 +27,11 @@ namespace t2 {
 
 constexpr int kRows = 128;               // MMA M
 constexpr uint32_t kPlane = 2048;        // bytes of one 8-column chunk of a 128-row activation buffer
-constexpr int kEpiWarps = 8;             // warps 4..11
+constexpr int kTeams = 2;                // epilogue teams: warps 4-7 and 8-11, one warp per 32-lane TMEM quarter
+constexpr int kTeamWarps = 4;
 constexpr int kThreads = 384;            // warp 0: MMA issue, warp 1: TMA, warps 2-3: idle, warps 4-11: epilogue
-constexpr int kMaxGroups = 80, kMaxStages = 64, kMaxLoads = 10, kMaxMma = 384;
+constexpr int kMaxGroups = 80, kMaxStages = 72, kMaxLoads = 10, kMaxMma = 384;
+constexpr int kMaxC0 = 64;               // block-0 output channels handled by the CUDA-core graph conv
 
 struct Mma {                 // one tcgen05.mma (M = 128, K = 16)
   uint32_t a_lo;             // descriptor low word relative to the dynamic smem base: (offset >> 4) | (LBO >> 4) << 16
@@ -37,59 +42,68 @@ struct Mma {                 // one tcgen05.mma (M = 128, K = 16)
 
 struct Group {               // G item: a run of MMAs followed by one commit
   uint16_t first, count;
-  int16_t wait_e, wait_l;    // E stage / L load that must have completed this tile (-1: none)
-  int16_t wait_e_prev;       // E stage of the PREVIOUS tile (-1: none)
-  int16_t pad[3];
+  int16_t wait_e[kTeams];    // stage of team 0 / 1 that must have completed this tile (-1: none)
+  int16_t wait_l;            // L load
+  int16_t prev_team, prev_stage;   // stage of the PREVIOUS tile that must have completed (-1: none): the token store
+  int16_t pad;
 };
 
-enum StageType { ST_PREP = 0, ST_CVT = 1, ST_TOKENS = 2 };
-enum StageFlags { SF_RELU = 1, SF_BIAS = 2, SF_DRAIN_STORE = 4 };
+enum StageType { ST_G0 = 0, ST_CVT = 1, ST_XEPI0 = 2, ST_TOKENS = 3 };
+enum StageFlags { SF_RELU = 1, SF_BIAS = 2, SF_TEAM_SYNC = 4 };
 
-struct Stage {               // E item
+struct Stage {               // E item (index = position in its TEAM's sequence)
   uint8_t type, flags;
   int16_t wait_g;            // G group of this tile (-1: none)
-  int16_t wait_l;            // L load (PREP: the poses)
-  int16_t wait_g_prev;       // G group of the previous tile (-1: none)
-  uint16_t tmem_col, n_cg;   // CVT / TOKENS: first accumulator column, number of 16-column groups
-  uint32_t dst_off;          // CVT: smem byte offset of destination column 0
+  int16_t wait_l;            // L load (block-0 stages: the poses)
+  int16_t wait_eo;           // stage of the OTHER team, this tile
+  int16_t wait_g_prev;       // G group of the previous tile
+  uint16_t tmem_col, n_cg;   // CVT / XEPI0 / TOKENS: first accumulator column, number of 16-column groups
+  uint32_t dst_off;          // smem byte offset of destination column 0 (G0: the ring slot)
   uint32_t bias_off;         // byte offset of the fp32 bias vector (period `bias_period` columns)
   uint16_t bias_period;
-  uint16_t p0, p1, p2;       // PREP: [p0, p1) time steps of A0; p2 = 1: also build A0x (all output times)
-  uint32_t pad;
+  uint16_t p0, p1;           // G0: input time steps [p0, p1); XEPI0: output time steps [p0, p1)
+  uint16_t pad[3];
 };
 
 enum LoadKind { LD_WEIGHTS = 0, LD_POSES = 1 };
 struct Load {                // L item
   uint8_t kind, pad0;
-  int16_t wait_g, wait_e;    // this tile
+  int16_t wait_g;            // this tile
+  int16_t wait_e[kTeams];
   int16_t wait_g_prev;       // previous tile
+  int16_t pad1;
   uint32_t dst_off, bytes;
-  uint32_t src_off, pad1;    // LD_WEIGHTS: byte offset of the image inside the model's blob (Plan::const_src)
+  uint32_t src_off, pad2;    // LD_WEIGHTS: byte offset of the image inside the model's blob (Plan::const_src)
 };
 
 struct Plan {                // kernel parameter (by value)
   int V, WT, rows, c_in, T0, S_out, c_last, cp_last, d_tok;
   int per_w;                 // floats per pose window
-  int n_groups, n_stages, n_loads, n_mma;
+  int n_groups, n_loads, n_mma;
+  int n_stages[kTeams];
   const unsigned char* const_src;   // resident images + fp32 tables, copied to smem once per CTA
   uint32_t const_bytes;
   // shared-memory map (byte offsets from the dynamic smem base)
-  uint32_t off_const, off_P, off_Q, off_W, off_bars, off_flags;
-  uint32_t off_xin, off_a0, off_a0x, off_stage_tok;
+  uint32_t off_const, off_P, off_Q, off_W, off_stage_tok, off_bars, off_flags;
+  uint32_t off_xin;
   uint32_t off_ell, off_hc, off_scale, off_shift;   // const blob: mix coefficients float4 (A_hat*scale_x, A_hat*scale_y, row delta, 0) [5|8][V],
                                                    // float2 [V] mixed BN shifts, BN1d scale / shift [c_in][V]
   int ell_width;
-  int a0_chunks, a0x_chunks, stride0;
-  int bar_g0, bar_e0, bar_l0, n_bars;           // barrier index bases
+  int cp0, stride0;
+  int bar_g0, bar_l0, n_bars;                   // barrier index bases
+  int bar_e0[kTeams];
   uint32_t smem_bytes;
+  // block 0 on the CUDA cores: fp32 tables in the const blob, per 4 output channels (w_x[4], w_y[4], bias[4]):
+  // graph-conv weight / bias, and the BN-folded residual 1x1 conv weight / output bias
+  uint32_t off_g0tab, off_r0tab;
   // The tile program itself travels in the kernel's parameter space (constant bank): the MMA-issuing thread reads
   // descriptors with uniform-datapath constant loads, no shared-memory round trip and no register -> uniform moves.
   Group groups[kMaxGroups];
-  Stage stages[kMaxStages];
+  Stage stages[kTeams][kMaxStages];
   Load loads[kMaxLoads];
   Mma mma[kMaxMma];
 };
-static_assert(sizeof(Plan) < 16000, "Plan travels as a kernel parameter");
+static_assert(sizeof(Plan) < 20000, "Plan travels as a kernel parameter");
 
 }  // namespace t2
 }  // namespace sf

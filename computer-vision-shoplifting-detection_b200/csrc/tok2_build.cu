@@ -18,12 +18,6 @@ inline uint16_t f2bf(float f) {       // round-to-nearest-even fp32 -> bf16
   u += 0x7fffu + ((u >> 16) & 1u);
   return (uint16_t)(u >> 16);
 }
-inline float bf2f(uint16_t h) {
-  uint32_t u = (uint32_t)h << 16;
-  float f;
-  memcpy(&f, &u, 4);
-  return f;
-}
 inline int pad16(int x) { return (x + 15) & ~15; }
 inline uint32_t up128(size_t x) { return (uint32_t)((x + 127) & ~size_t(127)); }
 
@@ -96,32 +90,25 @@ void build_static(const Tokenizer& tok, int pool_tokens, Static* out) {
     if (b > 0 && o.cin_p != s.blk[b - 1].cp) return fail("channel padding mismatch");
   }
   {
-    // block 0: K = 16 split images.  A columns per time step: [hx, hx, lx, hy, hy, ly, 1, 1]; B rows [w_hi, w_lo, w_hi | b_hi, b_lo]
+    // block 0 runs on the CUDA cores from fp32 tables (they travel in the kernel parameters); the tensor cores only
+    // need a zero A operand (two 8-column chunks) to clear the block-0 accumulator
     const TokBlock& t0 = tok.blk[0];
-    const int cp = s.blk[0].cp, co = t0.cout;
-    auto split_image = [&](uint32_t off, const float* w, const float* bias) {
-      fill_kmajor(bl.bf(off), 2 * cp, 16, [&](int n, int k) -> float {
-        const int half = n / cp, o = n % cp, kk = k % 8, kh = k / 8;
-        if (kh != half || o >= co) return 0.f;
-        float src;
-        bool lo;
-        if (kk < 6) {
-          const int ci = kk / 3, j = kk % 3;
-          if (ci >= t0.cin) return 0.f;
-          src = w[ci * co + o];
-          lo = j == 1;
-        } else {
-          src = bias[o];
-          lo = kk == 7;
-        }
-        const float hi = bf2f(f2bf(src));
-        return lo ? src - hi : hi;
-      });
+    if (s.blk[0].cp > kMaxC0) return fail("block 0 wider than 64 channels");
+    s.off_zero = bl.alloc((size_t)2 * kPlane);
+    const int cp = s.blk[0].cp;
+    auto table = [&](const float* w, const float* bias) {
+      const uint32_t off = bl.alloc((size_t)cp * 3 * 4);
+      float* t = bl.f32(off);
+      for (int o = 0; o < cp; ++o) {
+        float* e = t + (o / 4) * 12 + (o % 4);
+        e[0] = (o < t0.cout && t0.cin > 0) ? w[0 * t0.cout + o] : 0.f;
+        e[4] = (o < t0.cout && t0.cin > 1) ? w[1 * t0.cout + o] : 0.f;
+        e[8] = o < t0.cout ? bias[o] : 0.f;
+      }
+      return off;
     };
-    s.off_w0 = bl.alloc((size_t)2 * cp * 16 * 2);
-    split_image(s.off_w0, t0.gcn_w, t0.gcn_b);
-    s.off_r0 = bl.alloc((size_t)2 * cp * 16 * 2);
-    split_image(s.off_r0, t0.res_w, t0.out_b);
+    s.off_g0tab = table(t0.gcn_w, t0.gcn_b);
+    s.off_r0tab = table(t0.res_w, t0.out_b);
   }
   for (int b = 1; b < nb; ++b) {
     const TokBlock& tb = tok.blk[b];
@@ -208,8 +195,9 @@ struct Rng {
   int space;        // 0 = shared-memory bytes, 1 = TMEM columns
   uint32_t lo, hi;
 };
+enum Side { SIDE_G = 0, SIDE_L = 1, SIDE_E0 = 2, SIDE_E1 = 3, N_SIDES = 4 };
 struct Item {
-  int side, idx;    // 0 = G, 1 = E, 2 = L
+  int side, idx;
   std::vector<Rng> rd, wr;
 };
 bool overlap(const std::vector<Rng>& a, const std::vector<Rng>& b) {
@@ -241,27 +229,34 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
   if ((per_w * 4) % 16) return fail("window size not a multiple of 16 bytes");
   const uint32_t xin_bytes = (uint32_t)st.WT * per_w * 4, xin_alloc = up128(xin_bytes);
   const int cp0 = st.blk[0].cp;
-  const int n_sl = (T + 1) / 2;
-  const int a0_chunks = 2 * n_sl, a0x_chunks = 2 * ((Tout[0] + 1) / 2);
-  if (Tout[0] * cp0 + 4 * cp0 > 512) return fail("block-0 accumulators exceed tensor memory");
-  if (2 * cp0 > 256) return fail("block-0 width");
+  if (Tout[0] * cp0 > 512) return fail("block-0 accumulators exceed tensor memory");
+  if (cp0 != 16 && cp0 != 32 && cp0 != 64) return fail("block-0 width not 16 / 32 / 64");
+
+  // ---- block 0: time steps per CUDA-core slice and the ring of operand slots in Q
+  const uint32_t ring_cap_q = 49152;
+  int st0 = 2;                                          // time steps per slice
+  while (st0 > 1 && (uint32_t)(st0 * cp0 / 8) * kPlane * 2 > ring_cap_q) --st0;
+  const uint32_t ring0_slot = (uint32_t)(st0 * cp0 / 8) * kPlane;
+  const int n_sl = (T + st0 - 1) / st0;
+  const int ring0_slots = std::max(1, std::min(std::min(4, n_sl), (int)(ring_cap_q / ring0_slot)));
 
   // ---- chunking of blocks >= 1 (time steps per mix / graph-conv chunk) and region sizes
   int ct[kMaxBlocks] = {0}, nch[kMaxBlocks] = {0};
   uint32_t slot_bytes[kMaxBlocks] = {0};
   uint32_t x_bytes[kMaxBlocks + 1] = {0};          // x_b = input of block b (b >= 1), planar-chunk bf16
   for (int b = 1; b <= nb; ++b) x_bytes[b] = b < nb ? (uint32_t)(Tin[b] * st.blk[b].cin_p / 8) * kPlane : 0u;
-  const uint32_t ring0_slot = (uint32_t)(2 * cp0 / 8) * kPlane;
-  const int ring0_slots = std::min(3, n_sl);
-  uint32_t P_need = (uint32_t)(a0_chunks + a0x_chunks) * kPlane + xin_alloc, Q_need = ring0_slot * ring0_slots;
-  const uint32_t ring_cap_q = 49152;
+  uint32_t P_need = xin_alloc, Q_need = ring0_slot * ring0_slots;
   for (int b = 1; b < nb; ++b) {
     const BlockStatic& k = st.blk[b];
     const bool x_in_P = (b & 1) != 0;                 // x1 in P, x2 in Q, ...
     (x_in_P ? P_need : Q_need) = std::max(x_in_P ? P_need : Q_need, x_bytes[b]);
     const int accw = Tout[b] * k.cp;
+    // at least two chunks when the block is long enough: the second chunk's mix / graph conv run under the first
+    // chunk's epilogues
+    int c_max = Tin[b] >= 4 ? (Tin[b] + 1) / 2 : Tin[b];
+    if (b == 1) c_max = std::min(c_max, 8);        // block 0's output epilogue keeps one chunk's poses in registers
     int best = 0;
-    for (int c = Tin[b]; c >= 1; --c) {
+    for (int c = c_max; c >= 1; --c) {
       const int chunks = (Tin[b] + c - 1) / c;
       const uint32_t sb = (uint32_t)(c * std::max(k.cin_p, k.cp) / 8) * kPlane;
       const uint32_t ring = sb * (uint32_t)std::min(2, chunks);
@@ -279,15 +274,8 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
     const uint32_t ring = slot_bytes[b] * (uint32_t)std::min(2, nch[b]);
     (x_in_P ? Q_need : P_need) = std::max(x_in_P ? Q_need : P_need, ring);
   }
-  // token staging (fp32, the tile's tokens contiguous as in HBM) lives at the end of Q, clear of the last block's
-  // ring slot / input
   const int S_out = Tout[nb - 1], c_last = st.blk[nb - 1].cout, d_tok = c_last * V;
   const uint32_t stage_bytes = up128((size_t)st.WT * S_out * d_tok * 4);
-  {
-    const bool last_x_in_P = ((nb - 1) & 1) != 0;
-    const uint32_t q_used_last = last_x_in_P ? slot_bytes[nb - 1] * (uint32_t)std::min(2, nch[nb - 1]) : x_bytes[nb - 1];
-    Q_need = std::max(Q_need, up128(q_used_last) + stage_bytes);
-  }
   const uint32_t P_size = up128(P_need), Q_size = up128(Q_need);
   uint32_t W_size = 0;
   for (int b = 0; b < nb; ++b) W_size = std::max(W_size, st.blk[b].tcn_bytes);
@@ -306,39 +294,39 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
   pl.per_w = per_w;
   pl.const_bytes = st.const_bytes;
   pl.ell_width = st.ell_width;
-  pl.a0_chunks = a0_chunks;
-  pl.a0x_chunks = a0x_chunks;
+  pl.cp0 = cp0;
   pl.stride0 = st.blk[0].stride;
   uint32_t off = 0;
   pl.off_const = off; off += st.const_bytes;
   pl.off_P = off; off += P_size;
   pl.off_Q = off; off += Q_size;
   pl.off_W = off; off += up128(W_size);
+  pl.off_stage_tok = off; off += stage_bytes;
   pl.off_ell = pl.off_const + st.off_ell;
   pl.off_hc = pl.off_const + st.off_hc;
   pl.off_scale = pl.off_const + st.off_scale;
   pl.off_shift = pl.off_const + st.off_shift;
-  pl.off_a0 = pl.off_P;
-  pl.off_a0x = pl.off_P + (uint32_t)a0_chunks * kPlane;
+  pl.off_g0tab = pl.off_const + st.off_g0tab;
+  pl.off_r0tab = pl.off_const + st.off_r0tab;
+  // the raw poses sit at the END of P: x1 (block 0's output, written last) only reaches them with its final columns
   pl.off_xin = pl.off_P + P_size - xin_alloc;
-  pl.off_stage_tok = pl.off_Q + Q_size - stage_bytes;
 
   // ---- emit the items ----------------------------------------------------------------------------------------
   std::vector<Item> order;          // one valid sequential schedule of a tile
-  std::vector<Item*> dummy;
   auto smem_r = [](uint32_t lo, uint32_t bytes) { return Rng{0, lo, lo + bytes}; };
   auto tmem_r = [](int col, int n) { return Rng{1, (uint32_t)col, (uint32_t)(col + n)}; };
   const uint32_t c_lo = pl.off_const, c_hi = pl.off_const + st.const_bytes;
   auto is_const = [&](uint32_t o) { return o >= c_lo && o < c_hi; };
+  const std::vector<Rng> xin_rng{smem_r(pl.off_xin, xin_alloc)};
 
-  auto new_group = [&]() -> int {
+  auto new_group = [&]() {
     Group g;
     memset(&g, 0, sizeof(g));
     g.first = (uint16_t)pr.mma.size();
-    g.wait_e = g.wait_l = g.wait_e_prev = -1;
+    g.wait_e[0] = g.wait_e[1] = g.wait_l = -1;
+    g.prev_team = g.prev_stage = -1;
     pr.groups.push_back(g);
-    order.push_back(Item{0, (int)pr.groups.size() - 1, {}, {}});
-    return (int)pr.groups.size() - 1;
+    order.push_back(Item{SIDE_G, (int)pr.groups.size() - 1, {}, {}});
   };
   // one MMA: A K-major at a_off (LBO = a_lbo), B at b_off: K-major (LBO = b_lbo, rows = N) or MN-major (activation
   // buffer used with K = rows: K step kk at +256 B, N chunks one plane apart)
@@ -364,15 +352,18 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
     }
     it.wr.push_back(tmem_r(dcol, N));
   };
+  int next_team = 0;                 // stages alternate between the two epilogue teams
   auto new_stage = [&](int type, int flags) -> Stage& {
+    const int team = next_team;
+    next_team ^= 1;
     Stage s;
     memset(&s, 0, sizeof(s));
     s.type = (uint8_t)type;
     s.flags = (uint8_t)flags;
-    s.wait_g = s.wait_l = s.wait_g_prev = -1;
-    pr.stages.push_back(s);
-    order.push_back(Item{1, (int)pr.stages.size() - 1, {}, {}});
-    return pr.stages.back();
+    s.wait_g = s.wait_l = s.wait_eo = s.wait_g_prev = -1;
+    pr.stages[team].push_back(s);
+    order.push_back(Item{SIDE_E0 + team, (int)pr.stages[team].size() - 1, {}, {}});
+    return pr.stages[team].back();
   };
   auto cvt_stage = [&](int tmem_col, int ncols, uint32_t dst_off, int flags, uint32_t bias_off, int period) {
     Stage& s = new_stage(ST_CVT, flags);
@@ -388,94 +379,91 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
     Load l;
     memset(&l, 0, sizeof(l));
     l.kind = (uint8_t)kind;
-    l.wait_g = l.wait_e = l.wait_g_prev = -1;
+    l.wait_g = l.wait_e[0] = l.wait_e[1] = l.wait_g_prev = -1;
     l.dst_off = dst_off;
     l.bytes = bytes;
     l.src_off = src;
     pr.loads.push_back(l);
-    order.push_back(Item{2, (int)pr.loads.size() - 1, {}, {smem_r(dst_off, bytes)}});
+    order.push_back(Item{SIDE_L, (int)pr.loads.size() - 1, {}, {smem_r(dst_off, bytes)}});
+  };
+  // temporal-conv MMAs of input time steps [t0, t0 + nt) whose bf16 activations sit in `slot` (column = tl * cp + c)
+  auto tcn_mmas = [&](const BlockStatic& k, int b, uint32_t slot, int t0, int nt, int acc) {
+    const int cp = k.cp, s = k.stride;
+    const uint32_t w_plane = (uint32_t)kTaps * cp * 16;
+    for (int tl = 0; tl < nt; ++tl) {
+      const int t = t0 + tl;
+      int lo = (t - kHalo + s - 1) / s;
+      if (t - kHalo < 0) lo = 0;
+      const int hi = std::min(Tout[b] - 1, (t + kHalo) / s);
+      if (lo > hi) continue;
+      const int k_lo = t - s * lo + kHalo;
+      for (int n0 = lo; n0 <= hi;) {
+        const int cnt = std::min(hi - n0 + 1, 256 / cp);
+        const int ktap = k_lo - s * (n0 - lo);
+        for (int ks = 0; ks < cp / 16; ++ks)
+          add_mma(slot + (uint32_t)(tl * cp / 8 + 2 * ks) * kPlane, kPlane,
+                  pl.off_W + (uint32_t)(k.tap_pos[ktap] * cp) * 16 + (uint32_t)(2 * ks) * w_plane, w_plane, false, cnt * cp, acc + n0 * cp, true);
+        n0 += cnt;
+      }
+    }
+  };
+  auto drop_empty_group = [&]() {
+    if (pr.groups.back().count == 0) {
+      pr.groups.pop_back();
+      order.pop_back();
+    }
   };
 
   // ======================= block 0
   {
     const BlockStatic& k = st.blk[0];
-    const int cp = k.cp, s0 = k.stride;
-    const int acc = 0, stg[2] = {Tout[0] * cp, Tout[0] * cp + 2 * cp};
-    const uint32_t w_img = pl.off_W, w_plane = (uint32_t)kTaps * cp * 16;
+    const int cp = k.cp, accw = Tout[0] * cp;
     new_load(LD_WEIGHTS, pl.off_W, k.tcn_bytes, k.off_tcn);
-    auto prep = [&](int t0, int t1, bool with_x) {
-      Stage& s = new_stage(ST_PREP, 0);
-      s.p0 = (uint16_t)t0;
-      s.p1 = (uint16_t)t1;
-      s.p2 = with_x ? 1 : 0;
-      Item& it = order.back();
-      it.rd.push_back(smem_r(pl.off_xin, xin_bytes));
-      const int c1 = (t1 >= T) ? a0_chunks : t1;       // the last prep stage also clears the pad chunk
-      it.wr.push_back(smem_r(pl.off_a0 + (uint32_t)t0 * kPlane, (uint32_t)(c1 - t0) * kPlane));
-      if (with_x) it.wr.push_back(smem_r(pl.off_a0x, (uint32_t)a0x_chunks * kPlane));
-    };
-    const int sl_a = std::min(2, n_sl), sl_b = std::min(6, n_sl);
-    prep(0, std::min(T, 2 * sl_a), true);
     {
-      // residual conv of block 0 from the split raw poses: initialises every accumulator column (and adds the bias)
+      // clear the accumulator: zero A operand times the (always resident, finite) mix image, 128 columns per MMA
       new_group();
-      for (int j = 0; j < a0x_chunks / 2; ++j)
-        add_mma(pl.off_a0x + (uint32_t)(2 * j) * kPlane, kPlane, pl.off_const + st.off_r0, (uint32_t)(2 * cp) * 16, false,
-                (2 * j + 1 < Tout[0]) ? 2 * cp : cp, acc + 2 * j * cp, false);
+      for (int c0 = 0; c0 < accw; c0 += 128)
+        add_mma(pl.off_const + st.off_zero, kPlane, pl.off_const + st.off_ablk, kPlane, false, std::min(128, accw - c0), c0, false);
     }
-    auto gcn0 = [&](int i) {
-      new_group();
-      add_mma(pl.off_a0 + (uint32_t)(2 * i) * kPlane, kPlane, pl.off_const + st.off_w0, (uint32_t)(2 * cp) * 16, false, 2 * cp,
-              stg[i & 1], false);
-    };
-    auto epi0 = [&](int i) {
-      cvt_stage(stg[i & 1], 2 * cp, pl.off_Q + (uint32_t)(i % ring0_slots) * ring0_slot, SF_RELU, 0, 0);
-    };
-    auto tcn0 = [&](int i) {
-      new_group();
-      const uint32_t slot = pl.off_Q + (uint32_t)(i % ring0_slots) * ring0_slot;
-      for (int tl = 0; tl < 2; ++tl) {
-        const int t = 2 * i + tl;
-        if (t >= T) break;
-        int lo = (t - kHalo + s0 - 1) / s0;
-        if (t - kHalo < 0) lo = 0;
-        const int hi = std::min(Tout[0] - 1, (t + kHalo) / s0);
-        if (lo > hi) continue;
-        const int k_lo = t - s0 * lo + kHalo;
-        for (int n0 = lo; n0 <= hi;) {
-          const int cnt = std::min(hi - n0 + 1, 256 / cp);
-          const int ktap = k_lo - s0 * (n0 - lo);
-          for (int ks = 0; ks < cp / 16; ++ks)
-            add_mma(slot + (uint32_t)(tl * cp / 8 + 2 * ks) * kPlane, kPlane,
-                    w_img + (uint32_t)(k.tap_pos[ktap] * cp) * 16 + (uint32_t)(2 * ks) * w_plane, w_plane, false, cnt * cp,
-                    acc + n0 * cp, true);
-          n0 += cnt;
-        }
-      }
-    };
-    gcn0(0);
-    if (n_sl > 1) gcn0(1);
-    if (2 * sl_a < T) prep(2 * sl_a, std::min(T, 2 * sl_b), false);
-    bool prep2_done = 2 * sl_b >= T;
     for (int i = 0; i < n_sl; ++i) {
-      epi0(i);
-      if (!prep2_done && i >= 1) {
-        prep(2 * sl_b, T, false);
-        prep2_done = true;
-      }
-      tcn0(i);
-      if (pr.groups.back().count == 0) {          // (cannot happen for 9 taps / halo 4, kept for safety)
-        pr.groups.pop_back();
-        order.pop_back();
-      }
-      if (i + 2 < n_sl) gcn0(i + 2);
+      const uint32_t slot = pl.off_Q + (uint32_t)(i % ring0_slots) * ring0_slot;
+      const int t0 = i * st0, nt = std::min(st0, T - t0);
+      Stage& s = new_stage(ST_G0, SF_RELU);
+      s.p0 = (uint16_t)t0;
+      s.p1 = (uint16_t)(t0 + nt);
+      s.dst_off = slot;
+      order.back().rd = xin_rng;
+      order.back().wr.push_back(smem_r(slot, (uint32_t)(nt * cp / 8) * kPlane));
+      new_group();
+      tcn_mmas(k, 0, slot, t0, nt, 0);
+      drop_empty_group();
     }
-    if (!prep2_done) prep(2 * sl_b, T, false);
-    if (nb > 1) new_load(LD_WEIGHTS, pl.off_W, st.blk[1].tcn_bytes, st.blk[1].off_tcn);
-    // x1 = relu(acc) -> P (bias already inside the residual product); chunked like block 1's mix
-    const int cw = ct[1] * cp;
-    for (int c0 = 0; c0 < Tout[0] * cp; c0 += cw)
-      cvt_stage(acc + c0, std::min(cw, Tout[0] * cp - c0), pl.off_P + (uint32_t)(c0 / 8) * kPlane, SF_RELU, 0, 0);
+    new_load(LD_WEIGHTS, pl.off_W, st.blk[1].tcn_bytes, st.blk[1].off_tcn);
+    // x1 = relu(acc + residual conv of the raw poses + bias) -> P, chunked like block 1's mix
+    const int ctn = ct[1];
+    for (int tp0 = 0; tp0 < Tout[0];) {
+      int ntp = std::min(ctn, Tout[0] - tp0);
+      const uint32_t dst = pl.off_P + (uint32_t)(tp0 * cp / 8) * kPlane;
+      uint32_t bytes = (uint32_t)(ntp * cp / 8) * kPlane;
+      // the first chunk of x1 that reaches the pose slot takes all remaining columns: ONE stage whose threads first pull
+      // their poses into registers, then (team barrier) overwrite the slot -- no later stage needs the poses any more
+      const bool hits_xin = dst + bytes > pl.off_xin;
+      if (hits_xin) {
+        ntp = Tout[0] - tp0;
+        bytes = (uint32_t)(ntp * cp / 8) * kPlane;
+        if (ntp > 8) return fail("block-0 output chunk over the pose slot longer than 8 time steps");
+      }
+      Stage& s = new_stage(ST_XEPI0, SF_RELU | (hits_xin ? SF_TEAM_SYNC : 0));
+      s.tmem_col = (uint16_t)(tp0 * cp);
+      s.n_cg = (uint16_t)(ntp * cp / 16);
+      s.dst_off = dst;
+      s.p0 = (uint16_t)tp0;
+      s.p1 = (uint16_t)(tp0 + ntp);
+      order.back().rd = xin_rng;
+      order.back().rd.push_back(tmem_r(tp0 * cp, ntp * cp));
+      order.back().wr.push_back(smem_r(dst, bytes));
+      tp0 += ntp;
+    }
   }
 
   // ======================= blocks >= 1
@@ -487,7 +475,6 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
     const int accw = Tout[b] * cp, smw = ct[b] * cin;
     const int acc = x_in_P ? 512 - accw : 0;
     const int SM = x_in_P ? 0 : accw, SG = SM + smw;
-    const uint32_t w_img = pl.off_W, w_plane = (uint32_t)kTaps * cp * 16;
     const uint32_t g_img = pl.off_const + k.off_gcn, r_img = pl.off_const + k.off_res, gr_plane = (uint32_t)cp * 16;
     const bool last = b + 1 == nb;
     const int n_slots = std::min(2, nch[b]);
@@ -516,26 +503,6 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
           add_mma(xb + (uint32_t)((s * tp) * cin / 8 + 2 * ks) * kPlane, kPlane, r_img + (uint32_t)(2 * ks) * gr_plane, gr_plane, false, cp,
                   acc + tp * cp, ks > 0);
     };
-    auto tcn = [&](int c) {
-      new_group();
-      for (int tl = 0; tl < nt_of(c); ++tl) {
-        const int t = c * ct[b] + tl;
-        int lo = (t - kHalo + s - 1) / s;
-        if (t - kHalo < 0) lo = 0;
-        const int hi = std::min(Tout[b] - 1, (t + kHalo) / s);
-        if (lo > hi) continue;
-        const int k_lo = t - s * lo + kHalo;
-        for (int n0 = lo; n0 <= hi;) {
-          const int cnt = std::min(hi - n0 + 1, 256 / cp);
-          const int ktap = k_lo - s * (n0 - lo);
-          for (int ks = 0; ks < cp / 16; ++ks)
-            add_mma(slot_of(c) + (uint32_t)(tl * cp / 8 + 2 * ks) * kPlane, kPlane,
-                    w_img + (uint32_t)(k.tap_pos[ktap] * cp) * 16 + (uint32_t)(2 * ks) * w_plane, w_plane, false, cnt * cp,
-                    acc + n0 * cp, true);
-          n0 += cnt;
-        }
-      }
-    };
     mix(0);
     mepi(0);
     for (int c = 0; c < nch[b]; ++c) {
@@ -544,11 +511,9 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
       if (c == 0) res();
       gepi(c);
       if (c + 1 < nch[b]) mepi(c + 1);
-      tcn(c);
-      if (pr.groups.back().count == 0) {
-        pr.groups.pop_back();
-        order.pop_back();
-      }
+      new_group();
+      tcn_mmas(k, b, slot_of(c), c * ct[b], nt_of(c), acc);
+      drop_empty_group();
     }
     if (!last) {
       new_load(LD_WEIGHTS, pl.off_W, st.blk[b + 1].tcn_bytes, st.blk[b + 1].off_tcn);
@@ -567,100 +532,110 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
     }
   }
 
-  // ---- the next tile's poses: after the last item of this tile that touches the pose slot
+  // ---- the next tile's poses: after the last item of this tile that touches the pose slot (and after every other load:
+  // it is the last item of the L sequence)
   {
-    const std::vector<Rng> slot{smem_r(pl.off_xin, xin_alloc)};
-    size_t last_touch = 0;
+    size_t at = 0;
     for (size_t i = 0; i < order.size(); ++i)
-      if (overlap(order[i].rd, slot) || overlap(order[i].wr, slot)) last_touch = i;
+      if (overlap(order[i].rd, xin_rng) || overlap(order[i].wr, xin_rng) || order[i].side == SIDE_L) at = i + 1;
     Load l;
     memset(&l, 0, sizeof(l));
     l.kind = LD_POSES;
-    l.wait_g = l.wait_e = l.wait_g_prev = -1;
+    l.wait_g = l.wait_e[0] = l.wait_e[1] = l.wait_g_prev = -1;
     l.dst_off = pl.off_xin;
     l.bytes = xin_bytes;
-    // L items must stay in emission order on their side: the pose load goes LAST in the L sequence, so it has to be
-    // placed after every weight load as well
-    size_t at = last_touch + 1;
-    for (size_t i = 0; i < order.size(); ++i)
-      if (order[i].side == 2) at = std::max(at, i + 1);
     pr.loads.push_back(l);
-    order.insert(order.begin() + at, Item{2, (int)pr.loads.size() - 1, {}, slot});
+    order.insert(order.begin() + at, Item{SIDE_L, (int)pr.loads.size() - 1, {}, xin_rng});
   }
 
   // ---- cross-sequence waits from the read / write sets
   for (size_t i = 0; i < order.size(); ++i) {
     Item& x = order[i];
-    int w[3] = {-1, -1, -1};
+    int w[N_SIDES] = {-1, -1, -1, -1};
     for (size_t j = 0; j < i; ++j) {
       const Item& y = order[j];
       if (y.side == x.side) continue;
       if (overlap(y.wr, x.rd) || overlap(y.rd, x.wr) || overlap(y.wr, x.wr)) w[y.side] = std::max(w[y.side], y.idx);
     }
-    if (x.side == 0) {
-      pr.groups[x.idx].wait_e = (int16_t)w[1];
-      pr.groups[x.idx].wait_l = (int16_t)w[2];
-    } else if (x.side == 1) {
-      pr.stages[x.idx].wait_g = (int16_t)w[0];
-      pr.stages[x.idx].wait_l = (int16_t)w[2];
+    if (x.side == SIDE_G) {
+      pr.groups[x.idx].wait_e[0] = (int16_t)w[SIDE_E0];
+      pr.groups[x.idx].wait_e[1] = (int16_t)w[SIDE_E1];
+      pr.groups[x.idx].wait_l = (int16_t)w[SIDE_L];
+    } else if (x.side == SIDE_L) {
+      pr.loads[x.idx].wait_g = (int16_t)w[SIDE_G];
+      pr.loads[x.idx].wait_e[0] = (int16_t)w[SIDE_E0];
+      pr.loads[x.idx].wait_e[1] = (int16_t)w[SIDE_E1];
     } else {
-      pr.loads[x.idx].wait_g = (int16_t)w[0];
-      pr.loads[x.idx].wait_e = (int16_t)w[1];
+      const int team = x.side - SIDE_E0;
+      Stage& s = pr.stages[team][x.idx];
+      s.wait_g = (int16_t)w[SIDE_G];
+      s.wait_l = (int16_t)w[SIDE_L];
+      s.wait_eo = (int16_t)w[SIDE_E0 + (team ^ 1)];
     }
   }
-  // a wait that an earlier item of the same sequence already performed (or implied: E stages and G commits complete in
-  // order) is dropped -- most groups then issue without touching a barrier
+  // a wait that an earlier item of the same sequence already performed (or implied: stages of one team and G commits
+  // complete in order) is dropped -- most groups then issue without touching a barrier
   {
-    int seen_e = -1;
+    int seen_e[kTeams] = {-1, -1};
     std::vector<char> seen_l(pr.loads.size(), 0);
     for (Group& g : pr.groups) {
-      if (g.wait_e >= 0 && g.wait_e <= seen_e) g.wait_e = -1;
-      seen_e = std::max(seen_e, (int)g.wait_e);
+      for (int t = 0; t < kTeams; ++t) {
+        if (g.wait_e[t] >= 0 && g.wait_e[t] <= seen_e[t]) g.wait_e[t] = -1;
+        seen_e[t] = std::max(seen_e[t], (int)g.wait_e[t]);
+      }
       if (g.wait_l >= 0) {
         if (seen_l[g.wait_l]) g.wait_l = -1;
         else seen_l[g.wait_l] = 1;
       }
     }
-    int seen_g = -1;
-    for (Stage& s : pr.stages) {
-      if (s.wait_g >= 0 && s.wait_g <= seen_g) s.wait_g = -1;
-      seen_g = std::max(seen_g, (int)s.wait_g);
+    for (int t = 0; t < kTeams; ++t) {
+      int seen_g = -1, seen_o = -1;
+      for (Stage& s : pr.stages[t]) {
+        if (s.wait_g >= 0 && s.wait_g <= seen_g) s.wait_g = -1;
+        seen_g = std::max(seen_g, (int)s.wait_g);
+        if (s.wait_eo >= 0 && s.wait_eo <= seen_o) s.wait_eo = -1;
+        seen_o = std::max(seen_o, (int)s.wait_eo);
+      }
     }
   }
-  // tile boundary: the first prep stage overwrites the operand regions the previous tile's last MMAs read, the first
-  // weight load overwrites the weights they read; the prep stage reads the poses the previous tile's last load fetched
+  // tile boundary: each team's first stage overwrites operand regions the previous tile's last MMAs read, the first
+  // weight load overwrites the weights they read; every stage that reads the poses waits for the load the previous
+  // tile issued (the pose barrier is one completion ahead: the prologue load)
   const int last_g = (int)pr.groups.size() - 1;
-  pr.stages[0].wait_g_prev = (int16_t)last_g;
-  pr.stages[0].wait_l = (int16_t)((int)pr.loads.size() - 1);
-  pr.loads[0].wait_g_prev = (int16_t)last_g;
-  // the block-0 prep stages read the pose slot: all of them wait for the same load (same completion as stage 0)
-  for (Stage& s : pr.stages)
-    if (s.type == ST_PREP) s.wait_l = (int16_t)((int)pr.loads.size() - 1);
-  // stages that write over the token staging area first drain the previous tile's bulk store
-  {
-    const std::vector<Rng> stg{smem_r(pl.off_stage_tok, stage_bytes)};
-    for (const Item& it : order)
-      if (it.side == 1 && overlap(it.wr, stg)) pr.stages[it.idx].flags |= SF_DRAIN_STORE;
+  for (int t = 0; t < kTeams; ++t) {
+    if (pr.stages[t].empty()) return fail("an epilogue team has no work");
+    pr.stages[t][0].wait_g_prev = (int16_t)last_g;
+    for (Stage& s : pr.stages[t])
+      if (s.type == ST_G0 || s.type == ST_XEPI0) s.wait_l = (int16_t)((int)pr.loads.size() - 1);
   }
+  pr.loads[0].wait_g_prev = (int16_t)last_g;
+  // ... and the first MMA group overwrites accumulator columns the previous tile's token stage may still be reading
+  for (int t = 0; t < kTeams; ++t)
+    if (pr.stages[t].back().type == ST_TOKENS) {
+      pr.groups[0].prev_team = (int16_t)t;
+      pr.groups[0].prev_stage = (int16_t)((int)pr.stages[t].size() - 1);
+    }
 
   // ---- tables + barriers
   pl.n_groups = (int)pr.groups.size();
-  pl.n_stages = (int)pr.stages.size();
+  pl.n_stages[0] = (int)pr.stages[0].size();
+  pl.n_stages[1] = (int)pr.stages[1].size();
   pl.n_loads = (int)pr.loads.size();
   pl.n_mma = (int)pr.mma.size();
-  if (pl.n_groups > kMaxGroups || pl.n_stages > kMaxStages || pl.n_loads > kMaxLoads || pl.n_mma > kMaxMma)
+  if (pl.n_groups > kMaxGroups || pl.n_stages[0] > kMaxStages || pl.n_stages[1] > kMaxStages || pl.n_loads > kMaxLoads || pl.n_mma > kMaxMma)
     return fail("tile program too long");
   pl.bar_g0 = 0;
-  pl.bar_e0 = pl.n_groups;
-  pl.bar_l0 = pl.n_groups + pl.n_stages;
-  pl.n_bars = pl.n_groups + pl.n_stages + pl.n_loads;
+  pl.bar_e0[0] = pl.n_groups;
+  pl.bar_e0[1] = pl.bar_e0[0] + pl.n_stages[0];
+  pl.bar_l0 = pl.bar_e0[1] + pl.n_stages[1];
+  pl.n_bars = pl.bar_l0 + pl.n_loads;
   pl.off_bars = off; off += up128((size_t)pl.n_bars * 8);
   pl.off_flags = off; off += 512;
   pl.smem_bytes = off;
   if ((int)off > max_smem) return fail("tile does not fit shared memory (" + std::to_string(off) + " bytes)");
   if (off >= (1u << 18)) return fail("operand offsets exceed the descriptor range");
   memcpy(pl.groups, pr.groups.data(), pr.groups.size() * sizeof(Group));
-  memcpy(pl.stages, pr.stages.data(), pr.stages.size() * sizeof(Stage));
+  for (int t = 0; t < kTeams; ++t) memcpy(pl.stages[t], pr.stages[t].data(), pr.stages[t].size() * sizeof(Stage));
   memcpy(pl.loads, pr.loads.data(), pr.loads.size() * sizeof(Load));
   memcpy(pl.mma, pr.mma.data(), pr.mma.size() * sizeof(Mma));
   pr.ok = true;

@@ -123,13 +123,16 @@ bool emulate(const Static& st, const Program& pr, const float* poses, int64_t B,
   for (size_t i = 0; i < E.tmem.size(); ++i) E.tmem[i] = (float)((int)(E.rnd() % 2001) - 1000);
   const int64_t n_tiles = (B + pl.WT - 1) / pl.WT;
   if (n_tiles == 0) return true;
-  const int V = pl.V, rows = pl.rows, T0 = pl.T0, tv = T0 * V;
-  const int Tout0 = (T0 - 1) / pl.stride0 + 1;
+  const int V = pl.V, rows = pl.rows, T0 = pl.T0, tv = T0 * V, cp0 = pl.cp0;
   const float* scale = reinterpret_cast<const float*>(&E.smem[pl.off_scale]);
   const float* shift = reinterpret_cast<const float*>(&E.smem[pl.off_shift]);
+  const float* coef = reinterpret_cast<const float*>(&E.smem[pl.off_ell]);
+  const float* hcs = reinterpret_cast<const float*>(&E.smem[pl.off_hc]);
   std::vector<int> poison(128, 0);
+  const float* g0tab = reinterpret_cast<const float*>(&E.smem[pl.off_g0tab]);
+  const float* r0tab = reinterpret_cast<const float*>(&E.smem[pl.off_r0tab]);
+  auto tabv = [](const float* t, int which, int o) { return t[(o / 4) * 12 + which * 4 + (o % 4)]; };
 
-  // sequence state
   struct Pending { int idx; int64_t tile; bool effect_done; };
   int g_next = 0;
   int64_t g_it = 0;
@@ -138,16 +141,17 @@ bool emulate(const Static& st, const Program& pr, const float* poses, int64_t B,
   int64_t l_it = 0;
   std::deque<Pending> l_pending;
   struct WarpState { int e = 0; int64_t it = 0; int sub = 0; };
-  WarpState ws[kEpiWarps];
-  int named_arrived[2] = {0, 0};      // named barrier generations (0: drain, 1: tokens)
-  long named_gen[2] = {0, 0};
-  long warp_gen[kEpiWarps][2] = {{0}};
-  bool store_pending = false;          // bulk store issued, smem not yet read
-  std::vector<float> store_data;
+  WarpState ws[kTeams][kTeamWarps];
+  // named barrier of each team: generation counter + arrivals
+  int named_arrived[kTeams] = {0, 0};
+  long named_gen[kTeams] = {0, 0};
+  long warp_gen[kTeams][kTeamWarps] = {{0}};
+  bool store_pending = false;          // bulk store issued, staging not yet read
   int64_t store_tile = 0;
   int store_nw = 0;
+  // XEPI0 keeps the poses of its chunk in "registers" across the team barrier
+  std::vector<float> xreg((size_t)kTeams * kRows * 16 * 2, 0.f);
 
-  // prologue: poses of tile 0
   {
     Load l0 = pr.loads.back();
     E.load_effect(l0, poses, B, 0);
@@ -158,6 +162,18 @@ bool emulate(const Static& st, const Program& pr, const float* poses, int64_t B,
     if (w < 0) *ahead = true;
     return w == 1;
   };
+  auto do_store = [&]() {
+    const float* stg = reinterpret_cast<const float*>(&E.smem[pl.off_stage_tok]);
+    memcpy(tokens + (size_t)store_tile * pl.WT * pl.S_out * pl.d_tok, stg, (size_t)store_nw * pl.S_out * pl.d_tok * 4);
+    store_pending = false;
+  };
+  auto put16 = [&](uint32_t dst_off, int row, int cg, const float* a, bool relu) {
+    for (int j = 0; j < 16; ++j) {
+      const uint16_t h = pack_one(a[j], relu);
+      const int col = cg * 16 + j;
+      memcpy(&E.smem[dst_off + (uint32_t)(col / 8) * kPlane + (uint32_t)row * 16 + (uint32_t)(col % 8) * 2], &h, 2);
+    }
+  };
   const bool eager = seed == 0;
   long steps = 0;
   std::string ahead_msg;
@@ -165,19 +181,20 @@ bool emulate(const Static& st, const Program& pr, const float* poses, int64_t B,
     const bool g_done = g_it >= n_tiles && g_pending.empty();
     const bool l_done = l_it >= n_tiles && l_pending.empty();
     bool e_done = true;
-    for (auto& w : ws) e_done &= w.it >= n_tiles;
+    for (auto& tm : ws)
+      for (auto& w : tm) e_done &= w.it >= n_tiles;
     if (g_done && l_done && e_done && !store_pending) break;
-    if (++steps > 50000000) return fail("emulator: step limit");
-    // enumerate runnable actions
+    if (++steps > 80000000) return fail("emulator: step limit");
     enum { A_G_ISSUE, A_G_DONE, A_L_ISSUE, A_L_DONE, A_E0, A_STORE = 100 };
     std::vector<int> acts;
     bool ahead = false;
     if (g_it < n_tiles && (int)g_pending.size() < 6) {
       const Group& gr = pr.groups[g_next];
       bool ok = true;
-      if (gr.wait_e >= 0) ok &= bar_ok(pl.bar_e0 + gr.wait_e, g_it + 1, &ahead);
+      for (int t = 0; t < kTeams; ++t)
+        if (gr.wait_e[t] >= 0) ok &= bar_ok(pl.bar_e0[t] + gr.wait_e[t], g_it + 1, &ahead);
       if (gr.wait_l >= 0) ok &= bar_ok(pl.bar_l0 + gr.wait_l, g_it + 1, &ahead);
-      if (gr.wait_e_prev >= 0 && g_it > 0) ok &= bar_ok(pl.bar_e0 + gr.wait_e_prev, g_it, &ahead);
+      if (gr.prev_stage >= 0 && g_it > 0) ok &= bar_ok(pl.bar_e0[gr.prev_team] + gr.prev_stage, g_it, &ahead);
       if (ahead) ahead_msg = "G group " + std::to_string(g_next);
       if (ok) acts.push_back(A_G_ISSUE);
     }
@@ -186,35 +203,36 @@ bool emulate(const Static& st, const Program& pr, const float* poses, int64_t B,
       const Load& ld = pr.loads[l_next];
       bool ok = true, ah = false;
       if (ld.wait_g >= 0) ok &= bar_ok(pl.bar_g0 + ld.wait_g, l_it + 1, &ah);
-      if (ld.wait_e >= 0) ok &= bar_ok(pl.bar_e0 + ld.wait_e, l_it + 1, &ah);
+      for (int t = 0; t < kTeams; ++t)
+        if (ld.wait_e[t] >= 0) ok &= bar_ok(pl.bar_e0[t] + ld.wait_e[t], l_it + 1, &ah);
       if (ld.wait_g_prev >= 0 && l_it > 0) ok &= bar_ok(pl.bar_g0 + ld.wait_g_prev, l_it, &ah);
       if (ah) { ahead = true; ahead_msg = "L load " + std::to_string(l_next); }
       if (ok) acts.push_back(A_L_ISSUE);
     }
     if (!l_pending.empty()) acts.push_back(A_L_DONE);
-    for (int w = 0; w < kEpiWarps; ++w) {
-      WarpState& W = ws[w];
-      if (W.it >= n_tiles) continue;
-      const Stage& s = pr.stages[W.e];
-      bool ok = true, ah = false;
-      if (W.sub == 0) {
-        if (s.wait_g >= 0) ok &= bar_ok(pl.bar_g0 + s.wait_g, W.it + 1, &ah);
-        // the pose barrier is one completion ahead of the tile counter (prologue load)
-        if (s.wait_l >= 0) ok &= bar_ok(pl.bar_l0 + s.wait_l, W.it + 1, &ah);
-        if (s.wait_g_prev >= 0 && W.it > 0) ok &= bar_ok(pl.bar_g0 + s.wait_g_prev, W.it, &ah);
-      } else if (W.sub == 1) {
-        ok = named_gen[0] > warp_gen[w][0];       // waiting at the drain barrier
-      } else if (W.sub == 3) {
-        ok = named_gen[1] > warp_gen[w][1];       // waiting at the tokens barrier
+    for (int tm = 0; tm < kTeams; ++tm)
+      for (int w = 0; w < kTeamWarps; ++w) {
+        WarpState& W = ws[tm][w];
+        if (W.it >= n_tiles) continue;
+        const Stage& s = pr.stages[tm][W.e];
+        bool ok = true, ah = false;
+        if (W.sub == 0) {
+          if (s.wait_g >= 0) ok &= bar_ok(pl.bar_g0 + s.wait_g, W.it + 1, &ah);
+          if (s.wait_l >= 0) ok &= bar_ok(pl.bar_l0 + s.wait_l, W.it + 1, &ah);
+          if (s.wait_eo >= 0) ok &= bar_ok(pl.bar_e0[tm ^ 1] + s.wait_eo, W.it + 1, &ah);
+          if (s.wait_g_prev >= 0 && W.it > 0) ok &= bar_ok(pl.bar_g0 + s.wait_g_prev, W.it, &ah);
+        } else {
+          ok = named_gen[tm] > warp_gen[tm][w];       // parked at the team's named barrier
+        }
+        if (ah) { ahead = true; ahead_msg = "E team " + std::to_string(tm) + " stage " + std::to_string(W.e) + " warp " + std::to_string(w); }
+        if (ok) acts.push_back(A_E0 + tm * kTeamWarps + w);
       }
-      if (ah) { ahead = true; ahead_msg = "E stage " + std::to_string(W.e) + " warp " + std::to_string(w); }
-      if (ok) acts.push_back(A_E0 + w);
-    }
     if (store_pending) acts.push_back(A_STORE);
     if (ahead) return fail("emulator: a barrier ran a phase ahead of a waiter (" + ahead_msg + "): the GPU would hang");
     if (acts.empty()) {
       std::string m = "emulator: deadlock at G " + std::to_string(g_next) + "/it " + std::to_string(g_it) + ", L " + std::to_string(l_next) + ", E";
-      for (auto& w : ws) m += " " + std::to_string(w.e) + "." + std::to_string(w.sub);
+      for (auto& tm : ws)
+        for (auto& w : tm) m += " " + std::to_string(w.e) + "." + std::to_string(w.sub);
       return fail(m);
     }
     const int act = eager ? acts[0] : acts[E.rnd() % acts.size()];
@@ -246,111 +264,126 @@ bool emulate(const Static& st, const Program& pr, const float* poses, int64_t B,
       if (!p.effect_done) E.load_effect(pr.loads[p.idx], poses, B, p.tile);
       E.done[pl.bar_l0 + p.idx]++;
     } else if (act == A_STORE) {
-      // the bulk store reads the staging area now
-      const float* stg = reinterpret_cast<const float*>(&E.smem[pl.off_stage_tok]);
-      memcpy(tokens + (size_t)store_tile * pl.WT * pl.S_out * pl.d_tok, stg, (size_t)store_nw * pl.S_out * pl.d_tok * 4);
-      store_pending = false;
+      do_store();
     } else {
-      const int w = act - A_E0;
-      WarpState& W = ws[w];
-      const Stage& s = pr.stages[W.e];
-      const int q = w & 3, half = w >> 2;
+      const int tm = (act - A_E0) / kTeamWarps, w = (act - A_E0) % kTeamWarps;
+      WarpState& W = ws[tm][w];
+      const Stage& s = pr.stages[tm][W.e];
+      const int q = w;
       const int64_t tile = W.it;
       const int nw = (int)std::min<int64_t>(pl.WT, B - tile * pl.WT);
       const int par = (int)(W.it & 1);
-      auto arrive_named = [&](int which) {
-        warp_gen[w][which] = named_gen[which];
-        if (++named_arrived[which] == kEpiWarps) {
-          named_arrived[which] = 0;
-          named_gen[which]++;
+      auto arrive_named = [&]() {
+        warp_gen[tm][w] = named_gen[tm];
+        if (++named_arrived[tm] == kTeamWarps) {
+          named_arrived[tm] = 0;
+          named_gen[tm]++;
         }
       };
+      const float* xin = reinterpret_cast<const float*>(&E.smem[pl.off_xin]);
       bool finish = false;
-      if (W.sub == 0 && (s.flags & SF_DRAIN_STORE)) {
-        // thread 0 (warp 0) must see the previous store's reads complete before it arrives
-        if (w == 0 && store_pending) {
-          const float* stg = reinterpret_cast<const float*>(&E.smem[pl.off_stage_tok]);
-          memcpy(tokens + (size_t)store_tile * pl.WT * pl.S_out * pl.d_tok, stg, (size_t)store_nw * pl.S_out * pl.d_tok * 4);
-          store_pending = false;
-        }
-        arrive_named(0);
-        W.sub = 1;
-        continue;
-      }
-      if (W.sub == 0 || W.sub == 1) {
-        // ---- the stage body of this warp
-        if (s.type == ST_CVT) {
-          for (int cg = half; cg < s.n_cg; cg += 2)
-            for (int ln = 0; ln < 32; ++ln) {
-              const int row = q * 32 + ln;
-              for (int j = 0; j < 16; ++j) {
-                float a = E.tmem[(size_t)row * 512 + s.tmem_col + cg * 16 + j];
-                if (s.flags & SF_BIAS) a += reinterpret_cast<const float*>(&E.smem[s.bias_off])[(cg * 16) % s.bias_period + j];
-                const uint16_t h = pack_one(a, s.flags & SF_RELU);
-                const int col = cg * 16 + j;
-                memcpy(&E.smem[s.dst_off + (uint32_t)(col / 8) * kPlane + (uint32_t)row * 16 + (uint32_t)(col % 8) * 2], &h, 2);
-              }
+      if (s.type == ST_CVT) {
+        for (int cg = 0; cg < s.n_cg; ++cg)
+          for (int ln = 0; ln < 32; ++ln) {
+            const int row = q * 32 + ln;
+            float a[16];
+            for (int j = 0; j < 16; ++j) {
+              a[j] = E.tmem[(size_t)row * 512 + s.tmem_col + cg * 16 + j];
+              if (s.flags & SF_BIAS) a[j] += reinterpret_cast<const float*>(&E.smem[s.bias_off])[(cg * 16) % s.bias_period + j];
             }
-        } else if (s.type == ST_PREP) {
-          auto put = [&](uint32_t base, int chunk, int r, const float* m, bool valid) {
-            uint16_t o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            put16(s.dst_off, row, cg, a, s.flags & SF_RELU);
+          }
+        finish = true;
+      } else if (s.type == ST_G0) {
+        for (int ln = 0; ln < 32; ++ln) {
+          const int row = q * 32 + ln, ww = row / V, v = row - ww * V;
+          const bool valid = row < rows && ww < nw;
+          bool bad = false;
+          const float* xw = xin + ww * pl.per_w + v;
+          for (int t = s.p0; t < s.p1; ++t) {
+            float m[2] = {0.f, 0.f};
             if (valid) {
-              const float hx = bf2f(f2bf(m[0])), hy = bf2f(f2bf(m[1]));
-              o[0] = o[1] = f2bf(hx);
-              o[2] = f2bf(m[0] - hx);
-              o[3] = o[4] = f2bf(hy);
-              o[5] = f2bf(m[1] - hy);
-              o[6] = o[7] = 0x3F80;
+              m[0] = hcs[v * 2];
+              m[1] = hcs[v * 2 + 1];
+              for (int k = 0; k < pl.ell_width; ++k) {
+                const float* e = coef + (size_t)(k * V + v) * 4;
+                int dl;
+                memcpy(&dl, &e[2], 4);
+                for (int c = 0; c < pl.c_in; ++c) {
+                  const float xv = xw[t * V + c * tv + dl];
+                  bad |= !(std::fabs(xv) <= 3.0e38f);
+                  m[c] = std::fmaf(e[c], xv, m[c]);
+                }
+              }
+              if (bad) m[0] = m[1] = 0.f;
             }
-            memcpy(&E.smem[base + (uint32_t)chunk * kPlane + (uint32_t)r * 16], o, 16);
-          };
-          const float* xin = reinterpret_cast<const float*>(&E.smem[pl.off_xin]);
-          const float* coef = reinterpret_cast<const float*>(&E.smem[pl.off_ell]);
-          const float* hcs = reinterpret_cast<const float*>(&E.smem[pl.off_hc]);
-          // thread = (row, time parity `half`), as in the kernel
+            for (int cg = 0; cg < cp0 / 16; ++cg) {
+              float a[16];
+              for (int j = 0; j < 16; ++j) {
+                const int o = cg * 16 + j;
+                a[j] = valid ? std::fmaf(m[0], tabv(g0tab, 0, o), std::fmaf(m[1], tabv(g0tab, 1, o), tabv(g0tab, 2, o))) : 0.f;
+              }
+              put16(s.dst_off, row, (t - s.p0) * (cp0 / 16) + cg, a, true);
+            }
+          }
+          if (bad) poison[par * 64 + ww] = 1;
+        }
+        finish = true;
+      } else if (s.type == ST_XEPI0) {
+        float* xr = &xreg[(size_t)tm * kRows * 32];
+        auto body = [&]() {
+          for (int ln = 0; ln < 32; ++ln) {
+            const int row = q * 32 + ln;
+            for (int i = 0; i < s.p1 - s.p0; ++i)
+              for (int cg = 0; cg < cp0 / 16; ++cg) {
+                float a[16];
+                for (int j = 0; j < 16; ++j) {
+                  const int o = cg * 16 + j;
+                  a[j] = E.tmem[(size_t)row * 512 + s.tmem_col + i * cp0 + o] +
+                         std::fmaf(xr[row * 32 + i], tabv(r0tab, 0, o), std::fmaf(xr[row * 32 + 16 + i], tabv(r0tab, 1, o), tabv(r0tab, 2, o)));
+                }
+                put16(s.dst_off, row, i * (cp0 / 16) + cg, a, true);
+              }
+          }
+        };
+        if (W.sub == 0) {
           for (int ln = 0; ln < 32; ++ln) {
             const int row = q * 32 + ln, ww = row / V, v = row - ww * V;
             const bool valid = row < rows && ww < nw;
-            bool bad = false;
-            const float* xw = xin + ww * pl.per_w + v;
-            for (int t = s.p0 + half; t < s.p1; t += 2) {
-              float m[2] = {0.f, 0.f};
+            for (int i = 0; i < s.p1 - s.p0; ++i) {
+              float xa = 0.f, xb = 0.f;
               if (valid) {
-                m[0] = hcs[v * 2];
-                m[1] = hcs[v * 2 + 1];
-                for (int k = 0; k < pl.ell_width; ++k) {
-                  const float* e = coef + (size_t)(k * V + v) * 4;
-                  int dl;
-                  memcpy(&dl, &e[2], 4);
-                  for (int c = 0; c < pl.c_in; ++c) {
-                    const float xv = xw[t * V + c * tv + dl];
-                    bad |= !(std::fabs(xv) <= 3.0e38f);
-                    m[c] = std::fmaf(e[c], xv, m[c]);
-                  }
-                }
+                const float* xp = xin + ww * pl.per_w + v + pl.stride0 * (s.p0 + i) * V;
+                float u = xp[0], wv = pl.c_in > 1 ? xp[tv] : 0.f;
+                if (!(std::fabs(u) <= 3.0e38f) || !(std::fabs(wv) <= 3.0e38f)) u = wv = 0.f;
+                xa = std::fmaf(u, scale[v], shift[v]);
+                xb = pl.c_in > 1 ? std::fmaf(wv, scale[V + v], shift[V + v]) : 0.f;
               }
-              put(pl.off_a0, t, row, m, valid);
+              xr[row * 32 + i] = xa;
+              xr[row * 32 + 16 + i] = xb;
             }
-            if (s.p1 > s.p0 && s.p1 >= T0 && pl.a0_chunks > T0 && half == 0) memset(&E.smem[pl.off_a0 + (uint32_t)T0 * kPlane + (uint32_t)row * 16], 0, 16);
-            if (s.p2) {
-              for (int tp = half; tp < Tout0; tp += 2) {
-                float m[2] = {0.f, 0.f};
-                if (valid)
-                  for (int c = 0; c < pl.c_in; ++c) {
-                    const float xv = xw[pl.stride0 * tp * V + c * tv];
-                    bad |= !(std::fabs(xv) <= 3.0e38f);
-                    m[c] = std::fmaf(xv, scale[c * V + v], shift[c * V + v]);
-                  }
-                put(pl.off_a0x, tp, row, m, valid);
-              }
-              if (pl.a0x_chunks > Tout0 && half == 0) memset(&E.smem[pl.off_a0x + (uint32_t)Tout0 * kPlane + (uint32_t)row * 16], 0, 16);
-            }
-            if (bad) poison[par * 64 + ww] = 1;
           }
-        } else {   // ST_TOKENS, part 1: staging writes, then the named barrier
+          if (s.flags & SF_TEAM_SYNC) {
+            arrive_named();
+            W.sub = 1;
+            continue;
+          }
+          body();
+          finish = true;
+        } else {
+          body();
+          finish = true;
+        }
+      } else {   // ST_TOKENS: drain + barrier, staging writes + barrier, store
+        if (W.sub == 0) {
+          if (w == 0 && store_pending) do_store();          // thread 0 waits for the previous store's reads
+          arrive_named();
+          W.sub = 1;
+          continue;
+        } else if (W.sub == 1) {
           float* stg = reinterpret_cast<float*>(&E.smem[pl.off_stage_tok]);
           const float* bp = reinterpret_cast<const float*>(&E.smem[s.bias_off]);
-          for (int cg = half; cg < s.n_cg; cg += 2)
+          for (int cg = 0; cg < s.n_cg; ++cg)
             for (int ln = 0; ln < 32; ++ln) {
               const int row = q * 32 + ln, mw = row / V, mv = row - mw * V;
               if (!(row < rows && mw < nw)) continue;
@@ -363,30 +396,29 @@ bool emulate(const Static& st, const Program& pr, const float* poses, int64_t B,
                 stg[(mw * pl.S_out + t) * pl.d_tok + c * V + mv] = y;
               }
             }
-          if (w < 2)
-            for (int i = w * 32; i < w * 32 + 32; ++i) poison[(par ^ 1) * 64 + i] = 0;
-          arrive_named(1);
-          W.sub = 3;
+          arrive_named();
+          W.sub = 2;
           continue;
+        } else {
+          if (w < 2)
+            for (int i = w * 32; i < w * 32 + 32; ++i) poison[par * 64 + i] = 0;
+          if (w == 0) {
+            if (store_pending) return fail("emulator: token staging overwritten while a bulk store is pending");
+            store_pending = true;
+            store_tile = tile;
+            store_nw = nw;
+          }
+          finish = true;
         }
-        finish = true;
-      } else if (W.sub == 3) {
-        if (w == 0) {
-          if (store_pending) return fail("emulator: token staging overwritten while a bulk store is pending");
-          store_pending = true;
-          store_tile = tile;
-          store_nw = nw;
-        }
-        finish = true;
       }
       if (finish) {
-        const int bar = pl.bar_e0 + W.e;
-        if (++E.arrivals[bar] == kEpiWarps) {
+        const int bar = pl.bar_e0[tm] + W.e;
+        if (++E.arrivals[bar] == kTeamWarps) {
           E.arrivals[bar] = 0;
           E.done[bar]++;
         }
         W.sub = 0;
-        if (++W.e == pl.n_stages) { W.e = 0; ++W.it; }
+        if (++W.e == pl.n_stages[tm]) { W.e = 0; ++W.it; }
       }
     }
   }

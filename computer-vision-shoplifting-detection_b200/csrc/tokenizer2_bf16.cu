@@ -47,7 +47,6 @@ __device__ __forceinline__ uint32_t pack2_relu(float lo, float hi) {
   asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
   return d;
 }
-__device__ __forceinline__ float bf_hi(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 // A MMA with a 64-bit B descriptor whose high word depends on the operand kind
 __device__ __forceinline__ void issue_mma(uint32_t tmem, const Mma& m, uint32_t base16) {
@@ -58,28 +57,53 @@ __device__ __forceinline__ void issue_mma(uint32_t tmem, const Mma& m, uint32_t 
   umma_bf16(tmem + (m.d & 0x1FFu), ad, bd, m.idesc, (m.d >> 16) & 1u);
 }
 
-// Block-0 operand preparation of one prep stage for one thread (see the ST_PREP case).
+#define T2_STAMP(id)                                                      \
+  do {                                                                    \
+    if (timing && lane == 0 && stamp_i < stamp_end) {                     \
+      g_tok2_timing[stamp_i++] = (long long)(id);                         \
+      g_tok2_timing[stamp_i++] = clock64();                               \
+    }                                                                     \
+  } while (0)
+
+// 16 fp32 -> two 16-byte granules of bf16 (optionally through ReLU) at columns [16 cg, 16 cg + 16) of a planar-chunk buffer
+template <bool RELU>
+__device__ __forceinline__ void store16(unsigned char* dst_row, int cg, const float* a) {
+  uint4 o0, o1;
+  if (RELU) {
+    o0 = make_uint4(pack2_relu(a[0], a[1]), pack2_relu(a[2], a[3]), pack2_relu(a[4], a[5]), pack2_relu(a[6], a[7]));
+    o1 = make_uint4(pack2_relu(a[8], a[9]), pack2_relu(a[10], a[11]), pack2_relu(a[12], a[13]), pack2_relu(a[14], a[15]));
+  } else {
+    o0 = make_uint4(pack2(a[0], a[1]), pack2(a[2], a[3]), pack2(a[4], a[5]), pack2(a[6], a[7]));
+    o1 = make_uint4(pack2(a[8], a[9]), pack2(a[10], a[11]), pack2(a[12], a[13]), pack2(a[14], a[15]));
+  }
+  *reinterpret_cast<uint4*>(dst_row + (size_t)(2 * cg) * kPlane) = o0;
+  *reinterpret_cast<uint4*>(dst_row + (size_t)(2 * cg + 1) * kPlane) = o1;
+}
+
+// Block 0, one time slice [p0, p1) (at most two time steps) for one row (window w, keypoint v) on the CUDA cores, fp32:
+//   m_c = sum_u A_hat[v][u] * bn(x[c][t][u])      (BatchNorm1d folded into the coefficient row, shopformer/models/gcae.py:351-355)
+//   g_o = relu(m_x * W[x][o] + m_y * W[y][o] + b[o])   (graph conv, gcae.py:124-154)  -> bf16 operand slot of the temporal conv
+// The weight table is read once per 8 output channels and applied to both time steps (broadcast shared-memory loads).
 template <int KW>
-__device__ __forceinline__ void prep_stage(const Plan& pl, const Stage& s, unsigned char* smem, int row, int half, int my_w, int my_v,
-                                           int nw, int* pz) {
-  const int V = pl.V, T0 = pl.T0, tv = T0 * V;
+__device__ __forceinline__ void g0_stage(const Plan& pl, const Stage& s, unsigned char* smem, int row, int my_w, int my_v, int nw, int* pz) {
+  const int V = pl.V, tv = pl.T0 * V, cp0 = pl.cp0;
   const bool valid = row < pl.rows && my_w < nw;
-  const float* xw = reinterpret_cast<const float*>(smem + pl.off_xin) + my_w * pl.per_w + my_v;
   const bool two = pl.c_in > 1;
+  unsigned char* dst_row = smem + s.dst_off + (size_t)row * 16;
+  const int nt = (int)s.p1 - (int)s.p0;              // 1 or 2
+  float m0[2] = {0.f, 0.f}, m1[2] = {0.f, 0.f};
   bool bad = false;
-  if ((int)s.p1 > (int)s.p0) {
+  if (valid) {
+    const float4* coef = reinterpret_cast<const float4*>(smem + pl.off_ell);
+    const float2 hc = reinterpret_cast<const float2*>(smem + pl.off_hc)[my_v];
+    const float* xw = reinterpret_cast<const float*>(smem + pl.off_xin) + my_w * pl.per_w + my_v + (int)s.p0 * V;
     float4 cf[KW];
-    float2 hc = make_float2(0.f, 0.f);
-    if (valid) {
-      const float4* coef = reinterpret_cast<const float4*>(smem + pl.off_ell);
 #pragma unroll
-      for (int k = 0; k < KW; ++k) cf[k] = coef[k * V + my_v];
-      hc = reinterpret_cast<const float2*>(smem + pl.off_hc)[my_v];
-    }
-    for (int t = (int)s.p0 + half; t < (int)s.p1; t += 2) {
-      uint4 o = make_uint4(0, 0, 0, 0);
-      if (valid) {
-        const float* xp = xw + t * V;
+    for (int k = 0; k < KW; ++k) cf[k] = coef[k * V + my_v];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (h < nt) {
+        const float* xp = xw + h * V;
         float x0[KW], x1[KW];
 #pragma unroll
         for (int k = 0; k < KW; ++k) {
@@ -87,23 +111,54 @@ __device__ __forceinline__ void prep_stage(const Plan& pl, const Stage& s, unsig
           x0[k] = xp[dl];
           x1[k] = two ? xp[tv + dl] : 0.f;
         }
-        float m0 = hc.x, m1 = hc.y;
+        float a0 = hc.x, a1 = hc.y;
 #pragma unroll
         for (int k = 0; k < KW; ++k) {
           bad |= !(fabsf(x0[k]) <= 3.0e38f) | !(fabsf(x1[k]) <= 3.0e38f);
-          m0 = fmaf(cf[k].x, x0[k], m0);
-          m1 = fmaf(cf[k].y, x1[k], m1);
+          a0 = fmaf(cf[k].x, x0[k], a0);
+          a1 = fmaf(cf[k].y, x1[k], a1);
         }
-        const float hx = bf_hi(m0), hy = bf_hi(m1);
-        o = make_uint4(pack2(hx, hx), pack2(m0 - hx, hy), pack2(hy, m1 - hy), 0x3F803F80u);
+        m0[h] = bad ? 0.f : a0;
+        m1[h] = bad ? 0.f : a1;
       }
-      *reinterpret_cast<uint4*>(smem + pl.off_a0 + (size_t)t * kPlane + (size_t)row * 16) = o;
     }
-    if ((int)s.p1 >= T0 && pl.a0_chunks > T0 && half == 0)
-      *reinterpret_cast<uint4*>(smem + pl.off_a0 + (size_t)T0 * kPlane + (size_t)row * 16) = make_uint4(0, 0, 0, 0);
   }
-  if (s.p2) {
-    const int Tout0 = (T0 - 1) / pl.stride0 + 1;
+  const float4* tab = reinterpret_cast<const float4*>(smem + pl.off_g0tab);
+  const int chunks = cp0 / 8;                         // 8-channel granules per time step
+  for (int c8 = 0; c8 < chunks; ++c8) {
+    float w[24];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) *reinterpret_cast<float4*>(&w[4 * i]) = tab[c8 * 6 + i];     // (wx, wy, b) of outputs 8 c8 .. +4, then +4 .. +8
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (h < nt) {
+        float y[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int g = (j >> 2) * 12 + (j & 3);
+          y[j] = valid ? fmaf(m0[h], w[g], fmaf(m1[h], w[g + 4], w[g + 8])) : 0.f;
+        }
+        *reinterpret_cast<uint4*>(dst_row + (size_t)(h * chunks + c8) * kPlane) =
+            make_uint4(pack2_relu(y[0], y[1]), pack2_relu(y[2], y[3]), pack2_relu(y[4], y[5]), pack2_relu(y[6], y[7]));
+      }
+    }
+  }
+  // a window with a non-finite pose is reported as NaN tokens (the mix MMA would otherwise spread it over the tile)
+  if (bad) atomicOr(&pz[my_w], 1);
+}
+
+// Block 0 output for output times [p0, p1): x1 = relu(acc + BN-folded strided 1x1 residual conv of the raw poses + bias)
+// (gcae.py:237-259); the residual (2 input channels) is added in fp32 here instead of going through the tensor cores.
+__device__ __forceinline__ void xepi0_stage(const Plan& pl, const Stage& s, unsigned char* smem, uint32_t lane_base, int row, int my_w, int my_v,
+                                            int nw, int team) {
+  const int V = pl.V, tv = pl.T0 * V, cp0 = pl.cp0;
+  const bool valid = row < pl.rows && my_w < nw;
+  const bool two = pl.c_in > 1;
+  constexpr int kMaxT = 8;                               // output time steps per stage
+  float xa[kMaxT], xb[kMaxT];
+  const int ntp = (int)s.p1 - (int)s.p0;
+  {
+    const float* xw = reinterpret_cast<const float*>(smem + pl.off_xin) + my_w * pl.per_w + my_v;
     float sc0 = 0.f, sh0 = 0.f, sc1 = 0.f, sh1 = 0.f;
     if (valid) {
       const float* scale = reinterpret_cast<const float*>(smem + pl.off_scale);
@@ -115,32 +170,49 @@ __device__ __forceinline__ void prep_stage(const Plan& pl, const Stage& s, unsig
         sh1 = shift[V + my_v];
       }
     }
-    for (int tp = half; tp < Tout0; tp += 2) {
-      uint4 o = make_uint4(0, 0, 0, 0);
-      if (valid) {
-        const float* xp = xw + pl.stride0 * tp * V;
-        const float xa = xp[0], xb = two ? xp[tv] : 0.f;
-        bad |= !(fabsf(xa) <= 3.0e38f) | !(fabsf(xb) <= 3.0e38f);
-        const float m0 = fmaf(xa, sc0, sh0), m1 = fmaf(xb, sc1, sh1);
-        const float hx = bf_hi(m0), hy = bf_hi(m1);
-        o = make_uint4(pack2(hx, hx), pack2(m0 - hx, hy), pack2(hy, m1 - hy), 0x3F803F80u);
+#pragma unroll
+    for (int i = 0; i < kMaxT; ++i) {
+      xa[i] = xb[i] = 0.f;
+      if (valid && i < ntp) {
+        const float* xp = xw + pl.stride0 * ((int)s.p0 + i) * V;
+        float u = xp[0], w = two ? xp[tv] : 0.f;
+        if (!(fabsf(u) <= 3.0e38f) || !(fabsf(w) <= 3.0e38f)) u = w = 0.f;       // (the window is already flagged by its G0 stages)
+        xa[i] = fmaf(u, sc0, sh0);
+        xb[i] = fmaf(w, sc1, sh1);
       }
-      *reinterpret_cast<uint4*>(smem + pl.off_a0x + (size_t)tp * kPlane + (size_t)row * 16) = o;
     }
-    if (pl.a0x_chunks > Tout0 && half == 0)
-      *reinterpret_cast<uint4*>(smem + pl.off_a0x + (size_t)Tout0 * kPlane + (size_t)row * 16) = make_uint4(0, 0, 0, 0);
   }
-  // a window with a non-finite pose is reported as NaN tokens (the mix MMA would otherwise spread it over the tile)
-  if (bad) atomicOr(&pz[my_w], 1);
+  // this chunk of x1 overwrites the pose slot: every thread of the team has its poses in registers first
+  if (s.flags & SF_TEAM_SYNC) named_bar_sync(1 + team, kTeamWarps * 32);
+  unsigned char* dst_row = smem + s.dst_off + (size_t)row * 16;
+  const float4* tab = reinterpret_cast<const float4*>(smem + pl.off_r0tab);
+  const int cgs = cp0 / 16;
+  for (int cg = 0; cg < cgs; ++cg) {
+    float w[48];                                        // (rx, ry, rb) of 16 output channels
+#pragma unroll
+    for (int i = 0; i < 12; ++i) *reinterpret_cast<float4*>(&w[4 * i]) = tab[cg * 12 + i];
+#pragma unroll
+    for (int i0 = 0; i0 < kMaxT; i0 += 2) {
+      if (i0 < ntp) {
+        float a[2][16];
+        tmem_ld16(lane_base + (uint32_t)(s.tmem_col + i0 * cp0 + cg * 16), a[0]);
+        if (i0 + 1 < ntp) tmem_ld16(lane_base + (uint32_t)(s.tmem_col + (i0 + 1) * cp0 + cg * 16), a[1]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (i0 + h < ntp) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int g = (j >> 2) * 12 + (j & 3);
+              a[h][j] += fmaf(xa[i0 + h], w[g], fmaf(xb[i0 + h], w[g + 4], w[g + 8]));
+            }
+            store16<true>(dst_row, (i0 + h) * cgs + cg, a[h]);
+          }
+        }
+      }
+    }
+  }
 }
-
-#define T2_STAMP(id)                                                      \
-  do {                                                                    \
-    if (timing && lane == 0 && stamp_i < stamp_end) {                     \
-      g_tok2_timing[stamp_i++] = (long long)(id);                         \
-      g_tok2_timing[stamp_i++] = clock64();                               \
-    }                                                                     \
-  } while (0)
 
 __global__ void __launch_bounds__(kThreads, 1)
 tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ poses, float* __restrict__ tokens, int64_t B) {
@@ -164,7 +236,8 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
   if (warp == 0) tmem_alloc(&tmem_base_s, 512);
   if (threadIdx.x == 0) {
     for (int i = 0; i < pl.n_groups; ++i) mbar_init(&bars[pl.bar_g0 + i], 1);
-    for (int i = 0; i < pl.n_stages; ++i) mbar_init(&bars[pl.bar_e0 + i], kEpiWarps);
+    for (int t = 0; t < kTeams; ++t)
+      for (int i = 0; i < pl.n_stages[t]; ++i) mbar_init(&bars[pl.bar_e0[t] + i], kTeamWarps);
     for (int i = 0; i < pl.n_loads; ++i) mbar_init(&bars[pl.bar_l0 + i], 1);
     fence_mbar_init();
   }
@@ -174,8 +247,9 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
   const bool timing = g_tok2_timing_on && blockIdx.x == 0;
-  int stamp_i = warp == 0 ? 0 : 1024;                      // MMA warp: first quarter of the buffer, epilogue warp 4: the rest
-  const int stamp_end = warp == 0 ? 1022 : 4094;
+  // debug stamps: MMA warp in [0, 1024), team 0 (warp 4) in [1024, 2560), team 1 (warp 8) in [2560, 4096)
+  int stamp_i = warp == 0 ? 0 : (warp == 4 ? 1024 : 2560);
+  const int stamp_end = warp == 0 ? 1022 : (warp == 4 ? 2558 : 4094);
   const uint32_t stamp_it = (int64_t)blockIdx.x + gridDim.x < n_tiles ? 1u : 0u;     // steady-state tile when there is one
 
   if (warp == 0) {
@@ -186,9 +260,10 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
       const uint32_t par = it & 1u;
       for (int g = 0; g < pl.n_groups; ++g) {
         const Group gr = pl.groups[g];
-        if (gr.wait_e >= 0) mbar_wait(&bars[pl.bar_e0 + gr.wait_e], par);
+        if (gr.wait_e[0] >= 0) mbar_wait(&bars[pl.bar_e0[0] + gr.wait_e[0]], par);
+        if (gr.wait_e[1] >= 0) mbar_wait(&bars[pl.bar_e0[1] + gr.wait_e[1]], par);
         if (gr.wait_l >= 0) mbar_wait(&bars[pl.bar_l0 + gr.wait_l], par);
-        if (gr.wait_e_prev >= 0 && it > 0) mbar_wait(&bars[pl.bar_e0 + gr.wait_e_prev], par ^ 1u);
+        if (gr.prev_stage >= 0 && it > 0) mbar_wait(&bars[pl.bar_e0[gr.prev_team] + gr.prev_stage], par ^ 1u);
         tc_fence_after();
         if (timing && it == stamp_it) T2_STAMP(1000 + g);
         if (elect_one()) {
@@ -218,61 +293,58 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
         const uint32_t par = it & 1u;
         for (int l = 0; l < pl.n_loads; ++l) {
           const Load ld = pl.loads[l];
-          // the pose barrier is one completion ahead (the prologue load): the load of tile n+1 is completion n+1
           if (ld.wait_g >= 0) mbar_wait(&bars[pl.bar_g0 + ld.wait_g], par);
-          if (ld.wait_e >= 0) mbar_wait(&bars[pl.bar_e0 + ld.wait_e], par);
+          if (ld.wait_e[0] >= 0) mbar_wait(&bars[pl.bar_e0[0] + ld.wait_e[0]], par);
+          if (ld.wait_e[1] >= 0) mbar_wait(&bars[pl.bar_e0[1] + ld.wait_e[1]], par);
           if (ld.wait_g_prev >= 0 && it > 0) mbar_wait(&bars[pl.bar_g0 + ld.wait_g_prev], par ^ 1u);
           if (ld.kind == LD_WEIGHTS) {
             uint64_t* bar = &bars[pl.bar_l0 + l];
             mbar_expect_tx(bar, ld.bytes);
             tma_load_1d(smem + ld.dst_off, pl.const_src + ld.src_off, ld.bytes, bar);
           } else {
-            pose_load(tile + gridDim.x);
+            pose_load(tile + gridDim.x);          // the pose barrier is one completion ahead (the prologue load)
           }
         }
       }
     }
   } else if (warp >= 4) {
-    // =================================================================== epilogue / prep (8 warps)
-    const int et = (int)threadIdx.x - 128;                  // 0..255
-    const int q = warp & 3, half = (warp - 4) >> 2;
+    // =================================================================== epilogue: two teams of four warps
+    const int team = (warp - 4) >> 2, q = warp & 3;
+    const int tt = (int)threadIdx.x - 128 - team * 128;     // thread within the team = MMA row
     const int row = q * 32 + lane;
     const int V = pl.V, rows = pl.rows;
     const int my_w = row / V, my_v = row - my_w * V;
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+    const int n_st = pl.n_stages[team];
+    const int bar_mine = pl.bar_e0[team], bar_other = pl.bar_e0[team ^ 1];
     uint32_t it = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const uint32_t par = it & 1u;
       const int64_t w_first = tile * pl.WT;
       const int nw = (int)((B - w_first) < (int64_t)pl.WT ? (B - w_first) : (int64_t)pl.WT);
       int* pz = poison + par * 64;
-      for (int e = 0; e < pl.n_stages; ++e) {
-        const Stage s = pl.stages[e];
-        if (timing && it == stamp_it && warp == 4) T2_STAMP(1500 + e);      // stage descriptor loaded, before the waits
+      for (int e = 0; e < n_st; ++e) {
+        const Stage s = pl.stages[team][e];
         if (s.wait_g >= 0) mbar_wait(&bars[pl.bar_g0 + s.wait_g], par);
         if (s.wait_l >= 0) mbar_wait(&bars[pl.bar_l0 + s.wait_l], par);
+        if (s.wait_eo >= 0) mbar_wait(&bars[bar_other + s.wait_eo], par);
         if (s.wait_g_prev >= 0 && it > 0) mbar_wait(&bars[pl.bar_g0 + s.wait_g_prev], par ^ 1u);
         tc_fence_after();
-        if (timing && it == stamp_it && warp == 4) T2_STAMP(2000 + e);
-        if (s.flags & SF_DRAIN_STORE) {
-          if (et == 0) bulk_wait_read();
-          named_bar_sync(1, kEpiWarps * 32);
-        }
+        if (timing && it == stamp_it && q == 0) T2_STAMP(2000 + e);
         if (s.type == ST_CVT) {
           const bool relu = s.flags & SF_RELU, bias = s.flags & SF_BIAS;
           const float* bp = reinterpret_cast<const float*>(smem + s.bias_off);
           unsigned char* dst = smem + s.dst_off + (size_t)row * 16;
-          // this warp's column groups: cg = half, half + 2, ...; up to four TMEM loads in flight before one wait
-          for (int cg0 = half; cg0 < (int)s.n_cg; cg0 += 8) {
+          // up to four TMEM loads in flight before one wait
+          for (int cg0 = 0; cg0 < (int)s.n_cg; cg0 += 4) {
             float a[4][16];
 #pragma unroll
             for (int b = 0; b < 4; ++b)
-              if (cg0 + 2 * b < (int)s.n_cg) tmem_ld16(lane_base + (uint32_t)(s.tmem_col + (cg0 + 2 * b) * 16), a[b]);
+              if (cg0 + b < (int)s.n_cg) tmem_ld16(lane_base + (uint32_t)(s.tmem_col + (cg0 + b) * 16), a[b]);
             tmem_ld_wait();
-            if (timing && it == stamp_it && warp == 4) T2_STAMP(3000 + e);  // accumulators in registers
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
-              const int cg = cg0 + 2 * b;
+              const int cg = cg0 + b;
               if (cg < (int)s.n_cg) {
                 if (bias) {
                   const float* b16 = bp + (cg * 16) % s.bias_period;
@@ -282,31 +354,25 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
                     a[b][4 * j + 0] += bb.x; a[b][4 * j + 1] += bb.y; a[b][4 * j + 2] += bb.z; a[b][4 * j + 3] += bb.w;
                   }
                 }
-                uint4 o0, o1;
-                if (relu) {
-                  o0 = make_uint4(pack2_relu(a[b][0], a[b][1]), pack2_relu(a[b][2], a[b][3]), pack2_relu(a[b][4], a[b][5]), pack2_relu(a[b][6], a[b][7]));
-                  o1 = make_uint4(pack2_relu(a[b][8], a[b][9]), pack2_relu(a[b][10], a[b][11]), pack2_relu(a[b][12], a[b][13]), pack2_relu(a[b][14], a[b][15]));
-                } else {
-                  o0 = make_uint4(pack2(a[b][0], a[b][1]), pack2(a[b][2], a[b][3]), pack2(a[b][4], a[b][5]), pack2(a[b][6], a[b][7]));
-                  o1 = make_uint4(pack2(a[b][8], a[b][9]), pack2(a[b][10], a[b][11]), pack2(a[b][12], a[b][13]), pack2(a[b][14], a[b][15]));
-                }
-                *reinterpret_cast<uint4*>(dst + (size_t)(2 * cg) * kPlane) = o0;
-                *reinterpret_cast<uint4*>(dst + (size_t)(2 * cg + 1) * kPlane) = o1;
+                if (relu) store16<true>(dst, cg, a[b]);
+                else store16<false>(dst, cg, a[b]);
               }
             }
           }
-        } else if (s.type == ST_PREP) {
-          // A0 chunk t, row (w, v): [hi(mx), hi(mx), lo(mx), hi(my), hi(my), lo(my), 1, 1] of the adjacency-mixed, BatchNorm-folded
-          // pose; A0x chunk t' the same of the un-mixed pose at time stride * t' (operand of the residual conv).
-          // Thread = (row, time parity): its keypoint's coefficient row (A_hat[v][u] * bn_scale[c][u], row delta) is loaded once.
-          if (pl.ell_width <= 5) prep_stage<5>(pl, s, smem, row, half, my_w, my_v, nw, pz);
-          else prep_stage<8>(pl, s, smem, row, half, my_w, my_v, nw, pz);
+        } else if (s.type == ST_G0) {
+          if (pl.ell_width <= 5) g0_stage<5>(pl, s, smem, row, my_w, my_v, nw, pz);
+          else g0_stage<8>(pl, s, smem, row, my_w, my_v, nw, pz);
+        } else if (s.type == ST_XEPI0) {
+          xepi0_stage(pl, s, smem, lane_base, row, my_w, my_v, nw, team);
         } else {   // ST_TOKENS
           const float* bp = reinterpret_cast<const float*>(smem + s.bias_off);
           float* stg = reinterpret_cast<float*>(smem + pl.off_stage_tok);
           const bool live = row < rows && my_w < nw;
           const bool poisoned = live && pz[my_w] != 0;
-          for (int cg = half; cg < (int)s.n_cg; cg += 2) {
+          // the previous tile's bulk store has read the staging area before anyone overwrites it
+          if (tt == 0) bulk_wait_read();
+          named_bar_sync(1 + team, kTeamWarps * 32);
+          for (int cg = 0; cg < (int)s.n_cg; ++cg) {
             float a[16];
             tmem_ld16(lane_base + (uint32_t)(s.tmem_col + cg * 16), a);
             tmem_ld_wait();
@@ -322,21 +388,19 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
               }
             }
           }
-          if (et < 64) poison[(par ^ 1u) * 64 + et] = 0;           // the next tile's flags
           fence_proxy_async();
-          named_bar_sync(1, kEpiWarps * 32);
-          if (et == 0)
+          named_bar_sync(1 + team, kTeamWarps * 32);
+          if (tt < 64) pz[tt] = 0;          // every thread has read its flag; this buffer is next used two tiles from now
+          if (tt == 0)
             bulk_store(tokens + (size_t)w_first * pl.S_out * pl.d_tok, stg, (uint32_t)nw * (uint32_t)(pl.S_out * pl.d_tok) * 4u);
         }
-        if (timing && it == stamp_it && warp == 4) T2_STAMP(4000 + e);      // body done
         fence_proxy_async();
-        if (timing && it == stamp_it && warp == 4) T2_STAMP(5000 + e);      // proxy fence done
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars[pl.bar_e0 + e]);
+        if (lane == 0) mbar_arrive(&bars[bar_mine + e]);
       }
     }
-    if (et == 0) bulk_wait_all();
+    if (tt == 0) bulk_wait_all();
   }
   tc_fence_before();
   __syncthreads();

@@ -17,26 +17,21 @@ eng.tokenize(x, precision="bf16"); torch.cuda.synchronize()
 buf = (C.c_longlong * 4096)()
 lib.sfdbg_tokenizer2_timing(0, buf, 4096)
 a = np.array(buf[:]).reshape(-1, 2)
-g = a[:512][(a[:512, 0] >= 1000) & (a[:512, 0] < 1500)]
-ea = a[512:]
-e = ea[(ea[:, 0] >= 2000) & (ea[:, 0] < 3000)]
-sub = {k: {int(i) - k: int(t) for i, t in ea[(ea[:, 0] >= k) & (ea[:, 0] < k + 500)]} for k in (1500, 3000, 4000, 5000)}
+g = a[:512][(a[:512, 0] >= 1000) & (a[:512, 0] < 2000)]
+teams = [a[512:1280], a[1280:]]
+teams = [t[(t[:, 0] >= 2000) & (t[:, 0] < 3000)] for t in teams]
 if len(g) == 0:
     raise SystemExit("no stamps (tokenizer v2 not used for this shape?)")
-t0 = min(g[0, 1], e[0, 1])
+t0 = min([g[0, 1]] + [t[0, 1] for t in teams if len(t)])
 print("MMA groups (id, start, delta to previous):")
 prev = g[0, 1]
 for i, t in g:
     print(f"  G{i-1000:3d}  @{t-t0:7d}  +{t-prev:6d}")
     prev = t
-print("epilogue stages (warp 4):")
-prev = e[0, 1]
-for i, t in e:
-    k = int(i) - 2000
-    det = "  wait %5d" % (t - sub[1500][k]) if k in sub[1500] else ""
-    if k in sub[3000]: det += "  tmem-ld %5d" % (sub[3000][k] - t)
-    if k in sub[4000]: det += "  body-done %5d" % (sub[4000][k] - t)
-    if k in sub[5000] and k in sub[4000]: det += "  proxy-fence %5d" % (sub[5000][k] - sub[4000][k])
-    print(f"  E{k:3d}  @{t-t0:7d}  +{t-prev:6d}{det}")
-    prev = t
-print("tile span (G first -> last stamp):", g[-1, 1] - g[0, 1], " E:", e[-1, 1] - e[0, 1])
+for k, e in enumerate(teams):
+    print(f"epilogue team {k} stages (first warp of the team):")
+    prev = e[0, 1]
+    for i, t in e:
+        print(f"  E{k}.{i-2000:<3d}  @{t-t0:7d}  +{t-prev:6d}")
+        prev = t
+print("tile span (G first -> last stamp):", g[-1, 1] - g[0, 1])
