@@ -27,9 +27,9 @@ namespace t2 {
 
 constexpr int kRows = 128;               // MMA M
 constexpr uint32_t kPlane = 2048;        // bytes of one 8-column chunk of a 128-row activation buffer
-constexpr int kTeams = 2;                // epilogue teams: warps 4-7 and 8-11, one warp per 32-lane TMEM quarter
-constexpr int kTeamWarps = 4;
-constexpr int kThreads = 384;            // warp 0: MMA issue, warp 1: TMA, warps 2-3: idle, warps 4-11: epilogue
+constexpr int kTeams = 2;                // epilogue teams: warps 4-11 and 12-19; a team = 4 TMEM lane quarters x 2 column halves
+constexpr int kTeamWarps = 8;
+constexpr int kThreads = 128 + kTeams * kTeamWarps * 32;   // warp 0: MMA issue, warp 1: TMA, warps 2-3: idle, then the teams
 constexpr int kMaxGroups = 80, kMaxStages = 72, kMaxLoads = 10, kMaxMma = 384;
 constexpr int kMaxC0 = 64;               // block-0 output channels handled by the CUDA-core graph conv
 

@@ -269,7 +269,7 @@ bool emulate(const Static& st, const Program& pr, const float* poses, int64_t B,
       const int tm = (act - A_E0) / kTeamWarps, w = (act - A_E0) % kTeamWarps;
       WarpState& W = ws[tm][w];
       const Stage& s = pr.stages[tm][W.e];
-      const int q = w;
+      const int q = w & 3, half = w >> 2;
       const int64_t tile = W.it;
       const int nw = (int)std::min<int64_t>(pl.WT, B - tile * pl.WT);
       const int par = (int)(W.it & 1);
@@ -283,7 +283,7 @@ bool emulate(const Static& st, const Program& pr, const float* poses, int64_t B,
       const float* xin = reinterpret_cast<const float*>(&E.smem[pl.off_xin]);
       bool finish = false;
       if (s.type == ST_CVT) {
-        for (int cg = 0; cg < s.n_cg; ++cg)
+        for (int cg = half; cg < s.n_cg; cg += 2)
           for (int ln = 0; ln < 32; ++ln) {
             const int row = q * 32 + ln;
             float a[16];
@@ -317,14 +317,14 @@ bool emulate(const Static& st, const Program& pr, const float* poses, int64_t B,
               }
               if (bad) m[0] = m[1] = 0.f;
             }
-            for (int cg = 0; cg < cp0 / 16; ++cg) {
-              float a[16];
-              for (int j = 0; j < 16; ++j) {
-                const int o = cg * 16 + j;
-                a[j] = valid ? std::fmaf(m[0], tabv(g0tab, 0, o), std::fmaf(m[1], tabv(g0tab, 1, o), tabv(g0tab, 2, o))) : 0.f;
+            for (int c8 = half; c8 < cp0 / 8; c8 += 2)
+              for (int j = 0; j < 8; ++j) {
+                const int o = c8 * 8 + j;
+                const float y = std::fmaf(m[0], tabv(g0tab, 0, o), std::fmaf(m[1], tabv(g0tab, 1, o), tabv(g0tab, 2, o)));
+                const uint16_t hb = pack_one(y, true);
+                const int col = (t - s.p0) * cp0 + o;
+                memcpy(&E.smem[s.dst_off + (uint32_t)(col / 8) * kPlane + (uint32_t)row * 16 + (uint32_t)(col % 8) * 2], &hb, 2);
               }
-              put16(s.dst_off, row, (t - s.p0) * (cp0 / 16) + cg, a, true);
-            }
           }
           if (bad) poison[par * 64 + ww] = 1;
         }
@@ -335,7 +335,7 @@ bool emulate(const Static& st, const Program& pr, const float* poses, int64_t B,
           for (int ln = 0; ln < 32; ++ln) {
             const int row = q * 32 + ln;
             for (int i = 0; i < s.p1 - s.p0; ++i)
-              for (int cg = 0; cg < cp0 / 16; ++cg) {
+              for (int cg = half; cg < cp0 / 16; cg += 2) {
                 float a[16];
                 for (int j = 0; j < 16; ++j) {
                   const int o = cg * 16 + j;
@@ -383,7 +383,7 @@ bool emulate(const Static& st, const Program& pr, const float* poses, int64_t B,
         } else if (W.sub == 1) {
           float* stg = reinterpret_cast<float*>(&E.smem[pl.off_stage_tok]);
           const float* bp = reinterpret_cast<const float*>(&E.smem[s.bias_off]);
-          for (int cg = 0; cg < s.n_cg; ++cg)
+          for (int cg = half; cg < s.n_cg; cg += 2)
             for (int ln = 0; ln < 32; ++ln) {
               const int row = q * 32 + ln, mw = row / V, mv = row - mw * V;
               if (!(row < rows && mw < nw)) continue;

@@ -26,6 +26,24 @@ namespace {
 using namespace tc;
 using namespace t2;
 
+// Blocking wait with a suspend-time hint: the waiting warp is parked by the hardware instead of spinning through the
+// scheduler's issue slots (the MMA warp, the TMA thread and the idle epilogue team share their SM sub-partitions with the
+// team that is working).
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.b32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity), "r"(0x989680u)
+        : "memory");
+  } while (!ok);
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -45,6 +63,35 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
 __device__ __forceinline__ uint32_t pack2_relu(float lo, float hi) {
   uint32_t d;
   asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+
+// packed fp32 pairs (sm_100 FFMA2 / FADD2): two exact fp32 operations per issue slot
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n"
+      ".reg .b64 ra, rb, rc, rd;\n"
+      "mov.b64 ra, {%2, %3};\n"
+      "mov.b64 rb, {%4, %5};\n"
+      "mov.b64 rc, {%6, %7};\n"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n"
+      "mov.b64 {%0, %1}, rd;\n"
+      "}\n"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n"
+      ".reg .b64 ra, rb, rd;\n"
+      "mov.b64 ra, {%2, %3};\n"
+      "mov.b64 rb, {%4, %5};\n"
+      "add.rn.f32x2 rd, ra, rb;\n"
+      "mov.b64 {%0, %1}, rd;\n"
+      "}\n"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
   return d;
 }
 
@@ -83,74 +130,80 @@ __device__ __forceinline__ void store16(unsigned char* dst_row, int cg, const fl
 // Block 0, one time slice [p0, p1) (at most two time steps) for one row (window w, keypoint v) on the CUDA cores, fp32:
 //   m_c = sum_u A_hat[v][u] * bn(x[c][t][u])      (BatchNorm1d folded into the coefficient row, shopformer/models/gcae.py:351-355)
 //   g_o = relu(m_x * W[x][o] + m_y * W[y][o] + b[o])   (graph conv, gcae.py:124-154)  -> bf16 operand slot of the temporal conv
-// The weight table is read once per 8 output channels and applied to both time steps (broadcast shared-memory loads).
+// The two column halves of a team take alternate 8-channel granules; the weight table is read once per granule and
+// applied to both time steps (broadcast shared-memory loads, packed fp32x2 FMAs).  Rows beyond the tile's windows
+// produce finite values nobody reads.
 template <int KW>
-__device__ __forceinline__ void g0_stage(const Plan& pl, const Stage& s, unsigned char* smem, int row, int my_w, int my_v, int nw, int* pz) {
-  const int V = pl.V, tv = pl.T0 * V, cp0 = pl.cp0;
+__device__ __forceinline__ void g0_stage(const Plan& pl, const Stage& s, unsigned char* smem, int row, int half, int my_w, int my_v, int nw,
+                                         int* pz) {
+  const int V = pl.V, tv4 = pl.T0 * V * 4, cp0 = pl.cp0;
   const bool valid = row < pl.rows && my_w < nw;
   const bool two = pl.c_in > 1;
   unsigned char* dst_row = smem + s.dst_off + (size_t)row * 16;
   const int nt = (int)s.p1 - (int)s.p0;              // 1 or 2
-  float m0[2] = {0.f, 0.f}, m1[2] = {0.f, 0.f};
+  float2 mx[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, my[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
   bool bad = false;
   if (valid) {
     const float4* coef = reinterpret_cast<const float4*>(smem + pl.off_ell);
     const float2 hc = reinterpret_cast<const float2*>(smem + pl.off_hc)[my_v];
-    const float* xw = reinterpret_cast<const float*>(smem + pl.off_xin) + my_w * pl.per_w + my_v + (int)s.p0 * V;
+    const unsigned char* xw = smem + pl.off_xin + (size_t)(my_w * pl.per_w + my_v + (int)s.p0 * V) * 4;
     float4 cf[KW];
 #pragma unroll
     for (int k = 0; k < KW; ++k) cf[k] = coef[k * V + my_v];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       if (h < nt) {
-        const float* xp = xw + h * V;
+        const unsigned char* xp = xw + h * V * 4;
         float x0[KW], x1[KW];
 #pragma unroll
         for (int k = 0; k < KW; ++k) {
-          const int dl = __float_as_int(cf[k].z);
-          x0[k] = xp[dl];
-          x1[k] = two ? xp[tv + dl] : 0.f;
+          const int db = __float_as_int(cf[k].z) * 4;           // neighbour's byte offset
+          x0[k] = *reinterpret_cast<const float*>(xp + db);
+          x1[k] = two ? *reinterpret_cast<const float*>(xp + tv4 + db) : 0.f;
         }
-        float a0 = hc.x, a1 = hc.y;
+        float a0 = hc.x, a1 = hc.y, amax = 0.f;
 #pragma unroll
         for (int k = 0; k < KW; ++k) {
-          bad |= !(fabsf(x0[k]) <= 3.0e38f) | !(fabsf(x1[k]) <= 3.0e38f);
+          amax = fmaxf(amax, fmaxf(fabsf(x0[k]), fabsf(x1[k])));
           a0 = fmaf(cf[k].x, x0[k], a0);
           a1 = fmaf(cf[k].y, x1[k], a1);
         }
-        m0[h] = bad ? 0.f : a0;
-        m1[h] = bad ? 0.f : a1;
+        const bool b = !(amax <= 3.0e38f);                      // inf or NaN among the gathered poses
+        bad |= b;
+        mx[h] = b ? make_float2(0.f, 0.f) : make_float2(a0, a0);
+        my[h] = b ? make_float2(0.f, 0.f) : make_float2(a1, a1);
       }
     }
   }
   const float4* tab = reinterpret_cast<const float4*>(smem + pl.off_g0tab);
   const int chunks = cp0 / 8;                         // 8-channel granules per time step
-  for (int c8 = 0; c8 < chunks; ++c8) {
-    float w[24];
+  for (int c8 = half; c8 < chunks; c8 += 2) {
+    float4 w[6];                                      // (wx, wy, b) of outputs 8 c8 .. +4, then +4 .. +8
 #pragma unroll
-    for (int i = 0; i < 6; ++i) *reinterpret_cast<float4*>(&w[4 * i]) = tab[c8 * 6 + i];     // (wx, wy, b) of outputs 8 c8 .. +4, then +4 .. +8
+    for (int i = 0; i < 6; ++i) w[i] = tab[c8 * 6 + i];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       if (h < nt) {
-        float y[8];
+        float2 y[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int g = (j >> 2) * 12 + (j & 3);
-          y[j] = valid ? fmaf(m0[h], w[g], fmaf(m1[h], w[g + 4], w[g + 8])) : 0.f;
+        for (int g = 0; g < 2; ++g) {
+          y[2 * g] = fma2(mx[h], make_float2(w[3 * g].x, w[3 * g].y), fma2(my[h], make_float2(w[3 * g + 1].x, w[3 * g + 1].y), make_float2(w[3 * g + 2].x, w[3 * g + 2].y)));
+          y[2 * g + 1] = fma2(mx[h], make_float2(w[3 * g].z, w[3 * g].w), fma2(my[h], make_float2(w[3 * g + 1].z, w[3 * g + 1].w), make_float2(w[3 * g + 2].z, w[3 * g + 2].w)));
         }
         *reinterpret_cast<uint4*>(dst_row + (size_t)(h * chunks + c8) * kPlane) =
-            make_uint4(pack2_relu(y[0], y[1]), pack2_relu(y[2], y[3]), pack2_relu(y[4], y[5]), pack2_relu(y[6], y[7]));
+            make_uint4(pack2_relu(y[0].x, y[0].y), pack2_relu(y[1].x, y[1].y), pack2_relu(y[2].x, y[2].y), pack2_relu(y[3].x, y[3].y));
       }
     }
   }
   // a window with a non-finite pose is reported as NaN tokens (the mix MMA would otherwise spread it over the tile)
-  if (bad) atomicOr(&pz[my_w], 1);
+  if (bad && half == 0) atomicOr(&pz[my_w], 1);
 }
 
 // Block 0 output for output times [p0, p1): x1 = relu(acc + BN-folded strided 1x1 residual conv of the raw poses + bias)
 // (gcae.py:237-259); the residual (2 input channels) is added in fp32 here instead of going through the tensor cores.
-__device__ __forceinline__ void xepi0_stage(const Plan& pl, const Stage& s, unsigned char* smem, uint32_t lane_base, int row, int my_w, int my_v,
-                                            int nw, int team) {
+// The two column halves of a team take alternate 16-channel groups.
+__device__ __forceinline__ void xepi0_stage(const Plan& pl, const Stage& s, unsigned char* smem, uint32_t lane_base, int row, int half, int my_w,
+                                            int my_v, int nw, int team) {
   const int V = pl.V, tv = pl.T0 * V, cp0 = pl.cp0;
   const bool valid = row < pl.rows && my_w < nw;
   const bool two = pl.c_in > 1;
@@ -176,7 +229,7 @@ __device__ __forceinline__ void xepi0_stage(const Plan& pl, const Stage& s, unsi
       if (valid && i < ntp) {
         const float* xp = xw + pl.stride0 * ((int)s.p0 + i) * V;
         float u = xp[0], w = two ? xp[tv] : 0.f;
-        if (!(fabsf(u) <= 3.0e38f) || !(fabsf(w) <= 3.0e38f)) u = w = 0.f;       // (the window is already flagged by its G0 stages)
+        if (!(fmaxf(fabsf(u), fabsf(w)) <= 3.0e38f)) u = w = 0.f;       // (the window is already flagged by its G0 stages)
         xa[i] = fmaf(u, sc0, sh0);
         xb[i] = fmaf(w, sc1, sh1);
       }
@@ -187,28 +240,22 @@ __device__ __forceinline__ void xepi0_stage(const Plan& pl, const Stage& s, unsi
   unsigned char* dst_row = smem + s.dst_off + (size_t)row * 16;
   const float4* tab = reinterpret_cast<const float4*>(smem + pl.off_r0tab);
   const int cgs = cp0 / 16;
-  for (int cg = 0; cg < cgs; ++cg) {
-    float w[48];                                        // (rx, ry, rb) of 16 output channels
+  for (int cg = half; cg < cgs; cg += 2) {
 #pragma unroll
-    for (int i = 0; i < 12; ++i) *reinterpret_cast<float4*>(&w[4 * i]) = tab[cg * 12 + i];
-#pragma unroll
-    for (int i0 = 0; i0 < kMaxT; i0 += 2) {
-      if (i0 < ntp) {
-        float a[2][16];
-        tmem_ld16(lane_base + (uint32_t)(s.tmem_col + i0 * cp0 + cg * 16), a[0]);
-        if (i0 + 1 < ntp) tmem_ld16(lane_base + (uint32_t)(s.tmem_col + (i0 + 1) * cp0 + cg * 16), a[1]);
+    for (int i = 0; i < kMaxT; ++i) {
+      if (i < ntp) {
+        float a[16];
+        tmem_ld16(lane_base + (uint32_t)(s.tmem_col + i * cp0 + cg * 16), a);
         tmem_ld_wait();
+        const float2 u2 = make_float2(xa[i], xa[i]), w2 = make_float2(xb[i], xb[i]);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          if (i0 + h < ntp) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int g = (j >> 2) * 12 + (j & 3);
-              a[h][j] += fmaf(xa[i0 + h], w[g], fmaf(xb[i0 + h], w[g + 4], w[g + 8]));
-            }
-            store16<true>(dst_row, (i0 + h) * cgs + cg, a[h]);
-          }
+        for (int g = 0; g < 4; ++g) {                    // 4 output channels per table entry (rx, ry, rb)
+          const float4 rx = tab[cg * 12 + 3 * g], ry = tab[cg * 12 + 3 * g + 1], rb = tab[cg * 12 + 3 * g + 2];
+          const float2 r0 = fma2(u2, make_float2(rx.x, rx.y), fma2(w2, make_float2(ry.x, ry.y), make_float2(rb.x, rb.y)));
+          const float2 r1 = fma2(u2, make_float2(rx.z, rx.w), fma2(w2, make_float2(ry.z, ry.w), make_float2(rb.z, rb.w)));
+          a[4 * g + 0] += r0.x; a[4 * g + 1] += r0.y; a[4 * g + 2] += r1.x; a[4 * g + 3] += r1.y;
         }
+        store16<true>(dst_row, i * cgs + cg, a);
       }
     }
   }
@@ -260,10 +307,10 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
       const uint32_t par = it & 1u;
       for (int g = 0; g < pl.n_groups; ++g) {
         const Group gr = pl.groups[g];
-        if (gr.wait_e[0] >= 0) mbar_wait(&bars[pl.bar_e0[0] + gr.wait_e[0]], par);
-        if (gr.wait_e[1] >= 0) mbar_wait(&bars[pl.bar_e0[1] + gr.wait_e[1]], par);
-        if (gr.wait_l >= 0) mbar_wait(&bars[pl.bar_l0 + gr.wait_l], par);
-        if (gr.prev_stage >= 0 && it > 0) mbar_wait(&bars[pl.bar_e0[gr.prev_team] + gr.prev_stage], par ^ 1u);
+        if (gr.wait_e[0] >= 0) mbar_wait_parked(&bars[pl.bar_e0[0] + gr.wait_e[0]], par);
+        if (gr.wait_e[1] >= 0) mbar_wait_parked(&bars[pl.bar_e0[1] + gr.wait_e[1]], par);
+        if (gr.wait_l >= 0) mbar_wait_parked(&bars[pl.bar_l0 + gr.wait_l], par);
+        if (gr.prev_stage >= 0 && it > 0) mbar_wait_parked(&bars[pl.bar_e0[gr.prev_team] + gr.prev_stage], par ^ 1u);
         tc_fence_after();
         if (timing && it == stamp_it) T2_STAMP(1000 + g);
         if (elect_one()) {
@@ -293,10 +340,10 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
         const uint32_t par = it & 1u;
         for (int l = 0; l < pl.n_loads; ++l) {
           const Load ld = pl.loads[l];
-          if (ld.wait_g >= 0) mbar_wait(&bars[pl.bar_g0 + ld.wait_g], par);
-          if (ld.wait_e[0] >= 0) mbar_wait(&bars[pl.bar_e0[0] + ld.wait_e[0]], par);
-          if (ld.wait_e[1] >= 0) mbar_wait(&bars[pl.bar_e0[1] + ld.wait_e[1]], par);
-          if (ld.wait_g_prev >= 0 && it > 0) mbar_wait(&bars[pl.bar_g0 + ld.wait_g_prev], par ^ 1u);
+          if (ld.wait_g >= 0) mbar_wait_parked(&bars[pl.bar_g0 + ld.wait_g], par);
+          if (ld.wait_e[0] >= 0) mbar_wait_parked(&bars[pl.bar_e0[0] + ld.wait_e[0]], par);
+          if (ld.wait_e[1] >= 0) mbar_wait_parked(&bars[pl.bar_e0[1] + ld.wait_e[1]], par);
+          if (ld.wait_g_prev >= 0 && it > 0) mbar_wait_parked(&bars[pl.bar_g0 + ld.wait_g_prev], par ^ 1u);
           if (ld.kind == LD_WEIGHTS) {
             uint64_t* bar = &bars[pl.bar_l0 + l];
             mbar_expect_tx(bar, ld.bytes);
@@ -308,9 +355,10 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
       }
     }
   } else if (warp >= 4) {
-    // =================================================================== epilogue: two teams of four warps
-    const int team = (warp - 4) >> 2, q = warp & 3;
-    const int tt = (int)threadIdx.x - 128 - team * 128;     // thread within the team = MMA row
+    // =================================================================== epilogue: two teams of eight warps
+    // (a team = 4 TMEM lane quarters x 2 column halves; many resident warps are what hides the CUDA-core latencies)
+    const int team = (warp - 4) >> 3, q = warp & 3, half = ((warp - 4) >> 2) & 1;
+    const int tt = (int)threadIdx.x - 128 - team * (kTeamWarps * 32);     // thread within the team
     const int row = q * 32 + lane;
     const int V = pl.V, rows = pl.rows;
     const int my_w = row / V, my_v = row - my_w * V;
@@ -325,33 +373,35 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
       int* pz = poison + par * 64;
       for (int e = 0; e < n_st; ++e) {
         const Stage s = pl.stages[team][e];
-        if (s.wait_g >= 0) mbar_wait(&bars[pl.bar_g0 + s.wait_g], par);
-        if (s.wait_l >= 0) mbar_wait(&bars[pl.bar_l0 + s.wait_l], par);
-        if (s.wait_eo >= 0) mbar_wait(&bars[bar_other + s.wait_eo], par);
-        if (s.wait_g_prev >= 0 && it > 0) mbar_wait(&bars[pl.bar_g0 + s.wait_g_prev], par ^ 1u);
+        if (s.wait_g >= 0) mbar_wait_parked(&bars[pl.bar_g0 + s.wait_g], par);
+        if (s.wait_l >= 0) mbar_wait_parked(&bars[pl.bar_l0 + s.wait_l], par);
+        if (s.wait_eo >= 0) mbar_wait_parked(&bars[bar_other + s.wait_eo], par);
+        if (s.wait_g_prev >= 0 && it > 0) mbar_wait_parked(&bars[pl.bar_g0 + s.wait_g_prev], par ^ 1u);
         tc_fence_after();
         if (timing && it == stamp_it && q == 0) T2_STAMP(2000 + e);
         if (s.type == ST_CVT) {
           const bool relu = s.flags & SF_RELU, bias = s.flags & SF_BIAS;
           const float* bp = reinterpret_cast<const float*>(smem + s.bias_off);
           unsigned char* dst = smem + s.dst_off + (size_t)row * 16;
-          // up to four TMEM loads in flight before one wait
-          for (int cg0 = 0; cg0 < (int)s.n_cg; cg0 += 4) {
-            float a[4][16];
+          // this warp's column groups: cg = half, half + 2, ...; two TMEM loads in flight before one wait
+          for (int cg0 = half; cg0 < (int)s.n_cg; cg0 += 4) {
+            float a[2][16];
 #pragma unroll
-            for (int b = 0; b < 4; ++b)
-              if (cg0 + b < (int)s.n_cg) tmem_ld16(lane_base + (uint32_t)(s.tmem_col + (cg0 + b) * 16), a[b]);
+            for (int b = 0; b < 2; ++b)
+              if (cg0 + 2 * b < (int)s.n_cg) tmem_ld16(lane_base + (uint32_t)(s.tmem_col + (cg0 + 2 * b) * 16), a[b]);
             tmem_ld_wait();
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-              const int cg = cg0 + b;
+            for (int b = 0; b < 2; ++b) {
+              const int cg = cg0 + 2 * b;
               if (cg < (int)s.n_cg) {
                 if (bias) {
                   const float* b16 = bp + (cg * 16) % s.bias_period;
 #pragma unroll
                   for (int j = 0; j < 4; ++j) {
                     const float4 bb = *reinterpret_cast<const float4*>(b16 + 4 * j);
-                    a[b][4 * j + 0] += bb.x; a[b][4 * j + 1] += bb.y; a[b][4 * j + 2] += bb.z; a[b][4 * j + 3] += bb.w;
+                    const float2 s0 = add2(make_float2(a[b][4 * j], a[b][4 * j + 1]), make_float2(bb.x, bb.y));
+                    const float2 s1 = add2(make_float2(a[b][4 * j + 2], a[b][4 * j + 3]), make_float2(bb.z, bb.w));
+                    a[b][4 * j + 0] = s0.x; a[b][4 * j + 1] = s0.y; a[b][4 * j + 2] = s1.x; a[b][4 * j + 3] = s1.y;
                   }
                 }
                 if (relu) store16<true>(dst, cg, a[b]);
@@ -360,10 +410,10 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
             }
           }
         } else if (s.type == ST_G0) {
-          if (pl.ell_width <= 5) g0_stage<5>(pl, s, smem, row, my_w, my_v, nw, pz);
-          else g0_stage<8>(pl, s, smem, row, my_w, my_v, nw, pz);
+          if (pl.ell_width <= 5) g0_stage<5>(pl, s, smem, row, half, my_w, my_v, nw, pz);
+          else g0_stage<8>(pl, s, smem, row, half, my_w, my_v, nw, pz);
         } else if (s.type == ST_XEPI0) {
-          xepi0_stage(pl, s, smem, lane_base, row, my_w, my_v, nw, team);
+          xepi0_stage(pl, s, smem, lane_base, row, half, my_w, my_v, nw, team);
         } else {   // ST_TOKENS
           const float* bp = reinterpret_cast<const float*>(smem + s.bias_off);
           float* stg = reinterpret_cast<float*>(smem + pl.off_stage_tok);
@@ -372,7 +422,7 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
           // the previous tile's bulk store has read the staging area before anyone overwrites it
           if (tt == 0) bulk_wait_read();
           named_bar_sync(1 + team, kTeamWarps * 32);
-          for (int cg = 0; cg < (int)s.n_cg; ++cg) {
+          for (int cg = half; cg < (int)s.n_cg; cg += 2) {
             float a[16];
             tmem_ld16(lane_base + (uint32_t)(s.tmem_col + cg * 16), a);
             tmem_ld_wait();
