@@ -161,14 +161,14 @@ __device__ __forceinline__ void g0_stage(const Plan& pl, const Stage& s, unsigne
           x0[k] = *reinterpret_cast<const float*>(xp + db);
           x1[k] = two ? *reinterpret_cast<const float*>(xp + tv4 + db) : 0.f;
         }
-        float a0 = hc.x, a1 = hc.y, amax = 0.f;
+        float a0 = hc.x, a1 = hc.y, chk = 0.f;
 #pragma unroll
         for (int k = 0; k < KW; ++k) {
-          amax = fmaxf(amax, fmaxf(fabsf(x0[k]), fabsf(x1[k])));
+          chk = fmaf(x0[k], 0.f, fmaf(x1[k], 0.f, chk));        // stays 0 unless a gathered pose is inf or NaN
           a0 = fmaf(cf[k].x, x0[k], a0);
           a1 = fmaf(cf[k].y, x1[k], a1);
         }
-        const bool b = !(amax <= 3.0e38f);                      // inf or NaN among the gathered poses
+        const bool b = !(chk == 0.f);
         bad |= b;
         mx[h] = b ? make_float2(0.f, 0.f) : make_float2(a0, a0);
         my[h] = b ? make_float2(0.f, 0.f) : make_float2(a1, a1);
@@ -229,7 +229,7 @@ __device__ __forceinline__ void xepi0_stage(const Plan& pl, const Stage& s, unsi
       if (valid && i < ntp) {
         const float* xp = xw + pl.stride0 * ((int)s.p0 + i) * V;
         float u = xp[0], w = two ? xp[tv] : 0.f;
-        if (!(fmaxf(fabsf(u), fabsf(w)) <= 3.0e38f)) u = w = 0.f;       // (the window is already flagged by its G0 stages)
+        if (!(fmaf(u, 0.f, w * 0.f) == 0.f)) u = w = 0.f;                 // inf / NaN (the window is already flagged by its G0 stages)
         xa[i] = fmaf(u, sc0, sh0);
         xb[i] = fmaf(w, sc1, sh1);
       }

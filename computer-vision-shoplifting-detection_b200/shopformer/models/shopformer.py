@@ -81,9 +81,10 @@ class Shopformer(nn.Module, EngineCacheMixin):
     def forward(self, poses: torch.Tensor, return_tokens: bool = False) -> Dict[str, torch.Tensor]:
         if wants_native(self, poses):
             x = self.gcae.encoder._as_bctv(poses)
-            score, tokens, recon = self._sf_engine().score_windows(x, return_tokens=True, return_recon=True)
+            score, tokens, recon = self._sf_engine().score_windows(x, precision=self._sf_resolve_precision(),
+                                                                   return_tokens=True, return_recon=True)
             out = LazyOutput({"normality_score": score, "reconstructed_tokens": recon},
-                             {"gcae_reconstructed": lambda: self.gcae.decode(tokens)})
+                             {"gcae_reconstructed": lambda: self._decode_eval(tokens)})
             if return_tokens:
                 out["tokens"] = tokens
             return out
@@ -94,6 +95,18 @@ class Shopformer(nn.Module, EngineCacheMixin):
         if return_tokens:
             out["tokens"] = tokens
         return out
+
+    def _decode_eval(self, tokens: torch.Tensor) -> torch.Tensor:
+        """The pose decoder with the semantics of the call that produced `tokens` (eval-mode BatchNorm, no dropout, no
+        autograd graph), whatever mode the model is in when the lazy output is finally read."""
+        dec = self.gcae.decoder
+        was_training = dec.training
+        try:
+            dec.eval()
+            with torch.no_grad():
+                return dec(tokens)
+        finally:
+            dec.train(was_training)
 
     def predict(self, poses: torch.Tensor, threshold: float = 0.5) -> torch.Tensor:
         with torch.no_grad():

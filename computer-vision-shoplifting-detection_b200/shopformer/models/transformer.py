@@ -63,7 +63,7 @@ class ShopformerTransformer(nn.Module, _Owned):
         if wants_native(self, tokens):
             eng = self._engine()
             if eng is not None:
-                return eng.reconstruct_tokens(tokens)
+                return eng.reconstruct_tokens(tokens, precision=self._precision())
         memory = self.encode(tokens)
         start = torch.zeros(tokens.size(0), 1, self.d_model, device=tokens.device)
         shifted = torch.cat([start, tokens[:, :-1, :]], dim=1)

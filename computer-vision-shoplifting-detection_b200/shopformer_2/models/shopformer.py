@@ -89,7 +89,7 @@ class Shopformer(nn.Module, EngineCacheMixin):
         with torch.no_grad():
             if poses.is_cuda:
                 x = self.gcae.encoder._as_bctv(poses)
-                return self._sf_engine().score_windows(x, reduction=reduction)
+                return self._sf_engine().score_windows(x, reduction=reduction, precision=self._sf_resolve_precision())
             if not composite_eval_allowed():
                 raise RuntimeError("shopformer_b200: compute_anomaly_score runs on CUDA (sm_100a) only; "
                                    "there is no CPU fallback")

@@ -59,7 +59,7 @@ class ShopformerTransformer(nn.Module, _Owned):
         if unmasked and self.activation_name == "gelu" and wants_native(self, tokens):
             eng = self._engine()
             if eng is not None:
-                return eng.reconstruct_tokens(tokens)
+                return eng.reconstruct_tokens(tokens, precision=self._precision())
         x = self._embed(tokens)
         memory = self.encoder(x, mask=src_mask, src_key_padding_mask=src_key_padding_mask)
         out = self.decoder(x, memory, tgt_mask=tgt_mask, memory_mask=src_mask,

@@ -84,6 +84,9 @@ class ScoringEngine:
         self._lib = lib
         self._h = handle
         self._runners: Dict[Tuple[int, int], C.c_void_p] = {}
+        self._ws: Dict[int, torch.Tensor] = {}              # stream -> reusable workspace (grow-only)
+        self._auto: Dict[Tuple[str, int], str] = {}         # ("tok" | "xf", T or S) -> precision picked by "auto"
+        self._shape_cache: Dict[int, Tuple[int, int]] = {}
 
     # -- lifetime
     def close(self) -> None:
@@ -102,16 +105,43 @@ class ScoringEngine:
 
     # -- shapes
     def token_shape(self, T: int) -> Tuple[int, int]:
-        s, d = C.c_int32(), C.c_int32()
-        N.check(self._lib.sf_model_token_shape(self._h, T, C.byref(s), C.byref(d)), "sf_model_token_shape")
-        return s.value, d.value
+        hit = self._shape_cache.get(T)
+        if hit is None:
+            s, d = C.c_int32(), C.c_int32()
+            N.check(self._lib.sf_model_token_shape(self._h, T, C.byref(s), C.byref(d)), "sf_model_token_shape")
+            hit = self._shape_cache[T] = (s.value, d.value)
+        return hit
 
     def _workspace(self, B: int, T: int) -> Tuple[Optional[torch.Tensor], int]:
+        """Reusable per-stream workspace (grow-only): kernels of consecutive calls on one stream are ordered, so
+        the buffer of the previous call is free by the time the next call's kernels read it."""
         nbytes = self._lib.sf_workspace_bytes(self._h, B, T)
         N.check(int(min(nbytes, 0)), "sf_workspace_bytes")
         if nbytes == 0:
             return None, 0
-        return torch.empty(nbytes, dtype=torch.uint8, device=self.device), int(nbytes)
+        key = torch.cuda.current_stream(self.device).cuda_stream
+        buf = self._ws.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = self._ws[key] = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        return buf, int(nbytes)
+
+    # -- precision policy: "fp32" | "bf16" | "auto" (bf16 tensor-core kernels when they cover the shape, else fp32)
+    def _run_prec(self, kind: str, key: int, precision: str, call):
+        if precision in ("fp32", "bf16"):
+            return call(self._PREC[precision])
+        if precision != "auto":
+            raise ValueError(f"unknown precision {precision!r} (fp32 | bf16 | auto)")
+        pick = self._auto.get((kind, key))
+        if pick is None:
+            try:
+                out = call(N.SF_PREC_BF16)
+                self._auto[(kind, key)] = "bf16"
+                return out
+            except N.NativeError as exc:
+                if exc.code != -4:                 # only SF_E_UNSUPPORTED selects the other kernels
+                    raise
+                self._auto[(kind, key)] = pick = "fp32"
+        return call(self._PREC[pick])
 
     def _poses(self, poses: torch.Tensor) -> torch.Tensor:
         if poses.dim() != 4:
@@ -134,23 +164,38 @@ class ScoringEngine:
         elif out.shape != (B, S, D) or out.dtype != torch.float32 or not out.is_contiguous():
             raise ValueError("`out` must be a contiguous fp32 (B,S,D) tensor")
         ws, nb = self._workspace(B, T)
-        N.check(self._lib.sf_tokenize(self._h, _ptr(x), B, T, self._PREC[precision], _ptr(out), _ptr(ws), nb,
-                                      _stream_ptr(self.device)), "sf_tokenize")
+        st = _stream_ptr(self.device)
+        self._run_prec("tok", T, precision, lambda p: N.check(
+            self._lib.sf_tokenize(self._h, _ptr(x), B, T, p, _ptr(out), _ptr(ws), nb, st), "sf_tokenize"))
         return out
 
     def reconstruct_tokens(self, tokens: torch.Tensor, precision: str = "fp32", out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        t = tokens.to(self.device, torch.float32).contiguous()
+        t = self._tokens(tokens, "tokens")
         B, S, D = t.shape
         if out is None:
             out = torch.empty_like(t)
-        N.check(self._lib.sf_reconstruct_tokens(self._h, _ptr(t), B, S, self._PREC[precision], _ptr(out), None, 0,
-                                                _stream_ptr(self.device)),
-                "sf_reconstruct_tokens")
+        elif out.shape != t.shape or out.dtype != torch.float32 or not out.is_contiguous() or out.device != self.device:
+            raise ValueError("`out` must be a contiguous fp32 (B,S,D) tensor on the engine's device")
+        st = _stream_ptr(self.device)
+        self._run_prec("xf", S, precision, lambda p: N.check(
+            self._lib.sf_reconstruct_tokens(self._h, _ptr(t), B, S, p, _ptr(out), None, 0, st), "sf_reconstruct_tokens"))
         return out
 
+    def _tokens(self, t: torch.Tensor, what: str) -> torch.Tensor:
+        """(B,S,D) fp32 on the engine's device with the model's token width (the C ABI only receives S)."""
+        if t.dim() != 3 or t.shape[2] != self.cfg.channels[-1] * self.cfg.num_keypoints:
+            raise ValueError(f"{what} must be (B,S,{self.cfg.channels[-1] * self.cfg.num_keypoints}), got {tuple(t.shape)}")
+        if not 1 <= t.shape[1] <= 100:
+            raise ValueError(f"{what}: S={t.shape[1]} outside [1,100] (positional-encoding table)")
+        if not t.is_cuda:
+            raise RuntimeError("native scoring path takes CUDA tensors only (no CPU fallback)")
+        return t.to(self.device, torch.float32).contiguous()
+
     def normality_score(self, tokens: torch.Tensor, recon: torch.Tensor, reduction: str = "mean") -> torch.Tensor:
-        t = tokens.to(self.device, torch.float32).contiguous()
-        r = recon.to(self.device, torch.float32).contiguous()
+        t = self._tokens(tokens, "tokens")
+        if recon.shape != tokens.shape:
+            raise ValueError(f"recon {tuple(recon.shape)} must have the shape of tokens {tuple(tokens.shape)}")
+        r = self._tokens(recon, "recon")
         B, S, _ = t.shape
         red = self._reduction(reduction)
         out = torch.empty((B,) if red == N.SF_REDUCE_MEAN else (B, S), dtype=torch.float32, device=self.device)
@@ -174,7 +219,6 @@ class ScoringEngine:
         B, _, T, _ = x.shape
         S, D = self.token_shape(T)
         red = self._reduction(reduction)
-        prec = {"fp32": N.SF_PREC_FP32, "bf16": N.SF_PREC_BF16}[precision]
         shape = (B,) if red == N.SF_REDUCE_MEAN else (B, S)
         if out is not None:
             if out.shape != shape or out.dtype != torch.float32 or not out.is_contiguous() or out.device != self.device:
@@ -185,8 +229,10 @@ class ScoringEngine:
         tok = torch.empty(B, S, D, dtype=torch.float32, device=self.device) if return_tokens else None
         rec = torch.empty(B, S, D, dtype=torch.float32, device=self.device) if return_recon else None
         ws, nb = self._workspace(B, T)
-        N.check(self._lib.sf_score_windows(self._h, _ptr(x), B, T, red, prec, _ptr(scores), _ptr(tok), _ptr(rec), _ptr(ws), nb,
-                                           _stream_ptr(self.device)), "sf_score_windows")
+        st = _stream_ptr(self.device)
+        self._run_prec("score", T, precision, lambda p: N.check(
+            self._lib.sf_score_windows(self._h, _ptr(x), B, T, red, p, _ptr(scores), _ptr(tok), _ptr(rec), _ptr(ws), nb, st),
+            "sf_score_windows"))
         if return_tokens or return_recon:
             return scores, tok, rec
         return scores
@@ -205,9 +251,9 @@ class ScoringEngine:
             N.check(self._lib.sf_runner_create(self._h, T, chunk, C.byref(h)), "sf_runner_create")
             self._runners[key] = h
         out = np.empty(B, dtype=np.float32)
-        prec = {"fp32": N.SF_PREC_FP32, "bf16": N.SF_PREC_BF16}[precision]
-        N.check(self._lib.sf_runner_score(self._runners[key], C.c_void_p(a.ctypes.data), B, prec, C.c_void_p(out.ctypes.data)),
-                "sf_runner_score")
+        r = self._runners[key]
+        self._run_prec("score", T, precision, lambda p: N.check(
+            self._lib.sf_runner_score(r, C.c_void_p(a.ctypes.data), B, p, C.c_void_p(out.ctypes.data)), "sf_runner_score"))
         return out
 
 

@@ -8,31 +8,64 @@ correctness").
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
+import os
+from typing import List, Optional, Tuple
 
 import torch
 import torch.nn as nn
 
 from .engine import EngineConfig, ScoringEngine
 
+PRECISIONS = ("auto", "bf16", "fp32")
+
 
 class EngineCacheMixin:
-    """Mixed into the facade nn.Modules.  Sub-classes implement ``_sf_config()``."""
+    """Mixed into the facade nn.Modules.  Sub-classes implement ``_sf_config()``.
+
+    Precision policy of the eval-mode native path (every entry point of the facade and of its sub-modules):
+    ``model.sf_precision`` if set, else the environment variable ``SHOPFORMER_B200_PRECISION``, else ``"auto"`` =
+    the bf16 tcgen05 kernels (score within 1e-2 of the reference, north-star contract) whenever they cover the
+    shape, the fp32 kernels (1e-3 contract) otherwise.  Set ``"fp32"`` to force the precise path."""
+
+    sf_precision: Optional[str] = None
+
+    def _sf_resolve_precision(self) -> str:
+        p = self.sf_precision or os.environ.get("SHOPFORMER_B200_PRECISION") or "auto"
+        if p not in PRECISIONS:
+            raise ValueError(f"sf_precision / SHOPFORMER_B200_PRECISION must be one of {PRECISIONS}, got {p!r}")
+        return p
+
+    # The fingerprint walks a cached tensor list (no module traversal on the per-batch path).  The list is rebuilt
+    # whenever the module tree may have swapped tensors (``_apply`` = .to()/.cuda()/.half(), ``load_state_dict``) and,
+    # as a safety net against parameters replaced by attribute assignment, every 256 calls.
+    def _sf_tensors(self) -> List[torch.Tensor]:
+        d = self.__dict__
+        n = d.get("_sf_calls", 0) + 1
+        d["_sf_calls"] = n
+        lst = d.get("_sf_tensor_list")
+        if lst is None or (n & 255) == 0:
+            lst = d["_sf_tensor_list"] = list(self.parameters()) + list(self.buffers())
+        return lst
+
+    def _apply(self, fn, *a, **kw):
+        self.__dict__.pop("_sf_tensor_list", None)
+        return super()._apply(fn, *a, **kw)
+
+    def load_state_dict(self, *a, **kw):
+        self.__dict__.pop("_sf_tensor_list", None)
+        return super().load_state_dict(*a, **kw)
 
     def _sf_fingerprint(self) -> Tuple:
-        fp = []
-        for t in list(self.parameters()) + list(self.buffers()):
-            fp.append((t.data_ptr(), t._version, t.device.index))
-        return tuple(fp)
+        return tuple((t.data_ptr(), t._version) for t in self._sf_tensors())
 
     def _sf_engine(self) -> ScoringEngine:
-        dev = next(self.parameters()).device
-        if dev.type != "cuda":
-            raise RuntimeError("shopformer_b200: the model must live on a CUDA device for inference (no CPU fallback)")
         fp = self._sf_fingerprint()
         cached = self.__dict__.get("_sf_cache")
         if cached is not None and cached[0] == fp:
             return cached[1]
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("shopformer_b200: the model must live on a CUDA device for inference (no CPU fallback)")
         if cached is not None:
             cached[1].close()
         eng = ScoringEngine(self._sf_config(), self.state_dict(), dev)
@@ -52,6 +85,10 @@ class LazyOutput(dict):
     def __init__(self, eager: dict, lazy: dict):
         super().__init__(eager)
         self._lazy = dict(lazy)
+
+    def copy(self):
+        self._materialise()
+        return dict(self)
 
     def _materialise(self) -> None:
         while self._lazy:

@@ -121,6 +121,12 @@ def wants_native(module: nn.Module, x: torch.Tensor) -> bool:
     """True when this call is eval-mode inference and must run on the sm_100a kernels."""
     if module.training or torch.is_grad_enabled():
         return False                      # training / autograd: ATen composition below
+    owner_ref = getattr(module, "_sf_owner", None)
+    owner = owner_ref() if owner_ref is not None else None
+    if owner is not None and owner.training:
+        # stage-2 training with a frozen, eval-mode tokenizer (shopformer_2 freeze_gcae): the facade's other
+        # parameters change every optimizer step, so a packed native model would be rebuilt every step
+        return False
     if x.is_cuda:
         return True
     if composite_eval_allowed():
@@ -137,6 +143,10 @@ class _Owned:
     def _engine(self):
         owner = self._sf_owner() if self._sf_owner is not None else None
         return owner._sf_engine() if owner is not None else None
+
+    def _precision(self) -> str:
+        owner = self._sf_owner() if self._sf_owner is not None else None
+        return owner._sf_resolve_precision() if owner is not None else "auto"
 
 
 def adopt(owner: nn.Module, *children: nn.Module) -> None:
@@ -242,7 +252,7 @@ class GCAEEncoder(nn.Module, _Owned):
         if wants_native(self, x):
             eng = self._engine()
             if eng is not None:
-                return eng.tokenize(x)
+                return eng.tokenize(x, precision=self._precision())
         b, c, t, v = x.shape
         y = self.bn_input(x.permute(0, 1, 3, 2).reshape(b, c * v, t))
         x = y.view(b, c, v, t).permute(0, 1, 3, 2).contiguous()

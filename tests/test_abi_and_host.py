@@ -72,9 +72,17 @@ def test_training_path_is_autograd_capable(dropin1, dropin2):
     m2.train()
     assert not m2.gcae.training and m2.transformer.training
     x2 = torch.from_numpy(synth_windows(4, 12, 18, seed=0)[0])
-    # frozen tokenizer in eval mode under no_grad on a CPU tensor must refuse (it would be inference)
+    # stage 2 (facade in train mode, frozen tokenizer in eval mode): a training step, so the encoder runs the ATen
+    # composition too -- a packed native model would have to be rebuilt after every optimizer step
+    loss2 = m2.compute_transformer_loss(x2)
+    loss2.backward()
+    assert m2.transformer.output_projection is not None and "_sf_cache" not in m2.__dict__
+    assert all(p.grad is None for p in m2.gcae.parameters())
+    assert any(p.grad is not None for p in m2.transformer.parameters())
+    # ... while eval-mode inference on a CPU tensor still refuses: there is no CPU inference path
+    m2.eval()
     with pytest.raises(RuntimeError):
-        m2.compute_transformer_loss(x2)
+        m2.compute_anomaly_score(x2)
 
 
 def test_state_dict_surface(dropin1, dropin2):

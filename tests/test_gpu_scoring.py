@@ -20,6 +20,13 @@ pytestmark = pytest.mark.gpu
 FP32_TOL = 5e-5          # asserted; the contract is 1e-3
 
 
+@pytest.fixture(autouse=True)
+def _precise_kernels_through_the_facades(monkeypatch):
+    """This file checks the fp32 kernels at 5e-5 through the facades; the facades' default ("auto" = the bf16 tensor-core
+    kernels) is covered by test_gpu_reference_api.py."""
+    monkeypatch.setenv("SHOPFORMER_B200_PRECISION", "fp32")
+
+
 def gpu_scores(model, name, x):
     with torch.no_grad():
         if CFG.variant_of(name) == 1:
