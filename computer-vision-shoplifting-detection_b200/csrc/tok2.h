@@ -51,18 +51,16 @@ struct Group {               // G item: a run of MMAs followed by one commit
 enum StageType { ST_G0 = 0, ST_CVT = 1, ST_XEPI0 = 2, ST_TOKENS = 3 };
 enum StageFlags { SF_RELU = 1, SF_BIAS = 2, SF_TEAM_SYNC = 4 };
 
-struct Stage {               // E item (index = position in its TEAM's sequence)
-  uint8_t type, flags;
-  int16_t wait_g;            // G group of this tile (-1: none)
-  int16_t wait_l;            // L load (block-0 stages: the poses)
-  int16_t wait_eo;           // stage of the OTHER team, this tile
-  int16_t wait_g_prev;       // G group of the previous tile
-  uint16_t tmem_col, n_cg;   // CVT / XEPI0 / TOKENS: first accumulator column, number of 16-column groups
+struct Stage {               // E item (index = position in its TEAM's sequence); 32-bit fields: read with uniform constant loads
+  int32_t type, flags;
+  int32_t wait_g, wait_l, wait_eo, wait_g_prev;   // item indices (-1: none): G group / L load / other team's stage (this tile), G group (previous tile)
+  // the same waits as shared-memory byte offsets of the mbarriers (0: none), and this stage's own barrier
+  uint32_t bar_g, bar_l, bar_eo, bar_g_prev, bar_self;
+  int32_t tmem_col, n_cg;    // CVT / XEPI0 / TOKENS: first accumulator column, number of 16-column groups
   uint32_t dst_off;          // smem byte offset of destination column 0 (G0: the ring slot)
   uint32_t bias_off;         // byte offset of the fp32 bias vector (period `bias_period` columns)
-  uint16_t bias_period;
-  uint16_t p0, p1;           // G0: input time steps [p0, p1); XEPI0: output time steps [p0, p1)
-  uint16_t pad[3];
+  int32_t bias_period;
+  int32_t p0, p1;            // G0: input time steps [p0, p1); XEPI0: output time steps [p0, p1)
 };
 
 enum LoadKind { LD_WEIGHTS = 0, LD_POSES = 1 };

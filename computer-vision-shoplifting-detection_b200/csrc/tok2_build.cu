@@ -358,8 +358,8 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
     next_team ^= 1;
     Stage s;
     memset(&s, 0, sizeof(s));
-    s.type = (uint8_t)type;
-    s.flags = (uint8_t)flags;
+    s.type = type;
+    s.flags = flags;
     s.wait_g = s.wait_l = s.wait_eo = s.wait_g_prev = -1;
     pr.stages[team].push_back(s);
     order.push_back(Item{SIDE_E0 + team, (int)pr.stages[team].size() - 1, {}, {}});
@@ -367,11 +367,11 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
   };
   auto cvt_stage = [&](int tmem_col, int ncols, uint32_t dst_off, int flags, uint32_t bias_off, int period) {
     Stage& s = new_stage(ST_CVT, flags);
-    s.tmem_col = (uint16_t)tmem_col;
-    s.n_cg = (uint16_t)(ncols / 16);
+    s.tmem_col = tmem_col;
+    s.n_cg = ncols / 16;
     s.dst_off = dst_off;
     s.bias_off = bias_off;
-    s.bias_period = (uint16_t)period;
+    s.bias_period = period;
     order.back().rd.push_back(tmem_r(tmem_col, ncols));
     order.back().wr.push_back(smem_r(dst_off, (uint32_t)(ncols / 8) * kPlane));
   };
@@ -429,8 +429,8 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
       const uint32_t slot = pl.off_Q + (uint32_t)(i % ring0_slots) * ring0_slot;
       const int t0 = i * st0, nt = std::min(st0, T - t0);
       Stage& s = new_stage(ST_G0, SF_RELU);
-      s.p0 = (uint16_t)t0;
-      s.p1 = (uint16_t)(t0 + nt);
+      s.p0 = t0;
+      s.p1 = t0 + nt;
       s.dst_off = slot;
       order.back().rd = xin_rng;
       order.back().wr.push_back(smem_r(slot, (uint32_t)(nt * cp / 8) * kPlane));
@@ -454,11 +454,11 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
         if (ntp > 8) return fail("block-0 output chunk over the pose slot longer than 8 time steps");
       }
       Stage& s = new_stage(ST_XEPI0, SF_RELU | (hits_xin ? SF_TEAM_SYNC : 0));
-      s.tmem_col = (uint16_t)(tp0 * cp);
-      s.n_cg = (uint16_t)(ntp * cp / 16);
+      s.tmem_col = tp0 * cp;
+      s.n_cg = ntp * cp / 16;
       s.dst_off = dst;
-      s.p0 = (uint16_t)tp0;
-      s.p1 = (uint16_t)(tp0 + ntp);
+      s.p0 = tp0;
+      s.p1 = tp0 + ntp;
       order.back().rd = xin_rng;
       order.back().rd.push_back(tmem_r(tp0 * cp, ntp * cp));
       order.back().wr.push_back(smem_r(dst, bytes));
@@ -523,10 +523,10 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
         cvt_stage(acc + c0, std::min(cw, accw - c0), xn + (uint32_t)(c0 / 8) * kPlane, SF_RELU | SF_BIAS, pl.off_const + k.off_bias_o, cp);
     } else {
       Stage& s2 = new_stage(ST_TOKENS, SF_RELU | SF_BIAS);
-      s2.tmem_col = (uint16_t)acc;
-      s2.n_cg = (uint16_t)(accw / 16);
+      s2.tmem_col = acc;
+      s2.n_cg = accw / 16;
       s2.bias_off = pl.off_const + k.off_bias_o;
-      s2.bias_period = (uint16_t)cp;
+      s2.bias_period = cp;
       order.back().rd.push_back(tmem_r(acc, accw));
       order.back().wr.push_back(smem_r(pl.off_stage_tok, stage_bytes));
     }
@@ -568,9 +568,9 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
     } else {
       const int team = x.side - SIDE_E0;
       Stage& s = pr.stages[team][x.idx];
-      s.wait_g = (int16_t)w[SIDE_G];
-      s.wait_l = (int16_t)w[SIDE_L];
-      s.wait_eo = (int16_t)w[SIDE_E0 + (team ^ 1)];
+      s.wait_g = w[SIDE_G];
+      s.wait_l = w[SIDE_L];
+      s.wait_eo = w[SIDE_E0 + (team ^ 1)];
     }
   }
   // a wait that an earlier item of the same sequence already performed (or implied: stages of one team and G commits
@@ -604,9 +604,9 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
   const int last_g = (int)pr.groups.size() - 1;
   for (int t = 0; t < kTeams; ++t) {
     if (pr.stages[t].empty()) return fail("an epilogue team has no work");
-    pr.stages[t][0].wait_g_prev = (int16_t)last_g;
+    pr.stages[t][0].wait_g_prev = last_g;
     for (Stage& s : pr.stages[t])
-      if (s.type == ST_G0 || s.type == ST_XEPI0) s.wait_l = (int16_t)((int)pr.loads.size() - 1);
+      if (s.type == ST_G0 || s.type == ST_XEPI0) s.wait_l = (int)pr.loads.size() - 1;
   }
   pr.loads[0].wait_g_prev = (int16_t)last_g;
   // ... and the first MMA group overwrites accumulator columns the previous tile's token stage may still be reading
@@ -631,6 +631,16 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
   pl.n_bars = pl.bar_l0 + pl.n_loads;
   pl.off_bars = off; off += up128((size_t)pl.n_bars * 8);
   pl.off_flags = off; off += 512;
+  for (int t = 0; t < kTeams; ++t)
+    for (size_t i = 0; i < pr.stages[t].size(); ++i) {
+      Stage& s = pr.stages[t][i];
+      auto bar = [&](int base, int idx) { return idx >= 0 ? pl.off_bars + 8u * (uint32_t)(base + idx) : 0u; };
+      s.bar_g = bar(pl.bar_g0, s.wait_g);
+      s.bar_l = bar(pl.bar_l0, s.wait_l);
+      s.bar_eo = bar(pl.bar_e0[t ^ 1], s.wait_eo);
+      s.bar_g_prev = bar(pl.bar_g0, s.wait_g_prev);
+      s.bar_self = bar(pl.bar_e0[t], (int)i);
+    }
   pl.smem_bytes = off;
   if ((int)off > max_smem) return fail("tile does not fit shared memory (" + std::to_string(off) + " bytes)");
   if (off >= (1u << 18)) return fail("operand offsets exceed the descriptor range");

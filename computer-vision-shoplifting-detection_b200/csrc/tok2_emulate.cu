@@ -300,7 +300,8 @@ bool emulate(const Static& st, const Program& pr, const float* poses, int64_t B,
           const bool valid = row < rows && ww < nw;
           bool bad = false;
           const float* xw = xin + ww * pl.per_w + v;
-          for (int t = s.p0; t < s.p1; ++t) {
+          const int t = s.p0 + half;                           // thread = (row, time step p0 + half)
+          if (t < s.p1) {
             float m[2] = {0.f, 0.f};
             if (valid) {
               m[0] = hcs[v * 2];
@@ -317,14 +318,12 @@ bool emulate(const Static& st, const Program& pr, const float* poses, int64_t B,
               }
               if (bad) m[0] = m[1] = 0.f;
             }
-            for (int c8 = half; c8 < cp0 / 8; c8 += 2)
-              for (int j = 0; j < 8; ++j) {
-                const int o = c8 * 8 + j;
-                const float y = std::fmaf(m[0], tabv(g0tab, 0, o), std::fmaf(m[1], tabv(g0tab, 1, o), tabv(g0tab, 2, o)));
-                const uint16_t hb = pack_one(y, true);
-                const int col = (t - s.p0) * cp0 + o;
-                memcpy(&E.smem[s.dst_off + (uint32_t)(col / 8) * kPlane + (uint32_t)row * 16 + (uint32_t)(col % 8) * 2], &hb, 2);
-              }
+            for (int o = 0; o < cp0; ++o) {
+              const float y = std::fmaf(m[0], tabv(g0tab, 0, o), std::fmaf(m[1], tabv(g0tab, 1, o), tabv(g0tab, 2, o)));
+              const uint16_t hb = pack_one(y, true);
+              const int col = (t - s.p0) * cp0 + o;
+              memcpy(&E.smem[s.dst_off + (uint32_t)(col / 8) * kPlane + (uint32_t)row * 16 + (uint32_t)(col % 8) * 2], &hb, 2);
+            }
           }
           if (bad) poison[par * 64 + ww] = 1;
         }

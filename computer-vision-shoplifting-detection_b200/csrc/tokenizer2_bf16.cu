@@ -26,24 +26,6 @@ namespace {
 using namespace tc;
 using namespace t2;
 
-// Blocking wait with a suspend-time hint: the waiting warp is parked by the hardware instead of spinning through the
-// scheduler's issue slots (the MMA warp, the TMA thread and the idle epilogue team share their SM sub-partitions with the
-// team that is working).
-__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
-        "selp.b32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(addr), "r"(parity), "r"(0x989680u)
-        : "memory");
-  } while (!ok);
-}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -127,76 +109,67 @@ __device__ __forceinline__ void store16(unsigned char* dst_row, int cg, const fl
   *reinterpret_cast<uint4*>(dst_row + (size_t)(2 * cg + 1) * kPlane) = o1;
 }
 
-// Block 0, one time slice [p0, p1) (at most two time steps) for one row (window w, keypoint v) on the CUDA cores, fp32:
+// Block 0, one time slice [p0, p1) (at most two time steps) on the CUDA cores, fp32: thread = (row (window w, keypoint v),
+// time step p0 + half):
 //   m_c = sum_u A_hat[v][u] * bn(x[c][t][u])      (BatchNorm1d folded into the coefficient row, shopformer/models/gcae.py:351-355)
 //   g_o = relu(m_x * W[x][o] + m_y * W[y][o] + b[o])   (graph conv, gcae.py:124-154)  -> bf16 operand slot of the temporal conv
-// The two column halves of a team take alternate 8-channel granules; the weight table is read once per granule and
-// applied to both time steps (broadcast shared-memory loads, packed fp32x2 FMAs).  Rows beyond the tile's windows
-// produce finite values nobody reads.
+// The weight table is read with broadcast shared-memory loads, the FMAs are packed fp32x2.  Rows beyond the tile's
+// windows produce finite values nobody reads.
 template <int KW>
 __device__ __forceinline__ void g0_stage(const Plan& pl, const Stage& s, unsigned char* smem, int row, int half, int my_w, int my_v, int nw,
                                          int* pz) {
+  const int t = s.p0 + half;
+  if (t >= s.p1) return;
   const int V = pl.V, tv4 = pl.T0 * V * 4, cp0 = pl.cp0;
   const bool valid = row < pl.rows && my_w < nw;
   const bool two = pl.c_in > 1;
-  unsigned char* dst_row = smem + s.dst_off + (size_t)row * 16;
-  const int nt = (int)s.p1 - (int)s.p0;              // 1 or 2
-  float2 mx[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, my[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-  bool bad = false;
+  const int chunks = cp0 / 8;                         // 8-channel granules per time step
+  unsigned char* dst_row = smem + s.dst_off + (size_t)(half * chunks) * kPlane + (size_t)row * 16;
+  float2 mx = make_float2(0.f, 0.f), my = make_float2(0.f, 0.f);
   if (valid) {
     const float4* coef = reinterpret_cast<const float4*>(smem + pl.off_ell);
     const float2 hc = reinterpret_cast<const float2*>(smem + pl.off_hc)[my_v];
-    const unsigned char* xw = smem + pl.off_xin + (size_t)(my_w * pl.per_w + my_v + (int)s.p0 * V) * 4;
+    const unsigned char* xp = smem + pl.off_xin + (size_t)(my_w * pl.per_w + my_v + t * V) * 4;
     float4 cf[KW];
 #pragma unroll
     for (int k = 0; k < KW; ++k) cf[k] = coef[k * V + my_v];
+    float x0[KW], x1[KW];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      if (h < nt) {
-        const unsigned char* xp = xw + h * V * 4;
-        float x0[KW], x1[KW];
+    for (int k = 0; k < KW; ++k) {
+      const int db = __float_as_int(cf[k].z) * 4;           // neighbour's byte offset
+      x0[k] = *reinterpret_cast<const float*>(xp + db);
+      x1[k] = two ? *reinterpret_cast<const float*>(xp + tv4 + db) : 0.f;
+    }
+    float a0 = hc.x, a1 = hc.y, chk = 0.f;
 #pragma unroll
-        for (int k = 0; k < KW; ++k) {
-          const int db = __float_as_int(cf[k].z) * 4;           // neighbour's byte offset
-          x0[k] = *reinterpret_cast<const float*>(xp + db);
-          x1[k] = two ? *reinterpret_cast<const float*>(xp + tv4 + db) : 0.f;
-        }
-        float a0 = hc.x, a1 = hc.y, chk = 0.f;
-#pragma unroll
-        for (int k = 0; k < KW; ++k) {
-          chk = fmaf(x0[k], 0.f, fmaf(x1[k], 0.f, chk));        // stays 0 unless a gathered pose is inf or NaN
-          a0 = fmaf(cf[k].x, x0[k], a0);
-          a1 = fmaf(cf[k].y, x1[k], a1);
-        }
-        const bool b = !(chk == 0.f);
-        bad |= b;
-        mx[h] = b ? make_float2(0.f, 0.f) : make_float2(a0, a0);
-        my[h] = b ? make_float2(0.f, 0.f) : make_float2(a1, a1);
-      }
+    for (int k = 0; k < KW; ++k) {
+      chk = fmaf(x0[k], 0.f, fmaf(x1[k], 0.f, chk));        // stays 0 unless a gathered pose is inf or NaN
+      a0 = fmaf(cf[k].x, x0[k], a0);
+      a1 = fmaf(cf[k].y, x1[k], a1);
+    }
+    if (chk == 0.f) {
+      mx = make_float2(a0, a0);
+      my = make_float2(a1, a1);
+    } else {
+      // a window with a non-finite pose is reported as NaN tokens (the mix MMA would otherwise spread it over the tile)
+      atomicOr(&pz[my_w], 1);
     }
   }
   const float4* tab = reinterpret_cast<const float4*>(smem + pl.off_g0tab);
-  const int chunks = cp0 / 8;                         // 8-channel granules per time step
-  for (int c8 = half; c8 < chunks; c8 += 2) {
+#pragma unroll 2
+  for (int c8 = 0; c8 < chunks; ++c8) {
     float4 w[6];                                      // (wx, wy, b) of outputs 8 c8 .. +4, then +4 .. +8
 #pragma unroll
     for (int i = 0; i < 6; ++i) w[i] = tab[c8 * 6 + i];
+    float2 y[4];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      if (h < nt) {
-        float2 y[4];
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          y[2 * g] = fma2(mx[h], make_float2(w[3 * g].x, w[3 * g].y), fma2(my[h], make_float2(w[3 * g + 1].x, w[3 * g + 1].y), make_float2(w[3 * g + 2].x, w[3 * g + 2].y)));
-          y[2 * g + 1] = fma2(mx[h], make_float2(w[3 * g].z, w[3 * g].w), fma2(my[h], make_float2(w[3 * g + 1].z, w[3 * g + 1].w), make_float2(w[3 * g + 2].z, w[3 * g + 2].w)));
-        }
-        *reinterpret_cast<uint4*>(dst_row + (size_t)(h * chunks + c8) * kPlane) =
-            make_uint4(pack2_relu(y[0].x, y[0].y), pack2_relu(y[1].x, y[1].y), pack2_relu(y[2].x, y[2].y), pack2_relu(y[3].x, y[3].y));
-      }
+    for (int g = 0; g < 2; ++g) {
+      y[2 * g] = fma2(mx, make_float2(w[3 * g].x, w[3 * g].y), fma2(my, make_float2(w[3 * g + 1].x, w[3 * g + 1].y), make_float2(w[3 * g + 2].x, w[3 * g + 2].y)));
+      y[2 * g + 1] = fma2(mx, make_float2(w[3 * g].z, w[3 * g].w), fma2(my, make_float2(w[3 * g + 1].z, w[3 * g + 1].w), make_float2(w[3 * g + 2].z, w[3 * g + 2].w)));
     }
+    *reinterpret_cast<uint4*>(dst_row + (size_t)c8 * kPlane) =
+        make_uint4(pack2_relu(y[0].x, y[0].y), pack2_relu(y[1].x, y[1].y), pack2_relu(y[2].x, y[2].y), pack2_relu(y[3].x, y[3].y));
   }
-  // a window with a non-finite pose is reported as NaN tokens (the mix MMA would otherwise spread it over the tile)
-  if (bad && half == 0) atomicOr(&pz[my_w], 1);
 }
 
 // Block 0 output for output times [p0, p1): x1 = relu(acc + BN-folded strided 1x1 residual conv of the raw poses + bias)
@@ -307,10 +280,10 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
       const uint32_t par = it & 1u;
       for (int g = 0; g < pl.n_groups; ++g) {
         const Group gr = pl.groups[g];
-        if (gr.wait_e[0] >= 0) mbar_wait_parked(&bars[pl.bar_e0[0] + gr.wait_e[0]], par);
-        if (gr.wait_e[1] >= 0) mbar_wait_parked(&bars[pl.bar_e0[1] + gr.wait_e[1]], par);
-        if (gr.wait_l >= 0) mbar_wait_parked(&bars[pl.bar_l0 + gr.wait_l], par);
-        if (gr.prev_stage >= 0 && it > 0) mbar_wait_parked(&bars[pl.bar_e0[gr.prev_team] + gr.prev_stage], par ^ 1u);
+        if (gr.wait_e[0] >= 0) mbar_wait(&bars[pl.bar_e0[0] + gr.wait_e[0]], par);
+        if (gr.wait_e[1] >= 0) mbar_wait(&bars[pl.bar_e0[1] + gr.wait_e[1]], par);
+        if (gr.wait_l >= 0) mbar_wait(&bars[pl.bar_l0 + gr.wait_l], par);
+        if (gr.prev_stage >= 0 && it > 0) mbar_wait(&bars[pl.bar_e0[gr.prev_team] + gr.prev_stage], par ^ 1u);
         tc_fence_after();
         if (timing && it == stamp_it) T2_STAMP(1000 + g);
         if (elect_one()) {
@@ -340,10 +313,10 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
         const uint32_t par = it & 1u;
         for (int l = 0; l < pl.n_loads; ++l) {
           const Load ld = pl.loads[l];
-          if (ld.wait_g >= 0) mbar_wait_parked(&bars[pl.bar_g0 + ld.wait_g], par);
-          if (ld.wait_e[0] >= 0) mbar_wait_parked(&bars[pl.bar_e0[0] + ld.wait_e[0]], par);
-          if (ld.wait_e[1] >= 0) mbar_wait_parked(&bars[pl.bar_e0[1] + ld.wait_e[1]], par);
-          if (ld.wait_g_prev >= 0 && it > 0) mbar_wait_parked(&bars[pl.bar_g0 + ld.wait_g_prev], par ^ 1u);
+          if (ld.wait_g >= 0) mbar_wait(&bars[pl.bar_g0 + ld.wait_g], par);
+          if (ld.wait_e[0] >= 0) mbar_wait(&bars[pl.bar_e0[0] + ld.wait_e[0]], par);
+          if (ld.wait_e[1] >= 0) mbar_wait(&bars[pl.bar_e0[1] + ld.wait_e[1]], par);
+          if (ld.wait_g_prev >= 0 && it > 0) mbar_wait(&bars[pl.bar_g0 + ld.wait_g_prev], par ^ 1u);
           if (ld.kind == LD_WEIGHTS) {
             uint64_t* bar = &bars[pl.bar_l0 + l];
             mbar_expect_tx(bar, ld.bytes);
@@ -364,7 +337,6 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
     const int my_w = row / V, my_v = row - my_w * V;
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
     const int n_st = pl.n_stages[team];
-    const int bar_mine = pl.bar_e0[team], bar_other = pl.bar_e0[team ^ 1];
     uint32_t it = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const uint32_t par = it & 1u;
@@ -372,11 +344,11 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
       const int nw = (int)((B - w_first) < (int64_t)pl.WT ? (B - w_first) : (int64_t)pl.WT);
       int* pz = poison + par * 64;
       for (int e = 0; e < n_st; ++e) {
-        const Stage s = pl.stages[team][e];
-        if (s.wait_g >= 0) mbar_wait_parked(&bars[pl.bar_g0 + s.wait_g], par);
-        if (s.wait_l >= 0) mbar_wait_parked(&bars[pl.bar_l0 + s.wait_l], par);
-        if (s.wait_eo >= 0) mbar_wait_parked(&bars[bar_other + s.wait_eo], par);
-        if (s.wait_g_prev >= 0 && it > 0) mbar_wait_parked(&bars[pl.bar_g0 + s.wait_g_prev], par ^ 1u);
+        const Stage& s = pl.stages[team][e];
+        if (s.bar_g) mbar_wait(reinterpret_cast<uint64_t*>(smem + s.bar_g), par);
+        if (s.bar_l) mbar_wait(reinterpret_cast<uint64_t*>(smem + s.bar_l), par);
+        if (s.bar_eo) mbar_wait(reinterpret_cast<uint64_t*>(smem + s.bar_eo), par);
+        if (s.bar_g_prev && it > 0) mbar_wait(reinterpret_cast<uint64_t*>(smem + s.bar_g_prev), par ^ 1u);
         tc_fence_after();
         if (timing && it == stamp_it && q == 0) T2_STAMP(2000 + e);
         if (s.type == ST_CVT) {
@@ -447,7 +419,7 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
         fence_proxy_async();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars[bar_mine + e]);
+        if (lane == 0) mbar_arrive(reinterpret_cast<uint64_t*>(smem + s.bar_self));
       }
     }
     if (tt == 0) bulk_wait_all();
