@@ -40,12 +40,15 @@ struct Mma {                 // one tcgen05.mma (M = 128, K = 16)
   uint32_t idesc;
 };
 
-struct Group {               // G item: a run of MMAs followed by one commit
+struct Group {               // G item: a run of MMAs followed by one commit (32 bytes)
   uint16_t first, count;
   int16_t wait_e[kTeams];    // stage of team 0 / 1 that must have completed this tile (-1: none)
   int16_t wait_l;            // L load
   int16_t prev_team, prev_stage;   // stage of the PREVIOUS tile that must have completed (-1: none): the token store
-  int16_t pad;
+  int16_t run_len;           // > 0: head of a fused run of `run_len` groups issued in one burst after the head's waits
+                             // (the members' own waits are folded into the head's); 0: member of a run
+  // the waits as shared-memory byte offsets of the mbarriers (0: none), and this group's own barrier
+  uint32_t bar_e[kTeams], bar_l, bar_self;
 };
 
 enum StageType { ST_PREP = 0, ST_CVT = 1, ST_TOKENS = 2 };
@@ -82,7 +85,7 @@ struct Plan {                // kernel parameter (by value)
   const unsigned char* const_src;   // resident images + fp32 tables, copied to smem once per CTA
   uint32_t const_bytes;
   // shared-memory map (byte offsets from the dynamic smem base)
-  uint32_t off_const, off_P, off_Q, off_W, off_stage_tok, off_bars, off_flags;
+  uint32_t off_const, off_P, off_Q, off_W, off_stage_tok, off_bars, off_flags, off_gtab, off_mtab;
   uint32_t off_xin, off_a0, off_a0x;
   uint32_t off_ell, off_hc, off_scale, off_shift;   // const blob: mix coefficients float4 (A_hat*scale_x, A_hat*scale_y, row delta, 0) [5|8][V],
                                                    // float2 [V] mixed BN shifts, BN1d scale / shift [c_in][V]
@@ -98,7 +101,7 @@ struct Plan {                // kernel parameter (by value)
   Load loads[kMaxLoads];
   Mma mma[kMaxMma];
 };
-static_assert(sizeof(Plan) < 20000, "Plan travels as a kernel parameter");
+static_assert(sizeof(Plan) < 28000, "Plan travels as a kernel parameter");
 
 }  // namespace t2
 }  // namespace sf

@@ -349,6 +349,7 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
     g.first = (uint16_t)pr.mma.size();
     g.wait_e[0] = g.wait_e[1] = g.wait_l = -1;
     g.prev_team = g.prev_stage = -1;
+    g.run_len = 1;
     pr.groups.push_back(g);
     order.push_back(Item{SIDE_G, (int)pr.groups.size() - 1, {}, {}});
   };
@@ -376,6 +377,8 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
     }
     it.wr.push_back(tmem_r(dcol, N));
   };
+  std::vector<int> run_starts;       // first G group of every fused issue burst (one per diagonal step)
+  auto begin_run = [&]() { run_starts.push_back((int)pr.groups.size()); };
   int next_team = 0;                 // stages alternate between the two epilogue teams
   auto new_stage = [&](int type, int flags) -> Stage& {
     const int team = next_team;
@@ -481,6 +484,7 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
     // diagonal schedule: step s issues the graph conv of slice s (short, its staging buffer is free once slice s-2 is
     // converted) and then the temporal conv of slice s-2; the epilogue of slice s-1 runs under both
     for (int sidx = 0; sidx < n_sl + 2; ++sidx) {
+      begin_run();
       if (sidx < n_sl) gcn0(sidx);
       if (sidx >= 2) tcn0(sidx - 2);
       if (sidx >= 1 && sidx - 1 < n_sl) epi0(sidx - 1);
@@ -534,6 +538,7 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
     // (oldest dependency first); the epilogues of chunk s (mix) and s-1 (graph conv) run on the two teams
     const int n = nch[b];
     for (int sidx = 0; sidx < n + 2; ++sidx) {
+      begin_run();
       if (sidx >= 2) {
         if (sidx == 2) res();
         new_group();
@@ -628,6 +633,32 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
       }
     }
   }
+  // fused issue bursts: the groups of one diagonal step are issued back to back after ONE set of waits (the head's,
+  // which takes over the members' waits -- all waits are "at least this item", so the maximum per sequence covers them)
+  {
+    run_starts.push_back((int)pr.groups.size());
+    for (size_t r = 0; r + 1 < run_starts.size(); ++r) {
+      const int g0 = run_starts[r], g1 = run_starts[r + 1];
+      if (g1 - g0 < 2) continue;
+      Group& h = pr.groups[g0];
+      for (int g = g0 + 1; g < g1; ++g) {
+        Group& m = pr.groups[g];
+        for (int t = 0; t < kTeams; ++t) {
+          h.wait_e[t] = std::max(h.wait_e[t], m.wait_e[t]);
+          m.wait_e[t] = -1;
+        }
+        // loads complete in no particular order: at most one load wait per run is supported
+        if (m.wait_l >= 0) {
+          if (h.wait_l >= 0 && h.wait_l != m.wait_l) { h.run_len = 0; break; }
+          h.wait_l = m.wait_l;
+          m.wait_l = -1;
+        }
+        m.run_len = 0;
+      }
+      if (h.run_len == 0) return fail("internal: two load waits in one issue burst");
+      h.run_len = (int16_t)(g1 - g0);
+    }
+  }
   // tile boundary: each team's first stage overwrites operand regions the previous tile's last MMAs read, the first
   // weight load overwrites the weights they read; every stage that reads the poses waits for the load the previous
   // tile issued (the pose barrier is one completion ahead: the prologue load)
@@ -661,6 +692,16 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
   pl.n_bars = pl.bar_l0 + pl.n_loads;
   pl.off_bars = off; off += up128((size_t)pl.n_bars * 8);
   pl.off_flags = off; off += 512;
+  pl.off_gtab = off; off += up128(pr.groups.size() * sizeof(Group));
+  pl.off_mtab = off; off += up128(pr.mma.size() * sizeof(Mma));
+  for (size_t i = 0; i < pr.groups.size(); ++i) {
+    Group& g = pr.groups[i];
+    auto bar = [&](int base, int idx) { return idx >= 0 ? pl.off_bars + 8u * (uint32_t)(base + idx) : 0u; };
+    g.bar_e[0] = bar(pl.bar_e0[0], g.wait_e[0]);
+    g.bar_e[1] = bar(pl.bar_e0[1], g.wait_e[1]);
+    g.bar_l = bar(pl.bar_l0, g.wait_l);
+    g.bar_self = bar(pl.bar_g0, (int)i);
+  }
   for (int t = 0; t < kTeams; ++t)
     for (size_t i = 0; i < pr.stages[t].size(); ++i) {
       Stage& s = pr.stages[t][i];

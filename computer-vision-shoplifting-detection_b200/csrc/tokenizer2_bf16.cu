@@ -214,6 +214,13 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
     uint4* z = reinterpret_cast<uint4*>(smem + pl.off_P);                   // operand regions start out finite (0 * NaN = NaN)
     for (uint32_t i = threadIdx.x; i < (pl.off_bars - pl.off_P) / 16; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
     if (threadIdx.x < 128) poison[threadIdx.x] = 0;
+    // the MMA warp reads its tables from shared memory (a dependent constant-bank load costs ~200 cycles when it misses)
+    uint32_t* gt = reinterpret_cast<uint32_t*>(smem + pl.off_gtab);
+    const uint32_t* gs = reinterpret_cast<const uint32_t*>(pl.groups);
+    for (uint32_t i = threadIdx.x; i < (uint32_t)pl.n_groups * (sizeof(Group) / 4); i += kThreads) gt[i] = gs[i];
+    uint32_t* mt = reinterpret_cast<uint32_t*>(smem + pl.off_mtab);
+    const uint32_t* ms = reinterpret_cast<const uint32_t*>(pl.mma);
+    for (uint32_t i = threadIdx.x; i < (uint32_t)pl.n_mma * (sizeof(Mma) / 4); i += kThreads) mt[i] = ms[i];
   }
   if (warp == 0) tmem_alloc(&tmem_base_s, 512);
   if (threadIdx.x == 0) {
@@ -236,25 +243,42 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
 
   if (warp == 0) {
     // =================================================================== MMA issue
+    // One burst per diagonal step: the head group's waits, then every group of the run -- MMAs from the descriptor table,
+    // one commit per group -- without going back to the barriers.  Table entries are fetched four at a time ahead of the
+    // (volatile) MMA instructions.
     const uint32_t base16 = smem_u32(smem) >> 4;
+    const Group* gtab = reinterpret_cast<const Group*>(smem + pl.off_gtab);
+    const Mma* mtab = reinterpret_cast<const Mma*>(smem + pl.off_mtab);
     uint32_t it = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const uint32_t par = it & 1u;
-      for (int g = 0; g < pl.n_groups; ++g) {
-        const Group gr = pl.groups[g];
-        if (gr.wait_e[0] >= 0) mbar_wait(&bars[pl.bar_e0[0] + gr.wait_e[0]], par);
-        if (gr.wait_e[1] >= 0) mbar_wait(&bars[pl.bar_e0[1] + gr.wait_e[1]], par);
-        if (gr.wait_l >= 0) mbar_wait(&bars[pl.bar_l0 + gr.wait_l], par);
-        if (gr.prev_stage >= 0 && it > 0) mbar_wait(&bars[pl.bar_e0[gr.prev_team] + gr.prev_stage], par ^ 1u);
+      for (int g = 0; g < pl.n_groups;) {
+        const Group head = gtab[g];
+        if (timing && it == stamp_it) T2_STAMP(7000 + g);          // group entry loaded
+        if (head.bar_e[0]) mbar_wait(reinterpret_cast<uint64_t*>(smem + head.bar_e[0]), par);
+        if (head.bar_e[1]) mbar_wait(reinterpret_cast<uint64_t*>(smem + head.bar_e[1]), par);
+        if (head.bar_l) mbar_wait(reinterpret_cast<uint64_t*>(smem + head.bar_l), par);
+        if (head.prev_stage >= 0 && it > 0) mbar_wait(&bars[pl.bar_e0[head.prev_team] + head.prev_stage], par ^ 1u);
         tc_fence_after();
         if (timing && it == stamp_it) T2_STAMP(1000 + g);
+        const int run = head.run_len;
         if (elect_one()) {
-          // descriptors come straight from the parameter (constant) bank with a warp-uniform index
-          const int end = gr.first + gr.count;
-          for (int i = gr.first; i < end; ++i) issue_mma(tmem, pl.mma[i], base16);
-          umma_commit(&bars[pl.bar_g0 + g]);
+          for (int r = 0; r < run; ++r) {
+            const Group gr = gtab[g + r];
+            const int end = gr.first + gr.count;
+            for (int i = gr.first; i < end; i += 4) {
+              const Mma e0 = mtab[i], e1 = mtab[min(i + 1, end - 1)], e2 = mtab[min(i + 2, end - 1)], e3 = mtab[min(i + 3, end - 1)];
+              issue_mma(tmem, e0, base16);
+              if (i + 1 < end) issue_mma(tmem, e1, base16);
+              if (i + 2 < end) issue_mma(tmem, e2, base16);
+              if (i + 3 < end) issue_mma(tmem, e3, base16);
+            }
+            umma_commit(reinterpret_cast<uint64_t*>(smem + gr.bar_self));
+          }
+          if (timing && it == stamp_it) T2_STAMP(9000 + g);        // burst issued and committed
         }
         __syncwarp();
+        g += run;
       }
     }
   } else if (warp == 1) {

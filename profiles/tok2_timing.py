@@ -26,8 +26,15 @@ if len(g) == 0:
 t0 = min([g[0, 1]] + [t[0, 1] for t in teams if len(t)])
 print("MMA groups (id, start, delta to previous):")
 prev = g[0, 1]
+ga = a[:512]
+gsub = {k: {int(i) - k: int(t) for i, t in ga[(ga[:, 0] >= k) & (ga[:, 0] < k + 500)]} for k in (7000, 8000, 9000)}
 for i, t in g:
-    print(f"  G{i-1000:3d}  @{t-t0:7d}  +{t-prev:6d}")
+    j = int(i) - 1000
+    det = ""
+    if j in gsub[7000]: det += f"  waits+fence {t - gsub[7000][j]:5d}"
+    if j in gsub[8000]: det += f"  issue {gsub[8000][j] - t:5d}"
+    if j in gsub[9000] and j in gsub[8000]: det += f"  commit {gsub[9000][j] - gsub[8000][j]:5d}"
+    print(f"  G{j:3d}  @{t-t0:7d}  +{t-prev:6d}{det}")
     prev = t
 for k, e in enumerate(teams):
     print(f"epilogue team {k} stages (first warp of the team):")
