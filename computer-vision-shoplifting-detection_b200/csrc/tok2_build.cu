@@ -299,6 +299,14 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
   }
   const int S_out = Tout[nb - 1], c_last = st.blk[nb - 1].cout, d_tok = c_last * V;
   const uint32_t stage_bytes = up128((size_t)st.WT * S_out * d_tok * 4);
+  // token staging (fp32, the tile's tokens contiguous as in HBM) lives at the end of Q, clear of the last block's ring
+  // slots / input.  The next tile's block-0 ring reuses those bytes: the thread that issued the bulk store waits for its
+  // shared-memory reads in its team's first stage of the next tile, which every block-0 epilogue stage depends on.
+  {
+    const bool last_x_in_P = ((nb - 1) & 1) != 0;
+    const uint32_t q_used_last = last_x_in_P ? slot_bytes[nb - 1] * (uint32_t)n_slots[nb - 1] : x_bytes[nb - 1];
+    Q_need = std::max(Q_need, up128(q_used_last) + stage_bytes);
+  }
   const uint32_t P_size = up128(P_need), Q_size = up128(Q_need);
   uint32_t W_size = 0;
   for (int b = 0; b < nb; ++b) W_size = std::max(W_size, st.blk[b].tcn_bytes);
@@ -325,7 +333,7 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
   pl.off_P = off; off += P_size;
   pl.off_Q = off; off += Q_size;
   pl.off_W = off; off += up128(W_size);
-  pl.off_stage_tok = off; off += stage_bytes;
+  pl.off_stage_tok = pl.off_Q + Q_size - stage_bytes;
   pl.off_ell = pl.off_const + st.off_ell;
   pl.off_hc = pl.off_const + st.off_hc;
   pl.off_scale = pl.off_const + st.off_scale;

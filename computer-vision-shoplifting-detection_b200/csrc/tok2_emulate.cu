@@ -145,6 +145,7 @@ bool emulate(const Static& st, const Program& pr, const float* poses, int64_t B,
   long named_gen[kTeams] = {0, 0};
   long warp_gen[kTeams][kTeamWarps] = {{0}};
   bool store_pending = false;          // bulk store issued, staging not yet read
+  int store_team = 0;
   int64_t store_tile = 0;
   int store_nw = 0;
 
@@ -278,6 +279,7 @@ bool emulate(const Static& st, const Program& pr, const float* poses, int64_t B,
       };
       const float* xin = reinterpret_cast<const float*>(&E.smem[pl.off_xin]);
       bool finish = false;
+      if (W.e == 0 && W.sub == 0 && w == 0 && store_pending && tm == store_team) do_store();      // bulk_wait_read of the issuing thread
       if (s.type == ST_CVT) {
         for (int cg = half; cg < s.n_cg; cg += 2)
           for (int ln = 0; ln < 32; ++ln) {
@@ -374,6 +376,7 @@ bool emulate(const Static& st, const Program& pr, const float* poses, int64_t B,
           if (w == 0) {
             if (store_pending) return fail("emulator: token staging overwritten while a bulk store is pending");
             store_pending = true;
+            store_team = tm;
             store_tile = tile;
             store_nw = nw;
           }

@@ -340,6 +340,7 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
         if (s.bar_eo) mbar_wait(reinterpret_cast<uint64_t*>(smem + s.bar_eo), par);
         if (s.bar_g_prev && it > 0) mbar_wait(reinterpret_cast<uint64_t*>(smem + s.bar_g_prev), par ^ 1u);
         tc_fence_after();
+        if (e == 0 && tt == 0) bulk_wait_read();      // (the previous tile's token store has read its staging bytes, see tok2_build.cu)
         if (timing && it == stamp_it && q == 0 && half == 0) T2_STAMP(2000 + e);
         if (s.type == ST_CVT) {
           const bool relu = s.flags & SF_RELU, bias = s.flags & SF_BIAS;
