@@ -5,16 +5,16 @@
 //   * one tile = WT = floor(128 / V) whole windows; MMA row r = w * V + v  (window, keypoint),
 //     MMA column = (time, channel).  Every activation buffer is the planar-chunk layout of tc_common.cuh with
 //     128 rows: byte = (col / 8) * 2048 + row * 16 + (col % 8) * 2.
-//   * block 0 (2 raw coordinates): the epilogue warps fold BatchNorm1d into the adjacency coefficients, mix the poses in
-//     fp32 and split every mixed value into bf16 hi + lo; with weights split the same way ONE K = 16 MMA per two time
-//     steps reproduces the fp32 graph conv (and its bias, through a constant-one operand column);
+//   * block 0's graph conv (2 raw coordinates -> C channels) runs on the CUDA cores in fp32 straight from the poses
+//     (BatchNorm1d folded into the adjacency coefficients), one time-slice at a time into a ring of bf16 operand slots;
 //   * adjacency mix of the later blocks = one 128x128 block-diagonal A operand (I_WT (x) A_hat) times the activation
 //     buffer used as an MN-major B operand (K = rows);
 //   * graph-conv weights = per-time-step [128 x Cin] x [Cin x Cout] MMAs;
 //   * temporal conv = Toeplitz product done WITHOUT a Toeplitz matrix: for input time t the taps that are valid for
 //     consecutive output times t' are consecutive blocks of a tap image stored in descending-tap order per stride phase,
 //     so ONE MMA with N = (#valid t') * Cout adds time t's contribution to all its outputs; no padding taps are computed;
-//   * strided 1x1 residual conv = per-output-time MMAs into the same accumulator (they also initialise it).
+//   * strided 1x1 residual conv = per-output-time MMAs into the same accumulator (they also initialise it); block 0's
+//     (2 input channels) is added in fp32 by the epilogue that drains the accumulator.
 // The host flattens a (model, T) pair into four in-order item sequences -- G (MMA groups, one issuing thread),
 // E0 / E1 (epilogue stages of two 4-warp teams) and L (TMA loads, one thread) -- and derives every cross-sequence wait
 // from the items' read / write sets (shared-memory byte ranges and TMEM column ranges).  Each item owns one mbarrier
@@ -40,30 +40,27 @@ struct Mma {                 // one tcgen05.mma (M = 128, K = 16)
   uint32_t idesc;
 };
 
-struct Group {               // G item: a run of MMAs followed by one commit (32 bytes)
+struct Group {               // G item: a run of MMAs followed by one commit
   uint16_t first, count;
   int16_t wait_e[kTeams];    // stage of team 0 / 1 that must have completed this tile (-1: none)
   int16_t wait_l;            // L load
   int16_t prev_team, prev_stage;   // stage of the PREVIOUS tile that must have completed (-1: none): the token store
-  int16_t run_len;           // > 0: head of a fused run of `run_len` groups issued in one burst after the head's waits
-                             // (the members' own waits are folded into the head's); 0: member of a run
-  // the waits as shared-memory byte offsets of the mbarriers (0: none), and this group's own barrier
-  uint32_t bar_e[kTeams], bar_l, bar_self;
+  int16_t pad;
 };
 
-enum StageType { ST_PREP = 0, ST_CVT = 1, ST_TOKENS = 2 };
-enum StageFlags { SF_RELU = 1, SF_BIAS = 2 };
+enum StageType { ST_G0 = 0, ST_CVT = 1, ST_XEPI0 = 2, ST_TOKENS = 3 };
+enum StageFlags { SF_RELU = 1, SF_BIAS = 2, SF_TEAM_SYNC = 4 };
 
 struct Stage {               // E item (index = position in its TEAM's sequence); 32-bit fields: read with uniform constant loads
   int32_t type, flags;
   int32_t wait_g, wait_l, wait_eo, wait_g_prev;   // item indices (-1: none): G group / L load / other team's stage (this tile), G group (previous tile)
   // the same waits as shared-memory byte offsets of the mbarriers (0: none), and this stage's own barrier
   uint32_t bar_g, bar_l, bar_eo, bar_g_prev, bar_self;
-  int32_t tmem_col, n_cg;    // CVT / TOKENS: first accumulator column, number of 16-column groups
-  uint32_t dst_off;          // CVT: smem byte offset of destination column 0
+  int32_t tmem_col, n_cg;    // CVT / XEPI0 / TOKENS: first accumulator column, number of 16-column groups
+  uint32_t dst_off;          // smem byte offset of destination column 0 (G0: the ring slot)
   uint32_t bias_off;         // byte offset of the fp32 bias vector (period `bias_period` columns)
   int32_t bias_period;
-  int32_t p0, p1, p2;        // PREP: time steps [p0, p1) of the mixed operand A0; p2 = 1: also the un-mixed operand A0x (all output times)
+  int32_t p0, p1;            // G0: input time steps [p0, p1); XEPI0: output time steps [p0, p1)
 };
 
 enum LoadKind { LD_WEIGHTS = 0, LD_POSES = 1 };
@@ -85,15 +82,18 @@ struct Plan {                // kernel parameter (by value)
   const unsigned char* const_src;   // resident images + fp32 tables, copied to smem once per CTA
   uint32_t const_bytes;
   // shared-memory map (byte offsets from the dynamic smem base)
-  uint32_t off_const, off_P, off_Q, off_W, off_stage_tok, off_bars, off_flags, off_gtab, off_mtab;
-  uint32_t off_xin, off_a0, off_a0x;
+  uint32_t off_const, off_P, off_Q, off_W, off_stage_tok, off_bars, off_flags;
+  uint32_t off_xin;
   uint32_t off_ell, off_hc, off_scale, off_shift;   // const blob: mix coefficients float4 (A_hat*scale_x, A_hat*scale_y, row delta, 0) [5|8][V],
                                                    // float2 [V] mixed BN shifts, BN1d scale / shift [c_in][V]
   int ell_width;
-  int a0_chunks, a0x_chunks, stride0;
+  int cp0, stride0;
   int bar_g0, bar_l0, n_bars;                   // barrier index bases
   int bar_e0[kTeams];
   uint32_t smem_bytes;
+  // block 0 on the CUDA cores: fp32 tables in the const blob, per 4 output channels (w_x[4], w_y[4], bias[4]):
+  // graph-conv weight / bias, and the BN-folded residual 1x1 conv weight / output bias
+  uint32_t off_g0tab, off_r0tab;
   // The tile program itself travels in the kernel's parameter space (constant bank): the MMA-issuing thread reads
   // descriptors with uniform-datapath constant loads, no shared-memory round trip and no register -> uniform moves.
   Group groups[kMaxGroups];
@@ -101,7 +101,7 @@ struct Plan {                // kernel parameter (by value)
   Load loads[kMaxLoads];
   Mma mma[kMaxMma];
 };
-static_assert(sizeof(Plan) < 28000, "Plan travels as a kernel parameter");
+static_assert(sizeof(Plan) < 20000, "Plan travels as a kernel parameter");
 
 }  // namespace t2
 }  // namespace sf

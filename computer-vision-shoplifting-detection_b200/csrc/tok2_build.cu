@@ -3,7 +3,6 @@
 // conv + BN), :242-259 (block), :331-366 (encoder); shopformer_2/models/gcae.py:375-422.
 #include <algorithm>
 #include <cmath>
-#include <cstdlib>
 #include <cstring>
 
 #include "tok2_build.h"
@@ -91,39 +90,25 @@ void build_static(const Tokenizer& tok, int pool_tokens, Static* out) {
     if (b > 0 && o.cin_p != s.blk[b - 1].cp) return fail("channel padding mismatch");
   }
   {
-    // block 0: K = 16 split images.  A columns per time step: [hx, hx, lx, hy, hy, ly, 1, 1]; B rows [w_hi, w_lo, w_hi | b_hi, b_lo]
+    // block 0 runs on the CUDA cores from fp32 tables (they travel in the kernel parameters); the tensor cores only
+    // need a zero A operand (two 8-column chunks) to clear the block-0 accumulator
     const TokBlock& t0 = tok.blk[0];
-    const int cp = s.blk[0].cp, co = t0.cout;
-    auto bfr = [](float x) {
-      const uint16_t h = f2bf(x);
-      uint32_t u = (uint32_t)h << 16;
-      float f;
-      memcpy(&f, &u, 4);
-      return f;
+    if (s.blk[0].cp > kMaxC0) return fail("block 0 wider than 64 channels");
+    s.off_zero = bl.alloc((size_t)2 * kPlane);
+    const int cp = s.blk[0].cp;
+    auto table = [&](const float* w, const float* bias) {
+      const uint32_t off = bl.alloc((size_t)cp * 3 * 4);
+      float* t = bl.f32(off);
+      for (int o = 0; o < cp; ++o) {
+        float* e = t + (o / 4) * 12 + (o % 4);
+        e[0] = (o < t0.cout && t0.cin > 0) ? w[0 * t0.cout + o] : 0.f;
+        e[4] = (o < t0.cout && t0.cin > 1) ? w[1 * t0.cout + o] : 0.f;
+        e[8] = o < t0.cout ? bias[o] : 0.f;
+      }
+      return off;
     };
-    auto split_image = [&](uint32_t off, const float* w, const float* bias) {
-      fill_kmajor(bl.bf(off), 2 * cp, 16, [&](int n, int k) -> float {
-        const int half = n / cp, o = n % cp, kk = k % 8, kh = k / 8;
-        if (kh != half || o >= co) return 0.f;
-        float src;
-        bool lo;
-        if (kk < 6) {
-          const int ci = kk / 3, j = kk % 3;
-          if (ci >= t0.cin) return 0.f;
-          src = w[ci * co + o];
-          lo = j == 1;
-        } else {
-          src = bias[o];
-          lo = kk == 7;
-        }
-        const float hi = bfr(src);
-        return lo ? src - hi : hi;
-      });
-    };
-    s.off_w0 = bl.alloc((size_t)2 * cp * 16 * 2);
-    split_image(s.off_w0, t0.gcn_w, t0.gcn_b);
-    s.off_r0 = bl.alloc((size_t)2 * cp * 16 * 2);
-    split_image(s.off_r0, t0.res_w, t0.out_b);
+    s.off_g0tab = table(t0.gcn_w, t0.gcn_b);
+    s.off_r0tab = table(t0.res_w, t0.out_b);
   }
   for (int b = 1; b < nb; ++b) {
     const TokBlock& tb = tok.blk[b];
@@ -244,69 +229,53 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
   if ((per_w * 4) % 16) return fail("window size not a multiple of 16 bytes");
   const uint32_t xin_bytes = (uint32_t)st.WT * per_w * 4, xin_alloc = up128(xin_bytes);
   const int cp0 = st.blk[0].cp;
-  const int n_sl = (T + 1) / 2;                          // block-0 slices of two time steps (one K = 16 MMA each)
-  const int a0_chunks = 2 * n_sl, a0x_chunks = 2 * ((Tout[0] + 1) / 2);
-  if (Tout[0] * cp0 + 4 * cp0 > 512) return fail("block-0 accumulators exceed tensor memory");
-  if (2 * cp0 > 256) return fail("block-0 width");
+  if (Tout[0] * cp0 > 512) return fail("block-0 accumulators exceed tensor memory");
+  if (cp0 != 16 && cp0 != 32 && cp0 != 64) return fail("block-0 width not 16 / 32 / 64");
 
-  // ---- chunking / buffering of blocks >= 1 and region sizes.  Preference: two TMEM staging buffers for both the mix and
-  // the graph-conv output and three shared-memory operand slots, so that chunk c+1's MMAs run under chunk c's epilogues.
+  // ---- block 0: time steps per CUDA-core slice and the ring of operand slots in Q
   const uint32_t ring_cap_q = 49152;
-  int ct[kMaxBlocks] = {0}, nch[kMaxBlocks] = {0}, n_sm[kMaxBlocks] = {0}, n_sg[kMaxBlocks] = {0}, n_slots[kMaxBlocks] = {0};
+  int st0 = 2;                                          // time steps per slice
+  while (st0 > 1 && (uint32_t)(st0 * cp0 / 8) * kPlane * 2 > ring_cap_q) --st0;
+  const uint32_t ring0_slot = (uint32_t)(st0 * cp0 / 8) * kPlane;
+  const int n_sl = (T + st0 - 1) / st0;
+  const int ring0_slots = std::max(1, std::min(std::min(4, n_sl), (int)(ring_cap_q / ring0_slot)));
+
+  // ---- chunking of blocks >= 1 (time steps per mix / graph-conv chunk) and region sizes
+  int ct[kMaxBlocks] = {0}, nch[kMaxBlocks] = {0};
   uint32_t slot_bytes[kMaxBlocks] = {0};
   uint32_t x_bytes[kMaxBlocks + 1] = {0};          // x_b = input of block b (b >= 1), planar-chunk bf16
   for (int b = 1; b <= nb; ++b) x_bytes[b] = b < nb ? (uint32_t)(Tin[b] * st.blk[b].cin_p / 8) * kPlane : 0u;
-  const uint32_t ring0_slot = (uint32_t)(2 * cp0 / 8) * kPlane;
-  const int ring0_slots = std::max(1, std::min(std::min(3, n_sl), (int)(ring_cap_q / ring0_slot)));
-  uint32_t P_need = (uint32_t)(a0_chunks + a0x_chunks) * kPlane + xin_alloc, Q_need = ring0_slot * ring0_slots;
-  int want_chunks[kMaxBlocks];
-  for (int b = 1; b < nb; ++b) want_chunks[b] = Tin[b] >= 6 ? 3 : (Tin[b] >= 4 ? 2 : 1);
-  if (const char* e = getenv("SF_TOK2_CHUNKS")) {        // debugging aid: "n1,n2,..." chunks wanted for blocks 1, 2, ...
-    int b = 1;
-    for (const char* q = e; *q && b < nb; ++b) {
-      want_chunks[b] = std::max(1, atoi(q));
-      while (*q && *q != ',') ++q;
-      if (*q == ',') ++q;
-    }
-  }
+  uint32_t P_need = xin_alloc, Q_need = ring0_slot * ring0_slots;
   for (int b = 1; b < nb; ++b) {
     const BlockStatic& k = st.blk[b];
     const bool x_in_P = (b & 1) != 0;                 // x1 in P, x2 in Q, ...
     (x_in_P ? P_need : Q_need) = std::max(x_in_P ? P_need : Q_need, x_bytes[b]);
     const int accw = Tout[b] * k.cp;
-    const uint32_t cap = x_in_P ? ring_cap_q : std::max(P_need, (uint32_t)98304);
-    const int c_max = std::max(1, (Tin[b] + want_chunks[b] - 1) / want_chunks[b]);
+    // at least two chunks when the block is long enough: the second chunk's mix / graph conv run under the first
+    // chunk's epilogues
+    int c_max = Tin[b] >= 4 ? (Tin[b] + 1) / 2 : Tin[b];
+    if (b == 1) c_max = std::min(c_max, 8);        // block 0's output epilogue keeps one chunk's poses in registers
     int best = 0;
-    for (int depth = 2; depth >= 1 && !best; --depth)       // depth 2: double-buffered staging + 3 slots; depth 1: single + 2 slots
-      for (int c = c_max; c >= 1; --c) {
-        const int chunks = (Tin[b] + c - 1) / c;
-        const int sm = std::min(depth, chunks), sg = std::min(depth, chunks), sl = std::min(depth + 1, chunks);
-        const uint32_t sb = (uint32_t)(c * std::max(k.cin_p, k.cp) / 8) * kPlane;
-        if (c * k.cin_p > 256 || c * k.cp > 256) continue;
-        if (accw + sm * c * k.cin_p + sg * c * k.cp > 512) continue;
-        if (sb * (uint32_t)sl > cap) continue;
-        best = c;
-        n_sm[b] = sm;
-        n_sg[b] = sg;
-        n_slots[b] = sl;
-        break;
-      }
+    for (int c = c_max; c >= 1; --c) {
+      const int chunks = (Tin[b] + c - 1) / c;
+      const uint32_t sb = (uint32_t)(c * std::max(k.cin_p, k.cp) / 8) * kPlane;
+      const uint32_t ring = sb * (uint32_t)std::min(2, chunks);
+      if (c * k.cin_p > 256 || c * k.cp > 256) continue;
+      if (accw + c * k.cin_p + c * k.cp > 512) continue;
+      const uint32_t cap = x_in_P ? ring_cap_q : std::max(P_need, (uint32_t)98304);
+      if (ring > cap) continue;
+      best = c;
+      break;
+    }
     if (!best) return fail("no chunking fits tensor memory / shared memory");
     ct[b] = best;
     nch[b] = (Tin[b] + best - 1) / best;
     slot_bytes[b] = (uint32_t)(best * std::max(k.cin_p, k.cp) / 8) * kPlane;
-    (x_in_P ? Q_need : P_need) = std::max(x_in_P ? Q_need : P_need, slot_bytes[b] * (uint32_t)n_slots[b]);
+    const uint32_t ring = slot_bytes[b] * (uint32_t)std::min(2, nch[b]);
+    (x_in_P ? Q_need : P_need) = std::max(x_in_P ? Q_need : P_need, ring);
   }
   const int S_out = Tout[nb - 1], c_last = st.blk[nb - 1].cout, d_tok = c_last * V;
   const uint32_t stage_bytes = up128((size_t)st.WT * S_out * d_tok * 4);
-  // token staging (fp32, the tile's tokens contiguous as in HBM) lives at the end of Q, clear of the last block's ring
-  // slots / input.  The next tile's block-0 ring reuses those bytes: the thread that issued the bulk store waits for its
-  // shared-memory reads in its team's first stage of the next tile, which every block-0 epilogue stage depends on.
-  {
-    const bool last_x_in_P = ((nb - 1) & 1) != 0;
-    const uint32_t q_used_last = last_x_in_P ? slot_bytes[nb - 1] * (uint32_t)n_slots[nb - 1] : x_bytes[nb - 1];
-    Q_need = std::max(Q_need, up128(q_used_last) + stage_bytes);
-  }
   const uint32_t P_size = up128(P_need), Q_size = up128(Q_need);
   uint32_t W_size = 0;
   for (int b = 0; b < nb; ++b) W_size = std::max(W_size, st.blk[b].tcn_bytes);
@@ -325,22 +294,21 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
   pl.per_w = per_w;
   pl.const_bytes = st.const_bytes;
   pl.ell_width = st.ell_width;
-  pl.a0_chunks = a0_chunks;
-  pl.a0x_chunks = a0x_chunks;
+  pl.cp0 = cp0;
   pl.stride0 = st.blk[0].stride;
   uint32_t off = 0;
   pl.off_const = off; off += st.const_bytes;
   pl.off_P = off; off += P_size;
   pl.off_Q = off; off += Q_size;
   pl.off_W = off; off += up128(W_size);
-  pl.off_stage_tok = pl.off_Q + Q_size - stage_bytes;
+  pl.off_stage_tok = off; off += stage_bytes;
   pl.off_ell = pl.off_const + st.off_ell;
   pl.off_hc = pl.off_const + st.off_hc;
   pl.off_scale = pl.off_const + st.off_scale;
   pl.off_shift = pl.off_const + st.off_shift;
-  // block 0's operands at the start of P, the raw poses at its end (x1, written when block 0 is over, covers both)
-  pl.off_a0 = pl.off_P;
-  pl.off_a0x = pl.off_P + (uint32_t)a0_chunks * kPlane;
+  pl.off_g0tab = pl.off_const + st.off_g0tab;
+  pl.off_r0tab = pl.off_const + st.off_r0tab;
+  // the raw poses sit at the END of P: x1 (block 0's output, written last) only reaches them with its final columns
   pl.off_xin = pl.off_P + P_size - xin_alloc;
 
   // ---- emit the items ----------------------------------------------------------------------------------------
@@ -357,7 +325,6 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
     g.first = (uint16_t)pr.mma.size();
     g.wait_e[0] = g.wait_e[1] = g.wait_l = -1;
     g.prev_team = g.prev_stage = -1;
-    g.run_len = 1;
     pr.groups.push_back(g);
     order.push_back(Item{SIDE_G, (int)pr.groups.size() - 1, {}, {}});
   };
@@ -385,8 +352,6 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
     }
     it.wr.push_back(tmem_r(dcol, N));
   };
-  std::vector<int> run_starts;       // first G group of every fused issue burst (one per diagonal step)
-  auto begin_run = [&]() { run_starts.push_back((int)pr.groups.size()); };
   int next_team = 0;                 // stages alternate between the two epilogue teams
   auto new_stage = [&](int type, int flags) -> Stage& {
     const int team = next_team;
@@ -452,56 +417,53 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
   // ======================= block 0
   {
     const BlockStatic& k = st.blk[0];
-    const int cp = k.cp;
-    const int acc = 0, stg[2] = {Tout[0] * cp, Tout[0] * cp + 2 * cp};
+    const int cp = k.cp, accw = Tout[0] * cp;
     new_load(LD_WEIGHTS, pl.off_W, k.tcn_bytes, k.off_tcn);
-    auto prep = [&](int t0, int t1, bool with_x) {
-      Stage& s = new_stage(ST_PREP, 0);
-      s.p0 = t0;
-      s.p1 = t1;
-      s.p2 = with_x ? 1 : 0;
-      Item& it = order.back();
-      it.rd = xin_rng;
-      const int c1 = (t1 >= T) ? a0_chunks : t1;       // the last prep stage also clears the pad chunk
-      if (t1 > t0) it.wr.push_back(smem_r(pl.off_a0 + (uint32_t)t0 * kPlane, (uint32_t)(c1 - t0) * kPlane));
-      if (with_x) it.wr.push_back(smem_r(pl.off_a0x, (uint32_t)a0x_chunks * kPlane));
-    };
-    // operand preparation in four stages, two per team: the un-mixed residual operand + the first slices first
-    const int t_a = std::min(T, 4), t_b = std::min(T, std::max(t_a, (T + t_a) / 2 & ~1));
-    prep(0, t_a, false);
-    prep(0, 0, true);
-    if (t_a < t_b) prep(t_a, t_b, false);
-    if (t_b < T) prep(t_b, T, false);
     {
-      // residual conv of block 0 from the split raw poses: initialises every accumulator column (and adds the bias)
+      // clear the accumulator: zero A operand times the (always resident, finite) mix image, 128 columns per MMA
       new_group();
-      for (int j = 0; j < a0x_chunks / 2; ++j)
-        add_mma(pl.off_a0x + (uint32_t)(2 * j) * kPlane, kPlane, pl.off_const + st.off_r0, (uint32_t)(2 * cp) * 16, false,
-                (2 * j + 1 < Tout[0]) ? 2 * cp : cp, acc + 2 * j * cp, false);
+      for (int c0 = 0; c0 < accw; c0 += 128)
+        add_mma(pl.off_const + st.off_zero, kPlane, pl.off_const + st.off_ablk, kPlane, false, std::min(128, accw - c0), c0, false);
     }
-    auto gcn0 = [&](int i) {
+    for (int i = 0; i < n_sl; ++i) {
+      const uint32_t slot = pl.off_Q + (uint32_t)(i % ring0_slots) * ring0_slot;
+      const int t0 = i * st0, nt = std::min(st0, T - t0);
+      Stage& s = new_stage(ST_G0, SF_RELU);
+      s.p0 = t0;
+      s.p1 = t0 + nt;
+      s.dst_off = slot;
+      order.back().rd = xin_rng;
+      order.back().wr.push_back(smem_r(slot, (uint32_t)(nt * cp / 8) * kPlane));
       new_group();
-      add_mma(pl.off_a0 + (uint32_t)(2 * i) * kPlane, kPlane, pl.off_const + st.off_w0, (uint32_t)(2 * cp) * 16, false, 2 * cp, stg[i & 1], false);
-    };
-    auto epi0 = [&](int i) { cvt_stage(stg[i & 1], 2 * cp, pl.off_Q + (uint32_t)(i % ring0_slots) * ring0_slot, SF_RELU, 0, 0); };
-    auto tcn0 = [&](int i) {
-      new_group();
-      tcn_mmas(k, 0, pl.off_Q + (uint32_t)(i % ring0_slots) * ring0_slot, 2 * i, std::min(2, T - 2 * i), acc);
+      tcn_mmas(k, 0, slot, t0, nt, 0);
       drop_empty_group();
-    };
-    // diagonal schedule: step s issues the graph conv of slice s (short, its staging buffer is free once slice s-2 is
-    // converted) and then the temporal conv of slice s-2; the epilogue of slice s-1 runs under both
-    for (int sidx = 0; sidx < n_sl + 2; ++sidx) {
-      begin_run();
-      if (sidx < n_sl) gcn0(sidx);
-      if (sidx >= 2) tcn0(sidx - 2);
-      if (sidx >= 1 && sidx - 1 < n_sl) epi0(sidx - 1);
     }
     new_load(LD_WEIGHTS, pl.off_W, st.blk[1].tcn_bytes, st.blk[1].off_tcn);
-    // x1 = relu(acc) -> P (bias already inside the residual product); chunked like block 1's mix
-    const int cw = ct[1] * cp;
-    for (int c0 = 0; c0 < Tout[0] * cp; c0 += cw)
-      cvt_stage(acc + c0, std::min(cw, Tout[0] * cp - c0), pl.off_P + (uint32_t)(c0 / 8) * kPlane, SF_RELU, 0, 0);
+    // x1 = relu(acc + residual conv of the raw poses + bias) -> P, chunked like block 1's mix
+    const int ctn = ct[1];
+    for (int tp0 = 0; tp0 < Tout[0];) {
+      int ntp = std::min(ctn, Tout[0] - tp0);
+      const uint32_t dst = pl.off_P + (uint32_t)(tp0 * cp / 8) * kPlane;
+      uint32_t bytes = (uint32_t)(ntp * cp / 8) * kPlane;
+      // the first chunk of x1 that reaches the pose slot takes all remaining columns: ONE stage whose threads first pull
+      // their poses into registers, then (team barrier) overwrite the slot -- no later stage needs the poses any more
+      const bool hits_xin = dst + bytes > pl.off_xin;
+      if (hits_xin) {
+        ntp = Tout[0] - tp0;
+        bytes = (uint32_t)(ntp * cp / 8) * kPlane;
+        if (ntp > 8) return fail("block-0 output chunk over the pose slot longer than 8 time steps");
+      }
+      Stage& s = new_stage(ST_XEPI0, SF_RELU | (hits_xin ? SF_TEAM_SYNC : 0));
+      s.tmem_col = tp0 * cp;
+      s.n_cg = ntp * cp / 16;
+      s.dst_off = dst;
+      s.p0 = tp0;
+      s.p1 = tp0 + ntp;
+      order.back().rd = xin_rng;
+      order.back().rd.push_back(tmem_r(tp0 * cp, ntp * cp));
+      order.back().wr.push_back(smem_r(dst, bytes));
+      tp0 += ntp;
+    }
   }
 
   // ======================= blocks >= 1
@@ -510,31 +472,30 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
     const bool x_in_P = (b & 1) != 0;
     const uint32_t xb = x_in_P ? pl.off_P : pl.off_Q, ring = x_in_P ? pl.off_Q : pl.off_P;
     const int cin = k.cin_p, cp = k.cp, s = k.stride;
-    const int accw = Tout[b] * cp, smw = ct[b] * cin, sgw = ct[b] * cp;
+    const int accw = Tout[b] * cp, smw = ct[b] * cin;
     const int acc = x_in_P ? 512 - accw : 0;
-    const int stage0 = x_in_P ? 0 : accw;                 // staging columns: n_sm mix buffers, then n_sg graph-conv buffers
-    auto SM = [&](int c) { return stage0 + (c % n_sm[b]) * smw; };
-    auto SG = [&](int c) { return stage0 + n_sm[b] * smw + (c % n_sg[b]) * sgw; };
+    const int SM = x_in_P ? 0 : accw, SG = SM + smw;
     const uint32_t g_img = pl.off_const + k.off_gcn, r_img = pl.off_const + k.off_res, gr_plane = (uint32_t)cp * 16;
     const bool last = b + 1 == nb;
-    auto slot_of = [&](int c) { return ring + (uint32_t)(c % n_slots[b]) * slot_bytes[b]; };
+    const int n_slots = std::min(2, nch[b]);
+    auto slot_of = [&](int c) { return ring + (uint32_t)(c % n_slots) * slot_bytes[b]; };
     auto nt_of = [&](int c) { return std::min(ct[b], Tin[b] - c * ct[b]); };
     auto mix = [&](int c) {
       new_group();
       const int nt = nt_of(c);
       for (int kk = 0; kk < kRows / 16; ++kk)
         add_mma(pl.off_const + st.off_ablk + (uint32_t)(2 * kk) * kPlane, kPlane, xb + (uint32_t)(c * ct[b] * cin / 8) * kPlane + (uint32_t)kk * 256u, 0,
-                true, nt * cin, SM(c), kk > 0);
+                true, nt * cin, SM, kk > 0);
     };
-    auto mepi = [&](int c) { cvt_stage(SM(c), nt_of(c) * cin, slot_of(c), 0, 0, 0); };
+    auto mepi = [&](int c) { cvt_stage(SM, nt_of(c) * cin, slot_of(c), 0, 0, 0); };
     auto gcn = [&](int c) {
       new_group();
       for (int tl = 0; tl < nt_of(c); ++tl)
         for (int ks = 0; ks < cin / 16; ++ks)
           add_mma(slot_of(c) + (uint32_t)(tl * cin / 8 + 2 * ks) * kPlane, kPlane, g_img + (uint32_t)(2 * ks) * gr_plane, gr_plane, false, cp,
-                  SG(c) + tl * cp, ks > 0);
+                  SG + tl * cp, ks > 0);
     };
-    auto gepi = [&](int c) { cvt_stage(SG(c), nt_of(c) * cp, slot_of(c), SF_RELU | SF_BIAS, pl.off_const + k.off_bias_g, cp); };
+    auto gepi = [&](int c) { cvt_stage(SG, nt_of(c) * cp, slot_of(c), SF_RELU | SF_BIAS, pl.off_const + k.off_bias_g, cp); };
     auto res = [&]() {
       new_group();
       for (int tp = 0; tp < Tout[b]; ++tp)
@@ -542,21 +503,17 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
           add_mma(xb + (uint32_t)((s * tp) * cin / 8 + 2 * ks) * kPlane, kPlane, r_img + (uint32_t)(2 * ks) * gr_plane, gr_plane, false, cp,
                   acc + tp * cp, ks > 0);
     };
-    // diagonal schedule: step s issues the temporal conv of chunk s-2, the graph conv of chunk s-1 and the mix of chunk s
-    // (oldest dependency first); the epilogues of chunk s (mix) and s-1 (graph conv) run on the two teams
-    const int n = nch[b];
-    for (int sidx = 0; sidx < n + 2; ++sidx) {
-      begin_run();
-      if (sidx >= 2) {
-        if (sidx == 2) res();
-        new_group();
-        tcn_mmas(k, b, slot_of(sidx - 2), (sidx - 2) * ct[b], nt_of(sidx - 2), acc);
-        drop_empty_group();
-      }
-      if (sidx >= 1 && sidx - 1 < n) gcn(sidx - 1);
-      if (sidx < n) mix(sidx);
-      if (sidx < n) mepi(sidx);
-      if (sidx >= 1 && sidx - 1 < n) gepi(sidx - 1);
+    mix(0);
+    mepi(0);
+    for (int c = 0; c < nch[b]; ++c) {
+      gcn(c);
+      if (c + 1 < nch[b]) mix(c + 1);
+      if (c == 0) res();
+      gepi(c);
+      if (c + 1 < nch[b]) mepi(c + 1);
+      new_group();
+      tcn_mmas(k, b, slot_of(c), c * ct[b], nt_of(c), acc);
+      drop_empty_group();
     }
     if (!last) {
       new_load(LD_WEIGHTS, pl.off_W, st.blk[b + 1].tcn_bytes, st.blk[b + 1].off_tcn);
@@ -641,32 +598,6 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
       }
     }
   }
-  // fused issue bursts: the groups of one diagonal step are issued back to back after ONE set of waits (the head's,
-  // which takes over the members' waits -- all waits are "at least this item", so the maximum per sequence covers them)
-  {
-    run_starts.push_back((int)pr.groups.size());
-    for (size_t r = 0; r + 1 < run_starts.size(); ++r) {
-      const int g0 = run_starts[r], g1 = run_starts[r + 1];
-      if (g1 - g0 < 2) continue;
-      Group& h = pr.groups[g0];
-      for (int g = g0 + 1; g < g1; ++g) {
-        Group& m = pr.groups[g];
-        for (int t = 0; t < kTeams; ++t) {
-          h.wait_e[t] = std::max(h.wait_e[t], m.wait_e[t]);
-          m.wait_e[t] = -1;
-        }
-        // loads complete in no particular order: at most one load wait per run is supported
-        if (m.wait_l >= 0) {
-          if (h.wait_l >= 0 && h.wait_l != m.wait_l) { h.run_len = 0; break; }
-          h.wait_l = m.wait_l;
-          m.wait_l = -1;
-        }
-        m.run_len = 0;
-      }
-      if (h.run_len == 0) return fail("internal: two load waits in one issue burst");
-      h.run_len = (int16_t)(g1 - g0);
-    }
-  }
   // tile boundary: each team's first stage overwrites operand regions the previous tile's last MMAs read, the first
   // weight load overwrites the weights they read; every stage that reads the poses waits for the load the previous
   // tile issued (the pose barrier is one completion ahead: the prologue load)
@@ -675,7 +606,7 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
     if (pr.stages[t].empty()) return fail("an epilogue team has no work");
     pr.stages[t][0].wait_g_prev = last_g;
     for (Stage& s : pr.stages[t])
-      if (s.type == ST_PREP) s.wait_l = (int)pr.loads.size() - 1;
+      if (s.type == ST_G0 || s.type == ST_XEPI0) s.wait_l = (int)pr.loads.size() - 1;
   }
   pr.loads[0].wait_g_prev = (int16_t)last_g;
   // ... and the first MMA group overwrites accumulator columns the previous tile's token stage may still be reading
@@ -700,16 +631,6 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
   pl.n_bars = pl.bar_l0 + pl.n_loads;
   pl.off_bars = off; off += up128((size_t)pl.n_bars * 8);
   pl.off_flags = off; off += 512;
-  pl.off_gtab = off; off += up128(pr.groups.size() * sizeof(Group));
-  pl.off_mtab = off; off += up128(pr.mma.size() * sizeof(Mma));
-  for (size_t i = 0; i < pr.groups.size(); ++i) {
-    Group& g = pr.groups[i];
-    auto bar = [&](int base, int idx) { return idx >= 0 ? pl.off_bars + 8u * (uint32_t)(base + idx) : 0u; };
-    g.bar_e[0] = bar(pl.bar_e0[0], g.wait_e[0]);
-    g.bar_e[1] = bar(pl.bar_e0[1], g.wait_e[1]);
-    g.bar_l = bar(pl.bar_l0, g.wait_l);
-    g.bar_self = bar(pl.bar_g0, (int)i);
-  }
   for (int t = 0; t < kTeams; ++t)
     for (size_t i = 0; i < pr.stages[t].size(); ++i) {
       Stage& s = pr.stages[t][i];

@@ -22,7 +22,8 @@ struct Static {
   std::string why;
   int V = 0, WT = 0, rows = 0, c_in = 0, n_blocks = 0;
   BlockStatic blk[kMaxBlocks];
-  uint32_t off_ablk = 0, off_w0 = 0, off_r0 = 0, off_ell = 0, off_hc = 0, off_scale = 0, off_shift = 0;
+  uint32_t off_ablk = 0, off_zero = 0, off_ell = 0, off_hc = 0, off_scale = 0, off_shift = 0;
+  uint32_t off_g0tab = 0, off_r0tab = 0;                            // block 0 (CUDA cores), fp32 [cp0 / 4][w_x[4], w_y[4], b[4]]
   int ell_width = 5;
   uint32_t const_bytes = 0;
   std::vector<unsigned char> blob;  // const part [0, const_bytes) then the temporal-conv images

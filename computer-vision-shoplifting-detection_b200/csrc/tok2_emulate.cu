@@ -123,13 +123,15 @@ bool emulate(const Static& st, const Program& pr, const float* poses, int64_t B,
   for (size_t i = 0; i < E.tmem.size(); ++i) E.tmem[i] = (float)((int)(E.rnd() % 2001) - 1000);
   const int64_t n_tiles = (B + pl.WT - 1) / pl.WT;
   if (n_tiles == 0) return true;
-  const int V = pl.V, rows = pl.rows, T0 = pl.T0, tv = T0 * V;
-  const int Tout0 = (T0 - 1) / pl.stride0 + 1;
+  const int V = pl.V, rows = pl.rows, T0 = pl.T0, tv = T0 * V, cp0 = pl.cp0;
   const float* scale = reinterpret_cast<const float*>(&E.smem[pl.off_scale]);
   const float* shift = reinterpret_cast<const float*>(&E.smem[pl.off_shift]);
   const float* coef = reinterpret_cast<const float*>(&E.smem[pl.off_ell]);
   const float* hcs = reinterpret_cast<const float*>(&E.smem[pl.off_hc]);
   std::vector<int> poison(128, 0);
+  const float* g0tab = reinterpret_cast<const float*>(&E.smem[pl.off_g0tab]);
+  const float* r0tab = reinterpret_cast<const float*>(&E.smem[pl.off_r0tab]);
+  auto tabv = [](const float* t, int which, int o) { return t[(o / 4) * 12 + which * 4 + (o % 4)]; };
 
   struct Pending { int idx; int64_t tile; bool effect_done; };
   int g_next = 0;
@@ -145,9 +147,10 @@ bool emulate(const Static& st, const Program& pr, const float* poses, int64_t B,
   long named_gen[kTeams] = {0, 0};
   long warp_gen[kTeams][kTeamWarps] = {{0}};
   bool store_pending = false;          // bulk store issued, staging not yet read
-  int store_team = 0;
   int64_t store_tile = 0;
   int store_nw = 0;
+  // XEPI0 keeps the poses of its chunk in "registers" across the team barrier
+  std::vector<float> xreg((size_t)kTeams * kRows * 16 * 2, 0.f);
 
   {
     Load l0 = pr.loads.back();
@@ -279,7 +282,6 @@ bool emulate(const Static& st, const Program& pr, const float* poses, int64_t B,
       };
       const float* xin = reinterpret_cast<const float*>(&E.smem[pl.off_xin]);
       bool finish = false;
-      if (W.e == 0 && W.sub == 0 && w == 0 && store_pending && tm == store_team) do_store();      // bulk_wait_read of the issuing thread
       if (s.type == ST_CVT) {
         for (int cg = half; cg < s.n_cg; cg += 2)
           for (int ln = 0; ln < 32; ++ln) {
@@ -292,25 +294,14 @@ bool emulate(const Static& st, const Program& pr, const float* poses, int64_t B,
             put16(s.dst_off, row, cg, a, s.flags & SF_RELU);
           }
         finish = true;
-      } else if (s.type == ST_PREP) {
-        auto put = [&](uint32_t base, int chunk, int r, const float* m, bool valid) {
-          uint16_t o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-          if (valid) {
-            const float hx = bf2f(f2bf(m[0])), hy = bf2f(f2bf(m[1]));
-            o[0] = o[1] = f2bf(hx);
-            o[2] = f2bf(m[0] - hx);
-            o[3] = o[4] = f2bf(hy);
-            o[5] = f2bf(m[1] - hy);
-            o[6] = o[7] = 0x3F80;
-          }
-          memcpy(&E.smem[base + (uint32_t)chunk * kPlane + (uint32_t)r * 16], o, 16);
-        };
+      } else if (s.type == ST_G0) {
         for (int ln = 0; ln < 32; ++ln) {
           const int row = q * 32 + ln, ww = row / V, v = row - ww * V;
           const bool valid = row < rows && ww < nw;
-          bool bad = false;                                      // (cumulative over the thread's items, as in the kernel)
+          bool bad = false;
           const float* xw = xin + ww * pl.per_w + v;
-          for (int t = s.p0 + half; t < s.p1; t += 2) {
+          const int t = s.p0 + half;                           // thread = (row, time step p0 + half)
+          if (t < s.p1) {
             float m[2] = {0.f, 0.f};
             if (valid) {
               m[0] = hcs[v * 2];
@@ -325,26 +316,63 @@ bool emulate(const Static& st, const Program& pr, const float* poses, int64_t B,
                   m[c] = std::fmaf(e[c], xv, m[c]);
                 }
               }
+              if (bad) m[0] = m[1] = 0.f;
             }
-            put(pl.off_a0, t, row, m, valid && !bad);
-          }
-          if (s.p1 > s.p0 && s.p1 >= T0 && pl.a0_chunks > T0 && half == 0) memset(&E.smem[pl.off_a0 + (uint32_t)T0 * kPlane + (uint32_t)row * 16], 0, 16);
-          if (s.p2) {
-            for (int tp = half; tp < Tout0; tp += 2) {
-              float m[2] = {0.f, 0.f};
-              if (valid)
-                for (int c = 0; c < pl.c_in; ++c) {
-                  const float xv = xw[pl.stride0 * tp * V + c * tv];
-                  bad |= !(std::fabs(xv) <= 3.0e38f);
-                  m[c] = std::fmaf(xv, scale[c * V + v], shift[c * V + v]);
-                }
-              put(pl.off_a0x, tp, row, m, valid && !bad);
+            for (int o = 0; o < cp0; ++o) {
+              const float y = std::fmaf(m[0], tabv(g0tab, 0, o), std::fmaf(m[1], tabv(g0tab, 1, o), tabv(g0tab, 2, o)));
+              const uint16_t hb = pack_one(y, true);
+              const int col = (t - s.p0) * cp0 + o;
+              memcpy(&E.smem[s.dst_off + (uint32_t)(col / 8) * kPlane + (uint32_t)row * 16 + (uint32_t)(col % 8) * 2], &hb, 2);
             }
-            if (pl.a0x_chunks > Tout0 && half == 0) memset(&E.smem[pl.off_a0x + (uint32_t)Tout0 * kPlane + (uint32_t)row * 16], 0, 16);
           }
           if (bad) poison[par * 64 + ww] = 1;
         }
         finish = true;
+      } else if (s.type == ST_XEPI0) {
+        float* xr = &xreg[(size_t)tm * kRows * 32];
+        auto body = [&]() {
+          for (int ln = 0; ln < 32; ++ln) {
+            const int row = q * 32 + ln;
+            for (int i = 0; i < s.p1 - s.p0; ++i)
+              for (int cg = half; cg < cp0 / 16; cg += 2) {
+                float a[16];
+                for (int j = 0; j < 16; ++j) {
+                  const int o = cg * 16 + j;
+                  a[j] = E.tmem[(size_t)row * 512 + s.tmem_col + i * cp0 + o] +
+                         std::fmaf(xr[row * 32 + i], tabv(r0tab, 0, o), std::fmaf(xr[row * 32 + 16 + i], tabv(r0tab, 1, o), tabv(r0tab, 2, o)));
+                }
+                put16(s.dst_off, row, i * (cp0 / 16) + cg, a, true);
+              }
+          }
+        };
+        if (W.sub == 0) {
+          for (int ln = 0; ln < 32; ++ln) {
+            const int row = q * 32 + ln, ww = row / V, v = row - ww * V;
+            const bool valid = row < rows && ww < nw;
+            for (int i = 0; i < s.p1 - s.p0; ++i) {
+              float xa = 0.f, xb = 0.f;
+              if (valid) {
+                const float* xp = xin + ww * pl.per_w + v + pl.stride0 * (s.p0 + i) * V;
+                float u = xp[0], wv = pl.c_in > 1 ? xp[tv] : 0.f;
+                if (!(std::fabs(u) <= 3.0e38f) || !(std::fabs(wv) <= 3.0e38f)) u = wv = 0.f;
+                xa = std::fmaf(u, scale[v], shift[v]);
+                xb = pl.c_in > 1 ? std::fmaf(wv, scale[V + v], shift[V + v]) : 0.f;
+              }
+              xr[row * 32 + i] = xa;
+              xr[row * 32 + 16 + i] = xb;
+            }
+          }
+          if (s.flags & SF_TEAM_SYNC) {
+            arrive_named();
+            W.sub = 1;
+            continue;
+          }
+          body();
+          finish = true;
+        } else {
+          body();
+          finish = true;
+        }
       } else {   // ST_TOKENS: drain + barrier, staging writes + barrier, store
         if (W.sub == 0) {
           if (w == 0 && store_pending) do_store();          // thread 0 waits for the previous store's reads
@@ -376,7 +404,6 @@ bool emulate(const Static& st, const Program& pr, const float* poses, int64_t B,
           if (w == 0) {
             if (store_pending) return fail("emulator: token staging overwritten while a bulk store is pending");
             store_pending = true;
-            store_team = tm;
             store_tile = tile;
             store_nw = nw;
           }

@@ -109,62 +109,82 @@ __device__ __forceinline__ void store16(unsigned char* dst_row, int cg, const fl
   *reinterpret_cast<uint4*>(dst_row + (size_t)(2 * cg + 1) * kPlane) = o1;
 }
 
-__device__ __forceinline__ float bf_hi(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
-
-// Block-0 operand preparation (shopformer/models/gcae.py:351-355 BatchNorm1d, :137-141 adjacency mix): thread = (row
-// (window w, keypoint v), time parity).
-//   A0  chunk t : [hi(mx), hi(mx), lo(mx), hi(my), hi(my), lo(my), 1, 1] of m_c = sum_u A_hat[v][u] * bn(x[c][t][u])
-//   A0x chunk t': the same split of the un-mixed bn(x[c][stride * t'][v])  (operand of the residual 1x1 conv)
-// BatchNorm is folded into the coefficient row; the constant-one columns carry the biases through the MMAs.
+// Block 0, one time slice [p0, p1) (at most two time steps) on the CUDA cores, fp32: thread = (row (window w, keypoint v),
+// time step p0 + half):
+//   m_c = sum_u A_hat[v][u] * bn(x[c][t][u])      (BatchNorm1d folded into the coefficient row, shopformer/models/gcae.py:351-355)
+//   g_o = relu(m_x * W[x][o] + m_y * W[y][o] + b[o])   (graph conv, gcae.py:124-154)  -> bf16 operand slot of the temporal conv
+// The weight table is read with broadcast shared-memory loads, the FMAs are packed fp32x2.  Rows beyond the tile's
+// windows produce finite values nobody reads.
 template <int KW>
-__device__ __forceinline__ void prep_stage(const Plan& pl, const Stage& s, unsigned char* smem, int row, int half, int my_w, int my_v,
-                                           int nw, int* pz) {
-  const int V = pl.V, T0 = pl.T0, tv4 = T0 * V * 4;
+__device__ __forceinline__ void g0_stage(const Plan& pl, const Stage& s, unsigned char* smem, int row, int half, int my_w, int my_v, int nw,
+                                         int* pz) {
+  const int t = s.p0 + half;
+  if (t >= s.p1) return;
+  const int V = pl.V, tv4 = pl.T0 * V * 4, cp0 = pl.cp0;
   const bool valid = row < pl.rows && my_w < nw;
-  const unsigned char* xw = smem + pl.off_xin + (size_t)(my_w * pl.per_w + my_v) * 4;
   const bool two = pl.c_in > 1;
-  float chk = 0.f;                                       // stays 0 unless a pose of this thread is inf or NaN
-  if (s.p1 > s.p0) {
+  const int chunks = cp0 / 8;                         // 8-channel granules per time step
+  unsigned char* dst_row = smem + s.dst_off + (size_t)(half * chunks) * kPlane + (size_t)row * 16;
+  float2 mx = make_float2(0.f, 0.f), my = make_float2(0.f, 0.f);
+  if (valid) {
+    const float4* coef = reinterpret_cast<const float4*>(smem + pl.off_ell);
+    const float2 hc = reinterpret_cast<const float2*>(smem + pl.off_hc)[my_v];
+    const unsigned char* xp = smem + pl.off_xin + (size_t)(my_w * pl.per_w + my_v + t * V) * 4;
     float4 cf[KW];
-    float2 hc = make_float2(0.f, 0.f);
-    if (valid) {
-      const float4* coef = reinterpret_cast<const float4*>(smem + pl.off_ell);
 #pragma unroll
-      for (int k = 0; k < KW; ++k) {
-        cf[k] = coef[k * V + my_v];
-        cf[k].z = __int_as_float(__float_as_int(cf[k].z) * 4);        // neighbour's byte offset
-      }
-      hc = reinterpret_cast<const float2*>(smem + pl.off_hc)[my_v];
+    for (int k = 0; k < KW; ++k) cf[k] = coef[k * V + my_v];
+    float x0[KW], x1[KW];
+#pragma unroll
+    for (int k = 0; k < KW; ++k) {
+      const int db = __float_as_int(cf[k].z) * 4;           // neighbour's byte offset
+      x0[k] = *reinterpret_cast<const float*>(xp + db);
+      x1[k] = two ? *reinterpret_cast<const float*>(xp + tv4 + db) : 0.f;
     }
-    for (int t = s.p0 + half; t < s.p1; t += 2) {
-      uint4 o = make_uint4(0, 0, 0, 0);
-      if (valid) {
-        const unsigned char* xp = xw + t * V * 4;
-        float x0[KW], x1[KW];
+    float a0 = hc.x, a1 = hc.y, chk = 0.f;
 #pragma unroll
-        for (int k = 0; k < KW; ++k) {
-          const int db = __float_as_int(cf[k].z);
-          x0[k] = *reinterpret_cast<const float*>(xp + db);
-          x1[k] = two ? *reinterpret_cast<const float*>(xp + tv4 + db) : 0.f;
-        }
-        float m0 = hc.x, m1 = hc.y;
-#pragma unroll
-        for (int k = 0; k < KW; ++k) {
-          chk = fmaf(x0[k], 0.f, fmaf(x1[k], 0.f, chk));
-          m0 = fmaf(cf[k].x, x0[k], m0);
-          m1 = fmaf(cf[k].y, x1[k], m1);
-        }
-        const float hx = bf_hi(m0), hy = bf_hi(m1);
-        o = make_uint4(pack2(hx, hx), pack2(m0 - hx, hy), pack2(hy, m1 - hy), 0x3F803F80u);
-        if (!(chk == 0.f)) o = make_uint4(0, 0, 0, 0);
-      }
-      *reinterpret_cast<uint4*>(smem + pl.off_a0 + (size_t)t * kPlane + (size_t)row * 16) = o;
+    for (int k = 0; k < KW; ++k) {
+      chk = fmaf(x0[k], 0.f, fmaf(x1[k], 0.f, chk));        // stays 0 unless a gathered pose is inf or NaN
+      a0 = fmaf(cf[k].x, x0[k], a0);
+      a1 = fmaf(cf[k].y, x1[k], a1);
     }
-    if (s.p1 >= T0 && pl.a0_chunks > T0 && half == 0)
-      *reinterpret_cast<uint4*>(smem + pl.off_a0 + (size_t)T0 * kPlane + (size_t)row * 16) = make_uint4(0, 0, 0, 0);
+    if (chk == 0.f) {
+      mx = make_float2(a0, a0);
+      my = make_float2(a1, a1);
+    } else {
+      // a window with a non-finite pose is reported as NaN tokens (the mix MMA would otherwise spread it over the tile)
+      atomicOr(&pz[my_w], 1);
+    }
   }
-  if (s.p2) {
-    const int Tout0 = (T0 - 1) / pl.stride0 + 1;
+  const float4* tab = reinterpret_cast<const float4*>(smem + pl.off_g0tab);
+#pragma unroll 2
+  for (int c8 = 0; c8 < chunks; ++c8) {
+    float4 w[6];                                      // (wx, wy, b) of outputs 8 c8 .. +4, then +4 .. +8
+#pragma unroll
+    for (int i = 0; i < 6; ++i) w[i] = tab[c8 * 6 + i];
+    float2 y[4];
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      y[2 * g] = fma2(mx, make_float2(w[3 * g].x, w[3 * g].y), fma2(my, make_float2(w[3 * g + 1].x, w[3 * g + 1].y), make_float2(w[3 * g + 2].x, w[3 * g + 2].y)));
+      y[2 * g + 1] = fma2(mx, make_float2(w[3 * g].z, w[3 * g].w), fma2(my, make_float2(w[3 * g + 1].z, w[3 * g + 1].w), make_float2(w[3 * g + 2].z, w[3 * g + 2].w)));
+    }
+    *reinterpret_cast<uint4*>(dst_row + (size_t)c8 * kPlane) =
+        make_uint4(pack2_relu(y[0].x, y[0].y), pack2_relu(y[1].x, y[1].y), pack2_relu(y[2].x, y[2].y), pack2_relu(y[3].x, y[3].y));
+  }
+}
+
+// Block 0 output for output times [p0, p1): x1 = relu(acc + BN-folded strided 1x1 residual conv of the raw poses + bias)
+// (gcae.py:237-259); the residual (2 input channels) is added in fp32 here instead of going through the tensor cores.
+// The two column halves of a team take alternate 16-channel groups.
+__device__ __forceinline__ void xepi0_stage(const Plan& pl, const Stage& s, unsigned char* smem, uint32_t lane_base, int row, int half, int my_w,
+                                            int my_v, int nw, int team) {
+  const int V = pl.V, tv = pl.T0 * V, cp0 = pl.cp0;
+  const bool valid = row < pl.rows && my_w < nw;
+  const bool two = pl.c_in > 1;
+  constexpr int kMaxT = 8;                               // output time steps per stage
+  float xa[kMaxT], xb[kMaxT];
+  const int ntp = (int)s.p1 - (int)s.p0;
+  {
+    const float* xw = reinterpret_cast<const float*>(smem + pl.off_xin) + my_w * pl.per_w + my_v;
     float sc0 = 0.f, sh0 = 0.f, sc1 = 0.f, sh1 = 0.f;
     if (valid) {
       const float* scale = reinterpret_cast<const float*>(smem + pl.off_scale);
@@ -176,24 +196,42 @@ __device__ __forceinline__ void prep_stage(const Plan& pl, const Stage& s, unsig
         sh1 = shift[V + my_v];
       }
     }
-    for (int tp = half; tp < Tout0; tp += 2) {
-      uint4 o = make_uint4(0, 0, 0, 0);
-      if (valid) {
-        const unsigned char* xp = xw + pl.stride0 * tp * V * 4;
-        const float xa = *reinterpret_cast<const float*>(xp), xb = two ? *reinterpret_cast<const float*>(xp + tv4) : 0.f;
-        chk = fmaf(xa, 0.f, fmaf(xb, 0.f, chk));
-        const float m0 = fmaf(xa, sc0, sh0), m1 = fmaf(xb, sc1, sh1);
-        const float hx = bf_hi(m0), hy = bf_hi(m1);
-        o = make_uint4(pack2(hx, hx), pack2(m0 - hx, hy), pack2(hy, m1 - hy), 0x3F803F80u);
-        if (!(chk == 0.f)) o = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int i = 0; i < kMaxT; ++i) {
+      xa[i] = xb[i] = 0.f;
+      if (valid && i < ntp) {
+        const float* xp = xw + pl.stride0 * ((int)s.p0 + i) * V;
+        float u = xp[0], w = two ? xp[tv] : 0.f;
+        if (!(fmaf(u, 0.f, w * 0.f) == 0.f)) u = w = 0.f;                 // inf / NaN (the window is already flagged by its G0 stages)
+        xa[i] = fmaf(u, sc0, sh0);
+        xb[i] = fmaf(w, sc1, sh1);
       }
-      *reinterpret_cast<uint4*>(smem + pl.off_a0x + (size_t)tp * kPlane + (size_t)row * 16) = o;
     }
-    if (pl.a0x_chunks > Tout0 && half == 0)
-      *reinterpret_cast<uint4*>(smem + pl.off_a0x + (size_t)Tout0 * kPlane + (size_t)row * 16) = make_uint4(0, 0, 0, 0);
   }
-  // a window with a non-finite pose is reported as NaN tokens (the mix MMA would otherwise spread it over the tile)
-  if (!(chk == 0.f)) atomicOr(&pz[my_w], 1);
+  // this chunk of x1 overwrites the pose slot: every thread of the team has its poses in registers first
+  if (s.flags & SF_TEAM_SYNC) named_bar_sync(1 + team, kTeamWarps * 32);
+  unsigned char* dst_row = smem + s.dst_off + (size_t)row * 16;
+  const float4* tab = reinterpret_cast<const float4*>(smem + pl.off_r0tab);
+  const int cgs = cp0 / 16;
+  for (int cg = half; cg < cgs; cg += 2) {
+#pragma unroll
+    for (int i = 0; i < kMaxT; ++i) {
+      if (i < ntp) {
+        float a[16];
+        tmem_ld16(lane_base + (uint32_t)(s.tmem_col + i * cp0 + cg * 16), a);
+        tmem_ld_wait();
+        const float2 u2 = make_float2(xa[i], xa[i]), w2 = make_float2(xb[i], xb[i]);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {                    // 4 output channels per table entry (rx, ry, rb)
+          const float4 rx = tab[cg * 12 + 3 * g], ry = tab[cg * 12 + 3 * g + 1], rb = tab[cg * 12 + 3 * g + 2];
+          const float2 r0 = fma2(u2, make_float2(rx.x, rx.y), fma2(w2, make_float2(ry.x, ry.y), make_float2(rb.x, rb.y)));
+          const float2 r1 = fma2(u2, make_float2(rx.z, rx.w), fma2(w2, make_float2(ry.z, ry.w), make_float2(rb.z, rb.w)));
+          a[4 * g + 0] += r0.x; a[4 * g + 1] += r0.y; a[4 * g + 2] += r1.x; a[4 * g + 3] += r1.y;
+        }
+        store16<true>(dst_row, i * cgs + cg, a);
+      }
+    }
+  }
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -214,13 +252,6 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
     uint4* z = reinterpret_cast<uint4*>(smem + pl.off_P);                   // operand regions start out finite (0 * NaN = NaN)
     for (uint32_t i = threadIdx.x; i < (pl.off_bars - pl.off_P) / 16; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
     if (threadIdx.x < 128) poison[threadIdx.x] = 0;
-    // the MMA warp reads its tables from shared memory (a dependent constant-bank load costs ~200 cycles when it misses)
-    uint32_t* gt = reinterpret_cast<uint32_t*>(smem + pl.off_gtab);
-    const uint32_t* gs = reinterpret_cast<const uint32_t*>(pl.groups);
-    for (uint32_t i = threadIdx.x; i < (uint32_t)pl.n_groups * (sizeof(Group) / 4); i += kThreads) gt[i] = gs[i];
-    uint32_t* mt = reinterpret_cast<uint32_t*>(smem + pl.off_mtab);
-    const uint32_t* ms = reinterpret_cast<const uint32_t*>(pl.mma);
-    for (uint32_t i = threadIdx.x; i < (uint32_t)pl.n_mma * (sizeof(Mma) / 4); i += kThreads) mt[i] = ms[i];
   }
   if (warp == 0) tmem_alloc(&tmem_base_s, 512);
   if (threadIdx.x == 0) {
@@ -243,48 +274,31 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
 
   if (warp == 0) {
     // =================================================================== MMA issue
-    // One burst per diagonal step: the head group's waits, then every group of the run -- MMAs from the descriptor table,
-    // one commit per group -- without going back to the barriers.  Table entries are fetched four at a time ahead of the
-    // (volatile) MMA instructions.
     const uint32_t base16 = smem_u32(smem) >> 4;
-    const Group* gtab = reinterpret_cast<const Group*>(smem + pl.off_gtab);
-    const Mma* mtab = reinterpret_cast<const Mma*>(smem + pl.off_mtab);
     uint32_t it = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const uint32_t par = it & 1u;
-      for (int g = 0; g < pl.n_groups;) {
-        const Group head = gtab[g];
-        if (timing && it == stamp_it) T2_STAMP(7000 + g);          // group entry loaded
-        if (head.bar_e[0]) mbar_wait(reinterpret_cast<uint64_t*>(smem + head.bar_e[0]), par);
-        if (head.bar_e[1]) mbar_wait(reinterpret_cast<uint64_t*>(smem + head.bar_e[1]), par);
-        if (head.bar_l) mbar_wait(reinterpret_cast<uint64_t*>(smem + head.bar_l), par);
-        if (head.prev_stage >= 0 && it > 0) mbar_wait(&bars[pl.bar_e0[head.prev_team] + head.prev_stage], par ^ 1u);
+      for (int g = 0; g < pl.n_groups; ++g) {
+        const Group gr = pl.groups[g];
+        if (gr.wait_e[0] >= 0) mbar_wait(&bars[pl.bar_e0[0] + gr.wait_e[0]], par);
+        if (gr.wait_e[1] >= 0) mbar_wait(&bars[pl.bar_e0[1] + gr.wait_e[1]], par);
+        if (gr.wait_l >= 0) mbar_wait(&bars[pl.bar_l0 + gr.wait_l], par);
+        if (gr.prev_stage >= 0 && it > 0) mbar_wait(&bars[pl.bar_e0[gr.prev_team] + gr.prev_stage], par ^ 1u);
         tc_fence_after();
         if (timing && it == stamp_it) T2_STAMP(1000 + g);
-        const int run = head.run_len;
         if (elect_one()) {
-          for (int r = 0; r < run; ++r) {
-            const Group gr = gtab[g + r];
-            const int end = gr.first + gr.count;
-            for (int i = gr.first; i < end; i += 4) {
-              const Mma e0 = mtab[i], e1 = mtab[min(i + 1, end - 1)], e2 = mtab[min(i + 2, end - 1)], e3 = mtab[min(i + 3, end - 1)];
-              issue_mma(tmem, e0, base16);
-              if (i + 1 < end) issue_mma(tmem, e1, base16);
-              if (i + 2 < end) issue_mma(tmem, e2, base16);
-              if (i + 3 < end) issue_mma(tmem, e3, base16);
-            }
-            umma_commit(reinterpret_cast<uint64_t*>(smem + gr.bar_self));
-          }
-          if (timing && it == stamp_it) T2_STAMP(9000 + g);        // burst issued and committed
+          // descriptors come straight from the parameter (constant) bank with a warp-uniform index
+          const int end = gr.first + gr.count;
+          for (int i = gr.first; i < end; ++i) issue_mma(tmem, pl.mma[i], base16);
+          umma_commit(&bars[pl.bar_g0 + g]);
         }
         __syncwarp();
-        g += run;
       }
     }
   } else if (warp == 1) {
     // =================================================================== TMA
     // (the whole warp walks the L sequence and waits -- a converged warp is parked by a blocking try_wait, a lone lane
-    // would spin through the scheduler's issue slots -- and lane 0 issues the copies)
+    // spins through the scheduler's issue slots -- and lane 0 issues the copies)
     auto pose_load = [&](int64_t tile) {
       if (tile >= n_tiles || lane != 0) return;
       const int64_t w0 = tile * pl.WT;
@@ -334,14 +348,12 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
       int* pz = poison + par * 64;
       for (int e = 0; e < n_st; ++e) {
         const Stage& s = pl.stages[team][e];
-        if (timing && it == stamp_it && q == 0 && half == 0) T2_STAMP(1500 + e);        // before the waits
         if (s.bar_g) mbar_wait(reinterpret_cast<uint64_t*>(smem + s.bar_g), par);
         if (s.bar_l) mbar_wait(reinterpret_cast<uint64_t*>(smem + s.bar_l), par);
         if (s.bar_eo) mbar_wait(reinterpret_cast<uint64_t*>(smem + s.bar_eo), par);
         if (s.bar_g_prev && it > 0) mbar_wait(reinterpret_cast<uint64_t*>(smem + s.bar_g_prev), par ^ 1u);
         tc_fence_after();
-        if (e == 0 && tt == 0) bulk_wait_read();      // (the previous tile's token store has read its staging bytes, see tok2_build.cu)
-        if (timing && it == stamp_it && q == 0 && half == 0) T2_STAMP(2000 + e);
+        if (timing && it == stamp_it && q == 0) T2_STAMP(2000 + e);
         if (s.type == ST_CVT) {
           const bool relu = s.flags & SF_RELU, bias = s.flags & SF_BIAS;
           const float* bp = reinterpret_cast<const float*>(smem + s.bias_off);
@@ -372,9 +384,11 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
               }
             }
           }
-        } else if (s.type == ST_PREP) {
-          if (pl.ell_width <= 5) prep_stage<5>(pl, s, smem, row, half, my_w, my_v, nw, pz);
-          else prep_stage<8>(pl, s, smem, row, half, my_w, my_v, nw, pz);
+        } else if (s.type == ST_G0) {
+          if (pl.ell_width <= 5) g0_stage<5>(pl, s, smem, row, half, my_w, my_v, nw, pz);
+          else g0_stage<8>(pl, s, smem, row, half, my_w, my_v, nw, pz);
+        } else if (s.type == ST_XEPI0) {
+          xepi0_stage(pl, s, smem, lane_base, row, half, my_w, my_v, nw, team);
         } else {   // ST_TOKENS
           const float* bp = reinterpret_cast<const float*>(smem + s.bias_off);
           float* stg = reinterpret_cast<float*>(smem + pl.off_stage_tok);
@@ -406,11 +420,9 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
             bulk_store(tokens + (size_t)w_first * pl.S_out * pl.d_tok, stg, (uint32_t)nw * (uint32_t)(pl.S_out * pl.d_tok) * 4u);
         }
         fence_proxy_async();
-        if (timing && it == stamp_it && q == 0 && half == 0) T2_STAMP(5000 + e);        // proxy fence done
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(reinterpret_cast<uint64_t*>(smem + s.bar_self));
-        if (timing && it == stamp_it && q == 0 && half == 0) T2_STAMP(6000 + e);        // arrived
       }
     }
     if (tt == 0) bulk_wait_all();
