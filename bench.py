@@ -203,6 +203,85 @@ def run_streaming(a):
     print(json.dumps(line), flush=True)
 
 
+def run_windowing(a):
+    """HBM-bound kernels of the path: `sf_window_normalize` on packed synthetic tracks (SURVEY 8d recipe) and the
+    stand-alone `sf_normality_score`, CUDA-event timed, against the measured HBM copy bandwidth."""
+    from shopformer_b200 import configs as CFG
+    from shopformer_b200.engine import DeviceTracks, PackedTracks, window_normalize
+    from shopformer_b200.synthetic import synth_tracks
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    peaks = load_peaks()
+    C, T, V = CFG.input_shape(a.config)
+    stride = T // 2
+    # ~1500 frames per track -> ~124 windows per track at stride 12
+    n_tracks = max(8, int(a.windows / ((1515 - T) / stride)))
+    tr = synth_tracks(n_tracks, seed=1234)
+    packed = PackedTracks(kp=tr["kp"], frame_no=tr["frame_no"], track_offsets=tr["track_offsets"], track_video=tr["track_video"],
+                          gt=tr["gt"], gt_offsets=tr["gt_offsets"])
+    dt = DeviceTracks(packed, dev)
+    out = window_normalize(dt, T, stride, num_keypoints=V)
+    nwin = int(out["n_windows"])
+
+    def timed(fn, steps):
+        for _ in range(a.warmup):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    sampler = ClockSampler(0)
+    sampler.start()
+    ms_win = timed(lambda: window_normalize(dt, T, stride, num_keypoints=V, sync=False), a.steps)
+    # stand-alone MSE score on tokens / recon of the same number of windows
+    model = build_model(a.config).to(dev)
+    eng = model._sf_engine()
+    S, D = eng.token_shape(T)
+    tok = torch.randn(nwin, S, D, device=dev)
+    rec = torch.randn(nwin, S, D, device=dev)
+    ms_score = timed(lambda: eng.normality_score(tok, rec), a.steps)
+    clocks = sampler.stop()
+    # algorithmic bytes (SURVEY 8d): every raw frame once (stride * K * 12 B per window) + the (2, T, V) fp32 window written;
+    # score: both (S, D) fp32 token tensors read + 4 B written
+    b_win = stride * 17 * 12 + 2 * T * V * 4
+    b_score = 2 * S * D * 4 + 4
+    gb_win = b_win * nwin / (ms_win * 1e-3) / 1e9
+    gb_score = b_score * nwin / (ms_score * 1e-3) / 1e9
+    traffic = load_ncu_traffic("windowing")
+    line = {"metric": "shopformer_windowing_windows_per_sec", "value": nwin / (ms_win * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms_win, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"windowing + normalisation of {n_tracks} synthetic packed tracks ({dt.kp.shape[0]} detections, T={T}, stride {stride}, V={V}) "
+                                   f"-> {nwin} windows; stand-alone score on {nwin} x ({S},{D}) tokens",
+                       "l2": f"inputs larger than L2 ({dt.kp.numel() * 4 / 1e6:.0f} MB of keypoints + {nwin * 2 * T * V * 4 / 1e6:.0f} MB of windows vs 126 MB L2)"},
+            "clocks": clocks, "gpu_launches": 4 * a.steps,
+            "roofline": {"bound": "hbm", "kernel": "k_flag+k_scan+k_compact+k_gather (sf_window_normalize)", "achieved": gb_win, "peak": peaks["hbm_gbs"],
+                         "unit": "GB/s", "frac": gb_win / peaks["hbm_gbs"], "traffic": traffic.get("sf_window_normalize"),
+                         "bytes_per_window": b_win, "peak_source": f"{peaks['source']} HBM copy bandwidth (MEASURED_PEAKS.json)"},
+            "score_kernel": {"ms": ms_score, "windows_per_sec": nwin / (ms_score * 1e-3),
+                             "roofline": {"bound": "hbm", "kernel": "score_kernel (sf_normality_score)", "achieved": gb_score, "peak": peaks["hbm_gbs"],
+                                          "unit": "GB/s", "frac": gb_score / peaks["hbm_gbs"], "traffic": traffic.get("sf_normality_score"),
+                                          "bytes_per_window": b_score}}}
+    print(json.dumps(line), flush=True)
+
+
+def load_ncu_traffic(tag: str):
+    """DRAM bytes per launch parsed from the committed ncu CSVs (profiles/r2_traffic.json, written by
+    profiles/ncu_traffic.py from `ncu --page raw --csv` of the captures); {} when absent."""
+    path = REPO / "profiles" / "r2_traffic.json"
+    if not path.exists():
+        return {}
+    try:
+        return json.load(open(path)).get(tag, {})
+    except Exception:
+        return {}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -214,14 +293,17 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"])
     ap.add_argument("--ref-windows", type=int, default=4096, help="--impl reference / cpu_baseline sample per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mode", default="batch", choices=["batch", "streaming"],
-                    help="streaming: BASELINE config #5 (512 streams, one window per stream per tick, p50/p99 latency)")
+    ap.add_argument("--mode", default="batch", choices=["batch", "streaming", "windowing"],
+                    help="streaming: BASELINE config #5 (512 streams, one window per stream per tick, p50/p99 latency); "
+                         "windowing: the HBM-bound windowing / stand-alone score kernels against the HBM roofline")
     ap.add_argument("--streams", type=int, default=512)
     ap.add_argument("--ticks", type=int, default=2000)
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.mode == "streaming":
         return run_streaming(a)
+    if a.mode == "windowing":
+        return run_windowing(a)
     if a.impl == "reference":
         return run_reference(a)
 

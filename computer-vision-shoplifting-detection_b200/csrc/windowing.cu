@@ -14,9 +14,12 @@
 //   K_compact per-block scan + scatter of (track, start, label) to the compacted order
 //   K_gather  one warp per window: the T*K*3 floats of a window are CONTIGUOUS in the packed
 //             track array, so they are staged into shared memory with 16-byte loads
-//             (scalar head/tail for the 204-byte frame pitch), reduced (centre = mean of valid
-//             keypoints in fp64, scale = max |coord - centre|) with warp shuffles and written
-//             back as two T x V planes with 16-byte stores.
+//             (scalar head/tail for the 204-byte frame pitch); ONE pass over the staged keypoints
+//             collects count / sum / min / max of the valid ones (centre = mean, scale = largest
+//             |coord - centre| = max(max - centre, centre - min)), a second pass writes the
+//             normalised planes into a shared-memory slab in output order, and the slab goes to
+//             HBM with 16-byte streaming stores.  No division or modulo per element: every lane
+//             walks (t, v) incrementally.
 #include <algorithm>
 #include <vector>
 
@@ -36,6 +39,7 @@ struct WinCtx {
   const int64_t* gt_off;
   const uint8_t* gt;
   int n_tracks, K, T, stride, max_gap, V, normalize;
+  int add_neck, conf;           // synthetic 18th keypoint (variant 2); third output plane = raw confidence (variant 1 include_confidence)
   int64_t n_cand;
 };
 
@@ -166,7 +170,13 @@ k_compact(const WinCtx cx, const uint8_t* __restrict__ flag, const uint8_t* __re
 
 constexpr int kGatherWarps = 8;
 
-// One warp per window.  smem per warp: T*K*3 raw floats (+ T*2 neck floats when V == 18).
+// shared-memory floats per warp: staged raw keypoints (+ phase slack), neck, output slab
+__host__ __device__ inline int gather_raw_floats(int T, int K) { return (T * K * 3 + 7) & ~3; }
+__host__ __device__ inline int gather_neck_floats(int T) { return (2 * T + 3) & ~3; }
+__host__ __device__ inline int gather_out_floats(int T, int V, int C) { return (C * T * V + 3) & ~3; }
+inline int gather_per_warp(int T, int K, int V, int C) { return gather_raw_floats(T, K) + gather_neck_floats(T) + gather_out_floats(T, V, C); }
+
+// One warp per window.
 __global__ void __launch_bounds__(kGatherWarps * 32)
 k_gather(const WinCtx cx, const int64_t* __restrict__ n_windows, int64_t n_fixed, const int32_t* __restrict__ win_track,
          const int32_t* __restrict__ win_start, float* __restrict__ poses, int32_t* __restrict__ frame_idx, int per_warp) {
@@ -175,9 +185,14 @@ k_gather(const WinCtx cx, const int64_t* __restrict__ n_windows, int64_t n_fixed
   float* slab = smem + (size_t)warp * per_warp;
   const int T = cx.T, K = cx.K, V = cx.V;
   const int n_raw = T * K * 3;
-  float* neck = slab + ((n_raw + 7) & ~3);         // [T][2], only used when V == 18
-  const bool add_neck = (V == 18);
-  const int Vsrc = add_neck ? 17 : min(V, K);      // keypoints taken from the detection itself
+  const int C = cx.conf ? 3 : 2;
+  float* neck = slab + gather_raw_floats(T, K);     // [T][2], only used with add_neck
+  float* outs = neck + gather_neck_floats(T);       // [C][T][V]: the window in output order
+  const bool add_neck = cx.add_neck != 0;
+  const int Vsrc = add_neck ? min(V - 1, K) : min(V, K);      // keypoints taken from the detection itself
+  const int n_el = T * V;
+  // this lane's walk over (t, v): element i = lane, lane + 32, ...  (one division per kernel, none per element)
+  const int t_first = lane / V, v_first = lane - t_first * V, dt = 32 / V, dv = 32 - dt * V;
   const int64_t nw = n_windows ? *n_windows : n_fixed;      // pre-cut windows: the count is known on the host
   const int64_t warps_total = (int64_t)gridDim.x * kGatherWarps;
   for (int64_t w = (int64_t)blockIdx.x * kGatherWarps + warp; w < nw; w += warps_total) {
@@ -213,70 +228,78 @@ k_gather(const WinCtx cx, const int64_t* __restrict__ n_windows, int64_t n_fixed
       }
       __syncwarp();
     }
-    auto coord = [&](int t, int v, int c) -> float {
-      if (v < Vsrc) return raw[(t * K + v) * 3 + c];
-      if (add_neck && v == 17) return neck[2 * t + c];
-      return 0.f;                                   // zero padding when the detection has fewer keypoints
-    };
-    const int n_el = T * V;
-    float cxm = 0.f, cym = 0.f, scale = 1.f;
-    if (cx.normalize) {
-      double sx = 0.0, sy = 0.0;
-      int cnt = 0;
-      for (int i = lane; i < n_el; i += 32) {
-        const int t = i / V, v = i % V;
-        const float x = coord(t, v, 0), y = coord(t, v, 1);
-        if (x != 0.f || y != 0.f) { sx += (double)x; sy += (double)y; ++cnt; }
+    auto load_xy = [&](int t, int v, float& x, float& y) {
+      if (v < Vsrc) {
+        const float* p = raw + (t * K + v) * 3;
+        x = p[0];
+        y = p[1];
+      } else if (add_neck && v == V - 1) {
+        x = neck[2 * t];
+        y = neck[2 * t + 1];
+      } else {
+        x = y = 0.f;                                // zero padding when the detection has fewer keypoints
       }
+    };
+    float cxm = 0.f, cym = 0.f, inv = 1.f;
+    if (cx.normalize) {
+      // one pass: count, sums (fp32 per lane, fp64 across lanes), min / max of the valid keypoints
+      float sx = 0.f, sy = 0.f, lox = 3.0e38f, hix = -3.0e38f, loy = 3.0e38f, hiy = -3.0e38f;
+      int cnt = 0;
+      for (int t = t_first, v = v_first; t < T;) {
+        float x, y;
+        load_xy(t, v, x, y);
+        if (x != 0.f || y != 0.f) {
+          sx += x; sy += y; ++cnt;
+          lox = fminf(lox, x); hix = fmaxf(hix, x); loy = fminf(loy, y); hiy = fmaxf(hiy, y);
+        }
+        v += dv; t += dt;
+        if (v >= V) { v -= V; ++t; }
+      }
+      double dsx = (double)sx, dsy = (double)sy;
 #pragma unroll
       for (int o = 16; o; o >>= 1) {
-        sx += __shfl_xor_sync(0xffffffffu, sx, o);
-        sy += __shfl_xor_sync(0xffffffffu, sy, o);
+        dsx += __shfl_xor_sync(0xffffffffu, dsx, o);
+        dsy += __shfl_xor_sync(0xffffffffu, dsy, o);
         cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        lox = fminf(lox, __shfl_xor_sync(0xffffffffu, lox, o));
+        hix = fmaxf(hix, __shfl_xor_sync(0xffffffffu, hix, o));
+        loy = fminf(loy, __shfl_xor_sync(0xffffffffu, loy, o));
+        hiy = fmaxf(hiy, __shfl_xor_sync(0xffffffffu, hiy, o));
       }
       if (cnt > 0) {
-        cxm = (float)(sx / (double)cnt);
-        cym = (float)(sy / (double)cnt);
-        float mx = 0.f;
-        for (int i = lane; i < n_el; i += 32) {
-          const int t = i / V, v = i % V;
-          const float x = coord(t, v, 0), y = coord(t, v, 1);
-          if (x != 0.f || y != 0.f) mx = fmaxf(mx, fmaxf(fabsf(x - cxm), fabsf(y - cym)));
-        }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        scale = mx + 1e-6f;
+        cxm = (float)(dsx / (double)cnt);
+        cym = (float)(dsy / (double)cnt);
+        // max |coord - centre| over the valid keypoints = the larger distance of the centre to the per-axis extremes
+        // (fp32 subtraction is monotone, so this is exactly the maximum of the per-element fp32 differences)
+        const float mx = fmaxf(fmaxf(hix - cxm, cxm - lox), fmaxf(hiy - cym, cym - loy));
+        inv = 1.f / (mx + 1e-6f);
       }
     }
-    // ---- write two T x V planes; 2*T*V floats per window
-    float* dst = poses + (size_t)w * 2 * n_el;
-    const bool vec_ok = ((2 * n_el) & 3) == 0;
-    if (vec_ok) {
-      for (int q = lane; q < (2 * n_el) >> 2; q += 32) {
-        float o4[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int i = 4 * q + e;
-          const int c = i / n_el, r = i % n_el;
-          float val = coord(r / V, r % V, c);
-          if (cx.normalize) {
-            val = (val - (c ? cym : cxm)) / scale;
-            if (!isfinite(val)) val = 0.f;          // nan_to_num(nan=0, posinf=0, neginf=0)
-          }
-          o4[e] = val;
-        }
-        __stcs(reinterpret_cast<float4*>(dst) + q, make_float4(o4[0], o4[1], o4[2], o4[3]));
+    // ---- second pass: the window in output order ((C, T, V) planes) into the shared-memory slab
+    for (int t = t_first, v = v_first, i = lane; t < T; i += 32) {
+      float x, y;
+      load_xy(t, v, x, y);
+      if (cx.normalize) {
+        x = (x - cxm) * inv;
+        y = (y - cym) * inv;
+        if (!(fabsf(x) <= 3.0e38f)) x = 0.f;        // nan_to_num(nan=0, posinf=0, neginf=0)
+        if (!(fabsf(y) <= 3.0e38f)) y = 0.f;
       }
+      outs[i] = x;
+      outs[n_el + i] = y;
+      if (C == 3) outs[2 * n_el + i] = v < Vsrc ? raw[(t * K + v) * 3 + 2] : 0.f;
+      v += dv; t += dt;
+      if (v >= V) { v -= V; ++t; }
+    }
+    __syncwarp();
+    // ---- slab -> HBM
+    float* dst = poses + (size_t)w * C * n_el;
+    const int n_out = C * n_el;
+    if (((n_out & 3) == 0)) {
+      const float4* o4 = reinterpret_cast<const float4*>(outs);
+      for (int q = lane; q < (n_out >> 2); q += 32) __stcs(reinterpret_cast<float4*>(dst) + q, o4[q]);
     } else {
-      for (int i = lane; i < 2 * n_el; i += 32) {
-        const int c = i / n_el, r = i % n_el;
-        float val = coord(r / V, r % V, c);
-        if (cx.normalize) {
-          val = (val - (c ? cym : cxm)) / scale;
-          if (!isfinite(val)) val = 0.f;
-        }
-        dst[i] = val;
-      }
+      for (int i = lane; i < n_out; i += 32) dst[i] = outs[i];
     }
     __syncwarp();
   }
@@ -321,13 +344,28 @@ WsLayout layout(const sf_tracks* tr, const sf_window_params* p) {
   return L;
 }
 
+// Launch geometry of k_gather on the CURRENT device.  The opt-in shared-memory size is a per-device function attribute:
+// it is (re)applied whenever the device or the size changes, never cached across devices.
+int gather_launch_config(size_t smem, int64_t blocks_wanted, int* grid) {
+  int dev = 0, max_smem = 0, sms = 0, occ = 1;
+  SF_CUDA_OK(cudaGetDevice(&dev));
+  SF_CUDA_OK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  SF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  SF_REQUIRE(smem <= (size_t)max_smem, SF_E_UNSUPPORTED, "windowing: the window needs %zu bytes of shared memory per block", smem);
+  SF_CUDA_OK(cudaFuncSetAttribute(k_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gather, kGatherWarps * 32, smem));
+  *grid = (int)std::max<int64_t>(1, std::min<int64_t>(blocks_wanted, (int64_t)sms * std::max(occ, 1)));
+  return SF_OK;
+}
+
 int check(const sf_tracks* tr, const sf_window_params* p) {
   SF_REQUIRE(tr && p, SF_E_INVALID, "windowing: null argument");
   SF_REQUIRE(p->seq_len >= 1 && p->stride >= 1 && p->max_gap >= 0, SF_E_INVALID, "windowing: bad seq_len/stride/max_gap");
   SF_REQUIRE(tr->n_tracks >= 0 && tr->kp_per_frame >= 1, SF_E_INVALID, "windowing: bad track table");
   SF_REQUIRE(p->num_keypoints >= 1 && p->num_keypoints <= kMaxV, SF_E_UNSUPPORTED, "windowing: V=%d outside [1,%d]",
              p->num_keypoints, kMaxV);
-  SF_REQUIRE(p->num_keypoints != 18 || tr->kp_per_frame >= 17, SF_E_INVALID, "neck synthesis needs >= 17 source keypoints");
+  SF_REQUIRE(!p->add_neck || (p->num_keypoints >= 8 && tr->kp_per_frame >= 7), SF_E_INVALID,
+             "neck synthesis needs the shoulder keypoints 5 and 6 in the source and a slot for the neck");
   return SF_OK;
 }
 
@@ -354,6 +392,14 @@ extern "C" int sf_window_normalize(const sf_tracks* tr, const sf_window_params* 
   if (rc != SF_OK) return rc;
   SF_REQUIRE(n_windows_dev, SF_E_INVALID, "windowing: n_windows_dev is required");
   cudaStream_t st = (cudaStream_t)stream;
+  // run on the device that owns the track buffers, whatever the caller's current device is
+  DeviceGuard guard;
+  {
+    cudaPointerAttributes attr;
+    SF_CUDA_OK(cudaPointerGetAttributes(&attr, tr->kp_dev));
+    SF_REQUIRE(attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged, SF_E_INVALID, "windowing: kp_dev is not a device pointer");
+    SF_CUDA_OK(guard.enter(attr.device));
+  }
   const WsLayout L = layout(tr, p);
   SF_REQUIRE(workspace_dev && workspace_bytes >= (int64_t)L.total, SF_E_INVALID,
              "windowing: workspace of %lld bytes needed, got %lld", (long long)L.total, (long long)workspace_bytes);
@@ -392,6 +438,8 @@ extern "C" int sf_window_normalize(const sf_tracks* tr, const sf_window_params* 
   cx.max_gap = p->max_gap;
   cx.V = p->num_keypoints;
   cx.normalize = p->normalize;
+  cx.add_neck = p->add_neck ? 1 : 0;
+  cx.conf = p->include_confidence ? 1 : 0;
   cx.n_cand = L.n_cand;
   uint8_t* flag = (uint8_t*)(ws + L.flag);
   uint8_t* label = (uint8_t*)(ws + L.label);
@@ -400,19 +448,11 @@ extern "C" int sf_window_normalize(const sf_tracks* tr, const sf_window_params* 
   k_flag<<<L.n_blocks, kScanBlock, 0, st>>>(cx, flag, label, block_sum);
   k_scan<<<1, 1024, 0, st>>>(block_sum, block_off, L.n_blocks, n_windows_dev);
   k_compact<<<L.n_blocks, kScanBlock, 0, st>>>(cx, flag, label, block_off, labels_dev, window_track_dev, window_start_dev);
-  const int n_raw = cx.T * cx.K * 3;
-  const int per_warp = ((n_raw + 7) & ~3) + ((2 * cx.T + 3) & ~3);
+  const int per_warp = gather_per_warp(cx.T, cx.K, cx.V, cx.conf ? 3 : 2);
   const size_t smem = (size_t)per_warp * kGatherWarps * sizeof(float);
-  int dev = 0, max_smem = 0, sms = 0;
-  SF_CUDA_OK(cudaGetDevice(&dev));
-  SF_CUDA_OK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  SF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  SF_REQUIRE(smem <= (size_t)max_smem, SF_E_UNSUPPORTED, "windowing: seq_len=%d needs %zu bytes of shared memory", cx.T, smem);
-  SF_CUDA_OK(cudaFuncSetAttribute(k_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int occ = 1;
-  SF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gather, kGatherWarps * 32, smem));
-  const int64_t want = (L.n_cand + kGatherWarps - 1) / kGatherWarps;
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sms * std::max(occ, 1)));
+  int grid = 0;
+  rc = gather_launch_config(smem, (L.n_cand + kGatherWarps - 1) / kGatherWarps, &grid);
+  if (rc != SF_OK) return rc;
   k_gather<<<grid, kGatherWarps * 32, smem, st>>>(cx, n_windows_dev, 0, window_track_dev, window_start_dev, poses_dev,
                                                   frame_idx_dev, per_warp);
   SF_CUDA_OK(cudaGetLastError());
@@ -432,30 +472,26 @@ extern "C" int sf_normalize_windows(const float* raw_dev, int64_t B, int32_t T, 
              "sf_normalize_windows: bad argument");
   SF_REQUIRE(V != 18 || K >= 17, SF_E_INVALID, "neck synthesis needs >= 17 source keypoints");
   if (B == 0) return SF_OK;
+  DeviceGuard guard;
+  {
+    cudaPointerAttributes attr;
+    SF_CUDA_OK(cudaPointerGetAttributes(&attr, raw_dev));
+    SF_REQUIRE(attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged, SF_E_INVALID, "sf_normalize_windows: raw_dev is not a device pointer");
+    SF_CUDA_OK(guard.enter(attr.device));
+  }
   WinCtx cx{};
   cx.kp = raw_dev;
   cx.K = K;
   cx.T = T;
   cx.V = V;
   cx.normalize = normalize;
-  const int n_raw = T * K * 3;
-  const int per_warp = ((n_raw + 7) & ~3) + ((2 * T + 3) & ~3);
+  cx.add_neck = V == 18 ? 1 : 0;          // this entry point keeps the variant-2 convention: 18 keypoints = 17 + synthetic neck
+  cx.conf = 0;
+  const int per_warp = gather_per_warp(T, K, V, 2);
   const size_t smem = (size_t)per_warp * kGatherWarps * sizeof(float);
-  static thread_local int sms = 0, max_smem = 0, occ = 0, cfg_smem = -1;
-  if (!sms) {
-    int dev = 0;
-    SF_CUDA_OK(cudaGetDevice(&dev));
-    SF_CUDA_OK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    SF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  }
-  SF_REQUIRE(smem <= (size_t)max_smem, SF_E_UNSUPPORTED, "sf_normalize_windows: T=%d needs %zu bytes of shared memory", T, smem);
-  if (cfg_smem != (int)smem) {
-    SF_CUDA_OK(cudaFuncSetAttribute(k_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gather, kGatherWarps * 32, smem));
-    cfg_smem = (int)smem;
-  }
-  const int64_t want = (B + kGatherWarps - 1) / kGatherWarps;
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sms * std::max(occ, 1)));
+  int grid = 0;
+  int rc = gather_launch_config(smem, (B + kGatherWarps - 1) / kGatherWarps, &grid);
+  if (rc != SF_OK) return rc;
   k_gather<<<grid, kGatherWarps * 32, smem, (cudaStream_t)stream>>>(cx, nullptr, B, nullptr, nullptr, poses_dev, nullptr, per_warp);
   SF_CUDA_OK(cudaGetLastError());
   return SF_OK;

@@ -30,7 +30,7 @@ __all__ = ["PoseLiftDataset", "SyntheticPoseLiftDataset", "PoseLiftDataModule"]
 
 
 class _WindowStore(Dataset):
-    """Windows kept as one (N,2,T,V) CPU tensor; items are views of it."""
+    """Windows kept as one (N,C,T,V) CPU tensor; items are views of it."""
     poses: torch.Tensor
     labels: list
 
@@ -42,7 +42,7 @@ class _WindowStore(Dataset):
 
     @property
     def samples(self):
-        """Reference-format view: list of (T,V,2) fp32 arrays."""
+        """Reference-format view: list of (T,V,C) fp32 arrays."""
         return [p.permute(1, 2, 0).numpy() for p in self.poses]
 
 
@@ -50,16 +50,17 @@ class PoseLiftDataset(_WindowStore):
     def __init__(self, data_dir: str, split: str = "train", seq_len: int = 12, stride: int = 6,
                  num_keypoints: int = 17, normalize: bool = True, include_confidence: bool = False,
                  device: str = "cuda"):
-        if include_confidence:
-            raise NotImplementedError("include_confidence=True (3-channel windows) is not on the accelerated path")
         self.data_dir, self.split, self.seq_len, self.stride = data_dir, split, seq_len, stride
-        self.num_keypoints, self.normalize, self.include_confidence = num_keypoints, normalize, False
-        self.num_channels = 2
-        tracks = load_poselift_split(data_dir, split)          # raises FileNotFoundError like the reference
+        self.num_keypoints, self.normalize, self.include_confidence = num_keypoints, normalize, bool(include_confidence)
+        self.num_channels = 3 if include_confidence else 2
+        # variant 1 takes the detection's own first `num_keypoints` rows and zero-pads (poselift_dataset.py:345-354):
+        # keep that many source rows per detection; it never synthesises a neck
+        tracks = load_poselift_split(data_dir, split, kp_per_frame=max(17, num_keypoints))   # raises FileNotFoundError like the reference
         if not torch.cuda.is_available():
             raise RuntimeError("PoseLiftDataset windows poses on the GPU (sm_100a); no CUDA device is visible")
         dev = DeviceTracks(tracks, torch.device(device))
-        out = window_normalize(dev, seq_len, stride, num_keypoints=num_keypoints, max_gap=5, normalize=normalize)
+        out = window_normalize(dev, seq_len, stride, num_keypoints=num_keypoints, max_gap=5, normalize=normalize,
+                               add_neck=False, include_confidence=self.include_confidence)
         self.poses = out["poses"].cpu()
         self.labels = out["labels"].cpu().tolist()
         self.window_track = out["window_track"].cpu()

@@ -305,7 +305,8 @@ class DeviceTracks:
 
 
 def window_normalize(tracks: DeviceTracks, seq_len: int, stride: int, num_keypoints: int = 17, max_gap: int = 5,
-                     normalize: bool = True, want_frame_indices: bool = False, sync: bool = True):
+                     normalize: bool = True, want_frame_indices: bool = False, sync: bool = True,
+                     add_neck: Optional[bool] = None, include_confidence: bool = False):
     """Run the windowing kernels.  Returns a dict of CUDA tensors trimmed to the number of
     valid windows when ``sync`` (one 8-byte D2H), else capacity-sized tensors + ``n_windows``
     as a device scalar."""
@@ -314,12 +315,16 @@ def window_normalize(tracks: DeviceTracks, seq_len: int, stride: int, num_keypoi
     nt = tracks.native()
     p = N.SfWindowParams()
     p.seq_len, p.stride, p.max_gap, p.num_keypoints, p.normalize = seq_len, stride, max_gap, num_keypoints, int(normalize)
+    # default = the shopformer_2 convention (18 keypoints = COCO-17 + synthetic neck); shopformer/ passes add_neck=False
+    p.add_neck = int(num_keypoints == 18 if add_neck is None else add_neck)
+    p.include_confidence = int(include_confidence)
+    n_planes = 3 if include_confidence else 2
     cap = lib.sf_window_capacity(C.byref(nt), C.byref(p))
     N.check(int(min(cap, 0)), "sf_window_capacity")
     wsb = lib.sf_window_workspace_bytes(C.byref(nt), C.byref(p))
     N.check(int(min(wsb, 0)), "sf_window_workspace_bytes")
     capn = max(int(cap), 1)
-    poses = torch.empty(capn, 2, seq_len, num_keypoints, dtype=torch.float32, device=dev)
+    poses = torch.empty(capn, n_planes, seq_len, num_keypoints, dtype=torch.float32, device=dev)
     labels = torch.empty(capn, dtype=torch.int32, device=dev)
     wtrack = torch.empty(capn, dtype=torch.int32, device=dev)
     wstart = torch.empty(capn, dtype=torch.int32, device=dev)

@@ -73,7 +73,7 @@ def pack_videos(videos: Sequence[Tuple[str, Dict[Any, Any], Optional[np.ndarray]
                         gt_offsets=np.asarray(gt_offs, dtype=np.int64) if any_gt else None, video_names=names)
 
 
-def load_poselift_split(data_dir: str, split: str = "train") -> PackedTracks:
+def load_poselift_split(data_dir: str, split: str = "train", kp_per_frame: int = 17) -> PackedTracks:
     """Pickle_files/{Train|Test}/*.pkl (+ Pickle_files/GT/<video>.npy for the test split),
     file order and GT lookup as shopformer/data/poselift_dataset.py:231-254."""
     root = Path(data_dir)
@@ -89,4 +89,4 @@ def load_poselift_split(data_dir: str, split: str = "train") -> PackedTracks:
         if label_dir is not None and (label_dir / f"{pkl.stem}.npy").exists():
             labels = np.load(label_dir / f"{pkl.stem}.npy")
         videos.append((pkl.stem, data, labels))
-    return pack_videos(videos)
+    return pack_videos(videos, kp_per_frame=kp_per_frame)

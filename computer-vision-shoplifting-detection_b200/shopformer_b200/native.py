@@ -66,7 +66,8 @@ class SfTracks(C.Structure):
 class SfWindowParams(C.Structure):
     _fields_ = [
         ("seq_len", C.c_int32), ("stride", C.c_int32), ("max_gap", C.c_int32),
-        ("num_keypoints", C.c_int32), ("normalize", C.c_int32), ("reserved", C.c_int32 * 3),
+        ("num_keypoints", C.c_int32), ("normalize", C.c_int32), ("add_neck", C.c_int32),
+        ("include_confidence", C.c_int32), ("reserved", C.c_int32 * 1),
     ]
 
 

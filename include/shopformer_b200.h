@@ -153,9 +153,14 @@ typedef struct sf_window_params {
   int32_t seq_len;                 /* T                                                   */
   int32_t stride;
   int32_t max_gap;                 /* 5 in shopformer/, ctor arg in shopformer_2/         */
-  int32_t num_keypoints;           /* V: 17, or 18 = add neck (variant-2 semantics)       */
+  int32_t num_keypoints;           /* V keypoints per frame in the output                 */
   int32_t normalize;               /* centre / scale normalisation on/off                 */
-  int32_t reserved[3];
+  int32_t add_neck;                /* 1: keypoint V-1 = shoulder midpoint (shopformer_2 add_neck_keypoint,
+                                      data/poselift_dataset.py:57-91); 0: keypoints beyond the detection's are zero
+                                      rows (shopformer/data/poselift_dataset.py:352-354)                            */
+  int32_t include_confidence;      /* 1: third output plane = the detections' confidence (shopformer/ ctor flag,
+                                      data/poselift_dataset.py:216-225,349); poses_dev is then (cap, 3, T, V)        */
+  int32_t reserved[1];
 } sf_window_params;
 
 /* Upper bound on the number of windows (every candidate start position), host-only. */
@@ -169,7 +174,7 @@ int64_t sf_window_workspace_bytes(const sf_tracks* tr, const sf_window_params* p
  * Outputs sized by sf_window_capacity(); valid windows are compacted to the front in
  * the reference's order.  `n_windows_dev` (int64, device) receives the count; if
  * `n_windows_host` is non-NULL the call synchronises the stream and stores it there.
- *   poses_dev        (cap, 2, T, V) fp32
+ *   poses_dev        (cap, 2, T, V) fp32   ((cap, 3, T, V) with include_confidence)
  *   labels_dev       (cap) int32           majority vote of GT[min(f, len-1)]
  *   window_track_dev (cap) int32           which track each window came from
  *   window_start_dev (cap) int32           start position inside the track

@@ -189,13 +189,16 @@ def make_windowing(ref1, ref2, manifest):
         cases = [("v1_T12", 1, dict(seq_len=12, stride=6, num_keypoints=17)),
                  ("v1_T24", 1, dict(seq_len=24, stride=12, num_keypoints=17)),
                  ("v1_T24_nonorm", 1, dict(seq_len=24, stride=12, num_keypoints=17, normalize=False)),
+                 ("v1_T12_V18", 1, dict(seq_len=12, stride=6, num_keypoints=18)),
+                 ("v1_T12_conf", 1, dict(seq_len=12, stride=6, num_keypoints=17, include_confidence=True)),
                  ("v2_T24", 2, dict(seq_len=24, stride=12, num_keypoints=17)),
                  ("v2_T12_neck", 2, dict(seq_len=12, stride=6, num_keypoints=18)),
                  ("v2_T12_gap9", 2, dict(seq_len=12, stride=5, num_keypoints=18, max_gap=9))]
         for tag, var, kw in cases:
             cls = (ref1 if var == 1 else ref2)["data.poselift_dataset"].PoseLiftDataset
             ds = cls(str(root), split="test", **kw)
-            wins = np.stack(ds.samples) if len(ds.samples) else np.zeros((0, kw["seq_len"], kw["num_keypoints"], 2), np.float32)
+            nch = 3 if kw.get("include_confidence") else 2
+            wins = np.stack(ds.samples) if len(ds.samples) else np.zeros((0, kw["seq_len"], kw["num_keypoints"], nch), np.float32)
             out[f"{tag}_windows"] = wins.astype(np.float32)
             out[f"{tag}_labels"] = np.asarray(ds.labels, dtype=np.int64)
             item0 = ds[0][0].numpy()
@@ -209,7 +212,7 @@ def make_windowing(ref1, ref2, manifest):
                 frames, gt = videos[name]
                 w, l, fi = W.extract_windows(frames, gt, seq_len=kw["seq_len"], stride=kw["stride"],
                                              num_keypoints=kw["num_keypoints"], variant=var,
-                                             max_gap=kw.get("max_gap", 5), normalize=kw.get("normalize", True))
+                                             max_gap=kw.get("max_gap", 5), normalize=kw.get("normalize", True), channels=nch)
                 ow += w; ol += l; of += fi
             assert ol == list(ds.labels), f"{tag}: oracle labels differ"
             assert len(ow) == len(ds.samples) and all(np.array_equal(a, b) for a, b in zip(ow, ds.samples)), f"{tag}: oracle windows differ"

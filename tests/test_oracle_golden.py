@@ -58,6 +58,8 @@ def test_stride_rules():
 WIN_CASES = [("v1_T12", 1, dict(seq_len=12, stride=6, num_keypoints=17)),
              ("v1_T24", 1, dict(seq_len=24, stride=12, num_keypoints=17)),
              ("v1_T24_nonorm", 1, dict(seq_len=24, stride=12, num_keypoints=17, normalize=False)),
+             ("v1_T12_V18", 1, dict(seq_len=12, stride=6, num_keypoints=18)),          # variant 1: zero 18th keypoint, no neck
+             ("v1_T12_conf", 1, dict(seq_len=12, stride=6, num_keypoints=17, include_confidence=True)),
              ("v2_T24", 2, dict(seq_len=24, stride=12, num_keypoints=17)),
              ("v2_T12_neck", 2, dict(seq_len=12, stride=6, num_keypoints=18)),
              ("v2_T12_gap9", 2, dict(seq_len=12, stride=5, num_keypoints=18, max_gap=9))]
@@ -72,12 +74,13 @@ def test_windowing_oracle_bit_exact(tag, variant, kw, golden_dir):
     g = np.load(golden_dir / "windowing.npz")
     wins, labels, fidx = [], [], []
     for name, (frames, gt) in sorted(fixture_videos().items()):
-        w, l, f = W.extract_windows(frames, gt, variant=variant, **kw)
+        okw = {k: v for k, v in kw.items() if k != "include_confidence"}
+        w, l, f = W.extract_windows(frames, gt, variant=variant, channels=3 if kw.get("include_confidence") else 2, **okw)
         wins += w; labels += l; fidx += f
     assert np.array_equal(np.asarray(labels), g[f"{tag}_labels"])
     assert np.array_equal(np.asarray(fidx), g[f"{tag}_frame_indices"])
     assert np.array_equal(np.stack(wins), g[f"{tag}_windows"])            # bit-exact, floats included
-    assert W.windows_as_model_input(wins).shape == (len(wins), 2, kw["seq_len"], kw["num_keypoints"])
+    assert W.windows_as_model_input(wins).shape == (len(wins), 3 if kw.get("include_confidence") else 2, kw["seq_len"], kw["num_keypoints"])
 
 
 def test_windowing_oracle_edge_cases():
