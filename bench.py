@@ -55,7 +55,10 @@ def load_peaks():
 
 
 # DRAM bytes per launch of the dominant kernel, from the committed ncu capture (profiles/r1_bf16_summary.md)
-NCU_DRAM_BYTES = {("A", "bf16", "tokenizer"): 296_178_688}
+def ncu_traffic(config: str, precision: str, kernel: str):
+    """DRAM bytes per launch of a kernel (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture),
+    parsed from the committed ncu CSV by profiles/ncu_traffic.py into profiles/r2_traffic.json; None when absent."""
+    return load_ncu_traffic("batch").get(f"{config}/{precision}/{kernel}")
 
 
 def build_model(name: str):
@@ -196,7 +199,7 @@ def run_streaming(a):
     line = {"metric": "shopformer_streaming_tick_latency_ms", "value": float(np.percentile(lat, 50)), "unit": "ms",
             "higher_is_better": False, "n_gpus": 1, "p50_ms": float(np.percentile(lat, 50)), "p99_ms": float(np.percentile(lat, 99)),
             "mean_ms": float(lat.mean()), "windows_per_sec": a.streams / (float(lat.mean()) * 1e-3), "ticks": a.ticks,
-            "dtype": "f32" if a.precision == "fp32" else "bf16", "data": "synthetic",
+            "dtype": "f32" if a.precision == "fp32" else "/".join(sorted(set(sc.eng.tc_formats(T)))), "data": "synthetic",
             "config": {"workload": f"streaming config #5: {a.streams} streams, 1 new window (T={T}, stride {stride}) per stream per tick, "
                                    f"config {a.config}; latency = pinned H2D of the new frames + CUDA-graph replay "
                                    f"(ring shift, normalise, tokenizer, transformer, score) + D2H of the scores, host wall clock"}}
@@ -214,12 +217,15 @@ def run_windowing(a):
     peaks = load_peaks()
     C, T, V = CFG.input_shape(a.config)
     stride = T // 2
-    # ~1500 frames per track -> ~124 windows per track at stride 12
-    n_tracks = max(8, int(a.windows / ((1515 - T) / stride)))
-    tr = synth_tracks(n_tracks, seed=1234)
-    packed = PackedTracks(kp=tr["kp"], frame_no=tr["frame_no"], track_offsets=tr["track_offsets"], track_video=tr["track_video"],
-                          gt=tr["gt"], gt_offsets=tr["gt_offsets"])
-    dt = DeviceTracks(packed, dev)
+    # ~1500 frames per track -> ~124 windows per track at stride 12; generated on the device (the default 1 M windows are
+    # 12.6 M detections = 2.6 GB of keypoints: launch overheads of the four kernels are amortised as in a real sweep)
+    from shopformer_b200.synthetic import synth_tracks_device
+    n_win_target = a.windows if a.windows != 65536 else 1_048_576
+    n_tracks = max(8, int(n_win_target / ((1512 - T) // stride + 1)))
+    kp, fno, off, vid, gt, gto = synth_tracks_device(n_tracks, 1512, dev, seed=1234, channels=3)
+    dt = DeviceTracks.__new__(DeviceTracks)
+    dt.host, dt.device, dt.kp, dt.frame_no, dt.gt = None, dev, kp, fno, gt
+    dt._off, dt._vid, dt._gto = off, vid, gto
     out = window_normalize(dt, T, stride, num_keypoints=V)
     nwin = int(out["n_windows"])
 
@@ -290,20 +296,33 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="A")
     ap.add_argument("--windows", type=int, default=65536, help="windows per GPU per step")
-    ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default="tc", choices=["fp32", "tc", "bf16"],
+                    help="tc (alias bf16): the 16-bit tensor-core kernels, operand format per --tc-format; fp32: CUDA-core kernels")
+    ap.add_argument("--tc-format", default="auto", choices=["auto", "fp16", "bf16"],
+                    help="16-bit operand format of the tensor-core path (auto = fp16 when the weights fit its range)")
+    ap.add_argument("--total-windows", type=int, default=10_000_000, help="--mode tracks: windows of the whole sweep (strong scaling)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra legs (config C @ 262,144, model-call loop, from-tracks e2e)")
     ap.add_argument("--ref-windows", type=int, default=4096, help="--impl reference / cpu_baseline sample per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mode", default="batch", choices=["batch", "streaming", "windowing"],
+    ap.add_argument("--mode", default="batch", choices=["batch", "streaming", "windowing", "tracks"],
                     help="streaming: BASELINE config #5 (512 streams, one window per stream per tick, p50/p99 latency); "
-                         "windowing: the HBM-bound windowing / stand-alone score kernels against the HBM roofline")
+                         "windowing: the HBM-bound windowing / stand-alone score kernels against the HBM roofline; "
+                         "tracks: BASELINE config #4 (--total-windows windows cut from packed tracks sharded by track over the "
+                         "ranks, NCCL all-gather of the scores; strong scaling)")
     ap.add_argument("--streams", type=int, default=512)
     ap.add_argument("--ticks", type=int, default=2000)
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
+    if a.precision == "bf16":
+        a.precision = "tc"
+    if a.tc_format != "auto":
+        os.environ["SHOPFORMER_B200_TC_FORMAT"] = a.tc_format
     if a.mode == "streaming":
         return run_streaming(a)
     if a.mode == "windowing":
         return run_windowing(a)
+    if a.mode == "tracks":
+        return run_tracks(a)
     if a.impl == "reference":
         return run_reference(a)
 
@@ -330,6 +349,8 @@ def main():
     eng = model._sf_engine()
     C, T, V = CFG.input_shape(a.config)
     S, D = eng.token_shape(T)
+    fmt_tok, fmt_xf = eng.tc_formats(T)
+    dtype = "f32" if a.precision == "fp32" else (fmt_tok if fmt_tok == fmt_xf else f"{fmt_tok}+{fmt_xf}")
     n = a.windows
     xs = synth_windows(n, T, V, seed=1234 + rank)[0]
     x = torch.from_numpy(xs).to(dev)
@@ -416,8 +437,13 @@ def main():
     h2d = int(xs.nbytes)
     d2h = int(host_scores.nbytes)
 
+    # ---- extra end-to-end legs (rank 0's view, N = 1 only; the headline `e2e` above stays the pre-cut-window call)
+    extras = {}
+    if world == 1 and not a.no_extras:
+        extras = extra_legs(a, model, eng, xs, T, V, dev)
+
     # ---- the other precision of BASELINE configs[1] ("fp32 and bf16"), device resident, 3 steps
-    other = "fp32" if a.precision == "bf16" else "bf16"
+    other = "fp32" if a.precision != "fp32" else "tc"
     other_line = None
     try:
         eng.score_windows(x, precision=other)
@@ -446,10 +472,10 @@ def main():
         achieved = dom_flops * n / ((tok_ms if dom == "tokenizer" else xf_ms) * 1e-3) / 1e12
         peak = peaks["bf16_sustained"]
         roofline = {"bound": "tensor", "kernel": f"{dom}_{a.precision}", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": achieved / peak, "traffic": NCU_DRAM_BYTES.get((a.config, a.precision, dom)) if n == 65536 else None,
-                    "traffic_note": ("dram__bytes_read.sum + dram__bytes_write.sum of this kernel per 65,536-window launch, bytes, from the ncu "
-                                     "--set full capture summarised in profiles/r1_bf16_summary.md (algorithmic: 213.9 MB poses in + 106.9 MB "
-                                     "tokens out)") if (a.config, a.precision, dom) in NCU_DRAM_BYTES and n == 65536 else None,
+                    "frac": achieved / peak, "traffic": ncu_traffic(a.config, a.precision, dom) if n == 65536 else None,
+                    "traffic_note": ("dram__bytes_read.sum + dram__bytes_write.sum of this kernel per 65,536-window launch, bytes, parsed from the "
+                                     "committed ncu --set full CSV (profiles/r2_traffic.json; algorithmic: 213.9 MB poses in + 106.9 MB tokens out)")
+                    if n == 65536 and ncu_traffic(a.config, a.precision, dom) is not None else None,
                     "peak_source": f"{peaks['source']} bf16 sustained (MEASURED_PEAKS.json)",
                     "flops_per_window": dom_flops, "kernel_ms": {"tokenizer": tok_ms, "transformer": xf_ms, "sum_vs_step": (tok_ms + xf_ms) / (ms / a.steps)},
                     "path_frac": path_flops * n / ((tok_ms + xf_ms) * 1e-3) / 1e12 / peak,
@@ -480,20 +506,184 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32" if a.precision == "fp32" else "bf16", "data": "synthetic",
+        "dtype": dtype, "data": "synthetic",
         "config": {"workload": f"shopformer config {a.config}{' (BASELINE configs[1])' if a.config == 'A' else ''}: {n} synthetic windows per GPU, "
                                f"T={T}, V={V}, S={S}, d={D}, deterministic synthetic weights",
                    "windows_per_gpu_per_step": n, "precision": a.precision,
+                   "tc_operand_format": {"tokenizer": fmt_tok, "transformer": fmt_xf} if a.precision != "fp32" else None,
                    "l2": (f"inputs larger than L2 ({xs.nbytes / 1e6:.0f} MB of windows per step vs 126 MB L2)" if xs.nbytes > 126e6 else
                           f"inputs ({xs.nbytes / 1e6:.0f} MB) + tokens smaller than the 126 MB L2: not a headline configuration"),
                    "collective": "NCCL all-gather of fp32 scores" if world > 1 else "none (1 GPU)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "api": "sf_runner_score (C ABI, host buffers): the page-locked pose buffer is read in place by the tokenizer's TMA over PCIe (h2d bytes moved by the kernel), scores copied back; pageable sources go through a 4-slot pinned ring", "steps": e2e_steps},
+                "api": "sf_runner_score (C ABI, host buffers): 16,384-window chunks of the page-locked pose buffer are DMA-ed on a copy stream "
+                       "while the previous chunk is scored on the compute stream, scores copied back per chunk; pageable sources are staged "
+                       "through a 4-slot pinned ring", "steps": e2e_steps, **extras},
         "gpu_launches": 2 * a.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         "parity": {"max_rel_err_vs_cpu_oracle": err, "checked_windows": 256, "tolerance": 1e-3 if a.precision == "fp32" else 1e-2},
         "other_precision": other_line,
     }
     print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def extra_legs(a, model, eng, xs, T, V, dev):
+    """Extra keys of the N=1 line: (1) the same windows scored FROM PACKED TRACKS on the host (sf_runner_score_tracks:
+    x, y only, 12 new frames per stride-12 window = half the PCIe bytes of pre-cut windows), (2) the reference's own loop
+    shape -- `model(x)` on host tensors at batch 32 (train.py:evaluate) and 4096 -- so per-call host overhead is visible,
+    (3) BASELINE configs[2]: config C at 262,144 windows, device resident."""
+    from shopformer_b200 import configs as CFG
+    from shopformer_b200.engine import PackedTracks
+    from shopformer_b200.synthetic import synth_tracks, synth_windows
+    out = {}
+    n = xs.shape[0]
+    stride = T // 2
+    # (1) tracks of ~1500 detections -> about n windows; the confidence channel is dropped at ingest
+    try:
+        n_tracks = max(8, int(n / ((1515 - T) / stride)))
+        tr = synth_tracks(n_tracks, seed=4321)
+        kp2 = torch.from_numpy(np.ascontiguousarray(tr["kp"][:, :, :2])).pin_memory().numpy()
+        host = PackedTracks(kp=kp2, frame_no=tr["frame_no"], track_offsets=tr["track_offsets"], track_video=tr["track_video"],
+                            gt=tr["gt"], gt_offsets=tr["gt_offsets"])
+        kw = dict(add_neck=False, precision=a.precision, chunk=16384)
+        for _ in range(2):
+            res = eng.score_tracks_host(host, T, stride, **kw)
+        reps = 5
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            res = eng.score_tracks_host(host, T, stride, **kw)
+        dt = time.perf_counter() - t0
+        nw = int(res["n_windows"])
+        out["from_tracks"] = {"value": nw * reps / dt, "unit": UNIT, "windows_per_step": nw,
+                              "h2d_bytes_per_step": int(kp2.nbytes + tr["frame_no"].nbytes), "d2h_bytes_per_step": 16 * nw,
+                              "api": "sf_runner_score_tracks: host packed tracks (x, y) -> windowing + normalisation + scoring on the device -> "
+                                     "host scores, labels and window index; groups of whole tracks uploaded under the previous group's kernels"}
+    except Exception as exc:
+        out["from_tracks"] = {"error": str(exc)[:200]}
+    # (2) the reference's loop: model(x)['normality_score'] per batch, host tensors in, host scores out
+    try:
+        loop = {}
+        xt = torch.from_numpy(xs)
+        with torch.no_grad():
+            for bs, nb in ((32, 256), (4096, 16)):
+                tot = bs * nb
+                def run():
+                    acc = []
+                    for i in range(0, tot, bs):
+                        acc.append(model(xt[i:i + bs].to(dev))["normality_score"].cpu().numpy())
+                    return acc
+                run()
+                t0 = time.perf_counter()
+                run()
+                dt = time.perf_counter() - t0
+                loop[f"batch_{bs}"] = {"windows_per_sec": tot / dt, "us_per_call": 1e6 * dt / nb}
+        out["model_call_loop"] = {"api": "model(poses.to(device))['normality_score'].cpu().numpy() per batch (shopformer/train.py:311-319, "
+                                         "evaluate.py:89-99), pageable host tensors", **loop}
+    except Exception as exc:
+        out["model_call_loop"] = {"error": str(exc)[:200]}
+    # (3) BASELINE configs[2]
+    try:
+        if a.config == "A":
+            mc = build_model("C").to(dev)
+            ec = mc._sf_engine()
+            Cc, Tc, Vc = CFG.input_shape("C")
+            nC = 262144
+            xc = torch.from_numpy(synth_windows(nC, Tc, Vc, seed=99)[0]).to(dev)
+            ec.score_windows(xc, precision=a.precision)
+            torch.cuda.synchronize(dev)
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _ in range(3):
+                ec.score_windows(xc, precision=a.precision)
+            c1.record()
+            torch.cuda.synchronize(dev)
+            ms = c0.elapsed_time(c1) / 3
+            out["config_C_262144"] = {"value": nC / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "tc_operand_format": list(ec.tc_formats(Tc)),
+                                      "path_frac": CFG.USEFUL_FLOPS["C"] * nC / (ms * 1e-3) / 1e12 / load_peaks()["bf16_sustained"],
+                                      "workload": "BASELINE configs[2]: shopformer_2 default config (V=17 T=24 H=64, 12 heads, 4+4 layers, ff 512), "
+                                                  "262,144 windows device resident, 3 steps"}
+            del xc, ec, mc
+    except Exception as exc:
+        out["config_C_262144"] = {"error": str(exc)[:200]}
+    return out
+
+
+def run_tracks(a):
+    """BASELINE configs[3]: a sweep of --total-windows windows cut from packed tracks, sharded by track over the ranks with the
+    host prefix sum of per-track window counts (global window index = reference order), every rank windows + normalises +
+    scores its shard from device-resident tracks, the scores are all-gathered over NCCL.  Strong scaling."""
+    from shopformer_b200 import configs as CFG
+    from shopformer_b200.engine import DeviceTracks, PackedTracks
+    from shopformer_b200.sharding import gather_ragged, shard_tracks
+    from shopformer_b200.synthetic import synth_tracks_device
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    model = build_model(a.config).to(dev)
+    eng = model._sf_engine()
+    C, T, V = CFG.input_shape(a.config)
+    stride = T // 2
+    track_len = 1512
+    per_track = (track_len - T) // stride + 1
+    n_tracks = (a.total_windows + per_track - 1) // per_track
+    offsets = np.arange(n_tracks + 1, dtype=np.int64) * track_len
+    lo, hi, first = shard_tracks(offsets, T, stride, world)[rank]
+    # every rank generates only its own tracks (seeded by the first track index: the sweep is the same at every N)
+    kp, fno, off, vid, gt, gto = synth_tracks_device(hi - lo, track_len, dev, seed=1234 + lo, channels=2)
+    dt = DeviceTracks.__new__(DeviceTracks)
+    dt.host, dt.device, dt.kp, dt.frame_no, dt.gt = None, dev, kp, fno, gt
+    dt._off, dt._vid, dt._gto = off, vid, gto
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step():
+        r = eng.score_tracks(dt, T, stride, add_neck=False, precision=a.precision)
+        allv, counts = gather_ragged(r["scores"])
+        return r, allv, counts
+
+    for _ in range(max(a.warmup, 1)):
+        r, allv, counts = step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    steps = max(1, min(a.steps, 5))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        r, allv, counts = step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    total = int(sum(counts))
+    if rank == 0:
+        fmt = eng.tc_formats(T)
+        line = {"metric": METRIC, "value": total * steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(a.warmup, 1),
+                "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32" if a.precision == "fp32" else "/".join(sorted(set(fmt))), "data": "synthetic",
+                "config": {"workload": f"BASELINE configs[3]: sweep of {n_tracks} synthetic packed tracks x {track_len} detections (x, y; "
+                                       f"{n_tracks * track_len * V * 8 / 1e9:.1f} GB) -> {total} valid windows (T={T}, stride {stride}) of config {a.config}, "
+                                       f"sharded by track with the host prefix sum of per-track window counts, scores all-gathered",
+                           "windows_total": total, "windows_per_rank": counts, "precision": a.precision,
+                           "l2": "inputs larger than L2 (GBs of keypoints per rank)", "collective": "NCCL all-gather of fp32 scores (ragged: counts first)" if world > 1 else "none (1 GPU)"},
+                "gpu_launches": None, "clocks": clocks,
+                "note": "device-resident tracks; per step: k_flag/k_scan/k_compact once, then per 131,072-window pass k_gather + tokenizer + transformer"}
+        passes = (int(counts[0]) + 131071) // 131072
+        line["gpu_launches"] = steps * (3 + 3 * passes)
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

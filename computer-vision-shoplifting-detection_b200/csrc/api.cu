@@ -1,6 +1,8 @@
 // C-ABI entry points of the scoring hot path + the host-buffer runner.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "sf_internal.h"
 
@@ -22,9 +24,14 @@ int check_T(const sf_model* m, int T) {
 }
 // tensor-core tokenizer: the multi-window tile kernel (tokenizer2_bf16.cu) when it covers the shape, otherwise the
 // one-window-per-pass kernel (tokenizer_bf16.cu)
-int launch_tokenizer_tc(const sf_model* m, const float* poses, int64_t B, int T, float* tokens, cudaStream_t st) {
-  if (tokenizer2_supported(m, T)) return launch_tokenizer2(m, poses, B, T, tokens, st);
+int launch_tokenizer_tc(const sf_model* m, const float* poses, int64_t B, int T, float* tokens, cudaStream_t st, DevCount cnt = DevCount()) {
+  if (tokenizer2_supported(m, T)) return launch_tokenizer2(m, poses, B, T, tokens, st, cnt);
+  SF_REQUIRE(!cnt.n, SF_E_UNSUPPORTED, "device-side batch size needs tokenizer v2");
   return launch_tokenizer_bf16(m, poses, B, T, tokens, st);
+}
+// kernels that accept a device-side batch size (DevCount): tokenizer v2 + the tensor-core transformer
+bool supports_dev_count(const sf_model* m, int T, int precision) {
+  return precision == SF_PREC_BF16 && tokenizer2_supported(m, T) && transformer_bf16_supported(m, token_len(m, T));
 }
 }  // namespace
 
@@ -40,6 +47,14 @@ extern "C" int64_t sf_workspace_bytes(const sf_model* m, int64_t B, int32_t T) {
   const int S = token_len(m, T);
   // tokens staged between the two kernels when the caller does not ask for them
   return align256(B * (int64_t)S * m->xf.d_tok * (int64_t)sizeof(float)) + align256(tokenizer_fp32_workspace(m, B, T));
+}
+
+extern "C" int sf_model_tc_formats(const sf_model* m, int32_t T, int32_t* tokenizer_f16, int32_t* transformer_f16) {
+  SF_REQUIRE(m && T >= 1, SF_E_INVALID, "sf_model_tc_formats: bad argument");
+  // tokenizer v2 follows the model's format; the one-window-per-pass kernel (hidden-64 / pooled shapes) is bf16 only
+  if (tokenizer_f16) *tokenizer_f16 = (m->device >= 0 && tokenizer2_supported(m, T) && tokenizer2_f16(m)) ? 1 : 0;
+  if (transformer_f16) *transformer_f16 = m->xfprog.f16 ? 1 : 0;
+  return SF_OK;
 }
 
 extern "C" int sf_tokenize(const sf_model* m, const float* poses_dev, int64_t B, int32_t T, int32_t precision,
@@ -81,9 +96,21 @@ extern "C" int sf_normality_score(const sf_model* m, const float* tokens_dev, co
   return launch_score(m, tokens_dev, recon_dev, B, S, reduction, scores_dev, (cudaStream_t)stream);
 }
 
+static int score_windows_impl(const sf_model* m, const float* poses_dev, int64_t B, int32_t T, int32_t reduction,
+                              int32_t precision, float* scores_dev, float* tokens_dev, float* recon_dev,
+                              void* workspace_dev, int64_t workspace_bytes, void* stream, DevCount cnt);
+
 extern "C" int sf_score_windows(const sf_model* m, const float* poses_dev, int64_t B, int32_t T, int32_t reduction,
                                 int32_t precision, float* scores_dev, float* tokens_dev, float* recon_dev,
                                 void* workspace_dev, int64_t workspace_bytes, void* stream) {
+  return score_windows_impl(m, poses_dev, B, T, reduction, precision, scores_dev, tokens_dev, recon_dev, workspace_dev, workspace_bytes,
+                            stream, DevCount());
+}
+
+// `cnt`: optional device-side count of valid windows (B is then an upper bound; see DevCount)
+static int score_windows_impl(const sf_model* m, const float* poses_dev, int64_t B, int32_t T, int32_t reduction,
+                              int32_t precision, float* scores_dev, float* tokens_dev, float* recon_dev,
+                              void* workspace_dev, int64_t workspace_bytes, void* stream, DevCount cnt) {
   int rc = check_T(m, T);
   if (rc) return rc;
   SF_REQUIRE(B >= 0 && (B == 0 || (poses_dev && scores_dev)), SF_E_INVALID, "sf_score_windows: null buffer");
@@ -112,12 +139,130 @@ extern "C" int sf_score_windows(const sf_model* m, const float* poses_dev, int64
     const int64_t n = std::min(pass, B - off);
     float* tok = tokens_dev ? tokens_dev + off * tok_elems : tok_ws;
     const float* x = poses_dev + off * pose_elems;
-    rc = precision == SF_PREC_BF16 ? launch_tokenizer_tc(m, x, n, T, tok, st) : launch_tokenizer_fp32(m, x, n, T, tok, ws, ws_left, st);
+    SF_REQUIRE(!cnt.n || precision == SF_PREC_BF16, SF_E_UNSUPPORTED, "device-side batch size needs the tensor-core kernels");
+    const DevCount c{cnt.n, cnt.off + off};
+    rc = precision == SF_PREC_BF16 ? launch_tokenizer_tc(m, x, n, T, tok, st, c) : launch_tokenizer_fp32(m, x, n, T, tok, ws, ws_left, st);
     if (rc) return rc;
     float* rec = recon_dev ? recon_dev + off * tok_elems : nullptr;
     float* sc = scores_dev + off * score_stride;
-    rc = precision == SF_PREC_BF16 ? launch_transformer_bf16(m, tok, n, S, reduction, rec, sc, st)
+    rc = precision == SF_PREC_BF16 ? launch_transformer_bf16(m, tok, n, S, reduction, rec, sc, st, c)
                                    : launch_transformer_fp32(m, tok, n, S, reduction, rec, sc, st);
+    if (rc) return rc;
+  }
+  return SF_OK;
+}
+
+// ------------------------------------------------------------------------------------ tracks -> scores
+namespace {
+struct TrackScoreLayout {
+  int64_t win_ws, count, poses, score_ws, total, pass, cap;
+};
+TrackScoreLayout track_score_layout(const sf_model* m, const sf_tracks* tr, const sf_window_params* p) {
+  TrackScoreLayout L{};
+  L.cap = window_candidates(tr, p);
+  L.pass = std::max<int64_t>(1, std::min<int64_t>(L.cap, kScoreChunk));
+  const int64_t per_w = (int64_t)m->cfg.in_channels * p->seq_len * m->cfg.num_keypoints;
+  int64_t off = 0;
+  L.win_ws = off; off += align256(sf_window_workspace_bytes(tr, p));
+  L.count = off; off += 256;
+  L.poses = off; off += align256(L.pass * per_w * (int64_t)sizeof(float));
+  L.score_ws = off; off += align256(sf_workspace_bytes(m, L.pass, p->seq_len));
+  L.total = off;
+  return L;
+}
+int check_tracks_vs_model(const sf_model* m, const sf_tracks* tr, const sf_window_params* p) {
+  int rc = check_model(m);
+  if (rc) return rc;
+  SF_REQUIRE(tr && p, SF_E_INVALID, "null tracks / window parameters");
+  SF_REQUIRE(p->num_keypoints == m->cfg.num_keypoints, SF_E_INVALID, "window keypoints %d != model keypoints %d", p->num_keypoints,
+             m->cfg.num_keypoints);
+  SF_REQUIRE((p->include_confidence ? 3 : 2) == m->cfg.in_channels, SF_E_INVALID, "window channels do not match the model's in_channels=%d",
+             m->cfg.in_channels);
+  return check_T(m, p->seq_len);
+}
+}  // namespace
+
+extern "C" int64_t sf_score_from_tracks_workspace_bytes(const sf_model* m, const sf_tracks* tr, const sf_window_params* p) {
+  if (check_tracks_vs_model(m, tr, p) != SF_OK || sf_window_workspace_bytes(tr, p) < 0) return SF_E_INVALID;
+  return track_score_layout(m, tr, p).total;
+}
+
+// Sync-free core (kernels that take the window count from device memory): every pass is launched for its capacity and
+// clamps to the count on the device; the count stays in the workspace (`*n_windows_dev_out` points at it).
+static int score_from_tracks_async(const sf_model* m, const sf_tracks* tr, const sf_window_params* p, int32_t precision,
+                                   float* scores_dev, int32_t* labels_dev, int32_t* window_track_dev, int32_t* window_start_dev,
+                                   const int64_t** n_windows_dev_out, void* workspace_dev, int64_t workspace_bytes, cudaStream_t st) {
+  const TrackScoreLayout L = track_score_layout(m, tr, p);
+  char* ws = (char*)workspace_dev;
+  int64_t* n_dev = (int64_t*)(ws + L.count);
+  *n_windows_dev_out = n_dev;
+  int rc = window_index(tr, p, labels_dev, window_track_dev, window_start_dev, n_dev, ws + L.win_ws, L.poses - L.win_ws, st);
+  if (rc) return rc;
+  float* poses = (float*)(ws + L.poses);
+  for (int64_t off = 0; off < L.cap; off += L.pass) {
+    const int64_t cnt = std::min(L.pass, L.cap - off);
+    rc = window_gather(tr, p, window_track_dev, window_start_dev, n_dev, off, cnt, poses, nullptr, ws + L.win_ws, st);
+    if (rc) return rc;
+    rc = score_windows_impl(m, poses, cnt, p->seq_len, SF_REDUCE_MEAN, precision, scores_dev + off, nullptr, nullptr, ws + L.score_ws,
+                            L.total - L.score_ws, st, DevCount{n_dev, off});
+    if (rc) return rc;
+  }
+  return SF_OK;
+}
+
+extern "C" int sf_score_from_tracks(const sf_model* m, const sf_tracks* tr, const sf_window_params* p, int32_t precision,
+                                    float* scores_dev, int32_t* labels_dev, int32_t* window_track_dev, int32_t* window_start_dev,
+                                    int64_t* n_windows_host, void* workspace_dev, int64_t workspace_bytes, void* stream) {
+  int rc = check_tracks_vs_model(m, tr, p);
+  if (rc) return rc;
+  SF_REQUIRE(n_windows_host, SF_E_INVALID, "sf_score_from_tracks: n_windows_host is required");
+  SF_REQUIRE(precision == SF_PREC_FP32 || precision == SF_PREC_BF16, SF_E_INVALID, "unknown precision %d", precision);
+  SF_REQUIRE(sf_window_workspace_bytes(tr, p) >= 0, SF_E_INVALID, "bad tracks / window parameters");
+  const TrackScoreLayout L = track_score_layout(m, tr, p);
+  *n_windows_host = 0;
+  if (L.cap == 0) return SF_OK;
+  SF_REQUIRE(scores_dev && labels_dev && window_track_dev && window_start_dev, SF_E_INVALID, "sf_score_from_tracks: null output");
+  SF_REQUIRE(workspace_dev && workspace_bytes >= L.total, SF_E_INVALID, "sf_score_from_tracks: workspace of %lld bytes needed, got %lld",
+             (long long)L.total, (long long)workspace_bytes);
+  DeviceGuard guard;
+  SF_CUDA_OK(guard.enter(m->device));
+  int dev = 0;
+  rc = window_device_of(tr, &dev);
+  if (rc) return rc;
+  SF_REQUIRE(dev == m->device, SF_E_INVALID, "tracks live on device %d, the model on device %d", dev, m->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)workspace_dev;
+  int64_t* n_dev = (int64_t*)(ws + L.count);
+  if (supports_dev_count(m, p->seq_len, precision)) {
+    // everything is enqueued without knowing the count; it is read back once, behind the last kernel
+    const int64_t* n_out = nullptr;
+    rc = score_from_tracks_async(m, tr, p, precision, scores_dev, labels_dev, window_track_dev, window_start_dev, &n_out, workspace_dev,
+                                 workspace_bytes, st);
+    if (rc) return rc;
+    int64_t n = 0;
+    SF_CUDA_OK(cudaMemcpyAsync(&n, n_out, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    SF_CUDA_OK(cudaStreamSynchronize(st));
+    *n_windows_host = n;
+    return SF_OK;
+  }
+  rc = window_index(tr, p, labels_dev, window_track_dev, window_start_dev, n_dev, ws + L.win_ws, L.poses - L.win_ws, st);
+  if (rc) return rc;
+  // the first pass does not need the count: its gather clamps on the device, and the count arrives while it runs
+  float* poses = (float*)(ws + L.poses);
+  rc = window_gather(tr, p, window_track_dev, window_start_dev, n_dev, 0, L.pass, poses, nullptr, ws + L.win_ws, st);
+  if (rc) return rc;
+  int64_t n = 0;
+  SF_CUDA_OK(cudaMemcpyAsync(&n, n_dev, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  SF_CUDA_OK(cudaStreamSynchronize(st));
+  *n_windows_host = n;
+  for (int64_t off = 0; off < n; off += L.pass) {
+    const int64_t cnt = std::min(L.pass, n - off);
+    if (off > 0) {
+      rc = window_gather(tr, p, window_track_dev, window_start_dev, n_dev, off, L.pass, poses, nullptr, ws + L.win_ws, st);
+      if (rc) return rc;
+    }
+    rc = sf_score_windows(m, poses, cnt, p->seq_len, SF_REDUCE_MEAN, precision, scores_dev + off, nullptr, nullptr, ws + L.score_ws,
+                          L.total - L.score_ws, st);
     if (rc) return rc;
   }
   return SF_OK;
@@ -146,6 +291,20 @@ struct sf_runner {
   int64_t big_out_cap;
   void* big_ws;
   int64_t big_ws_bytes;
+  // sf_runner_score_tracks: two groups of tracks in flight (upload of group g+1 under the kernels of group g); grow-only
+  struct TrackSlot {
+    float* kp;
+    int32_t* frame_no;
+    int64_t frames_cap;
+    char* out_dev;         // scores | labels | window_track | window_start, `win_cap` entries each
+    char* out_pin;
+    int64_t win_cap;
+    void* ws;
+    int64_t ws_bytes;
+    cudaEvent_t uploaded, done;
+  } ts[2];
+  uint8_t* gt_dev;
+  int64_t gt_cap;
 };
 
 extern "C" int sf_runner_create(const sf_model* m, int32_t T, int64_t max_chunk, sf_runner** out) {
@@ -201,6 +360,17 @@ extern "C" void sf_runner_destroy(sf_runner* r) {
     if (r->computed[i]) cudaEventDestroy(r->computed[i]);
   }
   if (r->ws) cudaFree(r->ws);
+  for (int i = 0; i < 2; ++i) {
+    sf_runner::TrackSlot& s = r->ts[i];
+    if (s.kp) cudaFree(s.kp);
+    if (s.frame_no) cudaFree(s.frame_no);
+    if (s.out_dev) cudaFree(s.out_dev);
+    if (s.out_pin) cudaFreeHost(s.out_pin);
+    if (s.ws) cudaFree(s.ws);
+    if (s.uploaded) cudaEventDestroy(s.uploaded);
+    if (s.done) cudaEventDestroy(s.done);
+  }
+  if (r->gt_dev) cudaFree(r->gt_dev);
   if (r->big_out) cudaFree(r->big_out);
   if (r->big_ws) cudaFree(r->big_ws);
   if (r->copy_st) cudaStreamDestroy(r->copy_st);
@@ -225,7 +395,12 @@ extern "C" int sf_runner_score(sf_runner* r, const float* poses_host, int64_t B,
     if (cudaPointerGetAttributes(&attr, poses_host) == cudaSuccess) src_pinned = attr.type == cudaMemoryTypeHost;
     else cudaGetLastError();
   }
-  if (src_pinned) {
+  // A page-locked source is DMA-ed chunk by chunk straight out of the caller's buffer (no staging memcpy) by the ring
+  // below: the copy engine sustains ~55 GB/s over PCIe 5 against ~38 GB/s for kernel loads from mapped host memory, and
+  // the upload of chunk c+1 runs under the kernels of chunk c.  SF_RUNNER_INPLACE=1 keeps the older zero-copy mode (one
+  // pass of the kernels reading host memory in place), which wins only when the kernels, not PCIe, are the bottleneck.
+  static const bool inplace = getenv("SF_RUNNER_INPLACE") != nullptr;
+  if (src_pinned && inplace) {
     // Page-locked source: no staging copy at all.  The tokenizer's TMA (the precise path: its global loads) reads each
     // window straight out of host memory over PCIe one window ahead of use, so the whole batch is ONE pass of the two
     // kernels; only the scores come back.  (h2d bytes per call are the same B * window bytes, moved by the kernel.)
@@ -291,6 +466,185 @@ extern "C" int sf_runner_score(sf_runner* r, const float* poses_host, int64_t B,
       SF_CUDA_OK(cudaEventSynchronize(r->computed[s]));
       memcpy(scores_host + pending_off[s], r->pin_out[s], pending_n[s] * sizeof(float));
     }
+  return SF_OK;
+}
+
+// Host tracks -> host scores (see the header).  Groups of whole tracks of about `chunk` windows' worth of frames: the raw
+// detections of group g+1 are uploaded on the copy stream while group g is windowed and scored on the compute stream.
+extern "C" int sf_runner_score_tracks(sf_runner* r, const sf_tracks* th, const sf_window_params* p, int32_t precision,
+                                      float* scores_host, int32_t* labels_host, int32_t* window_track_host,
+                                      int32_t* window_start_host, int64_t* n_windows_host) {
+  SF_REQUIRE(r && th && p && n_windows_host, SF_E_INVALID, "sf_runner_score_tracks: null argument");
+  SF_REQUIRE(p->seq_len == r->T, SF_E_INVALID, "the runner was created for T=%d, the windows have T=%d", r->T, p->seq_len);
+  const sf_model* m = r->m;
+  int rc = check_tracks_vs_model(m, th, p);
+  if (rc) return rc;
+  *n_windows_host = 0;
+  const int64_t cap_total = sf_window_capacity(th, p);
+  SF_REQUIRE(cap_total >= 0, SF_E_INVALID, "sf_runner_score_tracks: bad tracks / window parameters");
+  if (cap_total == 0) return SF_OK;
+  SF_REQUIRE(scores_host && th->kp_dev && th->frame_no_dev && th->track_offsets_host, SF_E_INVALID, "sf_runner_score_tracks: null buffer");
+  DeviceGuard guard;
+  SF_CUDA_OK(guard.enter(m->device));
+  const int KC = th->kp_channels == 2 ? 2 : 3;
+  const size_t frame_floats = (size_t)th->kp_per_frame * KC;
+  const bool has_gt = th->gt_dev && th->gt_offsets_host && th->track_video_host && th->n_videos > 0;
+  if (has_gt) {                                      // frame labels of every video: uploaded once
+    const int64_t gt_bytes = th->gt_offsets_host[th->n_videos];
+    if (gt_bytes > r->gt_cap) {
+      if (r->gt_dev) cudaFree(r->gt_dev);
+      r->gt_dev = nullptr;
+      r->gt_cap = 0;
+      SF_CUDA_OK(cudaMalloc((void**)&r->gt_dev, (size_t)std::max<int64_t>(gt_bytes, 1)));
+      r->gt_cap = gt_bytes;
+    }
+    SF_CUDA_OK(cudaMemcpyAsync(r->gt_dev, th->gt_dev, (size_t)gt_bytes, cudaMemcpyHostToDevice, r->copy_st));
+  }
+  // ---- groups of whole tracks
+  const int64_t target_frames = std::max<int64_t>(r->chunk * (int64_t)p->stride, 1);
+  std::vector<int> g_begin;                          // first track of each group (+ sentinel)
+  {
+    int t = 0;
+    while (t < th->n_tracks) {
+      g_begin.push_back(t);
+      const int64_t f0 = th->track_offsets_host[t];
+      int e = t + 1;
+      while (e < th->n_tracks && th->track_offsets_host[e + 1] - f0 <= target_frames) ++e;
+      t = e;
+    }
+    g_begin.push_back(th->n_tracks);
+  }
+  const int n_groups = (int)g_begin.size() - 1;
+  struct Group {
+    sf_tracks tr;
+    std::vector<int64_t> off;                        // track offsets relative to the group's first frame
+    int64_t cap, n;
+    int t0;
+  };
+  std::vector<Group> groups((size_t)n_groups);
+  auto prepare = [&](int g) -> int {                 // size the slot and enqueue the upload of group g
+    Group& G = groups[g];
+    sf_runner::TrackSlot& s = r->ts[g & 1];
+    const int t0 = g_begin[g], t1 = g_begin[g + 1];
+    const int64_t f0 = th->track_offsets_host[t0], f1 = th->track_offsets_host[t1];
+    G.t0 = t0;
+    G.off.resize((size_t)(t1 - t0 + 1));
+    for (int t = t0; t <= t1; ++t) G.off[(size_t)(t - t0)] = th->track_offsets_host[t] - f0;
+    G.tr = *th;
+    G.tr.n_frames = f1 - f0;
+    G.tr.n_tracks = t1 - t0;
+    G.tr.track_offsets_host = G.off.data();
+    G.tr.track_video_host = has_gt ? th->track_video_host + t0 : nullptr;
+    G.tr.gt_dev = has_gt ? r->gt_dev : nullptr;
+    G.cap = sf_window_capacity(&G.tr, p);
+    G.n = 0;
+    if (f1 - f0 > s.frames_cap) {
+      if (s.kp) cudaFree(s.kp);
+      if (s.frame_no) cudaFree(s.frame_no);
+      s.kp = nullptr;
+      s.frame_no = nullptr;
+      s.frames_cap = 0;
+      const int64_t want = std::max(f1 - f0, target_frames + target_frames / 4);
+      SF_CUDA_OK(cudaMalloc((void**)&s.kp, (size_t)want * frame_floats * sizeof(float)));
+      SF_CUDA_OK(cudaMalloc((void**)&s.frame_no, (size_t)want * sizeof(int32_t)));
+      s.frames_cap = want;
+    }
+    if (G.cap > s.win_cap) {
+      if (s.out_dev) cudaFree(s.out_dev);
+      if (s.out_pin) cudaFreeHost(s.out_pin);
+      s.out_dev = s.out_pin = nullptr;
+      s.win_cap = 0;
+      const int64_t want = std::max(G.cap, r->chunk + r->chunk / 4);
+      SF_CUDA_OK(cudaMalloc((void**)&s.out_dev, (size_t)want * 16));
+      SF_CUDA_OK(cudaMallocHost((void**)&s.out_pin, (size_t)want * 16 + 256));
+      s.win_cap = want;
+    }
+    G.tr.kp_dev = s.kp;
+    G.tr.frame_no_dev = s.frame_no;
+    if (G.cap > 0) {
+      const int64_t need = sf_score_from_tracks_workspace_bytes(m, &G.tr, p);
+      SF_REQUIRE(need >= 0, SF_E_INVALID, "sf_runner_score_tracks: bad group");
+      if (need > s.ws_bytes) {
+        if (s.ws) cudaFree(s.ws);
+        s.ws = nullptr;
+        s.ws_bytes = 0;
+        SF_CUDA_OK(cudaMalloc(&s.ws, (size_t)(need + need / 4)));
+        s.ws_bytes = need + need / 4;
+      }
+    }
+    if (!s.uploaded) SF_CUDA_OK(cudaEventCreateWithFlags(&s.uploaded, cudaEventDisableTiming));
+    if (!s.done) SF_CUDA_OK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    // the slot's previous group (g - 2) has been drained by the caller before this point
+    SF_CUDA_OK(cudaMemcpyAsync(s.kp, th->kp_dev + (size_t)f0 * frame_floats, (size_t)(f1 - f0) * frame_floats * sizeof(float),
+                               cudaMemcpyHostToDevice, r->copy_st));
+    SF_CUDA_OK(cudaMemcpyAsync(s.frame_no, th->frame_no_dev + f0, (size_t)(f1 - f0) * sizeof(int32_t), cudaMemcpyHostToDevice, r->copy_st));
+    SF_CUDA_OK(cudaEventRecord(s.uploaded, r->copy_st));
+    return SF_OK;
+  };
+  int64_t out_off = 0;
+  auto drain = [&](int g) -> int {                   // D2H results of group g -> the caller's arrays
+    Group& G = groups[g];
+    sf_runner::TrackSlot& s = r->ts[g & 1];
+    SF_CUDA_OK(cudaEventSynchronize(s.done));
+    if (G.n < 0) memcpy(&G.n, s.out_pin + s.win_cap * 16, sizeof(int64_t));
+    const int64_t n = G.n, wc = s.win_cap;
+    memcpy(scores_host + out_off, s.out_pin, (size_t)n * 4);
+    if (labels_host) memcpy(labels_host + out_off, s.out_pin + wc * 4, (size_t)n * 4);
+    if (window_track_host) {
+      const int32_t* wt = (const int32_t*)(s.out_pin + wc * 8);
+      for (int64_t i = 0; i < n; ++i) window_track_host[out_off + i] = wt[i] + G.t0;
+    }
+    if (window_start_host) memcpy(window_start_host + out_off, s.out_pin + wc * 12, (size_t)n * 4);
+    out_off += n;
+    return SF_OK;
+  };
+  // Two groups in flight.  With kernels that take the window count from device memory (tokenizer v2 + the tensor-core
+  // transformer) a group is enqueued in full -- upload, windowing, scoring, D2H of capacity-sized results and the count --
+  // without any host synchronisation, so the GPU never waits for the host between groups; otherwise sf_score_from_tracks
+  // synchronises once per group.
+  const bool async = supports_dev_count(m, p->seq_len, precision);
+  auto launch = [&](int g) -> int {
+    Group& G = groups[g];
+    sf_runner::TrackSlot& s = r->ts[g & 1];
+    SF_CUDA_OK(cudaStreamWaitEvent(r->comp_st, s.uploaded, 0));
+    const int64_t wc = s.win_cap;
+    if (G.cap > 0) {
+      float* sc = (float*)s.out_dev;
+      int32_t *lb = (int32_t*)(s.out_dev + wc * 4), *wt = (int32_t*)(s.out_dev + wc * 8), *wsr = (int32_t*)(s.out_dev + wc * 12);
+      int64_t n_copy = 0;
+      if (async) {
+        const int64_t* n_dev = nullptr;
+        int rc2 = score_from_tracks_async(m, &G.tr, p, precision, sc, lb, wt, wsr, &n_dev, s.ws, s.ws_bytes, r->comp_st);
+        if (rc2) return rc2;
+        SF_CUDA_OK(cudaMemcpyAsync(s.out_pin + wc * 16, n_dev, sizeof(int64_t), cudaMemcpyDeviceToHost, r->comp_st));
+        G.n = -1;                                      // read from the pinned tail when the group is drained
+        n_copy = G.cap;
+      } else {
+        int rc2 = sf_score_from_tracks(m, &G.tr, p, precision, sc, lb, wt, wsr, &G.n, s.ws, s.ws_bytes, r->comp_st);
+        if (rc2) return rc2;
+        n_copy = G.n;
+      }
+      for (int k = 0; k < 4 && n_copy > 0; ++k)
+        SF_CUDA_OK(cudaMemcpyAsync(s.out_pin + wc * 4 * k, s.out_dev + wc * 4 * k, (size_t)n_copy * 4, cudaMemcpyDeviceToHost, r->comp_st));
+    }
+    SF_CUDA_OK(cudaEventRecord(s.done, r->comp_st));
+    return SF_OK;
+  };
+  for (int g = 0; g < n_groups; ++g) {
+    if (g >= 2) {                                    // slot g & 1 still holds group g - 2
+      rc = drain(g - 2);
+      if (rc) return rc;
+    }
+    rc = prepare(g);                                 // upload of this group runs under the previous group's kernels
+    if (rc) return rc;
+    rc = launch(g);
+    if (rc) return rc;
+  }
+  for (int g = std::max(0, n_groups - 2); g < n_groups; ++g) {
+    rc = drain(g);
+    if (rc) return rc;
+  }
+  *n_windows_host = out_off;
   return SF_OK;
 }
 

@@ -93,6 +93,27 @@ static inline uint16_t f2bf(float f) {       // round-to-nearest-even fp32 -> bf
   u += 0x7fffu + ((u >> 16) & 1u);
   return (uint16_t)(u >> 16);
 }
+static inline uint16_t f2h(float f) {        // round-to-nearest-even fp32 -> fp16 (|f| < 65520)
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  const uint16_t sign = (uint16_t)((u >> 16) & 0x8000u);
+  const int e = (int)((u >> 23) & 0xFF) - 127 + 15;
+  uint32_t m = u & 0x7FFFFFu;
+  if (e >= 31) return (uint16_t)(sign | 0x7C00u);
+  if (e <= 0) {
+    if (e < -10) return sign;
+    m |= 0x800000u;
+    const int sh = 14 - e;
+    uint32_t h = m >> sh;
+    const uint32_t rem = m & ((1u << sh) - 1), half = 1u << (sh - 1);
+    if (rem > half || (rem == half && (h & 1u))) ++h;
+    return (uint16_t)(sign | h);
+  }
+  uint32_t h = ((uint32_t)e << 10) | (m >> 13);
+  const uint32_t rem = m & 0x1FFFu;
+  if (rem > 0x1000u || (rem == 0x1000u && (h & 1u))) ++h;
+  return (uint16_t)(sign | h);
+}
 static inline int pad16(int x) { return (x + 15) & ~15; }
 
 struct LinOff {
@@ -417,14 +438,21 @@ extern "C" int sf_model_create(const sf_config* cfg, int32_t n_tensors, const ch
   const int ffc = std::min(pad16(dff), 128);                  // FFN hidden processed in chunks of <= 128 columns
   bool xf_ok = dp <= 160 && dtp <= 160 && hd % 4 == 0 && (H == 1 || H == 2 || H % 4 == 0) && d % 8 == 0 && d_tok % 8 == 0;
   int max_w_bytes = 0;
+  // 16-bit operand format of the transformer: fp16 (11 significant bits; activations saturate at +-65504) unless the
+  // config asks for bf16 or a packed value is outside fp16's range.  (tcgen05 kind::f16 needs A and B in the SAME
+  // format -- a mixed fp16 x bf16 descriptor is an illegal instruction -- so activations and weights switch together.)
+  bool xf_f16 = cfg->tc_format != SF_TC_BF16;
+  for (size_t i = 0; i < pk.arena.size() && xf_f16; ++i)
+    if (!(std::fabs(pk.arena[i]) < 32768.f)) xf_f16 = false;
   auto image = [&](const LinOff& lin, int n0, int n_cnt, int k0, int k_cnt, int Npad, int Kpad) {
     const size_t off = bf_alloc((size_t)Npad * Kpad);
+    const bool half = xf_f16;
     for (int kc = 0; kc < Kpad / 8; ++kc)
       for (int n = 0; n < Npad; ++n)
         for (int e = 0; e < 8; ++e) {
           const int k = kc * 8 + e;
           const float v = (n < n_cnt && k < k_cnt) ? pk.arena[lin.wt + (size_t)(k0 + k) * lin.N + (n0 + n)] : 0.f;
-          bf[off + ((size_t)kc * Npad + n) * 8 + e] = f2bf(v);
+          bf[off + ((size_t)kc * Npad + n) * 8 + e] = half ? f2h(v) : f2bf(v);
         }
     max_w_bytes = std::max(max_w_bytes, Npad * Kpad * 2);
     return off;
@@ -553,7 +581,7 @@ extern "C" int sf_model_create(const sf_config* cfg, int32_t n_tensors, const ch
   {
     Tokenizer host_tok;
     fill_tok(pk.arena.data(), host_tok);
-    m->tok2 = tok2_create(host_tok, cfg->pool_tokens, !host_only);
+    m->tok2 = tok2_create(host_tok, cfg->pool_tokens, !host_only, cfg->tc_format != SF_TC_BF16);
   }
   if (host_only) {
     m->host_arena = (float*)malloc(m->arena_bytes);
@@ -562,7 +590,7 @@ extern "C" int sf_model_create(const sf_config* cfg, int32_t n_tensors, const ch
     fill_tok(m->host_arena, m->tok);
     memset(&m->xf, 0, sizeof(m->xf));
     m->xf.d_tok = d_tok;
-    m->xfprog = XfProgram{nullptr, 0, 0, 0, 0, 0};
+    m->xfprog = XfProgram{nullptr, 0, 0, 0, 0, 0, 0};
     *out = m;
     return SF_OK;
   }
@@ -608,7 +636,7 @@ extern "C" int sf_model_create(const sf_config* cfg, int32_t n_tensors, const ch
       ops[i].ln_b = prog[i].has_ln ? A + prog[i].lb_off : nullptr;
     }
     m->xfops_dev = nullptr;
-    m->xfprog = XfProgram{nullptr, (int)ops.size(), dp, dtp, xf_ok && !ops.empty() ? 1 : 0, max_w_bytes};
+    m->xfprog = XfProgram{nullptr, (int)ops.size(), dp, dtp, xf_ok && !ops.empty() ? 1 : 0, max_w_bytes, xf_f16 ? 1 : 0};
     if (!ops.empty()) {
       e = cudaMalloc((void**)&m->xfops_dev, ops.size() * sizeof(XfOp));
       if (e == cudaSuccess) e = cudaMemcpy(m->xfops_dev, ops.data(), ops.size() * sizeof(XfOp), cudaMemcpyHostToDevice);

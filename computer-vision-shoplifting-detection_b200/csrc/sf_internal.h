@@ -140,7 +140,7 @@ enum XfPost { XP_NONE = 0, XP_COPY_TO_AOP = 1, XP_LN_INPLACE_TO_AOP = 2, XP_LN_T
 enum XfSrc { XS_AOP = 0, XS_HOP = 1, XS_MEM = 2 };
 struct XfOp {
   int32_t type, init_mode, a_src, K, N, tmem_col, accumulate, epi, act, post, also_mem, h_col;
-  const uint16_t* w;        // [K/8][N][8] bf16 operand image (K-major B)
+  const uint16_t* w;        // [K/8][N][8] 16-bit operand image (K-major B; fp16 or bf16, XfProgram::f16)
   const float* bias;        // [N] zero padded
   const float* ln_g;
   const float* ln_b;
@@ -149,6 +149,7 @@ struct XfProgram {
   const XfOp* ops;          // device
   int n_ops, dp, dtp, supported;
   int max_w_bytes;          // largest weight image (ring slot size)
+  int f16;                  // the 16-bit operands (weight images, activations) are fp16 instead of bf16
 };
 }  // namespace sf
 
@@ -182,17 +183,37 @@ int launch_transformer_fp32(const sf_model* m, const float* tokens, int64_t B, i
 int launch_score(const sf_model* m, const float* tokens, const float* recon, int64_t B, int S,
                  int reduction, float* scores, cudaStream_t st);
 int token_len(const sf_model* m, int T);
+// windowing.cu: the index (flag / scan / compact) and gather halves of sf_window_normalize
+int64_t window_candidates(const sf_tracks* tr, const sf_window_params* p);
+int window_index(const sf_tracks* tr, const sf_window_params* p, int32_t* labels_dev, int32_t* window_track_dev,
+                 int32_t* window_start_dev, int64_t* n_windows_dev, void* workspace_dev, int64_t workspace_bytes, cudaStream_t st);
+int window_gather(const sf_tracks* tr, const sf_window_params* p, const int32_t* window_track_dev, const int32_t* window_start_dev,
+                  const int64_t* n_windows_dev, int64_t w_begin, int64_t w_cap, float* poses_dev, int32_t* frame_idx_dev,
+                  void* workspace_dev, cudaStream_t st);
+int window_device_of(const sf_tracks* tr, int* device);
 // bf16 tcgen05 tokenizer (returns SF_E_UNSUPPORTED for shapes it does not cover)
 int launch_tokenizer_bf16(const sf_model* m, const float* poses, int64_t B, int T, float* tokens, cudaStream_t st);
 bool tokenizer_bf16_supported(const sf_model* m, int T);
 // tokenizer v2 (multi-window tiles, see tok2.h); `tokenizer_bf16` dispatches to it when the shape is covered
-Tok2State* tok2_create(const Tokenizer& host_tok, int pool_tokens, bool upload);
+Tok2State* tok2_create(const Tokenizer& host_tok, int pool_tokens, bool upload, bool allow_f16);
+bool tokenizer2_f16(const sf_model* m);
 void tok2_destroy(Tok2State* s);
 bool tokenizer2_supported(const sf_model* m, int T);
 const char* tokenizer2_why(const sf_model* m, int T);
-int launch_tokenizer2(const sf_model* m, const float* poses, int64_t B, int T, float* tokens, cudaStream_t st);
+// Optional device-side batch size: the kernels process min(B, max(0, *n - off)) windows, so a caller that only knows an
+// upper bound on the host (windows compacted on the device) can launch without reading the count back.
+struct DevCount {
+  const int64_t* n = nullptr;
+  int64_t off = 0;
+};
+__device__ __forceinline__ int64_t dev_count_clamp(const DevCount& c, int64_t B) {
+  if (!c.n) return B;
+  const int64_t left = *c.n - c.off;
+  return left < 0 ? 0 : (left < B ? left : B);
+}
+int launch_tokenizer2(const sf_model* m, const float* poses, int64_t B, int T, float* tokens, cudaStream_t st, DevCount cnt = DevCount());
 // bf16 tcgen05 transformer + fused score
 int launch_transformer_bf16(const sf_model* m, const float* tokens, int64_t B, int S, int reduction, float* recon,
-                            float* scores, cudaStream_t st);
+                            float* scores, cudaStream_t st, DevCount cnt = DevCount());
 bool transformer_bf16_supported(const sf_model* m, int S);
 }  // namespace sf

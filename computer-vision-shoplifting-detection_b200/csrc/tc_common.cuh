@@ -40,8 +40,9 @@ __device__ __forceinline__ uint64_t desc_advance(uint64_t d, uint32_t bytes) { r
 // 32-bit instruction descriptor for kind::f16 with bf16 A/B and fp32 accumulate:
 //   [4,6) D format = 1 (f32)  [7,10) A format = 1 (bf16)  [10,13) B format = 1 (bf16)
 //   [15] A major (0 = K)  [16] B major (0 = K, 1 = MN)  [17,23) N >> 3   [24,29) M >> 4
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) |
+// A / B formats are independent: 0 = fp16, 1 = bf16 (activations are bf16 for range; constant operands may be fp16).
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool b_mn_major, bool a_f16 = false, bool b_f16 = false) {
+  return (1u << 4) | ((a_f16 ? 0u : 1u) << 7) | ((b_f16 ? 0u : 1u) << 10) | ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) |
          ((uint32_t)(M >> 4) << 24);
 }
 
@@ -155,6 +156,15 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+// fp16 operands: saturating (an activation beyond +-65504 becomes the largest finite half instead of inf, so no NaN
+// can come out of the next MMA; weights are range-checked when the model is packed)
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+template <bool F16>
+__device__ __forceinline__ uint32_t pack_op2(float lo, float hi) { return F16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi); }
 // element (row, col) of the planar-chunk layout, in bf16 elements from the buffer base
 __device__ __forceinline__ uint32_t pc_index(int row, int col, int plane_rows) {
   return (uint32_t)((col >> 3) * plane_rows + row) * 8u + (uint32_t)(col & 7);

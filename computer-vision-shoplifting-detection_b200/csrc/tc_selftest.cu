@@ -1,6 +1,8 @@
 // sf_selftest_umma: one 128 x N x K tcgen05 product on a single CTA, used by the GPU tests to pin the
 // descriptor encodings (no-swizzle K-major A, K-major / MN-major B, arbitrary 16-byte row shifts of A),
 // the TMEM lane/column mapping of tcgen05.ld and the commit/mbarrier handshake against numpy.
+#include <cuda_fp16.h>
+
 #include <vector>
 
 #include "sf_internal.h"
@@ -15,7 +17,7 @@ using namespace tc;
 // B: mode 0 -> (N, K) row-major (K-major operand); mode 1 -> (K, N) row-major (MN-major operand).
 __global__ void __launch_bounds__(128, 1)
 umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D, int N, int K,
-                     int a_rows, int shift, int mode) {
+                     int a_rows, int shift, int mode, int a_f16, int b_f16) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base;
@@ -32,11 +34,13 @@ umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, f
   }
   for (int i = threadIdx.x; i < a_rows * K; i += blockDim.x) {
     const int r = i / K, c = i % K;
-    sA[pc_index(r, c, a_rows)] = __float2bfloat16(A[i]);
+    if (a_f16) reinterpret_cast<__half*>(sA)[pc_index(r, c, a_rows)] = __float2half_rn(A[i]);
+    else sA[pc_index(r, c, a_rows)] = __float2bfloat16(A[i]);
   }
   for (int i = threadIdx.x; i < b_rows * b_cols; i += blockDim.x) {
     const int r = i / b_cols, c = i % b_cols;
-    sB[pc_index(r, c, b_rows)] = __float2bfloat16(B[i]);
+    if (b_f16) reinterpret_cast<__half*>(sB)[pc_index(r, c, b_rows)] = __float2half_rn(B[i]);
+    else sB[pc_index(r, c, b_rows)] = __float2bfloat16(B[i]);
   }
   fence_proxy_async();
   tc_fence_before();
@@ -45,7 +49,7 @@ umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, f
   const uint32_t tbase = tmem_base;
 
   if (threadIdx.x == 0) {
-    const uint32_t idesc = make_idesc(128, N, mode == 1);
+    const uint32_t idesc = make_idesc(128, N, mode == 1, a_f16 != 0, b_f16 != 0);
     const uint32_t a_plane = (uint32_t)a_rows * 16u, b_plane = (uint32_t)b_rows * 16u;
     const uint64_t adesc0 = make_desc(smem_u32(sA) + (uint32_t)shift * 16u, /*lbo=*/a_plane, /*sbo=*/128u);
     // K-major B: LBO = next K chunk (plane), SBO = next 8 N rows (128 B).
@@ -88,7 +92,11 @@ umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, f
 extern "C" int sf_selftest_umma(int32_t mode, int32_t N, int32_t K, int32_t shift, const float* a_host,
                                 const float* b_host, float* d_host) {
   using namespace sf;
-  SF_REQUIRE((mode == 0 || mode == 1) && N >= 16 && N <= 64 && N % 16 == 0 && K >= 16 && K % 16 == 0 && K <= 512 &&
+  // mode bits: 0 = B is MN-major, 2 and 3 (value 12) = both operands hold fp16 instead of bf16
+  const int a_f16 = (mode >> 2) & 1, b_f16 = (mode >> 3) & 1;
+  mode &= 1;
+  SF_REQUIRE(a_f16 == b_f16, SF_E_INVALID, "tcgen05 kind::f16 takes A and B in the same format (a mixed descriptor is an illegal instruction)");
+  SF_REQUIRE(N >= 16 && N <= 64 && N % 16 == 0 && K >= 16 && K % 16 == 0 && K <= 512 &&
                  shift >= 0 && shift <= 64 && a_host && b_host && d_host,
              SF_E_INVALID, "sf_selftest_umma: bad argument");
   int rc = sf_device_count();
@@ -102,7 +110,7 @@ extern "C" int sf_selftest_umma(int32_t mode, int32_t N, int32_t K, int32_t shif
   SF_CUDA_OK(cudaMemcpy(dB, b_host, sizeof(float) * N * K, cudaMemcpyHostToDevice));
   const size_t smem = ((size_t)a_rows * K + (size_t)N * K) * 2 + 256;
   SF_CUDA_OK(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  umma_selftest_kernel<<<1, 128, smem>>>(dA, dB, dD, N, K, a_rows, shift, mode);
+  umma_selftest_kernel<<<1, 128, smem>>>(dA, dB, dD, N, K, a_rows, shift, mode, a_f16, b_f16);
   SF_CUDA_OK(cudaGetLastError());
   SF_CUDA_OK(cudaDeviceSynchronize());
   SF_CUDA_OK(cudaMemcpy(d_host, dD, sizeof(float) * 128 * N, cudaMemcpyDeviceToHost));

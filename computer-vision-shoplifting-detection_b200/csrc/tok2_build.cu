@@ -18,6 +18,27 @@ inline uint16_t f2bf(float f) {       // round-to-nearest-even fp32 -> bf16
   u += 0x7fffu + ((u >> 16) & 1u);
   return (uint16_t)(u >> 16);
 }
+inline uint16_t f2h(float f) {        // round-to-nearest-even fp32 -> fp16 (finite inputs; overflow saturates to inf)
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  const uint16_t sign = (uint16_t)((u >> 16) & 0x8000u);
+  const int e = (int)((u >> 23) & 0xFF) - 127 + 15;
+  uint32_t m = u & 0x7FFFFFu;
+  if (e >= 31) return (uint16_t)(sign | 0x7C00u);
+  if (e <= 0) {                                    // subnormal half (or zero)
+    if (e < -10) return sign;
+    m |= 0x800000u;
+    const int sh = 14 - e;                         // 24-bit significand -> 10 bits at exponent 1
+    uint32_t h = m >> sh;
+    const uint32_t rem = m & ((1u << sh) - 1), half = 1u << (sh - 1);
+    if (rem > half || (rem == half && (h & 1u))) ++h;
+    return (uint16_t)(sign | h);
+  }
+  uint32_t h = ((uint32_t)e << 10) | (m >> 13);
+  const uint32_t rem = m & 0x1FFFu;
+  if (rem > 0x1000u || (rem == 0x1000u && (h & 1u))) ++h;     // a carry into the exponent is the right result
+  return (uint16_t)(sign | h);
+}
 inline int pad16(int x) { return (x + 15) & ~15; }
 inline uint32_t up128(size_t x) { return (uint32_t)((x + 127) & ~size_t(127)); }
 
@@ -32,17 +53,20 @@ struct Blob {
   float* f32(uint32_t off) { return reinterpret_cast<float*>(b.data() + off); }
 };
 
-// K-major image [K/8][nrows][8] of val(n, k)
+// K-major image [K/8][nrows][8] of val(n, k), bf16 (or fp16 when `half`)
 template <class F>
-void fill_kmajor(uint16_t* dst, int nrows, int K, F val) {
+void fill_kmajor(uint16_t* dst, int nrows, int K, F val, bool half = false) {
   for (int kc = 0; kc < K / 8; ++kc)
     for (int n = 0; n < nrows; ++n)
-      for (int e = 0; e < 8; ++e) dst[((size_t)kc * nrows + n) * 8 + e] = f2bf(val(n, kc * 8 + e));
+      for (int e = 0; e < 8; ++e) {
+        const float x = val(n, kc * 8 + e);
+        dst[((size_t)kc * nrows + n) * 8 + e] = half ? f2h(x) : f2bf(x);
+      }
 }
 
 }  // namespace
 
-void build_static(const Tokenizer& tok, int pool_tokens, Static* out) {
+void build_static(const Tokenizer& tok, int pool_tokens, bool allow_f16, Static* out) {
   Static& s = *out;
   s = Static();
   const int V = tok.V, nb = tok.n_blocks;
@@ -70,13 +94,30 @@ void build_static(const Tokenizer& tok, int pool_tokens, Static* out) {
   if (tok.blk[0].ell_width > 8) return fail("adjacency rows with more than 8 non-zeros");
   if (tok.blk[0].identity_res) return fail("identity residual in block 0");
 
+  // Operand format: fp16 (11 significant bits instead of bf16's 8 -- a weight's rounding error is a fixed perturbation
+  // of the model that does not average out, and the normalised adjacency is a handful of irrational values every
+  // activation passes through once per block) unless the caller wants bf16 or a folded weight leaves fp16's range.
+  // tcgen05 kind::f16 takes A and B in the SAME format (a mixed descriptor is an illegal instruction), so the activations
+  // the epilogues write are fp16 too, saturating at +-65504 (tc_common.cuh pack_f16x2).
+  s.f16 = allow_f16;
+  for (int b = 0; b < nb && s.f16; ++b) {
+    const TokBlock& tb = tok.blk[b];
+    auto fits = [&](const float* w, size_t n) {
+      for (size_t i = 0; i < n; ++i)
+        if (!(std::fabs(w[i]) < 32768.f)) return false;
+      return true;
+    };
+    s.f16 = fits(tb.tcn_w, (size_t)tb.cout * kTaps * tb.cout);
+    if (b > 0 && s.f16) s.f16 = fits(tb.gcn_w, (size_t)tb.cin * tb.cout) && (tb.identity_res || fits(tb.res_w, (size_t)tb.cin * tb.cout));
+  }
+
   // ---- const part ------------------------------------------------------------------------------------------
   // block-diagonal mix operand (A, K-major): (m, k) = A_hat[v_m][u_k] iff same window
   s.off_ablk = bl.alloc((size_t)kRows * kRows * 2);
   fill_kmajor(bl.bf(s.off_ablk), kRows, kRows, [&](int m, int k) -> float {
     if (m >= s.rows || k >= s.rows || m / V != k / V) return 0.f;
     return adj[1][(size_t)(m % V) * V + (k % V)];
-  });
+  }, s.f16);
   for (int b = 0; b < nb; ++b) {
     const TokBlock& tb = tok.blk[b];
     BlockStatic& o = s.blk[b];
@@ -114,12 +155,12 @@ void build_static(const Tokenizer& tok, int pool_tokens, Static* out) {
     const TokBlock& tb = tok.blk[b];
     BlockStatic& o = s.blk[b];
     o.off_gcn = bl.alloc((size_t)o.cin_p * o.cp * 2);
-    fill_kmajor(bl.bf(o.off_gcn), o.cp, o.cin_p, [&](int n, int k) -> float { return (n < tb.cout && k < tb.cin) ? tb.gcn_w[k * tb.cout + n] : 0.f; });
+    fill_kmajor(bl.bf(o.off_gcn), o.cp, o.cin_p, [&](int n, int k) -> float { return (n < tb.cout && k < tb.cin) ? tb.gcn_w[k * tb.cout + n] : 0.f; }, s.f16);
     o.off_res = bl.alloc((size_t)o.cin_p * o.cp * 2);
     fill_kmajor(bl.bf(o.off_res), o.cp, o.cin_p, [&](int n, int k) -> float {
       if (n >= tb.cout || k >= tb.cin) return 0.f;
       return tb.identity_res ? (n == k ? 1.f : 0.f) : tb.res_w[k * tb.cout + n];
-    });
+    }, s.f16);
     o.off_bias_g = bl.alloc((size_t)o.cp * 4);
     o.off_bias_o = bl.alloc((size_t)o.cp * 4);
     for (int n = 0; n < tb.cout; ++n) {
@@ -182,7 +223,7 @@ void build_static(const Tokenizer& tok, int pool_tokens, Static* out) {
     fill_kmajor(bl.bf(o.off_tcn), kTaps * o.cp, o.cp, [&](int n, int c) -> float {
       const int k = tap_at[n / o.cp], oc = n % o.cp;
       return (c < co && oc < co) ? tb.tcn_w[((size_t)c * kTaps + k) * co + oc] : 0.f;
-    });
+    }, s.f16);
   }
   s.blob.resize(up128(s.blob.size()), 0);
   s.ok = true;
@@ -331,11 +372,12 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
   // one MMA: A K-major at a_off (LBO = a_lbo), B at b_off: K-major (LBO = b_lbo, rows = N) or MN-major (activation
   // buffer used with K = rows: K step kk at +256 B, N chunks one plane apart)
   auto add_mma = [&](uint32_t a_off, uint32_t a_lbo, uint32_t b_off, uint32_t b_lbo, bool b_mn, int N, int dcol, bool acc) {
+    const bool a_f16 = st.f16, b_f16 = st.f16;          // instruction descriptor formats: 0 = F16, 1 = BF16
     Mma m;
     m.a_lo = ((a_off >> 4) & 0x3FFFu) | ((a_lbo >> 4) << 16);
     m.b_lo = ((b_off >> 4) & 0x3FFFu) | (((b_mn ? 128u : b_lbo) >> 4) << 16);
     m.d = (uint32_t)dcol | (acc ? 1u << 16 : 0u) | (b_mn ? 1u << 17 : 0u);
-    m.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
+    m.idesc = (1u << 4) | ((a_f16 ? 0u : 1u) << 7) | ((b_f16 ? 0u : 1u) << 10) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
     pr.mma.push_back(m);
     pr.groups.back().count++;
     Item& it = order.back();

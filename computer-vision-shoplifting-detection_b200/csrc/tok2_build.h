@@ -25,12 +25,13 @@ struct Static {
   uint32_t off_ablk = 0, off_zero = 0, off_ell = 0, off_hc = 0, off_scale = 0, off_shift = 0;
   uint32_t off_g0tab = 0, off_r0tab = 0;                            // block 0 (CUDA cores), fp32 [cp0 / 4][w_x[4], w_y[4], b[4]]
   int ell_width = 5;
+  bool f16 = true;                  // 16-bit operands (images and activations) are fp16, else bf16; see build_static
   uint32_t const_bytes = 0;
   std::vector<unsigned char> blob;  // const part [0, const_bytes) then the temporal-conv images
 };
 
 // `tok` must point at HOST copies of the folded fp32 weights.
-void build_static(const Tokenizer& tok, int pool_tokens, Static* out);
+void build_static(const Tokenizer& tok, int pool_tokens, bool allow_f16, Static* out);
 
 struct Program {
   bool ok = false;

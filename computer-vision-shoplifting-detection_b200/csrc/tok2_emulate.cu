@@ -62,6 +62,13 @@ struct Emu {
     memcpy(&h, &smem[byte], 2);
     return bf2f(h);
   }
+  float h_at(uint32_t byte) const {          // fp16 operand element
+    uint16_t h;
+    memcpy(&h, &smem[byte], 2);
+    const int e = (h >> 10) & 31, m = h & 0x3FF;
+    float v = e == 0 ? std::ldexp((float)m, -24) : (e == 31 ? (m ? NAN : INFINITY) : std::ldexp((float)(m | 0x400), e - 25));
+    return (h & 0x8000) ? -v : v;
+  }
   void mma(const Mma& m) {
     const uint32_t a_off = (m.a_lo & 0x3FFFu) << 4, a_lbo = ((m.a_lo >> 16) & 0x3FFFu) << 4;
     const uint32_t b_off = (m.b_lo & 0x3FFFu) << 4, b_lbo = ((m.b_lo >> 16) & 0x3FFFu) << 4;
@@ -69,13 +76,20 @@ struct Emu {
     const int N = (int)((m.idesc >> 17) & 0x3Fu) << 3;
     const int dcol = (int)(m.d & 0x1FFu);
     const bool acc = (m.d >> 16) & 1u;
+    const bool a_f16 = ((m.idesc >> 7) & 7u) == 0;     // instruction descriptor: A format 0 = F16, 1 = BF16
     std::vector<float> A(128 * 16), Bm((size_t)16 * N);
     for (int r = 0; r < 128; ++r)
-      for (int k = 0; k < 16; ++k) A[r * 16 + k] = bf_at(a_off + (uint32_t)(k / 8) * a_lbo + (uint32_t)r * 16 + (uint32_t)(k % 8) * 2);
+      for (int k = 0; k < 16; ++k) {
+        const uint32_t at = a_off + (uint32_t)(k / 8) * a_lbo + (uint32_t)r * 16 + (uint32_t)(k % 8) * 2;
+        A[r * 16 + k] = a_f16 ? h_at(at) : bf_at(at);
+      }
+    const bool b_f16 = ((m.idesc >> 10) & 7u) == 0;
     for (int k = 0; k < 16; ++k)
-      for (int n = 0; n < N; ++n)
-        Bm[(size_t)k * N + n] = mn ? bf_at(b_off + (uint32_t)(n / 8) * kPlane + (uint32_t)(k / 8) * b_lbo + (uint32_t)(k % 8) * 16 + (uint32_t)(n % 8) * 2)
-                                   : bf_at(b_off + (uint32_t)(k / 8) * b_lbo + (uint32_t)n * 16 + (uint32_t)(k % 8) * 2);
+      for (int n = 0; n < N; ++n) {
+        const uint32_t at = mn ? b_off + (uint32_t)(n / 8) * kPlane + (uint32_t)(k / 8) * b_lbo + (uint32_t)(k % 8) * 16 + (uint32_t)(n % 8) * 2
+                               : b_off + (uint32_t)(k / 8) * b_lbo + (uint32_t)n * 16 + (uint32_t)(k % 8) * 2;
+        Bm[(size_t)k * N + n] = b_f16 ? h_at(at) : bf_at(at);
+      }
     for (int r = 0; r < 128; ++r)
       for (int n = 0; n < N; ++n) {
         float s = 0.f;
@@ -99,9 +113,33 @@ struct Emu {
   }
 };
 
-uint16_t pack_one(float x, bool relu) {
+inline uint16_t f2h_sat(float f) {     // round-to-nearest-even fp32 -> fp16, saturating at +-65504 (cvt.rn.satfinite.f16x2.f32)
+  if (f != f) return 0x7FFF;
+  if (f > 65504.f) f = 65504.f;
+  if (f < -65504.f) f = -65504.f;
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  const uint16_t sign = (uint16_t)((u >> 16) & 0x8000u);
+  const int e = (int)((u >> 23) & 0xFF) - 127 + 15;
+  uint32_t m = u & 0x7FFFFFu;
+  if (e <= 0) {
+    if (e < -10) return sign;
+    m |= 0x800000u;
+    const int sh = 14 - e;
+    uint32_t h = m >> sh;
+    const uint32_t rem = m & ((1u << sh) - 1), half = 1u << (sh - 1);
+    if (rem > half || (rem == half && (h & 1u))) ++h;
+    return (uint16_t)(sign | h);
+  }
+  uint32_t h = ((uint32_t)e << 10) | (m >> 13);
+  const uint32_t rem = m & 0x1FFFu;
+  if (rem > 0x1000u || (rem == 0x1000u && (h & 1u))) ++h;
+  if ((h & 0x7FFFu) >= 0x7C00u) h = 0x7BFFu;
+  return (uint16_t)(sign | h);
+}
+uint16_t pack_one(float x, bool relu, bool f16) {
   if (relu && !(x > 0.f)) x = 0.f;
-  return f2bf(x);
+  return f16 ? f2h_sat(x) : f2bf(x);
 }
 
 }  // namespace
@@ -169,7 +207,7 @@ bool emulate(const Static& st, const Program& pr, const float* poses, int64_t B,
   };
   auto put16 = [&](uint32_t dst_off, int row, int cg, const float* a, bool relu) {
     for (int j = 0; j < 16; ++j) {
-      const uint16_t h = pack_one(a[j], relu);
+      const uint16_t h = pack_one(a[j], relu, st.f16);
       const int col = cg * 16 + j;
       memcpy(&E.smem[dst_off + (uint32_t)(col / 8) * kPlane + (uint32_t)row * 16 + (uint32_t)(col % 8) * 2], &h, 2);
     }
@@ -320,7 +358,7 @@ bool emulate(const Static& st, const Program& pr, const float* poses, int64_t B,
             }
             for (int o = 0; o < cp0; ++o) {
               const float y = std::fmaf(m[0], tabv(g0tab, 0, o), std::fmaf(m[1], tabv(g0tab, 1, o), tabv(g0tab, 2, o)));
-              const uint16_t hb = pack_one(y, true);
+              const uint16_t hb = pack_one(y, true, st.f16);
               const int col = (t - s.p0) * cp0 + o;
               memcpy(&E.smem[s.dst_off + (uint32_t)(col / 8) * kPlane + (uint32_t)row * 16 + (uint32_t)(col % 8) * 2], &hb, 2);
             }

@@ -36,15 +36,19 @@ __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_
 }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-// two fp32 -> packed bf16x2 (lo in the low half), optionally through ReLU
+// two fp32 -> packed 16-bit pair (lo in the low half), optionally through ReLU; F16: fp16 (saturating) instead of bf16
+template <bool F16>
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   uint32_t d;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  if (F16) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
   return d;
 }
+template <bool F16>
 __device__ __forceinline__ uint32_t pack2_relu(float lo, float hi) {
   uint32_t d;
-  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  if (F16) asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
   return d;
 }
 
@@ -95,15 +99,15 @@ __device__ __forceinline__ void issue_mma(uint32_t tmem, const Mma& m, uint32_t 
   } while (0)
 
 // 16 fp32 -> two 16-byte granules of bf16 (optionally through ReLU) at columns [16 cg, 16 cg + 16) of a planar-chunk buffer
-template <bool RELU>
+template <bool RELU, bool F16>
 __device__ __forceinline__ void store16(unsigned char* dst_row, int cg, const float* a) {
   uint4 o0, o1;
   if (RELU) {
-    o0 = make_uint4(pack2_relu(a[0], a[1]), pack2_relu(a[2], a[3]), pack2_relu(a[4], a[5]), pack2_relu(a[6], a[7]));
-    o1 = make_uint4(pack2_relu(a[8], a[9]), pack2_relu(a[10], a[11]), pack2_relu(a[12], a[13]), pack2_relu(a[14], a[15]));
+    o0 = make_uint4(pack2_relu<F16>(a[0], a[1]), pack2_relu<F16>(a[2], a[3]), pack2_relu<F16>(a[4], a[5]), pack2_relu<F16>(a[6], a[7]));
+    o1 = make_uint4(pack2_relu<F16>(a[8], a[9]), pack2_relu<F16>(a[10], a[11]), pack2_relu<F16>(a[12], a[13]), pack2_relu<F16>(a[14], a[15]));
   } else {
-    o0 = make_uint4(pack2(a[0], a[1]), pack2(a[2], a[3]), pack2(a[4], a[5]), pack2(a[6], a[7]));
-    o1 = make_uint4(pack2(a[8], a[9]), pack2(a[10], a[11]), pack2(a[12], a[13]), pack2(a[14], a[15]));
+    o0 = make_uint4(pack2<F16>(a[0], a[1]), pack2<F16>(a[2], a[3]), pack2<F16>(a[4], a[5]), pack2<F16>(a[6], a[7]));
+    o1 = make_uint4(pack2<F16>(a[8], a[9]), pack2<F16>(a[10], a[11]), pack2<F16>(a[12], a[13]), pack2<F16>(a[14], a[15]));
   }
   *reinterpret_cast<uint4*>(dst_row + (size_t)(2 * cg) * kPlane) = o0;
   *reinterpret_cast<uint4*>(dst_row + (size_t)(2 * cg + 1) * kPlane) = o1;
@@ -115,7 +119,7 @@ __device__ __forceinline__ void store16(unsigned char* dst_row, int cg, const fl
 //   g_o = relu(m_x * W[x][o] + m_y * W[y][o] + b[o])   (graph conv, gcae.py:124-154)  -> bf16 operand slot of the temporal conv
 // The weight table is read with broadcast shared-memory loads, the FMAs are packed fp32x2.  Rows beyond the tile's
 // windows produce finite values nobody reads.
-template <int KW>
+template <int KW, bool F16>
 __device__ __forceinline__ void g0_stage(const Plan& pl, const Stage& s, unsigned char* smem, int row, int half, int my_w, int my_v, int nw,
                                          int* pz) {
   const int t = s.p0 + half;
@@ -168,13 +172,14 @@ __device__ __forceinline__ void g0_stage(const Plan& pl, const Stage& s, unsigne
       y[2 * g + 1] = fma2(mx, make_float2(w[3 * g].z, w[3 * g].w), fma2(my, make_float2(w[3 * g + 1].z, w[3 * g + 1].w), make_float2(w[3 * g + 2].z, w[3 * g + 2].w)));
     }
     *reinterpret_cast<uint4*>(dst_row + (size_t)c8 * kPlane) =
-        make_uint4(pack2_relu(y[0].x, y[0].y), pack2_relu(y[1].x, y[1].y), pack2_relu(y[2].x, y[2].y), pack2_relu(y[3].x, y[3].y));
+        make_uint4(pack2_relu<F16>(y[0].x, y[0].y), pack2_relu<F16>(y[1].x, y[1].y), pack2_relu<F16>(y[2].x, y[2].y), pack2_relu<F16>(y[3].x, y[3].y));
   }
 }
 
 // Block 0 output for output times [p0, p1): x1 = relu(acc + BN-folded strided 1x1 residual conv of the raw poses + bias)
 // (gcae.py:237-259); the residual (2 input channels) is added in fp32 here instead of going through the tensor cores.
 // The two column halves of a team take alternate 16-channel groups.
+template <bool F16>
 __device__ __forceinline__ void xepi0_stage(const Plan& pl, const Stage& s, unsigned char* smem, uint32_t lane_base, int row, int half, int my_w,
                                             int my_v, int nw, int team) {
   const int V = pl.V, tv = pl.T0 * V, cp0 = pl.cp0;
@@ -228,20 +233,22 @@ __device__ __forceinline__ void xepi0_stage(const Plan& pl, const Stage& s, unsi
           const float2 r1 = fma2(u2, make_float2(rx.z, rx.w), fma2(w2, make_float2(ry.z, ry.w), make_float2(rb.z, rb.w)));
           a[4 * g + 0] += r0.x; a[4 * g + 1] += r0.y; a[4 * g + 2] += r1.x; a[4 * g + 3] += r1.y;
         }
-        store16<true>(dst_row, i * cgs + cg, a);
+        store16<true, F16>(dst_row, i * cgs + cg, a);
       }
     }
   }
 }
 
+template <bool F16>
 __global__ void __launch_bounds__(kThreads, 1)
-tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ poses, float* __restrict__ tokens, int64_t B) {
+tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ poses, float* __restrict__ tokens, int64_t B_max, const DevCount cnt) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint32_t tmem_base_s;
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + pl.off_bars);
   int* poison = reinterpret_cast<int*>(smem + pl.off_flags);                 // [2][64]
+  const int64_t B = dev_count_clamp(cnt, B_max);
   const int64_t n_tiles = (B + pl.WT - 1) / pl.WT;
 
   // ------------------------------------------------------------------ one-time setup
@@ -379,16 +386,16 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
                     a[b][4 * j + 0] = s0.x; a[b][4 * j + 1] = s0.y; a[b][4 * j + 2] = s1.x; a[b][4 * j + 3] = s1.y;
                   }
                 }
-                if (relu) store16<true>(dst, cg, a[b]);
-                else store16<false>(dst, cg, a[b]);
+                if (relu) store16<true, F16>(dst, cg, a[b]);
+                else store16<false, F16>(dst, cg, a[b]);
               }
             }
           }
         } else if (s.type == ST_G0) {
-          if (pl.ell_width <= 5) g0_stage<5>(pl, s, smem, row, half, my_w, my_v, nw, pz);
-          else g0_stage<8>(pl, s, smem, row, half, my_w, my_v, nw, pz);
+          if (pl.ell_width <= 5) g0_stage<5, F16>(pl, s, smem, row, half, my_w, my_v, nw, pz);
+          else g0_stage<8, F16>(pl, s, smem, row, half, my_w, my_v, nw, pz);
         } else if (s.type == ST_XEPI0) {
-          xepi0_stage(pl, s, smem, lane_base, row, half, my_w, my_v, nw, team);
+          xepi0_stage<F16>(pl, s, smem, lane_base, row, half, my_w, my_v, nw, team);
         } else {   // ST_TOKENS
           const float* bp = reinterpret_cast<const float*>(smem + s.bias_off);
           float* stg = reinterpret_cast<float*>(smem + pl.off_stage_tok);
@@ -449,9 +456,9 @@ struct Tok2State {
   Cache cache;
 };
 
-Tok2State* tok2_create(const Tokenizer& host_tok, int pool_tokens, bool upload) {
+Tok2State* tok2_create(const Tokenizer& host_tok, int pool_tokens, bool upload, bool allow_f16) {
   Tok2State* s = new Tok2State();
-  t2::build_static(host_tok, pool_tokens, &s->st);
+  t2::build_static(host_tok, pool_tokens, allow_f16, &s->st);
   if (s->st.ok && upload) {
     if (cudaMalloc((void**)&s->blob_dev, s->st.blob.size()) != cudaSuccess ||
         cudaMemcpy(s->blob_dev, s->st.blob.data(), s->st.blob.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -485,6 +492,8 @@ static Uploaded* tok2_program(const sf_model* m, int T) {
   return u;
 }
 
+bool tokenizer2_f16(const sf_model* m) { return m->tok2 && m->tok2->st.ok && m->tok2->st.f16; }
+
 bool tokenizer2_supported(const sf_model* m, int T) {
   if (getenv("SF_TOK2_OFF")) return false;
   Uploaded* u = tok2_program(m, T);
@@ -498,7 +507,7 @@ const char* tokenizer2_why(const sf_model* m, int T) {
   return u ? u->prog.why.c_str() : "";
 }
 
-int launch_tokenizer2(const sf_model* m, const float* poses, int64_t B, int T, float* tokens, cudaStream_t st) {
+int launch_tokenizer2(const sf_model* m, const float* poses, int64_t B, int T, float* tokens, cudaStream_t st, DevCount cnt) {
   if (B == 0) return SF_OK;
   Uploaded* u = tok2_program(m, T);
   SF_REQUIRE(u && u->prog.ok, SF_E_UNSUPPORTED, "tokenizer v2 does not cover this shape: %s", tokenizer2_why(m, T));
@@ -507,8 +516,13 @@ int launch_tokenizer2(const sf_model* m, const float* poses, int64_t B, int T, f
   const Plan& pl = u->prog.plan;
   const int64_t n_tiles = (B + pl.WT - 1) / pl.WT;
   const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)m->sm_count);
-  SF_CUDA_OK(cudaFuncSetAttribute(tokenizer2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
-  tokenizer2_kernel<<<grid, kThreads, pl.smem_bytes, st>>>(pl, poses, tokens, B);
+  if (m->tok2->st.f16) {
+    SF_CUDA_OK(cudaFuncSetAttribute(tokenizer2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
+    tokenizer2_kernel<true><<<grid, kThreads, pl.smem_bytes, st>>>(pl, poses, tokens, B, cnt);
+  } else {
+    SF_CUDA_OK(cudaFuncSetAttribute(tokenizer2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
+    tokenizer2_kernel<false><<<grid, kThreads, pl.smem_bytes, st>>>(pl, poses, tokens, B, cnt);
+  }
   SF_CUDA_OK(cudaGetLastError());
   return SF_OK;
 }

@@ -57,8 +57,9 @@ __device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, uint32_t lbo_byt
   return ((smem_addr >> 4) & 0x3FFFu) | ((lbo_bytes >> 4) << 16);
 }
 __device__ __forceinline__ uint64_t desc_join(uint32_t lo) { return ((uint64_t)((128u >> 4) | (1u << 14)) << 32) | lo; }
+template <bool F16>
 __device__ __forceinline__ uint4 pack8(const float* f) {
-  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+  return make_uint4(pack_op2<F16>(f[0], f[1]), pack_op2<F16>(f[2], f[3]), pack_op2<F16>(f[4], f[5]), pack_op2<F16>(f[6], f[7]));
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 
@@ -109,15 +110,18 @@ __device__ __forceinline__ void lds16(const float* p, float* out) {
 }
 
 // write one 16-column group of a row into a planar-chunk operand buffer
+template <bool F16>
 __device__ __forceinline__ void store_group(unsigned char* buf, int plane, int row, int g, const float* y) {
-  *reinterpret_cast<uint4*>(buf + (size_t)(2 * g) * plane + row * 16) = pack8(y);
-  *reinterpret_cast<uint4*>(buf + (size_t)(2 * g + 1) * plane + row * 16) = pack8(y + 8);
+  *reinterpret_cast<uint4*>(buf + (size_t)(2 * g) * plane + row * 16) = pack8<F16>(y);
+  *reinterpret_cast<uint4*>(buf + (size_t)(2 * g + 1) * plane + row * 16) = pack8<F16>(y + 8);
 }
 
+// F16: the 16-bit operands (activations written by the epilogues and the weight images) are fp16 instead of bf16
+template <bool F16>
 __global__ void __launch_bounds__(kThreads, 1)
 transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo, const __grid_constant__ Transformer xf,
-                        const float* __restrict__ tokens, int64_t B, int reduction, float* __restrict__ recon_out,
-                        float* __restrict__ scores) {
+                        const float* __restrict__ tokens, int64_t B_max, int reduction, float* __restrict__ recon_out,
+                        float* __restrict__ scores, const DevCount cnt) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t bar, wbar[2];            // MMA completion; TMA completion per weight-ring slot
   __shared__ uint32_t tmem_base_s;
@@ -167,6 +171,7 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
     ops = reinterpret_cast<const XfOp*>(smem + geo.off_ops);
   }
 
+  const int64_t B = dev_count_clamp(cnt, B_max);
   const int64_t n_tiles = (B + geo.win_per_tile - 1) / geo.win_per_tile;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t window = tile * geo.win_per_tile + lane_grp * geo.wpw + win_l;
@@ -219,7 +224,7 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
             if (g < ng) {
               float y[16];
               ldg16(tok_row, g * 16, dt, valid, y);
-              store_group(sAop, plane, row, g, y);
+              store_group<F16>(sAop, plane, row, g, y);
             }
           }
         } else {
@@ -249,7 +254,7 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
         if (warp == 0 && elect_one()) {            // uniform-datapath issue: descriptors live in uniform registers
           tc_fence_after();
           const unsigned char* a = op.a_src == XS_AOP ? sAop : (op.a_src == XS_HOP ? sHop : sMem);
-          const uint32_t idesc = make_idesc(128, op.N, false);
+          const uint32_t idesc = make_idesc(128, op.N, false, F16, F16);
           const uint32_t w_plane = (uint32_t)op.N * 16u;
           uint32_t alo = desc_lo(smem_u32(a), (uint32_t)plane);
           uint32_t blo = desc_lo(smem_u32(sW + slot * geo.slot_bytes), w_plane);
@@ -380,7 +385,7 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
                       for (int e = 0; e < 4; ++e) o4[e] = fmaf(sc[j], __shfl_sync(0xffffffffu, v4[e], rot[j]), o4[e]);
                     }
                   const int c = c0 + c16 + 4 * e4;
-                  uint2 pk = make_uint2(pack_bf16x2(o4[0] * inv, o4[1] * inv), pack_bf16x2(o4[2] * inv, o4[3] * inv));
+                  uint2 pk = make_uint2(pack_op2<F16>(o4[0] * inv, o4[1] * inv), pack_op2<F16>(o4[2] * inv, o4[3] * inv));
                   *reinterpret_cast<uint2*>(sHop + (size_t)(c >> 3) * plane + row * 16 + (c & 7) * 2) = pk;
                 }
             }
@@ -400,7 +405,7 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
                 const float v = acc[q] + bs[q];
                 acc[q] = op.act == 2 ? gelu_erf(v) : fmaxf(v, 0.f);
               }
-              store_group(sHop, plane, row, g, acc);
+              store_group<F16>(sHop, plane, row, g, acc);
             }
           }
         } else if (op.epi == XE_STREAM_ADD || op.epi == XE_STREAM_SET_PE) {
@@ -487,7 +492,7 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
 #pragma unroll
         for (int i = 0; i < kSlots; ++i) {
           const int g = kParts * i + part;
-          if (g < ng) store_group(sAop, plane, row, g, st[i]);
+          if (g < ng) store_group<F16>(sAop, plane, row, g, st[i]);
         }
       } else if (post >= XP_LN_INPLACE_TO_AOP) {
         const int ng = dp >> 4;
@@ -538,8 +543,8 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
 #pragma unroll
               for (int q = 0; q < 16; ++q) st[i][q] = y[q];
             }
-            if (post == XP_LN_INPLACE_TO_AOP || post == XP_LN_TO_AOP) store_group(sAop, plane, row, g, y);
-            if (post == XP_LN_TO_MEM || op.also_mem) store_group(sMem, plane, row, g, y);
+            if (post == XP_LN_INPLACE_TO_AOP || post == XP_LN_TO_AOP) store_group<F16>(sAop, plane, row, g, y);
+            if (post == XP_LN_TO_MEM || op.also_mem) store_group<F16>(sMem, plane, row, g, y);
             if (post == XP_LN_SCORE) {
               float target[16];
               ldg16(tok_row, g * 16, dt, valid, target);
@@ -621,7 +626,7 @@ bool transformer_bf16_supported(const sf_model* m, int S) {
 }
 
 int launch_transformer_bf16(const sf_model* m, const float* tokens, int64_t B, int S, int reduction, float* recon,
-                            float* scores, cudaStream_t st) {
+                            float* scores, cudaStream_t st, DevCount cnt) {
   if (B == 0) return SF_OK;
   XfGeo g;
   SF_REQUIRE(make_geo(m, S, &g), SF_E_UNSUPPORTED,
@@ -630,10 +635,15 @@ int launch_transformer_bf16(const sf_model* m, const float* tokens, int64_t B, i
              SF_E_INVALID, "reduction %d not available for variant %d", reduction, m->xf.variant);
   SF_REQUIRE(((uintptr_t)tokens & 15) == 0 && ((uintptr_t)recon & 15) == 0, SF_E_INVALID,
              "token / reconstruction buffers must be 16-byte aligned");
-  SF_CUDA_OK(cudaFuncSetAttribute(transformer_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
   const int64_t n_tiles = (B + g.win_per_tile - 1) / g.win_per_tile;
   const int grid = (int)std::min<int64_t>(n_tiles, m->sm_count);
-  transformer_bf16_kernel<<<grid, kThreads, g.smem_bytes, st>>>(m->xfprog, g, m->xf, tokens, B, reduction, recon, scores);
+  if (m->xfprog.f16) {
+    SF_CUDA_OK(cudaFuncSetAttribute(transformer_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+    transformer_bf16_kernel<true><<<grid, kThreads, g.smem_bytes, st>>>(m->xfprog, g, m->xf, tokens, B, reduction, recon, scores, cnt);
+  } else {
+    SF_CUDA_OK(cudaFuncSetAttribute(transformer_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+    transformer_bf16_kernel<false><<<grid, kThreads, g.smem_bytes, st>>>(m->xfprog, g, m->xf, tokens, B, reduction, recon, scores, cnt);
+  }
   SF_CUDA_OK(cudaGetLastError());
   return SF_OK;
 }

@@ -39,6 +39,7 @@ struct WinCtx {
   const int64_t* gt_off;
   const uint8_t* gt;
   int n_tracks, K, T, stride, max_gap, V, normalize;
+  int KC;                       // floats per source keypoint: 3 (x, y, conf as PoseLift stores them) or 2 (x, y)
   int add_neck, conf;           // synthetic 18th keypoint (variant 2); third output plane = raw confidence (variant 1 include_confidence)
   int64_t n_cand;
 };
@@ -171,35 +172,38 @@ k_compact(const WinCtx cx, const uint8_t* __restrict__ flag, const uint8_t* __re
 constexpr int kGatherWarps = 8;
 
 // shared-memory floats per warp: staged raw keypoints (+ phase slack), neck, output slab
-__host__ __device__ inline int gather_raw_floats(int T, int K) { return (T * K * 3 + 7) & ~3; }
+__host__ __device__ inline int gather_raw_floats(int T, int K, int KC) { return (T * K * KC + 7) & ~3; }
 __host__ __device__ inline int gather_neck_floats(int T) { return (2 * T + 3) & ~3; }
 __host__ __device__ inline int gather_out_floats(int T, int V, int C) { return (C * T * V + 3) & ~3; }
-inline int gather_per_warp(int T, int K, int V, int C) { return gather_raw_floats(T, K) + gather_neck_floats(T) + gather_out_floats(T, V, C); }
+inline int gather_per_warp(int T, int K, int KC, int V, int C) { return gather_raw_floats(T, K, KC) + gather_neck_floats(T) + gather_out_floats(T, V, C); }
 
-// One warp per window.
+// One warp per window.  Windows [w_begin, min(count, w_begin + w_cap)) are written to poses[0 .. ) (a pass of a larger
+// sweep gathers its own range into a pass-sized buffer).
 __global__ void __launch_bounds__(kGatherWarps * 32)
 k_gather(const WinCtx cx, const int64_t* __restrict__ n_windows, int64_t n_fixed, const int32_t* __restrict__ win_track,
-         const int32_t* __restrict__ win_start, float* __restrict__ poses, int32_t* __restrict__ frame_idx, int per_warp) {
+         const int32_t* __restrict__ win_start, float* __restrict__ poses, int32_t* __restrict__ frame_idx, int per_warp,
+         int64_t w_begin, int64_t w_cap) {
   extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* slab = smem + (size_t)warp * per_warp;
-  const int T = cx.T, K = cx.K, V = cx.V;
-  const int n_raw = T * K * 3;
+  const int T = cx.T, K = cx.K, V = cx.V, KC = cx.KC;
+  const int n_raw = T * K * KC;
   const int C = cx.conf ? 3 : 2;
-  float* neck = slab + gather_raw_floats(T, K);     // [T][2], only used with add_neck
+  float* neck = slab + gather_raw_floats(T, K, KC); // [T][2], only used with add_neck
   float* outs = neck + gather_neck_floats(T);       // [C][T][V]: the window in output order
   const bool add_neck = cx.add_neck != 0;
   const int Vsrc = add_neck ? min(V - 1, K) : min(V, K);      // keypoints taken from the detection itself
   const int n_el = T * V;
   // this lane's walk over (t, v): element i = lane, lane + 32, ...  (one division per kernel, none per element)
   const int t_first = lane / V, v_first = lane - t_first * V, dt = 32 / V, dv = 32 - dt * V;
-  const int64_t nw = n_windows ? *n_windows : n_fixed;      // pre-cut windows: the count is known on the host
+  int64_t nw = n_windows ? *n_windows : n_fixed;            // pre-cut windows: the count is known on the host
+  if (nw > w_begin + w_cap) nw = w_begin + w_cap;
   const int64_t warps_total = (int64_t)gridDim.x * kGatherWarps;
-  for (int64_t w = (int64_t)blockIdx.x * kGatherWarps + warp; w < nw; w += warps_total) {
+  for (int64_t w = w_begin + (int64_t)blockIdx.x * kGatherWarps + warp; w < nw; w += warps_total) {
     // pre-cut mode (win_track == nullptr): window w is frames [w*T, (w+1)*T)
     const int64_t f0 = win_track ? __ldg(cx.track_off + __ldg(win_track + w)) + __ldg(win_start + w) : w * (int64_t)cx.T;
     // ---- stage the contiguous chunk: scalar head, 16-byte body, scalar tail
-    const float* src = cx.kp + (size_t)f0 * K * 3;
+    const float* src = cx.kp + (size_t)f0 * K * KC;
     const int mis = (int)((reinterpret_cast<uintptr_t>(src) >> 2) & 3);
     float* raw = slab + mis;                        // same 16-byte phase in smem as in HBM
     const int head = mis ? min(4 - mis, n_raw) : 0;
@@ -210,13 +214,13 @@ k_gather(const WinCtx cx, const int64_t* __restrict__ n_windows, int64_t n_fixed
     for (int i = lane; i < body4; i += 32) d4[i] = __ldg(s4 + i);
     for (int i = head + 4 * body4 + lane; i < n_raw; i += 32) raw[i] = __ldg(src + i);
     if (frame_idx && cx.frame_no)
-      for (int t = lane; t < T; t += 32) frame_idx[w * T + t] = __ldg(cx.frame_no + f0 + t);
+      for (int t = lane; t < T; t += 32) frame_idx[(w - w_begin) * T + t] = __ldg(cx.frame_no + f0 + t);
     __syncwarp();
     if (add_neck) {
       // add_neck_keypoint: midpoint of shoulders 5/6; np.allclose(.,0) == |x|,|y| <= 1e-8
       for (int t = lane; t < T; t += 32) {
-        const float lx = raw[(t * K + 5) * 3], ly = raw[(t * K + 5) * 3 + 1];
-        const float rx = raw[(t * K + 6) * 3], ry = raw[(t * K + 6) * 3 + 1];
+        const float lx = raw[(t * K + 5) * KC], ly = raw[(t * K + 5) * KC + 1];
+        const float rx = raw[(t * K + 6) * KC], ry = raw[(t * K + 6) * KC + 1];
         const bool l0 = fabsf(lx) <= 1e-8f && fabsf(ly) <= 1e-8f;
         const bool r0 = fabsf(rx) <= 1e-8f && fabsf(ry) <= 1e-8f;
         float nx = (lx + rx) * 0.5f, ny = (ly + ry) * 0.5f;
@@ -230,7 +234,7 @@ k_gather(const WinCtx cx, const int64_t* __restrict__ n_windows, int64_t n_fixed
     }
     auto load_xy = [&](int t, int v, float& x, float& y) {
       if (v < Vsrc) {
-        const float* p = raw + (t * K + v) * 3;
+        const float* p = raw + (t * K + v) * KC;
         x = p[0];
         y = p[1];
       } else if (add_neck && v == V - 1) {
@@ -287,13 +291,13 @@ k_gather(const WinCtx cx, const int64_t* __restrict__ n_windows, int64_t n_fixed
       }
       outs[i] = x;
       outs[n_el + i] = y;
-      if (C == 3) outs[2 * n_el + i] = v < Vsrc ? raw[(t * K + v) * 3 + 2] : 0.f;
+      if (C == 3) outs[2 * n_el + i] = v < Vsrc ? raw[(t * K + v) * KC + 2] : 0.f;
       v += dv; t += dt;
       if (v >= V) { v -= V; ++t; }
     }
     __syncwarp();
     // ---- slab -> HBM
-    float* dst = poses + (size_t)w * C * n_el;
+    float* dst = poses + (size_t)(w - w_begin) * C * n_el;
     const int n_out = C * n_el;
     if (((n_out & 3) == 0)) {
       const float4* o4 = reinterpret_cast<const float4*>(outs);
@@ -366,6 +370,8 @@ int check(const sf_tracks* tr, const sf_window_params* p) {
              p->num_keypoints, kMaxV);
   SF_REQUIRE(!p->add_neck || (p->num_keypoints >= 8 && tr->kp_per_frame >= 7), SF_E_INVALID,
              "neck synthesis needs the shoulder keypoints 5 and 6 in the source and a slot for the neck");
+  SF_REQUIRE(tr->kp_channels == 0 || tr->kp_channels == 2 || tr->kp_channels == 3, SF_E_INVALID, "windowing: kp_channels must be 2 or 3");
+  SF_REQUIRE(!p->include_confidence || tr->kp_channels != 2, SF_E_INVALID, "include_confidence needs (x, y, conf) source keypoints");
   return SF_OK;
 }
 
@@ -384,46 +390,14 @@ extern "C" int64_t sf_window_workspace_bytes(const sf_tracks* tr, const sf_windo
   return (int64_t)layout(tr, p).total;
 }
 
-extern "C" int sf_window_normalize(const sf_tracks* tr, const sf_window_params* p, float* poses_dev, int32_t* labels_dev,
-                                   int32_t* window_track_dev, int32_t* window_start_dev, int32_t* frame_idx_dev,
-                                   int64_t* n_windows_dev, int64_t* n_windows_host, void* workspace_dev,
-                                   int64_t workspace_bytes, void* stream) {
-  int rc = check(tr, p);
-  if (rc != SF_OK) return rc;
-  SF_REQUIRE(n_windows_dev, SF_E_INVALID, "windowing: n_windows_dev is required");
-  cudaStream_t st = (cudaStream_t)stream;
-  // run on the device that owns the track buffers, whatever the caller's current device is
-  DeviceGuard guard;
-  {
-    cudaPointerAttributes attr;
-    SF_CUDA_OK(cudaPointerGetAttributes(&attr, tr->kp_dev));
-    SF_REQUIRE(attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged, SF_E_INVALID, "windowing: kp_dev is not a device pointer");
-    SF_CUDA_OK(guard.enter(attr.device));
-  }
-  const WsLayout L = layout(tr, p);
-  SF_REQUIRE(workspace_dev && workspace_bytes >= (int64_t)L.total, SF_E_INVALID,
-             "windowing: workspace of %lld bytes needed, got %lld", (long long)L.total, (long long)workspace_bytes);
-  if (L.n_cand == 0) {
-    SF_CUDA_OK(cudaMemsetAsync(n_windows_dev, 0, sizeof(int64_t), st));
-    if (n_windows_host) {
-      SF_CUDA_OK(cudaStreamSynchronize(st));
-      *n_windows_host = 0;
-    }
-    return SF_OK;
-  }
-  SF_REQUIRE(poses_dev && labels_dev && window_track_dev && window_start_dev, SF_E_INVALID, "windowing: null output");
-  char* ws = (char*)workspace_dev;
-  std::vector<int64_t> cand_off;
-  candidates(tr, p, &cand_off);
-  SF_CUDA_OK(cudaMemcpyAsync(ws + L.track_off, tr->track_offsets_host, sizeof(int64_t) * (tr->n_tracks + 1), cudaMemcpyHostToDevice, st));
-  SF_CUDA_OK(cudaMemcpyAsync(ws + L.cand_off, cand_off.data(), sizeof(int64_t) * (tr->n_tracks + 1), cudaMemcpyHostToDevice, st));
+// ---- the two halves of the pipeline, shared by sf_window_normalize and sf_score_from_tracks (api.cu)
+namespace sf {
+
+int64_t window_candidates(const sf_tracks* tr, const sf_window_params* p) { return candidates(tr, p, nullptr); }
+
+static void fill_ctx(const sf_tracks* tr, const sf_window_params* p, const WsLayout& L, char* ws, WinCtx* out) {
+  WinCtx& cx = *out;
   const bool has_gt = tr->gt_dev && tr->gt_offsets_host && tr->track_video_host && tr->n_videos > 0;
-  if (has_gt) {
-    SF_CUDA_OK(cudaMemcpyAsync(ws + L.track_video, tr->track_video_host, sizeof(int32_t) * tr->n_tracks, cudaMemcpyHostToDevice, st));
-    SF_CUDA_OK(cudaMemcpyAsync(ws + L.gt_off, tr->gt_offsets_host, sizeof(int64_t) * (tr->n_videos + 1), cudaMemcpyHostToDevice, st));
-  }
-  // cand_off lives on this stack frame: the pageable copy above is staged before the call returns
-  WinCtx cx;
   cx.kp = tr->kp_dev;
   cx.frame_no = tr->frame_no_dev;
   cx.track_off = (const int64_t*)(ws + L.track_off);
@@ -433,6 +407,7 @@ extern "C" int sf_window_normalize(const sf_tracks* tr, const sf_window_params* 
   cx.gt = has_gt ? tr->gt_dev : nullptr;
   cx.n_tracks = tr->n_tracks;
   cx.K = tr->kp_per_frame;
+  cx.KC = tr->kp_channels == 2 ? 2 : 3;
   cx.T = p->seq_len;
   cx.stride = p->stride;
   cx.max_gap = p->max_gap;
@@ -441,6 +416,36 @@ extern "C" int sf_window_normalize(const sf_tracks* tr, const sf_window_params* 
   cx.add_neck = p->add_neck ? 1 : 0;
   cx.conf = p->include_confidence ? 1 : 0;
   cx.n_cand = L.n_cand;
+}
+
+// K_flag / K_scan / K_compact: which windows exist, in the reference's order, with their labels.  The per-track tables
+// are uploaded into the workspace (they stay there for window_gather).  No synchronisation.
+int window_index(const sf_tracks* tr, const sf_window_params* p, int32_t* labels_dev, int32_t* window_track_dev,
+                 int32_t* window_start_dev, int64_t* n_windows_dev, void* workspace_dev, int64_t workspace_bytes, cudaStream_t st) {
+  int rc = check(tr, p);
+  if (rc != SF_OK) return rc;
+  SF_REQUIRE(n_windows_dev, SF_E_INVALID, "windowing: n_windows_dev is required");
+  const WsLayout L = layout(tr, p);
+  SF_REQUIRE(workspace_dev && workspace_bytes >= (int64_t)L.total, SF_E_INVALID,
+             "windowing: workspace of %lld bytes needed, got %lld", (long long)L.total, (long long)workspace_bytes);
+  if (L.n_cand == 0) {
+    SF_CUDA_OK(cudaMemsetAsync(n_windows_dev, 0, sizeof(int64_t), st));
+    return SF_OK;
+  }
+  SF_REQUIRE(labels_dev && window_track_dev && window_start_dev, SF_E_INVALID, "windowing: null output");
+  char* ws = (char*)workspace_dev;
+  std::vector<int64_t> cand_off;
+  candidates(tr, p, &cand_off);
+  SF_CUDA_OK(cudaMemcpyAsync(ws + L.track_off, tr->track_offsets_host, sizeof(int64_t) * (tr->n_tracks + 1), cudaMemcpyHostToDevice, st));
+  // cand_off lives on this stack frame: a pageable source is staged before the call returns
+  SF_CUDA_OK(cudaMemcpyAsync(ws + L.cand_off, cand_off.data(), sizeof(int64_t) * (tr->n_tracks + 1), cudaMemcpyHostToDevice, st));
+  const bool has_gt = tr->gt_dev && tr->gt_offsets_host && tr->track_video_host && tr->n_videos > 0;
+  if (has_gt) {
+    SF_CUDA_OK(cudaMemcpyAsync(ws + L.track_video, tr->track_video_host, sizeof(int32_t) * tr->n_tracks, cudaMemcpyHostToDevice, st));
+    SF_CUDA_OK(cudaMemcpyAsync(ws + L.gt_off, tr->gt_offsets_host, sizeof(int64_t) * (tr->n_videos + 1), cudaMemcpyHostToDevice, st));
+  }
+  WinCtx cx;
+  fill_ctx(tr, p, L, ws, &cx);
   uint8_t* flag = (uint8_t*)(ws + L.flag);
   uint8_t* label = (uint8_t*)(ws + L.label);
   int32_t* block_sum = (int32_t*)(ws + L.block_sum);
@@ -448,14 +453,70 @@ extern "C" int sf_window_normalize(const sf_tracks* tr, const sf_window_params* 
   k_flag<<<L.n_blocks, kScanBlock, 0, st>>>(cx, flag, label, block_sum);
   k_scan<<<1, 1024, 0, st>>>(block_sum, block_off, L.n_blocks, n_windows_dev);
   k_compact<<<L.n_blocks, kScanBlock, 0, st>>>(cx, flag, label, block_off, labels_dev, window_track_dev, window_start_dev);
-  const int per_warp = gather_per_warp(cx.T, cx.K, cx.V, cx.conf ? 3 : 2);
+  SF_CUDA_OK(cudaGetLastError());
+  return SF_OK;
+}
+
+// K_gather for windows [w_begin, min(*n_windows_dev, w_begin + w_cap)) -> poses_dev[0 ..) (and frame_idx_dev[0 ..)).
+// `workspace_dev` must be the one window_index filled for the same tracks / parameters.
+int window_gather(const sf_tracks* tr, const sf_window_params* p, const int32_t* window_track_dev, const int32_t* window_start_dev,
+                  const int64_t* n_windows_dev, int64_t w_begin, int64_t w_cap, float* poses_dev, int32_t* frame_idx_dev,
+                  void* workspace_dev, cudaStream_t st) {
+  if (w_cap <= 0) return SF_OK;
+  const WsLayout L = layout(tr, p);
+  WinCtx cx;
+  fill_ctx(tr, p, L, (char*)workspace_dev, &cx);
+  const int per_warp = gather_per_warp(cx.T, cx.K, cx.KC, cx.V, cx.conf ? 3 : 2);
   const size_t smem = (size_t)per_warp * kGatherWarps * sizeof(float);
   int grid = 0;
-  rc = gather_launch_config(smem, (L.n_cand + kGatherWarps - 1) / kGatherWarps, &grid);
+  int rc = gather_launch_config(smem, (w_cap + kGatherWarps - 1) / kGatherWarps, &grid);
   if (rc != SF_OK) return rc;
-  k_gather<<<grid, kGatherWarps * 32, smem, st>>>(cx, n_windows_dev, 0, window_track_dev, window_start_dev, poses_dev,
-                                                  frame_idx_dev, per_warp);
+  k_gather<<<grid, kGatherWarps * 32, smem, st>>>(cx, n_windows_dev, 0, window_track_dev, window_start_dev, poses_dev, frame_idx_dev,
+                                                  per_warp, w_begin, w_cap);
   SF_CUDA_OK(cudaGetLastError());
+  return SF_OK;
+}
+
+int window_device_of(const sf_tracks* tr, int* device) {
+  cudaPointerAttributes attr;
+  SF_CUDA_OK(cudaPointerGetAttributes(&attr, tr->kp_dev));
+  SF_REQUIRE(attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged, SF_E_INVALID, "windowing: kp_dev is not a device pointer");
+  *device = attr.device;
+  return SF_OK;
+}
+
+}  // namespace sf
+
+extern "C" int sf_window_normalize(const sf_tracks* tr, const sf_window_params* p, float* poses_dev, int32_t* labels_dev,
+                                   int32_t* window_track_dev, int32_t* window_start_dev, int32_t* frame_idx_dev,
+                                   int64_t* n_windows_dev, int64_t* n_windows_host, void* workspace_dev,
+                                   int64_t workspace_bytes, void* stream) {
+  int rc = check(tr, p);
+  if (rc != SF_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  SF_REQUIRE(n_windows_dev, SF_E_INVALID, "windowing: n_windows_dev is required");
+  // run on the device that owns the track buffers, whatever the caller's current device is (no track long enough for a
+  // window: there may be no keypoint buffer at all -- the count's device then)
+  DeviceGuard guard;
+  int dev = 0;
+  if (candidates(tr, p, nullptr) == 0) {
+    cudaPointerAttributes attr;
+    SF_CUDA_OK(cudaPointerGetAttributes(&attr, n_windows_dev));
+    SF_REQUIRE(attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged, SF_E_INVALID, "windowing: n_windows_dev is not a device pointer");
+    dev = attr.device;
+  } else {
+    rc = window_device_of(tr, &dev);
+    if (rc != SF_OK) return rc;
+  }
+  SF_CUDA_OK(guard.enter(dev));
+  rc = window_index(tr, p, labels_dev, window_track_dev, window_start_dev, n_windows_dev, workspace_dev, workspace_bytes, st);
+  if (rc != SF_OK) return rc;
+  const int64_t n_cand = candidates(tr, p, nullptr);
+  if (n_cand > 0) {
+    SF_REQUIRE(poses_dev, SF_E_INVALID, "windowing: null output");
+    rc = window_gather(tr, p, window_track_dev, window_start_dev, n_windows_dev, 0, n_cand, poses_dev, frame_idx_dev, workspace_dev, st);
+    if (rc != SF_OK) return rc;
+  }
   if (n_windows_host) {
     SF_CUDA_OK(cudaMemcpyAsync(n_windows_host, n_windows_dev, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     SF_CUDA_OK(cudaStreamSynchronize(st));
@@ -482,17 +543,18 @@ extern "C" int sf_normalize_windows(const float* raw_dev, int64_t B, int32_t T, 
   WinCtx cx{};
   cx.kp = raw_dev;
   cx.K = K;
+  cx.KC = 3;
   cx.T = T;
   cx.V = V;
   cx.normalize = normalize;
   cx.add_neck = V == 18 ? 1 : 0;          // this entry point keeps the variant-2 convention: 18 keypoints = 17 + synthetic neck
   cx.conf = 0;
-  const int per_warp = gather_per_warp(T, K, V, 2);
+  const int per_warp = gather_per_warp(T, K, 3, V, 2);
   const size_t smem = (size_t)per_warp * kGatherWarps * sizeof(float);
   int grid = 0;
   int rc = gather_launch_config(smem, (B + kGatherWarps - 1) / kGatherWarps, &grid);
   if (rc != SF_OK) return rc;
-  k_gather<<<grid, kGatherWarps * 32, smem, (cudaStream_t)stream>>>(cx, nullptr, B, nullptr, nullptr, poses_dev, nullptr, per_warp);
+  k_gather<<<grid, kGatherWarps * 32, smem, (cudaStream_t)stream>>>(cx, nullptr, B, nullptr, nullptr, poses_dev, nullptr, per_warp, 0, B);
   SF_CUDA_OK(cudaGetLastError());
   return SF_OK;
 }

@@ -17,6 +17,7 @@ from shopformer_b200.engine import EngineConfig
 from shopformer_b200.facade import EngineCacheMixin, LazyOutput
 from shopformer_b200.modules import adopt, wants_native
 from shopformer_b200.native import SF_VARIANT_SHOPFORMER
+from shopformer_b200.ops import model_handle
 
 from .gcae import GCAE, GCAEEncoder  # noqa: F401
 from .transformer import PositionalEncoding, ShopformerTransformer
@@ -74,15 +75,15 @@ class Shopformer(nn.Module, EngineCacheMixin):
 
     def compute_normality_score(self, tokens: torch.Tensor, reconstructed: torch.Tensor) -> torch.Tensor:
         if wants_native(self, tokens):
-            return self._sf_engine().normality_score(tokens, reconstructed, "mean")
+            return torch.ops.shopformer_b200.normality_score(tokens, reconstructed, model_handle(self._sf_engine()), "mean")
         target = tokens + self.pos_encoder.pe[:, :tokens.size(1), :].expand(tokens.size(0), -1, -1)
         return F.mse_loss(reconstructed, target, reduction="none").mean(dim=[1, 2])
 
     def forward(self, poses: torch.Tensor, return_tokens: bool = False) -> Dict[str, torch.Tensor]:
         if wants_native(self, poses):
             x = self.gcae.encoder._as_bctv(poses)
-            score, tokens, recon = self._sf_engine().score_windows(x, precision=self._sf_resolve_precision(),
-                                                                   return_tokens=True, return_recon=True)
+            score, tokens, recon = torch.ops.shopformer_b200.score_fused_full(x, model_handle(self._sf_engine()),
+                                                                              self._sf_resolve_precision())
             out = LazyOutput({"normality_score": score, "reconstructed_tokens": recon},
                              {"gcae_reconstructed": lambda: self._decode_eval(tokens)})
             if return_tokens:

@@ -9,6 +9,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from shopformer_b200.ops import model_handle
 from shopformer_b200.modules import (PostLNDecoderLayer as TransformerDecoderLayer,
                                      PostLNEncoderLayer as TransformerEncoderLayer, _Owned, sinusoid_table,
                                      wants_native)
@@ -63,7 +64,7 @@ class ShopformerTransformer(nn.Module, _Owned):
         if wants_native(self, tokens):
             eng = self._engine()
             if eng is not None:
-                return eng.reconstruct_tokens(tokens, precision=self._precision())
+                return torch.ops.shopformer_b200.reconstruct_tokens(tokens, model_handle(eng), self._precision())
         memory = self.encode(tokens)
         start = torch.zeros(tokens.size(0), 1, self.d_model, device=tokens.device)
         shifted = torch.cat([start, tokens[:, :-1, :]], dim=1)

@@ -16,6 +16,7 @@ from shopformer_b200.engine import EngineConfig
 from shopformer_b200.facade import EngineCacheMixin
 from shopformer_b200.modules import adopt, composite_eval_allowed
 from shopformer_b200.native import SF_VARIANT_SHOPFORMER_2
+from shopformer_b200.ops import model_handle
 
 from .gcae import GCAE, GCAEEncoder  # noqa: F401
 from .transformer import ShopformerTransformer, build_transformer  # noqa: F401
@@ -89,7 +90,7 @@ class Shopformer(nn.Module, EngineCacheMixin):
         with torch.no_grad():
             if poses.is_cuda:
                 x = self.gcae.encoder._as_bctv(poses)
-                return self._sf_engine().score_windows(x, reduction=reduction, precision=self._sf_resolve_precision())
+                return torch.ops.shopformer_b200.score_fused(x, model_handle(self._sf_engine()), reduction, self._sf_resolve_precision())
             if not composite_eval_allowed():
                 raise RuntimeError("shopformer_b200: compute_anomaly_score runs on CUDA (sm_100a) only; "
                                    "there is no CPU fallback")

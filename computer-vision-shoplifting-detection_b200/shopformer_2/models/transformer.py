@@ -12,6 +12,7 @@ import torch
 import torch.nn as nn
 
 from shopformer_b200.modules import _Owned, sinusoid_table, wants_native
+from shopformer_b200.ops import model_handle
 
 __all__ = ["PositionalEncoding", "ShopformerTransformer", "TransformerConfig", "build_transformer"]
 
@@ -59,7 +60,7 @@ class ShopformerTransformer(nn.Module, _Owned):
         if unmasked and self.activation_name == "gelu" and wants_native(self, tokens):
             eng = self._engine()
             if eng is not None:
-                return eng.reconstruct_tokens(tokens, precision=self._precision())
+                return torch.ops.shopformer_b200.reconstruct_tokens(tokens, model_handle(eng), self._precision())
         x = self._embed(tokens)
         memory = self.encoder(x, mask=src_mask, src_key_padding_mask=src_key_padding_mask)
         out = self.decoder(x, memory, tgt_mask=tgt_mask, memory_mask=src_mask,

@@ -32,6 +32,9 @@ class EngineConfig:
     n_dec_layers: int
     d_ff: int
     pool_tokens: int = 0
+    # 16-bit operand format of the tensor-core path: "auto" (fp16 when every packed weight is inside fp16's range, else
+    # bf16) | "bf16" (wide range, 8 significant bits) | "fp16".  Env SHOPFORMER_B200_TC_FORMAT overrides "auto".
+    tc_format: str = "auto"
 
     def to_native(self) -> N.SfConfig:
         c = N.SfConfig()
@@ -45,6 +48,14 @@ class EngineConfig:
             c.strides[i] = int(v)
         c.pool_tokens, c.d_model, c.n_heads = self.pool_tokens, self.d_model, self.n_heads
         c.n_enc_layers, c.n_dec_layers, c.d_ff = self.n_enc_layers, self.n_dec_layers, self.d_ff
+        fmt = self.tc_format
+        if fmt == "auto":
+            import os
+            fmt = os.environ.get("SHOPFORMER_B200_TC_FORMAT", "auto").lower()
+        try:
+            c.tc_format = {"auto": N.SF_TC_AUTO, "bf16": N.SF_TC_BF16, "fp16": N.SF_TC_FP16, "f16": N.SF_TC_FP16}[fmt]
+        except KeyError:
+            raise ValueError(f"unknown tensor-core operand format {fmt!r} (auto | bf16 | fp16)") from None
         return c
 
 
@@ -125,12 +136,19 @@ class ScoringEngine:
             buf = self._ws[key] = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
         return buf, int(nbytes)
 
-    # -- precision policy: "fp32" | "bf16" | "auto" (bf16 tensor-core kernels when they cover the shape, else fp32)
+    def tc_formats(self, T: int) -> Tuple[str, str]:
+        """Operand formats ("f16" | "bf16") of the tensor-core tokenizer / transformer for windows of T frames."""
+        a, b = C.c_int32(), C.c_int32()
+        N.check(self._lib.sf_model_tc_formats(self._h, T, C.byref(a), C.byref(b)), "sf_model_tc_formats")
+        return ("f16" if a.value else "bf16", "f16" if b.value else "bf16")
+
+    # -- precision policy: "fp32" | "tc" (alias "bf16": the 16-bit tensor-core kernels; their operand format is the
+    # model's tc_format) | "auto" (tensor-core kernels when they cover the shape, else fp32)
     def _run_prec(self, kind: str, key: int, precision: str, call):
-        if precision in ("fp32", "bf16"):
+        if precision in self._PREC:
             return call(self._PREC[precision])
         if precision != "auto":
-            raise ValueError(f"unknown precision {precision!r} (fp32 | bf16 | auto)")
+            raise ValueError(f"unknown precision {precision!r} (fp32 | tc | bf16 | auto)")
         pick = self._auto.get((kind, key))
         if pick is None:
             try:
@@ -153,7 +171,7 @@ class ScoringEngine:
         return poses.to(self.device, torch.float32).contiguous()
 
     # -- the four reference-facing calls
-    _PREC = {"fp32": N.SF_PREC_FP32, "bf16": N.SF_PREC_BF16}
+    _PREC = {"fp32": N.SF_PREC_FP32, "bf16": N.SF_PREC_BF16, "tc": N.SF_PREC_BF16, "tc16": N.SF_PREC_BF16}
 
     def tokenize(self, poses: torch.Tensor, precision: str = "fp32", out: Optional[torch.Tensor] = None) -> torch.Tensor:
         x = self._poses(poses)
@@ -256,12 +274,99 @@ class ScoringEngine:
             self._lib.sf_runner_score(r, C.c_void_p(a.ctypes.data), B, p, C.c_void_p(out.ctypes.data)), "sf_runner_score"))
         return out
 
+    def _runner(self, T: int, chunk: int) -> C.c_void_p:
+        key = (T, chunk)
+        if key not in self._runners:
+            h = C.c_void_p()
+            N.check(self._lib.sf_runner_create(self._h, T, chunk, C.byref(h)), "sf_runner_create")
+            self._runners[key] = h
+        return self._runners[key]
+
+    # -- packed tracks in, scores + window index out (dataset construction + scoring loop of the reference in one call)
+    def score_tracks(self, tracks: "DeviceTracks", seq_len: int, stride: int, max_gap: int = 5, normalize: bool = True,
+                     add_neck: Optional[bool] = None, precision: str = "auto") -> Dict[str, torch.Tensor]:
+        """Device-resident tracks -> per-window scores, labels and (track, start) index in the reference's window order
+        (``sf_score_from_tracks``): the normalised windows only ever exist one 131,072-window pass at a time."""
+        if tracks.device != self.device:
+            raise ValueError(f"tracks live on {tracks.device}, the engine on {self.device}")
+        nt = tracks.native()
+        p = _window_params(seq_len, stride, max_gap, self.cfg.num_keypoints, normalize, add_neck, self.cfg.in_channels == 3)
+        cap = self._lib.sf_window_capacity(C.byref(nt), C.byref(p))
+        N.check(int(min(cap, 0)), "sf_window_capacity")
+        capn = max(int(cap), 1)
+        dev = self.device
+        scores = torch.empty(capn, dtype=torch.float32, device=dev)
+        labels = torch.empty(capn, dtype=torch.int32, device=dev)
+        wtrack = torch.empty(capn, dtype=torch.int32, device=dev)
+        wstart = torch.empty(capn, dtype=torch.int32, device=dev)
+        wsb = self._lib.sf_score_from_tracks_workspace_bytes(self._h, C.byref(nt), C.byref(p))
+        N.check(int(min(wsb, 0)), "sf_score_from_tracks_workspace_bytes")
+        key = ("tracks", torch.cuda.current_stream(dev).cuda_stream)
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < wsb:
+            ws = self._ws[key] = torch.empty(max(int(wsb), 1), dtype=torch.uint8, device=dev)
+        n_host = C.c_int64(0)
+        st = _stream_ptr(dev)
+        self._run_prec("score", seq_len, precision, lambda pr: N.check(
+            self._lib.sf_score_from_tracks(self._h, C.byref(nt), C.byref(p), pr, _ptr(scores), _ptr(labels), _ptr(wtrack), _ptr(wstart),
+                                           C.byref(n_host), _ptr(ws), int(wsb), st), "sf_score_from_tracks"))
+        n = int(n_host.value)
+        return {"scores": scores[:n], "labels": labels[:n], "window_track": wtrack[:n], "window_start": wstart[:n], "n_windows": n,
+                "capacity": int(cap)}
+
+    def score_tracks_host(self, tracks: "PackedTracks", seq_len: int, stride: int, max_gap: int = 5, normalize: bool = True,
+                          add_neck: Optional[bool] = None, precision: str = "auto", chunk: int = 16384) -> Dict[str, np.ndarray]:
+        """Host-resident tracks -> host scores + window index (``sf_runner_score_tracks``): groups of whole tracks are uploaded
+        on a copy stream while the previous group is windowed and scored."""
+        kp = np.ascontiguousarray(tracks.kp, dtype=np.float32)
+        fno = np.ascontiguousarray(tracks.frame_no, dtype=np.int32)
+        off = np.ascontiguousarray(tracks.track_offsets, dtype=np.int64)
+        vid = np.ascontiguousarray(tracks.track_video, dtype=np.int32)
+        has_gt = tracks.gt is not None and tracks.gt_offsets is not None and len(tracks.gt) > 0
+        gt = np.ascontiguousarray(tracks.gt, dtype=np.uint8) if has_gt else None
+        gto = np.ascontiguousarray(tracks.gt_offsets, dtype=np.int64) if has_gt else None
+        t = N.SfTracks()
+        t.kp_dev, t.frame_no_dev = kp.ctypes.data, fno.ctypes.data           # HOST pointers for this entry point
+        t.track_offsets_host, t.track_video_host = off.ctypes.data, vid.ctypes.data
+        t.gt_dev = gt.ctypes.data if has_gt else 0
+        t.gt_offsets_host = gto.ctypes.data if has_gt else 0
+        t.n_frames, t.n_tracks = int(kp.shape[0]), int(len(off) - 1)
+        t.n_videos = int(len(gto) - 1) if has_gt else 0
+        t.kp_per_frame, t.kp_channels = int(kp.shape[1]), int(kp.shape[2])
+        p = _window_params(seq_len, stride, max_gap, self.cfg.num_keypoints, normalize, add_neck, self.cfg.in_channels == 3)
+        cap = self._lib.sf_window_capacity(C.byref(t), C.byref(p))
+        N.check(int(min(cap, 0)), "sf_window_capacity")
+        capn = max(int(cap), 1)
+        scores = np.empty(capn, np.float32)
+        labels = np.empty(capn, np.int32)
+        wtrack = np.empty(capn, np.int32)
+        wstart = np.empty(capn, np.int32)
+        n_host = C.c_int64(0)
+        r = self._runner(seq_len, chunk)
+        self._run_prec("score", seq_len, precision, lambda pr: N.check(
+            self._lib.sf_runner_score_tracks(r, C.byref(t), C.byref(p), pr, C.c_void_p(scores.ctypes.data), C.c_void_p(labels.ctypes.data),
+                                             C.c_void_p(wtrack.ctypes.data), C.c_void_p(wstart.ctypes.data), C.byref(n_host)),
+            "sf_runner_score_tracks"))
+        n = int(n_host.value)
+        return {"scores": scores[:n], "labels": labels[:n], "window_track": wtrack[:n], "window_start": wstart[:n], "n_windows": n,
+                "capacity": int(cap)}
+
 
 # --------------------------------------------------------------------------- windowing
+def _window_params(seq_len: int, stride: int, max_gap: int, num_keypoints: int, normalize: bool, add_neck: Optional[bool],
+                   include_confidence: bool) -> N.SfWindowParams:
+    p = N.SfWindowParams()
+    p.seq_len, p.stride, p.max_gap, p.num_keypoints, p.normalize = seq_len, stride, max_gap, num_keypoints, int(normalize)
+    # default = the shopformer_2 convention (18 keypoints = COCO-17 + synthetic neck); shopformer/ passes add_neck=False
+    p.add_neck = int(num_keypoints == 18 if add_neck is None else add_neck)
+    p.include_confidence = int(include_confidence)
+    return p
+
+
 @dataclass
 class PackedTracks:
     """Packed per-person tracks (see include/shopformer_b200.h, ``sf_tracks``)."""
-    kp: np.ndarray                 # (F, K, 3) fp32
+    kp: np.ndarray                 # (F, K, 3) fp32 (x, y, conf), or (F, K, 2) when the confidence was dropped at ingest
     frame_no: np.ndarray           # (F,) int32
     track_offsets: np.ndarray      # (n_tracks+1,) int64
     track_video: np.ndarray        # (n_tracks,) int32
@@ -280,6 +385,8 @@ class DeviceTracks:
     def __init__(self, tracks: PackedTracks, device: torch.device):
         self.host = tracks
         self.device = torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.kp = torch.from_numpy(np.ascontiguousarray(tracks.kp, dtype=np.float32)).to(self.device)
         self.frame_no = torch.from_numpy(np.ascontiguousarray(tracks.frame_no, dtype=np.int32)).to(self.device)
         self.gt = None
@@ -301,6 +408,7 @@ class DeviceTracks:
         t.n_tracks = int(len(self._off) - 1)
         t.n_videos = 0 if self._gto is None else int(len(self._gto) - 1)
         t.kp_per_frame = int(self.kp.shape[1])
+        t.kp_channels = int(self.kp.shape[2])
         return t
 
 
@@ -313,11 +421,7 @@ def window_normalize(tracks: DeviceTracks, seq_len: int, stride: int, num_keypoi
     lib = N.load()
     dev = tracks.device
     nt = tracks.native()
-    p = N.SfWindowParams()
-    p.seq_len, p.stride, p.max_gap, p.num_keypoints, p.normalize = seq_len, stride, max_gap, num_keypoints, int(normalize)
-    # default = the shopformer_2 convention (18 keypoints = COCO-17 + synthetic neck); shopformer/ passes add_neck=False
-    p.add_neck = int(num_keypoints == 18 if add_neck is None else add_neck)
-    p.include_confidence = int(include_confidence)
+    p = _window_params(seq_len, stride, max_gap, num_keypoints, normalize, add_neck, include_confidence)
     n_planes = 3 if include_confidence else 2
     cap = lib.sf_window_capacity(C.byref(nt), C.byref(p))
     N.check(int(min(cap, 0)), "sf_window_capacity")
@@ -344,3 +448,66 @@ def window_normalize(tracks: DeviceTracks, seq_len: int, stride: int, num_keypoi
                 out[k] = out[k][:n]
         out["n_windows"] = n
     return out
+
+
+# --------------------------------------------------------------------------- after the path: aggregation + ranking metrics
+def video_aggregate(scores: torch.Tensor, video_ids: torch.Tensor, labels: Optional[torch.Tensor], n_videos: int) -> Dict[str, torch.Tensor]:
+    """Per-video max / mean / 95th percentile (float64, numpy semantics) of window scores, the video label (label of the
+    video's last window, as shopformer_2/evaluate.py:107-116 leaves it) and the window count, on the device
+    (``sf_video_aggregate``).  Videos without windows get NaN / label 0 / count 0."""
+    lib = N.load()
+    if not scores.is_cuda:
+        raise RuntimeError("video_aggregate takes CUDA tensors (no CPU fallback)")
+    dev = scores.device
+    s = scores.detach().to(torch.float32).contiguous().view(-1)
+    v = video_ids.to(dev, torch.int32).contiguous().view(-1)
+    lb = None if labels is None else labels.to(dev, torch.int32).contiguous().view(-1)
+    n = int(s.numel())
+    if v.numel() != n or (lb is not None and lb.numel() != n):
+        raise ValueError("scores, video_ids and labels must have the same length")
+    nv = int(n_videos)
+    out = {k: torch.empty(max(nv, 1), dtype=torch.float64, device=dev) for k in ("max", "mean", "percentile_95")}
+    vlabel = torch.zeros(max(nv, 1), dtype=torch.int32, device=dev)
+    count = torch.zeros(max(nv, 1), dtype=torch.int32, device=dev)
+    wsb = lib.sf_video_aggregate_workspace_bytes(n, nv)
+    N.check(int(min(wsb, 0)), "sf_video_aggregate_workspace_bytes")
+    ws = torch.empty(max(int(wsb), 1), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        N.check(lib.sf_video_aggregate(_ptr(s), _ptr(v), _ptr(lb), n, nv, _ptr(out["max"]), _ptr(out["mean"]), _ptr(out["percentile_95"]),
+                                       _ptr(vlabel), _ptr(count), _ptr(ws), int(wsb), _stream_ptr(dev)), "sf_video_aggregate")
+    res = {k: t[:nv] for k, t in out.items()}
+    res["label"] = vlabel[:nv]
+    res["count"] = count[:nv]
+    return res
+
+
+def ranking_metrics(scores: torch.Tensor, labels: torch.Tensor, threshold: Optional[float] = None) -> Dict[str, float]:
+    """AUC-ROC, average precision, the threshold (given, or the Youden-J optimum of the ROC curve like the reference's
+    ``compute_metrics``) and the confusion counts at it, computed on the device (``sf_ranking_metrics``: radix sort + scans).
+    Degenerate label sets follow the reference's conventions (AUC-ROC 0.5, AUC-PR 0.0)."""
+    lib = N.load()
+    if not scores.is_cuda:
+        raise RuntimeError("ranking_metrics takes CUDA tensors (no CPU fallback)")
+    dev = scores.device
+    s = scores.detach().to(torch.float32).contiguous().view(-1)
+    lb = labels.to(dev, torch.int32).contiguous().view(-1)
+    n = int(s.numel())
+    if lb.numel() != n or n == 0:
+        raise ValueError("scores and labels must be non-empty and of the same length")
+    wsb = lib.sf_ranking_metrics_workspace_bytes(n)
+    N.check(int(min(wsb, 0)), "sf_ranking_metrics_workspace_bytes")
+    ws = torch.empty(int(wsb), dtype=torch.uint8, device=dev)
+    out = (C.c_double * 8)()
+    thr = float("nan") if threshold is None else float(threshold)
+    with torch.cuda.device(dev):
+        N.check(lib.sf_ranking_metrics(_ptr(s), _ptr(lb), n, C.c_float(thr), out, _ptr(ws), int(wsb), _stream_ptr(dev)), "sf_ranking_metrics")
+    auc_roc, auc_pr, thr_used, n_pos, tp, fp, tn, fn = [float(x) for x in out]
+    if auc_roc != auc_roc:
+        auc_roc = 0.5
+    if auc_pr != auc_pr:
+        auc_pr = 0.0
+    precision = tp / (tp + fp) if tp + fp > 0 else 0.0
+    recall = tp / (tp + fn) if tp + fn > 0 else 0.0
+    f1 = 2 * precision * recall / (precision + recall) if precision + recall > 0 else 0.0
+    return {"auc_roc": auc_roc, "auc_pr": auc_pr, "accuracy": (tp + tn) / n, "precision": precision, "recall": recall, "f1": f1,
+            "threshold": thr_used, "tp": int(tp), "fp": int(fp), "tn": int(tn), "fn": int(fn), "n_positive": int(n_pos)}

@@ -16,7 +16,7 @@ import torch.nn as nn
 
 from .engine import EngineConfig, ScoringEngine
 
-PRECISIONS = ("auto", "bf16", "fp32")
+PRECISIONS = ("auto", "tc", "bf16", "fp32")
 
 
 class EngineCacheMixin:

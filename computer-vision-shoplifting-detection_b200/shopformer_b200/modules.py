@@ -26,6 +26,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .ops import model_handle
+
 # --------------------------------------------------------------------------- skeleton graphs
 _COCO17 = [(0, 1), (0, 2), (1, 3), (2, 4), (0, 5), (0, 6), (5, 7), (7, 9), (6, 8), (8, 10),
            (5, 11), (6, 12), (11, 12), (11, 13), (13, 15), (12, 14), (14, 16)]
@@ -252,7 +254,7 @@ class GCAEEncoder(nn.Module, _Owned):
         if wants_native(self, x):
             eng = self._engine()
             if eng is not None:
-                return eng.tokenize(x, precision=self._precision())
+                return torch.ops.shopformer_b200.tokenize(x, model_handle(eng), self._precision())
         b, c, t, v = x.shape
         y = self.bn_input(x.permute(0, 1, 3, 2).reshape(b, c * v, t))
         x = y.view(b, c, v, t).permute(0, 1, 3, 2).contiguous()

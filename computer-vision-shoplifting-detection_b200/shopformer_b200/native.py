@@ -21,6 +21,7 @@ SF_REDUCE_MEAN = 0
 SF_REDUCE_NONE = 1
 SF_PREC_FP32 = 0
 SF_PREC_BF16 = 1
+SF_TC_AUTO, SF_TC_BF16, SF_TC_FP16 = 0, 1, 2
 SF_MAX_BLOCKS = 8
 
 ERROR_NAMES = {-1: "SF_E_INVALID", -2: "SF_E_MISSING", -3: "SF_E_SHAPE", -4: "SF_E_UNSUPPORTED",
@@ -32,7 +33,9 @@ ABI_SYMBOLS = (
     "sf_model_token_shape", "sf_workspace_bytes", "sf_tokenize", "sf_reconstruct_tokens",
     "sf_normality_score", "sf_score_windows", "sf_window_capacity", "sf_window_workspace_bytes",
     "sf_window_normalize", "sf_runner_create", "sf_runner_destroy", "sf_runner_score",
-    "sf_runner_pinned_poses", "sf_selftest_umma", "sf_normalize_windows",
+    "sf_runner_pinned_poses", "sf_selftest_umma", "sf_normalize_windows", "sf_model_tc_formats",
+    "sf_score_from_tracks_workspace_bytes", "sf_score_from_tracks", "sf_runner_score_tracks",
+    "sf_video_aggregate_workspace_bytes", "sf_video_aggregate", "sf_ranking_metrics_workspace_bytes", "sf_ranking_metrics",
 )
 
 
@@ -50,7 +53,7 @@ class SfConfig(C.Structure):
         ("n_blocks", C.c_int32), ("channels", C.c_int32 * (SF_MAX_BLOCKS + 1)),
         ("strides", C.c_int32 * SF_MAX_BLOCKS), ("pool_tokens", C.c_int32), ("d_model", C.c_int32),
         ("n_heads", C.c_int32), ("n_enc_layers", C.c_int32), ("n_dec_layers", C.c_int32),
-        ("d_ff", C.c_int32), ("reserved", C.c_int32 * 8),
+        ("d_ff", C.c_int32), ("tc_format", C.c_int32), ("reserved", C.c_int32 * 7),
     ]
 
 
@@ -59,7 +62,7 @@ class SfTracks(C.Structure):
         ("kp_dev", C.c_void_p), ("frame_no_dev", C.c_void_p), ("track_offsets_host", C.c_void_p),
         ("track_video_host", C.c_void_p), ("gt_dev", C.c_void_p), ("gt_offsets_host", C.c_void_p),
         ("n_frames", C.c_int64), ("n_tracks", C.c_int32), ("n_videos", C.c_int32),
-        ("kp_per_frame", C.c_int32),
+        ("kp_per_frame", C.c_int32), ("kp_channels", C.c_int32),
     ]
 
 
@@ -94,6 +97,7 @@ def load() -> C.CDLL:
         "sf_model_destroy": (None, [vp]),
         "sf_model_token_shape": (C.c_int, [vp, i32, P(i32), P(i32)]),
         "sf_workspace_bytes": (i64, [vp, i64, i32]),
+        "sf_model_tc_formats": (C.c_int, [vp, i32, P(i32), P(i32)]),
         "sf_tokenize": (C.c_int, [vp, vp, i64, i32, i32, vp, vp, i64, vp]),
         "sf_reconstruct_tokens": (C.c_int, [vp, vp, i64, i32, i32, vp, vp, i64, vp]),
         "sf_normality_score": (C.c_int, [vp, vp, vp, i64, i32, i32, vp, vp]),
@@ -107,13 +111,20 @@ def load() -> C.CDLL:
         "sf_runner_pinned_poses": (vp, [vp, i32]),
         "sf_selftest_umma": (C.c_int, [i32, i32, i32, i32, vp, vp, vp]),
         "sf_normalize_windows": (C.c_int, [vp, i64, i32, i32, i32, i32, vp, vp]),
+        "sf_score_from_tracks_workspace_bytes": (i64, [vp, P(SfTracks), P(SfWindowParams)]),
+        "sf_score_from_tracks": (C.c_int, [vp, P(SfTracks), P(SfWindowParams), i32, vp, vp, vp, vp, P(i64), vp, i64, vp]),
+        "sf_runner_score_tracks": (C.c_int, [vp, P(SfTracks), P(SfWindowParams), i32, vp, vp, vp, vp, P(i64)]),
+        "sf_video_aggregate_workspace_bytes": (i64, [i64, i32]),
+        "sf_video_aggregate": (C.c_int, [vp, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp, i64, vp]),
+        "sf_ranking_metrics_workspace_bytes": (i64, [i64]),
+        "sf_ranking_metrics": (C.c_int, [vp, vp, i64, C.c_float, P(C.c_double), vp, i64, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.sf_abi_version() != 1:
-        raise ImportError(f"{LIB_PATH}: ABI version {lib.sf_abi_version()} != 1; rebuild")
+    if lib.sf_abi_version() != 2:
+        raise ImportError(f"{LIB_PATH}: ABI version {lib.sf_abi_version()} != 2; rebuild")
     _lib = lib
     return lib
 

@@ -179,3 +179,45 @@ def synth_tracks(n_tracks: int, seed: int = 1234, *, min_len: int = 30, max_len:
         "gt": np.concatenate(gts),
         "gt_offsets": np.asarray(gt_offs, dtype=np.int64),
     }
+
+
+def synth_tracks_device(n_tracks: int, track_len: int, device, seed: int = 1234, *, gap_every: int = 500, channels: int = 3,
+                        chunk_tracks: int = 2048):
+    """Bench-scale packed tracks generated ON the device (a 10 M-window sweep is ~120 M detections = 24.5 GB of
+    keypoints; numpy would take minutes): `n_tracks` tracks of `track_len` detections each, COCO-17 skeleton doing a random
+    walk in pixel units, a hole of 6..20 frames every ~`gap_every` detections (windows across it fail the continuity
+    test), one ground-truth array per track.  Returns (kp (F,17,channels) fp32 cuda, frame_no (F,) int32 cuda,
+    track_offsets (n+1,) int64 numpy, track_video (n,) int32 numpy, gt (sum,) uint8 cuda, gt_offsets (n+1,) int64 numpy)."""
+    import torch
+    dev = torch.device(device)
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    F = n_tracks * track_len
+    kp = torch.empty(F, 17, channels, dtype=torch.float32, device=dev)
+    frame_no = torch.empty(F, dtype=torch.int32, device=dev)
+    tmpl = torch.from_numpy((COCO17_TEMPLATE * np.array([300.0, 700.0])).astype(np.float32)).to(dev)
+    n_gaps = track_len // gap_every if gap_every > 0 else 0
+    gt_len = track_len + 21 * max(n_gaps, 1)
+    gt = torch.zeros(n_tracks * gt_len, dtype=torch.uint8, device=dev)
+    for t0 in range(0, n_tracks, chunk_tracks):
+        n = min(chunk_tracks, n_tracks - t0)
+        base = torch.rand(n, 1, 1, 2, device=dev, generator=g) * torch.tensor([1500.0, 300.0], device=dev)
+        walk = torch.cumsum(torch.randn(n, track_len, 1, 2, device=dev, generator=g) * 1.5, dim=1)
+        xy = tmpl.view(1, 1, 17, 2) + base + walk + torch.randn(n, track_len, 17, 2, device=dev, generator=g) * 3.0
+        view = kp[t0 * track_len:(t0 + n) * track_len].view(n, track_len, 17, channels)
+        view[..., :2] = xy
+        if channels == 3:
+            view[..., 2] = torch.rand(n, track_len, 17, device=dev, generator=g) * 0.9 + 0.1
+        fn = torch.arange(track_len, device=dev, dtype=torch.int32).repeat(n, 1)
+        for k in range(n_gaps):
+            at = (k + 1) * gap_every - torch.randint(0, gap_every // 4 + 1, (n, 1), device=dev, generator=g)
+            hole = torch.randint(6, 21, (n, 1), device=dev, generator=g, dtype=torch.int32)
+            fn += (torch.arange(track_len, device=dev).view(1, -1) >= at).to(torch.int32) * hole
+        frame_no[t0 * track_len:(t0 + n) * track_len] = fn.reshape(-1)
+        a = torch.randint(0, track_len, (n, 1), device=dev, generator=g)
+        ln = torch.randint(10, 200, (n, 1), device=dev, generator=g)
+        pos = torch.arange(gt_len, device=dev).view(1, -1)
+        gt[t0 * gt_len:(t0 + n) * gt_len] = ((pos >= a) & (pos < a + ln)).to(torch.uint8).reshape(-1)
+    track_offsets = np.arange(n_tracks + 1, dtype=np.int64) * track_len
+    gt_offsets = np.arange(n_tracks + 1, dtype=np.int64) * gt_len
+    return kp, frame_no, track_offsets, np.arange(n_tracks, dtype=np.int32), gt, gt_offsets

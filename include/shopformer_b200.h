@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define SF_ABI_VERSION 1
+#define SF_ABI_VERSION 2
 
 enum {
   SF_OK = 0,
@@ -49,8 +49,13 @@ enum {
 
 enum { SF_VARIANT_SHOPFORMER = 1, SF_VARIANT_SHOPFORMER_2 = 2 };
 enum { SF_REDUCE_MEAN = 0, SF_REDUCE_NONE = 1 };
-/* arithmetic of the tokenizer/transformer contractions */
-enum { SF_PREC_FP32 = 0, SF_PREC_BF16 = 1 };
+/* arithmetic of the tokenizer/transformer contractions: fp32 on the CUDA cores, or 16-bit operands with fp32
+ * accumulation on the tensor cores (SF_PREC_BF16 names the tensor-core path; its operand FORMAT is sf_config.tc_format) */
+enum { SF_PREC_FP32 = 0, SF_PREC_BF16 = 1, SF_PREC_TC16 = 1 };
+/* 16-bit operand format of the tensor-core path.  AUTO = fp16 (11 significant bits: 8x smaller rounding error than
+ * bf16 on weights and activations; activations saturate at +-65504) whenever every packed weight is inside fp16's
+ * range, else bf16.  BF16 forces the wide-range format (checkpoints whose activations can exceed 6e4). */
+enum { SF_TC_AUTO = 0, SF_TC_BF16 = 1, SF_TC_FP16 = 2 };
 
 #define SF_MAX_BLOCKS 8
 
@@ -70,7 +75,8 @@ typedef struct sf_config {
   int32_t n_enc_layers;
   int32_t n_dec_layers;
   int32_t d_ff;
-  int32_t reserved[8];
+  int32_t tc_format;               /* SF_TC_*                                             */
+  int32_t reserved[7];
 } sf_config;
 
 typedef struct sf_model sf_model;    /* packed, BatchNorm-folded weights resident in HBM */
@@ -95,6 +101,9 @@ int sf_model_create(const sf_config* cfg, int32_t n_tensors, const char* const* 
 void sf_model_destroy(sf_model* m);
 /* Token count S and token width D for windows of T frames (conv length (T-1)/s+1 per block). */
 int sf_model_token_shape(const sf_model* m, int32_t T, int32_t* S, int32_t* D);
+/* Operand format the tensor-core kernels use for windows of T frames: *tokenizer_f16 / *transformer_f16 = 1 for
+ * fp16, 0 for bf16 (the one-window-per-pass tokenizer that serves hidden-64 / pooled shapes is bf16 only). */
+int sf_model_tc_formats(const sf_model* m, int32_t T, int32_t* tokenizer_f16, int32_t* transformer_f16);
 /* Bytes of device workspace the calls below need for a batch of B windows of T frames.
  * Bounded: batches beyond 131,072 windows are processed in internal passes of that size. */
 int64_t sf_workspace_bytes(const sf_model* m, int64_t B, int32_t T);
@@ -130,6 +139,7 @@ int sf_score_windows(const sf_model* m, const float* poses_dev, int64_t B, int32
 /* Packed tracks (one entry per detection of one person, grouped per person in the
  * reference's first-seen order, frames ascending inside a track):
  *   kp_dev         (F, K, 3) fp32   x, y, conf as PoseLift stores them, K >= 17
+ *                  ((F, K, 2) x, y only when kp_channels == 2: ingest may drop the confidence, a third fewer bytes)
  *   frame_no_dev   (F) int32
  *   track_offsets  (n_tracks + 1) int64, host
  *   track_video    (n_tracks) int32, host        index into gt_offsets
@@ -147,6 +157,7 @@ typedef struct sf_tracks {
   int32_t n_tracks;
   int32_t n_videos;
   int32_t kp_per_frame;            /* K (17 for PoseLift)                                 */
+  int32_t kp_channels;             /* floats per keypoint in kp_dev: 3 (or 0) = x, y, conf; 2 = x, y */
 } sf_tracks;
 
 typedef struct sf_window_params {
@@ -192,6 +203,49 @@ int sf_window_normalize(const sf_tracks* tr, const sf_window_params* p, float* p
 int sf_normalize_windows(const float* raw_dev, int64_t B, int32_t T, int32_t K, int32_t V, int32_t normalize,
                          float* poses_dev, void* stream);
 
+/* Replaces the reference flow "dataset construction feeding the scoring loop":
+ *   PoseLiftDataset.__init__ -> _extract_sequences / _normalize_sequence / __getitem__
+ *   (shopformer/data/poselift_dataset.py:256-400) -> evaluate_model's loop (shopformer/evaluate.py:83-104;
+ *   shopformer_2/evaluate.py:36-63).  Packed tracks in, per-window scores and the window index out, in the
+ *   reference's window order.  The normalised windows never exist as a whole: they are cut, normalised and scored in
+ *   passes of 131,072 windows through the workspace.  Outputs are sized by sf_window_capacity().
+ *   Synchronises `stream` once, at the end (tensor-core kernels: every pass is launched for its capacity and clamps to the
+ *   device-side count) or after the windowing kernels (fp32 kernels: the count sizes the launches); the count is returned in
+ *   `n_windows_host` (required).  `labels_dev` / `window_track_dev` / `window_start_dev` are required (the index the
+ *   gather reads). */
+int64_t sf_score_from_tracks_workspace_bytes(const sf_model* m, const sf_tracks* tr, const sf_window_params* p);
+int sf_score_from_tracks(const sf_model* m, const sf_tracks* tr, const sf_window_params* p, int32_t precision,
+                         float* scores_dev, int32_t* labels_dev, int32_t* window_track_dev,
+                         int32_t* window_start_dev, int64_t* n_windows_host, void* workspace_dev,
+                         int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ after the path: aggregation + ranking metrics */
+/* Replaces: the per-video grouping of evaluate_video_level (shopformer_2/evaluate.py:65-118) and
+ *   compute_video_level_metrics' aggregation (shopformer_2/utils/metrics.py:148-188): per-video max / mean / 95th
+ *   percentile of the window scores, in float64 as numpy computes them from the python floats, and the video label =
+ *   the label of the video's LAST window in dataset order (what the reference's `video_labels[video_id] = info['label']`
+ *   leaves).  `video_id_dev` (n) int32 in [0, n_videos) (other ids are ignored); windows of a video need not be
+ *   contiguous.  The percentile is numpy's default (linear interpolation).
+ *   Outputs (n_videos): agg_max/agg_mean/agg_p95 float64 (NaN for a video without windows), video_label int32 (0 for a
+ *   video without windows), count int32.  Any output may be NULL.  No synchronisation. */
+int64_t sf_video_aggregate_workspace_bytes(int64_t n, int32_t n_videos);
+int sf_video_aggregate(const float* scores_dev, const int32_t* video_id_dev, const int32_t* labels_dev, int64_t n,
+                       int32_t n_videos, double* agg_max_dev, double* agg_mean_dev, double* agg_p95_dev,
+                       int32_t* video_label_dev, int32_t* count_dev, void* workspace_dev, int64_t workspace_bytes,
+                       void* stream);
+
+/* Replaces: compute_auc_roc / compute_auc_pr (shopformer/utils/metrics.py:18-77; shopformer_2/utils/metrics.py:21-145),
+ *   i.e. sklearn.metrics.roc_auc_score and average_precision_score, on the device: radix sort of the scores (descending),
+ *   tie groups, prefix sums of positives, trapezoid / step integration in float64, and compute_metrics' thresholding:
+ *   `threshold` NaN selects the Youden-J optimum of the ROC curve (first maximum of tpr - fpr in descending-score order,
+ *   +inf if no point beats the origin), predictions = score >= threshold.
+ *   out_host (8 doubles): auc_roc, auc_pr, threshold used, n_positive, tp, fp, tn, fn; auc_roc is NaN when only one class
+ *   is present and auc_pr when there is no positive (the reference returns 0.5 / 0.0 there: the facade applies that
+ *   convention).  Synchronises `stream`. */
+int64_t sf_ranking_metrics_workspace_bytes(int64_t n);
+int sf_ranking_metrics(const float* scores_dev, const int32_t* labels_dev, int64_t n, float threshold,
+                       double* out_host, void* workspace_dev, int64_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------ host-buffer runner */
 /* The call a reference-side loop makes per batch: poses on the HOST, scores back on the
  * HOST (shopformer/evaluate.py:90-99, shopformer/inference.py:67-94,
@@ -206,6 +260,16 @@ void sf_runner_destroy(sf_runner* r);
  * torch pinned memory) is read in place by the kernels over PCIe, with no staging copy. */
 int sf_runner_score(sf_runner* r, const float* poses_host, int64_t B, int32_t precision,
                     float* scores_host);
+/* Host tracks in, host scores + window index out: the reference flow of sf_score_from_tracks for a caller whose
+ * tracks live in host memory (what PoseLiftDataset reads from the pickle files).  Tracks are uploaded in groups of
+ * whole tracks on the copy stream while the previous group is windowed and scored on the compute stream; uploading
+ * the raw detections moves stride*K*kp_channels*4 bytes per window instead of the 2*T*V*4 of a pre-cut window.
+ * `tr->kp_dev`, `frame_no_dev` and `gt_dev` are HOST pointers here (pinned or pageable); outputs are host arrays
+ * sized by sf_window_capacity().  Blocking. */
+int sf_runner_score_tracks(sf_runner* r, const sf_tracks* tr_host, const sf_window_params* p, int32_t precision,
+                           float* scores_host, int32_t* labels_host, int32_t* window_track_host,
+                           int32_t* window_start_host, int64_t* n_windows_host);
+
 /* Pinned staging buffer of the runner (capacity one chunk of windows, slots 0..3) so that
  * producers can write windows straight into page-locked memory. */
 float* sf_runner_pinned_poses(sf_runner* r, int32_t slot);
@@ -214,7 +278,8 @@ float* sf_runner_pinned_poses(sf_runner* r, int32_t slot);
 /* One 128 x N x K bf16 tcgen05 product (fp32 accumulate in TMEM) on a single CTA, host in / host out.
  * Exists so that the tests can pin the shared-memory descriptor encodings the tensor-core kernels
  * rely on.  mode 0: B is (N,K) row-major (K-major operand); mode 1: B is (K,N) row-major (MN-major
- * operand).  A is (128+shift, K) row-major and the product uses rows [shift, shift+128).
+ * operand); mode | 12: both operands are rounded to fp16 instead of bf16 (kind::f16 takes A and B in the same format).
+ * A is (128+shift, K) row-major and the product uses rows [shift, shift+128).
  * Synchronises the device.  No reference counterpart. */
 int sf_selftest_umma(int32_t mode, int32_t N, int32_t K, int32_t shift, const float* a_host,
                      const float* b_host, float* d_host);

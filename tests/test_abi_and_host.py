@@ -141,3 +141,13 @@ def test_synthetic_generators_are_deterministic():
     m = torch.nn.Linear(4, 3)
     s1, s2 = synth_state_dict(m.state_dict(), 0), synth_state_dict(m.state_dict(), 0)
     assert all(torch.equal(s1[k], s2[k]) for k in s1) and not torch.equal(s1["weight"], synth_state_dict(m.state_dict(), 1)["weight"])
+
+
+def test_torch_ops_are_registered():
+    """`torch.ops.shopformer_b200.*` exist after importing the package's op shim (no compute without a GPU)."""
+    import torch
+    from shopformer_b200 import ops
+    for name in ops.OPS:
+        assert hasattr(torch.ops.shopformer_b200, name), name
+    schema = str(torch.ops.shopformer_b200.score_fused.default._schema)
+    assert "Tensor poses" in schema and "int model" in schema

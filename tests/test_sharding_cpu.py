@@ -55,3 +55,42 @@ def _worker(rank: int, world: int, port: int, n_total: int):
 @pytest.mark.parametrize("n_total", [10, 11])
 def test_sharded_score_allgather_world2(n_total):
     mp.spawn(_worker, args=(2, _free_port(), n_total), nprocs=2, join=True)
+
+
+# ---- sharding a sweep over packed tracks (BASELINE configs[3]: windows shard by video / track and window index)
+def test_shard_tracks_balances_and_covers():
+    import numpy as np
+    from shopformer_b200.sharding import shard_tracks, track_window_counts
+    rs = np.random.RandomState(0)
+    lens = rs.randint(1, 3000, 500)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    counts = track_window_counts(off, 24, 12)
+    assert counts[lens < 24].sum() == 0 and counts.sum() == sum((n - 24) // 12 + 1 for n in lens if n >= 24)
+    for world in (1, 2, 4, 8):
+        shards = shard_tracks(off, 24, 12, world)
+        assert shards[0][0] == 0 and shards[-1][1] == 500
+        assert all(a[1] == b[0] for a, b in zip(shards, shards[1:]))
+        per = [int(counts[lo:hi].sum()) for lo, hi, _ in shards]
+        assert sum(per) == counts.sum()
+        assert [s[2] for s in shards] == [int(counts[:lo].sum()) for lo, _, _ in shards]      # global index of the first window
+        assert max(per) - min(per) <= counts.max() * 2                                         # cut at track boundaries only
+    # degenerate: fewer tracks than ranks, and no windows at all
+    assert len(shard_tracks(np.array([0, 100]), 24, 12, 4)) == 4
+    assert shard_tracks(np.array([0, 5, 9]), 24, 12, 2) == [(0, 0, 0), (0, 2, 0)] or shard_tracks(np.array([0, 5, 9]), 24, 12, 2)[-1][1] == 2
+
+
+def _ragged_worker(rank: int, world: int, port: int):
+    from shopformer_b200.sharding import gather_ragged
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        local = torch.arange(5 + 3 * rank, dtype=torch.float32) + 100 * rank       # rank 0: 5 scores, rank 1: 8 scores
+        allv, counts = gather_ragged(local)
+        assert counts == [5, 8]
+        assert torch.equal(allv, torch.cat([torch.arange(5, dtype=torch.float32), torch.arange(8, dtype=torch.float32) + 100]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ragged_score_allgather_world2():
+    mp.spawn(_ragged_worker, args=(2, _free_port()), nprocs=2, join=True)
