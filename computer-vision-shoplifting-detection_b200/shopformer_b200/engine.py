@@ -352,6 +352,64 @@ class ScoringEngine:
                 "capacity": int(cap)}
 
 
+# --------------------------------------------------------------------------- pose decoder (optional output)
+class DecoderEngine:
+    """Packed GCAE pose decoder on one GPU (``sf_decoder``): tokens (B,S,latent*V) -> poses (B,C,seq_len,V) in eval mode.
+    Built from the decoder module's own ``state_dict()`` (BatchNorm folded natively)."""
+
+    def __init__(self, latent_channels: int, hidden_channels: int, out_channels: int, num_keypoints: int, seq_len: int,
+                 upsample: Sequence[int], state_dict: Dict[str, torch.Tensor], device: torch.device):
+        lib = N.load()
+        N.check(lib.sf_device_count(), "sf_device_count")
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("DecoderEngine needs a CUDA device; there is no CPU path")
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", idx)
+        self.out_shape = (out_channels, seq_len, num_keypoints)
+        self.d_tok = latent_channels * num_keypoints
+        names, arrays = [], []
+        for k, v in state_dict.items():
+            if torch.is_tensor(v) and v.is_floating_point():
+                names.append(k.encode())
+                arrays.append(np.ascontiguousarray(v.detach().to("cpu", torch.float32).numpy()))
+        n = len(names)
+        ups = (C.c_int32 * len(upsample))(*[int(u) for u in upsample])
+        h = C.c_void_p()
+        N.check(lib.sf_decoder_create(latent_channels, hidden_channels, out_channels, num_keypoints, seq_len, len(upsample), ups, n,
+                                      (C.c_char_p * n)(*names), (C.c_void_p * n)(*[a.ctypes.data for a in arrays]),
+                                      (C.c_int64 * n)(*[a.size for a in arrays]), idx, C.byref(h)), "sf_decoder_create")
+        self._lib, self._h = lib, h
+        self._ws: Optional[torch.Tensor] = None
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.sf_decoder_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def decode(self, tokens: torch.Tensor) -> torch.Tensor:
+        if tokens.dim() != 3 or tokens.shape[2] != self.d_tok:
+            raise ValueError(f"tokens must be (B,S,{self.d_tok}), got {tuple(tokens.shape)}")
+        if not tokens.is_cuda:
+            raise RuntimeError("native decoder takes CUDA tensors only (no CPU fallback)")
+        t = tokens.to(self.device, torch.float32).contiguous()
+        B, S, _ = t.shape
+        out = torch.empty((B,) + self.out_shape, dtype=torch.float32, device=self.device)
+        nb = self._lib.sf_decoder_workspace_bytes(self._h, B, S)
+        N.check(int(min(nb, 0)), "sf_decoder_workspace_bytes")
+        if self._ws is None or self._ws.numel() < nb:
+            self._ws = torch.empty(max(int(nb), 1), dtype=torch.uint8, device=self.device)
+        N.check(self._lib.sf_decode_poses(self._h, _ptr(t), B, S, _ptr(out), _ptr(self._ws), int(nb), _stream_ptr(self.device)),
+                "sf_decode_poses")
+        return out
+
+
 # --------------------------------------------------------------------------- windowing
 def _window_params(seq_len: int, stride: int, max_gap: int, num_keypoints: int, normalize: bool, add_neck: Optional[bool],
                    include_confidence: bool) -> N.SfWindowParams:

@@ -278,6 +278,7 @@ class GCAEDecoder(nn.Module):
             skeleton_edges(num_keypoints, layout, family)
         self.initial_proj = nn.Linear(in_channels * num_keypoints, hidden_channels * num_keypoints)
         ups = upsample_factors(num_tokens, seq_len, num_layers)
+        self._sf_hidden, self._sf_upsample = hidden_channels, list(ups)
         outs = [hidden_channels] * (num_layers - 1) + [out_channels]
         seq: List[nn.Module] = []
         for i, (u, oc) in enumerate(zip(ups, outs)):
@@ -289,7 +290,29 @@ class GCAEDecoder(nn.Module):
                 seq += [nn.BatchNorm2d(oc), nn.ReLU(inplace=True), nn.Dropout(dropout)]
         self.layers = nn.Sequential(*seq)
 
+    def _sf_decoder_engine(self):
+        """Packed native decoder (sf_decoder), rebuilt when a parameter / buffer changed or moved."""
+        from .engine import DecoderEngine
+        tensors = list(self.parameters()) + list(self.buffers())
+        fp = tuple((t.data_ptr(), t._version) for t in tensors)
+        cached = self.__dict__.get("_sf_dec_cache")
+        if cached is not None and cached[0] == fp:
+            return cached[1]
+        if cached is not None:
+            cached[1].close()
+        eng = DecoderEngine(self.in_channels, self._sf_hidden, self.out_channels, self.num_keypoints, self.seq_len, self._sf_upsample,
+                            self.state_dict(), self.initial_proj.weight.device)
+        self.__dict__["_sf_dec_cache"] = (fp, eng)
+        return eng
+
     def forward(self, z: torch.Tensor) -> torch.Tensor:
+        if z.dim() == 3 and wants_native(self, z):
+            from .native import NativeError
+            try:
+                return self._sf_decoder_engine().decode(z)
+            except NativeError as exc:
+                if exc.code != -4:                    # SF_E_UNSUPPORTED (a window's activations exceed shared memory): ATen below
+                    raise
         b, s, _ = z.shape
         h = self.initial_proj(z)
         h = h.view(b, s, h.shape[-1] // self.num_keypoints, self.num_keypoints).permute(0, 2, 1, 3).contiguous()

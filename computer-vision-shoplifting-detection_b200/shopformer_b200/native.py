@@ -36,6 +36,7 @@ ABI_SYMBOLS = (
     "sf_runner_pinned_poses", "sf_selftest_umma", "sf_normalize_windows", "sf_model_tc_formats",
     "sf_score_from_tracks_workspace_bytes", "sf_score_from_tracks", "sf_runner_score_tracks",
     "sf_video_aggregate_workspace_bytes", "sf_video_aggregate", "sf_ranking_metrics_workspace_bytes", "sf_ranking_metrics",
+    "sf_decoder_create", "sf_decoder_destroy", "sf_decoder_workspace_bytes", "sf_decode_poses",
 )
 
 
@@ -118,6 +119,10 @@ def load() -> C.CDLL:
         "sf_video_aggregate": (C.c_int, [vp, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp, i64, vp]),
         "sf_ranking_metrics_workspace_bytes": (i64, [i64]),
         "sf_ranking_metrics": (C.c_int, [vp, vp, i64, C.c_float, P(C.c_double), vp, i64, vp]),
+        "sf_decoder_create": (C.c_int, [i32, i32, i32, i32, i32, i32, P(i32), i32, P(C.c_char_p), P(vp), P(i64), i32, P(vp)]),
+        "sf_decoder_destroy": (None, [vp]),
+        "sf_decoder_workspace_bytes": (i64, [vp, i64, i32]),
+        "sf_decode_poses": (C.c_int, [vp, vp, i64, i32, vp, vp, i64, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

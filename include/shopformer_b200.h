@@ -219,6 +219,25 @@ int sf_score_from_tracks(const sf_model* m, const sf_tracks* tr, const sf_window
                          int32_t* window_start_dev, int64_t* n_windows_host, void* workspace_dev,
                          int64_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------ pose decoder (optional output) */
+/* Replaces: GCAEDecoder.forward in eval mode (shopformer/models/gcae.py:369-478; shopformer_2/models/gcae.py:425-534):
+ *   Linear latent*V -> hidden*V per token, n_layers x (ConvTranspose2d k=(u,1) stride (u,1) | Conv2d 1x1) with BatchNorm2d +
+ *   ReLU after all but the last, bilinear resize (align_corners=False) to seq_len when the stack's length differs.
+ * Not on the scoring path: `Shopformer.forward` returns `gcae_reconstructed`, the facade produces it on demand with this.
+ * `names` are the decoder's own state-dict keys ("initial_proj.weight", "layers.0.weight", "layers.1.running_mean", ...);
+ * `upsample[i]` is the temporal factor of layer i (1 = 1x1 conv).  BatchNorm is folded here.  Synchronises `device`. */
+typedef struct sf_decoder sf_decoder;
+int sf_decoder_create(int32_t latent_channels, int32_t hidden_channels, int32_t out_channels, int32_t num_keypoints,
+                      int32_t seq_len, int32_t n_layers, const int32_t* upsample, int32_t n_tensors,
+                      const char* const* names, const float* const* data_host, const int64_t* numel, int32_t device,
+                      sf_decoder** out);
+void sf_decoder_destroy(sf_decoder* d);
+int64_t sf_decoder_workspace_bytes(const sf_decoder* d, int64_t B, int32_t S);
+/* tokens_dev (B, S, latent*V) -> poses_dev (B, out_channels, seq_len, V).  SF_E_UNSUPPORTED when a window's activations do
+ * not fit shared memory.  No synchronisation. */
+int sf_decode_poses(const sf_decoder* d, const float* tokens_dev, int64_t B, int32_t S, float* poses_dev,
+                    void* workspace_dev, int64_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------ after the path: aggregation + ranking metrics */
 /* Replaces: the per-video grouping of evaluate_video_level (shopformer_2/evaluate.py:65-118) and
  *   compute_video_level_metrics' aggregation (shopformer_2/utils/metrics.py:148-188): per-video max / mean / 95th

@@ -35,9 +35,9 @@ def main():
     for name, recs in per.items():
         last = recs[-1]                                   # the last captured launch (warm)
         print(f"== {name}  ({len(recs)} launches captured)")
-        for k, (v, u) in sorted(last.items()):
+        for k, vu in sorted(last.items()):
             if not k.startswith("_"):
-                print(f"   {k:84s} {v:>16s} {u}")
+                print(f"   {k:84s} {vu[0]:>16s} {vu[1]}")
         print(f"   DRAM read {last['_read'] / 1e6:.1f} MB  write {last['_write'] / 1e6:.1f} MB")
         if name.startswith("tokenizer2_kernel"):
             traffic["batch"]["A/tc/tokenizer"] = int(last["_dram"])

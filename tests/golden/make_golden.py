@@ -172,6 +172,34 @@ def make_scores(ref1, ref2, ours1, ours2, manifest):
               f"score={float(sc64.mean()):.5f}+-{float(sc64.std()):.5f} ref32err={ref32:.2e} oracle32err={err32:.2e}")
 
 
+def make_decoder(ref1, ref2, manifest):
+    """GCAEDecoder.forward (shopformer/models/gcae.py:369-478; shopformer_2/models/gcae.py:425-534) of the
+    reference in float64 on the reference's own tokens, every config (incl. the bilinear-resize branch where the
+    transposed-conv stack overshoots seq_len)."""
+    out = {}
+    for name in CFG.ALL_CONFIGS:
+        var = CFG.variant_of(name)
+        ref = ref1 if var == 1 else ref2
+        torch.manual_seed(0)
+        r64 = build(ref, name)
+        r64.load_state_dict(synth_state_dict(r64.state_dict(), seed=0), strict=True)
+        r64.eval().double()
+        C, T, V = CFG.input_shape(name)
+        xs, _ = synth_windows(8, T, V, seed=21)
+        xs[4:] = np.random.RandomState(5).randn(4, C, T, V).astype(np.float32)
+        with torch.no_grad():
+            rec, tok = r64.gcae(torch.from_numpy(xs).double())
+            again = r64.gcae.decoder(tok)
+        assert torch.equal(rec, again)
+        out[f"{name}_poses_in"] = xs
+        out[f"{name}_tokens64"] = tok.numpy()
+        out[f"{name}_decoded64"] = rec.numpy()
+        manifest.setdefault("decoder", {})[name] = {"tokens": list(tok.shape), "decoded": list(rec.shape),
+                                                    "stack_length": int(r64.gcae.decoder.layers(torch.zeros(1, r64.gcae.decoder.initial_proj.out_features // V, tok.shape[1], V, dtype=torch.float64)).shape[2])}
+        print(f"[decoder] {name}: tokens {tuple(tok.shape)} -> {tuple(rec.shape)} (conv stack length {manifest['decoder'][name]['stack_length']})")
+    np.savez_compressed(HERE / "decoder.npz", **out)
+
+
 def make_windowing(ref1, ref2, manifest):
     import oracle.windowing_oracle as W
     videos = {f"vid{n:02d}": synth_poselift_video(seed=100 + n, n_frames=300 + 40 * n) for n in range(2)}
@@ -291,6 +319,8 @@ def main():
         make_scores(ref1, ref2, ours1, ours2, manifest)
     if a.only in ("", "windowing"):
         make_windowing(ref1, ref2, manifest)
+    if a.only in ("", "decoder"):
+        make_decoder(ref1, ref2, manifest)
     if a.train or a.only == "train":
         make_trained(ref1, manifest)
     json.dump(manifest, open(mpath, "w"), indent=1)
