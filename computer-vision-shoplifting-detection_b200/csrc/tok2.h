@@ -61,7 +61,9 @@ struct Stage {               // E item (index = position in its TEAM's sequence)
   uint32_t bias_off;         // byte offset of the fp32 bias vector (period `bias_period` columns)
   int32_t bias_period;
   int32_t p0, p1;            // G0: input time steps [p0, p1); XEPI0: output time steps [p0, p1)
+  int32_t pad[2];            // 80 bytes: the kernel loads a stage as five 16-byte words
 };
+static_assert(sizeof(Stage) == 80, "Stage is loaded as five 16-byte words");
 
 enum LoadKind { LD_WEIGHTS = 0, LD_POSES = 1 };
 struct Load {                // L item
@@ -94,6 +96,7 @@ struct Plan {                // kernel parameter (by value)
   // block 0 on the CUDA cores: fp32 tables in the const blob, per 4 output channels (w_x[4], w_y[4], bias[4]):
   // graph-conv weight / bias, and the BN-folded residual 1x1 conv weight / output bias
   uint32_t off_g0tab, off_r0tab;
+  uint32_t off_g0tab_h;      // fp16 operand format: graph-conv table in halves, per 8 output channels (w_x[8], w_y[8], bias[8])
   // The tile program itself travels in the kernel's parameter space (constant bank): the MMA-issuing thread reads
   // descriptors with uniform-datapath constant loads, no shared-memory round trip and no register -> uniform moves.
   Group groups[kMaxGroups];

@@ -3,6 +3,7 @@
 // conv + BN), :242-259 (block), :331-366 (encoder); shopformer_2/models/gcae.py:375-422.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "tok2_build.h"
@@ -149,6 +150,21 @@ void build_static(const Tokenizer& tok, int pool_tokens, bool allow_f16, Static*
       return off;
     };
     s.off_g0tab = table(t0.gcn_w, t0.gcn_b);
+    if (s.f16) {
+      // fp16 format: the graph conv of block 0 runs in packed half arithmetic (HFMA2 with fused ReLU writes the fp16
+      // operand directly: no fp32 -> fp16 conversions, half the table loads); its inputs (|m| of a few units, BN-folded
+      // weights) are far inside fp16's range
+      for (int i = 0; i < t0.cin * t0.cout; ++i)
+        if (!(std::fabs(t0.gcn_w[i]) < 32768.f)) return fail("block-0 graph-conv weight outside fp16's range");
+      s.off_g0tab_h = bl.alloc((size_t)cp * 3 * 2);
+      uint16_t* t = bl.bf(s.off_g0tab_h);
+      for (int o = 0; o < cp; ++o) {
+        uint16_t* e = t + (o / 8) * 24 + (o % 8);
+        e[0] = f2h((o < t0.cout && t0.cin > 0) ? t0.gcn_w[0 * t0.cout + o] : 0.f);
+        e[8] = f2h((o < t0.cout && t0.cin > 1) ? t0.gcn_w[1 * t0.cout + o] : 0.f);
+        e[16] = f2h(o < t0.cout ? t0.gcn_b[o] : 0.f);
+      }
+    }
     s.off_r0tab = table(t0.res_w, t0.out_b);
   }
   for (int b = 1; b < nb; ++b) {
@@ -231,6 +247,11 @@ void build_static(const Tokenizer& tok, int pool_tokens, bool allow_f16, Static*
 
 // ---------------------------------------------------------------------------------------------------------------
 namespace {
+
+// SF_TOK2_SPLIT=1 splits every conversion / block-0 stage between the two epilogue teams instead of alternating whole
+// stages (measured slower: 2.31 vs 1.91 ms -- the epilogue is bound by its instruction stream, not by per-stage latency,
+// and both teams then repeat the pose gather of block 0)
+const bool kSplitStages = getenv("SF_TOK2_SPLIT") != nullptr;
 
 struct Rng {
   int space;        // 0 = shared-memory bytes, 1 = TMEM columns
@@ -348,6 +369,7 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
   pl.off_scale = pl.off_const + st.off_scale;
   pl.off_shift = pl.off_const + st.off_shift;
   pl.off_g0tab = pl.off_const + st.off_g0tab;
+  pl.off_g0tab_h = pl.off_const + st.off_g0tab_h;
   pl.off_r0tab = pl.off_const + st.off_r0tab;
   // the raw poses sit at the END of P: x1 (block 0's output, written last) only reaches them with its final columns
   pl.off_xin = pl.off_P + P_size - xin_alloc;
@@ -394,10 +416,10 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
     }
     it.wr.push_back(tmem_r(dcol, N));
   };
-  int next_team = 0;                 // stages alternate between the two epilogue teams
-  auto new_stage = [&](int type, int flags) -> Stage& {
-    const int team = next_team;
-    next_team ^= 1;
+  int next_team = 0;                 // unsplit stages alternate between the two epilogue teams
+  auto new_stage = [&](int type, int flags, int on_team = -1) -> Stage& {
+    const int team = on_team >= 0 ? on_team : next_team;
+    if (on_team < 0) next_team ^= 1;
     Stage s;
     memset(&s, 0, sizeof(s));
     s.type = type;
@@ -407,15 +429,27 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
     order.push_back(Item{SIDE_E0 + team, (int)pr.stages[team].size() - 1, {}, {}});
     return pr.stages[team].back();
   };
+  // A conversion stage sits on the tile's critical path (MMA group -> stage -> MMA group), so its columns are split between
+  // the two teams, which run their halves at the same time; the consuming group waits for both.  The split point is a
+  // multiple of the bias period (a stage indexes its bias from its own first column).
   auto cvt_stage = [&](int tmem_col, int ncols, uint32_t dst_off, int flags, uint32_t bias_off, int period) {
-    Stage& s = new_stage(ST_CVT, flags);
-    s.tmem_col = tmem_col;
-    s.n_cg = ncols / 16;
-    s.dst_off = dst_off;
-    s.bias_off = bias_off;
-    s.bias_period = period;
-    order.back().rd.push_back(tmem_r(tmem_col, ncols));
-    order.back().wr.push_back(smem_r(dst_off, (uint32_t)(ncols / 8) * kPlane));
+    const int n_cg = ncols / 16;
+    const int unit = (flags & SF_BIAS) && period > 16 ? period / 16 : 1;
+    int n0 = (n_cg + 1) / 2;
+    n0 = (n0 + unit - 1) / unit * unit;
+    auto emit = [&](int cg0, int cgs, int team) {
+      Stage& s = new_stage(ST_CVT, flags, team);
+      s.tmem_col = tmem_col + cg0 * 16;
+      s.n_cg = cgs;
+      s.dst_off = dst_off + (uint32_t)(cg0 * 2) * kPlane;
+      s.bias_off = bias_off;
+      s.bias_period = period;
+      order.back().rd.push_back(tmem_r(tmem_col + cg0 * 16, cgs * 16));
+      order.back().wr.push_back(smem_r(dst_off + (uint32_t)(cg0 * 2) * kPlane, (uint32_t)(cgs * 2) * kPlane));
+    };
+    if (!kSplitStages || n0 >= n_cg) return emit(0, n_cg, -1);
+    emit(0, n0, 0);
+    emit(n0, n_cg - n0, 1);
   };
   auto new_load = [&](int kind, uint32_t dst_off, uint32_t bytes, uint32_t src) {
     Load l;
@@ -470,12 +504,21 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
     for (int i = 0; i < n_sl; ++i) {
       const uint32_t slot = pl.off_Q + (uint32_t)(i % ring0_slots) * ring0_slot;
       const int t0 = i * st0, nt = std::min(st0, T - t0);
-      Stage& s = new_stage(ST_G0, SF_RELU);
-      s.p0 = t0;
-      s.p1 = t0 + nt;
-      s.dst_off = slot;
-      order.back().rd = xin_rng;
-      order.back().wr.push_back(smem_r(slot, (uint32_t)(nt * cp / 8) * kPlane));
+      // both teams work on every slice, half of the output channels each (8-channel planes [c8, c8 + n) of every time
+      // step), so that two slices' MMAs are in flight while the third ring slot is being filled
+      const int chunks = cp / 8, halves = kSplitStages && chunks >= 2 ? 2 : 1;
+      for (int hh = 0; hh < halves; ++hh) {
+        const int c8 = hh * (chunks / halves), n8 = hh + 1 == halves ? chunks - c8 : chunks / halves;
+        Stage& s = new_stage(ST_G0, SF_RELU, halves == 2 ? hh : -1);
+        s.p0 = t0;
+        s.p1 = t0 + nt;
+        s.dst_off = slot;
+        s.tmem_col = c8;                       // G0: first 8-channel plane and number of planes this stage writes
+        s.n_cg = n8;
+        order.back().rd = xin_rng;
+        for (int tl = 0; tl < nt; ++tl)
+          order.back().wr.push_back(smem_r(slot + (uint32_t)(tl * chunks + c8) * kPlane, (uint32_t)n8 * kPlane));
+      }
       new_group();
       tcn_mmas(k, 0, slot, t0, nt, 0);
       drop_empty_group();

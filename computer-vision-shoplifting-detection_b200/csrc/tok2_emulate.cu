@@ -137,6 +137,11 @@ inline uint16_t f2h_sat(float f) {     // round-to-nearest-even fp32 -> fp16, sa
   if ((h & 0x7FFFu) >= 0x7C00u) h = 0x7BFFu;
   return (uint16_t)(sign | h);
 }
+inline float h2f(uint16_t h) {
+  const int e = (h >> 10) & 31, m = h & 0x3FF;
+  float v = e == 0 ? std::ldexp((float)m, -24) : (e == 31 ? (m ? NAN : INFINITY) : std::ldexp((float)(m | 0x400), e - 25));
+  return (h & 0x8000) ? -v : v;
+}
 uint16_t pack_one(float x, bool relu, bool f16) {
   if (relu && !(x > 0.f)) x = 0.f;
   return f16 ? f2h_sat(x) : f2bf(x);
@@ -356,9 +361,20 @@ bool emulate(const Static& st, const Program& pr, const float* poses, int64_t B,
               }
               if (bad) m[0] = m[1] = 0.f;
             }
-            for (int o = 0; o < cp0; ++o) {
-              const float y = std::fmaf(m[0], tabv(g0tab, 0, o), std::fmaf(m[1], tabv(g0tab, 1, o), tabv(g0tab, 2, o)));
-              const uint16_t hb = pack_one(y, true, st.f16);
+            for (int o = s.tmem_col * 8; o < (s.tmem_col + s.n_cg) * 8; ++o) {
+              uint16_t hb;
+              if (st.f16) {
+                // packed half arithmetic of the kernel: two fused multiply-adds, each rounded once to fp16
+                const uint16_t* th = reinterpret_cast<const uint16_t*>(&E.smem[pl.off_g0tab_h]) + (o / 8) * 24 + (o % 8);
+                const double mxh = h2f(f2h_sat(m[0])), myh = h2f(f2h_sat(m[1]));
+                const double inner = h2f(f2h_sat((float)(myh * h2f(th[8]) + h2f(th[16]))));
+                double y = mxh * h2f(th[0]) + inner;
+                if (!(y > 0.0)) y = 0.0;
+                hb = f2h_sat((float)y);
+              } else {
+                const float y = std::fmaf(m[0], tabv(g0tab, 0, o), std::fmaf(m[1], tabv(g0tab, 1, o), tabv(g0tab, 2, o)));
+                hb = pack_one(y, true, false);
+              }
               const int col = (t - s.p0) * cp0 + o;
               memcpy(&E.smem[s.dst_off + (uint32_t)(col / 8) * kPlane + (uint32_t)row * 16 + (uint32_t)(col % 8) * 2], &hb, 2);
             }

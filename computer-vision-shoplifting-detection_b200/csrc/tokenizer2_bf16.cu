@@ -128,6 +128,7 @@ __device__ __forceinline__ void g0_stage(const Plan& pl, const Stage& s, unsigne
   const bool valid = row < pl.rows && my_w < nw;
   const bool two = pl.c_in > 1;
   const int chunks = cp0 / 8;                         // 8-channel granules per time step
+  const int c8_lo = s.tmem_col, c8_hi = s.tmem_col + s.n_cg;     // this stage's share of the output channels
   unsigned char* dst_row = smem + s.dst_off + (size_t)(half * chunks) * kPlane + (size_t)row * 16;
   float2 mx = make_float2(0.f, 0.f), my = make_float2(0.f, 0.f);
   if (valid) {
@@ -159,9 +160,27 @@ __device__ __forceinline__ void g0_stage(const Plan& pl, const Stage& s, unsigne
       atomicOr(&pz[my_w], 1);
     }
   }
+  if (F16) {
+    // packed half arithmetic: y = relu(mx * w_x + (my * w_y + b)), two channels per HFMA2, ReLU fused into the second one
+    uint32_t mx2, my2;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %1;" : "=r"(mx2) : "f"(mx.x));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %1;" : "=r"(my2) : "f"(my.x));
+    const uint4* tabh = reinterpret_cast<const uint4*>(smem + pl.off_g0tab_h);
+#pragma unroll 2
+    for (int c8 = c8_lo; c8 < c8_hi; ++c8) {
+      const uint4 wx = tabh[c8 * 3], wy = tabh[c8 * 3 + 1], bb = tabh[c8 * 3 + 2];
+      uint4 y;
+      asm("{\n.reg .b32 t;\nfma.rn.f16x2 t, %1, %2, %3;\nfma.rn.relu.f16x2 %0, %4, %5, t;\n}" : "=r"(y.x) : "r"(my2), "r"(wy.x), "r"(bb.x), "r"(mx2), "r"(wx.x));
+      asm("{\n.reg .b32 t;\nfma.rn.f16x2 t, %1, %2, %3;\nfma.rn.relu.f16x2 %0, %4, %5, t;\n}" : "=r"(y.y) : "r"(my2), "r"(wy.y), "r"(bb.y), "r"(mx2), "r"(wx.y));
+      asm("{\n.reg .b32 t;\nfma.rn.f16x2 t, %1, %2, %3;\nfma.rn.relu.f16x2 %0, %4, %5, t;\n}" : "=r"(y.z) : "r"(my2), "r"(wy.z), "r"(bb.z), "r"(mx2), "r"(wx.z));
+      asm("{\n.reg .b32 t;\nfma.rn.f16x2 t, %1, %2, %3;\nfma.rn.relu.f16x2 %0, %4, %5, t;\n}" : "=r"(y.w) : "r"(my2), "r"(wy.w), "r"(bb.w), "r"(mx2), "r"(wx.w));
+      *reinterpret_cast<uint4*>(dst_row + (size_t)c8 * kPlane) = y;
+    }
+    return;
+  }
   const float4* tab = reinterpret_cast<const float4*>(smem + pl.off_g0tab);
 #pragma unroll 2
-  for (int c8 = 0; c8 < chunks; ++c8) {
+  for (int c8 = c8_lo; c8 < c8_hi; ++c8) {
     float4 w[6];                                      // (wx, wy, b) of outputs 8 c8 .. +4, then +4 .. +8
 #pragma unroll
     for (int i = 0; i < 6; ++i) w[i] = tab[c8 * 6 + i];
@@ -239,9 +258,24 @@ __device__ __forceinline__ void xepi0_stage(const Plan& pl, const Stage& s, unsi
   }
 }
 
+// The stage tables are read from global memory (L1-resident: 5 KB per team) with one burst of five 16-byte loads per
+// stage.  Reading them field by field from the kernel-parameter constant bank cost ~1.5 k cycles PER STAGE: the 20 KB plan
+// does not fit the constant cache, so every stage paid several dependent constant-cache misses.
+struct Tables {
+  const Stage* stages[kTeams];
+};
+__device__ __forceinline__ void load_stage(Stage* dst, const Stage* src) {
+  static_assert(sizeof(Stage) == 80, "Stage is loaded as five 16-byte words");
+  const uint4* p = reinterpret_cast<const uint4*>(src);
+  uint4* d = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int i = 0; i < 5; ++i) d[i] = __ldg(p + i);
+}
+
 template <bool F16>
 __global__ void __launch_bounds__(kThreads, 1)
-tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ poses, float* __restrict__ tokens, int64_t B_max, const DevCount cnt) {
+tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ poses, float* __restrict__ tokens, int64_t B_max, const DevCount cnt,
+                  const Tables tabs) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint32_t tmem_base_s;
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -354,7 +388,10 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
       const int nw = (int)((B - w_first) < (int64_t)pl.WT ? (B - w_first) : (int64_t)pl.WT);
       int* pz = poison + par * 64;
       for (int e = 0; e < n_st; ++e) {
-        const Stage& s = pl.stages[team][e];
+        Stage s;
+        load_stage(&s, tabs.stages[team] + e);
+        // (every warp of the team waits on the mbarriers itself: try_wait carries a suspend-time hint, see tc_common.cuh; one
+        // polling warp + a named barrier for the other seven measured slower, 1.93 vs 1.87 ms)
         if (s.bar_g) mbar_wait(reinterpret_cast<uint64_t*>(smem + s.bar_g), par);
         if (s.bar_l) mbar_wait(reinterpret_cast<uint64_t*>(smem + s.bar_l), par);
         if (s.bar_eo) mbar_wait(reinterpret_cast<uint64_t*>(smem + s.bar_eo), par);
@@ -365,6 +402,10 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
           const bool relu = s.flags & SF_RELU, bias = s.flags & SF_BIAS;
           const float* bp = reinterpret_cast<const float*>(smem + s.bias_off);
           unsigned char* dst = smem + s.dst_off + (size_t)row * 16;
+          // bias column of this warp's next column group, kept incrementally (no division in the loop): cg advances by 2
+          const int period = s.bias_period > 0 ? s.bias_period : 16;
+          int bcol = half * 16;
+          while (bcol >= period) bcol -= period;
           // this warp's column groups: cg = half, half + 2, ...; two TMEM loads in flight before one wait
           for (int cg0 = half; cg0 < (int)s.n_cg; cg0 += 4) {
             float a[2][16];
@@ -377,7 +418,7 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
               const int cg = cg0 + 2 * b;
               if (cg < (int)s.n_cg) {
                 if (bias) {
-                  const float* b16 = bp + (cg * 16) % s.bias_period;
+                  const float* b16 = bp + bcol;
 #pragma unroll
                   for (int j = 0; j < 4; ++j) {
                     const float4 bb = *reinterpret_cast<const float4*>(b16 + 4 * j);
@@ -389,6 +430,8 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
                 if (relu) store16<true, F16>(dst, cg, a[b]);
                 else store16<false, F16>(dst, cg, a[b]);
               }
+              bcol += 32;
+              while (bcol >= period) bcol -= period;
             }
           }
         } else if (s.type == ST_G0) {
@@ -409,9 +452,10 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
             tmem_ld16(lane_base + (uint32_t)(s.tmem_col + cg * 16), a);
             tmem_ld_wait();
             if (live) {
+              const int t = (cg * 16) / pl.cp_last, c0 = cg * 16 - t * pl.cp_last;      // cp_last is a multiple of 16
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
-                const int col = cg * 16 + j, t = col / pl.cp_last, c = col - t * pl.cp_last;
+                const int c = c0 + j;
                 if (c < pl.c_last) {
                   float y = fmaxf(a[j] + bp[c], 0.f);
                   if (poisoned) y = __int_as_float(0x7fc00000);
@@ -442,6 +486,11 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
 // ---- per-model cache of uploaded programs (one per window length)
 struct Uploaded {
   Program prog;
+  unsigned char* tables_dev = nullptr;       // [stages of team 0][stages of team 1]
+  Tables tabs;
+  ~Uploaded() {
+    if (tables_dev) cudaFree(tables_dev);
+  }
 };
 struct Cache {
   std::mutex mu;
@@ -487,7 +536,19 @@ static Uploaded* tok2_program(const sf_model* m, int T) {
   if (it != s->cache.by_T.end()) return it->second;
   Uploaded* u = new Uploaded();
   t2::build_program(s->st, T, m->max_smem_optin - 2304, &u->prog);   // minus the kernel's static shared memory
-  if (u->prog.ok) u->prog.plan.const_src = s->blob_dev;
+  if (u->prog.ok) {
+    u->prog.plan.const_src = s->blob_dev;
+    const size_t n0 = u->prog.stages[0].size(), n1 = u->prog.stages[1].size();
+    if (cudaMalloc((void**)&u->tables_dev, (n0 + n1) * sizeof(Stage)) != cudaSuccess ||
+        cudaMemcpy(u->tables_dev, u->prog.plan.stages[0], n0 * sizeof(Stage), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(u->tables_dev + n0 * sizeof(Stage), u->prog.plan.stages[1], n1 * sizeof(Stage), cudaMemcpyHostToDevice) != cudaSuccess) {
+      cudaGetLastError();
+      u->prog.ok = false;
+      u->prog.why = "uploading the stage tables failed";
+    }
+    u->tabs.stages[0] = reinterpret_cast<const Stage*>(u->tables_dev);
+    u->tabs.stages[1] = reinterpret_cast<const Stage*>(u->tables_dev + n0 * sizeof(Stage));
+  }
   s->cache.by_T[T] = u;
   return u;
 }
@@ -518,10 +579,10 @@ int launch_tokenizer2(const sf_model* m, const float* poses, int64_t B, int T, f
   const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)m->sm_count);
   if (m->tok2->st.f16) {
     SF_CUDA_OK(cudaFuncSetAttribute(tokenizer2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
-    tokenizer2_kernel<true><<<grid, kThreads, pl.smem_bytes, st>>>(pl, poses, tokens, B, cnt);
+    tokenizer2_kernel<true><<<grid, kThreads, pl.smem_bytes, st>>>(pl, poses, tokens, B, cnt, u->tabs);
   } else {
     SF_CUDA_OK(cudaFuncSetAttribute(tokenizer2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
-    tokenizer2_kernel<false><<<grid, kThreads, pl.smem_bytes, st>>>(pl, poses, tokens, B, cnt);
+    tokenizer2_kernel<false><<<grid, kThreads, pl.smem_bytes, st>>>(pl, poses, tokens, B, cnt, u->tabs);
   }
   SF_CUDA_OK(cudaGetLastError());
   return SF_OK;
