@@ -418,7 +418,7 @@ def main():
 
     # ---- end to end through the C-ABI host-buffer call: inputs in page-locked host memory, H2D + kernels + D2H
     # of every chunk pipelined on a copy + a compute stream inside sf_runner_score
-    chunk = 16384
+    chunk = 8192              # profiles/r2_e2e_sweep*.txt: 8,192-window uploads hide best behind the kernels
     xs_pinned = torch.from_numpy(xs).pin_memory()
     xs = xs_pinned.numpy()
     eng.score_host(xs, precision=a.precision, chunk=chunk)      # allocate the runner and touch every page once (the first device
@@ -428,6 +428,10 @@ def main():
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         host_scores = eng.score_host(xs, precision=a.precision, chunk=chunk)
+        if world > 1:
+            # the path's one collective is part of the end-to-end step: every rank ends up with every rank's scores on the host
+            sharded.my_slice().copy_(torch.from_numpy(host_scores), non_blocking=True)
+            all_host = sharded.gather().cpu()
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -515,9 +519,10 @@ def main():
                           f"inputs ({xs.nbytes / 1e6:.0f} MB) + tokens smaller than the 126 MB L2: not a headline configuration"),
                    "collective": "NCCL all-gather of fp32 scores" if world > 1 else "none (1 GPU)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "api": "sf_runner_score (C ABI, host buffers): 16,384-window chunks of the page-locked pose buffer are DMA-ed on a copy stream "
+                "api": "sf_runner_score (C ABI, host buffers): 8,192-window chunks of the page-locked pose buffer are DMA-ed on a copy stream "
                        "while the previous chunk is scored on the compute stream, scores copied back per chunk; pageable sources are staged "
-                       "through a 4-slot pinned ring", "steps": e2e_steps, **extras},
+                       "through a 4-slot pinned ring" + ("; followed by the NCCL all-gather of the scores and a D2H of the gathered vector" if world > 1 else ""),
+                "steps": e2e_steps, **extras},
         "gpu_launches": 2 * a.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         "parity": {"max_rel_err_vs_cpu_oracle": err, "checked_windows": 256, "tolerance": 1e-3 if a.precision == "fp32" else 1e-2},
         "other_precision": other_line,
@@ -581,6 +586,27 @@ def extra_legs(a, model, eng, xs, T, V, dev):
                                          "evaluate.py:89-99), pageable host tensors", **loop}
     except Exception as exc:
         out["model_call_loop"] = {"error": str(exc)[:200]}
+    # (4) BASELINE configs[4]: 512 streams, one new window per stream per tick (CUDA-graph tick), p50 / p99 latency
+    try:
+        if a.config == "A":
+            from shopformer_b200.streaming import StreamScorer
+            sc = StreamScorer(eng, 512, T, stride, precision=a.precision, use_graph=True)
+            new = np.random.RandomState(0).uniform(100, 900, (512, stride, 17, 3)).astype(np.float32)
+            for _ in range(20):
+                sc.tick(new)
+            lat = []
+            for _ in range(1000):
+                t0 = time.perf_counter()
+                sc.tick(new)
+                lat.append(time.perf_counter() - t0)
+            lat = np.asarray(lat) * 1e3
+            out["streaming_512"] = {"p50_ms": float(np.percentile(lat, 50)), "p99_ms": float(np.percentile(lat, 99)), "mean_ms": float(lat.mean()),
+                                    "windows_per_sec": 512 / (float(lat.mean()) * 1e-3), "ticks": 1000,
+                                    "workload": "BASELINE configs[4]: 512 streams x 1 new window per tick; pinned H2D of the new frames + CUDA-graph replay "
+                                                "(ring shift, normalise, tokenizer, transformer, score) + D2H of the scores, host wall clock per tick"}
+            del sc
+    except Exception as exc:
+        out["streaming_512"] = {"error": str(exc)[:200]}
     # (3) BASELINE configs[2]
     try:
         if a.config == "A":

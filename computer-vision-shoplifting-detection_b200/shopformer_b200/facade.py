@@ -49,10 +49,12 @@ class EngineCacheMixin:
 
     def _apply(self, fn, *a, **kw):
         self.__dict__.pop("_sf_tensor_list", None)
+        self.__dict__.pop("_sf_tok_tensor_list", None)
         return super()._apply(fn, *a, **kw)
 
     def load_state_dict(self, *a, **kw):
         self.__dict__.pop("_sf_tensor_list", None)
+        self.__dict__.pop("_sf_tok_tensor_list", None)
         return super().load_state_dict(*a, **kw)
 
     def _sf_fingerprint(self) -> Tuple:
@@ -70,6 +72,28 @@ class EngineCacheMixin:
             cached[1].close()
         eng = ScoringEngine(self._sf_config(), self.state_dict(), dev)
         self.__dict__["_sf_cache"] = (fp, eng)
+        return eng
+
+    def _sf_tok_engine(self) -> ScoringEngine:
+        """Packed model used for TOKENIZING ONLY while the facade trains with a frozen tokenizer (shopformer_2 stage 2,
+        shopformer_2/models/shopformer.py:94-101): keyed on the encoder's tensors alone, so optimizer steps on the
+        transformer do not invalidate it.  (Its transformer weights may be stale; nothing but `tokenize` is called.)"""
+        enc = self.gcae.encoder
+        d = self.__dict__
+        lst = d.get("_sf_tok_tensor_list")
+        if lst is None:
+            lst = d["_sf_tok_tensor_list"] = list(enc.parameters()) + list(enc.buffers())
+        fp = tuple((t.data_ptr(), t._version) for t in lst)
+        cached = d.get("_sf_tok_cache")
+        if cached is not None and cached[0] == fp:
+            return cached[1]
+        dev = lst[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("shopformer_b200: the model must live on a CUDA device for inference (no CPU fallback)")
+        if cached is not None:
+            cached[1].close()
+        eng = ScoringEngine(self._sf_config(), self.state_dict(), dev)
+        d["_sf_tok_cache"] = (fp, eng)
         return eng
 
     def _sf_config(self) -> EngineConfig:  # pragma: no cover - interface

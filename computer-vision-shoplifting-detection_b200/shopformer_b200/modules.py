@@ -126,9 +126,13 @@ def wants_native(module: nn.Module, x: torch.Tensor) -> bool:
     owner_ref = getattr(module, "_sf_owner", None)
     owner = owner_ref() if owner_ref is not None else None
     if owner is not None and owner.training:
-        # stage-2 training with a frozen, eval-mode tokenizer (shopformer_2 freeze_gcae): the facade's other
-        # parameters change every optimizer step, so a packed native model would be rebuilt every step
-        return False
+        # stage-2 training with a frozen, eval-mode tokenizer (shopformer_2 freeze_gcae): the facade's other parameters
+        # change every optimizer step, so the facade's packed model would be rebuilt every step.  The tokenizer itself
+        # still runs on the native kernels when it is the caller (`_sf_tok_only`): it gets its own packed model keyed on
+        # the encoder's tensors alone (first item).
+        if not (getattr(module, "_sf_tok_only", False) and x.is_cuda and all(not p.requires_grad for p in module.parameters())):
+            return False
+        return True
     if x.is_cuda:
         return True
     if composite_eval_allowed():
@@ -144,7 +148,11 @@ class _Owned:
 
     def _engine(self):
         owner = self._sf_owner() if self._sf_owner is not None else None
-        return owner._sf_engine() if owner is not None else None
+        if owner is None:
+            return None
+        if owner.training and getattr(self, "_sf_tok_only", False):
+            return owner._sf_tok_engine()          # frozen tokenizer inside a training facade
+        return owner._sf_engine()
 
     def _precision(self) -> str:
         owner = self._sf_owner() if self._sf_owner is not None else None
@@ -222,6 +230,7 @@ class STGCNBlock(nn.Module):
 
 class GCAEEncoder(nn.Module, _Owned):
     """Pose window (B,C,T,V) -> tokens (B,S,Cout*V).  ``family`` picks the stride/graph rules."""
+    _sf_tok_only = True        # a frozen, eval-mode tokenizer inside a training facade gets its own packed model
 
     def __init__(self, in_channels: int, hidden_channels: int, out_channels: int, num_keypoints: int,
                  seq_len: int, num_tokens: int, num_layers: int, dropout: float, layout: str, family: int):

@@ -188,3 +188,30 @@ def test_shopformer2_evaluation_loops_on_the_native_kernels(dropin2, monkeypatch
     video_labels = {k: int(i % 2) for i, k in enumerate(video_scores)}
     vm = dropin2["metrics"].compute_video_level_metrics(video_scores, video_labels, "max")
     assert "auc_roc" in vm
+
+
+def test_stage2_training_keeps_the_frozen_tokenizer_on_the_native_kernels(dropin2):
+    """shopformer_2 stage 2 (shopformer_2/train.py:266-429, models/shopformer.py:94-101): GCAE frozen and in eval mode, the
+    transformer trains.  `encode` must reach the native tokenizer (first item) through a packed model keyed
+    on the encoder alone -- optimizer steps on the transformer must not rebuild it -- and give the eval-mode tokens."""
+    import oracle.scoring_oracle as O
+    from helpers import build_model, max_abs_rel, oracle_kwargs
+    model = build_model(None, dropin2, "B").cuda()
+    model.sf_precision = "fp32"
+    x = torch.from_numpy(synth_windows(64, 12, 18, seed=4)[0]).cuda()
+    ref = O.tokenize({k: v.cpu() for k, v in model.state_dict().items()}, x.cpu().double(), oracle_kwargs(model, "B")["strides"]).numpy()
+    model.freeze_gcae()
+    model.train()
+    opt = torch.optim.SGD([p for p in model.parameters() if p.requires_grad], lr=1e-3)
+    engines = set()
+    for _ in range(3):
+        tokens = model.encode(x)                                   # no_grad inside, frozen tokenizer
+        assert not tokens.requires_grad
+        assert max_abs_rel(tokens.cpu().numpy(), ref) < 5e-5       # eval-mode BatchNorm statistics, native fp32 kernels
+        engines.add(id(model.__dict__["_sf_tok_cache"][1]))
+        loss = ((model.transformer(tokens) - tokens) ** 2).mean()
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+    assert len(engines) == 1, "the tokenizer's packed model was rebuilt by transformer updates"
+    assert "_sf_cache" not in model.__dict__, "the full packed model must not be built while training"
