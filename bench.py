@@ -607,6 +607,37 @@ def extra_legs(a, model, eng, xs, T, V, dev):
             del sc
     except Exception as exc:
         out["streaming_512"] = {"error": str(exc)[:200]}
+    # (5) the incumbent GPU number: eager PyTorch (ATen composition of the same modules, eval + no_grad, TF32 off) on this GPU
+    try:
+        os.environ["SHOPFORMER_B200_EAGER_BASELINE"] = "1"
+        tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        eager = {}
+        with torch.no_grad():
+            for bs in (32, 4096, 16384):
+                xb = torch.from_numpy(xs[:bs]).to(dev)
+                for _ in range(2):
+                    ref_scores = model(xb)["normality_score"]
+                torch.cuda.synchronize(dev)
+                reps = 20 if bs == 32 else 5
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record()
+                for _ in range(reps):
+                    ref_scores = model(xb)["normality_score"]
+                g1.record()
+                torch.cuda.synchronize(dev)
+                eager[f"batch_{bs}"] = {"windows_per_sec": bs * reps / (g0.elapsed_time(g1) * 1e-3), "ms_per_call": g0.elapsed_time(g1) / reps}
+            del os.environ["SHOPFORMER_B200_EAGER_BASELINE"]
+            native = model(xb)["normality_score"]
+        eager["max_rel_diff_vs_native"] = float(((native - ref_scores).abs() / ref_scores.abs()).max())
+        out["eager_aten_gpu"] = {"what": "ATen composition of the same nn.Modules (the drop-in's training path in eval mode) on this GPU, device-resident "
+                                         "inputs, fp32, TF32 off: stands in for the reference's eager PyTorch on 1xB200 (the reference itself cannot travel to "
+                                         "the GPU box); it also computes the GCAE decoder output, as the reference's forward does", **eager}
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    except Exception as exc:
+        os.environ.pop("SHOPFORMER_B200_EAGER_BASELINE", None)
+        out["eager_aten_gpu"] = {"error": str(exc)[:200]}
     # (3) BASELINE configs[2]
     try:
         if a.config == "A":

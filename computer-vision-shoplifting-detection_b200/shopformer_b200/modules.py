@@ -119,10 +119,18 @@ def composite_eval_allowed() -> bool:
     return os.environ.get("SHOPFORMER_B200_COMPOSITE_EVAL", "0") == "1"
 
 
+def eager_baseline_forced() -> bool:
+    """Measurement-only switch (bench.py's `eager_aten_gpu` leg): eval-mode inference runs the ATen composition of the
+    same modules on the GPU -- what the reference's eager PyTorch does on the same device -- instead of the native kernels."""
+    return os.environ.get("SHOPFORMER_B200_EAGER_BASELINE", "0") == "1"
+
+
 def wants_native(module: nn.Module, x: torch.Tensor) -> bool:
     """True when this call is eval-mode inference and must run on the sm_100a kernels."""
     if module.training or torch.is_grad_enabled():
         return False                      # training / autograd: ATen composition below
+    if x.is_cuda and eager_baseline_forced():
+        return False
     owner_ref = getattr(module, "_sf_owner", None)
     owner = owner_ref() if owner_ref is not None else None
     if owner is not None and owner.training:
