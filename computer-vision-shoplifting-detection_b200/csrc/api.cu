@@ -145,8 +145,11 @@ static int score_windows_impl(const sf_model* m, const float* poses_dev, int64_t
     if (rc) return rc;
     float* rec = recon_dev ? recon_dev + off * tok_elems : nullptr;
     float* sc = scores_dev + off * score_stride;
-    rc = precision == SF_PREC_BF16 ? launch_transformer_bf16(m, tok, n, S, reduction, rec, sc, st, c)
-                                   : launch_transformer_fp32(m, tok, n, S, reduction, rec, sc, st);
+    // The two kernels only share the fp32 tokens in HBM, so each picks its own path: a shape the tensor-core transformer
+    // does not cover (head width not a multiple of 4, S > 4, d_model > 160) still gets the tensor-core tokenizer.
+    const bool xf_tc = precision == SF_PREC_BF16 && transformer_bf16_supported(m, S);
+    SF_REQUIRE(!cnt.n || xf_tc, SF_E_UNSUPPORTED, "device-side batch size needs the tensor-core transformer");
+    rc = xf_tc ? launch_transformer_bf16(m, tok, n, S, reduction, rec, sc, st, c) : launch_transformer_fp32(m, tok, n, S, reduction, rec, sc, st);
     if (rc) return rc;
   }
   return SF_OK;

@@ -78,6 +78,8 @@ struct Load {                // L item
 
 struct Plan {                // kernel parameter (by value)
   int V, WT, rows, c_in, T0, S_out, c_last, cp_last, d_tok;
+  int T_last, pool;          // time steps of the last block's output; > 0: adaptive average pooling of them to `pool` = S_out tokens
+                             // (shopformer_2/models/gcae.py:406-415)
   int per_w;                 // floats per pose window
   int n_groups, n_loads, n_mma;
   int n_stages[kTeams];

@@ -72,7 +72,7 @@ void build_static(const Tokenizer& tok, int pool_tokens, bool allow_f16, Static*
   s = Static();
   const int V = tok.V, nb = tok.n_blocks;
   auto fail = [&](const char* w) { s.ok = false; s.why = w; };
-  if (pool_tokens > 0) return fail("adaptive pooling");
+  s.pool_tokens = pool_tokens > 0 ? pool_tokens : 0;
   if (tok.c_in > 2) return fail("more than 2 input channels");
   if (nb < 2) return fail("fewer than 2 blocks");
   if (V > 64 || V < 2) return fail("keypoint count outside [2,64]");
@@ -336,7 +336,8 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
     const uint32_t ring = slot_bytes[b] * (uint32_t)std::min(2, nch[b]);
     (x_in_P ? Q_need : P_need) = std::max(x_in_P ? Q_need : P_need, ring);
   }
-  const int S_out = Tout[nb - 1], c_last = st.blk[nb - 1].cout, d_tok = c_last * V;
+  const int T_last = Tout[nb - 1], S_out = st.pool_tokens > 0 ? st.pool_tokens : T_last;
+  const int c_last = st.blk[nb - 1].cout, d_tok = c_last * V;
   const uint32_t stage_bytes = up128((size_t)st.WT * S_out * d_tok * 4);
   const uint32_t P_size = up128(P_need), Q_size = up128(Q_need);
   uint32_t W_size = 0;
@@ -350,6 +351,8 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
   pl.c_in = st.c_in;
   pl.T0 = T;
   pl.S_out = S_out;
+  pl.T_last = T_last;
+  pl.pool = st.pool_tokens;
   pl.c_last = c_last;
   pl.cp_last = st.blk[nb - 1].cp;
   pl.d_tok = d_tok;
@@ -363,7 +366,12 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
   pl.off_P = off; off += P_size;
   pl.off_Q = off; off += Q_size;
   pl.off_W = off; off += up128(W_size);
-  pl.off_stage_tok = off; off += stage_bytes;
+  // The token staging area lives at the START of P (x1 / x3 / block-2 ring): by the token stage every MMA that reads P has
+  // completed (the stage drains the last accumulator), the next tile's poses sit at the END of P, and the next writers of
+  // P's head (block 0's output stages) come after the next tile's first MMA group, which waits for this stage.  The stage
+  // only completes once the bulk store has READ the staging area (cp.async.bulk.wait_group.read in the storing thread).
+  pl.off_stage_tok = pl.off_P;
+  if (stage_bytes + xin_alloc > P_size) return fail("token staging and the pose slot do not both fit the first activation buffer");
   pl.off_ell = pl.off_const + st.off_ell;
   pl.off_hc = pl.off_const + st.off_hc;
   pl.off_scale = pl.off_const + st.off_scale;

@@ -26,6 +26,7 @@ struct Static {
   uint32_t off_g0tab_h = 0;         // fp16 format: the block-0 graph-conv table as halves, per 8 channels (w_x[8], w_y[8], b[8])
   uint32_t off_g0tab = 0, off_r0tab = 0;                            // block 0 (CUDA cores), fp32 [cp0 / 4][w_x[4], w_y[4], b[4]]
   int ell_width = 5;
+  int pool_tokens = 0;              // > 0: AdaptiveAvgPool2d((pool_tokens, V)) after the last block
   bool f16 = true;                  // 16-bit operands (images and activations) are fp16, else bf16; see build_static
   uint32_t const_bytes = 0;
   std::vector<unsigned char> blob;  // const part [0, const_bytes) then the temporal-conv images

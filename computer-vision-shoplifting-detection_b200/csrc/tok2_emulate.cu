@@ -264,6 +264,10 @@ bool emulate(const Static& st, const Program& pr, const float* poses, int64_t B,
           if (s.wait_l >= 0) ok &= bar_ok(pl.bar_l0 + s.wait_l, W.it + 1, &ah);
           if (s.wait_eo >= 0) ok &= bar_ok(pl.bar_e0[tm ^ 1] + s.wait_eo, W.it + 1, &ah);
           if (s.wait_g_prev >= 0 && W.it > 0) ok &= bar_ok(pl.bar_g0 + s.wait_g_prev, W.it, &ah);
+        } else if (W.sub == 3) {
+          ok = !store_pending;                        // cp.async.bulk.wait_group.read
+        } else if (s.type == ST_TOKENS && W.sub == 1) {
+          ok = true;                                  // no barrier before the staging writes any more
         } else {
           ok = named_gen[tm] > warp_gen[tm][w];       // parked at the team's named barrier
         }
@@ -429,13 +433,32 @@ bool emulate(const Static& st, const Program& pr, const float* poses, int64_t B,
         }
       } else {   // ST_TOKENS: drain + barrier, staging writes + barrier, store
         if (W.sub == 0) {
-          if (w == 0 && store_pending) do_store();          // thread 0 waits for the previous store's reads
-          arrive_named();
+          if (store_pending) return fail("emulator: token stage entered while the previous bulk store has not read the staging area");
           W.sub = 1;
           continue;
         } else if (W.sub == 1) {
           float* stg = reinterpret_cast<float*>(&E.smem[pl.off_stage_tok]);
           const float* bp = reinterpret_cast<const float*>(&E.smem[s.bias_off]);
+          if (pl.pool > 0) {
+            for (int j = half; j < pl.pool; j += 2) {
+              const int t0 = (j * pl.T_last) / pl.pool, t1 = ((j + 1) * pl.T_last + pl.pool - 1) / pl.pool;
+              const float inv = 1.f / (float)(t1 - t0);
+              for (int ln = 0; ln < 32; ++ln) {
+                const int row = q * 32 + ln, mw = row / V, mv = row - mw * V;
+                if (!(row < rows && mw < nw)) continue;
+                for (int c = 0; c < pl.c_last; ++c) {
+                  float acc = 0.f;
+                  for (int t = t0; t < t1; ++t) {
+                    const float y = E.tmem[(size_t)row * 512 + s.tmem_col + t * pl.cp_last + c] + bp[c];
+                    acc += y > 0.f ? y : 0.f;
+                  }
+                  float y = acc * inv;
+                  if (poison[par * 64 + mw]) y = NAN;
+                  stg[(mw * pl.S_out + j) * pl.d_tok + c * V + mv] = y;
+                }
+              }
+            }
+          } else
           for (int cg = half; cg < s.n_cg; cg += 2)
             for (int ln = 0; ln < 32; ++ln) {
               const int row = q * 32 + ln, mw = row / V, mv = row - mw * V;
@@ -455,11 +478,14 @@ bool emulate(const Static& st, const Program& pr, const float* poses, int64_t B,
         } else {
           if (w < 2)
             for (int i = w * 32; i < w * 32 + 32; ++i) poison[par * 64 + i] = 0;
-          if (w == 0) {
+          if (w == 0 && W.sub == 2) {
+            // thread 0 issues the bulk store and waits for it to have read the staging area (which aliases activation storage)
             if (store_pending) return fail("emulator: token staging overwritten while a bulk store is pending");
             store_pending = true;
             store_tile = tile;
             store_nw = nw;
+            W.sub = 3;
+            continue;
           }
           finish = true;
         }

@@ -444,9 +444,43 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
           float* stg = reinterpret_cast<float*>(smem + pl.off_stage_tok);
           const bool live = row < rows && my_w < nw;
           const bool poisoned = live && pz[my_w] != 0;
-          // the previous tile's bulk store has read the staging area before anyone overwrites it
-          if (tt == 0) bulk_wait_read();
-          named_bar_sync(1 + team, kTeamWarps * 32);
+          // (the staging area is free: the previous tile's token stage completed only after its bulk store had read it)
+          if (pl.pool > 0) {
+            // adaptive average pooling over time (T_last -> pool tokens): token j = mean of relu(acc + b) over the time
+            // steps [floor(j T / P), ceil((j + 1) T / P)); every time step of a row sits in this thread's TMEM lane, so
+            // the two column halves of the team take alternate output tokens and sum in time order
+            const int cpt = pl.cp_last >> 4;                                // 16-column groups per time step
+            for (int j = half; j < pl.pool; j += 2) {
+              const int t0 = (j * pl.T_last) / pl.pool, t1 = ((j + 1) * pl.T_last + pl.pool - 1) / pl.pool;
+              const float inv = 1.f / (float)(t1 - t0);
+              for (int g = 0; g < cpt; ++g) {
+                float acc[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+                for (int t = t0; t < t1; ++t) {
+                  float a[16];
+                  tmem_ld16(lane_base + (uint32_t)(s.tmem_col + (t * cpt + g) * 16), a);
+                  tmem_ld_wait();
+#pragma unroll
+                  for (int e = 0; e < 16; ++e) {
+                    const int c = g * 16 + e;
+                    acc[e] += fmaxf(a[e] + (c < pl.c_last ? bp[c] : 0.f), 0.f);
+                  }
+                }
+                if (live) {
+#pragma unroll
+                  for (int e = 0; e < 16; ++e) {
+                    const int c = g * 16 + e;
+                    if (c < pl.c_last) {
+                      float y = acc[e] * inv;
+                      if (poisoned) y = __int_as_float(0x7fc00000);
+                      stg[(my_w * pl.S_out + j) * pl.d_tok + c * V + my_v] = y;
+                    }
+                  }
+                }
+              }
+            }
+          } else
           for (int cg = half; cg < (int)s.n_cg; cg += 2) {
             float a[16];
             tmem_ld16(lane_base + (uint32_t)(s.tmem_col + cg * 16), a);
@@ -467,8 +501,10 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
           fence_proxy_async();
           named_bar_sync(1 + team, kTeamWarps * 32);
           if (tt < 64) pz[tt] = 0;          // every thread has read its flag; this buffer is next used two tiles from now
-          if (tt == 0)
+          if (tt == 0) {
             bulk_store(tokens + (size_t)w_first * pl.S_out * pl.d_tok, stg, (uint32_t)nw * (uint32_t)(pl.S_out * pl.d_tok) * 4u);
+            bulk_wait_read();               // the staging area aliases activation storage: free it before the stage completes
+          }
         }
         fence_proxy_async();
         tc_fence_before();

@@ -282,9 +282,32 @@ def test_bf16_path_trained_checkpoint_ranking(golden_dir, dropin1):
 
 
 def test_bf16_unsupported_shapes_are_loud(dropin1, dropin2):
-    model = build_model(dropin1, dropin2, "P").cuda()          # adaptive pooling: not on the tensor-core path
+    """hidden_channels = 128 (shopformer/sweep.py:24-42) is outside both tensor-core tokenizers: an explicit request for
+    the tensor-core path fails loudly, the facades' "auto" policy selects the fp32 kernels."""
+    model = dropin1["models"].Shopformer(**{**CFG.ctor_args("A"), "hidden_channels": 128})
+    model.load_state_dict(synth_state_dict(model.state_dict(), seed=0), strict=True)
+    model = model.eval().cuda()
+    x = torch.from_numpy(synth_windows(4, 24, 17, seed=2)[0]).cuda()
     with pytest.raises(NativeError, match="SF_E_UNSUPPORTED"):
-        model._sf_engine().score_windows(torch.zeros(2, 2, 24, 17, device="cuda"), precision="bf16")
+        model._sf_engine().score_windows(x, precision="bf16")
+    auto = model._sf_engine().score_windows(x, precision="auto")
+    assert torch.equal(auto, model._sf_engine().score_windows(x, precision="fp32"))
+
+
+def test_adaptive_pooling_on_the_tensor_core_path(golden_dir, dropin1, dropin2):
+    """Config P (shopformer_2, num_tokens = 5: AdaptiveAvgPool of the last block's 6 time steps, gcae.py:406-415) runs on
+    tokenizer v2 (pooling in the token stage); its transformer (4 heads of width 34, S = 5) is outside the tensor-core
+    transformer and takes the fp32 kernel -- the two kernels pick their paths independently."""
+    g = np.load(golden_dir / "score_P.npz")
+    model = build_model(dropin1, dropin2, "P").cuda()
+    eng = model._sf_engine()
+    x = torch.from_numpy(g["poses"]).cuda()
+    assert eng.tc_formats(24)[0] == "f16", "config P did not reach tokenizer v2"
+    s, tok, rec = eng.score_windows(x, precision="tc", return_tokens=True, return_recon=True)
+    assert tuple(tok.shape[1:]) == (5, 136)
+    assert max_abs_rel(tok[:g["tokens64"].shape[0]].cpu().numpy(), g["tokens64"]) < 5e-3
+    assert rel_err(s.cpu().numpy(), g["score64"]) < BF16_TOL
+    assert rel_err(eng.score_windows(x, precision="fp32").cpu().numpy(), g["score64"]) < FP32_TOL
 
 
 @pytest.mark.parametrize("name", ["A", "A1", "A12", "B", "C"])
