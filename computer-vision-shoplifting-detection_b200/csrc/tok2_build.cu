@@ -136,7 +136,15 @@ void build_static(const Tokenizer& tok, int pool_tokens, bool allow_f16, Static*
     // need a zero A operand (two 8-column chunks) to clear the block-0 accumulator
     const TokBlock& t0 = tok.blk[0];
     if (s.blk[0].cp > kMaxC0) return fail("block 0 wider than 64 channels");
-    s.off_zero = bl.alloc((size_t)2 * kPlane);
+    // the all-zero A operand that clears block 0's accumulator: the mix image's last K chunk (columns 120..127) is zero in
+    // every row whenever the tile leaves at least 8 padding rows; both K halves of the MMA then read that one plane (LBO = 0)
+    if (kRows - s.rows >= 8) {
+      s.off_zero = s.off_ablk + (uint32_t)(kRows / 8 - 1) * kPlane;
+      s.zero_lbo = 0;
+    } else {
+      s.off_zero = bl.alloc((size_t)2 * kPlane);
+      s.zero_lbo = kPlane;
+    }
     const int cp = s.blk[0].cp;
     auto table = [&](const float* w, const float* bias) {
       const uint32_t off = bl.alloc((size_t)cp * 3 * 4);
@@ -295,7 +303,7 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
   if (cp0 != 16 && cp0 != 32 && cp0 != 64) return fail("block-0 width not 16 / 32 / 64");
 
   // ---- block 0: time steps per CUDA-core slice and the ring of operand slots in Q
-  const uint32_t ring_cap_q = 49152;
+  const uint32_t ring_cap_q = 65536;
   int st0 = 2;                                          // time steps per slice
   while (st0 > 1 && (uint32_t)(st0 * cp0 / 8) * kPlane * 2 > ring_cap_q) --st0;
   const uint32_t ring0_slot = (uint32_t)(st0 * cp0 / 8) * kPlane;
@@ -507,7 +515,7 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
       // clear the accumulator: zero A operand times the (always resident, finite) mix image, 128 columns per MMA
       new_group();
       for (int c0 = 0; c0 < accw; c0 += 128)
-        add_mma(pl.off_const + st.off_zero, kPlane, pl.off_const + st.off_ablk, kPlane, false, std::min(128, accw - c0), c0, false);
+        add_mma(pl.off_const + st.off_zero, st.zero_lbo, pl.off_const + st.off_ablk, kPlane, false, std::min(128, accw - c0), c0, false);
     }
     for (int i = 0; i < n_sl; ++i) {
       const uint32_t slot = pl.off_Q + (uint32_t)(i % ring0_slots) * ring0_slot;

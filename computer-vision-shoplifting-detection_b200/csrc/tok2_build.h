@@ -22,6 +22,7 @@ struct Static {
   std::string why;
   int V = 0, WT = 0, rows = 0, c_in = 0, n_blocks = 0;
   BlockStatic blk[kMaxBlocks];
+  uint32_t zero_lbo = 0;            // leading-dimension byte offset of the zero operand (0: both K halves read one plane)
   uint32_t off_ablk = 0, off_zero = 0, off_ell = 0, off_hc = 0, off_scale = 0, off_shift = 0;
   uint32_t off_g0tab_h = 0;         // fp16 format: the block-0 graph-conv table as halves, per 8 channels (w_x[8], w_y[8], b[8])
   uint32_t off_g0tab = 0, off_r0tab = 0;                            // block 0 (CUDA cores), fp32 [cp0 / 4][w_x[4], w_y[4], b[4]]

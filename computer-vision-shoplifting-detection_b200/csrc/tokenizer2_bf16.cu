@@ -11,6 +11,7 @@
 // Reference maths: shopformer/models/gcae.py:124-154,185-195,242-259,331-366; shopformer_2/models/gcae.py:375-422.
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <map>
 #include <mutex>
 
@@ -263,6 +264,8 @@ __device__ __forceinline__ void xepi0_stage(const Plan& pl, const Stage& s, unsi
 // does not fit the constant cache, so every stage paid several dependent constant-cache misses.
 struct Tables {
   const Stage* stages[kTeams];
+  const Group* groups;
+  const Mma* mma;
 };
 __device__ __forceinline__ void load_stage(Stage* dst, const Stage* src) {
   static_assert(sizeof(Stage) == 80, "Stage is loaded as five 16-byte words");
@@ -276,7 +279,7 @@ template <bool F16>
 __global__ void __launch_bounds__(kThreads, 1)
 tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ poses, float* __restrict__ tokens, int64_t B_max, const DevCount cnt,
                   const Tables tabs) {
-  extern __shared__ __align__(1024) unsigned char smem[];
+  extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint32_t tmem_base_s;
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -328,12 +331,17 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
         tc_fence_after();
         if (timing && it == stamp_it) T2_STAMP(1000 + g);
         if (elect_one()) {
-          // descriptors come straight from the parameter (constant) bank with a warp-uniform index
+          // Descriptors come straight from the parameter (constant) bank with a warp-uniform index (uniform datapath).
+          // A group's issue takes 500-800 cycles however its descriptors are fetched -- measured: prefetching entry i + 1
+          // before issuing MMA i changes nothing (1.82 vs 1.77 ms), and fetching the table with one coalesced load per lane
+          // before the waits + shuffles to lane 0 is far slower (2.64 ms: the MMA then issues from per-thread registers in a
+          // divergent branch) -- the issue rate is paced by the tensor pipe accepting the previous MMA.
           const int end = gr.first + gr.count;
           for (int i = gr.first; i < end; ++i) issue_mma(tmem, pl.mma[i], base16);
           umma_commit(&bars[pl.bar_g0 + g]);
         }
         __syncwarp();
+        if (timing && it == stamp_it) T2_STAMP(3000 + g);
       }
     }
   } else if (warp == 1) {
@@ -571,19 +579,26 @@ static Uploaded* tok2_program(const sf_model* m, int T) {
   auto it = s->cache.by_T.find(T);
   if (it != s->cache.by_T.end()) return it->second;
   Uploaded* u = new Uploaded();
-  t2::build_program(s->st, T, m->max_smem_optin - 2304, &u->prog);   // minus the kernel's static shared memory
+  t2::build_program(s->st, T, m->max_smem_optin - 256, &u->prog);    // minus the kernel's static shared memory (4 bytes) and the 128-byte alignment of the dynamic part
   if (u->prog.ok) {
     u->prog.plan.const_src = s->blob_dev;
     const size_t n0 = u->prog.stages[0].size(), n1 = u->prog.stages[1].size();
-    if (cudaMalloc((void**)&u->tables_dev, (n0 + n1) * sizeof(Stage)) != cudaSuccess ||
+    const size_t ng = u->prog.groups.size(), nm = u->prog.mma.size();
+    const size_t off_g = (n0 + n1) * sizeof(Stage), off_m = off_g + ng * sizeof(Group);
+    if (cudaMalloc((void**)&u->tables_dev, off_m + (nm + 64) * sizeof(Mma)) != cudaSuccess ||
+        cudaMemset(u->tables_dev, 0, off_m + (nm + 64) * sizeof(Mma)) != cudaSuccess ||
         cudaMemcpy(u->tables_dev, u->prog.plan.stages[0], n0 * sizeof(Stage), cudaMemcpyHostToDevice) != cudaSuccess ||
-        cudaMemcpy(u->tables_dev + n0 * sizeof(Stage), u->prog.plan.stages[1], n1 * sizeof(Stage), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaMemcpy(u->tables_dev + n0 * sizeof(Stage), u->prog.plan.stages[1], n1 * sizeof(Stage), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(u->tables_dev + off_g, u->prog.groups.data(), ng * sizeof(Group), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(u->tables_dev + off_m, u->prog.mma.data(), nm * sizeof(Mma), cudaMemcpyHostToDevice) != cudaSuccess) {
       cudaGetLastError();
       u->prog.ok = false;
       u->prog.why = "uploading the stage tables failed";
     }
     u->tabs.stages[0] = reinterpret_cast<const Stage*>(u->tables_dev);
     u->tabs.stages[1] = reinterpret_cast<const Stage*>(u->tables_dev + n0 * sizeof(Stage));
+    u->tabs.groups = reinterpret_cast<const Group*>(u->tables_dev + (n0 + n1) * sizeof(Stage));
+    u->tabs.mma = reinterpret_cast<const Mma*>(u->tables_dev + (n0 + n1) * sizeof(Stage) + u->prog.groups.size() * sizeof(Group));
   }
   s->cache.by_T[T] = u;
   return u;

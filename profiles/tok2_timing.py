@@ -23,10 +23,14 @@ teams = [t[(t[:, 0] >= 2000) & (t[:, 0] < 3000)] for t in teams]
 if len(g) == 0:
     raise SystemExit("no stamps (tokenizer v2 not used for this shape?)")
 t0 = min([g[0, 1]] + [t[0, 1] for t in teams if len(t)])
-print("MMA groups (id, start, delta to previous):")
+done = {int(i) - 3000: int(t) for i, t in a[:512] if 3000 <= i < 4000}
+print("MMA groups (id, issue start, delta to previous start, issue duration = start -> after commit, then wait for the next group's dependencies):")
 prev = g[0, 1]
-for i, t in g:
-    print(f"  G{i-1000:3d}  @{t-t0:7d}  +{t-prev:6d}")
+for k, (i, t) in enumerate(g):
+    gi = int(i) - 1000
+    dur = done.get(gi, t) - t
+    nxt = g[k + 1, 1] - done.get(gi, t) if k + 1 < len(g) and gi in done else 0
+    print(f"  G{gi:3d}  @{t-t0:7d}  +{t-prev:6d}   issue {dur:5d}   wait {nxt:5d}")
     prev = t
 for k, e in enumerate(teams):
     print(f"epilogue team {k} stages (first warp of the team):")
