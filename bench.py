@@ -548,8 +548,9 @@ def extra_legs(a, model, eng, xs, T, V, dev):
         n_tracks = max(8, int(n / ((1515 - T) / stride)))
         tr = synth_tracks(n_tracks, seed=4321)
         kp2 = torch.from_numpy(np.ascontiguousarray(tr["kp"][:, :, :2])).pin_memory().numpy()
-        host = PackedTracks(kp=kp2, frame_no=tr["frame_no"], track_offsets=tr["track_offsets"], track_video=tr["track_video"],
-                            gt=tr["gt"], gt_offsets=tr["gt_offsets"])
+        pin = lambda arr: torch.from_numpy(np.ascontiguousarray(arr)).pin_memory().numpy()      # every bulk array page-locked
+        host = PackedTracks(kp=kp2, frame_no=pin(tr["frame_no"]), track_offsets=tr["track_offsets"], track_video=tr["track_video"],
+                            gt=pin(tr["gt"]), gt_offsets=tr["gt_offsets"])
         kw = dict(add_neck=False, precision=a.precision, chunk=16384)
         for _ in range(2):
             res = eng.score_tracks_host(host, T, stride, **kw)

@@ -194,12 +194,13 @@ extern "C" int64_t sf_score_from_tracks_workspace_bytes(const sf_model* m, const
 // clamps to the count on the device; the count stays in the workspace (`*n_windows_dev_out` points at it).
 static int score_from_tracks_async(const sf_model* m, const sf_tracks* tr, const sf_window_params* p, int32_t precision,
                                    float* scores_dev, int32_t* labels_dev, int32_t* window_track_dev, int32_t* window_start_dev,
-                                   const int64_t** n_windows_dev_out, void* workspace_dev, int64_t workspace_bytes, cudaStream_t st) {
+                                   const int64_t** n_windows_dev_out, void* workspace_dev, int64_t workspace_bytes, cudaStream_t st,
+                                   bool tables_resident = false) {
   const TrackScoreLayout L = track_score_layout(m, tr, p);
   char* ws = (char*)workspace_dev;
   int64_t* n_dev = (int64_t*)(ws + L.count);
   *n_windows_dev_out = n_dev;
-  int rc = window_index(tr, p, labels_dev, window_track_dev, window_start_dev, n_dev, ws + L.win_ws, L.poses - L.win_ws, st);
+  int rc = window_index(tr, p, labels_dev, window_track_dev, window_start_dev, n_dev, ws + L.win_ws, L.poses - L.win_ws, st, tables_resident);
   if (rc) return rc;
   float* poses = (float*)(ws + L.poses);
   for (int64_t off = 0; off < L.cap; off += L.pass) {
@@ -304,6 +305,8 @@ struct sf_runner {
     int64_t win_cap;
     void* ws;
     int64_t ws_bytes;
+    char* tab_pin;         // per-track tables of the group, packed for one H2D copy on the copy stream
+    int64_t tab_cap;
     cudaEvent_t uploaded, done;
   } ts[2];
   uint8_t* gt_dev;
@@ -370,6 +373,7 @@ extern "C" void sf_runner_destroy(sf_runner* r) {
     if (s.out_dev) cudaFree(s.out_dev);
     if (s.out_pin) cudaFreeHost(s.out_pin);
     if (s.ws) cudaFree(s.ws);
+    if (s.tab_pin) cudaFreeHost(s.tab_pin);
     if (s.uploaded) cudaEventDestroy(s.uploaded);
     if (s.done) cudaEventDestroy(s.done);
   }
@@ -511,8 +515,10 @@ extern "C" int sf_runner_score_tracks(sf_runner* r, const sf_tracks* th, const s
     while (t < th->n_tracks) {
       g_begin.push_back(t);
       const int64_t f0 = th->track_offsets_host[t];
+      // the first upload is not hidden behind any kernel: start with a quarter-size group
+      const int64_t target = g_begin.size() == 1 ? std::max<int64_t>(target_frames / 4, 1) : target_frames;
       int e = t + 1;
-      while (e < th->n_tracks && th->track_offsets_host[e + 1] - f0 <= target_frames) ++e;
+      while (e < th->n_tracks && th->track_offsets_host[e + 1] - f0 <= target) ++e;
       t = e;
     }
     g_begin.push_back(th->n_tracks);
@@ -581,6 +587,20 @@ extern "C" int sf_runner_score_tracks(sf_runner* r, const sf_tracks* th, const s
     SF_CUDA_OK(cudaMemcpyAsync(s.kp, th->kp_dev + (size_t)f0 * frame_floats, (size_t)(f1 - f0) * frame_floats * sizeof(float),
                                cudaMemcpyHostToDevice, r->copy_st));
     SF_CUDA_OK(cudaMemcpyAsync(s.frame_no, th->frame_no_dev + f0, (size_t)(f1 - f0) * sizeof(int32_t), cudaMemcpyHostToDevice, r->copy_st));
+    if (G.cap > 0) {
+      // the group's per-track tables go through pinned staging on the copy stream too: a pageable copy on the compute
+      // stream would make the host wait for the previous group's kernels before it can enqueue this one
+      const int64_t tb = window_tables_bytes(&G.tr, p);
+      if (tb > s.tab_cap) {
+        if (s.tab_pin) cudaFreeHost(s.tab_pin);
+        s.tab_pin = nullptr;
+        s.tab_cap = 0;
+        SF_CUDA_OK(cudaMallocHost((void**)&s.tab_pin, (size_t)(tb + tb / 4)));
+        s.tab_cap = tb + tb / 4;
+      }
+      window_tables_pack(&G.tr, p, s.tab_pin);
+      SF_CUDA_OK(cudaMemcpyAsync(s.ws, s.tab_pin, (size_t)tb, cudaMemcpyHostToDevice, r->copy_st));
+    }
     SF_CUDA_OK(cudaEventRecord(s.uploaded, r->copy_st));
     return SF_OK;
   };
@@ -617,7 +637,7 @@ extern "C" int sf_runner_score_tracks(sf_runner* r, const sf_tracks* th, const s
       int64_t n_copy = 0;
       if (async) {
         const int64_t* n_dev = nullptr;
-        int rc2 = score_from_tracks_async(m, &G.tr, p, precision, sc, lb, wt, wsr, &n_dev, s.ws, s.ws_bytes, r->comp_st);
+        int rc2 = score_from_tracks_async(m, &G.tr, p, precision, sc, lb, wt, wsr, &n_dev, s.ws, s.ws_bytes, r->comp_st, true);
         if (rc2) return rc2;
         SF_CUDA_OK(cudaMemcpyAsync(s.out_pin + wc * 16, n_dev, sizeof(int64_t), cudaMemcpyDeviceToHost, r->comp_st));
         G.n = -1;                                      // read from the pinned tail when the group is drained

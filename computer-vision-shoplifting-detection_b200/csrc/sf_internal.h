@@ -186,7 +186,10 @@ int token_len(const sf_model* m, int T);
 // windowing.cu: the index (flag / scan / compact) and gather halves of sf_window_normalize
 int64_t window_candidates(const sf_tracks* tr, const sf_window_params* p);
 int window_index(const sf_tracks* tr, const sf_window_params* p, int32_t* labels_dev, int32_t* window_track_dev,
-                 int32_t* window_start_dev, int64_t* n_windows_dev, void* workspace_dev, int64_t workspace_bytes, cudaStream_t st);
+                 int32_t* window_start_dev, int64_t* n_windows_dev, void* workspace_dev, int64_t workspace_bytes, cudaStream_t st,
+                 bool tables_resident = false);
+int64_t window_tables_bytes(const sf_tracks* tr, const sf_window_params* p);
+void window_tables_pack(const sf_tracks* tr, const sf_window_params* p, char* host_dst);
 int window_gather(const sf_tracks* tr, const sf_window_params* p, const int32_t* window_track_dev, const int32_t* window_start_dev,
                   const int64_t* n_windows_dev, int64_t w_begin, int64_t w_cap, float* poses_dev, int32_t* frame_idx_dev,
                   void* workspace_dev, cudaStream_t st);

@@ -21,6 +21,7 @@
 //             HBM with 16-byte streaming stores.  No division or modulo per element: every lane
 //             walks (t, v) incrementally.
 #include <algorithm>
+#include <cstring>
 #include <vector>
 
 #include "sf_internal.h"
@@ -477,8 +478,32 @@ static void fill_ctx(const sf_tracks* tr, const sf_window_params* p, const WsLay
 
 // K_flag / K_scan / K_compact: which windows exist, in the reference's order, with their labels.  The per-track tables
 // are uploaded into the workspace (they stay there for window_gather).  No synchronisation.
+// The per-track tables (track offsets, candidate offsets, track -> video, ground-truth offsets) occupy the head of the
+// workspace.  A caller that uploads them itself (the host-track runner: through pinned staging on its copy stream, so that
+// no pageable copy ever sits on the compute stream) packs them with window_tables_pack and passes tables_resident.
+int64_t window_tables_bytes(const sf_tracks* tr, const sf_window_params* p) { return (int64_t)layout(tr, p).flag; }
+
+void window_tables_pack(const sf_tracks* tr, const sf_window_params* p, char* host_dst) {
+  const WsLayout L = layout(tr, p);
+  memset(host_dst, 0, L.flag);
+  memcpy(host_dst + L.track_off, tr->track_offsets_host, sizeof(int64_t) * (tr->n_tracks + 1));
+  int64_t n = 0;
+  int64_t* cand = reinterpret_cast<int64_t*>(host_dst + L.cand_off);
+  cand[0] = 0;
+  for (int i = 0; i < tr->n_tracks; ++i) {
+    const int64_t len = tr->track_offsets_host[i + 1] - tr->track_offsets_host[i];
+    if (len >= p->seq_len) n += (len - p->seq_len) / p->stride + 1;
+    cand[i + 1] = n;
+  }
+  if (tr->gt_dev && tr->gt_offsets_host && tr->track_video_host && tr->n_videos > 0) {
+    memcpy(host_dst + L.track_video, tr->track_video_host, sizeof(int32_t) * tr->n_tracks);
+    memcpy(host_dst + L.gt_off, tr->gt_offsets_host, sizeof(int64_t) * (tr->n_videos + 1));
+  }
+}
+
 int window_index(const sf_tracks* tr, const sf_window_params* p, int32_t* labels_dev, int32_t* window_track_dev,
-                 int32_t* window_start_dev, int64_t* n_windows_dev, void* workspace_dev, int64_t workspace_bytes, cudaStream_t st) {
+                 int32_t* window_start_dev, int64_t* n_windows_dev, void* workspace_dev, int64_t workspace_bytes, cudaStream_t st,
+                 bool tables_resident) {
   int rc = check(tr, p);
   if (rc != SF_OK) return rc;
   SF_REQUIRE(n_windows_dev, SF_E_INVALID, "windowing: n_windows_dev is required");
@@ -491,15 +516,17 @@ int window_index(const sf_tracks* tr, const sf_window_params* p, int32_t* labels
   }
   SF_REQUIRE(labels_dev && window_track_dev && window_start_dev, SF_E_INVALID, "windowing: null output");
   char* ws = (char*)workspace_dev;
-  std::vector<int64_t> cand_off;
-  candidates(tr, p, &cand_off);
-  SF_CUDA_OK(cudaMemcpyAsync(ws + L.track_off, tr->track_offsets_host, sizeof(int64_t) * (tr->n_tracks + 1), cudaMemcpyHostToDevice, st));
-  // cand_off lives on this stack frame: a pageable source is staged before the call returns
-  SF_CUDA_OK(cudaMemcpyAsync(ws + L.cand_off, cand_off.data(), sizeof(int64_t) * (tr->n_tracks + 1), cudaMemcpyHostToDevice, st));
-  const bool has_gt = tr->gt_dev && tr->gt_offsets_host && tr->track_video_host && tr->n_videos > 0;
-  if (has_gt) {
-    SF_CUDA_OK(cudaMemcpyAsync(ws + L.track_video, tr->track_video_host, sizeof(int32_t) * tr->n_tracks, cudaMemcpyHostToDevice, st));
-    SF_CUDA_OK(cudaMemcpyAsync(ws + L.gt_off, tr->gt_offsets_host, sizeof(int64_t) * (tr->n_videos + 1), cudaMemcpyHostToDevice, st));
+  if (!tables_resident) {
+    std::vector<int64_t> cand_off;
+    candidates(tr, p, &cand_off);
+    SF_CUDA_OK(cudaMemcpyAsync(ws + L.track_off, tr->track_offsets_host, sizeof(int64_t) * (tr->n_tracks + 1), cudaMemcpyHostToDevice, st));
+    // cand_off lives on this stack frame: a pageable source is staged before the call returns
+    SF_CUDA_OK(cudaMemcpyAsync(ws + L.cand_off, cand_off.data(), sizeof(int64_t) * (tr->n_tracks + 1), cudaMemcpyHostToDevice, st));
+    const bool has_gt = tr->gt_dev && tr->gt_offsets_host && tr->track_video_host && tr->n_videos > 0;
+    if (has_gt) {
+      SF_CUDA_OK(cudaMemcpyAsync(ws + L.track_video, tr->track_video_host, sizeof(int32_t) * tr->n_tracks, cudaMemcpyHostToDevice, st));
+      SF_CUDA_OK(cudaMemcpyAsync(ws + L.gt_off, tr->gt_offsets_host, sizeof(int64_t) * (tr->n_videos + 1), cudaMemcpyHostToDevice, st));
+    }
   }
   WinCtx cx;
   fill_ctx(tr, p, L, ws, &cx);
@@ -571,7 +598,7 @@ extern "C" int sf_window_normalize(const sf_tracks* tr, const sf_window_params* 
     if (rc != SF_OK) return rc;
   }
   SF_CUDA_OK(guard.enter(dev));
-  rc = window_index(tr, p, labels_dev, window_track_dev, window_start_dev, n_windows_dev, workspace_dev, workspace_bytes, st);
+  rc = window_index(tr, p, labels_dev, window_track_dev, window_start_dev, n_windows_dev, workspace_dev, workspace_bytes, st, false);
   if (rc != SF_OK) return rc;
   const int64_t n_cand = candidates(tr, p, nullptr);
   if (n_cand > 0) {

@@ -12,7 +12,8 @@ n = 65536
 xs = torch.from_numpy(synth_windows(n, 24, 17, seed=1)[0]).pin_memory().numpy()
 tr = synth_tracks(int(n / ((1515 - 24) / 12)), seed=4321)
 kp2 = torch.from_numpy(np.ascontiguousarray(tr["kp"][:, :, :2])).pin_memory().numpy()
-host = PackedTracks(kp=kp2, frame_no=tr["frame_no"], track_offsets=tr["track_offsets"], track_video=tr["track_video"], gt=tr["gt"], gt_offsets=tr["gt_offsets"])
+pin = lambda arr: torch.from_numpy(np.ascontiguousarray(arr)).pin_memory().numpy()
+host = PackedTracks(kp=kp2, frame_no=pin(tr["frame_no"]), track_offsets=tr["track_offsets"], track_video=tr["track_video"], gt=pin(tr["gt"]), gt_offsets=tr["gt_offsets"])
 for chunk in (4096, 8192, 16384, 32768, 65536):
     for _ in range(2):
         eng.score_host(xs, precision="tc", chunk=chunk)
