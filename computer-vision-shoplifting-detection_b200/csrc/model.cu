@@ -485,7 +485,8 @@ extern "C" int sf_model_create(const sf_config* cfg, int32_t n_tensors, const ch
   };
   // attention block: q, k, v into TMEM columns [0,dp) [dp,2dp) [2dp,3dp), attention epilogue -> Hop, out_proj -> stream
   auto attention = [&](const AttnOff& at, int kv_src) {
-    op_gemm(XS_AOP, at.qkv, 0, d, 0, d, dp, dp, 0, 0, XE_NONE, 0, true);
+    // q, k, v are issued in one phase (XfOp::chain = 3): only v's completion is waited for
+    prog[op_gemm(XS_AOP, at.qkv, 0, d, 0, d, dp, dp, 0, 0, XE_NONE, 0, true)].op.chain = 3;
     op_gemm(kv_src, at.qkv, d, d, 0, d, dp, dp, dp, 0, XE_NONE, 0, true);
     op_gemm(kv_src, at.qkv, 2 * d, d, 0, d, dp, dp, 2 * dp, 0, XE_ATTN, 0, true);
     return op_gemm(XS_HOP, at.out, 0, d, 0, d, dp, dp, 0, 0, XE_STREAM_ADD, 0, true);

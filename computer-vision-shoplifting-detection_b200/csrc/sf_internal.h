@@ -139,7 +139,7 @@ enum XfEpi { XE_NONE = 0, XE_ATTN = 1, XE_ACT_H = 2, XE_STREAM_ADD = 3, XE_STREA
 enum XfPost { XP_NONE = 0, XP_COPY_TO_AOP = 1, XP_LN_INPLACE_TO_AOP = 2, XP_LN_TO_AOP = 3, XP_LN_TO_MEM = 4, XP_LN_SCORE = 5 };
 enum XfSrc { XS_AOP = 0, XS_HOP = 1, XS_MEM = 2 };
 struct XfOp {
-  int32_t type, init_mode, a_src, K, N, tmem_col, accumulate, epi, act, post, also_mem, h_col;
+  int32_t type, init_mode, a_src, K, N, tmem_col, accumulate, epi, act, post, also_mem, chain;   // chain > 1: this GEMM and the next chain-1 GEMMs (no epilogue of their own) are issued in ONE phase
   const uint16_t* w;        // [K/8][N][8] 16-bit operand image (K-major B; fp16 or bf16, XfProgram::f16)
   const float* bias;        // [N] zero padded
   const float* ln_g;

@@ -18,6 +18,7 @@
 //     processed in chunks of <= 128 columns with the second GEMM accumulating in TMEM across chunks;
 //   * the squared error against the score target is reduced in the last epilogue: only B floats are written.
 #include <algorithm>
+#include <cstdlib>
 
 #include "sf_internal.h"
 #include "tc_common.cuh"
@@ -61,6 +62,75 @@ template <bool F16>
 __device__ __forceinline__ uint4 pack8(const float* f) {
   return make_uint4(pack_op2<F16>(f[0], f[1]), pack_op2<F16>(f[2], f[3]), pack_op2<F16>(f[4], f[5]), pack_op2<F16>(f[6], f[7]));
 }
+// packed fp32 pairs (sm_100 FFMA2 / FADD2 / FMUL2): two exact fp32 operations per issue slot -- the epilogues are bound by
+// their instruction stream, and every result is bit-identical to the scalar form
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n"
+      ".reg .b64 ra, rb, rc, rd;\n"
+      "mov.b64 ra, {%2, %3};\n"
+      "mov.b64 rb, {%4, %5};\n"
+      "mov.b64 rc, {%6, %7};\n"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n"
+      "mov.b64 {%0, %1}, rd;\n"
+      "}\n"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n"
+      ".reg .b64 ra, rb, rd;\n"
+      "mov.b64 ra, {%2, %3};\n"
+      "mov.b64 rb, {%4, %5};\n"
+      "add.rn.f32x2 rd, ra, rb;\n"
+      "mov.b64 {%0, %1}, rd;\n"
+      "}\n"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n"
+      ".reg .b64 ra, rb, rd;\n"
+      "mov.b64 ra, {%2, %3};\n"
+      "mov.b64 rb, {%4, %5};\n"
+      "sub.rn.f32x2 rd, ra, rb;\n"
+      "mov.b64 {%0, %1}, rd;\n"
+      "}\n"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n"
+      ".reg .b64 ra, rb, rd;\n"
+      "mov.b64 ra, {%2, %3};\n"
+      "mov.b64 rb, {%4, %5};\n"
+      "mul.rn.f32x2 rd, ra, rb;\n"
+      "mov.b64 {%0, %1}, rd;\n"
+      "}\n"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 pr(const float* p) { return make_float2(p[0], p[1]); }
+__device__ __forceinline__ void put(float* p, float2 v) { p[0] = v.x; p[1] = v.y; }
+// fp32 pairs -> packed 16-bit pair through ReLU (one conversion instruction, no separate max)
+template <bool F16>
+__device__ __forceinline__ uint32_t pack_relu2(float lo, float hi) {
+  uint32_t d;
+  if (F16) asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+template <bool F16>
+__device__ __forceinline__ uint4 pack8_relu(const float* f) {
+  return make_uint4(pack_relu2<F16>(f[0], f[1]), pack_relu2<F16>(f[2], f[3]), pack_relu2<F16>(f[4], f[5]), pack_relu2<F16>(f[6], f[7]));
+}
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 
 template <int KS>
@@ -74,6 +144,22 @@ __device__ __forceinline__ void gemm_issue(uint32_t d, uint32_t alo0, uint32_t b
   }
 #pragma unroll
   for (int ks = 0; ks < KS; ++ks) umma_bf16(d, desc_join(al[ks]), desc_join(bl[ks]), idesc, (accumulate || ks > 0) ? 1u : 0u);
+}
+
+// busy poll without a suspend hint: lowest wake-up latency when nothing else on the SM wants the issue slots
+__device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.b32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
 }
 
 // 16 consecutive floats of a 16-byte aligned global row; columns >= lim (lim % 4 == 0) or !ok read as zero
@@ -116,14 +202,20 @@ __device__ __forceinline__ void store_group(unsigned char* buf, int plane, int r
   *reinterpret_cast<uint4*>(buf + (size_t)(2 * g + 1) * plane + row * 16) = pack8<F16>(y + 8);
 }
 
+template <bool F16>
+__device__ __forceinline__ void store_group_relu(unsigned char* buf, int plane, int row, int g, const float* y) {
+  *reinterpret_cast<uint4*>(buf + (size_t)(2 * g) * plane + row * 16) = pack8_relu<F16>(y);
+  *reinterpret_cast<uint4*>(buf + (size_t)(2 * g + 1) * plane + row * 16) = pack8_relu<F16>(y + 8);
+}
+
 // F16: the 16-bit operands (activations written by the epilogues and the weight images) are fp16 instead of bf16
 template <bool F16>
 __global__ void __launch_bounds__(kThreads, 1)
 transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo, const __grid_constant__ Transformer xf,
                         const float* __restrict__ tokens, int64_t B_max, int reduction, float* __restrict__ recon_out,
-                        float* __restrict__ scores, const DevCount cnt) {
+                        float* __restrict__ scores, const DevCount cnt, const int flags) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ uint64_t bar, wbar[2];            // MMA completion; TMA completion per weight-ring slot
+  __shared__ uint64_t bar, cbar, wbar[2];      // MMA completion (phase / first GEMM of a chain); TMA completion per weight-ring slot
   __shared__ uint32_t tmem_base_s;
   unsigned char* sAop = smem + geo.off_aop;
   unsigned char* sHop = smem + geo.off_hop;
@@ -143,6 +235,7 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
   if (warp == 0) tmem_alloc(&tmem_base_s, 512);
   if (threadIdx.x == 0) {
     mbar_init(&bar, 1);
+    mbar_init(&cbar, 1);
     mbar_init(&wbar[0], 1);
     mbar_init(&wbar[1], 1);
     fence_mbar_init();
@@ -155,7 +248,7 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
-  uint32_t parity = 0, wpar = 0;
+  uint32_t parity = 0, wpar = 0, cpar = 0;
   const bool timing = g_xf_timing_on && blockIdx.x == 0;
   int stamp_i = 0;
 
@@ -210,7 +303,7 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
     }
 
     for (int oi = 0; oi < n_ops; ++oi) {
-      const XfOp op = ops[oi];
+      XfOp op = ops[oi];
       int post = op.post;
       XF_STAMP(oi * 8 + 0);
       const float* pbase = nullptr;              // staged parameters of this op (GEMM ops only)
@@ -245,47 +338,99 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
       }
       // ------------------------------------------------------------------ GEMM + epilogue
       if (op.type == XF_GEMM) {
-        if (warp == 0) mbar_wait(&wbar[slot], (wpar >> slot) & 1u);      // this op's weights + parameters have landed
+        // One MMA phase = `nch` GEMMs (1, or q / k / v of an attention block: XfOp::chain) issued back to back; only the
+        // last one's completion is waited for.  Two weight slots: GEMM c of the phase uses slot ^ (c & 1); its image is
+        // staged (TMA) as soon as the slot's previous reader has completed -- the GEMM before this phase for c = 1
+        // (complete since its epilogue ran), GEMM c - 2 of this phase for c = 2 (its own commit on `cbar`).
+        const int nch = (flags & 4) ? 1 : (op.chain > 1 ? op.chain : 1);
+        if (warp == 0) mbar_wait(&wbar[slot], (wpar >> slot) & 1u);      // the first GEMM's weights + parameters have landed
         wpar ^= 1u << slot;
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
         XF_STAMP(oi * 8 + 1);
-        if (warp == 0 && elect_one()) {            // uniform-datapath issue: descriptors live in uniform registers
+        auto issue = [&](const XfOp& o, int sl, uint64_t* commit_to) {     // elected thread of warp 0
           tc_fence_after();
-          const unsigned char* a = op.a_src == XS_AOP ? sAop : (op.a_src == XS_HOP ? sHop : sMem);
-          const uint32_t idesc = make_idesc(128, op.N, false, F16, F16);
-          const uint32_t w_plane = (uint32_t)op.N * 16u;
+          const unsigned char* a = o.a_src == XS_AOP ? sAop : (o.a_src == XS_HOP ? sHop : sMem);
+          const uint32_t idesc = make_idesc(128, o.N, false, F16, F16);
+          const uint32_t w_plane = (uint32_t)o.N * 16u;
           uint32_t alo = desc_lo(smem_u32(a), (uint32_t)plane);
-          uint32_t blo = desc_lo(smem_u32(sW + slot * geo.slot_bytes), w_plane);
-          const uint32_t dd = tmem + (uint32_t)op.tmem_col, astep = (2u * (uint32_t)plane) >> 4, bstep = (2u * w_plane) >> 4;
-          const uint32_t accf = op.accumulate ? 1u : 0u;
-          switch (op.K >> 4) {
+          uint32_t blo = desc_lo(smem_u32(sW + sl * geo.slot_bytes), w_plane);
+          const uint32_t dd = tmem + (uint32_t)o.tmem_col, astep = (2u * (uint32_t)plane) >> 4, bstep = (2u * w_plane) >> 4;
+          const uint32_t accf = o.accumulate ? 1u : 0u;
+          switch (o.K >> 4) {
             case 9: gemm_issue<9>(dd, alo, blo, astep, bstep, idesc, accf); break;
             case 4: gemm_issue<4>(dd, alo, blo, astep, bstep, idesc, accf); break;
             case 8: gemm_issue<8>(dd, alo, blo, astep, bstep, idesc, accf); break;
             case 10: gemm_issue<10>(dd, alo, blo, astep, bstep, idesc, accf); break;
             case 2: gemm_issue<2>(dd, alo, blo, astep, bstep, idesc, accf); break;
             default:
-              for (int ks = 0; ks < (op.K >> 4); ++ks) {
+              for (int ks = 0; ks < (o.K >> 4); ++ks) {
                 umma_bf16(dd, desc_join(alo), desc_join(blo), idesc, (accf || ks > 0) ? 1u : 0u);
                 alo += astep;
                 blo += bstep;
               }
           }
-          umma_commit(&bar);
-          XF_STAMP(oi * 8 + 2);
+          if (commit_to) umma_commit(commit_to);
+        };
+        if (nch == 1) {
+          if (warp == 0 && elect_one()) {            // uniform-datapath issue: descriptors live in uniform registers
+            issue(op, slot, &bar);
+            XF_STAMP(oi * 8 + 2);
+          }
+          {   // prefetch the next GEMM's weights into the other ring slot (its previous user has completed)
+            int nx = oi + 1;
+            while (nx < n_ops && ops[nx].type != XF_GEMM) ++nx;
+            if (nx < n_ops) stage_op(nx, slot ^ 1);
+          }
+          pbase = reinterpret_cast<const float*>(sW + slot * geo.slot_bytes + geo.param_off);
+          slot ^= 1;
+        } else {
+          // chain of three (nch == 3 is the only other value the host emits): slots  s, s^1, s
+          if (warp == 0) {
+            stage_op(oi + 1, slot ^ 1);                                   // k: the slot of the GEMM before this phase
+            __syncwarp();
+            if (elect_one()) issue(op, slot, &cbar);                      // q
+            __syncwarp();
+            mbar_wait(&wbar[slot ^ 1], (wpar >> (slot ^ 1)) & 1u);
+            if (elect_one()) issue(ops[oi + 1], slot ^ 1, nullptr);       // k
+            __syncwarp();
+            mbar_wait(&cbar, cpar);                                       // q has completed: its slot takes v
+            stage_op(oi + 2, slot);
+            __syncwarp();
+            mbar_wait(&wbar[slot], (wpar >> slot) & 1u);                  // (wpar was flipped for q above: this is v's phase)
+            if (elect_one()) {
+              issue(ops[oi + 2], slot, &bar);                             // v
+              XF_STAMP(oi * 8 + 2);
+            }
+            __syncwarp();
+          }
+          cpar ^= 1u;
+          // every warp reads v's parameter block (q / v bias): observe its TMA completion directly
+          if (warp != 0) mbar_wait(&wbar[slot], (wpar >> slot) & 1u);
+          wpar ^= 1u << (slot ^ 1);                                       // k
+          wpar ^= 1u << slot;                                             // v
+          pbase = reinterpret_cast<const float*>(sW + slot * geo.slot_bytes + geo.param_off);
+          oi += 2;
+          op = ops[oi];
+          post = op.post;
+          slot ^= 1;                                                      // three GEMMs = one net toggle
         }
-        {   // prefetch the next GEMM's weights into the other ring slot (its previous user has completed)
+        if (flags & 1) {
+          if (warp == 0) {                           // one polling warp; the others block in the hardware barrier
+            if (flags & 2) mbar_spin(&bar, parity);
+            else mbar_wait(&bar, parity);
+          }
+          __syncthreads();
+        } else {
+          mbar_wait(&bar, parity);                   // every warp sleeps on the mbarrier itself (measured faster than one
+        }                                            // polling warp + bar.sync: 1.197 -> 1.144 ms per 65,536 windows)
+        parity ^= 1;
+        if (nch > 1) {   // the next GEMM (out_proj) goes to the slot k used; k has completed with v
           int nx = oi + 1;
           while (nx < n_ops && ops[nx].type != XF_GEMM) ++nx;
-          if (nx < n_ops) stage_op(nx, slot ^ 1);
+          if (nx < n_ops) stage_op(nx, slot);
         }
-        pbase = reinterpret_cast<const float*>(sW + slot * geo.slot_bytes + geo.param_off);
-        slot ^= 1;
-        if (warp == 0) mbar_wait(&bar, parity);      // one polling warp; the others block in the hardware barrier
-        __syncthreads();
-        parity ^= 1;
         tc_fence_after();
         XF_STAMP(oi * 8 + 3);
 
@@ -308,11 +453,13 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
             const int f_lo = (cp * n4) / P, f_hi = ((cp + 1) * n4) / P;
             const int c0 = h * hd + 4 * f_lo, ncol = 4 * (f_hi - f_lo);
             float sc[kSMax];
+            float2 sc2[kSMax];
 #pragma unroll
-            for (int j = 0; j < kSMax; ++j) sc[j] = 0.f;
+            for (int j = 0; j < kSMax; ++j) sc2[j] = make_float2(0.f, 0.f);
             // 16 accumulator columns per TMEM round trip (columns past the range are loaded but not used).
             // The key bias adds the same q.b_k to every logit of a row -- softmax cancels it, so it is skipped.
-            // Own token first, then the other S-1 tokens of the window in rotating order (S-1 shuffles per value).
+            // Own token first, then the other S-1 tokens of the window in rotating order (S-1 shuffles per value);
+            // products accumulate as fp32 pairs (even / odd columns), summed once at the end.
             for (int c16 = 0; c16 < ncol; c16 += 16) {
               float q16[16], k16[16];
               tmem_ld16(tmem + lane_addr + (uint32_t)(c0 + c16), q16);
@@ -322,19 +469,24 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
               for (int e4 = 0; e4 < 4; ++e4)
                 if (c16 + 4 * e4 < ncol) {
                   const float4 bq4 = *reinterpret_cast<const float4*>(bq + c0 + c16 + 4 * e4);
-                  float* q4 = q16 + 4 * e4;
-                  float* k4 = k16 + 4 * e4;
-                  q4[0] += bq4.x; q4[1] += bq4.y; q4[2] += bq4.z; q4[3] += bq4.w;
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) sc[0] = fmaf(q4[e], k4[e], sc[0]);
+                  const float* k4 = k16 + 4 * e4;
+                  const float2 qa = add2(pr(q16 + 4 * e4), make_float2(bq4.x, bq4.y));
+                  const float2 qb = add2(pr(q16 + 4 * e4 + 2), make_float2(bq4.z, bq4.w));
+                  sc2[0] = fma2(qa, pr(k4), sc2[0]);
+                  sc2[0] = fma2(qb, pr(k4 + 2), sc2[0]);
 #pragma unroll
                   for (int j = 1; j < kSMax; ++j)
                     if (j < S) {
+                      float ks[4];
 #pragma unroll
-                      for (int e = 0; e < 4; ++e) sc[j] = fmaf(q4[e], __shfl_sync(0xffffffffu, k4[e], rot[j]), sc[j]);
+                      for (int e = 0; e < 4; ++e) ks[e] = __shfl_sync(0xffffffffu, k4[e], rot[j]);
+                      sc2[j] = fma2(qa, pr(ks), sc2[j]);
+                      sc2[j] = fma2(qb, pr(ks + 2), sc2[j]);
                     }
                 }
             }
+#pragma unroll
+            for (int j = 0; j < kSMax; ++j) sc[j] = sc2[j].x + sc2[j].y;
             XF_STAMP(oi * 8 + 5);
             if (P > 1) {   // uniform over the CTA (hpw == 1 here): one exchange per attention op
 #pragma unroll
@@ -372,20 +524,23 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
 #pragma unroll
               for (int e4 = 0; e4 < 4; ++e4)
                 if (c16 + 4 * e4 < ncol) {
+                  // sum_j p_j (v_j + b_v) = sum_j p_j v_j + b_v (the probabilities sum to 1): the bias is added once, after 1/den
                   const float4 bv4 = *reinterpret_cast<const float4*>(bv + c0 + c16 + 4 * e4);
-                  float* v4 = v16 + 4 * e4;
-                  v4[0] += bv4.x; v4[1] += bv4.y; v4[2] += bv4.z; v4[3] += bv4.w;
-                  float o4[4];
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) o4[e] = sc[0] * v4[e];
+                  const float* v4 = v16 + 4 * e4;
+                  float2 oa = mul2(make_float2(sc[0], sc[0]), pr(v4)), ob = mul2(make_float2(sc[0], sc[0]), pr(v4 + 2));
 #pragma unroll
                   for (int j = 1; j < kSMax; ++j)
                     if (j < S) {
+                      float vs[4];
 #pragma unroll
-                      for (int e = 0; e < 4; ++e) o4[e] = fmaf(sc[j], __shfl_sync(0xffffffffu, v4[e], rot[j]), o4[e]);
+                      for (int e = 0; e < 4; ++e) vs[e] = __shfl_sync(0xffffffffu, v4[e], rot[j]);
+                      oa = fma2(make_float2(sc[j], sc[j]), pr(vs), oa);
+                      ob = fma2(make_float2(sc[j], sc[j]), pr(vs + 2), ob);
                     }
+                  oa = fma2(oa, make_float2(inv, inv), make_float2(bv4.x, bv4.y));
+                  ob = fma2(ob, make_float2(inv, inv), make_float2(bv4.z, bv4.w));
                   const int c = c0 + c16 + 4 * e4;
-                  uint2 pk = make_uint2(pack_op2<F16>(o4[0] * inv, o4[1] * inv), pack_op2<F16>(o4[2] * inv, o4[3] * inv));
+                  uint2 pk = make_uint2(pack_op2<F16>(oa.x, oa.y), pack_op2<F16>(ob.x, ob.y));
                   *reinterpret_cast<uint2*>(sHop + (size_t)(c >> 3) * plane + row * 16 + (c & 7) * 2) = pk;
                 }
             }
@@ -401,11 +556,14 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
               lds16(pbase + g * 16, bs);
               tmem_ld_wait();
 #pragma unroll
-              for (int q = 0; q < 16; ++q) {
-                const float v = acc[q] + bs[q];
-                acc[q] = op.act == 2 ? gelu_erf(v) : fmaxf(v, 0.f);
+              for (int q = 0; q < 16; q += 2) put(acc + q, add2(pr(acc + q), pr(bs + q)));
+              if (op.act == 2) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) acc[q] = gelu_erf(acc[q]);
+                store_group<F16>(sHop, plane, row, g, acc);
+              } else {
+                store_group_relu<F16>(sHop, plane, row, g, acc);      // ReLU inside the 16-bit conversion
               }
-              store_group<F16>(sHop, plane, row, g, acc);
             }
           }
         } else if (op.epi == XE_STREAM_ADD || op.epi == XE_STREAM_SET_PE) {
@@ -427,7 +585,7 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
               } else {
                 tmem_ld_wait();
 #pragma unroll
-                for (int q = 0; q < 16; ++q) st[i][q] += acc[q] + bs[q];
+                for (int q = 0; q < 16; q += 2) put(st[i] + q, add2(pr(st[i] + q), add2(pr(acc + q), pr(bs + q))));
               }
             }
           }
@@ -499,18 +657,20 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
         // one-pass statistics (padded columns of the stream are exactly 0, so they need no masking); the four
         // warps of a lane group exchange partial sums through smem under their own named barrier, and two
         // alternating buffers make a single barrier per LayerNorm enough
-        float s1 = 0.f, s2 = 0.f;
+        float2 s1p = make_float2(0.f, 0.f), s2p = make_float2(0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < kSlots; ++i) {
           const int g = kParts * i + part;
           if (g < ng) {
 #pragma unroll
-            for (int q = 0; q < 16; ++q) {
-              s1 += st[i][q];
-              s2 = fmaf(st[i][q], st[i][q], s2);
+            for (int q = 0; q < 16; q += 2) {
+              const float2 x2 = pr(st[i] + q);
+              s1p = add2(s1p, x2);
+              s2p = fma2(x2, x2, s2p);
             }
           }
         }
+        const float s1 = s1p.x + s1p.y, s2 = s2p.x + s2p.y;
         float* rb = red + ln_buf * (2 * kParts * 128);
         ln_buf ^= 1;
         rb[part * 128 + row] = s1;
@@ -519,6 +679,7 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
         const float mean = red_sum(rb, row) / (float)d;
         const float var = fmaxf(red_sum(rb + kParts * 128, row) / (float)d - mean * mean, 0.f);
         const float rstd = rsqrtf(var + kLnEps);
+        const float2 mean2 = make_float2(mean, mean), rstd2 = make_float2(rstd, rstd);
         XF_STAMP(oi * 8 + 6);
         const float* ln_g = pbase ? pbase + 3 * kPW : op.ln_g;
         const float* ln_b = pbase ? pbase + 4 * kPW : op.ln_b;
@@ -534,10 +695,8 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
               // gamma / beta are zero beyond d_model (padded arena / zeroed staging block): padded columns give 0
               const float4 gm = *reinterpret_cast<const float4*>(ln_g + g * 16 + 4 * e);
               const float4 bt = *reinterpret_cast<const float4*>(ln_b + g * 16 + 4 * e);
-              y[4 * e + 0] = fmaf((st[i][4 * e + 0] - mean) * rstd, gm.x, bt.x);
-              y[4 * e + 1] = fmaf((st[i][4 * e + 1] - mean) * rstd, gm.y, bt.y);
-              y[4 * e + 2] = fmaf((st[i][4 * e + 2] - mean) * rstd, gm.z, bt.z);
-              y[4 * e + 3] = fmaf((st[i][4 * e + 3] - mean) * rstd, gm.w, bt.w);
+              put(y + 4 * e, fma2(mul2(sub2(pr(st[i] + 4 * e), mean2), rstd2), make_float2(gm.x, gm.y), make_float2(bt.x, bt.y)));
+              put(y + 4 * e + 2, fma2(mul2(sub2(pr(st[i] + 4 * e + 2), mean2), rstd2), make_float2(gm.z, gm.w), make_float2(bt.z, bt.w)));
             }
             if (post == XP_LN_INPLACE_TO_AOP) {
 #pragma unroll
@@ -637,12 +796,13 @@ int launch_transformer_bf16(const sf_model* m, const float* tokens, int64_t B, i
              "token / reconstruction buffers must be 16-byte aligned");
   const int64_t n_tiles = (B + g.win_per_tile - 1) / g.win_per_tile;
   const int grid = (int)std::min<int64_t>(n_tiles, m->sm_count);
+  static const int flags = getenv("SF_XF_FLAGS") ? atoi(getenv("SF_XF_FLAGS")) : 0;     // experiment switches (profiles/r2_summary.md)
   if (m->xfprog.f16) {
     SF_CUDA_OK(cudaFuncSetAttribute(transformer_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
-    transformer_bf16_kernel<true><<<grid, kThreads, g.smem_bytes, st>>>(m->xfprog, g, m->xf, tokens, B, reduction, recon, scores, cnt);
+    transformer_bf16_kernel<true><<<grid, kThreads, g.smem_bytes, st>>>(m->xfprog, g, m->xf, tokens, B, reduction, recon, scores, cnt, flags);
   } else {
     SF_CUDA_OK(cudaFuncSetAttribute(transformer_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
-    transformer_bf16_kernel<false><<<grid, kThreads, g.smem_bytes, st>>>(m->xfprog, g, m->xf, tokens, B, reduction, recon, scores, cnt);
+    transformer_bf16_kernel<false><<<grid, kThreads, g.smem_bytes, st>>>(m->xfprog, g, m->xf, tokens, B, reduction, recon, scores, cnt, flags);
   }
   SF_CUDA_OK(cudaGetLastError());
   return SF_OK;
