@@ -270,6 +270,15 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
     const int64_t window = tile * geo.win_per_tile + lane_grp * geo.wpw + win_l;
     const bool valid = lane_ok && window < B;
     const float* tok_row = tokens + ((size_t)(valid ? window : 0) * S + tok_s) * dt;
+    {   // the next tile's tokens (one contiguous range) start their way from HBM to L2 now, a whole tile ahead of use
+      const int64_t w0 = (tile + gridDim.x) * geo.win_per_tile;
+      if (w0 < B) {
+        const int64_t bytes = (int64_t)(B - w0 < geo.win_per_tile ? B - w0 : geo.win_per_tile) * S * dt * (int64_t)sizeof(float);
+        const char* base = reinterpret_cast<const char*>(tokens + (size_t)w0 * S * dt);
+        for (int64_t o = (int64_t)threadIdx.x * 128; o < bytes; o += (int64_t)kThreads * 128)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(base + o));
+      }
+    }
     float st[kSlots][16];
 #pragma unroll
     for (int i = 0; i < kSlots; ++i)
@@ -323,15 +332,21 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
         } else {
           const bool shift = op.init_mode == XI_SHIFT_TOK_PE;
           const int ng = dp >> 4;
+          // every token load of the row goes out before anything waits on one (a tile's tokens are a cold, latency-bound
+          // read; the positional encoding is cache resident)
+#pragma unroll
+          for (int i = 0; i < kSlots; ++i) {
+            const int g = kParts * i + part;
+            if (g < ng) ldg16(shift ? tok_row - dt : tok_row, g * 16, d, valid && (!shift || tok_s > 0), st[i]);   // zero start token + shift by one
+          }
 #pragma unroll
           for (int i = 0; i < kSlots; ++i) {
             const int g = kParts * i + part;
             if (g < ng) {
-              float pe16[16], tk[16];
+              float pe16[16];
               ldg16(xf.pe + tok_s * d, g * 16, d, valid, pe16);
-              ldg16(shift ? tok_row - dt : tok_row, g * 16, d, valid && (!shift || tok_s > 0), tk);   // zero start token + shift by one
 #pragma unroll
-              for (int q = 0; q < 16; ++q) st[i][q] = pe16[q] + tk[q];
+              for (int q = 0; q < 16; q += 2) put(st[i] + q, add2(pr(st[i] + q), pr(pe16 + q)));
             }
           }
         }
@@ -416,6 +431,28 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
           post = op.post;
           slot ^= 1;                                                      // three GEMMs = one net toggle
         }
+        if (op.epi == XE_SCORE) {
+          // the score target (tokens, plus the positional encoding for shopformer/) is fetched into the stream registers
+          // -- dead since the last LayerNorm wrote its operand -- while the projection's MMAs run
+          const int ng = op.N >> 4;
+#pragma unroll
+          for (int i = 0; i < kSlots; ++i) {
+            const int g = kParts * i + part;
+            if (g < ng) ldg16(tok_row, g * 16, dt, valid, st[i]);
+          }
+          if (xf.variant == SF_VARIANT_SHOPFORMER) {
+#pragma unroll
+            for (int i = 0; i < kSlots; ++i) {
+              const int g = kParts * i + part;
+              if (g < ng) {
+                float pe16[16];
+                ldg16(xf.pe_score + tok_s * dt, g * 16, dt, valid, pe16);
+#pragma unroll
+                for (int q = 0; q < 16; q += 2) put(st[i] + q, add2(pr(st[i] + q), pr(pe16 + q)));
+              }
+            }
+          }
+        }
         if (flags & 1) {
           if (warp == 0) {                           // one polling warp; the others block in the hardware barrier
             if (flags & 2) mbar_spin(&bar, parity);
@@ -423,7 +460,8 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
           }
           __syncthreads();
         } else {
-          mbar_wait(&bar, parity);                   // every warp sleeps on the mbarrier itself (measured faster than one
+          if (flags & 8) mbar_spin(&bar, parity);
+          else mbar_wait(&bar, parity);              // every warp sleeps on the mbarrier itself (measured faster than one
         }                                            // polling warp + bar.sync: 1.197 -> 1.144 ms per 65,536 windows)
         parity ^= 1;
         if (nch > 1) {   // the next GEMM (out_proj) goes to the slot k used; k has completed with v
@@ -597,16 +635,10 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
           for (int i = 0; i < kSlots; ++i) {
             const int g = kParts * i + part;
             if (g < ng) {
-              float acc[16], target[16], bs[16];
+              float acc[16], bs[16];
+              const float* target = st[i];
               tmem_ld16(tmem + lane_addr + (uint32_t)(op.tmem_col + g * 16), acc);
-              ldg16(tok_row, g * 16, dt, valid, target);
               lds16(pbase + g * 16, bs);
-              if (xf.variant == SF_VARIANT_SHOPFORMER) {
-                float pe16[16];
-                ldg16(xf.pe_score + tok_s * dt, g * 16, dt, valid, pe16);
-#pragma unroll
-                for (int q = 0; q < 16; ++q) target[q] += pe16[q];
-              }
               tmem_ld_wait();
 #pragma unroll
               for (int q = 0; q < 16; ++q) {
@@ -626,7 +658,7 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
             }
           }
           xsc[part * 128 + row] = sq;
-          __syncthreads();
+          group_barrier(lane_grp);         // the four column parts of a row live in the four warps of its lane group
           if (part == 0) {
             const float tot = red_sum(xsc, row);
             if (reduction == SF_REDUCE_NONE) {
@@ -638,8 +670,7 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
                 if (j < S) wsum += __shfl_sync(0xffffffffu, tot, (wb + j) & 31);
               if (valid && tok_s == 0 && scores) scores[window] = wsum / (float)(S * dt);
             }
-          }
-          __syncthreads();
+          }                                // (xsc is next written in the next tile, behind that tile's barriers)
           post = XP_NONE;
         }
       }
@@ -724,7 +755,7 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
         }
         if (post == XP_LN_SCORE) {
           xsc[part * 128 + row] = sq;
-          __syncthreads();
+          group_barrier(lane_grp);         // the four column parts of a row live in the four warps of its lane group
           if (part == 0) {
             const float tot = red_sum(xsc, row);
             if (reduction == SF_REDUCE_NONE) {
@@ -736,8 +767,7 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
                 if (j < S) wsum += __shfl_sync(0xffffffffu, tot, (wb + j) & 31);
               if (valid && tok_s == 0 && scores) scores[window] = wsum / (float)(S * dt);
             }
-          }
-          __syncthreads();
+          }                                // (xsc is next written in the next tile, behind that tile's barriers)
         }
       }
     }

@@ -1,5 +1,6 @@
 """Per-op timeline of CTA 0 of the bf16 transformer (debug aid): python profiles/xf_timing.py"""
-import ctypes as C, sys
+import ctypes as C, sys, os
+FULL = os.environ.get("XF_TIMING_FULL") is not None
 sys.path.insert(0, "."); sys.path.insert(0, "computer-vision-shoplifting-detection_b200")
 import numpy as np, torch
 import bench
@@ -23,5 +24,5 @@ for i in range(lo, hi + 1):
     op, ph = divmod(int(a[i, 0]), 8) if a[i, 0] != 9999 else (99, 5)
     dt = a[i, 1] - prev; prev = a[i, 1]
     agg[ph] = agg.get(ph, 0) + dt
-    if 3 <= op < 8 or op == 99: print(f"op {op:2d} {names.get(ph, 'tile end'):14s} +{dt:6d}  @{a[i,1]-t0:7d}")
+    if FULL or 3 <= op < 8 or op == 99: print(f"op {op:2d} {names.get(ph, 'tile end'):14s} +{dt:6d}  @{a[i,1]-t0:7d}")
 print({names.get(k, 'post/tile end'): int(v) for k, v in agg.items()}, "total", int(a[hi, 1] - t0))
