@@ -94,6 +94,15 @@ __device__ __forceinline__ void unpack8(const uint4& q, float* f) {
 __device__ __forceinline__ uint4 pack8(const float* f) {
   return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
 }
+// the same through ReLU: one conversion instruction per pair, no separate max
+__device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ uint4 pack8_relu(const float* f) {
+  return make_uint4(pack_relu_bf16x2(f[0], f[1]), pack_relu_bf16x2(f[2], f[3]), pack_relu_bf16x2(f[4], f[5]), pack_relu_bf16x2(f[6], f[7]));
+}
 
 
 // ---- branch-free, loads-first inner loops (the CUDA-core phases are latency bound: keep independent loads in flight)
@@ -446,8 +455,7 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
             umma_commit(&bar);
           }
         }
-        if (warp == 0) mbar_wait(&bar, parity);     // one polling warp; the others block in the hardware barrier
-        __syncthreads();
+        mbar_wait(&bar, parity);                    // every warp sleeps on the mbarrier itself (no polling warp + bar.sync hop)
         parity ^= 1;
         tc_fence_after();
         TOK_STAMP(113 + bi * 10);
@@ -467,13 +475,13 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
             float y[16];
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4) {
-              y[q4 * 4 + 0] = data ? fmaxf(acc[q4 * 4 + 0] + bb[q4].x, 0.f) : 0.f;
-              y[q4 * 4 + 1] = data ? fmaxf(acc[q4 * 4 + 1] + bb[q4].y, 0.f) : 0.f;
-              y[q4 * 4 + 2] = data ? fmaxf(acc[q4 * 4 + 2] + bb[q4].z, 0.f) : 0.f;
-              y[q4 * 4 + 3] = data ? fmaxf(acc[q4 * 4 + 3] + bb[q4].w, 0.f) : 0.f;
+              y[q4 * 4 + 0] = data ? acc[q4 * 4 + 0] + bb[q4].x : 0.f;
+              y[q4 * 4 + 1] = data ? acc[q4 * 4 + 1] + bb[q4].y : 0.f;
+              y[q4 * 4 + 2] = data ? acc[q4 * 4 + 2] + bb[q4].z : 0.f;
+              y[q4 * 4 + 3] = data ? acc[q4 * 4 + 3] + bb[q4].w : 0.f;
             }
-            *reinterpret_cast<uint4*>(sA + ((size_t)(gq * 2) * b.rtot + r) * 16) = pack8(y);
-            *reinterpret_cast<uint4*>(sA + ((size_t)(gq * 2 + 1) * b.rtot + r) * 16) = pack8(y + 8);
+            *reinterpret_cast<uint4*>(sA + ((size_t)(gq * 2) * b.rtot + r) * 16) = pack8_relu(y);        // ReLU inside the conversion
+            *reinterpret_cast<uint4*>(sA + ((size_t)(gq * 2 + 1) * b.rtot + r) * 16) = pack8_relu(y + 8);
           }
         }
       }
@@ -532,9 +540,8 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
         if (elect_one()) umma_commit(&bar);
         TOK_STAMP(118 + bi * 10);
       }
-      if (warp == 0) mbar_wait(&bar, parity);
+      mbar_wait(&bar, parity);
       TOK_STAMP(119 + bi * 10);
-      __syncthreads();
       parity ^= 1;
       tc_fence_after();
       TOK_STAMP(116 + bi * 10);
@@ -595,12 +602,12 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
 #pragma unroll
             for (int q = 0; q < 8; ++q) acc[8 + q] += f[q];
           }
-#pragma unroll
-          for (int q = 0; q < 16; ++q) acc[q] = fmaxf(acc[q], 0.f);
           if (!last) {
-            *reinterpret_cast<uint4*>(sXout + ((size_t)(gq * 2) * nxt_rtot + target) * 16) = pack8(acc);
-            *reinterpret_cast<uint4*>(sXout + ((size_t)(gq * 2 + 1) * nxt_rtot + target) * 16) = pack8(acc + 8);
+            *reinterpret_cast<uint4*>(sXout + ((size_t)(gq * 2) * nxt_rtot + target) * 16) = pack8_relu(acc);
+            *reinterpret_cast<uint4*>(sXout + ((size_t)(gq * 2 + 1) * nxt_rtot + target) * 16) = pack8_relu(acc + 8);
           } else {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) acc[q] = fmaxf(acc[q], 0.f);
             float* dst = tokens + (size_t)(w_first + w) * pl.S_out * (size_t)(pl.c_last * V) + target;
 #pragma unroll
             for (int q = 0; q < 16; ++q)
