@@ -784,8 +784,27 @@ int launch_tokenizer_bf16(const sf_model* m, const float* poses, int64_t B, int 
   // co-resident CTAs must all get their tensor-memory allocation or they would serialise on tcgen05.alloc.
   int smem_per_sm = 0;
   SF_CUDA_OK(cudaDeviceGetAttribute(&smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, m->device));
-  int occ = smem_per_sm / (int)(pl.smem_bytes + 1024 + 256);
-  occ = std::max(1, std::min(std::min(occ, kMaxOcc), (int)(512 / pl.tmem_cols)));
+  auto occupancy = [&](const BfPlan& p) {
+    const int o = smem_per_sm / (int)(p.smem_bytes + 1024 + 256);
+    return std::max(1, std::min(std::min(o, kMaxOcc), (int)(512 / p.tmem_cols)));
+  };
+  int occ = occupancy(pl);
+  // Windows per CTA pass.  A pass is a chain of fixed latencies (MMA completion, barriers, TMA) and SM throughput is the
+  // number of windows in flight: shapes that fit two or three CTAs per SM run one window per pass in each; a shape that only
+  // fits ONE CTA per SM (hidden 64) packs as many windows into its pass as shared and tensor memory allow instead
+  // (config B: two windows per pass, 8.31 -> 5.08 ms per 65,536 windows; C and A' only fit one).
+  if (occ == 1) {
+    int g_max = 4;
+    if (const char* e = getenv("SF_TOK_G")) g_max = std::max(1, atoi(e));
+    for (int G = g_max; G > 1; --G) {
+      BfPlan p2;
+      const char* w2 = "";
+      if (build_plan(m, T, G, &p2, &w2)) {
+        pl = p2;
+        break;
+      }
+    }
+  }
   if (const char* dbg = getenv("SF_TOK_OCC")) occ = std::max(1, std::min(occ, atoi(dbg)));     // debugging aid
   const int64_t n_groups = (B + pl.G - 1) / pl.G;
   const int grid = (int)std::min<int64_t>(n_groups, (int64_t)m->sm_count * occ);
