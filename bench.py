@@ -443,8 +443,10 @@ def main():
 
     # ---- extra end-to-end legs (rank 0's view, N = 1 only; the headline `e2e` above stays the pre-cut-window call)
     extras = {}
+    if not a.no_extras:
+        extras["from_tracks"] = tracks_e2e(a, eng, n, T, dev, world, rank)
     if world == 1 and not a.no_extras:
-        extras = extra_legs(a, model, eng, xs, T, V, dev)
+        extras.update(extra_legs(a, model, eng, xs, T, V, dev))
 
     # ---- the other precision of BASELINE configs[1] ("fp32 and bf16"), device resident, 3 steps
     other = "fp32" if a.precision != "fp32" else "tc"
@@ -532,6 +534,61 @@ def main():
         dist.destroy_process_group()
 
 
+def tracks_e2e(a, eng, n, T, dev, world, rank):
+    """`e2e.from_tracks`, every N: each rank scores its OWN packed tracks (about n windows) from page-locked host memory
+    through sf_runner_score_tracks -- x, y only, 12 new frames per stride-12 window = half the PCIe / host-memory bytes of
+    pre-cut windows; windowing + normalisation + scoring on the device -- then (N > 1) the ragged NCCL all-gather of the
+    scores and a D2H of the gathered vector.  Wall clock, max over ranks; windows = sum over ranks."""
+    from shopformer_b200.engine import PackedTracks
+    from shopformer_b200.sharding import gather_ragged
+    from shopformer_b200.synthetic import synth_tracks
+    stride = T // 2
+    try:
+        n_tracks = max(8, int(n / ((1515 - T) / stride)))
+        tr = synth_tracks(n_tracks, seed=4321 + rank)
+        pin = lambda arr: torch.from_numpy(np.ascontiguousarray(arr)).pin_memory().numpy()      # every bulk array page-locked
+        kp2 = pin(tr["kp"][:, :, :2])                                                            # the confidence channel is dropped at ingest
+        host = PackedTracks(kp=kp2, frame_no=pin(tr["frame_no"]), track_offsets=tr["track_offsets"], track_video=tr["track_video"],
+                            gt=pin(tr["gt"]), gt_offsets=tr["gt_offsets"])
+        kw = dict(add_neck=False, precision=a.precision, chunk=16384)
+
+        def one():
+            res = eng.score_tracks_host(host, T, stride, **kw)
+            if world > 1:
+                allsc, _ = gather_ragged(torch.from_numpy(res["scores"][:int(res["n_windows"])]).to(dev, non_blocking=True))
+                allsc.cpu()
+            return res
+        for _ in range(2):
+            res = one()
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        reps = 5
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            res = one()
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        nw = int(res["n_windows"])
+        tt = torch.tensor([dt, float(nw)], dtype=torch.float64, device=dev)
+        if world > 1:
+            t_max = tt[:1].clone()
+            dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+            n_sum = tt[1:].clone()
+            dist.all_reduce(n_sum, op=dist.ReduceOp.SUM)
+            dt, nw_all = float(t_max.item()), int(n_sum.item())
+        else:
+            nw_all = nw
+        return {"value": nw_all * reps / dt, "unit": UNIT, "windows_per_step": nw_all,
+                "h2d_bytes_per_step_per_gpu": int(kp2.nbytes + tr["frame_no"].nbytes), "d2h_bytes_per_step_per_gpu": 16 * nw,
+                "api": "sf_runner_score_tracks: host packed tracks (x, y) -> windowing + normalisation + scoring on the device -> "
+                       "host scores, labels and window index; groups of whole tracks uploaded under the previous group's kernels"
+                       + ("; then the ragged NCCL all-gather of the scores and a D2H of the gathered vector" if world > 1 else "")}
+    except Exception as exc:
+        return {"error": str(exc)[:200]}
+
+
 def extra_legs(a, model, eng, xs, T, V, dev):
     """Extra keys of the N=1 line: (1) the same windows scored FROM PACKED TRACKS on the host (sf_runner_score_tracks:
     x, y only, 12 new frames per stride-12 window = half the PCIe bytes of pre-cut windows), (2) the reference's own loop
@@ -543,29 +600,6 @@ def extra_legs(a, model, eng, xs, T, V, dev):
     out = {}
     n = xs.shape[0]
     stride = T // 2
-    # (1) tracks of ~1500 detections -> about n windows; the confidence channel is dropped at ingest
-    try:
-        n_tracks = max(8, int(n / ((1515 - T) / stride)))
-        tr = synth_tracks(n_tracks, seed=4321)
-        kp2 = torch.from_numpy(np.ascontiguousarray(tr["kp"][:, :, :2])).pin_memory().numpy()
-        pin = lambda arr: torch.from_numpy(np.ascontiguousarray(arr)).pin_memory().numpy()      # every bulk array page-locked
-        host = PackedTracks(kp=kp2, frame_no=pin(tr["frame_no"]), track_offsets=tr["track_offsets"], track_video=tr["track_video"],
-                            gt=pin(tr["gt"]), gt_offsets=tr["gt_offsets"])
-        kw = dict(add_neck=False, precision=a.precision, chunk=16384)
-        for _ in range(2):
-            res = eng.score_tracks_host(host, T, stride, **kw)
-        reps = 5
-        t0 = time.perf_counter()
-        for _ in range(reps):
-            res = eng.score_tracks_host(host, T, stride, **kw)
-        dt = time.perf_counter() - t0
-        nw = int(res["n_windows"])
-        out["from_tracks"] = {"value": nw * reps / dt, "unit": UNIT, "windows_per_step": nw,
-                              "h2d_bytes_per_step": int(kp2.nbytes + tr["frame_no"].nbytes), "d2h_bytes_per_step": 16 * nw,
-                              "api": "sf_runner_score_tracks: host packed tracks (x, y) -> windowing + normalisation + scoring on the device -> "
-                                     "host scores, labels and window index; groups of whole tracks uploaded under the previous group's kernels"}
-    except Exception as exc:
-        out["from_tracks"] = {"error": str(exc)[:200]}
     # (2) the reference's loop: model(x)['normality_score'] per batch, host tensors in, host scores out
     try:
         loop = {}
