@@ -4,6 +4,8 @@
 #include <cstring>
 #include <vector>
 
+#include <mutex>
+
 #include "sf_internal.h"
 
 using namespace sf;
@@ -135,22 +137,60 @@ static int score_windows_impl(const sf_model* m, const float* poses_dev, int64_t
     ws_left -= tok_bytes;
   }
   const int64_t score_stride = reduction == SF_REDUCE_NONE ? S : 1;
+  const bool xf_tc = precision == SF_PREC_BF16 && transformer_bf16_supported(m, S);
+  SF_REQUIRE(!cnt.n || (precision == SF_PREC_BF16 && xf_tc), SF_E_UNSUPPORTED, "device-side batch size needs the tensor-core kernels");
+  // one range of a pass on one stream: tokenizer, then transformer + score.  The two kernels only share the fp32 tokens in
+  // HBM, so each picks its own path: a shape the tensor-core transformer does not cover (head width not a multiple of 4,
+  // S > 4, d_model > 160) still gets the tensor-core tokenizer.
+  auto tokenize = [&](int64_t off, int64_t n, float* tok, cudaStream_t s2) -> int {
+    const DevCount c{cnt.n, cnt.off + off};
+    return precision == SF_PREC_BF16 ? launch_tokenizer_tc(m, poses_dev + off * pose_elems, n, T, tok, s2, c)
+                                     : launch_tokenizer_fp32(m, poses_dev + off * pose_elems, n, T, tok, ws, ws_left, s2);
+  };
+  auto reconstruct = [&](int64_t off, int64_t n, const float* tok, cudaStream_t s2) -> int {
+    const DevCount c{cnt.n, cnt.off + off};
+    float* rec = recon_dev ? recon_dev + off * tok_elems : nullptr;
+    float* sc = scores_dev + off * score_stride;
+    return xf_tc ? launch_transformer_bf16(m, tok, n, S, reduction, rec, sc, s2, c) : launch_transformer_fp32(m, tok, n, S, reduction, rec, sc, s2);
+  };
+  // Both tensor-core kernels are persistent (one CTA per SM walking equal tiles), so each ends in a partial wave: 65,536
+  // config-A windows are 11.07 waves of transformer tiles = 12 tile times.  A large pass is therefore cut in two halves that
+  // run on two streams: as the CTAs of one half's kernel retire, the SMs pick up the other half's CTAs, and only the
+  // last kernel's tail stays exposed.  (Not under stream capture, not for small batches; SF_SPLIT_STREAMS=0 disables it.)
+  static const bool split_on = !(getenv("SF_SPLIT_STREAMS") && atoi(getenv("SF_SPLIT_STREAMS")) == 0);
+  const int64_t unit = 280 * 4;                         // whole tokenizer (7-window) and transformer (40-window) tiles
   for (int64_t off = 0; off < B; off += pass) {
     const int64_t n = std::min(pass, B - off);
     float* tok = tokens_dev ? tokens_dev + off * tok_elems : tok_ws;
-    const float* x = poses_dev + off * pose_elems;
-    SF_REQUIRE(!cnt.n || precision == SF_PREC_BF16, SF_E_UNSUPPORTED, "device-side batch size needs the tensor-core kernels");
-    const DevCount c{cnt.n, cnt.off + off};
-    rc = precision == SF_PREC_BF16 ? launch_tokenizer_tc(m, x, n, T, tok, st, c) : launch_tokenizer_fp32(m, x, n, T, tok, ws, ws_left, st);
+    bool split = split_on && m->side && precision == SF_PREC_BF16 && xf_tc && n >= (int64_t)m->sm_count * 160;
+    if (split) {
+      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+      if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+        cudaGetLastError();
+        split = false;
+      }
+    }
+    if (!split) {
+      rc = tokenize(off, n, tok, st);
+      if (rc) return rc;
+      rc = reconstruct(off, n, tok, st);
+      if (rc) return rc;
+      continue;
+    }
+    const int64_t h1 = (n / 2 + unit - 1) / unit * unit, h2 = n - h1;
+    sf::SideStream* sd = m->side;
+    std::lock_guard<std::mutex> lock(sd->mu);
+    SF_CUDA_OK(cudaEventRecord(sd->fork, st));
+    SF_CUDA_OK(cudaStreamWaitEvent(sd->st, sd->fork, 0));
+    rc = tokenize(off, h1, tok, st);
+    if (!rc) rc = tokenize(off + h1, h2, tok + h1 * tok_elems, sd->st);
+    if (!rc) rc = reconstruct(off, h1, tok, st);
+    if (!rc) rc = reconstruct(off + h1, h2, tok + h1 * tok_elems, sd->st);
+    // always join, so that the caller's stream never runs ahead of work enqueued on the side stream
+    cudaError_t e = cudaEventRecord(sd->join, sd->st);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(st, sd->join, 0);
     if (rc) return rc;
-    float* rec = recon_dev ? recon_dev + off * tok_elems : nullptr;
-    float* sc = scores_dev + off * score_stride;
-    // The two kernels only share the fp32 tokens in HBM, so each picks its own path: a shape the tensor-core transformer
-    // does not cover (head width not a multiple of 4, S > 4, d_model > 160) still gets the tensor-core tokenizer.
-    const bool xf_tc = precision == SF_PREC_BF16 && transformer_bf16_supported(m, S);
-    SF_REQUIRE(!cnt.n || xf_tc, SF_E_UNSUPPORTED, "device-side batch size needs the tensor-core transformer");
-    rc = xf_tc ? launch_transformer_bf16(m, tok, n, S, reduction, rec, sc, st, c) : launch_transformer_fp32(m, tok, n, S, reduction, rec, sc, st);
-    if (rc) return rc;
+    SF_CUDA_OK(e);
   }
   return SF_OK;
 }

@@ -556,6 +556,7 @@ extern "C" int sf_model_create(const sf_config* cfg, int32_t n_tensors, const ch
   m->host_arena = nullptr;
   m->arena_bf16 = nullptr;
   m->xfops_dev = nullptr;
+  m->side = nullptr;
   auto fill_tok = [&](const float* A, Tokenizer& T) {
     T.n_blocks = nb;
     T.V = V;
@@ -603,6 +604,19 @@ extern "C" int sf_model_create(const sf_config* cfg, int32_t n_tensors, const ch
     tok2_destroy(m->tok2);
     delete m;
     return SF_E_CUDA;
+  }
+  {
+    sf::SideStream* sd = new sf::SideStream();
+    if (cudaStreamCreateWithFlags(&sd->st, cudaStreamNonBlocking) == cudaSuccess &&
+        cudaEventCreateWithFlags(&sd->fork, cudaEventDisableTiming) == cudaSuccess &&
+        cudaEventCreateWithFlags(&sd->join, cudaEventDisableTiming) == cudaSuccess) {
+      m->side = sd;
+    } else {
+      cudaGetLastError();
+      if (sd->fork) cudaEventDestroy(sd->fork);
+      if (sd->st) cudaStreamDestroy(sd->st);
+      delete sd;
+    }
   }
   m->arena_bf16 = nullptr;
   m->arena_bf16_bytes = bf.size() * sizeof(uint16_t);
@@ -690,6 +704,13 @@ extern "C" void sf_model_destroy(sf_model* m) {
   DeviceGuard guard;
   guard.enter(m->device);
   tok2_destroy(m->tok2);
+  if (m->side) {
+    cudaStreamSynchronize(m->side->st);
+    cudaEventDestroy(m->side->fork);
+    cudaEventDestroy(m->side->join);
+    cudaStreamDestroy(m->side->st);
+    delete m->side;
+  }
   if (m->arena) cudaFree(m->arena);
   if (m->arena_bf16) cudaFree(m->arena_bf16);
   if (m->xfops_dev) cudaFree(m->xfops_dev);

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -154,6 +155,15 @@ struct XfProgram {
 }  // namespace sf
 
 namespace sf { struct Tok2State; }
+namespace sf {
+// second stream of a model: sf_score_windows runs the two halves of a large batch side by side so that the partial last wave
+// of one half's persistent kernels is filled by the other half's CTAs (api.cu)
+struct SideStream {
+  cudaStream_t st = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  std::mutex mu;              // one fork / join sequence is enqueued at a time (the events are re-recorded per call)
+};
+}
 
 struct sf_model {
   sf_config cfg;
@@ -171,6 +181,7 @@ struct sf_model {
   sf::XfOp* xfops_dev;
   sf::Tok2State* tok2;      // tokenizer v2: operand images + per-T tile programs (tokenizer2_bf16.cu)
   float* host_arena;        // device < 0 only: a HOST model for the program emulator (tests); no entry point computes with it
+  sf::SideStream* side;     // nullptr when it could not be created (the batch then runs on the caller's stream alone)
 };
 
 namespace sf {
