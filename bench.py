@@ -13,7 +13,9 @@ scores its own 65,536 windows and the scores are all-gathered over NCCL (the pat
 One JSON line is printed by rank 0:
   value      windows/s, whole job, inputs resident in HBM, CUDA-event timed, max over ranks
   e2e        the same metric through the C-ABI host-buffer call (`sf_runner_score`: H2D of the poses
-             from pinned memory, kernels, D2H of the scores inside the timed region)
+             from pinned memory, kernels, D2H of the scores inside the timed region; at N > 1 also the
+             all-gather); `e2e.from_tracks` is the same from packed host TRACKS at every N
+             (`sf_runner_score_tracks`: half the bytes per window, windowing on the device)
   roofline   dominant kernel (tokenizer) useful FLOP/s against the measured bf16 tensor peak
   cpu_baseline  the CPU oracle port on the host cores on a bounded sample of the same workload
 `--impl reference` times the CPU restatement of the reference path (oracle/, torch CPU ops, all host

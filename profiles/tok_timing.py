@@ -6,9 +6,12 @@ import bench
 from shopformer_b200 import native as N
 from shopformer_b200.synthetic import synth_windows
 lib = N.load()
-model = bench.build_model("A").cuda()
+CFGN = sys.argv[1] if len(sys.argv) > 1 else "A"
+from shopformer_b200 import configs as CFG
+_, T_, V_ = CFG.input_shape(CFGN)
+model = bench.build_model(CFGN).cuda()
 eng = model._sf_engine()
-x = torch.from_numpy(synth_windows(65536, 24, 17, seed=1)[0]).cuda()
+x = torch.from_numpy(synth_windows(65536, T_, V_, seed=1)[0]).cuda()
 eng.tokenize(x, precision="bf16"); torch.cuda.synchronize()
 lib.sfdbg_tokenizer_timing(1, None, 0)
 eng.tokenize(x, precision="bf16"); torch.cuda.synchronize()

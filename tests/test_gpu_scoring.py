@@ -265,6 +265,27 @@ def test_bf16_path_ragged_and_deterministic(dropin1, dropin2):
     assert torch.equal(eng.score_windows(x[:1], precision="bf16"), s[:1])
 
 
+@pytest.mark.parametrize("name, n", [("B", 1203), ("B", 1), ("C", 257), ("A12", 515)])
+def test_one_window_tokenizer_passes_are_position_independent(name, n, dropin1, dropin2):
+    """Hidden-64 shapes run the one-window tokenizer, which packs several windows into a CTA pass when the shape only fits one
+    CTA per SM (config B: two).  A window's score must not depend on which pass slot or which neighbour it gets: odd batch
+    sizes (a last pass with one window), permutations and a batch of one give bit-identical per-window scores."""
+    model = build_model(dropin1, dropin2, name, seed=5)
+    _, T, V = CFG.input_shape(name)
+    xs, _ = synth_windows(n, T, V, seed=78)
+    ref = O.score_windows(model.state_dict(), torch.from_numpy(xs), dtype=torch.float64, **oracle_kwargs(model, name))
+    model = model.cuda()
+    eng = model._sf_engine()
+    x = torch.from_numpy(xs).cuda()
+    s = eng.score_windows(x, precision="bf16")
+    assert rel_err(s.cpu().numpy(), ref["score"].numpy()) < BF16_TOL
+    perm = torch.randperm(n, device="cuda", generator=torch.Generator("cuda").manual_seed(2))
+    assert torch.equal(eng.score_windows(x[perm].contiguous(), precision="bf16"), s[perm])
+    assert torch.equal(eng.score_windows(x[n - 1:], precision="bf16"), s[n - 1:])
+    if n > 2:
+        assert torch.equal(eng.score_windows(x[1:n - 1].contiguous(), precision="bf16"), s[1:n - 1])
+
+
 def test_bf16_path_trained_checkpoint_ranking(golden_dir, dropin1):
     from scipy.stats import spearmanr
     g = np.load(golden_dir / "trained_A.npz")
