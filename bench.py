@@ -471,6 +471,11 @@ def main():
             dist.destroy_process_group()
         return
 
+    # launches of OUR kernels per step: tokenizer + transformer, twice when sf_score_windows runs the pass as two halves on
+    # two streams (tensor-core path, >= sm_count * 160 windows, SF_SPLIT_STREAMS != 0; csrc/api.cu)
+    split = (a.precision != "fp32" and os.environ.get("SF_SPLIT_STREAMS", "1") != "0"
+             and n >= torch.cuda.get_device_properties(dev).multi_processor_count * 160 and n <= 131072)
+    launches_per_step = 4 if split else 2 * ((n + 131071) // 131072)
     # ---- roofline of the dominant kernel (tokenizer): useful FLOPs per launch / its duration
     tok_flops = {"A": 7_042_080, "A1": 26_988_384, "B": 7_729_344, "C": 17_057_120}.get(a.config)
     dom = "tokenizer" if tok_ms >= xf_ms else "transformer"
@@ -527,7 +532,7 @@ def main():
                        "while the previous chunk is scored on the compute stream, scores copied back per chunk; pageable sources are staged "
                        "through a 4-slot pinned ring" + ("; followed by the NCCL all-gather of the scores and a D2H of the gathered vector" if world > 1 else ""),
                 "steps": e2e_steps, **extras},
-        "gpu_launches": 2 * a.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "gpu_launches": launches_per_step * a.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         "parity": {"max_rel_err_vs_cpu_oracle": err, "checked_windows": 256, "tolerance": 1e-3 if a.precision == "fp32" else 1e-2},
         "other_precision": other_line,
     }
