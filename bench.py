@@ -473,9 +473,9 @@ def main():
 
     # launches of OUR kernels per step: tokenizer + transformer, twice when sf_score_windows runs the pass as two halves on
     # two streams (tensor-core path, >= sm_count * 160 windows, SF_SPLIT_STREAMS != 0; csrc/api.cu)
-    split = (a.precision != "fp32" and os.environ.get("SF_SPLIT_STREAMS", "1") != "0"
-             and n >= torch.cuda.get_device_properties(dev).multi_processor_count * 160 and n <= 131072)
-    launches_per_step = 4 if split else 2 * ((n + 131071) // 131072)
+    split_on = a.precision != "fp32" and os.environ.get("SF_SPLIT_STREAMS", "1") != "0"
+    split_min = torch.cuda.get_device_properties(dev).multi_processor_count * 160
+    launches_per_step = sum(4 if (split_on and min(131072, n - o) >= split_min) else 2 for o in range(0, n, 131072))
     # ---- roofline of the dominant kernel (tokenizer): useful FLOPs per launch / its duration
     tok_flops = {"A": 7_042_080, "A1": 26_988_384, "B": 7_729_344, "C": 17_057_120}.get(a.config)
     dom = "tokenizer" if tok_ms >= xf_ms else "transformer"
