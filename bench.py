@@ -704,6 +704,29 @@ def extra_legs(a, model, eng, xs, T, V, dev):
             del xc, ec, mc
     except Exception as exc:
         out["config_C_262144"] = {"error": str(exc)[:200]}
+    # (4) the other canonical configs at 65,536 windows, device resident, 5 steps: B = shopformer_2 paper config, A1 = shopformer/
+    # class defaults (hidden 64)
+    if a.config == "A":
+        for name in ("B", "A1"):
+            try:
+                mo = build_model(name).to(dev)
+                eo = mo._sf_engine()
+                _, To, Vo = CFG.input_shape(name)
+                xo = torch.from_numpy(synth_windows(65536, To, Vo, seed=98)[0]).to(dev)
+                eo.score_windows(xo, precision=a.precision)
+                torch.cuda.synchronize(dev)
+                c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                c0.record()
+                for _ in range(5):
+                    eo.score_windows(xo, precision=a.precision)
+                c1.record()
+                torch.cuda.synchronize(dev)
+                ms = c0.elapsed_time(c1) / 5
+                out[f"config_{name}_65536"] = {"value": 65536 / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "tc_operand_format": list(eo.tc_formats(To)),
+                                               "path_frac": CFG.USEFUL_FLOPS[name] * 65536 / (ms * 1e-3) / 1e12 / load_peaks()["bf16_sustained"]}
+                del xo, eo, mo
+            except Exception as exc:
+                out[f"config_{name}_65536"] = {"error": str(exc)[:200]}
     return out
 
 
