@@ -1,5 +1,6 @@
 // C-ABI entry points of the scoring hot path + the host-buffer runner.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <utility>
@@ -760,5 +761,44 @@ extern "C" int sfdbg_tok2_emulate(const sf_model* m, const float* poses_host, in
   }
   std::string err;
   SF_REQUIRE(t2::emulate(*st, pr, poses_host, B, tokens_host, schedule_seed, &err), SF_E_INVALID, "%s", err.c_str());
+  return SF_OK;
+}
+
+// Prints the tokenizer-v2 tile program of (m, T): groups (MMAs, waits), stages per team, loads.  Debugging aid that goes with
+// profiles/tok2_timing.py (the stamps there are group / stage indices); not part of the C ABI.
+extern "C" int sfdbg_tok2_describe(const sf_model* m, int32_t T) {
+  SF_REQUIRE(m && m->tok2, SF_E_INVALID, "sfdbg_tok2_describe: bad argument");
+  const t2::Static* st = tok2_static(m->tok2);
+  t2::Program pr;
+  t2::build_program(*st, T, m->max_smem_optin > 0 ? m->max_smem_optin - 256 : 232448 - 256, &pr);
+  SF_REQUIRE(pr.ok, SF_E_UNSUPPORTED, "tokenizer v2 does not cover this shape: %s", pr.why.c_str());
+  const t2::Plan& pl = pr.plan;
+  printf("plan: WT=%d rows=%d smem=%u P@%u Q@%u W@%u xin@%u const=%u groups=%d stages=%d+%d loads=%d mma=%d\n", pl.WT, pl.rows, pl.smem_bytes,
+         pl.off_P, pl.off_Q, pl.off_W, pl.off_xin, pl.const_bytes, pl.n_groups, pl.n_stages[0], pl.n_stages[1], pl.n_loads, pl.n_mma);
+  for (size_t g = 0; g < pr.groups.size(); ++g) {
+    const t2::Group& gr = pr.groups[g];
+    int ncols = 0, dmin = 1 << 30, dmax = 0;
+    for (int i = gr.first; i < gr.first + gr.count; ++i) {
+      const int N = (int)((pr.mma[i].idesc >> 17) & 0x3F) * 8, d = (int)(pr.mma[i].d & 0x1FF);
+      ncols += N;
+      dmin = std::min(dmin, d);
+      dmax = std::max(dmax, d + N);
+    }
+    printf("G%-3zu mma=%-3d sumN=%-5d tmem=[%d,%d) wait e0=%d e1=%d l=%d prev=%d.%d\n", g, gr.count, ncols, dmin, dmax, gr.wait_e[0], gr.wait_e[1],
+           gr.wait_l, gr.prev_team, gr.prev_stage);
+  }
+  static const char* kType[] = {"G0", "CVT", "XEPI0", "TOKENS"};
+  for (int t = 0; t < t2::kTeams; ++t)
+    for (size_t e = 0; e < pr.stages[t].size(); ++e) {
+      const t2::Stage& s = pr.stages[t][e];
+      printf("E%d.%-3zu %-6s flags=%d wait g=%d l=%d eo=%d gprev=%d tmem_col=%d n_cg=%d dst=%u p=[%d,%d)\n", t, e, kType[s.type], s.flags, s.wait_g,
+             s.wait_l, s.wait_eo, s.wait_g_prev, s.tmem_col, s.n_cg, s.dst_off, s.p0, s.p1);
+    }
+  for (size_t l = 0; l < pr.loads.size(); ++l) {
+    const t2::Load& ld = pr.loads[l];
+    printf("L%-2zu kind=%d bytes=%u dst=%u wait g=%d e0=%d e1=%d gprev=%d\n", l, ld.kind, ld.bytes, ld.dst_off, ld.wait_g, ld.wait_e[0], ld.wait_e[1],
+           ld.wait_g_prev);
+  }
+  fflush(stdout);
   return SF_OK;
 }

@@ -83,8 +83,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// SF_MBAR_SLEEP_NS > 0: a failed try_wait backs off with nanosleep before polling again (experiment switch: a warp that
+// spins in the try_wait loop takes issue slots from the working warps of its scheduler)
+#ifndef SF_MBAR_SLEEP_NS
+#define SF_MBAR_SLEEP_NS 0
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
+    if (SF_MBAR_SLEEP_NS > 0) __nanosleep(SF_MBAR_SLEEP_NS);
   }
 }
 

@@ -228,3 +228,113 @@ extern "C" int sfdbg_umma_timing(int N, int n_mma, int shift, int mode, long lon
   cudaFree(d);
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// TMEM -> register read bandwidth (tcgen05.ld.32x32b): `warps` warps (warp w reads lane quarter w & 3) each issue `n_ld` loads
+// of COLS columns, PW loads in flight per tcgen05.wait::ld; mode 1 also converts every value to fp16 and stores it to shared
+// memory (what a conversion stage of the tokenizer / transformer epilogues does).  out[0] = cycles of the slowest warp,
+// out[1] = bytes read.  Every accumulator element of both tensor-core kernels moves through this path once per GEMM, so
+// bytes / cycles here bounds their epilogues.
+namespace sf {
+namespace {
+template <int COLS, int PW, int MODE>
+__global__ void __launch_bounds__(544, 1) tmem_ld_timing_kernel(int n_ld, int n_mma, int mma_n, long long* out) {
+  extern __shared__ __align__(128) unsigned char sbuf[];     // mode 1: [col / 8][128 rows][16 B] planar-chunk buffer, 512 columns
+  __shared__ uint32_t tmem_base_s;
+  __shared__ uint64_t bar;
+  __shared__ long long t_end[17];
+  using namespace tc;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_conv = (int)(blockDim.x >> 5) - (n_mma > 0 ? 1 : 0);       // with n_mma > 0 the LAST warp issues MMAs meanwhile
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == n_conv) {
+    // n_mma back-to-back 128 x mma_n x 16 MMAs on no-swizzle operands inside the buffer the other warps write (garbage data),
+    // accumulating into TMEM columns [256, 256 + mma_n): tensor-pipe operand reads from shared memory + accumulator writes
+    const long long t0 = clock64();
+    if (elect_one()) {
+      const uint64_t ad = make_desc(smem_u32(sbuf), 2048u, 128u), bd = make_desc(smem_u32(sbuf) + 8192u, (uint32_t)mma_n * 16u, 128u);
+      const uint32_t idesc = make_idesc(128, mma_n, false, true, true);
+      for (int k = 0; k < n_mma; ++k) umma_bf16(tmem_base_s + 256u, ad, bd, idesc, 1u);
+      umma_commit(&bar);
+      while (!mbar_try_wait(&bar, 0)) {
+      }
+    }
+    __syncwarp();
+    if (lane == 0) t_end[16] = clock64() - t0;
+  }
+  const uint32_t base = tmem_base_s + ((uint32_t)((warp & 3) * 32) << 16);
+  const int row = (warp & 3) * 32 + lane;
+  float acc = 0.f;
+  const long long t0 = clock64();
+  const uint32_t cmask = n_mma > 0 ? 255u : 511u;                       // stay clear of the MMA's accumulator columns
+  uint32_t col = (uint32_t)((warp >> 2) * COLS * PW) & cmask;
+  if (warp < n_conv)
+  for (int i = 0; i < n_ld; i += PW) {
+    float v[PW][COLS];
+#pragma unroll
+    for (int j = 0; j < PW; ++j) {
+      const uint32_t c = (col + (uint32_t)(j * COLS)) & cmask;
+      if (COLS == 16) tmem_ld16(base + c, v[j]);
+      else tmem_ld32(base + c, v[j]);
+    }
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < PW; ++j) {
+      if (MODE == 1) {
+        const uint32_t c = (col + (uint32_t)(j * COLS)) & cmask;
+#pragma unroll
+        for (int q = 0; q < COLS; q += 8)
+          *reinterpret_cast<uint4*>(sbuf + (size_t)((c + q) >> 3) * 2048 + row * 16) =
+              make_uint4(pack_f16x2(v[j][q], v[j][q + 1]), pack_f16x2(v[j][q + 2], v[j][q + 3]), pack_f16x2(v[j][q + 4], v[j][q + 5]),
+                         pack_f16x2(v[j][q + 6], v[j][q + 7]));
+      } else {
+        acc += v[j][0] + v[j][COLS - 1];
+      }
+    }
+    col = (col + (uint32_t)(COLS * PW * 4)) & cmask;
+  }
+  const long long t1 = clock64();
+  if (lane == 0 && warp < n_conv) t_end[warp] = t1 - t0;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long mx = 0;
+    for (int w = 0; w < n_conv; ++w) mx = t_end[w] > mx ? t_end[w] : mx;
+    out[0] = mx;
+    out[1] = (long long)n_conv * n_ld * COLS * 32 * 4;
+    out[2] = (long long)(acc == 12345.f);      // keeps the loads alive
+    out[3] = n_mma > 0 ? t_end[16] : 0;        // cycles of the MMA stream (issue -> completion)
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base_s, 512);
+}
+template <int COLS, int PW, int MODE>
+int run_tmem_ld(int warps, int n_ld, int n_mma, int mma_n, long long* d) {
+  const int smem = 64 * 2048;
+  cudaFuncSetAttribute(tmem_ld_timing_kernel<COLS, PW, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  tmem_ld_timing_kernel<COLS, PW, MODE><<<1, (warps + (n_mma > 0 ? 1 : 0)) * 32, smem>>>(n_ld / PW * PW, n_mma, mma_n, d);
+  return cudaDeviceSynchronize() == cudaSuccess ? 0 : -2;
+}
+}  // namespace
+}  // namespace sf
+
+extern "C" int sfdbg_tmem_ld_timing(int warps, int n_ld, int cols, int per_wait, int mode, int n_mma, int mma_n, long long* out_host) {
+  if (warps < 1 || warps > 16 || n_ld < 4 || n_mma < 0 || (n_mma > 0 && (mma_n < 16 || mma_n > 256 || mma_n % 16))) return -3;
+  long long* d = nullptr;
+  if (cudaMalloc(&d, 32) != cudaSuccess) return -1;
+  int rc = -3;
+#define SF_CASE(C_, P_, M_) if (cols == C_ && per_wait == P_ && mode == M_) rc = sf::run_tmem_ld<C_, P_, M_>(warps, n_ld, n_mma, mma_n, d);
+  SF_CASE(16, 1, 0) SF_CASE(16, 2, 0) SF_CASE(16, 4, 0) SF_CASE(32, 1, 0) SF_CASE(32, 2, 0)
+  SF_CASE(16, 1, 1) SF_CASE(16, 2, 1) SF_CASE(32, 1, 1)
+#undef SF_CASE
+  if (rc == 0) cudaMemcpy(out_host, d, 32, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return rc;
+}

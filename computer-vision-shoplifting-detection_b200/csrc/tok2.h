@@ -29,7 +29,15 @@ constexpr int kRows = 128;               // MMA M
 constexpr uint32_t kPlane = 2048;        // bytes of one 8-column chunk of a 128-row activation buffer
 constexpr int kTeams = 2;                // epilogue teams: warps 4-11 and 12-19; a team = 4 TMEM lane quarters x 2 column halves
 constexpr int kTeamWarps = 8;
-constexpr int kThreads = 128 + kTeams * kTeamWarps * 32;   // warp 0: MMA issue, warp 1: TMA, warps 2-3: idle, then the teams
+// warp 0: MMA issue, warp 1: TMA, then the teams from warp kFirstEpiWarp on.  A warp reads the TMEM lane quarter warp % 4, and a
+// team needs two warps per quarter: any even first warp works.  Starting at warp 2 (no idle warps, 576 threads) gives every
+// thread 112 registers instead of 96 at 640 threads (SF_TOK2_FIRST_EPI_WARP=4 restores the older layout).
+#ifndef SF_TOK2_FIRST_EPI_WARP
+#define SF_TOK2_FIRST_EPI_WARP 2
+#endif
+constexpr int kFirstEpiWarp = SF_TOK2_FIRST_EPI_WARP;
+static_assert(kFirstEpiWarp >= 2 && kFirstEpiWarp % 2 == 0, "teams start at an even warp behind the MMA and TMA warps");
+constexpr int kThreads = kFirstEpiWarp * 32 + kTeams * kTeamWarps * 32;
 constexpr int kMaxGroups = 80, kMaxStages = 72, kMaxLoads = 10, kMaxMma = 384;
 constexpr int kMaxC0 = 64;               // block-0 output channels handled by the CUDA-core graph conv
 
@@ -64,6 +72,52 @@ struct Stage {               // E item (index = position in its TEAM's sequence)
   int32_t pad[2];            // 80 bytes: the kernel loads a stage as five 16-byte words
 };
 static_assert(sizeof(Stage) == 80, "Stage is loaded as five 16-byte words");
+
+// Kernel form of a Stage: 32 bytes = two 16-byte loads per stage instead of five, and 6 live registers instead of 14 (the
+// epilogue loop runs at the 96-register limit of 18 resident warps).  Barrier offsets are stored / 8 (0: none).
+struct StageK {
+  uint32_t w0;               // type [0,2) | flags [2,5) | n_cg [5,13) | tmem_col [13,22) | bias_period [22,30)
+  uint32_t w1;               // bar_g | bar_l << 16
+  uint32_t w2;               // bar_eo | bar_g_prev << 16
+  uint32_t w3;               // bar_self | p0 << 16 | (p1 - p0) << 24
+  uint32_t dst_off, bias_off;
+  uint32_t pad[2];
+#ifdef __CUDACC__
+#define SF_HD __host__ __device__ __forceinline__
+#else
+#define SF_HD inline
+#endif
+  SF_HD int type() const { return (int)(w0 & 3u); }
+  SF_HD int flags() const { return (int)((w0 >> 2) & 7u); }
+  SF_HD int n_cg() const { return (int)((w0 >> 5) & 0xFFu); }
+  SF_HD int tmem_col() const { return (int)((w0 >> 13) & 0x1FFu); }
+  SF_HD int bias_period() const { return (int)((w0 >> 22) & 0xFFu); }
+  SF_HD uint32_t bar_g() const { return (w1 & 0xFFFFu) << 3; }
+  SF_HD uint32_t bar_l() const { return (w1 >> 16) << 3; }
+  SF_HD uint32_t bar_eo() const { return (w2 & 0xFFFFu) << 3; }
+  SF_HD uint32_t bar_g_prev() const { return (w2 >> 16) << 3; }
+  SF_HD uint32_t bar_self() const { return (w3 & 0xFFFFu) << 3; }
+  SF_HD int p0() const { return (int)((w3 >> 16) & 0xFFu); }
+  SF_HD int p1() const { return (int)((w3 >> 16) & 0xFFu) + (int)(w3 >> 24); }
+#undef SF_HD
+};
+static_assert(sizeof(StageK) == 32, "StageK is loaded as two 16-byte words");
+// false when a field does not fit its bit range
+inline bool pack_stage(const Stage& s, StageK* k) {
+  auto bar = [](uint32_t off) { return off >> 3; };
+  const bool ok = s.type >= 0 && s.type < 4 && s.flags >= 0 && s.flags < 8 && s.n_cg >= 0 && s.n_cg < 256 && s.tmem_col >= 0 && s.tmem_col < 512 &&
+                  s.bias_period >= 0 && s.bias_period < 256 && s.p0 >= 0 && s.p0 < 256 && s.p1 >= s.p0 && s.p1 - s.p0 < 256 &&
+                  !((s.bar_g | s.bar_l | s.bar_eo | s.bar_g_prev | s.bar_self) & 7u) &&
+                  bar(s.bar_g | s.bar_l | s.bar_eo | s.bar_g_prev | s.bar_self) < 65536u;
+  k->w0 = (uint32_t)s.type | (uint32_t)s.flags << 2 | (uint32_t)s.n_cg << 5 | (uint32_t)s.tmem_col << 13 | (uint32_t)s.bias_period << 22;
+  k->w1 = bar(s.bar_g) | bar(s.bar_l) << 16;
+  k->w2 = bar(s.bar_eo) | bar(s.bar_g_prev) << 16;
+  k->w3 = bar(s.bar_self) | (uint32_t)s.p0 << 16 | (uint32_t)(s.p1 - s.p0) << 24;
+  k->dst_off = s.dst_off;
+  k->bias_off = s.bias_off;
+  k->pad[0] = k->pad[1] = 0;
+  return ok;
+}
 
 enum LoadKind { LD_WEIGHTS = 0, LD_POSES = 1 };
 struct Load {                // L item

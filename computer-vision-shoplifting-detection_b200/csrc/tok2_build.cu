@@ -706,8 +706,12 @@ void build_program(const Static& st, int T, int max_smem, Program* out) {
   for (int t = 0; t < kTeams; ++t) {
     if (pr.stages[t].empty()) return fail("an epilogue team has no work");
     pr.stages[t][0].wait_g_prev = last_g;
+    // (only the team's FIRST pose-reading stage of a tile waits: its later stages run behind it in program order)
     for (Stage& s : pr.stages[t])
-      if (s.type == ST_G0 || s.type == ST_XEPI0) s.wait_l = (int)pr.loads.size() - 1;
+      if (s.type == ST_G0 || s.type == ST_XEPI0) {
+        s.wait_l = (int)pr.loads.size() - 1;
+        break;
+      }
   }
   pr.loads[0].wait_g_prev = (int16_t)last_g;
   // ... and the first MMA group overwrites accumulator columns the previous tile's token stage may still be reading

@@ -14,6 +14,7 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <vector>
 
 #include "sf_internal.h"
 #include "tc_common.cuh"
@@ -91,6 +92,13 @@ __device__ __forceinline__ void issue_mma(uint32_t tmem, const Mma& m, uint32_t 
   umma_bf16(tmem + (m.d & 0x1FFu), ad, bd, m.idesc, (m.d >> 16) & 1u);
 }
 
+// per-stage phase stamps (table loaded / body done / arrived; one stamping warp per team) cost registers in the epilogue
+// loop: only with `make EXTRA=-DSF_TOK2_FINE_STAMPS` (profiles/tok2_stage_timing.py)
+#ifdef SF_TOK2_FINE_STAMPS
+#define T2_FINE(id) T2_STAMP(id)
+#else
+#define T2_FINE(id) do { } while (0)
+#endif
 #define T2_STAMP(id)                                                      \
   do {                                                                    \
     if (timing && lane == 0 && stamp_i < stamp_end) {                     \
@@ -121,15 +129,15 @@ __device__ __forceinline__ void store16(unsigned char* dst_row, int cg, const fl
 // The weight table is read with broadcast shared-memory loads, the FMAs are packed fp32x2.  Rows beyond the tile's
 // windows produce finite values nobody reads.
 template <int KW, bool F16>
-__device__ __forceinline__ void g0_stage(const Plan& pl, const Stage& s, unsigned char* smem, int row, int half, int my_w, int my_v, int nw,
+__device__ __forceinline__ void g0_stage(const Plan& pl, const StageK& s, unsigned char* smem, int row, int half, int my_w, int my_v, int nw,
                                          int* pz) {
-  const int t = s.p0 + half;
-  if (t >= s.p1) return;
+  const int t = s.p0() + half;
+  if (t >= s.p1()) return;
   const int V = pl.V, tv4 = pl.T0 * V * 4, cp0 = pl.cp0;
   const bool valid = row < pl.rows && my_w < nw;
   const bool two = pl.c_in > 1;
   const int chunks = cp0 / 8;                         // 8-channel granules per time step
-  const int c8_lo = s.tmem_col, c8_hi = s.tmem_col + s.n_cg;     // this stage's share of the output channels
+  const int c8_lo = s.tmem_col(), c8_hi = s.tmem_col() + s.n_cg();     // this stage's share of the output channels
   unsigned char* dst_row = smem + s.dst_off + (size_t)(half * chunks) * kPlane + (size_t)row * 16;
   float2 mx = make_float2(0.f, 0.f), my = make_float2(0.f, 0.f);
   if (valid) {
@@ -146,13 +154,21 @@ __device__ __forceinline__ void g0_stage(const Plan& pl, const Stage& s, unsigne
       x0[k] = *reinterpret_cast<const float*>(xp + db);
       x1[k] = two ? *reinterpret_cast<const float*>(xp + tv4 + db) : 0.f;
     }
-    float a0 = hc.x, a1 = hc.y, chk = 0.f;
+    float a0 = hc.x, a1 = hc.y;
 #pragma unroll
     for (int k = 0; k < KW; ++k) {
-      chk = fmaf(x0[k], 0.f, fmaf(x1[k], 0.f, chk));        // stays 0 unless a gathered pose is inf or NaN
       a0 = fmaf(cf[k].x, x0[k], a0);
       a1 = fmaf(cf[k].y, x1[k], a1);
     }
+#ifdef SF_TOK2_G0_CHK_CHAIN
+    float chk = 0.f;
+#pragma unroll
+    for (int k = 0; k < KW; ++k) chk = fmaf(x0[k], 0.f, fmaf(x1[k], 0.f, chk));
+#else
+    // stays 0 unless a gathered pose is inf or NaN: a non-finite input makes its mixed value non-finite whatever the
+    // coefficient (0 * inf = NaN; unused ELL entries have coefficient 0 and gather the thread's own keypoint)
+    const float chk = fmaf(a0, 0.f, a1 * 0.f);
+#endif
     if (chk == 0.f) {
       mx = make_float2(a0, a0);
       my = make_float2(a1, a1);
@@ -196,18 +212,23 @@ __device__ __forceinline__ void g0_stage(const Plan& pl, const Stage& s, unsigne
   }
 }
 
+#ifndef SF_TOK2_XEPI_LOADS
+#define SF_TOK2_XEPI_LOADS 1
+#endif
+constexpr int kXepiLoads = SF_TOK2_XEPI_LOADS;     // TMEM loads in flight per wait in block 0's output stage (1, 2 or 4)
+
 // Block 0 output for output times [p0, p1): x1 = relu(acc + BN-folded strided 1x1 residual conv of the raw poses + bias)
 // (gcae.py:237-259); the residual (2 input channels) is added in fp32 here instead of going through the tensor cores.
 // The two column halves of a team take alternate 16-channel groups.
 template <bool F16>
-__device__ __forceinline__ void xepi0_stage(const Plan& pl, const Stage& s, unsigned char* smem, uint32_t lane_base, int row, int half, int my_w,
+__device__ __forceinline__ void xepi0_stage(const Plan& pl, const StageK& s, unsigned char* smem, uint32_t lane_base, int row, int half, int my_w,
                                             int my_v, int nw, int team) {
   const int V = pl.V, tv = pl.T0 * V, cp0 = pl.cp0;
   const bool valid = row < pl.rows && my_w < nw;
   const bool two = pl.c_in > 1;
   constexpr int kMaxT = 8;                               // output time steps per stage
   float xa[kMaxT], xb[kMaxT];
-  const int ntp = (int)s.p1 - (int)s.p0;
+  const int ntp = (int)s.p1() - (int)s.p0();
   {
     const float* xw = reinterpret_cast<const float*>(smem + pl.off_xin) + my_w * pl.per_w + my_v;
     float sc0 = 0.f, sh0 = 0.f, sc1 = 0.f, sh1 = 0.f;
@@ -225,7 +246,7 @@ __device__ __forceinline__ void xepi0_stage(const Plan& pl, const Stage& s, unsi
     for (int i = 0; i < kMaxT; ++i) {
       xa[i] = xb[i] = 0.f;
       if (valid && i < ntp) {
-        const float* xp = xw + pl.stride0 * ((int)s.p0 + i) * V;
+        const float* xp = xw + pl.stride0 * ((int)s.p0() + i) * V;
         float u = xp[0], w = two ? xp[tv] : 0.f;
         if (!(fmaf(u, 0.f, w * 0.f) == 0.f)) u = w = 0.f;                 // inf / NaN (the window is already flagged by its G0 stages)
         xa[i] = fmaf(u, sc0, sh0);
@@ -234,26 +255,34 @@ __device__ __forceinline__ void xepi0_stage(const Plan& pl, const Stage& s, unsi
     }
   }
   // this chunk of x1 overwrites the pose slot: every thread of the team has its poses in registers first
-  if (s.flags & SF_TEAM_SYNC) named_bar_sync(1 + team, kTeamWarps * 32);
+  if (s.flags() & SF_TEAM_SYNC) named_bar_sync(1 + team, kTeamWarps * 32);
   unsigned char* dst_row = smem + s.dst_off + (size_t)row * 16;
   const float4* tab = reinterpret_cast<const float4*>(smem + pl.off_r0tab);
   const int cgs = cp0 / 16;
   for (int cg = half; cg < cgs; cg += 2) {
 #pragma unroll
-    for (int i = 0; i < kMaxT; ++i) {
-      if (i < ntp) {
-        float a[16];
-        tmem_ld16(lane_base + (uint32_t)(s.tmem_col + i * cp0 + cg * 16), a);
-        tmem_ld_wait();
-        const float2 u2 = make_float2(xa[i], xa[i]), w2 = make_float2(xb[i], xb[i]);
+    for (int i0 = 0; i0 < kMaxT; i0 += kXepiLoads) {
+      if (i0 < ntp) {
+        float a[kXepiLoads][16];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {                    // 4 output channels per table entry (rx, ry, rb)
-          const float4 rx = tab[cg * 12 + 3 * g], ry = tab[cg * 12 + 3 * g + 1], rb = tab[cg * 12 + 3 * g + 2];
-          const float2 r0 = fma2(u2, make_float2(rx.x, rx.y), fma2(w2, make_float2(ry.x, ry.y), make_float2(rb.x, rb.y)));
-          const float2 r1 = fma2(u2, make_float2(rx.z, rx.w), fma2(w2, make_float2(ry.z, ry.w), make_float2(rb.z, rb.w)));
-          a[4 * g + 0] += r0.x; a[4 * g + 1] += r0.y; a[4 * g + 2] += r1.x; a[4 * g + 3] += r1.y;
+        for (int u = 0; u < kXepiLoads; ++u)
+          if (i0 + u < ntp) tmem_ld16(lane_base + (uint32_t)(s.tmem_col() + (i0 + u) * cp0 + cg * 16), a[u]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int u = 0; u < kXepiLoads; ++u) {
+          const int i = i0 + u;
+          if (i < ntp) {
+            const float2 u2 = make_float2(xa[i], xa[i]), w2 = make_float2(xb[i], xb[i]);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {                    // 4 output channels per table entry (rx, ry, rb)
+              const float4 rx = tab[cg * 12 + 3 * g], ry = tab[cg * 12 + 3 * g + 1], rb = tab[cg * 12 + 3 * g + 2];
+              const float2 r0 = fma2(u2, make_float2(rx.x, rx.y), fma2(w2, make_float2(ry.x, ry.y), make_float2(rb.x, rb.y)));
+              const float2 r1 = fma2(u2, make_float2(rx.z, rx.w), fma2(w2, make_float2(ry.z, ry.w), make_float2(rb.z, rb.w)));
+              a[u][4 * g + 0] += r0.x; a[u][4 * g + 1] += r0.y; a[u][4 * g + 2] += r1.x; a[u][4 * g + 3] += r1.y;
+            }
+            store16<true, F16>(dst_row, i * cgs + cg, a[u]);
+          }
         }
-        store16<true, F16>(dst_row, i * cgs + cg, a);
       }
     }
   }
@@ -263,17 +292,21 @@ __device__ __forceinline__ void xepi0_stage(const Plan& pl, const Stage& s, unsi
 // stage.  Reading them field by field from the kernel-parameter constant bank cost ~1.5 k cycles PER STAGE: the 20 KB plan
 // does not fit the constant cache, so every stage paid several dependent constant-cache misses.
 struct Tables {
-  const Stage* stages[kTeams];
+  const StageK* stages[kTeams];
   const Group* groups;
   const Mma* mma;
 };
-__device__ __forceinline__ void load_stage(Stage* dst, const Stage* src) {
-  static_assert(sizeof(Stage) == 80, "Stage is loaded as five 16-byte words");
+__device__ __forceinline__ void load_stage(StageK* dst, const StageK* src) {
   const uint4* p = reinterpret_cast<const uint4*>(src);
-  uint4* d = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-  for (int i = 0; i < 5; ++i) d[i] = __ldg(p + i);
+  const uint4 a = __ldg(p), b = __ldg(p + 1);
+  dst->w0 = a.x; dst->w1 = a.y; dst->w2 = a.z; dst->w3 = a.w;
+  dst->dst_off = b.x; dst->bias_off = b.y;
 }
+
+#ifndef SF_TOK2_CVT_LOADS
+#define SF_TOK2_CVT_LOADS 2
+#endif
+constexpr int kCvtLoads = SF_TOK2_CVT_LOADS;      // TMEM loads in flight per wait in a conversion stage
 
 template <bool F16>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -310,10 +343,14 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
+#ifdef SF_TOK2_FINE_STAMPS
+  const bool timing = g_tok2_timing_on && blockIdx.x == 0 && (warp == 0 || warp == kFirstEpiWarp || warp == kFirstEpiWarp + kTeamWarps);   // one stamping warp per role
+#else
   const bool timing = g_tok2_timing_on && blockIdx.x == 0;
-  // debug stamps: MMA warp in [0, 1024), team 0 (warp 4) in [1024, 2560), team 1 (warp 8) in [2560, 4096)
-  int stamp_i = warp == 0 ? 0 : (warp == 4 ? 1024 : 2560);
-  const int stamp_end = warp == 0 ? 1022 : (warp == 4 ? 2558 : 4094);
+#endif
+  // debug stamps: MMA warp in [0, 1024), first warp of team 0 in [1024, 2560), first warp of team 1 in [2560, 4096)
+  int stamp_i = warp == 0 ? 0 : (warp == kFirstEpiWarp ? 1024 : 2560);
+  const int stamp_end = warp == 0 ? 1022 : (warp == kFirstEpiWarp ? 2558 : 4094);
   const uint32_t stamp_it = (int64_t)blockIdx.x + gridDim.x < n_tiles ? 1u : 0u;     // steady-state tile when there is one
 
   if (warp == 0) {
@@ -379,11 +416,11 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
         }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= kFirstEpiWarp) {
     // =================================================================== epilogue: two teams of eight warps
     // (a team = 4 TMEM lane quarters x 2 column halves; many resident warps are what hides the CUDA-core latencies)
-    const int team = (warp - 4) >> 3, q = warp & 3, half = ((warp - 4) >> 2) & 1;
-    const int tt = (int)threadIdx.x - 128 - team * (kTeamWarps * 32);     // thread within the team
+    const int team = (warp - kFirstEpiWarp) >> 3, q = warp & 3, half = ((warp - kFirstEpiWarp) >> 2) & 1;
+    const int tt = (int)threadIdx.x - kFirstEpiWarp * 32 - team * (kTeamWarps * 32);     // thread within the team
     const int row = q * 32 + lane;
     const int V = pl.V, rows = pl.rows;
     const int my_w = row / V, my_v = row - my_w * V;
@@ -396,35 +433,38 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
       const int nw = (int)((B - w_first) < (int64_t)pl.WT ? (B - w_first) : (int64_t)pl.WT);
       int* pz = poison + par * 64;
       for (int e = 0; e < n_st; ++e) {
-        Stage s;
-        load_stage(&s, tabs.stages[team] + e);
+        StageK s;
+        load_stage(&s, tabs.stages[team] + e);     // (hoisting this pointer out of the loop costs two registers -> spills: measured slower)
+        if (timing && it == stamp_it && tt < 32) T2_FINE(5000 + e);
         // (every warp of the team waits on the mbarriers itself: try_wait carries a suspend-time hint, see tc_common.cuh; one
         // polling warp + a named barrier for the other seven measured slower, 1.93 vs 1.87 ms)
-        if (s.bar_g) mbar_wait(reinterpret_cast<uint64_t*>(smem + s.bar_g), par);
-        if (s.bar_l) mbar_wait(reinterpret_cast<uint64_t*>(smem + s.bar_l), par);
-        if (s.bar_eo) mbar_wait(reinterpret_cast<uint64_t*>(smem + s.bar_eo), par);
-        if (s.bar_g_prev && it > 0) mbar_wait(reinterpret_cast<uint64_t*>(smem + s.bar_g_prev), par ^ 1u);
+        if (s.bar_g()) mbar_wait(reinterpret_cast<uint64_t*>(smem + s.bar_g()), par);
+        if (s.bar_l()) mbar_wait(reinterpret_cast<uint64_t*>(smem + s.bar_l()), par);
+        if (s.bar_eo()) mbar_wait(reinterpret_cast<uint64_t*>(smem + s.bar_eo()), par);
+        if (s.bar_g_prev() && it > 0) mbar_wait(reinterpret_cast<uint64_t*>(smem + s.bar_g_prev()), par ^ 1u);
         tc_fence_after();
-        if (timing && it == stamp_it && q == 0) T2_STAMP(2000 + e);
-        if (s.type == ST_CVT) {
-          const bool relu = s.flags & SF_RELU, bias = s.flags & SF_BIAS;
+        if (timing && it == stamp_it && tt < 32) T2_STAMP(2000 + e);
+        if (s.type() == ST_CVT) {
+          const bool relu = s.flags() & SF_RELU, bias = s.flags() & SF_BIAS;
           const float* bp = reinterpret_cast<const float*>(smem + s.bias_off);
           unsigned char* dst = smem + s.dst_off + (size_t)row * 16;
           // bias column of this warp's next column group, kept incrementally (no division in the loop): cg advances by 2
-          const int period = s.bias_period > 0 ? s.bias_period : 16;
+          const int period = s.bias_period() > 0 ? s.bias_period() : 16;
           int bcol = half * 16;
           while (bcol >= period) bcol -= period;
-          // this warp's column groups: cg = half, half + 2, ...; two TMEM loads in flight before one wait
-          for (int cg0 = half; cg0 < (int)s.n_cg; cg0 += 4) {
-            float a[2][16];
+          // this warp's column groups: cg = half, half + 2, ...; kCvtLoads TMEM loads in flight before one wait (a TMEM load
+          // takes 300+ cycles while the tensor pipe is busy with the next group: fewer, wider round trips per stage)
+          for (int cg0 = half; cg0 < (int)s.n_cg(); cg0 += 2 * kCvtLoads) {
+            float a[kCvtLoads][16];
 #pragma unroll
-            for (int b = 0; b < 2; ++b)
-              if (cg0 + 2 * b < (int)s.n_cg) tmem_ld16(lane_base + (uint32_t)(s.tmem_col + (cg0 + 2 * b) * 16), a[b]);
+            for (int b = 0; b < kCvtLoads; ++b)
+              if (cg0 + 2 * b < (int)s.n_cg()) tmem_ld16(lane_base + (uint32_t)(s.tmem_col() + (cg0 + 2 * b) * 16), a[b]);
             tmem_ld_wait();
+            if (timing && it == stamp_it && tt < 32 && cg0 == half) T2_FINE(8000 + e);
 #pragma unroll
-            for (int b = 0; b < 2; ++b) {
+            for (int b = 0; b < kCvtLoads; ++b) {
               const int cg = cg0 + 2 * b;
-              if (cg < (int)s.n_cg) {
+              if (cg < (int)s.n_cg()) {
                 if (bias) {
                   const float* b16 = bp + bcol;
 #pragma unroll
@@ -441,11 +481,12 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
               bcol += 32;
               while (bcol >= period) bcol -= period;
             }
+            if (timing && it == stamp_it && tt < 32 && cg0 == half) T2_FINE(9000 + e);
           }
-        } else if (s.type == ST_G0) {
+        } else if (s.type() == ST_G0) {
           if (pl.ell_width <= 5) g0_stage<5, F16>(pl, s, smem, row, half, my_w, my_v, nw, pz);
           else g0_stage<8, F16>(pl, s, smem, row, half, my_w, my_v, nw, pz);
-        } else if (s.type == ST_XEPI0) {
+        } else if (s.type() == ST_XEPI0) {
           xepi0_stage<F16>(pl, s, smem, lane_base, row, half, my_w, my_v, nw, team);
         } else {   // ST_TOKENS
           const float* bp = reinterpret_cast<const float*>(smem + s.bias_off);
@@ -467,7 +508,7 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
                 for (int e = 0; e < 16; ++e) acc[e] = 0.f;
                 for (int t = t0; t < t1; ++t) {
                   float a[16];
-                  tmem_ld16(lane_base + (uint32_t)(s.tmem_col + (t * cpt + g) * 16), a);
+                  tmem_ld16(lane_base + (uint32_t)(s.tmem_col() + (t * cpt + g) * 16), a);
                   tmem_ld_wait();
 #pragma unroll
                   for (int e = 0; e < 16; ++e) {
@@ -489,9 +530,9 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
               }
             }
           } else
-          for (int cg = half; cg < (int)s.n_cg; cg += 2) {
+          for (int cg = half; cg < (int)s.n_cg(); cg += 2) {
             float a[16];
-            tmem_ld16(lane_base + (uint32_t)(s.tmem_col + cg * 16), a);
+            tmem_ld16(lane_base + (uint32_t)(s.tmem_col() + cg * 16), a);
             tmem_ld_wait();
             if (live) {
               const int t = (cg * 16) / pl.cp_last, c0 = cg * 16 - t * pl.cp_last;      // cp_last is a multiple of 16
@@ -514,10 +555,12 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
             bulk_wait_read();               // the staging area aliases activation storage: free it before the stage completes
           }
         }
+        if (timing && it == stamp_it && tt < 32) T2_FINE(6000 + e);
         fence_proxy_async();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(reinterpret_cast<uint64_t*>(smem + s.bar_self));
+        if (lane == 0) mbar_arrive(reinterpret_cast<uint64_t*>(smem + s.bar_self()));
+        if (timing && it == stamp_it && tt < 32) T2_FINE(7000 + e);
       }
     }
     if (tt == 0) bulk_wait_all();
@@ -584,21 +627,24 @@ static Uploaded* tok2_program(const sf_model* m, int T) {
     u->prog.plan.const_src = s->blob_dev;
     const size_t n0 = u->prog.stages[0].size(), n1 = u->prog.stages[1].size();
     const size_t ng = u->prog.groups.size(), nm = u->prog.mma.size();
-    const size_t off_g = (n0 + n1) * sizeof(Stage), off_m = off_g + ng * sizeof(Group);
-    if (cudaMalloc((void**)&u->tables_dev, off_m + (nm + 64) * sizeof(Mma)) != cudaSuccess ||
+    std::vector<StageK> sk(n0 + n1);
+    bool packed = true;
+    for (size_t i = 0; i < n0; ++i) packed &= pack_stage(u->prog.plan.stages[0][i], &sk[i]);
+    for (size_t i = 0; i < n1; ++i) packed &= pack_stage(u->prog.plan.stages[1][i], &sk[n0 + i]);
+    const size_t off_g = (n0 + n1) * sizeof(StageK), off_m = off_g + ng * sizeof(Group);
+    if (!packed || cudaMalloc((void**)&u->tables_dev, off_m + (nm + 64) * sizeof(Mma)) != cudaSuccess ||
         cudaMemset(u->tables_dev, 0, off_m + (nm + 64) * sizeof(Mma)) != cudaSuccess ||
-        cudaMemcpy(u->tables_dev, u->prog.plan.stages[0], n0 * sizeof(Stage), cudaMemcpyHostToDevice) != cudaSuccess ||
-        cudaMemcpy(u->tables_dev + n0 * sizeof(Stage), u->prog.plan.stages[1], n1 * sizeof(Stage), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(u->tables_dev, sk.data(), (n0 + n1) * sizeof(StageK), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(u->tables_dev + off_g, u->prog.groups.data(), ng * sizeof(Group), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(u->tables_dev + off_m, u->prog.mma.data(), nm * sizeof(Mma), cudaMemcpyHostToDevice) != cudaSuccess) {
       cudaGetLastError();
       u->prog.ok = false;
-      u->prog.why = "uploading the stage tables failed";
+      u->prog.why = packed ? "uploading the stage tables failed" : "a stage field does not fit the packed stage table";
     }
-    u->tabs.stages[0] = reinterpret_cast<const Stage*>(u->tables_dev);
-    u->tabs.stages[1] = reinterpret_cast<const Stage*>(u->tables_dev + n0 * sizeof(Stage));
-    u->tabs.groups = reinterpret_cast<const Group*>(u->tables_dev + (n0 + n1) * sizeof(Stage));
-    u->tabs.mma = reinterpret_cast<const Mma*>(u->tables_dev + (n0 + n1) * sizeof(Stage) + u->prog.groups.size() * sizeof(Group));
+    u->tabs.stages[0] = reinterpret_cast<const StageK*>(u->tables_dev);
+    u->tabs.stages[1] = reinterpret_cast<const StageK*>(u->tables_dev + n0 * sizeof(StageK));
+    u->tabs.groups = reinterpret_cast<const Group*>(u->tables_dev + off_g);
+    u->tabs.mma = reinterpret_cast<const Mma*>(u->tables_dev + off_m);
   }
   s->cache.by_T[T] = u;
   return u;
