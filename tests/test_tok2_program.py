@@ -97,3 +97,18 @@ def test_host_model_is_rejected_by_compute_entry_points(dropin1, dropin2):
         assert rc == -1
     finally:
         lib.sf_model_destroy(h)
+
+
+def test_program_dump_runs(dropin1, dropin2, capfd):
+    """`sfdbg_tok2_describe` (the listing profiles/tok2_describe.py prints next to the GPU timelines) walks the same program."""
+    model = build_model(dropin1, dropin2, "A")
+    lib, h = host_model(model)
+    try:
+        lib.sfdbg_tok2_describe.restype = C.c_int
+        lib.sfdbg_tok2_describe.argtypes = [C.c_void_p, C.c_int32]
+        N.check(lib.sfdbg_tok2_describe(h, 24), "sfdbg_tok2_describe")
+        out = capfd.readouterr().out
+        assert "plan: WT=7" in out and "TOKENS" in out and "G0 " in out
+        assert lib.sfdbg_tok2_describe(h, 100000) != 0          # window length outside the program's range
+    finally:
+        lib.sf_model_destroy(h)
