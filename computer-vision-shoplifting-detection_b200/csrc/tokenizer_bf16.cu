@@ -201,6 +201,12 @@ __device__ __forceinline__ void conv_issue(uint32_t d, uint32_t a_lo0, uint32_t 
   for (int ks = 0; ks < RS; ++ks) umma_bf16(d, desc_join(r_alo + ks * astep), desc_join(r_blo + ks * bstep), idesc, 1u);
 }
 
+// The clock64 stamps of the timeline tools (profiles/*_timing.py) are compiled in only with `make EXTRA=-DSF_STAMPS`: even
+// disabled at run time they cost the production kernels 2-5 % (tokenizer v2 1.717 -> 1.631 ms, transformer 1.086 -> 1.065 ms,
+// one-window tokenizer on config B 5.08 -> 4.89 ms per 65,536 windows).
+#if !defined(SF_STAMPS) && !defined(SF_TOK2_FINE_STAMPS)
+#define TOK_STAMP(id) do { } while (0)
+#else
 #define TOK_STAMP(id)                                                                   \
   do {                                                                                  \
     if (timing && threadIdx.x == 0 && stamp_i < 510) {                                  \
@@ -208,6 +214,7 @@ __device__ __forceinline__ void conv_issue(uint32_t d, uint32_t a_lo0, uint32_t 
       g_tok_timing[stamp_i++] = clock64();                                              \
     }                                                                                   \
   } while (0)
+#endif
 
 template <int kThreads>
 __global__ void __launch_bounds__(kThreads, kThreads == 256 ? kMaxOcc : 1)
@@ -335,6 +342,7 @@ tokenizer_bf16_kernel(const __grid_constant__ BfPlan pl, const float* __restrict
   uint32_t parity = 0;
   const bool timing = g_tok_timing_on && blockIdx.x == 0;
   int stamp_i = 0;
+  (void)timing; (void)stamp_i;                       // only used with -DSF_STAMPS
 
   const int64_t n_groups = (B + G - 1) / G;
   // raw poses of a window group are fetched by TMA one iteration ahead (one bulk copy, issued by thread 0)

@@ -30,6 +30,12 @@ namespace {
 
 using namespace tc;
 
+// The clock64 stamps of the timeline tools (profiles/*_timing.py) are compiled in only with `make EXTRA=-DSF_STAMPS`: even
+// disabled at run time they cost the production kernels 2-5 % (tokenizer v2 1.717 -> 1.631 ms, transformer 1.086 -> 1.065 ms,
+// one-window tokenizer on config B 5.08 -> 4.89 ms per 65,536 windows).
+#if !defined(SF_STAMPS) && !defined(SF_TOK2_FINE_STAMPS)
+#define XF_STAMP(id) do { } while (0)
+#else
 #define XF_STAMP(id)                                                             \
   do {                                                                           \
     if (timing && threadIdx.x == 0 && stamp_i < 1022) {                          \
@@ -37,6 +43,7 @@ using namespace tc;
       g_xf_timing[stamp_i++] = clock64();                                        \
     }                                                                            \
   } while (0)
+#endif
 
 constexpr int kThreads = 512;
 constexpr int kParts = kThreads / 128;  // warps sharing one 32-row lane group: each owns every kParts-th 16-column group
@@ -213,7 +220,16 @@ template <bool F16>
 __global__ void __launch_bounds__(kThreads, 1)
 transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo, const __grid_constant__ Transformer xf,
                         const float* __restrict__ tokens, int64_t B_max, int reduction, float* __restrict__ recon_out,
-                        float* __restrict__ scores, const DevCount cnt, const int flags) {
+                        float* __restrict__ scores, const DevCount cnt, const int flags_rt) {
+  // experiment switches of profiles/r2_summary.md (1: one polling warp + bar.sync, 2 / 8: busy test_wait spin, 4: q / k / v as three
+  // phases): a run-time value only with -DSF_XF_FLAGS_RUNTIME (SF_XF_FLAGS in the environment), otherwise the constant 0 so
+  // that the branches fold away
+#ifdef SF_XF_FLAGS_RUNTIME
+  const int flags = flags_rt;
+#else
+  constexpr int flags = 0;
+  (void)flags_rt;
+#endif
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t bar, cbar, wbar[2];      // MMA completion (phase / first GEMM of a chain); TMA completion per weight-ring slot
   __shared__ uint32_t tmem_base_s;
@@ -251,6 +267,7 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
   uint32_t parity = 0, wpar = 0, cpar = 0;
   const bool timing = g_xf_timing_on && blockIdx.x == 0;
   int stamp_i = 0;
+  (void)timing; (void)stamp_i;                       // only used with -DSF_STAMPS
 
   // index of the first / next GEMM op (for the weight ring)
   const int n_ops = prog.n_ops;

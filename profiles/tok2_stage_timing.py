@@ -1,4 +1,6 @@
-"""Per-stage phases of tokenizer v2's epilogue teams (CTA 0, steady-state tile): python profiles/tok2_stage_timing.py [config]
+"""(needs the stamps compiled in: `make -C computer-vision-shoplifting-detection_b200/csrc EXTRA=-DSF_STAMPS` after touching the kernel sources;
+the default build leaves them out because they cost the kernels 2-5 %)
+Per-stage phases of tokenizer v2's epilogue teams (CTA 0, steady-state tile): python profiles/tok2_stage_timing.py [config]
 For every stage of warp 4 (team 0) and warp 12 (team 1): table entry loaded -> waits done (start) -> body done -> arrived.
 Goes with profiles/tok2_describe.py (what each stage / group is).  Needs the fine stamps compiled in:
 `make -C computer-vision-shoplifting-detection_b200/csrc EXTRA=-DSF_TOK2_FINE_STAMPS` after touching tokenizer2_bf16.cu (they cost registers, so the

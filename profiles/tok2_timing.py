@@ -1,4 +1,6 @@
-"""Group / stage start stamps of CTA 0's second tile of tokenizer v2 (debug aid): python profiles/tok2_timing.py
+"""(needs the stamps compiled in: `make -C computer-vision-shoplifting-detection_b200/csrc EXTRA=-DSF_STAMPS` after touching the kernel sources;
+the default build leaves them out because they cost the kernels 2-5 %)
+Group / stage start stamps of CTA 0's second tile of tokenizer v2 (debug aid): python profiles/tok2_timing.py
 MMA warp: one stamp per G group just before its MMAs are issued (id 1000 + g); epilogue warp 4: one stamp per E stage
 after its waits (id 2000 + e).  Prints both timelines relative to the first stamp, cycles @ SM clock."""
 import ctypes as C, sys

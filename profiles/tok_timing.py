@@ -1,4 +1,6 @@
-"""Phase timeline of CTA 0 of the bf16 tokenizer (debug aid): python profiles/tok_timing.py"""
+"""(needs the stamps compiled in: `make -C computer-vision-shoplifting-detection_b200/csrc EXTRA=-DSF_STAMPS` after touching the kernel sources;
+the default build leaves them out because they cost the kernels 2-5 %)
+Phase timeline of CTA 0 of the bf16 tokenizer (debug aid): python profiles/tok_timing.py"""
 import ctypes as C, sys
 sys.path.insert(0, "."); sys.path.insert(0, "computer-vision-shoplifting-detection_b200")
 import numpy as np, torch

@@ -1,4 +1,6 @@
-"""Per-op timeline of CTA 0 of the bf16 transformer (debug aid): python profiles/xf_timing.py"""
+"""(needs the stamps compiled in: `make -C computer-vision-shoplifting-detection_b200/csrc EXTRA=-DSF_STAMPS` after touching the kernel sources;
+the default build leaves them out because they cost the kernels 2-5 %)
+Per-op timeline of CTA 0 of the bf16 transformer (debug aid): python profiles/xf_timing.py"""
 import ctypes as C, sys, os
 FULL = os.environ.get("XF_TIMING_FULL") is not None
 sys.path.insert(0, "."); sys.path.insert(0, "computer-vision-shoplifting-detection_b200")
