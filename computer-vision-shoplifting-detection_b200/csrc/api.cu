@@ -12,6 +12,18 @@
 
 using namespace sf;
 
+#include <atomic>
+namespace sf {
+static std::atomic<long long> g_launches[LK_COUNT];
+void count_launch(int kind) { g_launches[kind].fetch_add(1, std::memory_order_relaxed); }
+}  // namespace sf
+// Launches so far of [tokenizer v2, one-window tensor-core tokenizer, fp32 tokenizer, tensor-core transformer, fp32 transformer]
+// (host-side counters; debugging / test aid, not part of the C ABI)
+extern "C" int sfdbg_launch_counts(long long* out, int n) {
+  for (int i = 0; i < n && i < LK_COUNT; ++i) out[i] = g_launches[i].load(std::memory_order_relaxed);
+  return LK_COUNT;
+}
+
 namespace {
 inline int64_t align256(int64_t x) { return (x + 255) & ~int64_t(255); }
 

@@ -19,6 +19,9 @@ constexpr int kHalo = 4;          // its padding
 
 // ---- error plumbing -----------------------------------------------------------------
 void set_error(const char* fmt, ...);
+// host-side launch counters (sfdbg_launch_counts): which kernel served a call -- the tests' proof that the tensor-core kernels ran
+enum LaunchKind { LK_TOK2 = 0, LK_TOK_BF16 = 1, LK_TOK_FP32 = 2, LK_XF_TC = 3, LK_XF_FP32 = 4, LK_COUNT = 5 };
+void count_launch(int kind);
 #define SF_CUDA_OK(expr)                                                                    \
   do {                                                                                      \
     cudaError_t _e = (expr);                                                                \

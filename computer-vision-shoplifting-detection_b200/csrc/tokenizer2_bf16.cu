@@ -682,6 +682,7 @@ int launch_tokenizer2(const sf_model* m, const float* poses, int64_t B, int T, f
   const Plan& pl = u->prog.plan;
   const int64_t n_tiles = (B + pl.WT - 1) / pl.WT;
   const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)m->sm_count);
+  count_launch(LK_TOK2);
   if (m->tok2->st.f16) {
     SF_CUDA_OK(cudaFuncSetAttribute(tokenizer2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
     tokenizer2_kernel<true><<<grid, kThreads, pl.smem_bytes, st>>>(pl, poses, tokens, B, cnt, u->tabs);

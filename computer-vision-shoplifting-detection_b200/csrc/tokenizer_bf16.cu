@@ -788,6 +788,7 @@ int launch_tokenizer_bf16(const sf_model* m, const float* poses, int64_t B, int 
   const char* why = "";
   SF_REQUIRE(build_plan(m, T, 1, &pl, &why), SF_E_UNSUPPORTED, "bf16 tensor-core tokenizer does not cover this shape: %s", why);
   SF_REQUIRE(((uintptr_t)poses & 15) == 0, SF_E_INVALID, "pose buffer must be 16-byte aligned (TMA bulk copies)");
+  count_launch(LK_TOK_BF16);
   // CTAs per SM: shared memory (1 KB driver reservation per CTA), registers (128 x 256 threads) and TMEM columns --
   // co-resident CTAs must all get their tensor-memory allocation or they would serialise on tcgen05.alloc.
   int smem_per_sm = 0;

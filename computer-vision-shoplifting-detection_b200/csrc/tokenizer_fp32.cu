@@ -413,6 +413,7 @@ int64_t tokenizer_fp32_workspace(const sf_model* m, int64_t B, int T) {
 int launch_tokenizer_fp32(const sf_model* m, const float* poses, int64_t B, int T, float* tokens, void* ws,
                           int64_t ws_bytes, cudaStream_t st) {
   if (B == 0) return SF_OK;
+  count_launch(LK_TOK_FP32);
   TokGeom g;
   build_geom(m, T, &g);
   const size_t smem = (size_t)g.slab * sizeof(float);

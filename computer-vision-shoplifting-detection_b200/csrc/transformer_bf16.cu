@@ -843,6 +843,7 @@ int launch_transformer_bf16(const sf_model* m, const float* tokens, int64_t B, i
              "token / reconstruction buffers must be 16-byte aligned");
   const int64_t n_tiles = (B + g.win_per_tile - 1) / g.win_per_tile;
   const int grid = (int)std::min<int64_t>(n_tiles, m->sm_count);
+  count_launch(LK_XF_TC);
   static const int flags = getenv("SF_XF_FLAGS") ? atoi(getenv("SF_XF_FLAGS")) : 0;     // experiment switches (profiles/r2_summary.md)
   if (m->xfprog.f16) {
     SF_CUDA_OK(cudaFuncSetAttribute(transformer_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));

@@ -352,6 +352,7 @@ int launch_transformer_fp32(const sf_model* m, const float* tokens, int64_t B, i
   if (B == 0) return SF_OK;
   const Transformer& xf = m->xf;
   SF_REQUIRE(S >= 1 && S <= kSMax, SF_E_UNSUPPORTED, "token count S=%d outside [1,%d]", S, kSMax);
+  count_launch(LK_XF_FP32);
   SF_REQUIRE(S <= 100, SF_E_INVALID, "S=%d exceeds the positional-encoding table (100)", S);
   SF_REQUIRE(reduction == SF_REDUCE_MEAN || (reduction == SF_REDUCE_NONE && xf.variant == SF_VARIANT_SHOPFORMER_2),
              SF_E_INVALID, "reduction %d not available for variant %d", reduction, xf.variant);

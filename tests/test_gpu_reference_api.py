@@ -29,12 +29,12 @@ PKG = REPO / "computer-vision-shoplifting-detection_b200"
 STAGED = REPO / "tests" / "_ref_scripts"
 
 
-def _launch_counter():
-    """(tok2 stamps are a debugging aid) -- which tokenizer kernel ran last: True if the multi-window tcgen05 kernel."""
+def _launches():
+    """Host-side launch counters of the library: [tokenizer v2, one-window tc tokenizer, fp32 tokenizer, tc transformer, fp32 transformer]."""
     lib = N.load()
-    buf = (C.c_longlong * 4)()
-    lib.sfdbg_tokenizer2_timing(0, buf, 4)
-    return buf[0] >= 1000
+    buf = (C.c_longlong * 5)()
+    lib.sfdbg_launch_counts(buf, 5)
+    return list(buf)
 
 
 @pytest.mark.parametrize("name", ["A", "B", "C"])
@@ -117,11 +117,12 @@ def test_reference_scripts_run_unchanged_on_the_native_kernels(tmp_path, monkeyp
     staged = STAGED / "shopformer"
     out = tmp_path / "ckpt"
     if (staged / "train.py").exists():
-        lib.sfdbg_tokenizer2_timing(1, None, 0)
+        before = _launches()
         _run_script(staged / "train.py", ["--use_synthetic", "--stage1_epochs", "1", "--stage2_epochs", "1", "--output_dir", str(out),
                                           "--batch_size", "64"], tmp_path, monkeypatch, "shopformer")
         assert (out / "final_model.pt").exists() and (out / "config.json").exists()
-        assert _launch_counter(), "train.py's evaluate() did not reach the tensor-core tokenizer"
+        after = _launches()
+        assert after[0] > before[0] and after[3] > before[3], "train.py's evaluate() did not reach the tensor-core kernels"
         res = tmp_path / "res.json"
         _run_script(staged / "inference.py", ["--checkpoint", str(out / "final_model.pt"), "--use_synthetic", "--output", str(res)],
                     tmp_path, monkeypatch, "shopformer")
