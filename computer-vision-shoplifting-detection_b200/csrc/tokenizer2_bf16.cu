@@ -325,8 +325,9 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
   const int lane = threadIdx.x & 31;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + pl.off_bars);
   int* poison = reinterpret_cast<int*>(smem + pl.off_flags);                 // [2][64]
-  const int64_t B = dev_count_clamp(cnt, B_max);
-  const int64_t n_tiles = (B + pl.WT - 1) / pl.WT;
+  // 32-bit window / tile indices (the launcher bounds B): two registers less per index in the 96-register epilogue loop
+  const int B = (int)dev_count_clamp(cnt, B_max);
+  const int n_tiles = (B + pl.WT - 1) / pl.WT;
 
   // ------------------------------------------------------------------ one-time setup
   {
@@ -358,14 +359,14 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
   // debug stamps: MMA warp in [0, 1024), first warp of team 0 in [1024, 2560), first warp of team 1 in [2560, 4096)
   int stamp_i = warp == 0 ? 0 : (warp == kFirstEpiWarp ? 1024 : 2560);
   const int stamp_end = warp == 0 ? 1022 : (warp == kFirstEpiWarp ? 2558 : 4094);
-  const uint32_t stamp_it = (int64_t)blockIdx.x + gridDim.x < n_tiles ? 1u : 0u;     // steady-state tile when there is one
+  const uint32_t stamp_it = (int)(blockIdx.x + gridDim.x) < n_tiles ? 1u : 0u;     // steady-state tile when there is one
   (void)timing; (void)stamp_i; (void)stamp_end; (void)stamp_it;                       // only used with -DSF_STAMPS
 
   if (warp == 0) {
     // =================================================================== MMA issue
     const uint32_t base16 = smem_u32(smem) >> 4;
     uint32_t it = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    for (int tile = (int)blockIdx.x; tile < n_tiles; tile += (int)gridDim.x, ++it) {
       const uint32_t par = it & 1u;
       for (int g = 0; g < pl.n_groups; ++g) {
         const Group gr = pl.groups[g];
@@ -393,10 +394,10 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
     // =================================================================== TMA
     // (the whole warp walks the L sequence and waits -- a converged warp is parked by a blocking try_wait, a lone lane
     // spins through the scheduler's issue slots -- and lane 0 issues the copies)
-    auto pose_load = [&](int64_t tile) {
+    auto pose_load = [&](int tile) {
       if (tile >= n_tiles || lane != 0) return;
-      const int64_t w0 = tile * pl.WT;
-      const uint32_t nw = (uint32_t)((B - w0) < (int64_t)pl.WT ? (B - w0) : (int64_t)pl.WT);
+      const int w0 = tile * pl.WT;
+      const uint32_t nw = (uint32_t)((B - w0) < pl.WT ? (B - w0) : pl.WT);
       const uint32_t bytes = nw * (uint32_t)pl.per_w * 4u;
       uint64_t* bar = &bars[pl.bar_l0 + pl.n_loads - 1];
       mbar_expect_tx(bar, bytes);
@@ -404,7 +405,7 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
     };
     pose_load(blockIdx.x);
     uint32_t it = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    for (int tile = (int)blockIdx.x; tile < n_tiles; tile += (int)gridDim.x, ++it) {
       const uint32_t par = it & 1u;
       for (int l = 0; l < pl.n_loads; ++l) {
         const Load ld = pl.loads[l];
@@ -435,10 +436,10 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
     const int n_st = pl.n_stages[team];
     uint32_t it = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    for (int tile = (int)blockIdx.x; tile < n_tiles; tile += (int)gridDim.x, ++it) {
       const uint32_t par = it & 1u;
-      const int64_t w_first = tile * pl.WT;
-      const int nw = (int)((B - w_first) < (int64_t)pl.WT ? (B - w_first) : (int64_t)pl.WT);
+      const int w_first = tile * pl.WT;
+      const int nw = (B - w_first) < pl.WT ? (B - w_first) : pl.WT;
       int* pz = poison + par * 64;
       for (int e = 0; e < n_st; ++e) {
         StageK s;
@@ -680,6 +681,7 @@ int launch_tokenizer2(const sf_model* m, const float* poses, int64_t B, int T, f
   SF_REQUIRE(((uintptr_t)poses & 15) == 0 && ((uintptr_t)tokens & 15) == 0, SF_E_INVALID,
              "pose / token buffers must be 16-byte aligned (TMA bulk copies)");
   const Plan& pl = u->prog.plan;
+  SF_REQUIRE(B <= (int64_t)0x7FFFFF00, SF_E_INVALID, "tokenizer v2 takes at most 2^31 - 256 windows per launch");
   const int64_t n_tiles = (B + pl.WT - 1) / pl.WT;
   const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)m->sm_count);
   count_launch(LK_TOK2);

@@ -281,18 +281,19 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
     ops = reinterpret_cast<const XfOp*>(smem + geo.off_ops);
   }
 
-  const int64_t B = dev_count_clamp(cnt, B_max);
-  const int64_t n_tiles = (B + geo.win_per_tile - 1) / geo.win_per_tile;
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t window = tile * geo.win_per_tile + lane_grp * geo.wpw + win_l;
+  // 32-bit window / tile indices (the launcher bounds B): fewer live registers in a kernel that runs at the 128-register limit
+  const int B = (int)dev_count_clamp(cnt, B_max);
+  const int n_tiles = (B + geo.win_per_tile - 1) / geo.win_per_tile;
+  for (int tile = (int)blockIdx.x; tile < n_tiles; tile += (int)gridDim.x) {
+    const int window = tile * geo.win_per_tile + lane_grp * geo.wpw + win_l;
     const bool valid = lane_ok && window < B;
     const float* tok_row = tokens + ((size_t)(valid ? window : 0) * S + tok_s) * dt;
     {   // the next tile's tokens (one contiguous range) start their way from HBM to L2 now, a whole tile ahead of use
-      const int64_t w0 = (tile + gridDim.x) * geo.win_per_tile;
+      const int w0 = (tile + (int)gridDim.x) * geo.win_per_tile;
       if (w0 < B) {
-        const int64_t bytes = (int64_t)(B - w0 < geo.win_per_tile ? B - w0 : geo.win_per_tile) * S * dt * (int64_t)sizeof(float);
+        const int bytes = (B - w0 < geo.win_per_tile ? B - w0 : geo.win_per_tile) * S * dt * (int)sizeof(float);
         const char* base = reinterpret_cast<const char*>(tokens + (size_t)w0 * S * dt);
-        for (int64_t o = (int64_t)threadIdx.x * 128; o < bytes; o += (int64_t)kThreads * 128)
+        for (int o = (int)threadIdx.x * 128; o < bytes; o += kThreads * 128)
           asm volatile("prefetch.global.L2 [%0];" ::"l"(base + o));
       }
     }
@@ -841,6 +842,7 @@ int launch_transformer_bf16(const sf_model* m, const float* tokens, int64_t B, i
              SF_E_INVALID, "reduction %d not available for variant %d", reduction, m->xf.variant);
   SF_REQUIRE(((uintptr_t)tokens & 15) == 0 && ((uintptr_t)recon & 15) == 0, SF_E_INVALID,
              "token / reconstruction buffers must be 16-byte aligned");
+  SF_REQUIRE(B <= (int64_t)0x7FFF0000, SF_E_INVALID, "the tensor-core transformer takes at most 2^31 - 65,536 windows per launch");
   const int64_t n_tiles = (B + g.win_per_tile - 1) / g.win_per_tile;
   const int grid = (int)std::min<int64_t>(n_tiles, m->sm_count);
   count_launch(LK_XF_TC);
