@@ -315,7 +315,10 @@ __device__ __forceinline__ void load_stage(StageK* dst, const StageK* src) {
 #endif
 constexpr int kCvtLoads = SF_TOK2_CVT_LOADS;      // TMEM loads in flight per wait in a conversion stage
 
-template <bool F16>
+// POOL: adaptive average pooling in the token stage (shopformer_2 configs with num_tokens not dividing the last length); KW: ELL
+// width of block 0's mix (5 covers the skeleton graphs, 8 the general case).  Template parameters so that the common
+// instantiation carries neither path: the epilogue loop runs at the 96-register limit
+template <bool F16, bool POOL, int KW>
 __global__ void __launch_bounds__(kThreads, 1)
 tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ poses, float* __restrict__ tokens, int64_t B_max, const DevCount cnt,
                   const Tables tabs) {
@@ -493,8 +496,7 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
             if (timing && it == stamp_it && tt < 32 && cg0 == half) T2_FINE(9000 + e);
           }
         } else if (s.type() == ST_G0) {
-          if (pl.ell_width <= 5) g0_stage<5, F16>(pl, s, smem, row, half, my_w, my_v, nw, pz);
-          else g0_stage<8, F16>(pl, s, smem, row, half, my_w, my_v, nw, pz);
+          g0_stage<KW, F16>(pl, s, smem, row, half, my_w, my_v, nw, pz);
         } else if (s.type() == ST_XEPI0) {
           xepi0_stage<F16>(pl, s, smem, lane_base, row, half, my_w, my_v, nw, team);
         } else {   // ST_TOKENS
@@ -503,7 +505,7 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
           const bool live = row < rows && my_w < nw;
           const bool poisoned = live && pz[my_w] != 0;
           // (the staging area is free: the previous tile's token stage completed only after its bulk store had read it)
-          if (pl.pool > 0) {
+          if (POOL) {
             // adaptive average pooling over time (T_last -> pool tokens): token j = mean of relu(acc + b) over the time
             // steps [floor(j T / P), ceil((j + 1) T / P)); every time step of a row sits in this thread's TMEM lane, so
             // the two column halves of the team take alternate output tokens and sum in time order
@@ -685,13 +687,18 @@ int launch_tokenizer2(const sf_model* m, const float* poses, int64_t B, int T, f
   const int64_t n_tiles = (B + pl.WT - 1) / pl.WT;
   const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)m->sm_count);
   count_launch(LK_TOK2);
-  if (m->tok2->st.f16) {
-    SF_CUDA_OK(cudaFuncSetAttribute(tokenizer2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
-    tokenizer2_kernel<true><<<grid, kThreads, pl.smem_bytes, st>>>(pl, poses, tokens, B, cnt, u->tabs);
-  } else {
-    SF_CUDA_OK(cudaFuncSetAttribute(tokenizer2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
-    tokenizer2_kernel<false><<<grid, kThreads, pl.smem_bytes, st>>>(pl, poses, tokens, B, cnt, u->tabs);
-  }
+  auto go = [&](auto kern) -> int {
+    SF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
+    kern<<<grid, kThreads, pl.smem_bytes, st>>>(pl, poses, tokens, B, cnt, u->tabs);
+    return SF_OK;
+  };
+  const bool f16 = m->tok2->st.f16, pool = pl.pool > 0, kw5 = pl.ell_width <= 5;
+  int rc;
+#define SF_T2_GO(F, P) (kw5 ? go(tokenizer2_kernel<F, P, 5>) : go(tokenizer2_kernel<F, P, 8>))
+  if (f16) rc = pool ? SF_T2_GO(true, true) : SF_T2_GO(true, false);
+  else rc = pool ? SF_T2_GO(false, true) : SF_T2_GO(false, false);
+#undef SF_T2_GO
+  if (rc) return rc;
   SF_CUDA_OK(cudaGetLastError());
   return SF_OK;
 }

@@ -216,10 +216,13 @@ __device__ __forceinline__ void store_group_relu(unsigned char* buf, int plane, 
 }
 
 // F16: the 16-bit operands (activations written by the epilogues and the weight images) are fp16 instead of bf16
-template <bool F16>
+// (the reduction mode stays a run-time value: as a template parameter it made config C 0.9 % slower)
+// RECON: the reconstructed tokens are written out (sf_reconstruct_tokens / explicit recon buffer); the scoring path compiles the
+// stores, the pointer and its predicates away (122 instead of 128 registers: 1.3 % on sf_score_windows)
+template <bool F16, bool RECON>
 __global__ void __launch_bounds__(kThreads, 1)
 transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo, const __grid_constant__ Transformer xf,
-                        const float* __restrict__ tokens, int64_t B_max, int reduction, float* __restrict__ recon_out,
+                        const float* __restrict__ tokens, int64_t B_max, int reduction, float* __restrict__ recon_out_param,
                         float* __restrict__ scores, const DevCount cnt, const int flags_rt) {
   // experiment switches of profiles/r2_summary.md (1: one polling warp + bar.sync, 2 / 8: busy test_wait spin, 4: q / k / v as three
   // phases): a run-time value only with -DSF_XF_FLAGS_RUNTIME (SF_XF_FLAGS in the environment), otherwise the constant 0 so
@@ -230,6 +233,7 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
   constexpr int flags = 0;
   (void)flags_rt;
 #endif
+  float* const recon_out = RECON ? recon_out_param : nullptr;
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t bar, cbar, wbar[2];      // MMA completion (phase / first GEMM of a chain); TMA completion per weight-ring slot
   __shared__ uint32_t tmem_base_s;
@@ -847,13 +851,15 @@ int launch_transformer_bf16(const sf_model* m, const float* tokens, int64_t B, i
   const int grid = (int)std::min<int64_t>(n_tiles, m->sm_count);
   count_launch(LK_XF_TC);
   static const int flags = getenv("SF_XF_FLAGS") ? atoi(getenv("SF_XF_FLAGS")) : 0;     // experiment switches (profiles/r2_summary.md)
-  if (m->xfprog.f16) {
-    SF_CUDA_OK(cudaFuncSetAttribute(transformer_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
-    transformer_bf16_kernel<true><<<grid, kThreads, g.smem_bytes, st>>>(m->xfprog, g, m->xf, tokens, B, reduction, recon, scores, cnt, flags);
-  } else {
-    SF_CUDA_OK(cudaFuncSetAttribute(transformer_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
-    transformer_bf16_kernel<false><<<grid, kThreads, g.smem_bytes, st>>>(m->xfprog, g, m->xf, tokens, B, reduction, recon, scores, cnt, flags);
-  }
+  auto go = [&](auto kern) -> int {
+    SF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+    kern<<<grid, kThreads, g.smem_bytes, st>>>(m->xfprog, g, m->xf, tokens, B, reduction, recon, scores, cnt, flags);
+    return SF_OK;
+  };
+  int rc;
+  if (m->xfprog.f16) rc = recon ? go(transformer_bf16_kernel<true, true>) : go(transformer_bf16_kernel<true, false>);
+  else rc = recon ? go(transformer_bf16_kernel<false, true>) : go(transformer_bf16_kernel<false, false>);
+  if (rc) return rc;
   SF_CUDA_OK(cudaGetLastError());
   return SF_OK;
 }
