@@ -217,9 +217,10 @@ __device__ __forceinline__ void store_group_relu(unsigned char* buf, int plane, 
 
 // F16: the 16-bit operands (activations written by the epilogues and the weight images) are fp16 instead of bf16
 // (the reduction mode stays a run-time value: as a template parameter it made config C 0.9 % slower)
+// V1: shopformer/ (post-LN, ReLU, positional encoding added to the score target); else shopformer_2/ (pre-LN, exact GELU).
 // RECON: the reconstructed tokens are written out (sf_reconstruct_tokens / explicit recon buffer); the scoring path compiles the
 // stores, the pointer and its predicates away (122 instead of 128 registers: 1.3 % on sf_score_windows)
-template <bool F16, bool RECON>
+template <bool F16, bool RECON, bool V1>
 __global__ void __launch_bounds__(kThreads, 1)
 transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo, const __grid_constant__ Transformer xf,
                         const float* __restrict__ tokens, int64_t B_max, int reduction, float* __restrict__ recon_out_param,
@@ -462,7 +463,7 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
             const int g = kParts * i + part;
             if (g < ng) ldg16(tok_row, g * 16, dt, valid, st[i]);
           }
-          if (xf.variant == SF_VARIANT_SHOPFORMER) {
+          if (V1) {
 #pragma unroll
             for (int i = 0; i < kSlots; ++i) {
               const int g = kParts * i + part;
@@ -617,7 +618,7 @@ transformer_bf16_kernel(const XfProgram prog, const __grid_constant__ XfGeo geo,
               tmem_ld_wait();
 #pragma unroll
               for (int q = 0; q < 16; q += 2) put(acc + q, add2(pr(acc + q), pr(bs + q)));
-              if (op.act == 2) {
+              if (!V1 && op.act == 2) {
 #pragma unroll
                 for (int q = 0; q < 16; ++q) acc[q] = gelu_erf(acc[q]);
                 store_group<F16>(sHop, plane, row, g, acc);
@@ -856,9 +857,12 @@ int launch_transformer_bf16(const sf_model* m, const float* tokens, int64_t B, i
     kern<<<grid, kThreads, g.smem_bytes, st>>>(m->xfprog, g, m->xf, tokens, B, reduction, recon, scores, cnt, flags);
     return SF_OK;
   };
+  const bool v1 = m->xf.variant == SF_VARIANT_SHOPFORMER;
   int rc;
-  if (m->xfprog.f16) rc = recon ? go(transformer_bf16_kernel<true, true>) : go(transformer_bf16_kernel<true, false>);
-  else rc = recon ? go(transformer_bf16_kernel<false, true>) : go(transformer_bf16_kernel<false, false>);
+#define SF_XF_GO(F, R) (v1 ? go(transformer_bf16_kernel<F, R, true>) : go(transformer_bf16_kernel<F, R, false>))
+  if (m->xfprog.f16) rc = recon ? SF_XF_GO(true, true) : SF_XF_GO(true, false);
+  else rc = recon ? SF_XF_GO(false, true) : SF_XF_GO(false, false);
+#undef SF_XF_GO
   if (rc) return rc;
   SF_CUDA_OK(cudaGetLastError());
   return SF_OK;
