@@ -9,6 +9,7 @@
 //               tokens (fp32) staged in shared memory and written by ONE bulk store per tile.
 // Nothing but poses in and tokens out touches HBM; MMA groups of one chunk run under the epilogue of the previous one.
 // Reference maths: shopformer/models/gcae.py:124-154,185-195,242-259,331-366; shopformer_2/models/gcae.py:375-422.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -227,13 +228,13 @@ constexpr int kXepiLoads = SF_TOK2_XEPI_LOADS;     // TMEM loads in flight per w
 // Block 0 output for output times [p0, p1): x1 = relu(acc + BN-folded strided 1x1 residual conv of the raw poses + bias)
 // (gcae.py:237-259); the residual (2 input channels) is added in fp32 here instead of going through the tensor cores.
 // The two column halves of a team take alternate 16-channel groups.
-template <bool F16>
+template <bool F16, int kMaxT>
 __device__ __forceinline__ void xepi0_stage(const Plan& pl, const StageK& s, unsigned char* smem, uint32_t lane_base, int row, int half, int my_w,
                                             int my_v, int nw, int team) {
   const int V = pl.V, tv = pl.T0 * V, cp0 = pl.cp0;
   const bool valid = row < pl.rows && my_w < nw;
   const bool two = pl.c_in > 1;
-  constexpr int kMaxT = 8;                               // output time steps per stage
+  // kMaxT: output time steps per stage the instantiation supports (4 or 8; the host picks the smallest that covers the program)
   float xa[kMaxT], xb[kMaxT];
   const int ntp = (int)s.p1() - (int)s.p0();
   {
@@ -318,7 +319,7 @@ constexpr int kCvtLoads = SF_TOK2_CVT_LOADS;      // TMEM loads in flight per wa
 // POOL: adaptive average pooling in the token stage (shopformer_2 configs with num_tokens not dividing the last length); KW: ELL
 // width of block 0's mix (5 covers the skeleton graphs, 8 the general case).  Template parameters so that the common
 // instantiation carries neither path: the epilogue loop runs at the 96-register limit
-template <bool F16, bool POOL, int KW>
+template <bool F16, bool POOL, int KW, int MAXT>
 __global__ void __launch_bounds__(kThreads, 1)
 tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ poses, float* __restrict__ tokens, int64_t B_max, const DevCount cnt,
                   const Tables tabs) {
@@ -498,7 +499,7 @@ tokenizer2_kernel(const __grid_constant__ Plan pl, const float* __restrict__ pos
         } else if (s.type() == ST_G0) {
           g0_stage<KW, F16>(pl, s, smem, row, half, my_w, my_v, nw, pz);
         } else if (s.type() == ST_XEPI0) {
-          xepi0_stage<F16>(pl, s, smem, lane_base, row, half, my_w, my_v, nw, team);
+          xepi0_stage<F16, MAXT>(pl, s, smem, lane_base, row, half, my_w, my_v, nw, team);
         } else {   // ST_TOKENS
           const float* bp = reinterpret_cast<const float*>(smem + s.bias_off);
           float* stg = reinterpret_cast<float*>(smem + pl.off_stage_tok);
@@ -693,8 +694,14 @@ int launch_tokenizer2(const sf_model* m, const float* poses, int64_t B, int T, f
     return SF_OK;
   };
   const bool f16 = m->tok2->st.f16, pool = pl.pool > 0, kw5 = pl.ell_width <= 5;
+  int maxt = 0;                                   // longest block-0 output stage of this program
+  for (int t = 0; t < kTeams; ++t)
+    for (int e = 0; e < pl.n_stages[t]; ++e)
+      if (pl.stages[t][e].type == ST_XEPI0) maxt = std::max(maxt, (int)(pl.stages[t][e].p1 - pl.stages[t][e].p0));
+  const bool t4 = maxt <= 4;
   int rc;
-#define SF_T2_GO(F, P) (kw5 ? go(tokenizer2_kernel<F, P, 5>) : go(tokenizer2_kernel<F, P, 8>))
+#define SF_T2_GO(F, P) (kw5 ? (t4 ? go(tokenizer2_kernel<F, P, 5, 4>) : go(tokenizer2_kernel<F, P, 5, 8>)) \
+                            : (t4 ? go(tokenizer2_kernel<F, P, 8, 4>) : go(tokenizer2_kernel<F, P, 8, 8>)))
   if (f16) rc = pool ? SF_T2_GO(true, true) : SF_T2_GO(true, false);
   else rc = pool ? SF_T2_GO(false, true) : SF_T2_GO(false, false);
 #undef SF_T2_GO
